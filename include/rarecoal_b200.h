@@ -1,0 +1,177 @@
+/* rarecoal_b200.h — C ABI of librarecoal_b200.so
+ *
+ * Drop-in boundary for ONE path of stschiff/rarecoal: the probability of every allele-sharing
+ * pattern of a histogram under a ModelSpec and the multinomial log-likelihood built on it.
+ * The reference has no FFI of its own; the seam this library replaces is the per-pattern fan-out
+ *
+ *     src/RarecoalLib/MaxUtils.hs:107-110
+ *         let jointStateSpace = makeJointStateSpace nrPops maxAf
+ *             coreFunc        = C1.getProb modelSpec jointStateSpace nVecModelMapped
+ *         patternProbs <- sequence $ parMap rdeepseq coreFunc standardOrderModelMapped
+ *
+ * plus the reduction at MaxUtils.hs:85-91 (computeLogLikelihoodFromSpec).  A Haskell maintainer
+ * binds these entry points with `foreign import ccall` (see INTEGRATION.md and
+ * haskell/RarecoalB200.hs).  Plain pointers and sizes only; the caller owns every host array, the
+ * library owns all device memory inside rc_ctx.  One rc_ctx per OS thread / per GPU; a context is
+ * not re-entrant.  There is NO CPU fallback: every entry point that computes fails with
+ * RC_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef RARECOAL_B200_H
+#define RARECOAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rc_ctx rc_ctx;
+
+/* Return codes.  Positive codes mirror the reference's exception constructors
+ * (src/RarecoalLib/Utils.hs:47-52); negative codes are library-level failures. */
+enum {
+    RC_OK = 0,
+    RC_ERR_MODEL = 1,        /* RarecoalModelException  (validateModel, StateSpace.hs:163-197)      */
+    RC_ERR_COMP = 2,         /* RarecoalCompException   (Core.hs:42,53-56; MaxUtils.hs:72-75)        */
+    RC_ERR_ARG = -1,         /* bad argument / call order                                            */
+    RC_ERR_CUDA = -2,        /* CUDA runtime failure or no device                                    */
+    RC_ERR_UNSUPPORTED = -3  /* problem exceeds a compiled-in limit (see rc_last_error)              */
+};
+
+/* ModelEvent / EventType (src/RarecoalLib/StateSpace.hs:30-40).
+ *   type 0  Join k l        : branch l merges into k                       (v unused)
+ *   type 1  Split k l m     : fraction v=m of branch l moves to k
+ *   type 2  SetPopSize k p  : v = p                                        (l unused)
+ *   type 3  SetFreeze k b   : v != 0 -> frozen                             (l unused)            */
+enum { RC_EV_JOIN = 0, RC_EV_SPLIT = 1, RC_EV_POPSIZE = 2, RC_EV_FREEZE = 3 };
+typedef struct {
+    double t;
+    int32_t type;
+    int32_t k;
+    int32_t l;
+    double v;
+} rc_event;
+
+/* Counters of the last rc_eval / rc_eval_partial on this context. */
+typedef struct {
+    int64_t state_steps;     /* executed b(x) updates over all models (SURVEY.md §8d unit, Core.hs:248) */
+    int64_t slots;           /* live states resident at t=0 over all models                            */
+    double kernel_ms;        /* CUDA-event time of the propagation kernel(s) on the eval stream         */
+    double tables_ms;        /* CUDA-event time of the per-model table kernel                           */
+    double total_ms;         /* CUDA-event time first launch -> last launch of the call                 */
+    int32_t launches;        /* kernels launched by the call                                            */
+    int32_t plan_cache_hit;  /* 1 if every model reused a cached transition plan                        */
+    int32_t n_epochs;        /* structural epochs of the last model                                     */
+    int32_t n_steps;         /* grid steps executed by the last model                                   */
+} rc_stats;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+
+/* Creates a context bound to CUDA device `device` (cudaSetDevice).  Fails with RC_ERR_CUDA when the
+ * device cannot be used.                                                                           */
+int rc_create(int device, rc_ctx** out);
+void rc_destroy(rc_ctx* ctx);
+/* Message of the last failing call on this context ("" if none).  Valid until the next call.       */
+const char* rc_last_error(rc_ctx* ctx);
+
+/* ---- problem = what computeFrequencySpectrum closes over (MaxUtils.hs:97-107) ------------------- */
+
+/* patterns: [nPat][P] in model-branch order, normally computeStandardOrder (Utils.hs:169-177) mapped
+ * through turnHistPatternIntoModelPattern (Utils.hs:114-119); nVec likewise; counts[i] = histogram
+ * count of pattern i (0 if unseen, MaxUtils.hs:112); totalSites = raTotalNrSites.  Every pattern
+ * must satisfy 1 <= sum <= maxAf (the JointStateSpace of StateSpace.hs:73-87 has no other states). */
+int rc_set_problem(rc_ctx* ctx, int P, int maxAf, int nPat, const int32_t* patterns,
+                   const int32_t* nVec, const int64_t* counts, int64_t totalSites);
+
+/* Pattern sharding for the multi-GPU path: this context evaluates only the patterns dealt to `rank`
+ * of `world` (work-sorted round-robin).  Call after rc_set_problem; default (0,1).                 */
+int rc_set_shard(rc_ctx* ctx, int rank, int world);
+
+/* mTimeSteps (StateSpace.hs:44; Utils.hs:64-73).  t[0..T) strictly increasing, > 0.               */
+int rc_set_times(rc_ctx* ctx, int T, const double* t);
+
+/* getTimeSteps n0 lingen tMax (Utils.hs:64-73) computed by the library; returns the number of grid
+ * points and fills out[0..min(n,cap)).                                                             */
+int rc_time_steps(int n0, int lingen, double tMax, double* out, int cap);
+
+/* ---- evaluation ------------------------------------------------------------------------------- */
+
+/* Evaluates B models (ModelSpecs sharing the time grid) on the current problem.
+ *   ev / evOff : events of model b are ev[evOff[b] .. evOff[b+1])  (mEvents, any order; sorted
+ *                stably by time inside, Core.hs:292-294)
+ *   theta[b]   : mTheta;  disc[b*P .. b*P+P) : mDiscoveryRates;  noShortcut : mNoShortcut
+ *   siteRed    : effective-site reduction factor of computeLogLikelihoodFromSpec (MaxUtils.hs:85-91)
+ *   outProbs   : NULL or [B][nPat] — getProb of every pattern (Core.hs:38-56)
+ *   outLogl    : [B] — siteRed * (sum cnt_i log p_i + (total - sum cnt_i) log(1 - sum p_i))
+ *   outStatus  : [B] — RC_OK, RC_ERR_MODEL (validateModel failed) or RC_ERR_COMP (binomial overflow,
+ *                pattern outside nVec); outLogl[b] is NaN for a failed model
+ * Returns RC_OK when the call itself ran (individual models may still carry a status).  With a
+ * shard set, outProbs holds zeros for patterns owned by other ranks and outLogl is computed from
+ * this rank's partial sums only — use rc_eval_partial + rc_finalize for the sharded path.          */
+int rc_eval(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta,
+            const double* disc, int noShortcut, double siteRed, double* outProbs, double* outLogl,
+            int32_t* outStatus);
+
+/* Sharded path: like rc_eval, but leaves this rank's partial sums on the DEVICE.
+ *   dPartial   : device pointer, [2*B] doubles: (sum cnt_i log p_i, sum p_i) per model, this shard
+ *   dProbs     : device pointer or NULL, [B][nPat]; entries of patterns owned by other ranks are 0
+ *   stream     : cudaStream_t to launch on (NULL = default stream); the call does not synchronise
+ * The caller all-reduces (sum) dPartial (and dProbs) across ranks — torch.distributed / NCCL — and
+ * then calls rc_finalize.                                                                          */
+int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta,
+                    const double* disc, int noShortcut, double* dPartial, double* dProbs, void* stream,
+                    int32_t* outStatus);
+
+/* outLogl[b] = siteRed * (ll_b + (totalSites - sum counts) * log(1 - sp_b)) from reduced partials
+ * (device pointer, [2*B]); synchronises `stream` and writes host outLogl[B].                       */
+int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRed, void* stream,
+                double* outLogl);
+
+/* getProb for ONE pattern (Core.hs:38-56; the `rarecoal prob` command, Prob.hs:28): builds a
+ * one-pattern problem on a scratch context state.  nVec/config have length P.                      */
+int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_t* config,
+                const rc_event* ev, int nEv, double theta, const double* disc, int noShortcut,
+                double* outProb);
+
+int rc_last_stats(rc_ctx* ctx, rc_stats* out);
+
+/* Measures the FP64 FMA rate of the device with a register-resident DFMA chain kernel (the
+ * roofline denominator; MEASURED_PEAKS.json carries none for FP64).  Returns TFLOP/s in *out.      */
+int rc_fp64_peak(rc_ctx* ctx, double* outTflops);
+
+/* ---- host-side mirrors of small reference functions (no device work) --------------------------- */
+
+/* computeAllConfigs maxAf nVec (Utils.hs:100-104): returns n, fills out[n][P] up to cap rows.      */
+int rc_all_configs(int maxAf, int P, const int32_t* nVec, int32_t* out, int cap);
+/* validateModel (StateSpace.hs:163-197): RC_OK or RC_ERR_MODEL with a message in err.              */
+int rc_validate_model(int P, const double* disc, const rc_event* ev, int nEv, char* err, int errCap);
+/* getRegularizationPenalty (StateSpace.hs:199-221).                                                */
+double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv);
+/* choose n k (Utils.hs:208-210).                                                                   */
+double rc_choose(int n, int k);
+
+/* Runs the host planner only (no device): executed state-steps (one unit = one iteration of the
+ * updateB loop, Core.hs:248), live states at t=0, largest live set of a pattern, structural epochs and
+ * kernel bins for this problem/model.  Used for roofline accounting and to check the planner on CPU. */
+int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T,
+                  const double* times, const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps,
+                  int64_t* slots0, int32_t* maxLive, int32_t* nEpochs, int32_t* nBins);
+
+/* JointStateSpace (StateSpace.hs:20-28,73-124): ids are positions in computeAllConfigs.            */
+typedef struct rc_statespace rc_statespace;
+rc_statespace* rc_ss_create(int P, int maxAf);
+void rc_ss_destroy(rc_statespace* ss);
+int rc_ss_nr_states(const rc_statespace* ss);
+int rc_ss_state_to_id(const rc_statespace* ss, const int32_t* x);            /* -1 if not a state   */
+int rc_ss_id_to_state(const rc_statespace* ss, int id, int32_t* x);
+int rc_ss_x1up(const rc_statespace* ss, int id, int32_t* out);               /* -1 where sum>maxAf  */
+int rc_ss_x1(const rc_statespace* ss, int k);
+/* fillUpStateSpace (StateSpace.hs:145-160): returns n, fills out up to cap.                        */
+int rc_ss_fill_up(const rc_statespace* ss, const int32_t* ids, int n, int32_t* out, int cap);
+
+const char* rc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RARECOAL_B200_H */

@@ -1,0 +1,957 @@
+// rc_api.cu — context, model resolution and the C ABI of librarecoal_b200.so (include/rarecoal_b200.h).
+//
+// Host side of the path, mirroring the reference:
+//   validateModel            StateSpace.hs:163-197        -> validate_model()
+//   makeInitModelState       Core.hs:290-298 (stable sort) -> resolve_model()
+//   singleStep event firing  Core.hs:120-135 (strict t < nextTime; events do not move the clock)
+//                                                          -> events are resolved to grid-step indices
+//   computeFrequencySpectrum MaxUtils.hs:93-119            -> rc_eval (one launch for all patterns)
+//   computeLogLikelihoodFromSpec MaxUtils.hs:85-91         -> rc_reduce_kernel + rc_finalize_kernel
+// There is no CPU fallback: without a usable CUDA device rc_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rarecoal_b200.h"
+#include "rc_kernels.h"
+#include "rc_plan.h"
+
+namespace {
+
+#define CK(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return RC_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PlanEntry {
+    rc::PlanHost h;
+    RcPlanDev d;
+    std::vector<void*> allocs;
+    bool allShortcut = false;
+    void release() {
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+    }
+};
+
+struct SegHost {
+    int sBegin;
+    unsigned mask;
+    double N[RC_MAX_P];
+};
+
+struct ModelHost {
+    int status = RC_OK;
+    std::string err;
+    std::vector<SegHost> segs;
+    std::vector<rc::StructEv> sev;
+    std::vector<int> sevStep;
+    std::vector<double> sevM;
+    std::vector<rc::GapInfo> gaps;
+    bool hasSplit = false;
+    int sShort = -1;
+    std::string sig;
+    PlanEntry* plan = nullptr;
+};
+
+}  // namespace
+
+struct rc_statespace {
+    rc::StateSpace* ss;
+};
+
+struct rc_ctx {
+    int device = 0;
+    int smemOptin = 0;
+    int smCount = 0;
+    std::string err;
+    // problem
+    int P = 0, maxAf = 0, nPatGlobal = 0;
+    std::vector<int32_t> patG, nVec;
+    std::vector<int64_t> cntG;
+    int64_t totalSites = 0;
+    long long sumCounts = 0;
+    bool compErr = false;
+    std::string compErrMsg;
+    int rank = 0, world = 1;
+    // shard
+    int nPat = 0;
+    std::vector<int32_t> patS;
+    std::vector<int> patGlobalIdx;
+    DevBuf dAInit, dCombFac, dSupport, dPatGlobal, dCounts;
+    // grid
+    std::vector<double> times, dts;
+    DevBuf dDts;
+    // plans
+    std::map<std::string, PlanEntry*> plans;
+    // eval scratch
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs;
+    PinBuf hBlob, hOut;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool statsPending = false;
+    bool blobInFlight = false;
+    rc_stats stats;
+    rc_ctx* child = nullptr;
+
+    void clear_plans() {
+        for (auto& kv : plans) {
+            kv.second->release();
+            delete kv.second;
+        }
+        plans.clear();
+    }
+};
+
+namespace {
+
+// ---- validateModel (StateSpace.hs:163-197) -------------------------------------------------------
+int validate_model(int P, const double* disc, const std::vector<rc_event>& sorted, std::string& err) {
+    for (const rc_event& e : sorted)
+        if (e.t < 0) { err = "Negative event times"; return RC_ERR_MODEL; }
+    for (int k = 0; k < P; ++k)
+        if (disc[k] <= 0 || disc[k] > 1) { err = "illegal discovery Rate"; return RC_ERR_MODEL; }
+    const int n = (int)sorted.size();
+    auto bad_idx = [&](int i) { return i < 0 || i >= P; };
+    char buf[160];
+    for (int i = 0; i < n; ++i) {
+        const rc_event& e = sorted[i];
+        if (e.type == RC_EV_JOIN) {
+            if (bad_idx(e.k) || bad_idx(e.l)) { err = "illegal branch indices in event Join"; return RC_ERR_MODEL; }
+            bool reuse = false;   // branch l must not be referenced by any later event
+            for (int j = i + 1; j < n && !reuse; ++j) {
+                const rc_event& r = sorted[j];
+                reuse = r.k == e.l || ((r.type == RC_EV_JOIN || r.type == RC_EV_SPLIT) && r.l == e.l);
+            }
+            if (e.k == e.l || reuse) {
+                std::snprintf(buf, sizeof buf, "Illegal join from %d to %d at time %g", e.l, e.k, e.t);
+                err = buf;
+                return RC_ERR_MODEL;
+            }
+        } else if (e.type == RC_EV_POPSIZE) {
+            if (bad_idx(e.k)) { err = "illegal branch indices in event SetPopSize"; return RC_ERR_MODEL; }
+            if (e.v <= 0) { std::snprintf(buf, sizeof buf, "Illegal population size: %g", e.v); err = buf; return RC_ERR_MODEL; }
+        } else if (e.type == RC_EV_SPLIT) {
+            if (bad_idx(e.k) || bad_idx(e.l)) { err = "illegal branch indices in event Split"; return RC_ERR_MODEL; }
+            if (e.v < 0.0 || e.v > 1.0) { std::snprintf(buf, sizeof buf, "Illegal split rate%g", e.v); err = buf; return RC_ERR_MODEL; }
+            // The reference does not check k /= l for Split; its state update would then leave the
+            // state space (Core.hs:213) and abort in stateToId.  Reported as a model error here.
+            if (e.k == e.l) { err = "Illegal split of a branch into itself"; return RC_ERR_MODEL; }
+        } else if (e.type == RC_EV_FREEZE) {
+            if (bad_idx(e.k)) { err = "illegal branch indices in event SetFreeze"; return RC_ERR_MODEL; }
+        } else {
+            err = "unknown event type";
+            return RC_ERR_MODEL;
+        }
+    }
+    return RC_OK;
+}
+
+std::vector<rc_event> sort_events(const rc_event* ev, int n) {
+    std::vector<rc_event> v(ev, ev + n);
+    // sortBy time is stable (Core.hs:292-294): template order survives for equal times
+    std::stable_sort(v.begin(), v.end(), [](const rc_event& a, const rc_event& b) { return a.t < b.t; });
+    return v;
+}
+
+// GHC's (^): square-and-multiply with the accumulator order of GHC.Real.powImpl / powImplAcc, so the
+// binomial factor m^s (1-m)^(x_l-s) (Core.hs:216) rounds as in the reference.
+double ghc_pow(double x, int n) {
+    if (n == 0) return 1.0;
+    while ((n & 1) == 0) { x = x * x; n >>= 1; }
+    if (n == 1) return x;
+    double acc = x;
+    x = x * x;
+    n >>= 1;
+    while (true) {
+        if (n & 1) {
+            if (n == 1) return x * acc;
+            acc = x * acc;
+        }
+        x = x * x;
+        n >>= 1;
+    }
+}
+
+unsigned seg_mask_at(const std::vector<SegHost>& segs, int s) {
+    size_t i = 0;
+    while (i + 1 < segs.size() && segs[i + 1].sBegin <= s) ++i;
+    return segs[i].mask;
+}
+
+// Resolves one ModelSpec against the grid: event firing steps, (popSize, freeze) segments,
+// structural events and the structural signature.
+void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double* disc, int noShortcut, ModelHost& mh) {
+    const int P = ctx->P, T = (int)ctx->times.size();
+    std::vector<rc_event> sorted = sort_events(ev, nEv);
+    mh.status = validate_model(P, disc, sorted, mh.err);
+    if (mh.status != RC_OK) return;
+    SegHost cur;
+    cur.sBegin = 0;
+    cur.mask = 0;
+    for (int k = 0; k < RC_MAX_P; ++k) cur.N[k] = 1.0;       // Core.hs:296-297
+    mh.segs.assign(1, cur);
+    bool allFire = true;
+    int lastFire = -1;
+    for (const rc_event& e : sorted) {
+        // fires in the first step whose nextTime > t (Core.hs:125)
+        int f = (int)(std::upper_bound(ctx->times.begin(), ctx->times.end(), e.t) - ctx->times.begin());
+        if (f >= T) { allFire = false; continue; }
+        lastFire = f;
+        if (e.type == RC_EV_POPSIZE || e.type == RC_EV_FREEZE) {
+            if (mh.segs.back().sBegin != f) {
+                cur.sBegin = f;
+                mh.segs.push_back(cur);
+            }
+            SegHost& sg = mh.segs.back();
+            if (e.type == RC_EV_POPSIZE) sg.N[e.k] = e.v;
+            else if (e.v != 0.0) sg.mask |= (1u << e.k);
+            else sg.mask &= ~(1u << e.k);
+            cur = sg;
+        } else {
+            rc::StructEv se;
+            se.type = e.type;
+            se.k = e.k;
+            se.l = e.l;
+            se.mclass = 2;
+            if (e.type == RC_EV_SPLIT) {
+                mh.hasSplit = true;
+                se.mclass = e.v == 0.0 ? 0 : (e.v == 1.0 ? 1 : 2);
+            }
+            mh.sev.push_back(se);
+            mh.sevStep.push_back(f);
+            mh.sevM.push_back(e.v);
+        }
+    }
+    // the shortcut test needs an empty event queue (Core.hs:88-89)
+    mh.sShort = -1;
+    if (!noShortcut && allFire) {
+        int s = lastFire + 1;
+        if (s < T) mh.sShort = s;
+    }
+    // signature
+    std::string& sig = mh.sig;
+    sig.reserve(8 * mh.sev.size() + 8);
+    for (const rc::StructEv& se : mh.sev) {
+        sig.push_back((char)se.type);
+        sig.push_back((char)se.k);
+        sig.push_back((char)se.l);
+        sig.push_back((char)se.mclass);
+    }
+    if (mh.hasSplit) {
+        mh.gaps.resize(mh.sev.size());
+        int prev = 0;
+        for (size_t g = 0; g < mh.sev.size(); ++g) {
+            int cnt = std::min(mh.sevStep[g] - prev, ctx->maxAf);
+            sig.push_back('|');
+            sig.push_back((char)cnt);
+            for (int s = 0; s < cnt; ++s) {
+                unsigned m = seg_mask_at(mh.segs, prev + s);
+                mh.gaps[g].masks.push_back(m);
+                sig.append(reinterpret_cast<const char*>(&m), sizeof m);
+            }
+            prev = mh.sevStep[g];
+        }
+    }
+}
+
+template <typename T>
+int upload(rc_ctx* ctx, PlanEntry* pe, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CK(cudaMalloc(&p, n));
+    pe->allocs.push_back(p);
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(p);
+    return RC_OK;
+}
+
+int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
+    auto it = ctx->plans.find(mh.sig);
+    if (it != ctx->plans.end()) {
+        mh.plan = it->second;
+        return RC_OK;
+    }
+    *hit = false;
+    PlanEntry* pe = new PlanEntry();
+    std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
+                                   mh.hasSplit, ctx->smemOptin, pe->h);
+    if (!e.empty()) {
+        delete pe;
+        ctx->err = e;
+        return RC_ERR_UNSUPPORTED;
+    }
+    RcPlanDev& d = pe->d;
+    std::memset(&d, 0, sizeof d);
+    const rc::PlanHost& h = pe->h;
+    d.P = h.P; d.maxAf = h.maxAf; d.A1 = h.maxAf + 1; d.nPat = h.nPat; d.nEpochs = h.nEpochs; d.nnzw = h.nnzw;
+    d.nBins = h.nBins; d.cap = h.cap;
+    int rc;
+    if ((rc = upload(ctx, pe, h.binPatOff, &d.binPatOff))) return rc;
+    if ((rc = upload(ctx, pe, h.binPats, &d.binPats))) return rc;
+    if ((rc = upload(ctx, pe, h.slotOff, &d.slotOff))) return rc;
+    if ((rc = upload(ctx, pe, h.epochBase, &d.epochBase))) return rc;
+    if ((rc = upload(ctx, pe, h.words, &d.words))) return rc;
+    if ((rc = upload(ctx, pe, h.meta, &d.meta))) return rc;
+    if ((rc = upload(ctx, pe, h.trBase, &d.trBase))) return rc;
+    if ((rc = upload(ctx, pe, h.trOff, &d.trOff))) return rc;
+    if ((rc = upload(ctx, pe, h.trEntBase, &d.trEntBase))) return rc;
+    if ((rc = upload(ctx, pe, h.trEnt, &d.trEnt))) return rc;
+    if ((rc = upload(ctx, pe, h.shortcutOK, &d.shortcutOK))) return rc;
+    d.aInit = (const int32_t*)ctx->dAInit.p;
+    d.combFac = (const double*)ctx->dCombFac.p;
+    d.support = (const uint8_t*)ctx->dSupport.p;
+    d.patGlobal = (const int32_t*)ctx->dPatGlobal.p;
+    pe->allShortcut = true;
+    for (uint8_t f : h.shortcutOK) pe->allShortcut = pe->allShortcut && f;
+    ctx->plans[mh.sig] = pe;
+    mh.plan = pe;
+    return RC_OK;
+}
+
+size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
+
+// Executed state-steps (one unit = one iteration of Core.hs:248): live states x update
+// steps, epoch by epoch; patterns that take the shortcut stop at sShort, the others run to T.
+long long count_state_steps(const ModelHost& mh, const rc::PlanHost& h, int T) {
+    long long W = 0;
+    int prev = 0;
+    for (int e = 0; e < h.nEpochs; ++e) {
+        bool last = e + 1 == h.nEpochs;
+        int endFull = last ? T : mh.sevStep[(size_t)e];
+        int endShort = last ? (mh.sShort >= 0 ? mh.sShort : T) : endFull;
+        W += h.epochSlotsShort[(size_t)e] * (long long)(endShort - prev) +
+             (h.epochSlots[(size_t)e] - h.epochSlotsShort[(size_t)e]) * (long long)(endFull - prev);
+        prev = endFull;
+    }
+    return W;
+}
+
+// The whole evaluation up to the per-model partial sums (left on the device).
+int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
+              int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus) {
+    if (ctx->P == 0) { ctx->err = "rc_set_problem has not been called"; return RC_ERR_ARG; }
+    if (ctx->times.empty()) { ctx->err = "rc_set_times has not been called"; return RC_ERR_ARG; }
+    if (B <= 0) return RC_OK;
+    if (B > 32768) { ctx->err = "at most 32768 models per call; split the batch"; return RC_ERR_ARG; }
+    if (ctx->plans.size() >= 64) ctx->clear_plans();   // bounded plan cache
+    const int P = ctx->P, A1 = ctx->maxAf + 1, T = (int)ctx->times.size();
+    const int rowLen = rc_row_len(P, A1);
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->statsPending = false;
+
+    std::vector<ModelHost> mhs((size_t)B);
+    bool hit = true;
+    for (int b = 0; b < B; ++b) {
+        ModelHost& mh = mhs[(size_t)b];
+        if (ctx->compErr) {
+            mh.status = RC_ERR_COMP;
+            mh.err = ctx->compErrMsg;
+        } else {
+            resolve_model(ctx, ev + evOff[b], evOff[b + 1] - evOff[b], disc + (size_t)b * P, noShortcut, mh);
+            if (mh.status == RC_OK && ctx->nPat > 0) {
+                int rc = get_plan(ctx, mh, &hit);
+                if (rc != RC_OK) return rc;
+            }
+        }
+        if (outStatus) outStatus[b] = mh.status;
+        if (mh.status != RC_OK && ctx->err.empty()) ctx->err = mh.err;
+    }
+    // order models by plan so that each plan is one launch
+    std::vector<int> order((size_t)B);
+    for (int b = 0; b < B; ++b) order[(size_t)b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mhs[(size_t)x].plan < mhs[(size_t)y].plan; });
+
+    // ---- pack the per-call blob: headers | structural events | segment offsets | segments | weights
+    size_t nSev = 0, nSeg = 0, nW = 0;
+    for (auto& mh : mhs) {
+        if (mh.status != RC_OK) continue;
+        nSev += mh.sev.size();
+        nSeg += mh.segs.size();
+        for (auto& se : mh.sev) if (se.type == RC_EV_SPLIT) nW += (size_t)A1 * A1;
+    }
+    size_t oModels = 0;
+    size_t oSev = align16(oModels + (size_t)B * sizeof(RcModelDev));
+    size_t oSegOff = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
+    size_t oSegs = align16(oSegOff + (size_t)(B + 1) * sizeof(int));
+    size_t oW = align16(oSegs + std::max<size_t>(nSeg, 1) * sizeof(RcSegDev));
+    size_t blobBytes = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
+    // the pinned staging buffer is reused: wait until the previous call's upload has left it
+    if (ctx->blobInFlight) {
+        CK(cudaEventSynchronize(ctx->evt[5]));
+        ctx->blobInFlight = false;
+    }
+    if (blobBytes > ctx->dBlob.cap) CK(cudaStreamSynchronize(st));   // kernels of the previous call may still read it
+    CK(ctx->hBlob.ensure(blobBytes));
+    CK(ctx->dBlob.ensure(blobBytes));
+    unsigned char* hb = (unsigned char*)ctx->hBlob.p;
+    std::memset(hb, 0, blobBytes);
+    RcModelDev* hM = (RcModelDev*)(hb + oModels);
+    RcSEvDev* hSev = (RcSEvDev*)(hb + oSev);
+    int* hSegOff = (int*)(hb + oSegOff);
+    RcSegDev* hSegs = (RcSegDev*)(hb + oSegs);
+    double* hW = (double*)(hb + oW);
+
+    long long tabDoubles = 0;
+    int rowsMax = 0;
+    size_t sevPos = 0, segPos = 0, wPos = 0;
+    long long W = 0, slots0 = 0;
+    for (int pos = 0; pos < B; ++pos) {
+        const int b = order[(size_t)pos];
+        ModelHost& mh = mhs[(size_t)b];
+        RcModelDev& M = hM[pos];
+        hSegOff[pos] = (int)segPos;
+        M.pad = b;   // original model index: rows of partial / dProbs
+        if (mh.status != RC_OK || ctx->nPat == 0) {
+            M.nSteps = mh.status != RC_OK ? -1 : 0;
+            continue;
+        }
+        const PlanEntry* pe = mh.plan;
+        M.nSteps = T;
+        M.sShort = mh.sShort;
+        M.nSEv = (int)mh.sev.size();
+        M.sevOff = (int)sevPos;
+        M.rowsAvail = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
+        M.tabOff = tabDoubles;
+        M.wPool = 0;
+        M.theta = theta[b];
+        for (int k = 0; k < P; ++k) M.disc[k] = disc[(size_t)b * P + k];
+        tabDoubles += (long long)M.rowsAvail * rowLen;
+        rowsMax = std::max(rowsMax, M.rowsAvail);
+        for (size_t g = 0; g < mh.sev.size(); ++g) {
+            RcSEvDev& d = hSev[sevPos++];
+            d.step = mh.sevStep[g];
+            d.type = mh.sev[g].type;
+            d.k = mh.sev[g].k;
+            d.l = mh.sev[g].l;
+            d.m = mh.sevM[g];
+            d.wOff = 0;
+            if (d.type == RC_EV_SPLIT) {
+                d.wOff = (int)wPos;
+                const double m = d.m;
+                for (int xl = 0; xl < A1; ++xl)
+                    for (int s = 0; s <= xl; ++s)   // Core.hs:216
+                        hW[wPos + (size_t)xl * A1 + s] = ghc_pow(m, s) * ghc_pow(1.0 - m, xl - s) * rc::choose(xl, s);
+                wPos += (size_t)A1 * A1;
+            }
+        }
+        for (const SegHost& sg : mh.segs) {
+            RcSegDev& d = hSegs[segPos++];
+            d.sBegin = sg.sBegin;
+            d.frozenMask = sg.mask;
+            std::memcpy(d.N, sg.N, sizeof d.N);
+        }
+        const rc::PlanHost& h = pe->h;
+        W += count_state_steps(mh, h, T);
+        slots0 += h.epochSlots[0];
+        ctx->stats.n_epochs = h.nEpochs;
+        ctx->stats.n_steps = M.rowsAvail;
+    }
+    hSegOff[B] = (int)segPos;
+    ctx->stats.state_steps = W;
+    ctx->stats.slots = slots0;
+    ctx->stats.plan_cache_hit = hit ? 1 : 0;
+
+    {
+        size_t needTab = (size_t)std::max<long long>(tabDoubles, 1) * sizeof(double);
+        size_t needOut = (size_t)B * std::max(ctx->nPat, 1) * sizeof(double);
+        if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap) CK(cudaStreamSynchronize(st));
+        CK(ctx->dTab.ensure(needTab));
+        CK(ctx->dPOut.ensure(needOut));
+    }
+
+    unsigned char* db = (unsigned char*)ctx->dBlob.p;
+    const RcModelDev* dM = (const RcModelDev*)(db + oModels);
+    const RcSEvDev* dSev = (const RcSEvDev*)(db + oSev);
+    const int* dSegOff = (const int*)(db + oSegOff);
+    const RcSegDev* dSegs = (const RcSegDev*)(db + oSegs);
+    const double* dW = (const double*)(db + oW);
+
+    CK(cudaEventRecord(ctx->evt[0], st));
+    CK(cudaMemcpyAsync(db, hb, blobBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->evt[5], st));
+    ctx->blobInFlight = true;
+    if (dProbs && ctx->world > 1) CK(cudaMemsetAsync(dProbs, 0, (size_t)B * ctx->nPatGlobal * sizeof(double), st));
+    CK(cudaEventRecord(ctx->evt[1], st));
+    int launches = 0;
+    if (rowsMax > 0) {
+        CK(rc_launch_tables(dM, dSegs, dSegOff, (const double*)ctx->dDts.p, (double*)ctx->dTab.p, P, A1, rowsMax, B, st));
+        ++launches;
+    }
+    CK(cudaEventRecord(ctx->evt[2], st));
+    for (int pos = 0; pos < B;) {
+        const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
+        int end = pos + 1;
+        while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
+        if (pe && ctx->nPat > 0) {
+            CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+            ++launches;
+        }
+        pos = end;
+    }
+    CK(cudaEventRecord(ctx->evt[3], st));
+    CK(rc_launch_reduce((const double*)ctx->dPOut.p, (const long long*)ctx->dCounts.p, (const int*)ctx->dPatGlobal.p, dM,
+                        ctx->nPat, ctx->nPatGlobal, B, dPartial, dProbs, st));
+    ++launches;
+    CK(cudaEventRecord(ctx->evt[4], st));
+    ctx->stats.launches = launches;
+    ctx->statsPending = true;
+    return RC_OK;
+}
+
+int collect_stats(rc_ctx* ctx) {
+    if (!ctx->statsPending) return RC_OK;
+    float ms = 0;
+    CK(cudaEventSynchronize(ctx->evt[4]));
+    CK(cudaEventElapsedTime(&ms, ctx->evt[1], ctx->evt[2])); ctx->stats.tables_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->evt[2], ctx->evt[3])); ctx->stats.kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->evt[0], ctx->evt[4])); ctx->stats.total_ms = ms;
+    ctx->statsPending = false;
+    return RC_OK;
+}
+
+int build_shard(rc_ctx* ctx) {
+    const int P = ctx->P, n = ctx->nPatGlobal;
+    ctx->clear_plans();
+    // work proxy: live states at t=0 = prod max(1, m_k); deal work-sorted patterns round-robin
+    std::vector<int> order((size_t)n);
+    std::vector<long long> work((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        long long w = 1;
+        for (int k = 0; k < P; ++k) w *= std::max(1, ctx->patG[(size_t)i * P + k]);
+        work[(size_t)i] = w;
+        order[(size_t)i] = i;
+    }
+    if (ctx->world > 1)
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[(size_t)a] > work[(size_t)b]; });
+    ctx->patGlobalIdx.clear();
+    for (int j = 0; j < n; ++j)
+        if (j % ctx->world == ctx->rank) ctx->patGlobalIdx.push_back(order[(size_t)j]);
+    std::sort(ctx->patGlobalIdx.begin(), ctx->patGlobalIdx.end());
+    ctx->nPat = (int)ctx->patGlobalIdx.size();
+    const int m = ctx->nPat;
+    ctx->patS.resize((size_t)m * P);
+    std::vector<int32_t> aInit((size_t)m * P);
+    std::vector<uint8_t> support((size_t)m * P);
+    std::vector<double> comb((size_t)m);
+    std::vector<long long> cnt((size_t)m);
+    for (int i = 0; i < m; ++i) {
+        int g = ctx->patGlobalIdx[(size_t)i];
+        double cf = 1.0;
+        for (int k = 0; k < P; ++k) {
+            int mk = ctx->patG[(size_t)g * P + k], nk = ctx->nVec[(size_t)k];
+            ctx->patS[(size_t)i * P + k] = mk;
+            aInit[(size_t)i * P + k] = nk - mk;
+            support[(size_t)i * P + k] = mk > 0;
+            cf = cf * rc::choose(nk, mk);        // Core.hs:49
+        }
+        comb[(size_t)i] = cf;
+        cnt[(size_t)i] = ctx->cntG[(size_t)g];
+    }
+    size_t one = 1;
+    CK(ctx->dAInit.ensure(std::max(one, aInit.size()) * sizeof(int32_t)));
+    CK(ctx->dSupport.ensure(std::max(one, support.size())));
+    CK(ctx->dCombFac.ensure(std::max(one, comb.size()) * sizeof(double)));
+    CK(ctx->dCounts.ensure(std::max(one, cnt.size()) * sizeof(long long)));
+    CK(ctx->dPatGlobal.ensure(std::max(one, (size_t)m) * sizeof(int)));
+    if (m > 0) {
+        CK(cudaMemcpy(ctx->dAInit.p, aInit.data(), aInit.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dSupport.p, support.data(), support.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dCombFac.p, comb.data(), comb.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dCounts.p, cnt.data(), cnt.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dPatGlobal.p, ctx->patGlobalIdx.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return RC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* rc_version(void) { return "rarecoal_b200 0.1 (sm_100a)"; }
+
+int rc_create(int device, rc_ctx** out) {
+    if (!out) return RC_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RC_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return RC_ERR_CUDA;
+    rc_ctx* ctx = new rc_ctx();
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    for (auto& e : ctx->evt)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    *out = ctx;
+    return RC_OK;
+}
+
+void rc_destroy(rc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->child) rc_destroy(ctx->child);
+    ctx->clear_plans();
+    DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
+                      &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs};
+    for (DevBuf* b : bufs) b->release();
+    ctx->hBlob.release();
+    ctx->hOut.release();
+    for (auto& e : ctx->evt) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rc_last_error(rc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rc_set_problem(rc_ctx* ctx, int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
+                   const int64_t* counts, int64_t totalSites) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    if (P < 1 || P > RC_MAX_P || maxAf < 1 || maxAf > RC_MAX_AF || nPat < 0 || !nVec || (nPat > 0 && !patterns)) {
+        ctx->err = "rc_set_problem: need 1 <= P <= 32, 1 <= maxAf <= 62";
+        return RC_ERR_ARG;
+    }
+    if (!rc::key_fits(P, maxAf)) { ctx->err = "rc_set_problem: (maxAf+1)^P exceeds 63 bits"; return RC_ERR_UNSUPPORTED; }
+    ctx->compErr = false;
+    ctx->compErrMsg.clear();
+    for (int i = 0; i < nPat; ++i) {
+        int sum = 0;
+        for (int k = 0; k < P; ++k) {
+            int m = patterns[(size_t)i * P + k];
+            if (m < 0) { ctx->err = "rc_set_problem: negative pattern entry"; return RC_ERR_ARG; }
+            sum += m;
+            // choose n k is 0 for k > n: "Overflow Error in getProb" (Core.hs:53-56)
+            if (m > nVec[k] && !ctx->compErr) {
+                ctx->compErr = true;
+                ctx->compErrMsg = "Overflow Error in getProb: pattern " + std::to_string(i) + " exceeds nVec";
+            }
+        }
+        if (sum < 1 || sum > maxAf) {
+            ctx->err = "rc_set_problem: pattern " + std::to_string(i) + " is outside the state space (need 1 <= sum <= maxAf)";
+            return RC_ERR_ARG;
+        }
+    }
+    ctx->P = P;
+    ctx->maxAf = maxAf;
+    ctx->nPatGlobal = nPat;
+    ctx->patG.assign(patterns, patterns + (size_t)nPat * P);
+    ctx->nVec.assign(nVec, nVec + P);
+    ctx->cntG.assign((size_t)nPat, 0);
+    ctx->sumCounts = 0;
+    if (counts)
+        for (int i = 0; i < nPat; ++i) {
+            ctx->cntG[(size_t)i] = counts[i];
+            ctx->sumCounts += counts[i];
+        }
+    ctx->totalSites = totalSites;
+    ctx->rank = 0;
+    ctx->world = 1;
+    return build_shard(ctx);
+}
+
+int rc_set_shard(rc_ctx* ctx, int rank, int world) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (ctx->P == 0) { ctx->err = "rc_set_shard: call rc_set_problem first"; return RC_ERR_ARG; }
+    if (world < 1 || rank < 0 || rank >= world) { ctx->err = "rc_set_shard: bad rank/world"; return RC_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->rank = rank;
+    ctx->world = world;
+    return build_shard(ctx);
+}
+
+int rc_set_times(rc_ctx* ctx, int T, const double* t) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (T < 1 || !t) { ctx->err = "rc_set_times: empty grid"; return RC_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->times.assign(t, t + T);
+    ctx->dts.resize((size_t)T);
+    // deltaT = nextTime - t; t += deltaT (Core.hs:129,135) — the running clock is kept as the reference keeps it
+    double clock = 0.0;
+    for (int s = 0; s < T; ++s) {
+        double dt = t[s] - clock;
+        ctx->dts[(size_t)s] = dt;
+        if (dt > 0) clock = clock + dt;
+        if (s > 0 && !(t[s] >= t[s - 1])) { ctx->err = "rc_set_times: grid must be non-decreasing"; return RC_ERR_ARG; }
+    }
+    CK(ctx->dDts.ensure((size_t)T * sizeof(double)));
+    CK(cudaMemcpy(ctx->dDts.p, ctx->dts.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->clear_plans();
+    return RC_OK;
+}
+
+int rc_time_steps(int n0, int lingen, double tMax, double* out, int cap) {
+    // getTimeSteps (Utils.hs:64-73)
+    double tMin = 1.0 / (2.0 * (double)n0);
+    double alpha = (double)lingen / (2.0 * (double)n0);
+    double lg = std::log(1.0 + tMax / alpha);
+    int nr = (int)std::floor(lg / std::log(1.0 + tMin / alpha));
+    int n = nr - 1 > 0 ? nr - 1 : 0;
+    for (int i = 1; i <= n && i <= cap; ++i)
+        if (out) out[i - 1] = alpha * std::exp((double)i / (double)nr * lg) - alpha;
+    return n;
+}
+
+int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta,
+                    const double* disc, int noShortcut, double* dPartial, double* dProbs, void* stream,
+                    int32_t* outStatus) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (B < 0 || !evOff || !theta || !disc || !dPartial) { ctx->err = "rc_eval_partial: null argument"; return RC_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    return eval_impl(ctx, B, ev, evOff, theta, disc, noShortcut, dPartial, dProbs, (cudaStream_t)stream, outStatus);
+}
+
+int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRed, void* stream, double* outLogl) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (B <= 0) return RC_OK;
+    if (!dPartialReduced || !outLogl) { ctx->err = "rc_finalize: null argument"; return RC_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(ctx->dLogl.ensure((size_t)B * sizeof(double)));
+    CK(ctx->hOut.ensure((size_t)B * sizeof(double)));
+    double other = (double)(ctx->totalSites - ctx->sumCounts);     // MaxUtils.hs:90
+    CK(rc_launch_finalize(dPartialReduced, B, other, siteRed, (double*)ctx->dLogl.p, st));
+    CK(cudaMemcpyAsync(ctx->hOut.p, ctx->dLogl.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(outLogl, ctx->hOut.p, (size_t)B * sizeof(double));
+    ctx->stats.launches += 1;
+    return collect_stats(ctx);
+}
+
+int rc_eval(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
+            int noShortcut, double siteRed, double* outProbs, double* outLogl, int32_t* outStatus) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (B < 0 || !evOff || !theta || !disc || !outLogl) { ctx->err = "rc_eval: null argument"; return RC_ERR_ARG; }
+    if (B == 0) return RC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dPartial.ensure((size_t)2 * B * sizeof(double)));
+    double* dProbs = nullptr;
+    size_t probBytes = (size_t)B * std::max(ctx->nPatGlobal, 1) * sizeof(double);
+    if (outProbs) {
+        CK(ctx->dProbs.ensure(probBytes));
+        dProbs = (double*)ctx->dProbs.p;
+    }
+    int rc = eval_impl(ctx, B, ev, evOff, theta, disc, noShortcut, (double*)ctx->dPartial.p, dProbs, ctx->stream, outStatus);
+    if (rc != RC_OK) return rc;
+    if (outProbs && ctx->nPatGlobal > 0) {
+        CK(ctx->hOut.ensure(std::max(probBytes, (size_t)B * sizeof(double))));
+        CK(cudaMemcpyAsync(ctx->hOut.p, dProbs, probBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(outProbs, ctx->hOut.p, probBytes);
+    }
+    return rc_finalize(ctx, B, (const double*)ctx->dPartial.p, siteRed, ctx->stream, outLogl);
+}
+
+int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_t* config, const rc_event* ev, int nEv,
+                double theta, const double* disc, int noShortcut, double* outProb) {
+    if (!ctx) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (ctx->times.empty()) { ctx->err = "rc_get_prob: rc_set_times has not been called"; return RC_ERR_ARG; }
+    if (!ctx->child) {
+        int rc = rc_create(ctx->device, &ctx->child);
+        if (rc != RC_OK) { ctx->err = "rc_get_prob: cannot create scratch context"; return rc; }
+    }
+    rc_ctx* c = ctx->child;
+    int64_t zero = 0;
+    int rc = rc_set_problem(c, P, maxAf, 1, config, nVec, &zero, 0);
+    if (rc == RC_OK) rc = rc_set_times(c, (int)ctx->times.size(), ctx->times.data());
+    int32_t off[2] = {0, nEv};
+    int32_t status = 0;
+    double logl = 0, prob = 0;
+    if (rc == RC_OK) rc = rc_eval(c, 1, ev, off, &theta, disc, noShortcut, 1.0, &prob, &logl, &status);
+    if (rc != RC_OK) { ctx->err = c->err; return rc; }
+    if (status != RC_OK) { ctx->err = c->err; return status; }
+    *outProb = prob;
+    return RC_OK;
+}
+
+int rc_last_stats(rc_ctx* ctx, rc_stats* out) {
+    if (!ctx || !out) return RC_ERR_ARG;
+    int rc = collect_stats(ctx);
+    *out = ctx->stats;
+    return rc;
+}
+
+int rc_fp64_peak(rc_ctx* ctx, double* outTflops) {
+    if (!ctx || !outTflops) return RC_ERR_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->smCount * 16, iters = 4096;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(a, ctx->stream));
+        CK(rc_launch_fp64_peak(d, blocks, iters, ctx->stream));
+        CK(cudaEventRecord(b, ctx->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *outTflops = best;
+    return RC_OK;
+}
+
+// ---- host-side mirrors -------------------------------------------------------------------------
+int rc_all_configs(int maxAf, int P, const int32_t* nVec, int32_t* out, int cap) {
+    if (P < 1 || maxAf < 1 || !nVec) return RC_ERR_ARG;
+    auto v = rc::all_configs(maxAf, std::vector<int>(nVec, nVec + P));
+    if (out)
+        for (size_t i = 0; i < v.size() && (int)i < cap; ++i)
+            for (int k = 0; k < P; ++k) out[i * P + k] = v[i][k];
+    return (int)v.size();
+}
+
+int rc_validate_model(int P, const double* disc, const rc_event* ev, int nEv, char* err, int errCap) {
+    if (P < 1 || P > RC_MAX_P || !disc || nEv < 0) return RC_ERR_ARG;
+    std::string msg;
+    int rc = validate_model(P, disc, sort_events(ev, nEv), msg);
+    if (err && errCap > 0) std::snprintf(err, (size_t)errCap, "%s", msg.c_str());
+    return rc;
+}
+
+double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv) {
+    // getRegularizationPenalty (StateSpace.hs:199-221): sizes tracked through SetPopSize events only
+    std::vector<rc_event> s = sort_events(ev, nEv);
+    std::vector<double> size((size_t)std::max(P, 1), 1.0);
+    auto term = [reg](double from, double to) {
+        double ratio = to > from ? to / from : from / to;
+        return reg * ((ratio - 1.0) * (ratio - 1.0));
+    };
+    double total = 0.0;
+    for (const rc_event& e : s) {
+        if (e.type == RC_EV_POPSIZE) {
+            if (e.t != 0.0) total = total + term(size[(size_t)e.k], e.v);
+            size[(size_t)e.k] = e.v;
+        } else if (e.type == RC_EV_JOIN) {
+            total = total + term(size[(size_t)e.l], size[(size_t)e.k]);
+        }
+    }
+    return total;
+}
+
+double rc_choose(int n, int k) { return rc::choose(n, k); }
+
+int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T, const double* times,
+                  const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps, int64_t* slots0, int32_t* maxLive,
+                  int32_t* nEpochs, int32_t* nBins) {
+    if (P < 1 || P > RC_MAX_P || maxAf < 1 || maxAf > RC_MAX_AF || nPat < 1 || !patterns || !nVec || T < 1 || !times)
+        return RC_ERR_ARG;
+    rc_ctx tmp;   // host-only use: no CUDA call is made on this object
+    tmp.P = P;
+    tmp.maxAf = maxAf;
+    tmp.times.assign(times, times + T);
+    std::vector<double> disc((size_t)P, 1.0);
+    ModelHost mh;
+    resolve_model(&tmp, ev, nEv, disc.data(), noShortcut, mh);
+    if (mh.status != RC_OK) return mh.status;
+    rc::PlanHost h;
+    std::string e = rc::build_plan(P, maxAf, nPat, patterns, nVec, mh.sev, mh.gaps, mh.hasSplit, 227 * 1024, h);
+    if (!e.empty()) return RC_ERR_UNSUPPORTED;
+    if (stateSteps) *stateSteps = count_state_steps(mh, h, T);
+    if (slots0) *slots0 = h.epochSlots[0];
+    if (maxLive) *maxLive = h.maxLive;
+    if (nEpochs) *nEpochs = h.nEpochs;
+    if (nBins) *nBins = h.nBins;
+    return RC_OK;
+}
+
+rc_statespace* rc_ss_create(int P, int maxAf) {
+    rc::StateSpace* s = rc::make_state_space(P, maxAf);
+    if (!s) return nullptr;
+    rc_statespace* h = new rc_statespace();
+    h->ss = s;
+    return h;
+}
+void rc_ss_destroy(rc_statespace* ss) {
+    if (!ss) return;
+    delete ss->ss;
+    delete ss;
+}
+int rc_ss_nr_states(const rc_statespace* ss) { return ss ? ss->ss->nrStates : RC_ERR_ARG; }
+int rc_ss_state_to_id(const rc_statespace* ss, const int32_t* x) { return ss && x ? ss->ss->state_to_id(x) : RC_ERR_ARG; }
+int rc_ss_id_to_state(const rc_statespace* ss, int id, int32_t* x) {
+    if (!ss || !x || id < 0 || id >= ss->ss->nrStates) return RC_ERR_ARG;
+    for (int k = 0; k < ss->ss->P; ++k) x[k] = ss->ss->states[(size_t)id * ss->ss->P + k];
+    return RC_OK;
+}
+int rc_ss_x1up(const rc_statespace* ss, int id, int32_t* out) {
+    if (!ss || !out || id < 0 || id >= ss->ss->nrStates) return RC_ERR_ARG;
+    for (int k = 0; k < ss->ss->P; ++k) out[k] = ss->ss->x1up[(size_t)id * ss->ss->P + k];
+    return RC_OK;
+}
+int rc_ss_x1(const rc_statespace* ss, int k) { return ss && k >= 0 && k < ss->ss->P ? ss->ss->x1[(size_t)k] : RC_ERR_ARG; }
+int rc_ss_fill_up(const rc_statespace* ss, const int32_t* ids, int n, int32_t* out, int cap) {
+    if (!ss || (n > 0 && !ids)) return RC_ERR_ARG;
+    std::vector<int> r = ss->ss->fill_up(std::vector<int>(ids, ids + n));
+    if (out) for (size_t i = 0; i < r.size() && (int)i < cap; ++i) out[i] = r[i];
+    return (int)r.size();
+}
+
+}  // extern "C"

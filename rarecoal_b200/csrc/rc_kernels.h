@@ -1,0 +1,20 @@
+// rc_kernels.h — launch wrappers of the sm_100a kernels (rc_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "rc_types.h"
+
+size_t rc_propagate_smem_bytes(int cap, int nnzw, int P, int rowLen);
+
+cudaError_t rc_launch_tables(const RcModelDev* models, const RcSegDev* segs, const int* segOff, const double* dts,
+                             double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st);
+cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
+                                const double* tab, const double* wpool, double* pOut, int b0, int nB,
+                                cudaStream_t st);
+cudaError_t rc_launch_reduce(const double* pOut, const long long* counts, const int* patGlobal,
+                             const RcModelDev* models, int nPat, int nPatGlobal, int B, double* partial,
+                             double* dProbs, cudaStream_t st);
+cudaError_t rc_launch_finalize(const double* partial, int B, double other, double siteRed, double* logl,
+                               cudaStream_t st);
+cudaError_t rc_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t st);

@@ -1,0 +1,516 @@
+// rc_plan.cpp — host planner (see rc_plan.h).
+//
+// The planner resolves, once per (problem, event structure), everything about the propagation that
+// does not depend on continuous parameters:
+//   * the live-state list of every pattern in every structural epoch, in the reference's own order
+//     (fillUpStateSpace . nub, StateSpace.hs:145-160; Core.hs:67,188,221);
+//   * for each live state the neighbour slots x + e_k read by updateB (Core.hs:272-280; the
+//     reference's dense `x1up` table, StateSpace.hs:77-79, restricted to the live set);
+//   * the Join / Split transition tables (Core.hs:172-221) as gather lists: new_b[y] = sum over
+//     sources of old_b[x] * w, with w = 1 (Join) or an index into the per-model binomial table
+//     m^s (1-m)^(x_l-s) choose(x_l, s) (Split);
+//   * whether the pattern can take the closed-form shortcut (Core.hs:80-89) once the event queue is
+//     empty.
+// The kernels then do arithmetic only.
+#include "rc_plan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <thread>
+
+namespace rc {
+
+// ---- enumeration -------------------------------------------------------------------------------
+// computeAllConfigs (Utils.hs:100-112,121-127).  The reference enumerates (P-1)-subsets of
+// {1..P+af-1} in `allSubsets` order (those without the largest element first) and takes gaps; that
+// is the same as: last component descending from af to 0, and for each value the (P-1)-prefixes of
+// the remainder in the same order.
+static void compositions(int P, int af, std::vector<int>& cur, std::vector<std::vector<int>>& out) {
+    if (P == 1) {
+        cur[0] = af;
+        out.push_back(cur);
+        return;
+    }
+    for (int v = af; v >= 0; --v) {
+        cur[P - 1] = v;
+        compositions(P - 1, af - v, cur, out);
+    }
+}
+
+std::vector<std::vector<int>> all_configs(int maxAf, const std::vector<int>& nVec) {
+    int P = (int)nVec.size();
+    std::vector<std::vector<int>> all, out;
+    std::vector<int> cur((size_t)P, 0);
+    for (int af = 1; af <= maxAf; ++af) compositions(P, af, cur, all);
+    for (auto& v : all) {
+        bool ok = true;
+        for (int k = 0; k < P && ok; ++k) ok = v[k] <= nVec[k];
+        if (ok) out.push_back(v);
+    }
+    return out;
+}
+
+// choose n k (Utils.hs:208-210): left product of (n+1-j)/j.
+double choose(int n, int k) {
+    double p = 1.0;
+    for (int j = 1; j <= k; ++j) p = p * ((double)(n + 1 - j) / (double)j);
+    return p;
+}
+
+// ---- state space -------------------------------------------------------------------------------
+bool key_fits(int P, int maxAf) {
+    long double v = 1.0L;
+    for (int k = 0; k < P; ++k) v *= (long double)(maxAf + 1);
+    return v < 9.0e18L;
+}
+
+uint64_t StateSpace::key(const int32_t* x) const {
+    uint64_t h = 0;
+    for (int k = 0; k < P; ++k) h = h * (uint64_t)(maxAf + 1) + (uint64_t)x[k];
+    return h;
+}
+
+int StateSpace::state_to_id(const int32_t* x) const {
+    for (int k = 0; k < P; ++k)
+        if (x[k] < 0 || x[k] > maxAf) return -1;
+    auto it = toId.find(key(x));
+    return it == toId.end() ? -1 : it->second;
+}
+
+StateSpace* make_state_space(int P, int maxAf) {
+    if (P < 1 || P > RC_MAX_P || maxAf < 1 || maxAf > RC_MAX_AF || !key_fits(P, maxAf)) return nullptr;
+    StateSpace* ss = new StateSpace();
+    ss->P = P;
+    ss->maxAf = maxAf;
+    auto cfg = all_configs(maxAf, std::vector<int>((size_t)P, maxAf));
+    ss->nrStates = (int)cfg.size();
+    ss->states.resize((size_t)ss->nrStates * P);
+    std::vector<int32_t> x((size_t)P);
+    for (int i = 0; i < ss->nrStates; ++i) {
+        for (int k = 0; k < P; ++k) {
+            ss->states[(size_t)i * P + k] = (uint8_t)cfg[i][k];
+            x[k] = cfg[i][k];
+        }
+        ss->toId[ss->key(x.data())] = i;
+    }
+    ss->x1up.assign((size_t)ss->nrStates * P, -1);
+    for (int i = 0; i < ss->nrStates; ++i) {
+        int sum = 0;
+        for (int k = 0; k < P; ++k) {
+            x[k] = ss->states[(size_t)i * P + k];
+            sum += x[k];
+        }
+        if (sum + 1 > maxAf) continue;   // StateSpace.hs:79
+        for (int k = 0; k < P; ++k) {
+            x[k] += 1;
+            ss->x1up[(size_t)i * P + k] = ss->state_to_id(x.data());
+            x[k] -= 1;
+        }
+    }
+    ss->x1.resize((size_t)P);
+    for (int k = 0; k < P; ++k) {
+        std::fill(x.begin(), x.end(), 0);
+        x[k] = 1;
+        ss->x1[k] = ss->state_to_id(x.data());
+    }
+    return ss;
+}
+
+std::vector<int> StateSpace::fill_up(const std::vector<int>& ids) const {
+    std::vector<int> out;
+    std::vector<char> seen((size_t)nrStates, 0);
+    std::vector<int32_t> lo((size_t)P), hi((size_t)P);
+    for (int id : ids) {
+        if (id < 0 || id >= nrStates) continue;
+        for (int k = 0; k < P; ++k) {
+            hi[k] = states[(size_t)id * P + k];
+            lo[k] = hi[k] ? 1 : 0;
+        }
+        for (;;) {
+            int y = state_to_id(lo.data());
+            if (y >= 0 && !seen[y]) {
+                seen[y] = 1;
+                out.push_back(y);
+            }
+            int k = P - 1;
+            while (k >= 0 && (hi[k] == 0 || lo[k] == hi[k])) {
+                if (hi[k]) lo[k] = 1;
+                --k;
+            }
+            if (k < 0) break;
+            lo[k] += 1;
+        }
+    }
+    return out;
+}
+
+// ---- per-pattern plan ----------------------------------------------------------------------------
+namespace {
+
+struct St {
+    uint8_t x[RC_MAX_P];
+};
+
+struct PatPlan {
+    std::vector<int> live;          // [nEpochs]
+    std::vector<uint32_t> words;    // per epoch: live * stride
+    std::vector<uint32_t> meta;     // per epoch: live
+    std::vector<int> trCnt;         // per transition: live_{e+1} counts
+    std::vector<uint32_t> trEnt;
+    bool shortcutOK = false;
+    int maxLive = 0;
+    int maxNnz = 0;
+    std::string err;
+};
+
+struct Ctx {
+    int P, maxAf, stride;
+    uint64_t base;
+    uint64_t key(const St& s) const {
+        uint64_t h = 0;
+        for (int k = 0; k < P; ++k) h = h * base + s.x[k];
+        return h;
+    }
+};
+
+typedef std::unordered_map<uint64_t, int> Index;
+
+// fillUpStateSpace over explicit states: for every seed, every y with 1 <= y_k <= x_k where x_k > 0
+// (component 0 slowest), first occurrence kept (nub).
+void fill_up_states(const Ctx& c, const std::vector<St>& seeds, std::vector<St>& out, Index& idx) {
+    out.clear();
+    idx.clear();
+    St cur;
+    for (const St& hi : seeds) {
+        for (int k = 0; k < c.P; ++k) cur.x[k] = hi.x[k] ? 1 : 0;
+        for (;;) {
+            uint64_t h = c.key(cur);
+            if (idx.find(h) == idx.end()) {
+                idx.emplace(h, (int)out.size());
+                out.push_back(cur);
+            }
+            int k = c.P - 1;
+            while (k >= 0 && (hi.x[k] == 0 || cur.x[k] == hi.x[k])) {
+                if (hi.x[k]) cur.x[k] = 1;
+                --k;
+            }
+            if (k < 0) break;
+            cur.x[k] += 1;
+        }
+    }
+}
+
+void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPlan& pp) {
+    pp.live.push_back((int)L.size());
+    pp.maxLive = std::max(pp.maxLive, (int)L.size());
+    size_t w0 = pp.words.size();
+    pp.words.resize(w0 + L.size() * (size_t)c.stride, 0u);
+    for (size_t i = 0; i < L.size(); ++i) {
+        St s = L[i];
+        int nnz = 0, sum = 0;
+        for (int k = 0; k < c.P; ++k) {
+            int xk = s.x[k];
+            if (!xk) continue;
+            sum += xk;
+            s.x[k] = (uint8_t)(xk + 1);
+            uint32_t up = RC_NO_UP;
+            if (xk + 1 <= c.maxAf) {
+                auto it = idx.find(c.key(s));
+                if (it != idx.end()) up = (uint32_t)it->second;
+            }
+            s.x[k] = (uint8_t)xk;
+            pp.words[w0 + i * c.stride + nnz] = (uint32_t)k | ((uint32_t)xk << 8) | (up << 16);
+            ++nnz;
+        }
+        pp.maxNnz = std::max(pp.maxNnz, nnz);
+        uint32_t m = (uint32_t)nnz | ((uint32_t)sum << 16);
+        if (nnz == 1 && sum == 1) m |= RC_META_UNIT;
+        pp.meta.push_back(m);
+    }
+}
+
+void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std::vector<StructEv>& sev,
+                  const std::vector<GapInfo>& gaps, bool hasSplit, PatPlan& pp) {
+    const int P = c.P;
+    std::vector<St> L, L2, seeds;
+    Index idx, idx2;
+    St m0;
+    std::memset(&m0, 0, sizeof(m0));
+    for (int k = 0; k < P; ++k) m0.x[k] = (uint8_t)m[k];
+    seeds.assign(1, m0);
+    fill_up_states(c, seeds, L, idx);                    // Core.hs:67
+    std::vector<char> Z(L.size(), 0), Z2;                // Z[i] <=> b(L[i]) > 0 (symbolically)
+    Z[idx[c.key(m0)]] = 1;                               // Core.hs:66
+    bool apos[RC_MAX_P];
+    for (int k = 0; k < P; ++k) apos[k] = (nVec[k] - m[k]) > 0;
+    emit_epoch(c, L, idx, pp);
+
+    for (size_t g = 0; g < sev.size(); ++g) {
+        // updateB spreads positivity one level down per executed step (Core.hs:272-280)
+        if (hasSplit) {
+            for (unsigned mask : gaps[g].masks) {
+                bool all = true, changed = false;
+                Z2 = Z;
+                for (size_t i = 0; i < L.size(); ++i) {
+                    if (Z[i]) continue;
+                    St s = L[i];
+                    for (int k = 0; k < P && !Z2[i]; ++k) {
+                        if (!s.x[k] || ((mask >> k) & 1u)) continue;
+                        s.x[k] += 1;
+                        auto it = idx.find(c.key(s));
+                        if (it != idx.end() && Z[it->second]) Z2[i] = 1;
+                        s.x[k] -= 1;
+                    }
+                    if (Z2[i]) changed = true; else all = false;
+                }
+                Z.swap(Z2);
+                if (all || !changed) break;
+            }
+        }
+        const StructEv& e = sev[g];
+        const int k = e.k, l = e.l;
+        // (target, src, widx) records in the reference's accumulation order
+        struct Rec { uint64_t key; int src; uint32_t widx; };
+        std::vector<Rec> recs;
+        seeds.clear();
+        std::unordered_map<uint64_t, char> pos;          // target -> b' > 0 ?
+        if (e.type == RC_EV_JOIN_D) {                      // Core.hs:172-188
+            Index seen;
+            for (size_t i = 0; i < L.size(); ++i) {
+                St y = L[i];
+                int v = y.x[k] + y.x[l];
+                if (v > c.maxAf) { pp.err = "state outside the state space after Join"; return; }
+                y.x[k] = (uint8_t)v;
+                y.x[l] = 0;
+                uint64_t h = c.key(y);
+                recs.push_back({h, (int)i, RC_W_ONE});
+                if (seen.emplace(h, 0).second) seeds.push_back(y);   // nub newNonZeroStateIds (no b>0 filter)
+                char& pz = pos[h];
+                pz = pz || Z[i];
+            }
+            apos[k] = apos[k] || apos[l];                // Core.hs:165-170
+            apos[l] = false;
+        } else {                                         // Core.hs:202-221
+            std::vector<std::pair<uint64_t, St>> targets;
+            for (size_t i = 0; i < L.size(); ++i) {
+                int xl = L[i].x[l], xk = L[i].x[k];
+                for (int s = 0; s <= xl; ++s) {
+                    St y = L[i];
+                    y.x[k] = (uint8_t)(xk + s);
+                    y.x[l] = (uint8_t)(xl - s);
+                    uint64_t h = c.key(y);
+                    recs.push_back({h, (int)i, (uint32_t)(xl * (c.maxAf + 1) + s)});
+                    bool wpos = e.mclass == 2 || (e.mclass == 0 && s == 0) || (e.mclass == 1 && s == xl);
+                    char& pz = pos[h];
+                    pz = pz || (Z[i] && wpos);
+                    targets.emplace_back(h, y);
+                }
+            }
+            Index seen;
+            for (auto& t : targets)                      // filterM (b > 0) then nub, Core.hs:220-221
+                if (pos[t.first] && seen.emplace(t.first, 0).second) seeds.push_back(t.second);
+            bool al = apos[l];                           // Core.hs:195-200
+            apos[k] = apos[k] || (al && e.mclass != 0);
+            apos[l] = al && e.mclass != 1;
+        }
+        fill_up_states(c, seeds, L2, idx2);
+        if (L2.size() > 0xFFFEu) { pp.err = "live set of one pattern exceeds 65534 states"; return; }
+        // gather lists per new slot, preserving source order
+        std::vector<int> cnt(L2.size(), 0);
+        std::vector<int> tgt(recs.size(), -1);
+        for (size_t r = 0; r < recs.size(); ++r) {
+            auto it = idx2.find(recs[r].key);
+            if (it == idx2.end()) continue;              // target filtered out (its b' is exactly 0)
+            tgt[r] = it->second;
+            cnt[it->second]++;
+        }
+        std::vector<int> off(L2.size() + 1, 0);
+        for (size_t i = 0; i < L2.size(); ++i) off[i + 1] = off[i] + cnt[i];
+        size_t e0 = pp.trEnt.size();
+        pp.trEnt.resize(e0 + (size_t)off[L2.size()]);
+        std::vector<int> fillp(off.begin(), off.end() - 1);
+        for (size_t r = 0; r < recs.size(); ++r) {
+            if (tgt[r] < 0) continue;
+            pp.trEnt[e0 + (size_t)fillp[tgt[r]]++] = (uint32_t)recs[r].src | (recs[r].widx << 16);
+        }
+        pp.trCnt.insert(pp.trCnt.end(), cnt.begin(), cnt.end());
+        Z2.assign(L2.size(), 0);
+        for (size_t i = 0; i < L2.size(); ++i) {
+            auto it = pos.find(c.key(L2[i]));
+            Z2[i] = it != pos.end() && it->second;
+        }
+        L.swap(L2);
+        idx.swap(idx2);
+        Z.swap(Z2);
+        emit_epoch(c, L, idx, pp);
+    }
+    // canUseShortcut (Core.hs:80-89), evaluated when the event queue is empty
+    bool single = true;
+    size_t last = pp.meta.size() - L.size();
+    for (size_t i = 0; i < L.size(); ++i) single = single && ((pp.meta[last + i] & 0xFFu) == 1u);
+    int na = 0;
+    for (int k = 0; k < P; ++k) na += apos[k] ? 1 : 0;
+    pp.shortcutOK = single && na == 1;
+}
+
+}  // namespace
+
+std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
+                       const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
+                       int smemBudgetBytes, PlanHost& out) {
+    if (!key_fits(P, maxAf)) return "state key (maxAf+1)^P does not fit 63 bits";
+    Ctx c;
+    c.P = P;
+    c.maxAf = maxAf;
+    c.stride = std::min(P, maxAf);
+    c.base = (uint64_t)(maxAf + 1);
+    const int nEpochs = (int)sev.size() + 1;
+    std::vector<PatPlan> pps((size_t)nPat);
+
+    int nThreads = (int)std::thread::hardware_concurrency();
+    if (nThreads < 1) nThreads = 1;
+    if (nThreads > 16) nThreads = 16;
+    if (nPat < 256) nThreads = 1;
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            int i0 = next.fetch_add(64);
+            if (i0 >= nPat) break;
+            int i1 = std::min(nPat, i0 + 64);
+            for (int i = i0; i < i1; ++i)
+                plan_pattern(c, patterns + (size_t)i * P, nVec, sev, gaps, hasSplit, pps[(size_t)i]);
+        }
+    };
+    if (nThreads == 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nThreads; ++t) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+    int nnzw = 1, maxLive = 1;
+    for (auto& pp : pps) {
+        if (!pp.err.empty()) return pp.err;
+        nnzw = std::max(nnzw, pp.maxNnz);
+        maxLive = std::max(maxLive, pp.maxLive);
+    }
+
+    out = PlanHost();
+    out.P = P; out.maxAf = maxAf; out.nPat = nPat; out.nEpochs = nEpochs; out.nnzw = nnzw; out.maxLive = maxLive;
+
+    // block capacity: a multiple of the block size that holds the largest pattern; bounded by shared memory
+    int cap = ((maxLive + RC_BLOCK - 1) / RC_BLOCK) * RC_BLOCK;
+    // bytes per slot in the kernel: 2 b buffers + d accumulator (24) + words (4*nnzw) + meta (4) + owner (2)
+    int perSlot = 24 + 4 * nnzw + 4 + 2;
+    int fixed = RC_NPB * P * 16 + RC_NPB * 32 + rc_row_len(P, maxAf + 1) * 8 + 1024;
+    if ((long long)cap * perSlot + fixed > smemBudgetBytes)
+        return "live set of one pattern (" + std::to_string(maxLive) + " states) exceeds the shared-memory tier";
+    out.cap = cap;
+
+    // bins: best-fit decreasing on the per-pattern maximum live size
+    std::vector<int> order((size_t)nPat);
+    for (int i = 0; i < nPat; ++i) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pps[(size_t)a].maxLive > pps[(size_t)b].maxLive; });
+    std::vector<std::vector<int>> bins;
+    std::vector<int> binFree;
+    std::multimap<int, int> open;   // free capacity -> bin
+    for (int i : order) {
+        int sz = pps[(size_t)i].maxLive;
+        auto it = open.lower_bound(sz);
+        int b;
+        if (it == open.end()) {
+            b = (int)bins.size();
+            bins.emplace_back();
+            binFree.push_back(cap);
+        } else {
+            b = it->second;
+            open.erase(it);
+        }
+        bins[(size_t)b].push_back(i);
+        binFree[(size_t)b] -= sz;
+        if ((int)bins[(size_t)b].size() < RC_NPB && binFree[(size_t)b] > 0) open.emplace(binFree[(size_t)b], b);
+    }
+    // heaviest bins first so the hardware block scheduler ends with the light ones
+    std::vector<int> border(bins.size());
+    for (size_t b = 0; b < bins.size(); ++b) border[b] = (int)b;
+    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return binFree[(size_t)a] < binFree[(size_t)b]; });
+    out.nBins = (int)bins.size();
+    out.binPatOff.assign(1, 0);
+    for (int b : border) {
+        for (int i : bins[(size_t)b]) out.binPats.push_back(i);
+        out.binPatOff.push_back((int)out.binPats.size());
+    }
+
+    // concatenate per-epoch arrays
+    out.slotOff.assign((size_t)nEpochs * (nPat + 1), 0);
+    out.epochBase.assign((size_t)nEpochs, 0);
+    out.epochSlots.assign((size_t)nEpochs, 0);
+    out.epochSlotsShort.assign((size_t)nEpochs, 0);
+    out.shortcutOK.resize((size_t)nPat);
+    long long total = 0;
+    for (int e = 0; e < nEpochs; ++e) {
+        out.epochBase[(size_t)e] = total;
+        int* so = &out.slotOff[(size_t)e * (nPat + 1)];
+        long long tot = 0, totS = 0;
+        for (int i = 0; i < nPat; ++i) {
+            so[i] = (int)tot;
+            tot += pps[(size_t)i].live[(size_t)e];
+            if (pps[(size_t)i].shortcutOK) totS += pps[(size_t)i].live[(size_t)e];
+        }
+        if (tot > 0x7FFFFFFFLL) return "too many live states in one epoch";
+        so[nPat] = (int)tot;
+        out.epochSlots[(size_t)e] = tot;
+        out.epochSlotsShort[(size_t)e] = totS;
+        total += tot;
+    }
+    out.totalSlots = total;
+    out.words.assign((size_t)total * nnzw, 0u);
+    out.meta.assign((size_t)total, 0u);
+    for (int i = 0; i < nPat; ++i) {
+        const PatPlan& pp = pps[(size_t)i];
+        out.shortcutOK[(size_t)i] = pp.shortcutOK ? 1 : 0;
+        size_t wp = 0, mp = 0;
+        for (int e = 0; e < nEpochs; ++e) {
+            long long g0 = out.epochBase[(size_t)e] + out.slotOff[(size_t)e * (nPat + 1) + i];
+            int n = pp.live[(size_t)e];
+            for (int s = 0; s < n; ++s) {
+                for (int d = 0; d < nnzw; ++d) out.words[(size_t)(g0 + s) * nnzw + d] = pp.words[wp + (size_t)s * c.stride + d];
+                out.meta[(size_t)(g0 + s)] = pp.meta[mp + s];
+            }
+            wp += (size_t)n * c.stride;
+            mp += (size_t)n;
+        }
+    }
+    // transitions
+    out.trBase.assign((size_t)nEpochs, 0);
+    out.trEntBase.assign((size_t)nEpochs, 0);
+    long long tb = 0, te = 0;
+    std::vector<size_t> cntPos((size_t)nPat, 0), entPos((size_t)nPat, 0);
+    for (int e = 0; e + 1 < nEpochs; ++e) {
+        out.trBase[(size_t)e] = tb;
+        out.trEntBase[(size_t)e] = te;
+        long long nNew = out.epochSlots[(size_t)e + 1];
+        out.trOff.resize((size_t)(tb + nNew + 1));
+        long long run = 0;
+        for (int i = 0; i < nPat; ++i) {
+            const PatPlan& pp = pps[(size_t)i];
+            int n = pp.live[(size_t)e + 1];
+            long long s0 = tb + out.slotOff[(size_t)(e + 1) * (nPat + 1) + i];
+            for (int s = 0; s < n; ++s) {
+                out.trOff[(size_t)(s0 + s)] = (int)run;
+                int cn = pp.trCnt[cntPos[(size_t)i] + s];
+                for (int q = 0; q < cn; ++q) out.trEnt.push_back(pp.trEnt[entPos[(size_t)i]++]);
+                run += cn;
+            }
+            cntPos[(size_t)i] += (size_t)n;
+        }
+        if (run > 0x7FFFFFFFLL) return "too many transition entries in one epoch";
+        out.trOff[(size_t)(tb + nNew)] = (int)run;
+        tb += nNew + 1;
+        te += run;
+    }
+    return "";
+}
+
+}  // namespace rc

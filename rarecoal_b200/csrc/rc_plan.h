@@ -1,0 +1,68 @@
+// rc_plan.h — host-side planner: enumerations, JointStateSpace mirror, and the compiler that turns
+// (patterns, ordered Join/Split structure) into per-epoch live-state lists, neighbour tables and
+// Join/Split transition tables for the kernels ("uploaded once per model structure").
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "rc_types.h"
+
+namespace rc {
+
+// ---- enumeration / binomials (Utils.hs:100-127,208-215) -----------------------------------------
+std::vector<std::vector<int>> all_configs(int maxAf, const std::vector<int>& nVec);
+double choose(int n, int k);
+
+// ---- JointStateSpace (StateSpace.hs:20-28,73-124,145-160) ----------------------------------------
+struct StateSpace {
+    int P = 0, maxAf = 0, nrStates = 0;
+    std::vector<uint8_t> states;                 // [nrStates][P]
+    std::unordered_map<uint64_t, int> toId;      // mixed-radix key -> id
+    std::vector<int> x1up;                       // [nrStates][P]
+    std::vector<int> x1;                         // [P]
+    uint64_t key(const int32_t* x) const;
+    int state_to_id(const int32_t* x) const;
+    std::vector<int> fill_up(const std::vector<int>& ids) const;
+};
+StateSpace* make_state_space(int P, int maxAf);
+bool key_fits(int P, int maxAf);
+
+// ---- structural signature of a model --------------------------------------------------------------
+struct StructEv {
+    int type;     // RC_EV_JOIN_D / RC_EV_SPLIT_D
+    int k, l;
+    int mclass;   // split fraction class: 0 -> m == 0, 1 -> m == 1, 2 -> 0 < m < 1 (Join: 2)
+};
+// Update steps executed before structural event g (after event g-1), capped at maxAf, with the
+// frozen mask of each — needed only to track which b(x) are still exactly zero when a Split applies
+// its `b > 0` filter (Core.hs:220).
+struct GapInfo {
+    std::vector<unsigned> masks;
+};
+
+struct PlanHost {
+    int P = 0, maxAf = 0, nPat = 0, nEpochs = 0, nnzw = 1, nBins = 0, cap = RC_BLOCK;
+    std::vector<int> binPatOff, binPats;
+    std::vector<int> slotOff;              // [nEpochs][nPat+1]
+    std::vector<long long> epochBase;      // [nEpochs]
+    std::vector<uint32_t> words, meta;
+    std::vector<long long> trBase, trEntBase;
+    std::vector<int> trOff;
+    std::vector<uint32_t> trEnt;
+    std::vector<uint8_t> shortcutOK;       // [nPat]
+    std::vector<long long> epochSlots;     // [nEpochs] total live states per epoch
+    std::vector<long long> epochSlotsShort;// [nEpochs] same, restricted to patterns that take the shortcut
+    int maxLive = 0;
+    long long totalSlots = 0;
+};
+
+// Builds the plan for `patterns` ([nPat][P]) with initial ancestral counts n_k - m_k.  Returns "" on
+// success, else an error message (RC_ERR_UNSUPPORTED).
+std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
+                       const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
+                       int smemBudgetBytes, PlanHost& out);
+
+}  // namespace rc

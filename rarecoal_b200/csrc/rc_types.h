@@ -1,0 +1,97 @@
+// rc_types.h — POD layouts shared by the host planner and the sm_100a kernels.
+#pragma once
+#include <stdint.h>
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+#endif
+
+#define RC_MAX_P 32          // branches (k is stored in 8 bits; tables are P*(maxAf+1) doubles per step)
+#define RC_MAX_AF 62         // maxAf (x stored in 8 bits; weight index (maxAf+1)^2 must fit 16 bits minus sentinel)
+#define RC_BLOCK 256         // threads per propagation block
+// event type codes (same values as RC_EV_JOIN / RC_EV_SPLIT in include/rarecoal_b200.h)
+#define RC_EV_JOIN_D 0
+#define RC_EV_SPLIT_D 1
+#define RC_NPB 64            // patterns per bin (block) at most
+
+// Packed per-slot dimension entry: one per non-zero component x_k of a live state x.
+//   bits  0..7   k        branch index
+//   bits  8..15  x_k      (>= 1)
+//   bits 16..31  up       pattern-relative slot of x + e_k, RC_NO_UP if that state is not live
+#define RC_NO_UP 0xFFFFu
+#define RC_W_ONE 0xFFFFu     // transition weight index meaning "1.0" (Join)
+
+// Per-slot meta word:  bits 0..7 nnz, bit 8 isUnit (x == e_k), bits 16..23 |x| = sum x
+#define RC_META_UNIT 0x100u
+
+// One transition entry (epoch e -> e+1): new_b[slot] += old_b[src] * W[widx]
+//   bits 0..15 src (pattern-relative slot in epoch e), bits 16..31 widx (x_l*(maxAf+1)+s, or RC_W_ONE)
+
+// Device view of a compiled plan (one per problem x event-structure signature).
+struct RcPlanDev {
+    int P, maxAf, A1;            // A1 = maxAf + 1
+    int nPat;                    // patterns in this shard
+    int nEpochs;                 // structural epochs = fired Join/Split events + 1
+    int nnzw;                    // words per slot
+    int nBins;
+    int cap;                     // slots per block
+    const int* binPatOff;        // [nBins+1]
+    const int* binPats;          // shard-local pattern ids, bin after bin
+    const int* slotOff;          // [nEpochs][nPat+1]  slot offsets inside the epoch's arrays
+    const long long* epochBase;  // [nEpochs]  base of epoch e inside words/meta (in slots)
+    const uint32_t* words;       // [totalSlots][nnzw]
+    const uint32_t* meta;        // [totalSlots]
+    const long long* trBase;     // [nEpochs]   base of transition e (into epoch e+1 slots) in trOff space
+    const int* trOff;            // per new slot: [.. +1] offsets into trEnt, relative to trEntBase[e]
+    const long long* trEntBase;  // [nEpochs]
+    const uint32_t* trEnt;
+    const uint8_t* shortcutOK;   // [nPat] structural+positivity shortcut test (Core.hs:80-89) at the shortcut step
+    const int32_t* aInit;        // [nPat][P]  n_k - m_k
+    const uint8_t* aEvtPos;      // unused in v1
+    const double* combFac;       // [nPat]  prod choose(n_k, m_k)   (Core.hs:49)
+    const uint8_t* support;      // [nPat][P] 1 where m_k > 0        (Core.hs:50-52)
+    const int32_t* patGlobal;    // [nPat] index in the caller's pattern order
+};
+
+// Structural event as executed by the kernel.
+struct RcSEvDev {
+    int step;      // grid step at which it fires (before that step's update, Core.hs:120-135)
+    int type;      // RC_EV_JOIN / RC_EV_SPLIT
+    int k, l;
+    double m;      // split fraction
+    int wOff;      // offset (in doubles) of this event's weight table W[x_l][s] in the model pool
+    int pad;
+};
+
+// Per-model header.
+struct RcModelDev {
+    int nSteps;        // grid steps to run at most (T)
+    int sShort;        // step at which the shortcut test applies, -1 = never
+    int nSEv;
+    int sevOff;        // first structural event of this model in the pooled RcSEvDev array
+    int rowsAvail;     // table rows computed for this model
+    int pad;
+    long long tabOff;  // offset (doubles) of row 0 in the table pool
+    long long wPool;   // offset (doubles) of split weight tables in the weight pool
+    double theta;
+    double disc[RC_MAX_P];
+};
+
+// Piecewise-constant (popSize, freeze) segments used by the table kernel.
+struct RcSegDev {
+    int sBegin;
+    unsigned frozenMask;
+    double N[RC_MAX_P];
+};
+
+// Table row layout (doubles), one row per (model, grid step):
+//   [0, P*A1)            E2[k][j] = 1 - exp(-(j(j+1)/2) * (1/N_k) * dt)      (Core.hs:279), 0 if frozen
+//   [P*A1, 2*P*A1)       CN[k][j] = j(j-1)/2 * (1/N_k)                        (Core.hs:270), 0 if frozen
+//   [2*P*A1, +P)         EA[k]    = exp(-0.5*dt/N_k)                          (Core.hs:240)
+//   [.. +P)              invN[k]  = 1/N_k (0 if frozen, so r_k = a_k*invN_k drops out of t1)
+//   [.. +P)              N[k]
+//   [.. +1]              dt
+//   [.. +1]              frozen mask (as double)
+static inline __host__ __device__ int rc_row_len(int P, int A1) { return 2 * P * A1 + 3 * P + 2; }

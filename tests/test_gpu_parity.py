@@ -1,0 +1,237 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's
+known answers.  Tolerances are BASELINE.json's: per-pattern probabilities 1e-10 relative, total
+log-likelihood 1e-9 relative."""
+import numpy as np
+import pytest
+
+import rarecoal_b200 as R
+from rarecoal_b200 import workloads as Wk
+from rarecoal_b200 import _lib as L
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PROB_RTOL = 1e-10
+LOGL_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = R.Engine(0)
+    yield e
+    e.close()
+
+
+def _spec(P, times, events, theta=0.0005, disc=None, no_shortcut=False):
+    return R.ModelSpec(P, times, theta, disc or [1.0] * P, 0.0, no_shortcut,
+                       [R.ModelEvent.from_tuple(e) for e in events])
+
+
+def _counts(f, std):
+    d = {tuple(p): c for p, c in zip(f["patterns"], f["counts"])}
+    return np.array([d.get(tuple(int(v) for v in p), 0) for p in std], dtype=np.int64)
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / np.abs(b))
+
+
+def test_getprob_known_answers(eng, fivepop, default_times):
+    # Core/Test.hs:167-184
+    spec = _spec(5, default_times, fivepop["events"], fivepop["theta"])
+    for e in fivepop["kat"]:
+        maxaf = max(4, sum(e["config"]))
+        p = eng.getProb(spec, R.JointStateSpace(5, maxaf), fivepop["nVec"], e["config"])
+        assert abs(p - e["prob"]) / e["prob"] < PROB_RTOL, (e, p)
+
+
+@pytest.mark.parametrize("max_af", [4, 10])
+def test_fourpop_vs_oracle_and_golden(eng, fourpop, default_times, max_af):
+    # config 1 (maxAf=4, whole-path golden) and config 2's real-data twin (maxAf=10): Join+Split+SetPopSize
+    std = R.computeStandardOrder(fourpop["nVec"], max_af)
+    cnt = _counts(fourpop, std)
+    eng.set_problem(fourpop["nVec"], max_af, std, cnt, fourpop["totalSites"])
+    spec = _spec(4, default_times, fourpop["events"], fourpop["theta"])
+    logl, probs, status = eng.eval_models([spec], want_probs=True)
+    assert status[0] == 0
+    ll_o, probs_o, w_o = O.logl(4, max_af, default_times, fourpop["theta"], [1.0] * 4, False, fourpop["events"],
+                                fourpop["nVec"], std, cnt, fourpop["totalSites"])
+    assert _relerr(probs[0], probs_o) < PROB_RTOL
+    assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert eng.stats()["state_steps"] == w_o
+    if max_af == 4:
+        assert abs(-logl[0] - fourpop["score_m4_maxl"]) / fourpop["score_m4_maxl"] < LOGL_RTOL
+    # reference-named entry points agree with the batch call
+    assert eng.computeLogLikelihood(spec) == logl[0]
+    spec_list = eng.computeFrequencySpectrum(spec)
+    assert R.computeLogLikelihoodFromSpec(fourpop["totalSites"], 1.0, spec_list) == pytest.approx(logl[0], rel=1e-12)
+
+
+def test_c3_eight_pop_tree_sample_vs_oracle(eng, default_times):
+    # config 3 at full size on the GPU; oracle on a seeded sample of patterns (getProb is per pattern)
+    nvec, pats, cnt = Wk.c3_problem()
+    eng.set_problem(nvec, 10, pats, cnt, Wk.TOTAL_SITES)
+    ev = Wk.c3_events()
+    spec = _spec(8, default_times, ev)
+    logl, probs, status = eng.eval_models([spec], want_probs=True)
+    assert status[0] == 0 and np.isfinite(logl[0])
+    st = eng.stats()
+    assert st["state_steps"] == 298329136
+    rng = np.random.default_rng(3)
+    idx = np.sort(rng.choice(len(pats), 1500, replace=False))
+    _, probs_o, _ = O.logl(8, 10, default_times, 0.0005, [1.0] * 8, False, ev, nvec, pats[idx],
+                           np.zeros(len(idx), dtype=np.int64), 0)
+    assert _relerr(probs[0][idx], probs_o) < PROB_RTOL
+    # size-independent properties at full size
+    p = probs[0]
+    assert np.all(p > 0) and p.sum() < 1.0
+    # permutation symmetry of the balanced tree is broken by sizes; instead: batching is consistent
+    logl2, probs2, _ = eng.eval_models([spec, spec, spec], want_probs=True)
+    assert np.array_equal(probs2[0], p) and np.array_equal(probs2[2], p) and np.all(logl2 == logl[0])
+
+
+def test_c4_batched_parameter_vectors(eng, default_times):
+    # config 4: batch of perturbed parameter vectors in one launch == one-at-a-time, and vs oracle on a sample
+    nvec, pats, cnt = Wk.c3_problem(max_af=6)
+    eng.set_problem(nvec, 6, pats, cnt, Wk.TOTAL_SITES)
+    batch = Wk.c4_batch(23)
+    specs = [_spec(8, default_times, ev) for ev in batch]
+    logl, probs, status = eng.eval_models(specs, want_probs=True)
+    assert not status.any()
+    for b in (0, 7, 22):
+        l1, p1, _ = eng.eval_models([specs[b]], want_probs=True)
+        assert np.array_equal(p1[0], probs[b]) and l1[0] == logl[b]
+    for b in (1, 12, 20):
+        ll_o, probs_o, _ = O.logl(8, 6, default_times, 0.0005, [1.0] * 8, False, batch[b], nvec, pats, cnt,
+                                  Wk.TOTAL_SITES)
+        assert _relerr(probs[b], probs_o) < PROB_RTOL
+        assert abs(logl[b] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert len(set(logl.tolist())) > 10     # the perturbations do change the likelihood
+
+
+def test_c5_admixture_ten_pop_vs_oracle(eng, default_times):
+    # config 5 structure: 10 pops, maxAf 4, Join + Split pulses + size changes
+    nvec = [100] * 10
+    pats = R.computeStandardOrder(nvec, 4)
+    cnt = Wk.synthetic_counts(pats)
+    eng.set_problem(nvec, 4, pats, cnt, Wk.TOTAL_SITES)
+    ev = Wk.c5_events()
+    logl, probs, status = eng.eval_models([_spec(10, default_times, ev)], want_probs=True)
+    assert status[0] == 0
+    ll_o, probs_o, w_o = O.logl(10, 4, default_times, 0.0005, [1.0] * 10, False, ev, nvec, pats, cnt, Wk.TOTAL_SITES)
+    assert _relerr(probs[0], probs_o) < PROB_RTOL
+    assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert eng.stats()["state_steps"] == w_o
+
+
+def _small_problem(eng, P=3, max_af=5, n=12):
+    nvec = [n] * P
+    pats = R.computeStandardOrder(nvec, max_af)
+    cnt = Wk.synthetic_counts(pats, total_sites=10 ** 7, seed=1)
+    eng.set_problem(nvec, max_af, pats, cnt, 10 ** 7)
+    return nvec, pats, cnt
+
+
+@pytest.mark.parametrize("name,events,no_shortcut,disc", [
+    ("no_events", [], False, None),
+    ("no_events_noshortcut", [], True, None),
+    ("tree_noshortcut", [(0.01, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)], True, None),
+    ("freeze", [(0.0, 3, 2, 0, 1.0), (0.004, 3, 2, 0, 0.0), (0.01, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)], False, None),
+    ("freeze_forever", [(0.0, 3, 2, 0, 1.0), (0.01, 0, 0, 1, 0)], False, None),
+    ("split_m0_m1", [(0.002, 1, 0, 1, 0.0), (0.003, 1, 2, 1, 1.0), (0.01, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)], False, None),
+    ("early_split_before_first_step", [(0.0, 1, 0, 1, 0.3), (0.00001, 1, 2, 0, 0.5), (0.02, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)],
+     False, None),
+    ("split_after_two_steps", [(0.00006, 1, 0, 1, 0.3), (0.02, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)], False, None),
+    ("same_time_events", [(0.01, 0, 0, 1, 0), (0.01, 2, 0, 0, 3.0), (0.01, 1, 0, 2, 0.25), (0.01, 2, 0, 0, 0.5),
+                          (0.05, 0, 0, 2, 0)], False, None),
+    ("event_beyond_grid", [(0.01, 0, 0, 1, 0), (25.0, 0, 0, 2, 0)], False, None),
+    ("popsize_tiny_large", [(0.0, 2, 0, 0, 0.01), (0.0, 2, 1, 0, 50.0), (0.02, 0, 0, 1, 0), (0.04, 0, 0, 2, 0)], False, None),
+    ("discovery_rates", [(0.01, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)], False, [0.5, 1.0, 0.25]),
+    ("unjoined_branch", [(0.01, 0, 0, 1, 0)], False, None),
+])
+def test_event_semantics_vs_oracle(eng, default_times, name, events, no_shortcut, disc):
+    # strict t < nextTime firing, stable ties, freeze, split filter, shortcut on/off
+    nvec, pats, cnt = _small_problem(eng)
+    times = default_times if not no_shortcut and name != "unjoined_branch" and name != "freeze_forever" \
+        and name != "event_beyond_grid" else default_times[:400]
+    disc = disc or [1.0] * 3
+    logl, probs, status = eng.eval_models([_spec(3, times, events, 0.001, disc, no_shortcut)], want_probs=True)
+    assert status[0] == 0
+    ll_o, probs_o, w_o = O.logl(3, 5, times, 0.001, disc, no_shortcut, events, nvec, pats, cnt, 10 ** 7)
+    assert _relerr(probs[0], probs_o) < PROB_RTOL, name
+    assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert eng.stats()["state_steps"] == w_o
+
+
+def test_growth_as_per_step_popsize(eng, default_times):
+    # SetGrowthRate has no reference semantics; as sugar it is one SetPopSize per grid
+    # step, which the oracle pins.
+    nvec, pats, cnt = _small_problem(eng)
+    times = default_times[:600]
+    ev = [(0.0, 2, 0, 0, 1.0)]
+    ev += [(float(t), 2, 0, 0, float(np.exp(-40.0 * t))) for t in times[:300]]
+    ev += [(0.01, 0, 0, 1, 0), (0.02, 0, 0, 2, 0)]
+    logl, probs, status = eng.eval_models([_spec(3, times, ev, 0.001)], want_probs=True)
+    ll_o, probs_o, _ = O.logl(3, 5, times, 0.001, [1.0] * 3, False, ev, nvec, pats, cnt, 10 ** 7)
+    assert status[0] == 0
+    assert _relerr(probs[0], probs_o) < PROB_RTOL
+    assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+
+
+def test_model_errors_and_statuses(eng, default_times):
+    nvec, pats, cnt = _small_problem(eng)
+    good = _spec(3, default_times, [(0.01, 0, 0, 1, 0), (0.03, 0, 0, 2, 0)])
+    bad_reuse = _spec(3, default_times, [(0.01, 0, 0, 1, 0), (0.02, 2, 1, 0, 2.0)])     # branch used after join
+    bad_neg = _spec(3, default_times, [(-0.01, 0, 0, 1, 0)])
+    bad_disc = _spec(3, default_times, [], disc=[1.0, 0.0, 1.0])
+    logl, probs, status = eng.eval_models([good, bad_reuse, bad_neg, good, bad_disc], want_probs=True)
+    assert status.tolist() == [0, 1, 1, 0, 1]
+    assert np.isfinite(logl[0]) and logl[0] == logl[3]
+    assert np.isnan(logl[1]) and np.isnan(logl[2]) and np.isnan(logl[4])
+    with pytest.raises(R.RarecoalModelException):
+        eng.computeLogLikelihood(bad_reuse)
+    with pytest.raises(R.RarecoalCompException):
+        eng.getProb(good, R.JointStateSpace(3, 5), [12, 12], [1, 0])       # Core.hs:42
+    # pattern with m_k > n_k: combinatorial factor 0 -> RarecoalCompException (Core.hs:53-56)
+    eng.set_problem([2, 2, 2], 5, [[3, 0, 0], [1, 0, 0]], [1, 1], 100)
+    _, _, st = eng.eval_models([good])
+    assert st[0] == L.RC_ERR_COMP
+    with pytest.raises(ValueError):
+        eng.set_problem([2, 2, 2], 5, [[0, 0, 0]], [1], 100)           # zero state is not in the state space
+
+
+def test_sharded_partials_sum_to_whole(default_times, fourpop):
+    # multi-GPU path, ranks emulated as contexts on one device: partial sums add up to the single-GPU result
+    import torch
+    std = R.computeStandardOrder(fourpop["nVec"], 10)
+    cnt = _counts(fourpop, std)
+    spec = _spec(4, default_times, fourpop["events"], fourpop["theta"])
+    whole = R.Engine(0)
+    whole.set_problem(fourpop["nVec"], 10, std, cnt, fourpop["totalSites"])
+    logl, probs, _ = whole.eval_models([spec, spec], want_probs=True)
+    world = 3
+    acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+    accp = torch.zeros(2 * len(std), dtype=torch.float64, device="cuda")
+    engines = []
+    for r in range(world):
+        e = R.Engine(0)
+        e.set_problem(fourpop["nVec"], 10, std, cnt, fourpop["totalSites"])
+        e.set_shard(r, world)
+        e.set_times(default_times)
+        ev, off, theta, disc = e._pack([spec, spec])
+        part = torch.zeros(4, dtype=torch.float64, device="cuda")
+        pr = torch.zeros(2 * len(std), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        st = e.eval_partial(ev, off, theta, disc, False, part.data_ptr(), pr.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert not st.any()
+        acc += part
+        accp += pr
+        engines.append(e)
+    torch.cuda.synchronize()
+    out = engines[0].finalize(2, acc.data_ptr())
+    assert abs(out[0] - logl[0]) / abs(logl[0]) < 1e-13
+    assert np.array_equal(accp.cpu().numpy().reshape(2, -1), probs)
+    for e in engines:
+        e.close()
+    whole.close()
