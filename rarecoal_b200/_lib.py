@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "librarecoal_b200.so")
+SO = os.environ.get("RARECOAL_B200_LIB", os.path.join(HERE, "librarecoal_b200.so"))   # override: kernel A/B experiments
 
 RC_OK, RC_ERR_MODEL, RC_ERR_COMP, RC_ERR_ARG, RC_ERR_CUDA, RC_ERR_UNSUPPORTED = 0, 1, 2, -1, -2, -3
 RC_EV_JOIN, RC_EV_SPLIT, RC_EV_POPSIZE, RC_EV_FREEZE = 0, 1, 2, 3

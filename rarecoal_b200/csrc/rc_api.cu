@@ -335,8 +335,11 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     std::memset(&d, 0, sizeof d);
     const rc::PlanHost& h = pe->h;
     d.P = h.P; d.maxAf = h.maxAf; d.A1 = h.maxAf + 1; d.nPat = h.nPat; d.nEpochs = h.nEpochs; d.nnzw = h.nnzw;
-    d.nBins = h.nBins; d.cap = h.cap;
+    d.nBins = h.nBins; d.cap = h.cap; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
     int rc;
+    if ((rc = upload(ctx, pe, h.fBinPatOff, &d.fBinPatOff))) return rc;
+    if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
+    if ((rc = upload(ctx, pe, h.maxX, &d.maxX))) return rc;
     if ((rc = upload(ctx, pe, h.binPatOff, &d.binPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.binPats, &d.binPats))) return rc;
     if ((rc = upload(ctx, pe, h.slotOff, &d.slotOff))) return rc;
@@ -534,8 +537,14 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         int end = pos + 1;
         while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
         if (pe && ctx->nPat > 0) {
-            CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
-            ++launches;
+            if (pe->d.nFastBins > 0) {
+                CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+                ++launches;
+            }
+            if (pe->d.nBins > 0) {
+                CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+                ++launches;
+            }
         }
         pos = end;
     }
@@ -918,7 +927,7 @@ int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int
     if (slots0) *slots0 = h.epochSlots[0];
     if (maxLive) *maxLive = h.maxLive;
     if (nEpochs) *nEpochs = h.nEpochs;
-    if (nBins) *nBins = h.nBins;
+    if (nBins) *nBins = h.nBins + h.nFastBins;
     return RC_OK;
 }
 

@@ -8,6 +8,7 @@
 //   rc_fp64_peak_kernel  DFMA-rate microbenchmark (roofline denominator)
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "rc_kernels.h"
@@ -33,23 +34,21 @@ __global__ void rc_tables_kernel(const RcModelDev* __restrict__ models, const Rc
     double* row = tab + M.tabOff + (long long)s * rowLen;
     const int nE = P * A1;
     for (int i = threadIdx.x; i < rowLen; i += blockDim.x) {
-        double v;
-        if (i < 2 * nE) {
-            int ii = i < nE ? i : i - nE;
-            int k = ii / A1, j = ii - k * A1;
-            bool frozen = (sg.frozenMask >> k) & 1u;
-            double xx = (double)j, pp = sg.N[k];
-            if (frozen) v = 0.0;
-            else if (i < nE) v = 1.0 - exp(-(xx * (xx + 1.0) / 2.0 * (1.0 / pp) * dt));
+        double v = 0.0;
+        if (i == 0) v = dt;
+        else if (i == 1) v = (double)sg.frozenMask;
+        else if (i < RC_ROW_PAIRS + 2 * nE) {
+            const int q = i - RC_ROW_PAIRS;
+            const int pi = q >> 1, k = pi / A1, j = pi - k * A1;
+            const bool frozen = (sg.frozenMask >> k) & 1u;
+            const double xx = (double)j, pp = sg.N[k];
+            if (j == 0) {
+                if (q & 1) v = frozen ? 0.0 : 1.0 / pp;
+                else v = (frozen || !(dt > 0.0)) ? 1.0 : exp(-(0.5 * dt / pp));
+            } else if (frozen) v = 0.0;
+            else if (q & 1) v = 1.0 - exp(-(xx * (xx + 1.0) / 2.0 * (1.0 / pp) * dt));
             else v = xx * (xx - 1.0) / 2.0 * (1.0 / pp);
-        } else {
-            int r = i - 2 * nE;
-            if (r < P) v = exp(-(0.5 * dt / sg.N[r]));
-            else if (r < 2 * P) v = ((sg.frozenMask >> (r - P)) & 1u) ? 0.0 : 1.0 / sg.N[r - P];
-            else if (r < 3 * P) v = sg.N[r - 2 * P];
-            else if (r == 3 * P) v = dt;
-            else v = (double)sg.frozenMask;
-        }
+        } else if (i < RC_ROW_PAIRS + 2 * nE + P) v = sg.N[i - RC_ROW_PAIRS - 2 * nE];
         row[i] = v;
     }
 }
@@ -120,14 +119,11 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
     const int bin = blockIdx.x, b = blockIdx.y;
     const RcModelDev& M = models[b];
     if (M.nSteps < 0) return;   // model failed validation on the host
-    const int P = pl.P, A1 = pl.A1, nnzw = pl.nnzw, nPat = pl.nPat;
+    const int P = pl.P, A1 = pl.A1, nnzw = pl.nnzw, nPat = pl.nPat, cap = pl.cap;
     const int rowLen = rc_row_len(P, A1);
     RcSmem S = rc_carve(smemRaw, pl.cap, nnzw, P, rowLen);
-    const double* E2 = S.tab;
-    const double* CN = S.tab + P * A1;
-    const double* EA = S.tab + 2 * P * A1;
-    const double* invN = EA + P;
-    const int dtIdx = 2 * P * A1 + 3 * P;
+    const double* PR = S.tab + RC_ROW_PAIRS;   // pairs: (k,0) = {EA, invN}, (k,j) = {CN, E2}
+    const int dtIdx = 0;
 
     const int pat0 = pl.binPatOff[bin];
     const int np = pl.binPatOff[bin + 1] - pat0;
@@ -161,7 +157,7 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
         int local = slot - S.patOff[p];
         int pid = S.patId[p];
         long long g = pl.epochBase[0] + pl.slotOff[pid] + local;
-        for (int d = 0; d < nnzw; ++d) S.words[slot * nnzw + d] = pl.words[g * nnzw + d];
+        for (int d = 0; d < nnzw; ++d) S.words[d * cap + slot] = pl.words[g * nnzw + d];
         S.meta[slot] = pl.meta[g];
         S.owner[slot] = (unsigned short)p;
         S.dacc[slot] = 0.0;
@@ -188,7 +184,7 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
                         nrA = nrA + aP[k];
                         if (popIndex < 0 && aP[k] > 0.0) popIndex = k;
                     }
-                    const double* rowN = tab + M.tabOff + (long long)s * rowLen + 2 * P * A1 + 2 * P;
+                    const double* rowN = tab + M.tabOff + (long long)s * rowLen + rc_row_n(P, A1);
                     double popSize = rowN[popIndex < 0 ? 0 : popIndex];
                     int base = S.patOff[tid], n = S.patOff[tid + 1] - base;
                     double acc = S.dpat[tid], add = 0.0;
@@ -255,7 +251,7 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
                 }
                 bn[slot] = acc;
                 long long g = eb + gl;
-                for (int d = 0; d < nnzw; ++d) S.words[slot * nnzw + d] = pl.words[g * nnzw + d];
+                for (int d = 0; d < nnzw; ++d) S.words[d * cap + slot] = pl.words[g * nnzw + d];
                 S.meta[slot] = pl.meta[g];
                 S.owner[slot] = (unsigned short)p;
                 S.dacc[slot] = 0.0;
@@ -275,16 +271,16 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
         const double dt = S.tab[dtIdx];
         if (dt > 0.0) {
             // ---- updateA (Core.hs:229-240) ----
-            const unsigned fmask = (unsigned)S.tab[dtIdx + 1];
             for (int i = tid; i < np * P; i += nthr) {
                 int p = i / P, k = i - p * P;
                 if (S.patDone[p]) continue;
                 double a = S.a[i];
-                if (!((fmask >> k) & 1u) && a >= 1.0) {
-                    a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * EA[k]);
+                const double ea = PR[2 * k * A1], invN = PR[2 * k * A1 + 1];
+                if (ea != 1.0 && a >= 1.0) {         // EA == 1 encodes a frozen branch
+                    a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * ea);
                     S.a[i] = a;
                 }
-                S.r[i] = a * invN[k];
+                S.r[i] = a * invN;
             }
             __syncthreads();
             // ---- updateB + updateD (Core.hs:242-288) ----
@@ -297,11 +293,11 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
                 const double* rP = S.r + p * P;
                 double t1 = 0.0, t2 = 0.0;
                 for (int d = 0; d < nnz; ++d) {
-                    const uint32_t w = S.words[slot * nnzw + d];
+                    const uint32_t w = S.words[d * cap + slot];
                     const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
                     const uint32_t up = w >> 16;
-                    t1 = t1 + (CN[k * A1 + x] + (double)x * rP[k]);
-                    if (up != RC_NO_UP) t2 = t2 + bc[base + (int)up] * E2[k * A1 + x];
+                    t1 = t1 + (PR[2 * (k * A1 + x)] + (double)x * rP[k]);
+                    if (up != RC_NO_UP) t2 = t2 + bc[base + (int)up] * PR[2 * (k * A1 + x) + 1];
                 }
                 const double bnew = bc[slot] * exp(-(t1 * dt)) + t2;
                 bn[slot] = bnew;
@@ -324,6 +320,463 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
         double discFac = 1.0;
         for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? M.disc[k] : 1.0);
         pOut[(size_t)b * nPat + pid] = d * M.theta * pl.combFac[pid] * discFac;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fast tier: one live state per thread, structure in registers, ONE barrier per grid step.
+//
+//   * every thread owns one slot (live state x of one pattern): b(x), its decay factor and, per non-zero
+//     component k, two ABSOLUTE shared-memory addresses resolved once per structural epoch from the plan: the
+//     16-byte pair {rate row, 1-exp table entry} and the neighbour b(x+e_k) (an always-zero slot if that state
+//     is not live);
+//   * thread (p,k) additionally owns the ancestral lineage count a_k of pattern p (updateA, Core.hs:229-240),
+//     carried as u = 1/a - 1 so that propagateA is one multiply and one division, and publishes ONE GRID STEP
+//     AHEAD of the states the pairs
+//         RE[p][k][j] = { j(j-1)/2 (1/N_k) + j a_k (1/N_k)   (k-th term of t1, Core.hs:270),
+//                         1 - exp(-j(j+1)/2 dt/N_k)          (factor of b(x+e_k) in t2, Core.hs:279) }
+//     so a state issues one LDS.128, one add, one LDS.64 and one FMA per non-zero component;
+//   * exp(-t1 dt) of consecutive steps differs by exp(-delta) with |delta| ~ 1e-4: the factor is carried
+//     multiplicatively with a 4-term series (truncation < 1e-17) and re-anchored with a true exp() after
+//     every event, every 128 steps and whenever |delta| >= 2^-10;
+//   * the time loop is unrolled by two so that all buffer parities are immediates; table rows are
+//     prefetched two steps ahead into a two-slot ring.
+// BLOCK threads per block (64, 128 or 256): a block holds whole patterns, so BLOCK bounds the live set of a
+// pattern in this tier; small blocks keep the per-step barrier between few warps.
+template <int BLOCK>
+struct RcFastSmem {                        // every member at a compile-time offset: accesses are base + immediate
+    static constexpr int BSTRIDE = BLOCK + 8;      // doubles per b buffer; entry BLOCK is the always-zero neighbour
+    static constexpr int RCAP = 2 * BLOCK;         // pair rows per parity
+    double bbuf[2 * BSTRIDE];
+    double RE[2 * 2 * RCAP];               // [parity][row]{rate, e2}; row RCAP-1 = {0,0} padding, RCAP-2 = {dt,0}
+    double tabS[2 * RC_ROWCAP];            // two-slot ring of table rows
+    double dslot[BLOCK];
+    double aS[BLOCK];
+    double dpat[RC_NPB];
+    uint32_t metaS[BLOCK];
+    int patOff[RC_NPB + 1];
+    int patOff2[RC_NPB + 1];
+    int patR[RC_NPB + 1];
+    int patId[RC_NPB];
+    int patDone[RC_NPB];
+};
+
+size_t rc_fast_smem_bytes(int block) {
+    size_t n = block == 64 ? sizeof(RcFastSmem<64>) : block == 128 ? sizeof(RcFastSmem<128>) : sizeof(RcFastSmem<256>);
+    return (n + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ double rc_lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void rc_lds128(unsigned addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void rc_sts64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void rc_sts128(unsigned addr, double a, double b) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+
+// Per-thread state of the fast kernel (all in registers; every function below is force-inlined).
+template <int NNZ>
+struct RcFastRegs {
+    unsigned aRE[NNZ], aB[NNZ];   // absolute shared addresses at parity 0
+    int nw;                       // components to visit (warp maximum)
+    bool unit, slotOn, anchor;
+    double bv, D, zprev, dacc;
+    unsigned myB;                 // absolute address of this thread's b slot at parity 0
+    // A-task (thread tid <-> pattern tid / P of the bin, branch tid % P)
+    bool taskOn, aProp;
+    double av, uv;                // a (when !aProp) or u = 1/a - 1 (when aProp, i.e. a >= 1)
+    unsigned tTab;                // absolute address of pair (tk, 0) = {EA, invN} in ring slot 0
+    unsigned tRE;                 // absolute address of this task's pairs at parity 0
+    int taskM;                    // number of pairs (largest x_k over the pattern's live states)
+};
+
+template <int BLOCK>
+struct RcFastK {
+    typedef RcFastSmem<BLOCK> SM;
+    static constexpr unsigned B_PAR = SM::BSTRIDE * 8u;        // byte distance between the two b buffers
+    static constexpr unsigned RE_PAR = SM::RCAP * 16u;         // ... the two pair buffers
+    static constexpr unsigned T_PAR = RC_ROWCAP * 8u;          // ... the two ring slots
+    static constexpr unsigned RE_DT = (SM::RCAP - 2) * 16u;    // pair holding {dt, 0}
+    static constexpr unsigned RE_ZERO = (SM::RCAP - 1) * 16u;  // pair holding {0, 0}
+    static constexpr unsigned O_B = (unsigned)offsetof(SM, bbuf);
+    static constexpr unsigned O_RE = (unsigned)offsetof(SM, RE);
+    static constexpr unsigned O_T = (unsigned)offsetof(SM, tabS);
+    static_assert(O_RE % 16 == 0 && O_T % 16 == 0, "16-byte alignment of pair tables");
+};
+
+// updateA for one grid step from ring slot TPH, pairs written at parity RPH.
+template <int NNZ, int BLOCK, int TPH, int RPH>
+__device__ __forceinline__ void rc_fast_taskA(RcFastRegs<NNZ>& R) {
+    typedef RcFastK<BLOCK> K;
+    if (R.taskOn) {
+        double ea, invN;
+        rc_lds128(R.tTab + TPH * K::T_PAR, ea, invN);
+        double a = R.av;
+        if (R.aProp) {
+            R.uv = R.uv * ea;                               // EA == 1 when frozen or dt <= 0
+            a = 1.0 / (1.0 + R.uv);                         // propagateA, Core.hs:239-240
+        }
+        const double r = a * invN;
+        unsigned src = R.tTab + TPH * K::T_PAR + 16u, dst = R.tRE + RPH * K::RE_PAR;
+        double jj = 1.0;
+        for (int j = 0; j < R.taskM; ++j, jj += 1.0, src += 16u, dst += 16u) {
+            double cn, e2;
+            rc_lds128(src, cn, e2);
+            rc_sts128(dst, fma(jj, r, cn), e2);
+        }
+    }
+}
+
+template <int NNZ, int BLOCK, int N, int PH>
+__device__ __forceinline__ void rc_fast_dims(const RcFastRegs<NNZ>& R, double& t1, double& t2) {
+    typedef RcFastK<BLOCK> K;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        double rate, e2;
+        rc_lds128(R.aRE[d] + PH * K::RE_PAR, rate, e2);
+        t1 += rate;
+        t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
+    }
+}
+
+// One grid step with compile-time buffer parity PH (b, RE and the table ring all alternate).
+template <int NNZ, int BLOCK, int PH>
+__device__ __forceinline__ void rc_fast_step(RcFastRegs<NNZ>& R, const unsigned sBase, const double* __restrict__ pf,
+                                             const int rowLen, const bool havePre, const bool doA, const int s) {
+    typedef RcFastK<BLOCK> K;
+    constexpr int QH = PH ^ 1;
+    constexpr int NPRE = (RC_ROWCAP + BLOCK - 1) / BLOCK;
+    // table row of step s+2: issued now, stored at the end (its ring slot held row s, which is dead)
+    double pre[NPRE];
+#pragma unroll
+    for (int i = 0; i < NPRE; ++i) {
+        pre[i] = 0.0;
+        if (havePre && (int)threadIdx.x + i * BLOCK < rowLen) pre[i] = __ldg(pf + i * BLOCK);
+    }
+    const double dt = rc_lds64(sBase + K::O_RE + PH * K::RE_PAR + K::RE_DT);
+    // ---- updateB + updateD for this thread's state (Core.hs:242-288) ----
+    if (R.slotOn) {
+        if (dt > 0.0) {
+            double t1 = 0.0, t2 = 0.0;
+            switch (R.nw) {
+                case 1: rc_fast_dims<NNZ, BLOCK, 1, PH>(R, t1, t2); break;
+                case 2: rc_fast_dims<NNZ, BLOCK, 2, PH>(R, t1, t2); break;
+                case 3: rc_fast_dims<NNZ, BLOCK, (NNZ >= 3 ? 3 : NNZ), PH>(R, t1, t2); break;
+                case 4: rc_fast_dims<NNZ, BLOCK, (NNZ >= 4 ? 4 : NNZ), PH>(R, t1, t2); break;
+                case 5: rc_fast_dims<NNZ, BLOCK, (NNZ >= 5 ? 5 : NNZ), PH>(R, t1, t2); break;
+                case 6: rc_fast_dims<NNZ, BLOCK, (NNZ >= 6 ? 6 : NNZ), PH>(R, t1, t2); break;
+                case 7: rc_fast_dims<NNZ, BLOCK, (NNZ >= 7 ? 7 : NNZ), PH>(R, t1, t2); break;
+                case 8: rc_fast_dims<NNZ, BLOCK, (NNZ >= 8 ? 8 : NNZ), PH>(R, t1, t2); break;
+                default: break;
+            }
+            const double z = t1 * dt;
+            const double del = z - R.zprev;
+            R.zprev = z;
+            if (!R.anchor && fabs(del) < 0.0009765625 && (s & 127)) {
+                // exp(-del) - 1 = del * (-1 + del/2 - del^2/6 + del^3/24)
+                double q = fma(del, 1.0 / 24.0, -1.0 / 6.0);
+                q = fma(q, del, 0.5);
+                q = fma(q, del, -1.0);
+                R.D = fma(R.D, del * q, R.D);
+            } else {
+                R.D = exp(-z);
+                R.anchor = false;
+            }
+            R.bv = fma(R.bv, R.D, t2);
+            if (R.unit) R.dacc = fma(dt, R.bv, R.dacc);
+        }
+        rc_sts64(R.myB + QH * K::B_PAR, R.bv);
+    }
+    // ---- updateA one step ahead and the pairs of step s+1 (from ring slot QH, to parity QH) ----
+    if (doA) {
+        if (threadIdx.x == 0)
+            rc_sts128(sBase + K::O_RE + QH * K::RE_PAR + K::RE_DT, rc_lds64(sBase + K::O_T + QH * K::T_PAR), 0.0);
+        rc_fast_taskA<NNZ, BLOCK, QH, QH>(R);
+    }
+#pragma unroll
+    for (int i = 0; i < NPRE; ++i)
+        if (havePre && (int)threadIdx.x + i * BLOCK < rowLen)
+            rc_sts64(sBase + K::O_T + PH * K::T_PAR + (threadIdx.x + i * BLOCK) * 8u, pre[i]);
+    __syncthreads();
+}
+
+template <int NNZ, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
+rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const RcSEvDev* __restrict__ sevs,
+                         const double* __restrict__ tab, const double* __restrict__ wpool,
+                         double* __restrict__ pOut) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int tid = threadIdx.x;
+    const int bin = blockIdx.x, b = blockIdx.y;
+    if (models[b].nSteps < 0) return;                    // model failed validation on the host
+    const int P = pl.P, A1 = pl.A1;
+    const int rowLen = rc_row_len(P, A1);
+    typedef RcFastSmem<BLOCK> SM;
+    typedef RcFastK<BLOCK> K;
+    SM& S = *reinterpret_cast<SM*>(smemRaw);
+    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const int pat0 = pl.fBinPatOff[bin];
+    const int np = pl.fBinPatOff[bin + 1] - pat0;
+    const int rowsAvail = models[b].rowsAvail, nSteps = models[b].nSteps, sShort = models[b].sShort;
+    const int nSEv = models[b].nSEv;
+    const double* rows = tab + models[b].tabOff;
+    const RcSEvDev* sev = sevs + models[b].sevOff;
+
+    const int tp = tid / P, tk = tid - tp * P;
+    const bool isTask = tp < np;
+
+    RcFastRegs<NNZ> R;
+    const unsigned zeroRE = sBase + K::O_RE + K::RE_ZERO;
+    const unsigned zeroB = sBase + K::O_B + BLOCK * 8u;
+#pragma unroll
+    for (int d = 0; d < NNZ; ++d) { R.aRE[d] = zeroRE; R.aB[d] = zeroB; }
+    R.nw = 0; R.unit = false; R.slotOn = false; R.anchor = true;
+    R.bv = 0.0; R.D = 1.0; R.zprev = 0.0; R.dacc = 0.0;
+    R.myB = sBase + K::O_B + (unsigned)tid * 8u;
+    R.taskOn = false; R.aProp = false; R.av = 0.0; R.uv = 0.0;
+    R.tTab = sBase + K::O_T + (unsigned)(RC_ROW_PAIRS + 2 * tk * A1) * 8u;
+    R.tRE = zeroRE; R.taskM = 0;
+
+    if (tid < np) {
+        S.patId[tid] = pl.fBinPats[pat0 + tid];
+        S.patDone[tid] = 0;
+        S.dpat[tid] = 0.0;
+    }
+    if (tid < 4) S.RE[(tid >> 1) * 2 * SM::RCAP + 2 * (SM::RCAP - 1) + (tid & 1)] = 0.0;    // {0,0} padding pairs
+    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + BLOCK] = 0.0;                               // zero neighbours
+    __syncthreads();
+    if (isTask) R.av = (double)pl.aInit[(size_t)S.patId[tp] * P + tk];   // makeInitCoalState, Core.hs:60
+
+    int epoch = 0, nextEv = 0;
+    int nextEvStep = nSEv > 0 ? sev[0].step : -1;
+    int s = 0;
+    int cp = 0;               // parity of the buffer that holds the current b when the slow path is entered
+    bool init = true;
+
+    for (;;) {
+        // ================= slow path: shortcut test, structural events, epoch set-up =================
+        // On exit everything is normalised to parity 0: b in bbuf[0], pairs and dt of step s at parity 0,
+        // table rows s and s+1 in ring slots 0 and 1.
+        {
+            const int nnzw = pl.nnzw, nPat = pl.nPat;
+            for (int r = 0; r < 2 && s + r < rowsAvail; ++r)
+                for (int i = tid; i < rowLen; i += BLOCK) S.tabS[r * RC_ROWCAP + i] = rows[(long long)(s + r) * rowLen + i];
+            if (isTask) S.aS[tid] = R.aProp ? 1.0 / (1.0 + R.uv) : R.av;
+            S.dslot[tid] = R.dacc;
+            R.dacc = 0.0;
+            __syncthreads();
+            if (tid < np && !S.patDone[tid] && !init) {       // updateD contributions so far (Core.hs:282-288)
+                const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+                double acc = S.dpat[tid];
+                for (int i = 0; i < cnt; ++i)
+                    if (S.metaS[base + i] & RC_META_UNIT) acc = acc + S.dslot[base + i];
+                S.dpat[tid] = acc;
+            }
+            if (s == sShort && !init) {                       // canUseShortcut / propagateStateShortcut, Core.hs:80-118
+                int ok = 1;
+                if (tid < np && !S.patDone[tid]) {
+                    if (pl.shortcutOK[S.patId[tid]]) {
+                        const double* aP = S.aS + tid * P;
+                        double nrA = 0.0;
+                        int popIndex = -1;
+                        for (int k = 0; k < P; ++k) {
+                            nrA = nrA + aP[k];
+                            if (popIndex < 0 && aP[k] > 0.0) popIndex = k;
+                        }
+                        const double popSize = S.tabS[rc_row_n(P, A1) + (popIndex < 0 ? 0 : popIndex)];
+                        const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+                        const double* bc = S.bbuf + cp * SM::BSTRIDE + base;
+                        double add = 0.0;
+                        for (int i = 0; i < cnt; ++i) {
+                            const int nd = (int)(S.metaS[base + i] >> 16);
+                            const double withComb = 2.0 * popSize / (double)nd;
+                            add = add + bc[i] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
+                        }
+                        S.dpat[tid] = S.dpat[tid] + add;
+                        S.patDone[tid] = 2;
+                    } else ok = 0;
+                }
+                if (__syncthreads_and(ok)) break;
+            }
+            // the initial state is handled as a pseudo-event that builds epoch 0 without a transition
+            bool first = init;
+            bool rebuilt = false;
+            while (first || (nextEv < nSEv && nextEvStep == s)) {
+                const double* W = wpool + models[b].wPool;
+                if (!first) {
+                    const RcSEvDev ev = sev[nextEv];
+                    if (tid < np && !S.patDone[tid]) {
+                        double* aP = S.aS + tid * P;
+                        const double al = aP[ev.l], ak = aP[ev.k];
+                        if (ev.type == RC_EV_JOIN_D) {            // popJoinA, Core.hs:165-170
+                            aP[ev.l] = 0.0;
+                            aP[ev.k] = al + ak;
+                        } else {                                  // popSplitA, Core.hs:195-200
+                            aP[ev.l] = (1.0 - ev.m) * al;
+                            aP[ev.k] = ev.m * al + ak;
+                        }
+                    }
+                    W += ev.wOff;
+                    ++epoch;
+                    ++nextEv;
+                    nextEvStep = nextEv < nSEv ? sev[nextEv].step : -1;
+                }
+                // ---- per-thread structure of `epoch`; b is carried through the event's transition table
+                //      (popJoinB/popSplitB as a gather, Core.hs:172-221)
+                const int* so = pl.slotOff + (size_t)epoch * (nPat + 1);
+                if (tid < np) {
+                    int pid = S.patId[tid];
+                    S.patOff2[tid] = so[pid + 1] - so[pid];
+                    const uint8_t* mx = pl.maxX + ((size_t)epoch * nPat + pid) * P;
+                    int r = 0;
+                    for (int k = 0; k < P; ++k) r += mx[k];
+                    S.patR[tid] = r;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int run = 0, rr = 0;
+                    for (int p = 0; p < np; ++p) {
+                        int sz = S.patOff2[p]; S.patOff2[p] = run; run += sz;
+                        int q = S.patR[p]; S.patR[p] = rr; rr += q;
+                    }
+                    S.patOff2[np] = run;
+                    S.patR[np] = rr;
+                }
+                __syncthreads();
+                if (isTask) {
+                    const uint8_t* mx = pl.maxX + ((size_t)epoch * nPat + S.patId[tp]) * P;
+                    int off = S.patR[tp];
+                    for (int k = 0; k < tk; ++k) off += mx[k];
+                    R.tRE = sBase + K::O_RE + (unsigned)off * 16u;
+                    R.taskM = mx[tk];
+                }
+                const int nNew = S.patOff2[np];
+                R.slotOn = tid < nNew;
+                int n = 0;
+                R.unit = false; R.anchor = true; R.bv = 0.0;
+#pragma unroll
+                for (int d = 0; d < NNZ; ++d) { R.aRE[d] = zeroRE; R.aB[d] = zeroB; }
+                if (R.slotOn) {
+                    const int p = rc_find_owner(S.patOff2, np, tid);
+                    const int local = tid - S.patOff2[p];
+                    const int pid = S.patId[p];
+                    const int gl = so[pid] + local;
+                    const long long g = pl.epochBase[epoch] + gl;
+                    if (S.patDone[p]) R.slotOn = false;
+                    if (!first) {
+                        const int* trOff = pl.trOff + pl.trBase[epoch - 1];
+                        const uint32_t* trEnt = pl.trEnt + pl.trEntBase[epoch - 1];
+                        const double* bo = S.bbuf + cp * SM::BSTRIDE + S.patOff[p];
+                        const int e0 = trOff[gl], e1 = trOff[gl + 1];
+                        double acc = 0.0;
+                        for (int q = e0; q < e1; ++q) {
+                            const uint32_t en = trEnt[q];
+                            const uint32_t widx = en >> 16;
+                            const double old = bo[en & 0xFFFFu];
+                            acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
+                        }
+                        R.bv = acc;
+                    } else {
+                        // the seed state m is the last one fillUp emits (all components at their maximum)
+                        R.bv = (tid + 1 == S.patOff2[p + 1]) ? 1.0 : 0.0;
+                    }
+                    const uint32_t mt = pl.meta[g];
+                    S.metaS[tid] = mt;
+                    n = (int)(mt & 0xFFu);
+                    R.unit = (mt & RC_META_UNIT) != 0;
+                    const uint8_t* mx = pl.maxX + ((size_t)epoch * nPat + pid) * P;
+                    const int rBase = S.patR[p], bBase = S.patOff2[p];
+#pragma unroll
+                    for (int d = 0; d < NNZ; ++d) {
+                        if (d < n) {
+                            const uint32_t w = pl.words[g * nnzw + d];
+                            const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                            const uint32_t up = w >> 16;
+                            int off = rBase;
+                            for (int kk = 0; kk < k; ++kk) off += mx[kk];
+                            R.aRE[d] = sBase + K::O_RE + (unsigned)(off + x - 1) * 16u;
+                            if (up != RC_NO_UP)
+                                R.aB[d] = sBase + K::O_B + (unsigned)(bBase + (int)up) * 8u;
+                        }
+                    }
+                }
+                R.nw = __reduce_max_sync(0xFFFFFFFFu, n);
+                __syncthreads();                      // every gather has read the old layout
+                S.bbuf[tid] = R.bv;                   // new layout lives at parity 0
+                cp = 0;
+                if (tid <= np) S.patOff[tid] = S.patOff2[tid];
+                first = false;
+                rebuilt = true;
+                __syncthreads();
+            }
+            init = false;
+            if (!rebuilt) {                           // no event: only move b to parity 0 and refresh activity
+                S.bbuf[tid] = R.bv;
+                if (R.slotOn) {
+                    const int p = rc_find_owner(S.patOff, np, tid);
+                    if (S.patDone[p]) R.slotOn = false;
+                }
+            }
+            // ---- a (possibly changed by events) back into the task registers; updateA of step s in place
+            if (isTask) {
+                R.av = S.aS[tid];
+                R.aProp = R.av >= 1.0;
+                if (R.aProp) R.uv = 1.0 / R.av - 1.0;
+                R.taskOn = !S.patDone[tp];
+            }
+            if (s >= nSteps) break;
+            if (tid == 0) { S.RE[2 * (SM::RCAP - 2)] = S.tabS[0]; S.RE[2 * (SM::RCAP - 2) + 1] = 0.0; }
+            rc_fast_taskA<NNZ, BLOCK, 0, 0>(R);
+            __syncthreads();
+        }
+        // ================================ fast path: two grid steps per trip ================================
+        // next step index at which the slow path must run again
+        int nextStop = nSteps;
+        if (sShort > s && sShort < nextStop) nextStop = sShort;
+        if (nextEvStep > s && nextEvStep < nextStop) nextStop = nextEvStep;
+        const int pfStop = min(nextStop, rowsAvail - 1);       // last row worth prefetching
+        const double* pf = rows + (long long)(s + 2) * rowLen + tid;
+        for (;;) {
+            {
+                const bool bnd = s + 1 == nextStop;
+                rc_fast_step<NNZ, BLOCK, 0>(R, sBase, pf, rowLen, s + 2 <= pfStop, !bnd, s);
+                ++s;
+                pf += rowLen;
+                if (bnd) { cp = 1; break; }
+            }
+            {
+                const bool bnd = s + 1 == nextStop;
+                rc_fast_step<NNZ, BLOCK, 1>(R, sBase, pf, rowLen, s + 2 <= pfStop, !bnd, s);
+                ++s;
+                pf += rowLen;
+                if (bnd) { cp = 0; break; }
+            }
+        }
+        if (s >= nSteps && s != sShort) break;
+    }
+    // ---- getProb epilogue (Core.hs:49-54) ----
+    __syncthreads();
+    S.dslot[tid] = R.dacc;
+    __syncthreads();
+    if (tid < np) {
+        const int pid = S.patId[tid];
+        double d = S.dpat[tid];
+        if (S.patDone[tid] != 2) {
+            const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+            for (int i = 0; i < cnt; ++i)
+                if (S.metaS[base + i] & RC_META_UNIT) d = d + S.dslot[base + i];
+        }
+        double discFac = 1.0;
+        for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
+        pOut[(size_t)b * pl.nPat + pid] = d * models[b].theta * pl.combFac[pid] * discFac;
     }
 }
 
@@ -401,6 +854,37 @@ cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, c
     dim3 grid((unsigned)pl.nBins, (unsigned)nB);
     rc_propagate_kernel<<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, sevs, tab, wpool, pOut + (size_t)b0 * pl.nPat);
     return cudaGetLastError();
+}
+
+template <int NNZ, int BLOCK>
+static cudaError_t rc_launch_fast_t(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs, const double* tab,
+                                    const double* wpool, double* pOut, int nB, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = rc_fast_smem_bytes(BLOCK);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rc_propagate_fast_kernel<NNZ, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(rc_propagate_fast_kernel<NNZ, BLOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((unsigned)pl.nFastBins, (unsigned)nB);
+    rc_propagate_fast_kernel<NNZ, BLOCK><<<grid, BLOCK, smem, st>>>(pl, models, sevs, tab, wpool, pOut);
+    return cudaGetLastError();
+}
+
+cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
+                                     const double* tab, const double* wpool, double* pOut, int b0, int nB,
+                                     cudaStream_t st) {
+    if (pl.nFastBins <= 0 || nB <= 0) return cudaSuccess;
+    const RcModelDev* m = models + b0;
+    double* out = pOut + (size_t)b0 * pl.nPat;
+    const bool n4 = pl.nnzw <= 4;
+    switch (pl.fastBlock) {
+        case 64: return n4 ? rc_launch_fast_t<4, 64>(pl, m, sevs, tab, wpool, out, nB, st) : rc_launch_fast_t<8, 64>(pl, m, sevs, tab, wpool, out, nB, st);
+        case 128: return n4 ? rc_launch_fast_t<4, 128>(pl, m, sevs, tab, wpool, out, nB, st) : rc_launch_fast_t<8, 128>(pl, m, sevs, tab, wpool, out, nB, st);
+        default: return n4 ? rc_launch_fast_t<4, 256>(pl, m, sevs, tab, wpool, out, nB, st) : rc_launch_fast_t<8, 256>(pl, m, sevs, tab, wpool, out, nB, st);
+    }
 }
 
 cudaError_t rc_launch_reduce(const double* pOut, const long long* counts, const int* patGlobal,

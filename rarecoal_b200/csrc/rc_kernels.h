@@ -12,6 +12,10 @@ cudaError_t rc_launch_tables(const RcModelDev* models, const RcSegDev* segs, con
 cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
                                 const double* tab, const double* wpool, double* pOut, int b0, int nB,
                                 cudaStream_t st);
+cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
+                                     const double* tab, const double* wpool, double* pOut, int b0, int nB,
+                                     cudaStream_t st);
+size_t rc_fast_smem_bytes(int block);
 cudaError_t rc_launch_reduce(const double* pOut, const long long* counts, const int* patGlobal,
                              const RcModelDev* models, int nPat, int nPatGlobal, int B, double* partial,
                              double* dProbs, cudaStream_t st);

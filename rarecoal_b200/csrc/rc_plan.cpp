@@ -159,9 +159,11 @@ struct PatPlan {
     std::vector<uint32_t> meta;     // per epoch: live
     std::vector<int> trCnt;         // per transition: live_{e+1} counts
     std::vector<uint32_t> trEnt;
+    std::vector<uint8_t> mx;        // per epoch: P bytes, largest x_k over the live states
     bool shortcutOK = false;
     int maxLive = 0;
     int maxNnz = 0;
+    int maxR = 0;                   // largest sum_k mx[k] over epochs (rows of the per-step rate table)
     std::string err;
 };
 
@@ -207,11 +209,14 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     pp.maxLive = std::max(pp.maxLive, (int)L.size());
     size_t w0 = pp.words.size();
     pp.words.resize(w0 + L.size() * (size_t)c.stride, 0u);
+    size_t m0 = pp.mx.size();
+    pp.mx.resize(m0 + (size_t)c.P, 0);
     for (size_t i = 0; i < L.size(); ++i) {
         St s = L[i];
         int nnz = 0, sum = 0;
         for (int k = 0; k < c.P; ++k) {
             int xk = s.x[k];
+            if (xk > pp.mx[m0 + (size_t)k]) pp.mx[m0 + (size_t)k] = (uint8_t)xk;
             if (!xk) continue;
             sum += xk;
             s.x[k] = (uint8_t)(xk + 1);
@@ -229,6 +234,9 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
         if (nnz == 1 && sum == 1) m |= RC_META_UNIT;
         pp.meta.push_back(m);
     }
+    int r = 0;
+    for (int k = 0; k < c.P; ++k) r += pp.mx[m0 + (size_t)k];
+    pp.maxR = std::max(pp.maxR, r);
 }
 
 void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std::vector<StructEv>& sev,
@@ -399,48 +407,78 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     out = PlanHost();
     out.P = P; out.maxAf = maxAf; out.nPat = nPat; out.nEpochs = nEpochs; out.nnzw = nnzw; out.maxLive = maxLive;
 
-    // block capacity: a multiple of the block size that holds the largest pattern; bounded by shared memory
-    int cap = ((maxLive + RC_BLOCK - 1) / RC_BLOCK) * RC_BLOCK;
-    // bytes per slot in the kernel: 2 b buffers + d accumulator (24) + words (4*nnzw) + meta (4) + owner (2)
+    // Two tiers.  Fast tier (rc_propagate_fast_kernel): one live state per thread, <= RC_BLOCK states per
+    // pattern, <= 8 non-zero components per state.  Big tier (rc_propagate_kernel): several states per thread,
+    // block capacity = the largest pattern rounded up to the block size, bounded by shared memory.
+    std::vector<int> fastIds, bigIds;
+    int maxLiveBig = 0, maxLiveFast = 1;
+    const bool fastOK = nnzw <= 8 && rc_row_len(P, maxAf + 1) <= RC_ROWCAP;
+    for (int i = 0; i < nPat; ++i) {
+        const PatPlan& pp = pps[(size_t)i];
+        if (fastOK && pp.maxLive <= RC_BLOCK && pp.maxR <= 2 * RC_BLOCK - 2) {
+            fastIds.push_back(i);
+            maxLiveFast = std::max(maxLiveFast, pp.maxLive);
+        } else { bigIds.push_back(i); maxLiveBig = std::max(maxLiveBig, pp.maxLive); }
+    }
+    // smallest block that holds the largest fast-tier pattern: fewer warps per barrier, finer packing
+    (void)maxLiveFast;
+    int fastBlock = 256;   // measured on C3: 256-thread blocks beat 64-thread blocks (141 vs 226 ms per 44 models)
+    for (int i : fastIds)
+        while (pps[(size_t)i].maxR > 2 * fastBlock - 2) fastBlock *= 2;
+    out.fastBlock = fastBlock;
+    const int maxPatFast = std::max(1, std::min(RC_NPB, fastBlock / P));
+    int cap = ((std::max(maxLiveBig, 1) + RC_BLOCK - 1) / RC_BLOCK) * RC_BLOCK;
+    // bytes per slot in the big-tier kernel: 2 b buffers + d accumulator (24) + words (4*nnzw) + meta (4) + owner (2)
     int perSlot = 24 + 4 * nnzw + 4 + 2;
     int fixed = RC_NPB * P * 16 + RC_NPB * 32 + rc_row_len(P, maxAf + 1) * 8 + 1024;
-    if ((long long)cap * perSlot + fixed > smemBudgetBytes)
-        return "live set of one pattern (" + std::to_string(maxLive) + " states) exceeds the shared-memory tier";
+    if (!bigIds.empty() && (long long)cap * perSlot + fixed > smemBudgetBytes)
+        return "live set of one pattern (" + std::to_string(maxLiveBig) + " states) exceeds the shared-memory tier";
     out.cap = cap;
 
-    // bins: best-fit decreasing on the per-pattern maximum live size
-    std::vector<int> order((size_t)nPat);
-    for (int i = 0; i < nPat; ++i) order[(size_t)i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pps[(size_t)a].maxLive > pps[(size_t)b].maxLive; });
-    std::vector<std::vector<int>> bins;
-    std::vector<int> binFree;
-    std::multimap<int, int> open;   // free capacity -> bin
-    for (int i : order) {
-        int sz = pps[(size_t)i].maxLive;
-        auto it = open.lower_bound(sz);
-        int b;
-        if (it == open.end()) {
-            b = (int)bins.size();
-            bins.emplace_back();
-            binFree.push_back(cap);
-        } else {
-            b = it->second;
-            open.erase(it);
+    // best-fit decreasing on the per-pattern maximum live size, under the tier's pattern / rate-row limits
+    auto pack = [&](const std::vector<int>& ids, int capSlots, int maxPats, int capR, std::vector<int>& patOff,
+                    std::vector<int>& pats) {
+        std::vector<int> order(ids);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pps[(size_t)a].maxLive > pps[(size_t)b].maxLive; });
+        std::vector<std::vector<int>> bins;
+        std::vector<int> freeSlots, freeR;
+        std::multimap<int, int> open;   // free slots -> bin
+        for (int i : order) {
+            int sz = pps[(size_t)i].maxLive, rr = pps[(size_t)i].maxR;
+            int b = -1, tries = 0;
+            for (auto it = open.lower_bound(sz); it != open.end() && tries < 8; ++it, ++tries)
+                if (freeR[(size_t)it->second] >= rr) { b = it->second; open.erase(it); break; }
+            if (b < 0) {
+                b = (int)bins.size();
+                bins.emplace_back();
+                freeSlots.push_back(capSlots);
+                freeR.push_back(capR);
+            }
+            bins[(size_t)b].push_back(i);
+            freeSlots[(size_t)b] -= sz;
+            freeR[(size_t)b] -= rr;
+            if ((int)bins[(size_t)b].size() < maxPats && freeSlots[(size_t)b] > 0 && freeR[(size_t)b] > 0)
+                open.emplace(freeSlots[(size_t)b], b);
         }
-        bins[(size_t)b].push_back(i);
-        binFree[(size_t)b] -= sz;
-        if ((int)bins[(size_t)b].size() < RC_NPB && binFree[(size_t)b] > 0) open.emplace(binFree[(size_t)b], b);
-    }
-    // heaviest bins first so the hardware block scheduler ends with the light ones
-    std::vector<int> border(bins.size());
-    for (size_t b = 0; b < bins.size(); ++b) border[b] = (int)b;
-    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return binFree[(size_t)a] < binFree[(size_t)b]; });
-    out.nBins = (int)bins.size();
-    out.binPatOff.assign(1, 0);
-    for (int b : border) {
-        for (int i : bins[(size_t)b]) out.binPats.push_back(i);
-        out.binPatOff.push_back((int)out.binPats.size());
-    }
+        // heaviest bins first so the hardware block scheduler ends with the light ones
+        std::vector<int> border(bins.size());
+        for (size_t b = 0; b < bins.size(); ++b) border[b] = (int)b;
+        std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return freeSlots[(size_t)a] < freeSlots[(size_t)b]; });
+        patOff.assign(1, 0);
+        pats.clear();
+        for (int b : border) {
+            for (int i : bins[(size_t)b]) pats.push_back(i);
+            patOff.push_back((int)pats.size());
+        }
+        return (int)bins.size();
+    };
+    out.nFastBins = pack(fastIds, fastBlock, maxPatFast, 2 * fastBlock - 2, out.fBinPatOff, out.fBinPats);
+    out.nBins = pack(bigIds, cap, RC_NPB, 1 << 30, out.binPatOff, out.binPats);
+    out.maxX.assign((size_t)nEpochs * nPat * P, 0);
+    for (int e = 0; e < nEpochs; ++e)
+        for (int i = 0; i < nPat; ++i)
+            for (int k = 0; k < P; ++k)
+                out.maxX[((size_t)e * nPat + i) * P + k] = pps[(size_t)i].mx[(size_t)e * P + k];
 
     // concatenate per-epoch arrays
     out.slotOff.assign((size_t)nEpochs * (nPat + 1), 0);

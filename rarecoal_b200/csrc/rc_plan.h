@@ -45,7 +45,11 @@ struct GapInfo {
 
 struct PlanHost {
     int P = 0, maxAf = 0, nPat = 0, nEpochs = 0, nnzw = 1, nBins = 0, cap = RC_BLOCK;
-    std::vector<int> binPatOff, binPats;
+    std::vector<int> binPatOff, binPats;   // big tier bins
+    int nFastBins = 0;
+    int fastBlock = RC_BLOCK;              // 64, 128 or 256 state slots per fast-tier block
+    std::vector<int> fBinPatOff, fBinPats; // fast tier bins
+    std::vector<uint8_t> maxX;             // [nEpochs][nPat][P] largest x_k over the live states
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]
     std::vector<uint32_t> words, meta;

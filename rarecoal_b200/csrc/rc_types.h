@@ -37,8 +37,13 @@ struct RcPlanDev {
     int nnzw;                    // words per slot
     int nBins;
     int cap;                     // slots per block
-    const int* binPatOff;        // [nBins+1]
+    const int* binPatOff;        // [nBins+1]          big-tier bins (several states per thread)
     const int* binPats;          // shard-local pattern ids, bin after bin
+    int nFastBins;
+    int fastBlock;               // threads (= state slots) per fast-tier block: 64, 128 or 256
+    const int* fBinPatOff;       // [nFastBins+1]      fast-tier bins (one state per thread)
+    const int* fBinPats;
+    const uint8_t* maxX;         // [nEpochs][nPat][P] largest x_k over the live states of a pattern
     const int* slotOff;          // [nEpochs][nPat+1]  slot offsets inside the epoch's arrays
     const long long* epochBase;  // [nEpochs]  base of epoch e inside words/meta (in slots)
     const uint32_t* words;       // [totalSlots][nnzw]
@@ -87,11 +92,19 @@ struct RcSegDev {
 };
 
 // Table row layout (doubles), one row per (model, grid step):
-//   [0, P*A1)            E2[k][j] = 1 - exp(-(j(j+1)/2) * (1/N_k) * dt)      (Core.hs:279), 0 if frozen
-//   [P*A1, 2*P*A1)       CN[k][j] = j(j-1)/2 * (1/N_k)                        (Core.hs:270), 0 if frozen
-//   [2*P*A1, +P)         EA[k]    = exp(-0.5*dt/N_k)                          (Core.hs:240)
-//   [.. +P)              invN[k]  = 1/N_k (0 if frozen, so r_k = a_k*invN_k drops out of t1)
-//   [.. +P)              N[k]
-//   [.. +1]              dt
-//   [.. +1]              frozen mask (as double)
-static inline __host__ __device__ int rc_row_len(int P, int A1) { return 2 * P * A1 + 3 * P + 2; }
+//   [0]                      dt
+//   [1]                      frozen mask (as double)
+//   [2 + 2*(k*A1 + j)]       16-byte pairs, k < P, j < A1:
+//                              j == 0 : { EA[k], invN[k] }
+//                                       EA[k]   = exp(-0.5*dt/N_k)   (Core.hs:240); exactly 1.0 if the branch is
+//                                                 frozen or dt <= 0 (updateA is then the identity)
+//                                       invN[k] = 1/N_k, 0 if frozen (so a_k/N_k drops out of t1)
+//                              j >= 1 : { CN[k][j], E2[k][j] }
+//                                       CN = j(j-1)/2 * (1/N_k)                       (Core.hs:270), 0 if frozen
+//                                       E2 = 1 - exp(-(j(j+1)/2) * (1/N_k) * dt)      (Core.hs:279), 0 if frozen
+//   [2 + 2*P*A1 + k]         N[k]
+// Rows are padded to an even number of doubles so that every pair stays 16-byte aligned.
+#define RC_ROW_PAIRS 2
+static inline __host__ __device__ int rc_row_n(int P, int A1) { return RC_ROW_PAIRS + 2 * P * A1; }
+static inline __host__ __device__ int rc_row_len(int P, int A1) { return (RC_ROW_PAIRS + 2 * P * A1 + P + 1) & ~1; }
+#define RC_ROWCAP 256        // fast tier: table rows of at most this many doubles (two-slot ring in shared memory)
