@@ -133,6 +133,13 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
                 const rc_event* ev, int nEv, double theta, const double* disc, int noShortcut,
                 double* outProb);
 
+/* Tuning switches (defaults in parentheses):
+ *   "keyed" (1)            patterns of the fast tier go through the trajectory-key kernels when the table fits;
+ *                          0 forces the self-contained kernels (used by the parity tests to cover both)
+ *   "ktab_model_mb" (1024) largest trajectory table of one model; a model above it uses the self-contained kernels
+ *   "ktab_total_mb" (12288) largest trajectory table memory of one call                                   */
+int rc_set_option(rc_ctx* ctx, const char* name, double value);
+
 int rc_last_stats(rc_ctx* ctx, rc_stats* out);
 
 /* Measures the FP64 FMA rate of the device with a register-resident DFMA chain kernel (the

@@ -37,6 +37,7 @@ SIGNATURES = {
     "rc_eval_partial": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, C.c_int, _vp, _vp, _vp, _ip]),
     "rc_finalize": (C.c_int, [_vp, C.c_int, _vp, C.c_double, _vp, _dp]),
     "rc_get_prob": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _evp, C.c_int, C.c_double, _dp, C.c_int, _dp]),
+    "rc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "rc_last_stats": (C.c_int, [_vp, C.POINTER(rc_stats)]),
     "rc_fp64_peak": (C.c_int, [_vp, _dp]),
     "rc_all_configs": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.c_int]),

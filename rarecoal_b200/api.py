@@ -370,6 +370,10 @@ class Engine:
                                           C.c_void_p(stream) if stream else None, _dp(logl)))
         return logl
 
+    def set_option(self, name, value):
+        """rc_set_option: "keyed", "ktab_model_mb", "ktab_total_mb"."""
+        self._check(self._lib.rc_set_option(self._h, name.encode(), float(value)))
+
     def stats(self):
         st = L.rc_stats()
         self._check(self._lib.rc_last_stats(self._h, C.byref(st)))

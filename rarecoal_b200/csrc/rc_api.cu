@@ -135,7 +135,11 @@ struct rc_ctx {
     // plans
     std::map<std::string, PlanEntry*> plans;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort;
+    // options (rc_set_option)
+    int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
+    double optKtabModelMB = 1024.0;   // largest trajectory table of one model
+    double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
     PinBuf hBlob, hOut;
     cudaStream_t stream = nullptr;
     cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -340,6 +344,29 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     if ((rc = upload(ctx, pe, h.fBinPatOff, &d.fBinPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
     if ((rc = upload(ctx, pe, h.maxX, &d.maxX))) return rc;
+    {
+        std::vector<RcEpochDev> eps(h.ep.size());
+        for (size_t e = 0; e < h.ep.size(); ++e) {
+            eps[e].nKeys = h.ep[e].nKeys; eps[e].nThr = h.ep[e].nThr; eps[e].rowPairs = h.ep[e].rowPairs;
+            eps[e].keyOff = h.ep[e].keyOff; eps[e].thrOff = h.ep[e].thrOff;
+        }
+        if ((rc = upload(ctx, pe, eps, &d.ep))) return rc;
+    }
+    d.totalKeys = h.totalKeys;
+    d.nKeysLast = h.ep.empty() ? 0 : h.ep.back().nKeys;
+    if ((rc = upload(ctx, pe, h.keyBranch, &d.keyBranch))) return rc;
+    if ((rc = upload(ctx, pe, h.keyMaxJ, &d.keyMaxJ))) return rc;
+    if ((rc = upload(ctx, pe, h.keyOp, &d.keyOp))) return rc;
+    if ((rc = upload(ctx, pe, h.keyPa, &d.keyPa))) return rc;
+    if ((rc = upload(ctx, pe, h.keyPb, &d.keyPb))) return rc;
+    if ((rc = upload(ctx, pe, h.keyInit, &d.keyInit))) return rc;
+    if ((rc = upload(ctx, pe, h.keyPairBase, &d.keyPairBase))) return rc;
+    if ((rc = upload(ctx, pe, h.keyThrBase, &d.keyThrBase))) return rc;
+    if ((rc = upload(ctx, pe, h.thrKey, &d.thrKey))) return rc;
+    if ((rc = upload(ctx, pe, h.lastKeyId, &d.lastKeyId))) return rc;
+    if ((rc = upload(ctx, pe, h.fetchOff, &d.fetchOff))) return rc;
+    if ((rc = upload(ctx, pe, h.fetchRows, &d.fetchRows))) return rc;
+    if ((rc = upload(ctx, pe, h.rowBase, &d.rowBase))) return rc;
     if ((rc = upload(ctx, pe, h.binPatOff, &d.binPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.binPats, &d.binPats))) return rc;
     if ((rc = upload(ctx, pe, h.slotOff, &d.slotOff))) return rc;
@@ -416,9 +443,10 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mhs[(size_t)x].plan < mhs[(size_t)y].plan; });
 
     // ---- pack the per-call blob: headers | structural events | segment offsets | segments | weights
-    size_t nSev = 0, nSeg = 0, nW = 0;
+    size_t nSev = 0, nSeg = 0, nW = 0, nMep = 0;
     for (auto& mh : mhs) {
         if (mh.status != RC_OK) continue;
+        nMep += mh.sev.size() + 1;
         nSev += mh.sev.size();
         nSeg += mh.segs.size();
         for (auto& se : mh.sev) if (se.type == RC_EV_SPLIT) nW += (size_t)A1 * A1;
@@ -428,7 +456,8 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     size_t oSegOff = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
     size_t oSegs = align16(oSegOff + (size_t)(B + 1) * sizeof(int));
     size_t oW = align16(oSegs + std::max<size_t>(nSeg, 1) * sizeof(RcSegDev));
-    size_t blobBytes = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
+    size_t oMep = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
+    size_t blobBytes = align16(oMep + std::max<size_t>(nMep, 1) * sizeof(RcModelEpochDev));
     // the pinned staging buffer is reused: wait until the previous call's upload has left it
     if (ctx->blobInFlight) {
         CK(cudaEventSynchronize(ctx->evt[5]));
@@ -444,6 +473,11 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     int* hSegOff = (int*)(hb + oSegOff);
     RcSegDev* hSegs = (RcSegDev*)(hb + oSegs);
     double* hW = (double*)(hb + oW);
+    RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
+    size_t mepPos = 0;
+    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0;
+    const long long ktabModelMax = (long long)(ctx->optKtabModelMB * 1048576.0 / 16.0);
+    const long long ktabTotalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
 
     long long tabDoubles = 0;
     int rowsMax = 0;
@@ -464,7 +498,36 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         M.sShort = mh.sShort;
         M.nSEv = (int)mh.sev.size();
         M.sevOff = (int)sevPos;
-        M.rowsAvail = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
+        const rc::PlanHost& hp = pe->h;
+        // ---- keyed mode: per-epoch step ranges and the model's slice of the trajectory table ----
+        {
+            const int finalEnd = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort : T;
+            long long pairs = 0;
+            M.mepOff = (int)mepPos;
+            for (int e = 0; e < hp.nEpochs; ++e) {
+                RcModelEpochDev& me = hMep[mepPos++];
+                me.beg = e == 0 ? 0 : mh.sevStep[(size_t)e - 1];
+                me.end = e + 1 < hp.nEpochs ? mh.sevStep[(size_t)e] : finalEnd;
+                if (me.end < me.beg) me.end = me.beg;
+                me.tabBase = ktabPairs + pairs;
+                pairs += (long long)(me.end - me.beg) * hp.ep[(size_t)e].rowPairs;
+            }
+            M.mode = (ctx->optKeyed && hp.nFastBins > 0 && pairs <= ktabModelMax && ktabPairs + pairs <= ktabTotalMax) ? 1 : 0;
+            if (M.mode == 1) {
+                ktabPairs += pairs;
+                M.aEndOff = aEndDoubles;
+                M.aShortOff = aShortDoubles;
+                aEndDoubles += hp.totalKeys;
+                aShortDoubles += hp.ep.back().nKeys;
+            }
+            if (mh.sShort >= 0) {
+                size_t si = 0;
+                while (si + 1 < mh.segs.size() && mh.segs[si + 1].sBegin <= mh.sShort) ++si;
+                for (int k = 0; k < P; ++k) M.Nshort[k] = mh.segs[si].N[k];
+            }
+        }
+        // table rows are needed by the self-contained tiers only
+        M.rowsAvail = (M.mode == 1 && hp.nBins == 0) ? 0 : ((mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T);
         M.tabOff = tabDoubles;
         M.wPool = 0;
         M.theta = theta[b];
@@ -498,7 +561,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         W += count_state_steps(mh, h, T);
         slots0 += h.epochSlots[0];
         ctx->stats.n_epochs = h.nEpochs;
-        ctx->stats.n_steps = M.rowsAvail;
+        ctx->stats.n_steps = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
     }
     hSegOff[B] = (int)segPos;
     ctx->stats.state_steps = W;
@@ -508,9 +571,17 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     {
         size_t needTab = (size_t)std::max<long long>(tabDoubles, 1) * sizeof(double);
         size_t needOut = (size_t)B * std::max(ctx->nPat, 1) * sizeof(double);
-        if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap) CK(cudaStreamSynchronize(st));
+        size_t needK = (size_t)std::max<long long>(ktabPairs, 1) * 16;
+        size_t needA = (size_t)std::max<long long>(aEndDoubles, 1) * sizeof(double);
+        size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
+        if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap || needK > ctx->dKTab.cap || needA > ctx->dAEnd.cap ||
+            needS > ctx->dAShort.cap)
+            CK(cudaStreamSynchronize(st));
         CK(ctx->dTab.ensure(needTab));
         CK(ctx->dPOut.ensure(needOut));
+        CK(ctx->dKTab.ensure(needK));
+        CK(ctx->dAEnd.ensure(needA));
+        CK(ctx->dAShort.ensure(needS));
     }
 
     unsigned char* db = (unsigned char*)ctx->dBlob.p;
@@ -519,6 +590,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     const int* dSegOff = (const int*)(db + oSegOff);
     const RcSegDev* dSegs = (const RcSegDev*)(db + oSegs);
     const double* dW = (const double*)(db + oW);
+    const RcModelEpochDev* dMep = (const RcModelEpochDev*)(db + oMep);
 
     CK(cudaEventRecord(ctx->evt[0], st));
     CK(cudaMemcpyAsync(db, hb, blobBytes, cudaMemcpyHostToDevice, st));
@@ -537,7 +609,19 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         int end = pos + 1;
         while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
         if (pe && ctx->nPat > 0) {
-            if (pe->d.nFastBins > 0) {
+            bool anyKeyed = false, anySelf = false;
+            for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
+            if (pe->d.nFastBins > 0 && anyKeyed) {
+                for (int e = 0; e < pe->h.nEpochs; ++e) {
+                    CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, dSegs, dSegOff, (const double*)ctx->dDts.p,
+                                      (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, st));
+                    ++launches;
+                }
+                CK(rc_launch_propagate_keyed(pe->d, dM, dMep, dSev, (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW,
+                                             (double*)ctx->dPOut.p, pos, end - pos, st));
+                ++launches;
+            }
+            if (pe->d.nFastBins > 0 && anySelf) {
                 CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
                 ++launches;
             }
@@ -654,7 +738,8 @@ void rc_destroy(rc_ctx* ctx) {
     if (ctx->child) rc_destroy(ctx->child);
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
-                      &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs};
+                      &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
+                      &ctx->dAShort};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();
@@ -829,6 +914,17 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
     if (rc != RC_OK) { ctx->err = c->err; return rc; }
     if (status != RC_OK) { ctx->err = c->err; return status; }
     *outProb = prob;
+    return RC_OK;
+}
+
+int rc_set_option(rc_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return RC_ERR_ARG;
+    ctx->err.clear();
+    std::string n(name);
+    if (n == "keyed") ctx->optKeyed = value != 0.0;
+    else if (n == "ktab_model_mb") ctx->optKtabModelMB = value;
+    else if (n == "ktab_total_mb") ctx->optKtabTotalMB = value;
+    else { ctx->err = "rc_set_option: unknown option " + n; return RC_ERR_ARG; }
     return RC_OK;
 }
 

@@ -516,7 +516,7 @@ rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, co
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x;
     const int bin = blockIdx.x, b = blockIdx.y;
-    if (models[b].nSteps < 0) return;                    // model failed validation on the host
+    if (models[b].nSteps < 0 || models[b].mode != 0) return;   // failed validation / handled by the keyed kernel
     const int P = pl.P, A1 = pl.A1;
     const int rowLen = rc_row_len(P, A1);
     typedef RcFastSmem<BLOCK> SM;
@@ -781,6 +781,417 @@ rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Keyed fast tier.
+//
+// rc_traj_kernel — one launch per structural epoch.  Thread (key, j) follows the ancestral count a of one
+// trajectory key (branch k, derived-allele counts on the leaves merged into k) through the epoch's grid steps
+// with the reference's own formulas (updateA, Core.hs:229-240; the starting value comes from the parent keys via
+// popJoinA / popSplitA, Core.hs:165-170,195-200) and writes, for every step, the pair
+//     { G = exp(-(j(j-1)/2 (1/N_k) + j a_k (1/N_k)) dt),   E2 = 1 - exp(-j(j+1)/2 (1/N_k) dt) }
+// i.e. the k-th factor of exp(-t1 dt) for a state with x_k = j (Core.hs:259,270) and the coalescence factor of
+// b(x+e_k) (Core.hs:279).  All patterns that share the key read the same pairs.
+__global__ void __launch_bounds__(128)
+rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+               const RcSEvDev* __restrict__ sevs, const RcSegDev* __restrict__ segs, const int* __restrict__ segOff,
+               const double* __restrict__ dts, double* __restrict__ ktab, double* __restrict__ aEnd,
+               double* __restrict__ aShort) {
+    const int b = blockIdx.y;
+    const RcModelDev& M = models[b];
+    if (M.nSteps < 0 || M.mode != 1) return;
+    const RcEpochDev E = pl.ep[e];
+    const RcModelEpochDev me = mep[M.mepOff + e];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nst = me.end - me.beg;
+    const bool lastEpoch = e + 1 == pl.nEpochs;
+    // pair 0 of every step row: {dt, 0}; a step with dt <= 0 performs no update (Core.hs:130)
+    for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
+        const double dt = dts[me.beg + i];
+        double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
+        p0[0] = dt > 0.0 ? dt : 0.0;
+        p0[1] = 0.0;
+    }
+    if (t >= E.nThr) return;
+    const int key = pl.thrKey[E.thrOff + t];
+    const int kk = E.keyOff + key;
+    const int k = pl.keyBranch[kk];
+    const int j = t - pl.keyThrBase[kk] + 1;
+    const bool hasPair = j <= (int)pl.keyMaxJ[kk];
+    // ---- starting value ----
+    double a;
+    {
+        const int op = pl.keyOp[kk];
+        const double* aPrev = e > 0 ? aEnd + M.aEndOff + pl.ep[e - 1].keyOff : aEnd;
+        const int pa = pl.keyPa[kk], pb = pl.keyPb[kk];
+        if (op == RC_KOP_INIT) a = (double)pl.keyInit[kk];                 // makeInitCoalState, Core.hs:60
+        else if (op == RC_KOP_COPY) a = aPrev[pa];
+        else if (op == RC_KOP_JOIN) a = aPrev[pb] + aPrev[pa];             // popJoinA: al + ak
+        else if (op == RC_KOP_ZERO) a = 0.0;
+        else {
+            const double m = sevs[M.sevOff + e - 1].m;
+            if (op == RC_KOP_SPLIT_K) a = m * aPrev[pb] + aPrev[pa];       // popSplitA: m * al + ak
+            else a = (1.0 - m) * aPrev[pa];                                // (1 - m) * al
+        }
+    }
+    // ---- (popSize, freeze) segment of the first step ----
+    int si = segOff[b];
+    const int sEnd = segOff[b + 1];
+    while (si + 1 < sEnd && segs[si + 1].sBegin <= me.beg) ++si;
+    double N = segs[si].N[k];
+    bool frozen = (segs[si].frozenMask >> k) & 1u;
+    int nextSeg = si + 1 < sEnd ? segs[si + 1].sBegin : 0x7fffffff;
+    const double xx = (double)j;
+    double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2;
+    const long long stride = (long long)E.rowPairs * 2;
+    for (int s = me.beg; s < me.end; ++s, out += stride) {
+        while (s >= nextSeg) {
+            ++si;
+            N = segs[si].N[k];
+            frozen = (segs[si].frozenMask >> k) & 1u;
+            nextSeg = si + 1 < sEnd ? segs[si + 1].sBegin : 0x7fffffff;
+        }
+        if (lastEpoch && s == M.sShort && j == 1) aShort[M.aShortOff + key] = a;
+        const double dt = dts[s];
+        double G = 1.0, E2 = 0.0;
+        if (dt > 0.0 && !frozen) {
+            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * exp(-(0.5 * dt / N)));     // propagateA, Core.hs:239-240
+            if (hasPair) {
+                const double t1k = xx * (xx - 1.0) / 2.0 * (1.0 / N) + xx * a * (1.0 / N);  // Core.hs:270 (new a)
+                G = exp(-(t1k * dt));
+                E2 = 1.0 - exp(-(xx * (xx + 1.0) / 2.0 * (1.0 / N) * dt));                   // Core.hs:279
+            }
+        }
+        if (hasPair) { out[0] = G; out[1] = E2; }
+    }
+    if (j == 1) {
+        aEnd[M.aEndOff + kk] = a;
+        if (lastEpoch && M.sShort == me.end) aShort[M.aShortOff + key] = a;
+    }
+}
+
+// rc_propagate_keyed_kernel — the state side.  One live state per thread; per non-zero component one LDS.128 of the
+// pair {G, E2}, one multiply into the decay factor, one LDS.64 of the neighbour and one FMA:
+//     b'(x) = b(x) * prod_k G_k(x_k) + sum_k b(x + e_k) E2_k(x_k)            (Core.hs:259)
+// Pairs of the bin's keys are staged from the trajectory table into shared memory two steps ahead by the first
+// lanes of the block (one pair row per lane); one barrier per grid step; the time loop is unrolled by two so that
+// buffer parities are immediates.
+struct RcKeySmem {
+    static constexpr int BSTRIDE = RC_BLOCK + 8;       // entry RC_BLOCK of each b buffer is the always-zero neighbour
+    double bbuf[2 * BSTRIDE];
+    double RE[2 * 2 * RC_KROWS];                       // [parity][row]{G, E2}; row 0 = {dt, 0}; last row = {1, 0}
+    double dslot[RC_BLOCK];
+    double dpat[RC_NPB];
+    uint32_t metaS[RC_BLOCK];
+    int patOff[RC_NPB + 1];
+    int patOff2[RC_NPB + 1];
+    int patId[RC_NPB];
+    int patDone[RC_NPB];
+};
+struct RcKeyK {
+    static constexpr unsigned B_PAR = RcKeySmem::BSTRIDE * 8u;
+    static constexpr unsigned RE_PAR = RC_KROWS * 16u;
+    static constexpr unsigned RE_PAD = (RC_KROWS - 1) * 16u;
+    static constexpr unsigned O_B = (unsigned)offsetof(RcKeySmem, bbuf);
+    static constexpr unsigned O_RE = (unsigned)offsetof(RcKeySmem, RE);
+    static_assert(O_RE % 16 == 0, "16-byte alignment of the pair table");
+};
+
+template <int NNZ>
+struct RcKeyRegs {
+    unsigned aRE[NNZ], aB[NNZ];   // absolute shared addresses at parity 0
+    int nw;
+    bool unit, slotOn, fetchOn;
+    double bv, dacc;
+    double preA0, preA1, preB0, preB1;   // two prefetch register sets (pairs of step s+1 / s+2)
+    const double* fPtr;           // this lane's pair in the step row being prefetched
+};
+
+__device__ __forceinline__ void rc_ldg128(const double* p, double& a, double& b) {
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+
+template <int NNZ, int N, int PH>
+__device__ __forceinline__ void rc_key_dims(const RcKeyRegs<NNZ>& R, double& D, double& t2) {
+    typedef RcKeyK K;
+    double g, e2;
+    rc_lds128(R.aRE[0] + PH * K::RE_PAR, g, e2);
+    D = g;
+    t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
+#pragma unroll
+    for (int d = 1; d < N; ++d) {
+        rc_lds128(R.aRE[d] + PH * K::RE_PAR, g, e2);
+        D *= g;
+        t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
+    }
+}
+
+template <int NNZ, int PH>
+__device__ __forceinline__ void rc_key_step(RcKeyRegs<NNZ>& R, const unsigned sBase, const long long strideD,
+                                            const bool doPre, const bool doStore) {
+    typedef RcKeyK K;
+    constexpr int QH = PH ^ 1;
+    // pairs of step s+2 -> register set PH (set QH holds step s+1, loaded one step ago)
+    if (doPre && R.fetchOn) {
+        if (PH == 0) rc_ldg128(R.fPtr, R.preA0, R.preA1);
+        else rc_ldg128(R.fPtr, R.preB0, R.preB1);
+    }
+    R.fPtr += strideD;
+    if (R.slotOn) {
+        double D = 1.0, t2 = 0.0;
+        switch (R.nw) {
+            case 1: rc_key_dims<NNZ, 1, PH>(R, D, t2); break;
+            case 2: rc_key_dims<NNZ, 2, PH>(R, D, t2); break;
+            case 3: rc_key_dims<NNZ, (NNZ >= 3 ? 3 : NNZ), PH>(R, D, t2); break;
+            case 4: rc_key_dims<NNZ, (NNZ >= 4 ? 4 : NNZ), PH>(R, D, t2); break;
+            case 5: rc_key_dims<NNZ, (NNZ >= 5 ? 5 : NNZ), PH>(R, D, t2); break;
+            case 6: rc_key_dims<NNZ, (NNZ >= 6 ? 6 : NNZ), PH>(R, D, t2); break;
+            case 7: rc_key_dims<NNZ, (NNZ >= 7 ? 7 : NNZ), PH>(R, D, t2); break;
+            case 8: rc_key_dims<NNZ, (NNZ >= 8 ? 8 : NNZ), PH>(R, D, t2); break;
+            default: break;
+        }
+        R.bv = fma(R.bv, D, t2);                                     // updateB, Core.hs:259
+        rc_sts64(sBase + K::O_B + QH * K::B_PAR + threadIdx.x * 8u, R.bv);
+        if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + PH * K::RE_PAR), R.bv, R.dacc);   // updateD, Core.hs:282-288
+    }
+    if (doStore && R.fetchOn) {
+        if (PH == 0) rc_sts128(sBase + K::O_RE + QH * K::RE_PAR + threadIdx.x * 16u, R.preB0, R.preB1);
+        else rc_sts128(sBase + K::O_RE + QH * K::RE_PAR + threadIdx.x * 16u, R.preA0, R.preA1);
+    }
+    __syncthreads();
+}
+
+template <int NNZ>
+__global__ void __launch_bounds__(RC_BLOCK, 4)
+rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+                          const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab,
+                          const double* __restrict__ aShort, const double* __restrict__ wpool,
+                          double* __restrict__ pOut) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    typedef RcKeySmem SM;
+    typedef RcKeyK K;
+    const int tid = threadIdx.x;
+    const int bin = blockIdx.x, b = blockIdx.y;
+    if (models[b].nSteps < 0 || models[b].mode != 1) return;
+    const int P = pl.P;
+    SM& S = *reinterpret_cast<SM*>(smemRaw);
+    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const int pat0 = pl.fBinPatOff[bin];
+    const int np = pl.fBinPatOff[bin + 1] - pat0;
+    const int nSteps = models[b].nSteps, sShort = models[b].sShort, nSEv = models[b].nSEv;
+    const RcSEvDev* sev = sevs + models[b].sevOff;
+    const RcModelEpochDev* me = mep + models[b].mepOff;
+    const int nFP = pl.fBinPatOff[pl.nFastBins];
+
+    RcKeyRegs<NNZ> R;
+    const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
+    const unsigned zeroB = sBase + K::O_B + RC_BLOCK * 8u;
+#pragma unroll
+    for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+    R.nw = 0; R.unit = false; R.slotOn = false; R.fetchOn = false;
+    R.bv = 0.0; R.dacc = 0.0; R.preA0 = R.preA1 = R.preB0 = R.preB1 = 0.0;
+    R.fPtr = ktab;
+
+    if (tid < np) {
+        S.patId[tid] = pl.fBinPats[pat0 + tid];
+        S.patDone[tid] = 0;
+        S.dpat[tid] = 0.0;
+    }
+    if (tid < 4) S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;   // {1,0} padding pairs
+    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                                               // zero neighbours
+    __syncthreads();
+
+    int epoch = 0, nextEv = 0;
+    int nextEvStep = nSEv > 0 ? sev[0].step : -1;
+    int s = 0;
+    int cp = 0;               // parity of the buffer that holds the current b when the slow path is entered
+    bool init = true;
+
+    for (;;) {
+        // ================= slow path: shortcut test, structural events, epoch set-up =================
+        // On exit everything is normalised to parity 0: b in bbuf[0], pairs of step s in RE[0], pairs of step
+        // s+1 in prefetch set B, fPtr at step s+2.
+        {
+            const int nnzw = pl.nnzw, nPat = pl.nPat;
+            S.dslot[tid] = R.dacc;
+            R.dacc = 0.0;
+            __syncthreads();
+            if (tid < np && !S.patDone[tid] && !init) {       // updateD contributions so far (Core.hs:282-288)
+                const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+                double acc = S.dpat[tid];
+                for (int i = 0; i < cnt; ++i)
+                    if (S.metaS[base + i] & RC_META_UNIT) acc = acc + S.dslot[base + i];
+                S.dpat[tid] = acc;
+            }
+            if (s == sShort && !init) {                       // canUseShortcut / propagateStateShortcut, Core.hs:80-118
+                int ok = 1;
+                if (tid < np && !S.patDone[tid]) {
+                    const int pid = S.patId[tid];
+                    if (pl.shortcutOK[pid]) {
+                        const double* aK = aShort + models[b].aShortOff;
+                        const int* kid = pl.lastKeyId + (size_t)pid * P;
+                        double nrA = 0.0;
+                        int popIndex = -1;
+                        for (int k = 0; k < P; ++k) {
+                            const double ak = aK[kid[k]];
+                            nrA = nrA + ak;
+                            if (popIndex < 0 && ak > 0.0) popIndex = k;
+                        }
+                        const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
+                        const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+                        const double* bc = S.bbuf + cp * SM::BSTRIDE + base;
+                        double add = 0.0;
+                        for (int i = 0; i < cnt; ++i) {
+                            const int nd = (int)(S.metaS[base + i] >> 16);
+                            const double withComb = 2.0 * popSize / (double)nd;
+                            add = add + bc[i] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
+                        }
+                        S.dpat[tid] = S.dpat[tid] + add;
+                        S.patDone[tid] = 2;
+                    } else ok = 0;
+                }
+                if (__syncthreads_and(ok)) break;
+            }
+            // the initial state is handled as a pseudo-event that builds epoch 0 without a transition
+            bool first = init;
+            bool rebuilt = false;
+            while (first || (nextEv < nSEv && nextEvStep == s)) {
+                const double* W = wpool + models[b].wPool;
+                if (!first) {
+                    W += sev[nextEv].wOff;
+                    ++epoch;
+                    ++nextEv;
+                    nextEvStep = nextEv < nSEv ? sev[nextEv].step : -1;
+                }
+                // ---- per-thread structure of `epoch`; b is carried through the event's transition table
+                //      (popJoinB/popSplitB as a gather, Core.hs:172-221)
+                const int* so = pl.slotOff + (size_t)epoch * (nPat + 1);
+                if (tid < np) {
+                    const int pid = S.patId[tid];
+                    S.patOff2[tid] = so[pid + 1] - so[pid];
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int run = 0;
+                    for (int p = 0; p < np; ++p) { int sz = S.patOff2[p]; S.patOff2[p] = run; run += sz; }
+                    S.patOff2[np] = run;
+                }
+                __syncthreads();
+                const int nNew = S.patOff2[np];
+                R.slotOn = tid < nNew;
+                int n = 0;
+                R.unit = false; R.bv = 0.0;
+#pragma unroll
+                for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+                if (R.slotOn) {
+                    const int p = rc_find_owner(S.patOff2, np, tid);
+                    const int local = tid - S.patOff2[p];
+                    const int pid = S.patId[p];
+                    const int gl = so[pid] + local;
+                    const long long g = pl.epochBase[epoch] + gl;
+                    if (S.patDone[p]) R.slotOn = false;
+                    if (!first) {
+                        const int* trOff = pl.trOff + pl.trBase[epoch - 1];
+                        const uint32_t* trEnt = pl.trEnt + pl.trEntBase[epoch - 1];
+                        const double* bo = S.bbuf + cp * SM::BSTRIDE + S.patOff[p];
+                        const int e0 = trOff[gl], e1 = trOff[gl + 1];
+                        double acc = 0.0;
+                        for (int q = e0; q < e1; ++q) {
+                            const uint32_t en = trEnt[q];
+                            const uint32_t widx = en >> 16;
+                            const double old = bo[en & 0xFFFFu];
+                            acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
+                        }
+                        R.bv = acc;
+                    } else {
+                        // the seed state m is the last one fillUp emits (all components at their maximum)
+                        R.bv = (tid + 1 == S.patOff2[p + 1]) ? 1.0 : 0.0;
+                    }
+                    const uint32_t mt = pl.meta[g];
+                    S.metaS[tid] = mt;
+                    n = (int)(mt & 0xFFu);
+                    R.unit = (mt & RC_META_UNIT) != 0;
+                    const uint16_t* rb = pl.rowBase + ((size_t)epoch * nFP + pat0 + p) * P;
+                    const int bBase = S.patOff2[p];
+#pragma unroll
+                    for (int d = 0; d < NNZ; ++d) {
+                        if (d < n) {
+                            const uint32_t w = pl.words[g * nnzw + d];
+                            const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                            const uint32_t up = w >> 16;
+                            R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
+                            if (up != RC_NO_UP) R.aB[d] = sBase + K::O_B + (unsigned)(bBase + (int)up) * 8u;
+                        }
+                    }
+                }
+                R.nw = __reduce_max_sync(0xFFFFFFFFu, n);
+                __syncthreads();                      // every gather has read the old layout
+                S.bbuf[tid] = R.bv;                   // new layout lives at parity 0
+                cp = 0;
+                if (tid <= np) S.patOff[tid] = S.patOff2[tid];
+                first = false;
+                rebuilt = true;
+                __syncthreads();
+            }
+            init = false;
+            if (!rebuilt) {                           // no event: only move b to parity 0 and refresh activity
+                S.bbuf[tid] = R.bv;
+                if (R.slotOn) {
+                    const int p = rc_find_owner(S.patOff, np, tid);
+                    if (S.patDone[p]) R.slotOn = false;
+                }
+            }
+            if (s >= nSteps) break;
+            // ---- stage the pairs of step s (shared memory, parity 0) and of step s+1 (prefetch set B) ----
+            const RcModelEpochDev mE = me[epoch];
+            const int rowPairs = pl.ep[epoch].rowPairs;
+            const int* fo = pl.fetchOff + (size_t)epoch * (pl.nFastBins + 1) + bin;
+            const int nFetch = fo[1] - fo[0];
+            R.fetchOn = tid < nFetch;
+            const int fOff = R.fetchOn ? pl.fetchRows[fo[0] + tid] : 0;
+            const double* row = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+            if (R.fetchOn) {
+                double g0, g1;
+                rc_ldg128(row, g0, g1);
+                S.RE[2 * tid] = g0;
+                S.RE[2 * tid + 1] = g1;
+                if (s + 1 < mE.end) rc_ldg128(row + (long long)rowPairs * 2, R.preB0, R.preB1);
+            }
+            R.fPtr = row + (long long)rowPairs * 4;
+            __syncthreads();
+        }
+        // ================================ fast path: two grid steps per trip ================================
+        int nextStop = nSteps;
+        if (sShort > s && sShort < nextStop) nextStop = sShort;
+        if (nextEvStep > s && nextEvStep < nextStop) nextStop = nextEvStep;
+        const long long strideD = (long long)pl.ep[epoch].rowPairs * 2;
+        for (;;) {
+            rc_key_step<NNZ, 0>(R, sBase, strideD, s + 2 < nextStop, s + 1 < nextStop);
+            ++s;
+            if (s == nextStop) { cp = 1; break; }
+            rc_key_step<NNZ, 1>(R, sBase, strideD, s + 2 < nextStop, s + 1 < nextStop);
+            ++s;
+            if (s == nextStop) { cp = 0; break; }
+        }
+        if (s >= nSteps && s != sShort) break;
+    }
+    // ---- getProb epilogue (Core.hs:49-54) ----
+    __syncthreads();
+    S.dslot[tid] = R.dacc;
+    __syncthreads();
+    if (tid < np) {
+        const int pid = S.patId[tid];
+        double d = S.dpat[tid];
+        if (S.patDone[tid] != 2) {
+            const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+            for (int i = 0; i < cnt; ++i)
+                if (S.metaS[base + i] & RC_META_UNIT) d = d + S.dslot[base + i];
+        }
+        double discFac = 1.0;
+        for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
+        pOut[(size_t)b * pl.nPat + pid] = d * models[b].theta * pl.combFac[pid] * discFac;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One block per model; fixed summation order (thread-strided partials, then a shared-memory tree),
 // so results are reproducible run to run.
 __global__ void __launch_bounds__(1024)
@@ -885,6 +1296,41 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
         case 128: return n4 ? rc_launch_fast_t<4, 128>(pl, m, sevs, tab, wpool, out, nB, st) : rc_launch_fast_t<8, 128>(pl, m, sevs, tab, wpool, out, nB, st);
         default: return n4 ? rc_launch_fast_t<4, 256>(pl, m, sevs, tab, wpool, out, nB, st) : rc_launch_fast_t<8, 256>(pl, m, sevs, tab, wpool, out, nB, st);
     }
+}
+
+cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
+                           const RcSEvDev* sevs, const RcSegDev* segs, const int* segOff, const double* dts, double* ktab,
+                           double* aEnd, double* aShort, int b0, int nB, cudaStream_t st) {
+    if (nB <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((nThr + 127) / 128), (unsigned)nB);
+    rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, segs, segOff + b0, dts, ktab, aEnd, aShort);
+    return cudaGetLastError();
+}
+
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, const RcModelDev* models, const RcModelEpochDev* mep,
+                                      const RcSEvDev* sevs, const double* ktab, const double* aShort, const double* wpool,
+                                      double* pOut, int b0, int nB, cudaStream_t st) {
+    if (pl.nFastBins <= 0 || nB <= 0) return cudaSuccess;
+    const size_t smem = (sizeof(RcKeySmem) + 15) & ~(size_t)15;
+    static bool c4 = false, c8 = false;
+    dim3 grid((unsigned)pl.nFastBins, (unsigned)nB);
+    double* out = pOut + (size_t)b0 * pl.nPat;
+    if (pl.nnzw <= 4) {
+        if (!c4) {
+            cudaError_t e = cudaFuncSetAttribute(rc_propagate_keyed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            c4 = true;
+        }
+        rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, mep, sevs, ktab, aShort, wpool, out);
+    } else {
+        if (!c8) {
+            cudaError_t e = cudaFuncSetAttribute(rc_propagate_keyed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            c8 = true;
+        }
+        rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, mep, sevs, ktab, aShort, wpool, out);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t rc_launch_reduce(const double* pOut, const long long* counts, const int* patGlobal,

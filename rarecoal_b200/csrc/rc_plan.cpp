@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <thread>
@@ -472,7 +474,188 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         }
         return (int)bins.size();
     };
-    out.nFastBins = pack(fastIds, fastBlock, maxPatFast, 2 * fastBlock - 2, out.fBinPatOff, out.fBinPats);
+    // ---- trajectory keys (see rc_plan.h): a_k(t) of a pattern depends only on the pattern's derived-allele counts
+    //      on the leaves merged into branch k so far, so it is computed once per distinct (branch, sub-tuple)
+    {
+        std::vector<uint32_t> leaf((size_t)P);
+        std::vector<char> dead((size_t)P, 0);
+        for (int k = 0; k < P; ++k) leaf[(size_t)k] = 1u << k;
+        out.keyId.assign((size_t)nEpochs * nPat * P, 0);
+        out.ep.assign((size_t)nEpochs, PlanHost::Epoch());
+        std::vector<int> prevKeyOff(1, 0);
+        for (int e = 0; e < nEpochs; ++e) {
+            if (e > 0) {
+                const StructEv& ev = sev[(size_t)e - 1];
+                leaf[(size_t)ev.k] |= leaf[(size_t)ev.l];
+                if (ev.type == RC_EV_JOIN_D) { leaf[(size_t)ev.l] = 0; dead[(size_t)ev.l] = 1; }
+            }
+            PlanHost::Epoch& E = out.ep[(size_t)e];
+            E.keyOff = (int)out.keyBranch.size();
+            std::unordered_map<std::string, int> ids;
+            std::string ks;
+            for (int i = 0; i < nPat; ++i) {
+                const int32_t* m = patterns + (size_t)i * P;
+                for (int k = 0; k < P; ++k) {
+                    ks.assign(1, (char)k);
+                    if (dead[(size_t)k]) ks.push_back((char)0xFF);
+                    else for (int q = 0; q < P; ++q) if ((leaf[(size_t)k] >> q) & 1u) ks.push_back((char)m[q]);
+                    auto it = ids.find(ks);
+                    int id;
+                    if (it == ids.end()) {
+                        id = (int)ids.size();
+                        ids.emplace(ks, id);
+                        out.keyBranch.push_back((uint8_t)k);
+                        out.keyMaxJ.push_back(0);
+                        int pa = -1, pb = -1, op = RC_KOP_COPY, init = 0;
+                        if (e == 0) { op = RC_KOP_INIT; init = nVec[k] - m[k]; }
+                        else {
+                            const StructEv& ev = sev[(size_t)e - 1];
+                            const int* prev = &out.keyId[((size_t)(e - 1) * nPat + i) * P];
+                            pa = prev[k];
+                            if (ev.type == RC_EV_JOIN_D) {
+                                if (k == ev.k) { op = RC_KOP_JOIN; pb = prev[ev.l]; }
+                                else if (k == ev.l) { op = RC_KOP_ZERO; }
+                            } else {
+                                if (k == ev.k) { op = RC_KOP_SPLIT_K; pb = prev[ev.l]; }
+                                else if (k == ev.l) { op = RC_KOP_SPLIT_L; }
+                            }
+                        }
+                        out.keyPa.push_back(pa);
+                        out.keyPb.push_back(pb);
+                        out.keyOp.push_back((uint8_t)op);
+                        out.keyInit.push_back(init);
+                    } else id = it->second;
+                    out.keyId[((size_t)e * nPat + i) * P + k] = id;
+                    uint8_t mxk = pps[(size_t)i].mx[(size_t)e * P + k];
+                    uint8_t& mj = out.keyMaxJ[(size_t)E.keyOff + id];
+                    if (mxk > mj) mj = mxk;
+                }
+            }
+            E.nKeys = (int)ids.size();
+            E.thrOff = (int)out.thrKey.size();
+            int pairs = 1;   // pair 0 of every step row is {dt, 0}
+            for (int q = 0; q < E.nKeys; ++q) {
+                int mj = out.keyMaxJ[(size_t)E.keyOff + q];
+                out.keyThrBase.push_back((int)out.thrKey.size() - E.thrOff);
+                out.keyPairBase.push_back(pairs);
+                pairs += mj;
+                for (int t = 0; t < std::max(1, mj); ++t) out.thrKey.push_back(q);
+            }
+            E.nThr = (int)out.thrKey.size() - E.thrOff;
+            E.rowPairs = pairs;
+        }
+        out.totalKeys = (int)out.keyBranch.size();
+        out.lastKeyId.assign(out.keyId.end() - (size_t)nPat * P, out.keyId.end());
+    }
+
+    // ---- fast-tier bins: patterns in lexicographic order (neighbours share trajectory keys), packed sequentially under
+    //      the slot / pattern / pair-row limits; per bin and epoch the de-duplicated list of pair rows to fetch
+    {
+        std::vector<int> order(fastIds);
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            const int32_t* x = patterns + (size_t)a * P;
+            const int32_t* y = patterns + (size_t)b * P;
+            for (int k = 0; k < P; ++k) if (x[k] != y[k]) return x[k] < y[k];
+            return a < b;
+        });
+        const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
+        out.fBinPatOff.assign(1, 0);
+        out.fBinPats.clear();
+        std::vector<std::unordered_map<int, int>> keyRows((size_t)nEpochs);   // key -> rows needed, current bin
+        std::vector<int> rowsUsed((size_t)nEpochs, 0), rowsSelf((size_t)nEpochs, 0);
+        int slots = 0, cnt = 0;
+        auto close_bin = [&]() {
+            if (cnt == 0) return;
+            out.fBinPatOff.push_back((int)out.fBinPats.size());
+            for (int e = 0; e < nEpochs; ++e) { keyRows[(size_t)e].clear(); rowsUsed[(size_t)e] = 0; rowsSelf[(size_t)e] = 0; }
+            slots = 0; cnt = 0;
+        };
+        for (int i : order) {
+            const PatPlan& pp = pps[(size_t)i];
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                bool fits = slots + pp.maxLive <= fastBlock && cnt + 1 <= maxPatFast;
+                std::vector<int> add((size_t)nEpochs, 0), addSelf((size_t)nEpochs, 0);
+                for (int e = 0; e < nEpochs && fits; ++e) {
+                    for (int k = 0; k < P; ++k) {
+                        int mxk = pp.mx[(size_t)e * P + k];
+                        if (!mxk) continue;
+                        addSelf[(size_t)e] += mxk;
+                        int key = out.keyId[((size_t)e * nPat + i) * P + k];
+                        auto it = keyRows[(size_t)e].find(key);
+                        int have = it == keyRows[(size_t)e].end() ? 0 : it->second;
+                        if (mxk > have) add[(size_t)e] += mxk - have;
+                    }
+                    fits = rowsUsed[(size_t)e] + add[(size_t)e] <= rowCap && rowsSelf[(size_t)e] + addSelf[(size_t)e] <= 2 * fastBlock - 2;
+                }
+                if (!fits && cnt > 0) { close_bin(); continue; }
+                for (int e = 0; e < nEpochs; ++e) {
+                    for (int k = 0; k < P; ++k) {
+                        int mxk = pp.mx[(size_t)e * P + k];
+                        if (!mxk) continue;
+                        int key = out.keyId[((size_t)e * nPat + i) * P + k];
+                        int& have = keyRows[(size_t)e][key];
+                        if (mxk > have) { rowsUsed[(size_t)e] += mxk - have; have = mxk; }
+                    }
+                    rowsSelf[(size_t)e] += addSelf[(size_t)e];
+                }
+                out.fBinPats.push_back(i);
+                slots += pp.maxLive;
+                ++cnt;
+                break;
+            }
+        }
+        close_bin();
+        out.nFastBins = (int)out.fBinPatOff.size() - 1;
+        // fetch lists and per-(pattern, branch) pair-row bases
+        const int nFP = (int)out.fBinPats.size();
+        out.fetchOff.assign((size_t)nEpochs * (out.nFastBins + 1), 0);
+        out.rowBase.assign((size_t)nEpochs * nFP * P, 0xFFFF);
+        for (int e = 0; e < nEpochs; ++e) {
+            const PlanHost::Epoch& E = out.ep[(size_t)e];
+            for (int bI = 0; bI < out.nFastBins; ++bI) {
+                out.fetchOff[(size_t)e * (out.nFastBins + 1) + bI] = (int)out.fetchRows.size();
+                std::unordered_map<int, int> rowsOf, startOf;
+                std::vector<int> keyOrder;
+                for (int q = out.fBinPatOff[(size_t)bI]; q < out.fBinPatOff[(size_t)bI + 1]; ++q) {
+                    int i = out.fBinPats[(size_t)q];
+                    for (int k = 0; k < P; ++k) {
+                        int mxk = pps[(size_t)i].mx[(size_t)e * P + k];
+                        if (!mxk) continue;
+                        int key = out.keyId[((size_t)e * nPat + i) * P + k];
+                        auto it = rowsOf.find(key);
+                        if (it == rowsOf.end()) { rowsOf.emplace(key, mxk); keyOrder.push_back(key); }
+                        else if (mxk > it->second) it->second = mxk;
+                    }
+                }
+                out.fetchRows.push_back(0);                 // smem pair row 0 <- {dt, 0}
+                int row = 1;
+                for (int key : keyOrder) {
+                    startOf[key] = row;
+                    int n = rowsOf[key];
+                    for (int j = 0; j < n; ++j) out.fetchRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
+                    row += n;
+                }
+                for (int q = out.fBinPatOff[(size_t)bI]; q < out.fBinPatOff[(size_t)bI + 1]; ++q) {
+                    int i = out.fBinPats[(size_t)q];
+                    for (int k = 0; k < P; ++k) {
+                        if (!pps[(size_t)i].mx[(size_t)e * P + k]) continue;
+                        int key = out.keyId[((size_t)e * nPat + i) * P + k];
+                        out.rowBase[((size_t)e * nFP + q) * P + k] = (uint16_t)startOf[key];
+                    }
+                }
+            }
+            out.fetchOff[(size_t)e * (out.nFastBins + 1) + out.nFastBins] = (int)out.fetchRows.size();
+        }
+        if (std::getenv("RC_PLAN_DEBUG")) {
+            for (int e = 0; e < nEpochs; ++e) {
+                const PlanHost::Epoch& E = out.ep[(size_t)e];
+                int f0 = out.fetchOff[(size_t)e * (out.nFastBins + 1)], f1 = out.fetchOff[(size_t)e * (out.nFastBins + 1) + out.nFastBins];
+                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d fetch rows/bin %.1f\n", e, E.nKeys, E.nThr,
+                             E.rowPairs, out.nFastBins ? (double)(f1 - f0) / out.nFastBins : 0.0);
+            }
+            std::fprintf(stderr, "[rc plan] fast bins %d (block %d), big bins %d (cap %d)\n", out.nFastBins, fastBlock, out.nBins, cap);
+        }
+    }
     out.nBins = pack(bigIds, cap, RC_NPB, 1 << 30, out.binPatOff, out.binPats);
     out.maxX.assign((size_t)nEpochs * nPat * P, 0);
     for (int e = 0; e < nEpochs; ++e)

@@ -50,6 +50,23 @@ struct PlanHost {
     int fastBlock = RC_BLOCK;              // 64, 128 or 256 state slots per fast-tier block
     std::vector<int> fBinPatOff, fBinPats; // fast tier bins
     std::vector<uint8_t> maxX;             // [nEpochs][nPat][P] largest x_k over the live states
+    // Trajectory keys.  The ancestral count a_k(t) of a pattern (updateA, Core.hs:229-240, and the a-part of
+    // Join/Split, Core.hs:165-170,195-200) is a function of the model and of the pattern's counts m on the leaves
+    // merged into branch k so far.  One key per distinct (epoch, branch, sub-tuple); the trajectory kernel computes
+    // each key once and all patterns sharing it read the result.
+    struct Epoch {
+        int nKeys = 0, nThr = 0, rowPairs = 0, keyOff = 0, thrOff = 0;
+    };
+    std::vector<Epoch> ep;                 // [nEpochs]
+    std::vector<uint8_t> keyBranch, keyMaxJ, keyOp;       // concatenated over epochs (Epoch::keyOff)
+    std::vector<int> keyPa, keyPb, keyInit, keyPairBase, keyThrBase;
+    std::vector<int> thrKey;               // trajectory-kernel thread -> key (Epoch::thrOff)
+    std::vector<int> keyId;                // [nEpochs][nPat][P] (host only)
+    std::vector<int> lastKeyId;            // [nPat][P] keys of the final epoch (shortcut reads a from them)
+    int totalKeys = 0;
+    std::vector<int> fetchOff;             // [nEpochs][nFastBins+1] -> fetchRows
+    std::vector<int> fetchRows;            // pair offsets inside a step row, one per shared-memory pair row
+    std::vector<uint16_t> rowBase;         // [nEpochs][fast pattern slot][P] first shared-memory pair row of (pattern, branch)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]
     std::vector<uint32_t> words, meta;

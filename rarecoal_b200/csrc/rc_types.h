@@ -14,6 +14,15 @@
 // event type codes (same values as RC_EV_JOIN / RC_EV_SPLIT in include/rarecoal_b200.h)
 #define RC_EV_JOIN_D 0
 #define RC_EV_SPLIT_D 1
+// keyed fast tier: shared-memory pair rows per parity (row 0 = {dt,0}, last row = {1,0} padding)
+#define RC_KROWS 256
+// how a trajectory key obtains its starting a from the previous epoch (popJoinA / popSplitA, Core.hs:165-170,195-200)
+#define RC_KOP_INIT 0        // a = n_k - m_k
+#define RC_KOP_COPY 1        // a = a[pa]
+#define RC_KOP_JOIN 2        // a = a[pb] + a[pa]           (pa: this branch, pb: the branch joined in)
+#define RC_KOP_ZERO 3        // a = 0                       (branch joined away)
+#define RC_KOP_SPLIT_K 4     // a = m * a[pb] + a[pa]
+#define RC_KOP_SPLIT_L 5     // a = (1 - m) * a[pa]
 #define RC_NPB 64            // patterns per bin (block) at most
 
 // Packed per-slot dimension entry: one per non-zero component x_k of a live state x.
@@ -58,6 +67,33 @@ struct RcPlanDev {
     const double* combFac;       // [nPat]  prod choose(n_k, m_k)   (Core.hs:49)
     const uint8_t* support;      // [nPat][P] 1 where m_k > 0        (Core.hs:50-52)
     const int32_t* patGlobal;    // [nPat] index in the caller's pattern order
+    // ---- trajectory keys (keyed fast tier) ----
+    const struct RcEpochDev* ep; // [nEpochs]
+    int totalKeys, nKeysLast;
+    const uint8_t* keyBranch;    // per key (concatenated over epochs, RcEpochDev::keyOff)
+    const uint8_t* keyMaxJ;      // pairs of the key = largest x_k any pattern with this key reaches in the epoch
+    const uint8_t* keyOp;        // RC_KOP_*
+    const int* keyPa;            // parent keys in the previous epoch (-1: none)
+    const int* keyPb;
+    const int* keyInit;          // n_k - m_k for RC_KOP_INIT
+    const int* keyPairBase;      // first pair of the key inside a step row (pair 0 of every row is {dt, 0})
+    const int* keyThrBase;       // first trajectory-kernel thread of the key
+    const int* thrKey;           // trajectory-kernel thread -> key (RcEpochDev::thrOff)
+    const int* lastKeyId;        // [nPat][P] keys of the final epoch
+    const int* fetchOff;         // [nEpochs][nFastBins+1] -> fetchRows
+    const int* fetchRows;        // pair offset inside a step row for every shared-memory pair row of a bin
+    const uint16_t* rowBase;     // [nEpochs][fast pattern slot][P] first shared-memory pair row of (pattern, branch)
+};
+
+struct RcEpochDev {
+    int nKeys, nThr, rowPairs, keyOff, thrOff;
+};
+
+// Per (model, epoch): grid steps [beg, end) executed in that epoch and where its first step row starts in the
+// trajectory table (in pairs).
+struct RcModelEpochDev {
+    int beg, end;
+    long long tabBase;
 };
 
 // Structural event as executed by the kernel.
@@ -77,11 +113,16 @@ struct RcModelDev {
     int nSEv;
     int sevOff;        // first structural event of this model in the pooled RcSEvDev array
     int rowsAvail;     // table rows computed for this model
-    int pad;
+    int pad;           // caller's model index
+    int mode;          // 0: self-contained tiers only; 1: fast-tier patterns use the keyed kernel
+    int mepOff;        // first RcModelEpochDev of this model
+    long long aEndOff; // offset (doubles) of this model's per-key end-of-epoch a values
+    long long aShortOff; // offset (doubles) of this model's per-key a at the shortcut step (final epoch keys)
     long long tabOff;  // offset (doubles) of row 0 in the table pool
     long long wPool;   // offset (doubles) of split weight tables in the weight pool
     double theta;
     double disc[RC_MAX_P];
+    double Nshort[RC_MAX_P];   // population sizes at the shortcut step
 };
 
 // Piecewise-constant (popSize, freeze) segments used by the table kernel.

@@ -15,9 +15,11 @@ PROB_RTOL = 1e-10
 LOGL_RTOL = 1e-9
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["keyed", "selfcontained"])
+def eng(request):
+    # both fast-tier code paths: trajectory-key kernels (default) and the self-contained kernel
     e = R.Engine(0)
+    e.set_option("keyed", 1.0 if request.param == "keyed" else 0.0)
     yield e
     e.close()
 
