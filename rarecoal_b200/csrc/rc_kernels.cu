@@ -871,13 +871,14 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
 // rc_propagate_keyed_kernel — the state side.  One live state per thread; per non-zero component one LDS.128 of the
 // pair {G, E2}, one multiply into the decay factor, one LDS.64 of the neighbour and one FMA:
 //     b'(x) = b(x) * prod_k G_k(x_k) + sum_k b(x + e_k) E2_k(x_k)            (Core.hs:259)
-// Pairs of the bin's keys are staged from the trajectory table into shared memory two steps ahead by the first
-// lanes of the block (one pair row per lane); one barrier per grid step; the time loop is unrolled by two so that
-// buffer parities are immediates.
+// The pairs of the bin's keys are staged from the trajectory table into an RC_KDEPTH-deep shared-memory ring with
+// cp.async (one 16-byte pair row per lane, RC_KDEPTH-1 grid steps ahead); one barrier per grid step; the time loop is
+// specialised per number of components and unrolled by the ring depth so that every buffer offset is an immediate.
+#define RC_KDEPTH 8
 struct RcKeySmem {
     static constexpr int BSTRIDE = RC_BLOCK + 8;       // entry RC_BLOCK of each b buffer is the always-zero neighbour
     double bbuf[2 * BSTRIDE];
-    double RE[2 * 2 * RC_KROWS];                       // [parity][row]{G, E2}; row 0 = {dt, 0}; last row = {1, 0}
+    double RE[RC_KDEPTH * 2 * RC_KROWS];               // [slot][row]{G, E2}; row 0 = {dt, 0}; last row = {1, 0}
     double dslot[RC_BLOCK];
     double dpat[RC_NPB];
     uint32_t metaS[RC_BLOCK];
@@ -888,7 +889,7 @@ struct RcKeySmem {
 };
 struct RcKeyK {
     static constexpr unsigned B_PAR = RcKeySmem::BSTRIDE * 8u;
-    static constexpr unsigned RE_PAR = RC_KROWS * 16u;
+    static constexpr unsigned RE_SLOT = RC_KROWS * 16u;
     static constexpr unsigned RE_PAD = (RC_KROWS - 1) * 16u;
     static constexpr unsigned O_B = (unsigned)offsetof(RcKeySmem, bbuf);
     static constexpr unsigned O_RE = (unsigned)offsetof(RcKeySmem, RE);
@@ -897,66 +898,61 @@ struct RcKeyK {
 
 template <int NNZ>
 struct RcKeyRegs {
-    unsigned aRE[NNZ], aB[NNZ];   // absolute shared addresses at parity 0
+    unsigned aRE[NNZ], aB[NNZ];   // absolute shared addresses (ring slot 0 / b parity 0)
     int nw;
     bool unit, slotOn, fetchOn;
     double bv, dacc;
-    double preA0, preA1, preB0, preB1;   // two prefetch register sets (pairs of step s+1 / s+2)
-    const double* fPtr;           // this lane's pair in the step row being prefetched
+    const double* fPtr;           // this lane's pair in the step row to be copied next
 };
 
-__device__ __forceinline__ void rc_ldg128(const double* p, double& a, double& b) {
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+__device__ __forceinline__ void rc_cp_async16(unsigned dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void rc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rc_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NNZ, int N, int PH>
-__device__ __forceinline__ void rc_key_dims(const RcKeyRegs<NNZ>& R, double& D, double& t2) {
+// Grid steps s .. nextStop-1 for a warp whose states have at most N non-zero components.  Returns the parity of the
+// b buffer that holds the result.
+template <int NNZ, int N>
+__device__ __forceinline__ int rc_key_run(RcKeyRegs<NNZ>& R, const unsigned sBase, const long long strideD, int& s,
+                                          const int nextStop) {
     typedef RcKeyK K;
-    double g, e2;
-    rc_lds128(R.aRE[0] + PH * K::RE_PAR, g, e2);
-    D = g;
-    t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
+    const unsigned myRE = sBase + K::O_RE + threadIdx.x * 16u;
+    const unsigned myB = sBase + K::O_B + threadIdx.x * 8u;
+    for (;;) {
 #pragma unroll
-    for (int d = 1; d < N; ++d) {
-        rc_lds128(R.aRE[d] + PH * K::RE_PAR, g, e2);
-        D *= g;
-        t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
-    }
-}
-
-template <int NNZ, int PH>
-__device__ __forceinline__ void rc_key_step(RcKeyRegs<NNZ>& R, const unsigned sBase, const long long strideD,
-                                            const bool doPre, const bool doStore) {
-    typedef RcKeyK K;
-    constexpr int QH = PH ^ 1;
-    // pairs of step s+2 -> register set PH (set QH holds step s+1, loaded one step ago)
-    if (doPre && R.fetchOn) {
-        if (PH == 0) rc_ldg128(R.fPtr, R.preA0, R.preA1);
-        else rc_ldg128(R.fPtr, R.preB0, R.preB1);
-    }
-    R.fPtr += strideD;
-    if (R.slotOn) {
-        double D = 1.0, t2 = 0.0;
-        switch (R.nw) {
-            case 1: rc_key_dims<NNZ, 1, PH>(R, D, t2); break;
-            case 2: rc_key_dims<NNZ, 2, PH>(R, D, t2); break;
-            case 3: rc_key_dims<NNZ, (NNZ >= 3 ? 3 : NNZ), PH>(R, D, t2); break;
-            case 4: rc_key_dims<NNZ, (NNZ >= 4 ? 4 : NNZ), PH>(R, D, t2); break;
-            case 5: rc_key_dims<NNZ, (NNZ >= 5 ? 5 : NNZ), PH>(R, D, t2); break;
-            case 6: rc_key_dims<NNZ, (NNZ >= 6 ? 6 : NNZ), PH>(R, D, t2); break;
-            case 7: rc_key_dims<NNZ, (NNZ >= 7 ? 7 : NNZ), PH>(R, D, t2); break;
-            case 8: rc_key_dims<NNZ, (NNZ >= 8 ? 8 : NNZ), PH>(R, D, t2); break;
-            default: break;
+        for (int u = 0; u < RC_KDEPTH; ++u) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int PH = u & 1, QH = PH ^ 1;
+            const unsigned slot = (unsigned)u * K::RE_SLOT;
+            // pairs of step s + DEPTH - 1 -> ring slot (u - 1) mod DEPTH (read one step ago)
+            if (R.fetchOn && s + RC_KDEPTH - 1 < nextStop)
+                rc_cp_async16(myRE + (unsigned)((u + RC_KDEPTH - 1) % RC_KDEPTH) * K::RE_SLOT, R.fPtr);
+            rc_cp_commit();
+            R.fPtr += strideD;
+            if (R.slotOn) {
+                double g, e2;
+                rc_lds128(R.aRE[0] + slot, g, e2);
+                double D = g;
+                double t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
+#pragma unroll
+                for (int d = 1; d < N; ++d) {
+                    rc_lds128(R.aRE[d] + slot, g, e2);
+                    D *= g;
+                    t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
+                }
+                R.bv = fma(R.bv, D, t2);                                               // updateB, Core.hs:259
+                rc_sts64(myB + QH * K::B_PAR, R.bv);
+                if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.bv, R.dacc);   // updateD, Core.hs:282-288
+            }
+            rc_cp_wait<RC_KDEPTH - 2>();       // the pairs of step s+1 have landed
+            __syncthreads();
+            ++s;
+            if (s == nextStop) return QH;
         }
-        R.bv = fma(R.bv, D, t2);                                     // updateB, Core.hs:259
-        rc_sts64(sBase + K::O_B + QH * K::B_PAR + threadIdx.x * 8u, R.bv);
-        if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + PH * K::RE_PAR), R.bv, R.dacc);   // updateD, Core.hs:282-288
     }
-    if (doStore && R.fetchOn) {
-        if (PH == 0) rc_sts128(sBase + K::O_RE + QH * K::RE_PAR + threadIdx.x * 16u, R.preB0, R.preB1);
-        else rc_sts128(sBase + K::O_RE + QH * K::RE_PAR + threadIdx.x * 16u, R.preA0, R.preA1);
-    }
-    __syncthreads();
 }
 
 template <int NNZ>
@@ -987,7 +983,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
 #pragma unroll
     for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
     R.nw = 0; R.unit = false; R.slotOn = false; R.fetchOn = false;
-    R.bv = 0.0; R.dacc = 0.0; R.preA0 = R.preA1 = R.preB0 = R.preB1 = 0.0;
+    R.bv = 0.0; R.dacc = 0.0;
     R.fPtr = ktab;
 
     if (tid < np) {
@@ -995,8 +991,9 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
         S.patDone[tid] = 0;
         S.dpat[tid] = 0.0;
     }
-    if (tid < 4) S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;   // {1,0} padding pairs
-    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                                               // zero neighbours
+    if (tid < 2 * RC_KDEPTH)                                                   // {1,0} padding pair of every ring slot
+        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
+    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                   // zero neighbours
     __syncthreads();
 
     int epoch = 0, nextEv = 0;
@@ -1007,10 +1004,11 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
 
     for (;;) {
         // ================= slow path: shortcut test, structural events, epoch set-up =================
-        // On exit everything is normalised to parity 0: b in bbuf[0], pairs of step s in RE[0], pairs of step
-        // s+1 in prefetch set B, fPtr at step s+2.
+        // On exit everything is normalised: b in bbuf[0], pairs of steps s .. s+DEPTH-2 in (or on their way to) ring
+        // slots 0 .. DEPTH-2, fPtr at step s+DEPTH-1.
         {
             const int nnzw = pl.nnzw, nPat = pl.nPat;
+            rc_cp_wait<0>();
             S.dslot[tid] = R.dacc;
             R.dacc = 0.0;
             __syncthreads();
@@ -1139,41 +1137,46 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
                     if (S.patDone[p]) R.slotOn = false;
                 }
             }
+            if (R.nw < 1) R.nw = 1;
             if (s >= nSteps) break;
-            // ---- stage the pairs of step s (shared memory, parity 0) and of step s+1 (prefetch set B) ----
+        }
+        int nextStop = nSteps;
+        if (sShort > s && sShort < nextStop) nextStop = sShort;
+        if (nextEvStep > s && nextEvStep < nextStop) nextStop = nextEvStep;
+        {
+            // ---- start the ring: pairs of steps s .. s+DEPTH-2 into slots 0 .. DEPTH-2 ----
             const RcModelEpochDev mE = me[epoch];
             const int rowPairs = pl.ep[epoch].rowPairs;
             const int* fo = pl.fetchOff + (size_t)epoch * (pl.nFastBins + 1) + bin;
             const int nFetch = fo[1] - fo[0];
             R.fetchOn = tid < nFetch;
             const int fOff = R.fetchOn ? pl.fetchRows[fo[0] + tid] : 0;
-            const double* row = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
-            if (R.fetchOn) {
-                double g0, g1;
-                rc_ldg128(row, g0, g1);
-                S.RE[2 * tid] = g0;
-                S.RE[2 * tid + 1] = g1;
-                if (s + 1 < mE.end) rc_ldg128(row + (long long)rowPairs * 2, R.preB0, R.preB1);
+            R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+            const long long strideD = (long long)rowPairs * 2;
+#pragma unroll
+            for (int u = 0; u < RC_KDEPTH - 1; ++u) {
+                if (R.fetchOn && s + u < nextStop) rc_cp_async16(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr);
+                rc_cp_commit();
+                R.fPtr += strideD;
             }
-            R.fPtr = row + (long long)rowPairs * 4;
+            rc_cp_wait<RC_KDEPTH - 2>();
             __syncthreads();
-        }
-        // ================================ fast path: two grid steps per trip ================================
-        int nextStop = nSteps;
-        if (sShort > s && sShort < nextStop) nextStop = sShort;
-        if (nextEvStep > s && nextEvStep < nextStop) nextStop = nextEvStep;
-        const long long strideD = (long long)pl.ep[epoch].rowPairs * 2;
-        for (;;) {
-            rc_key_step<NNZ, 0>(R, sBase, strideD, s + 2 < nextStop, s + 1 < nextStop);
-            ++s;
-            if (s == nextStop) { cp = 1; break; }
-            rc_key_step<NNZ, 1>(R, sBase, strideD, s + 2 < nextStop, s + 1 < nextStop);
-            ++s;
-            if (s == nextStop) { cp = 0; break; }
+            // ================================ fast path ================================
+            switch (R.nw) {
+                case 1: cp = rc_key_run<NNZ, 1>(R, sBase, strideD, s, nextStop); break;
+                case 2: cp = rc_key_run<NNZ, 2>(R, sBase, strideD, s, nextStop); break;
+                case 3: cp = rc_key_run<NNZ, (NNZ >= 3 ? 3 : NNZ)>(R, sBase, strideD, s, nextStop); break;
+                case 4: cp = rc_key_run<NNZ, (NNZ >= 4 ? 4 : NNZ)>(R, sBase, strideD, s, nextStop); break;
+                case 5: cp = rc_key_run<NNZ, (NNZ >= 5 ? 5 : NNZ)>(R, sBase, strideD, s, nextStop); break;
+                case 6: cp = rc_key_run<NNZ, (NNZ >= 6 ? 6 : NNZ)>(R, sBase, strideD, s, nextStop); break;
+                case 7: cp = rc_key_run<NNZ, (NNZ >= 7 ? 7 : NNZ)>(R, sBase, strideD, s, nextStop); break;
+                default: cp = rc_key_run<NNZ, NNZ>(R, sBase, strideD, s, nextStop); break;
+            }
         }
         if (s >= nSteps && s != sShort) break;
     }
     // ---- getProb epilogue (Core.hs:49-54) ----
+    rc_cp_wait<0>();
     __syncthreads();
     S.dslot[tid] = R.dacc;
     __syncthreads();
