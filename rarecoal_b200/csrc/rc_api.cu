@@ -475,7 +475,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     double* hW = (double*)(hb + oW);
     RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
     size_t mepPos = 0;
-    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0;
+    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0;
     const long long ktabModelMax = (long long)(ctx->optKtabModelMB * 1048576.0 / 16.0);
     const long long ktabTotalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
 
@@ -511,6 +511,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
                 if (me.end < me.beg) me.end = me.beg;
                 me.tabBase = ktabPairs + pairs;
                 pairs += (long long)(me.end - me.beg) * hp.ep[(size_t)e].rowPairs;
+                maxRowPairs = std::max<long long>(maxRowPairs, hp.ep[(size_t)e].rowPairs);
             }
             M.mode = (ctx->optKeyed && hp.nFastBins > 0 && pairs <= ktabModelMax && ktabPairs + pairs <= ktabTotalMax) ? 1 : 0;
             if (M.mode == 1) {
@@ -571,7 +572,8 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     {
         size_t needTab = (size_t)std::max<long long>(tabDoubles, 1) * sizeof(double);
         size_t needOut = (size_t)B * std::max(ctx->nPat, 1) * sizeof(double);
-        size_t needK = (size_t)std::max<long long>(ktabPairs, 1) * 16;
+        // the keyed kernel prefetches up to 8 step rows past the end of an epoch: keep that much slack
+        size_t needK = (size_t)(std::max<long long>(ktabPairs, 1) + 8 * maxRowPairs + 64) * 16;
         size_t needA = (size_t)std::max<long long>(aEndDoubles, 1) * sizeof(double);
         size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
         if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap || needK > ctx->dKTab.cap || needA > ctx->dAEnd.cap ||

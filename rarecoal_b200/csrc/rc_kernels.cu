@@ -908,9 +908,45 @@ struct RcKeyRegs {
 __device__ __forceinline__ void rc_cp_async16(unsigned dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// predicated form: no branch around the copy
+__device__ __forceinline__ void rc_cp_async16_if(unsigned dst, const double* src, unsigned pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"(pred)
+                 : "memory");
+}
 __device__ __forceinline__ void rc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void rc_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One grid step of the keyed kernel; ring slot U (compile time), b parity U & 1.
+template <int NNZ, int N, int U>
+__device__ __forceinline__ void rc_key_step(RcKeyRegs<NNZ>& R, const unsigned sBase, const unsigned myRE, const unsigned myB,
+                                            const long long strideD, const unsigned fetchPred, const bool warpOn) {
+    typedef RcKeyK K;
+    constexpr int PH = U & 1, QH = PH ^ 1;
+    constexpr unsigned slot = (unsigned)U * K::RE_SLOT;
+    // pairs of step s + DEPTH - 1 -> ring slot (U - 1) mod DEPTH (read one step ago).  Steps past the end of the epoch
+    // read rows that are never used (the table carries RC_KDEPTH rows of slack).
+    rc_cp_async16_if(myRE + (unsigned)((U + RC_KDEPTH - 1) % RC_KDEPTH) * K::RE_SLOT, R.fPtr, fetchPred);
+    rc_cp_commit();
+    R.fPtr += strideD;
+    if (warpOn) {      // warp-uniform; lanes without a state run on the padding pair / zero neighbour and keep b = 0
+        double g, e2;
+        rc_lds128(R.aRE[0] + slot, g, e2);
+        double D = g;
+        double t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
+#pragma unroll
+        for (int d = 1; d < N; ++d) {
+            rc_lds128(R.aRE[d] + slot, g, e2);
+            D *= g;
+            t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
+        }
+        R.bv = fma(R.bv, D, t2);                                               // updateB, Core.hs:259
+        rc_sts64(myB + QH * K::B_PAR, R.bv);
+        if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.bv, R.dacc);   // updateD, Core.hs:282-288
+    }
+    rc_cp_wait<RC_KDEPTH - 2>();       // the pairs of the next step have landed
+    __syncthreads();
+}
 
 // Grid steps s .. nextStop-1 for a warp whose states have at most N non-zero components.  Returns the parity of the
 // b buffer that holds the result.
@@ -920,39 +956,31 @@ __device__ __forceinline__ int rc_key_run(RcKeyRegs<NNZ>& R, const unsigned sBas
     typedef RcKeyK K;
     const unsigned myRE = sBase + K::O_RE + threadIdx.x * 16u;
     const unsigned myB = sBase + K::O_B + threadIdx.x * 8u;
-    for (;;) {
-#pragma unroll
-        for (int u = 0; u < RC_KDEPTH; ++u) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int PH = u & 1, QH = PH ^ 1;
-            const unsigned slot = (unsigned)u * K::RE_SLOT;
-            // pairs of step s + DEPTH - 1 -> ring slot (u - 1) mod DEPTH (read one step ago)
-            if (R.fetchOn && s + RC_KDEPTH - 1 < nextStop)
-                rc_cp_async16(myRE + (unsigned)((u + RC_KDEPTH - 1) % RC_KDEPTH) * K::RE_SLOT, R.fPtr);
-            rc_cp_commit();
-            R.fPtr += strideD;
-            if (R.slotOn) {
-                double g, e2;
-                rc_lds128(R.aRE[0] + slot, g, e2);
-                double D = g;
-                double t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
-#pragma unroll
-                for (int d = 1; d < N; ++d) {
-                    rc_lds128(R.aRE[d] + slot, g, e2);
-                    D *= g;
-                    t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
-                }
-                R.bv = fma(R.bv, D, t2);                                               // updateB, Core.hs:259
-                rc_sts64(myB + QH * K::B_PAR, R.bv);
-                if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.bv, R.dacc);   // updateD, Core.hs:282-288
-            }
-            rc_cp_wait<RC_KDEPTH - 2>();       // the pairs of step s+1 have landed
-            __syncthreads();
-            ++s;
-            if (s == nextStop) return QH;
-        }
+    const unsigned fetchPred = R.fetchOn ? 1u : 0u;
+    const bool warpOn = __any_sync(0xFFFFFFFFu, R.slotOn);
+    const int s0 = s;
+    // whole ring turns without exit tests
+    while (s + RC_KDEPTH <= nextStop) {
+        rc_key_step<NNZ, N, 0>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 1>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 2>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 3>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 4>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 5>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 6>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        rc_key_step<NNZ, N, 7>(R, sBase, myRE, myB, strideD, fetchPred, warpOn);
+        s += RC_KDEPTH;
     }
+    static_assert(RC_KDEPTH == 8, "the unrolled ring turn above assumes a depth of 8");
+    // remainder (< DEPTH steps)
+    if (s < nextStop) { rc_key_step<NNZ, N, 0>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 1>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 2>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 3>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 4>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 5>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    if (s < nextStop) { rc_key_step<NNZ, N, 6>(R, sBase, myRE, myB, strideD, fetchPred, warpOn); ++s; }
+    return (s - s0) & 1;
 }
 
 template <int NNZ>
@@ -1134,7 +1162,12 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
                 S.bbuf[tid] = R.bv;
                 if (R.slotOn) {
                     const int p = rc_find_owner(S.patOff, np, tid);
-                    if (S.patDone[p]) R.slotOn = false;
+                    if (S.patDone[p]) {               // pattern took the shortcut: park the lane on the padding pair
+                        R.slotOn = false;
+                        R.unit = false;
+#pragma unroll
+                        for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+                    }
                 }
             }
             if (R.nw < 1) R.nw = 1;
@@ -1155,7 +1188,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
             const long long strideD = (long long)rowPairs * 2;
 #pragma unroll
             for (int u = 0; u < RC_KDEPTH - 1; ++u) {
-                if (R.fetchOn && s + u < nextStop) rc_cp_async16(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr);
+                rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
                 rc_cp_commit();
                 R.fPtr += strideD;
             }
