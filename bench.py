@@ -33,6 +33,15 @@ sys.path.insert(0, ROOT)
 
 P_C3, MAXAF_C3 = 8, 10
 FLOPS_PER_STATE_STEP = 4 * P_C3 + 27
+def _traffic():
+    """dram read+write bytes of one rc_propagate_keyed_kernel launch from the committed ncu capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_keyed_traffic.json")))
+    except Exception:
+        return None
+
+
+TRAFFIC = _traffic()
 METRIC = "logl_evals_per_sec"
 UNIT = "logl evals/s"
 WORKLOAD = "C3: synthetic 8-pop balanced tree, maxAf=10, 43757 patterns, nVec=[100]*8, 3043-step grid"
@@ -112,7 +121,7 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    sample_every = 16
+    sample_every = 2
     for i in range(args.warmup + args.steps):
         v, cores, dt, sample = cpu_baseline_run(sample_every)
         if i >= args.warmup:
@@ -208,7 +217,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches, w_steps = [], 0, 0
+    kernel_ms, traj_ms, launches, w_steps = [], [], 0, 0
     barrier()
     e0.record(stream)
     for i in range(args.warmup, n_it):
@@ -221,7 +230,8 @@ def main():
         step_device(i)
         torch.cuda.synchronize()
         st = eng.stats()
-        kernel_ms.append(st["kernel_ms"])
+        kernel_ms.append(st["kernel_ms"] - st["traj_ms"])
+        traj_ms.append(st["traj_ms"])
         launches += st["launches"] + (1 if world > 1 else 0)
         w_steps = st["state_steps"]
     # ---- end-to-end timing (host buffers in, host logl out) ---------------------------------------------------
@@ -238,8 +248,20 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert last is not None and np.all(np.isfinite(last))
+    # single-model latency through the host-buffer call (what `rarecoal logl` would see), rank 0 / 1 GPU only
+    lat_ms = None
+    if world == 1:
+        ev1 = R.api._events_array(batches[0][0])
+        off1 = np.array([0, len(batches[0][0])], dtype=np.int32)
+        for _ in range(3):
+            eng.eval_raw(ev1, off1, np.full(1, 0.0005), np.ones(P_C3), False, 1.0)
+        t1 = time.perf_counter()
+        for _ in range(10):
+            eng.eval_raw(ev1, off1, np.full(1, 0.0005), np.ones(P_C3), False, 1.0)
+        lat_ms = (time.perf_counter() - t1) * 100.0
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
+    traj_mean = float(np.mean(traj_ms))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, k_ms = (float(v) for v in t.cpu())
@@ -256,21 +278,23 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": B,
                        "parallelism": f"patterns sharded over {world} rank(s), all-reduce of 2*B doubles",
-                       "l2": "fresh parameter batch each step; per-step tables (B x 441 x 840 B) are rewritten every step",
+                       "l2": "fresh parameter batch each step; the trajectory tables (~60 MB per model, larger than L2 for the "
+                             "batch) are rewritten by rc_traj_kernel every step",
+                       "single_logl_latency_ms": lat_ms,
                        "pattern_probs_per_sec": value * len(pats),
                        "state_steps_per_sec": float(w_total.item()) * args.steps / (dev_ms * 1e-3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "rc_propagate_kernel", "kernel_ms": k_ms,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": TRAFFIC,
+                         "kernel": "rc_propagate_keyed_kernel", "kernel_ms": k_ms, "traj_kernels_ms": traj_mean,
                          "algorithmic": f"{w_steps} state-steps x {FLOPS_PER_STATE_STEP} flops per launch (rank 0)",
                          "peak_source": "rc_fp64_peak DFMA microbenchmark on this GPU (no FP64 figure in MEASURED_PEAKS.json)",
                          "hbm_note": "algorithmic HBM bytes ~24 B x patterns x models per launch: not the bound"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            v, cores, dt, sample = cpu_baseline_run(8)
+            v, cores, dt, sample = cpu_baseline_run(1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "seconds": dt}
         print(json.dumps(line))

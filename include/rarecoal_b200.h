@@ -56,7 +56,8 @@ typedef struct {
 typedef struct {
     int64_t state_steps;     /* executed b(x) updates over all models (SURVEY.md §8d unit, Core.hs:248) */
     int64_t slots;           /* live states resident at t=0 over all models                            */
-    double kernel_ms;        /* CUDA-event time of the propagation kernel(s) on the eval stream         */
+    double kernel_ms;        /* CUDA-event time of trajectory + propagation kernels on the eval stream   */
+    double traj_ms;          /* of which: trajectory kernels (first plan group)                          */
     double tables_ms;        /* CUDA-event time of the per-model table kernel                           */
     double total_ms;         /* CUDA-event time first launch -> last launch of the call                 */
     int32_t launches;        /* kernels launched by the call                                            */
@@ -156,6 +157,10 @@ int rc_validate_model(int P, const double* disc, const rc_event* ev, int nEv, ch
 double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv);
 /* choose n k (Utils.hs:208-210).                                                                   */
 double rc_choose(int n, int k);
+
+/* The pattern indices rc_set_shard(rank, world) assigns to `rank` (host only): returns the count, fills out up to cap.
+ * Shards of all ranks are disjoint and cover every pattern.                                                     */
+int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int world, int32_t* out, int cap);
 
 /* Runs the host planner only (no device): executed state-steps (one unit = one iteration of the
  * updateB loop, Core.hs:248), live states at t=0, largest live set of a pattern, structural epochs and

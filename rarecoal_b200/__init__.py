@@ -6,6 +6,6 @@ from .api import (Engine, Join, JointStateSpace, ModelEvent, ModelSpec, Rarecoal
                   RarecoalDeviceError, RarecoalException, RarecoalHistogramException, RarecoalModelException,
                   SetFreeze, SetPopSize, SpectrumEntry, Split, choose, computeAllConfigs,
                   computeLogLikelihoodFromSpec, computeStandardOrder, defaultTimes, getRegularizationPenalty,
-                  getTimeSteps, makeJointStateSpace, planStats, validateModel)
+                  getTimeSteps, makeJointStateSpace, planStats, shardPatterns, validateModel)
 
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ class rc_event(C.Structure):
 
 class rc_stats(C.Structure):
     _fields_ = [("state_steps", C.c_int64), ("slots", C.c_int64), ("kernel_ms", C.c_double),
-                ("tables_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32),
+                ("traj_ms", C.c_double), ("tables_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32),
                 ("plan_cache_hit", C.c_int32), ("n_epochs", C.c_int32), ("n_steps", C.c_int32)]
 
 
@@ -44,6 +44,7 @@ SIGNATURES = {
     "rc_validate_model": (C.c_int, [C.c_int, _dp, _evp, C.c_int, C.c_char_p, C.c_int]),
     "rc_reg_penalty": (C.c_double, [C.c_int, C.c_double, _evp, C.c_int]),
     "rc_choose": (C.c_double, [C.c_int, C.c_int]),
+    "rc_shard_patterns": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.c_int, _ip, C.c_int]),
     "rc_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp, _evp, C.c_int, C.c_int,
                                 _lp, _lp, _ip, _ip, _ip]),
     "rc_ss_create": (_vp, [C.c_int, C.c_int]),

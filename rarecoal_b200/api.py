@@ -192,6 +192,16 @@ def getRegularizationPenalty(modelSpec: ModelSpec):
     return L.load().rc_reg_penalty(modelSpec.mNrPops, modelSpec.mPopSizeRegularization, ev, len(modelSpec.mEvents))
 
 
+def shardPatterns(patterns, rank, world):
+    """Pattern indices that Engine.set_shard(rank, world) evaluates on `rank` (host only)."""
+    pats = _i32(patterns)
+    out = np.zeros(len(pats), dtype=np.int32)
+    n = L.load().rc_shard_patterns(pats.shape[1], len(pats), _ip(pats), int(rank), int(world), _ip(out), len(out))
+    if n < 0:
+        raise ValueError("rc_shard_patterns: bad arguments")
+    return out[:n]
+
+
 def planStats(nVec, maxAf, patterns, times, events, noShortcut=False):
     """Host planner only (no device): dict(state_steps, slots0, max_live, n_epochs, n_bins)."""
     pats = _i32(patterns); nv = _i32(nVec); t = _f64(times)

@@ -142,7 +142,8 @@ struct rc_ctx {
     double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
     PinBuf hBlob, hOut;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool trajTimed = false;
     bool statsPending = false;
     bool blobInFlight = false;
     rc_stats stats;
@@ -606,6 +607,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         ++launches;
     }
     CK(cudaEventRecord(ctx->evt[2], st));
+    ctx->trajTimed = false;
     for (int pos = 0; pos < B;) {
         const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
         int end = pos + 1;
@@ -614,11 +616,14 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
             bool anyKeyed = false, anySelf = false;
             for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
             if (pe->d.nFastBins > 0 && anyKeyed) {
+                const bool timeIt = !ctx->trajTimed;      // trajectory kernels of the first plan group are timed
+                if (timeIt) CK(cudaEventRecord(ctx->evt[6], st));
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, dSegs, dSegOff, (const double*)ctx->dDts.p,
                                       (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, st));
                     ++launches;
                 }
+                if (timeIt) { CK(cudaEventRecord(ctx->evt[7], st)); ctx->trajTimed = true; }
                 CK(rc_launch_propagate_keyed(pe->d, dM, dMep, dSev, (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW,
                                              (double*)ctx->dPOut.p, pos, end - pos, st));
                 ++launches;
@@ -650,29 +655,36 @@ int collect_stats(rc_ctx* ctx) {
     CK(cudaEventSynchronize(ctx->evt[4]));
     CK(cudaEventElapsedTime(&ms, ctx->evt[1], ctx->evt[2])); ctx->stats.tables_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->evt[2], ctx->evt[3])); ctx->stats.kernel_ms = ms;
+    ctx->stats.traj_ms = 0.0;
+    if (ctx->trajTimed) { CK(cudaEventElapsedTime(&ms, ctx->evt[6], ctx->evt[7])); ctx->stats.traj_ms = ms; }
     CK(cudaEventElapsedTime(&ms, ctx->evt[0], ctx->evt[4])); ctx->stats.total_ms = ms;
     ctx->statsPending = false;
     return RC_OK;
 }
 
-int build_shard(rc_ctx* ctx) {
-    const int P = ctx->P, n = ctx->nPatGlobal;
-    ctx->clear_plans();
-    // work proxy: live states at t=0 = prod max(1, m_k); deal work-sorted patterns round-robin
+// Work-sorted round-robin deal of patterns to ranks (host only).  Work proxy: live states at t=0 = prod max(1, m_k).
+std::vector<int> shard_patterns(int P, int n, const int32_t* pats, int rank, int world) {
     std::vector<int> order((size_t)n);
     std::vector<long long> work((size_t)n);
     for (int i = 0; i < n; ++i) {
         long long w = 1;
-        for (int k = 0; k < P; ++k) w *= std::max(1, ctx->patG[(size_t)i * P + k]);
+        for (int k = 0; k < P; ++k) w *= std::max(1, pats[(size_t)i * P + k]);
         work[(size_t)i] = w;
         order[(size_t)i] = i;
     }
-    if (ctx->world > 1)
+    if (world > 1)
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[(size_t)a] > work[(size_t)b]; });
-    ctx->patGlobalIdx.clear();
+    std::vector<int> mine;
     for (int j = 0; j < n; ++j)
-        if (j % ctx->world == ctx->rank) ctx->patGlobalIdx.push_back(order[(size_t)j]);
-    std::sort(ctx->patGlobalIdx.begin(), ctx->patGlobalIdx.end());
+        if (j % world == rank) mine.push_back(order[(size_t)j]);
+    std::sort(mine.begin(), mine.end());
+    return mine;
+}
+
+int build_shard(rc_ctx* ctx) {
+    const int P = ctx->P;
+    ctx->clear_plans();
+    ctx->patGlobalIdx = shard_patterns(P, ctx->nPatGlobal, ctx->patG.data(), ctx->rank, ctx->world);
     ctx->nPat = (int)ctx->patGlobalIdx.size();
     const int m = ctx->nPat;
     ctx->patS.resize((size_t)m * P);
@@ -1004,6 +1016,14 @@ double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv) {
 }
 
 double rc_choose(int n, int k) { return rc::choose(n, k); }
+
+int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int world, int32_t* out, int cap) {
+    if (P < 1 || nPat < 0 || (nPat > 0 && !patterns) || world < 1 || rank < 0 || rank >= world) return RC_ERR_ARG;
+    std::vector<int> mine = shard_patterns(P, nPat, patterns, rank, world);
+    if (out)
+        for (size_t i = 0; i < mine.size() && (int)i < cap; ++i) out[i] = mine[i];
+    return (int)mine.size();
+}
 
 int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T, const double* times,
                   const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps, int64_t* slots0, int32_t* maxLive,

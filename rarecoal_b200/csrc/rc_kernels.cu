@@ -983,8 +983,11 @@ __device__ __forceinline__ int rc_key_run(RcKeyRegs<NNZ>& R, const unsigned sBas
     return (s - s0) & 1;
 }
 
+#ifndef RC_KEYED_MINB
+#define RC_KEYED_MINB 4
+#endif
 template <int NNZ>
-__global__ void __launch_bounds__(RC_BLOCK, 4)
+__global__ void __launch_bounds__(RC_BLOCK, RC_KEYED_MINB)
 rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                           const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab,
                           const double* __restrict__ aShort, const double* __restrict__ wpool,
