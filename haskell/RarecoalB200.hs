@@ -27,7 +27,7 @@ import           RarecoalLib.Utils      (RarecoalException (..))
 data RcCtx
 newtype B200Context = B200Context (Ptr RcCtx)
 
--- | rc_event: { double t; int32 type; int32 k; int32 l; double v }  (24 bytes, 8-byte aligned)
+-- | rc_event: { double t; int32 type; int32 k; int32 l; double v }  (32 bytes: v sits at offset 24 after padding)
 data RcEvent = RcEvent !Double !Int32 !Int32 !Int32 !Double
 
 instance Storable RcEvent where

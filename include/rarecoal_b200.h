@@ -33,6 +33,8 @@ enum {
     RC_OK = 0,
     RC_ERR_MODEL = 1,        /* RarecoalModelException  (validateModel, StateSpace.hs:163-197)      */
     RC_ERR_COMP = 2,         /* RarecoalCompException   (Core.hs:42,53-56; MaxUtils.hs:72-75)        */
+    RC_ERR_TEMPLATE = 3,     /* RarecoalModeltemplateException (ModelTemplate.hs:65,226)              */
+    RC_ERR_HIST = 4,         /* RarecoalHistogramException (Utils.hs:133,143,153,162,203)             */
     RC_ERR_ARG = -1,         /* bad argument / call order                                            */
     RC_ERR_CUDA = -2,        /* CUDA runtime failure or no device                                    */
     RC_ERR_UNSUPPORTED = -3  /* problem exceeds a compiled-in limit (see rc_last_error)              */
@@ -180,6 +182,36 @@ int rc_ss_x1up(const rc_statespace* ss, int id, int32_t* out);               /* 
 int rc_ss_x1(const rc_statespace* ss, int k);
 /* fillUpStateSpace (StateSpace.hs:145-160): returns n, fills out up to cap.                        */
 int rc_ss_fill_up(const rc_statespace* ss, const int32_t* ids, int n, int32_t* out, int cap);
+
+/* ---- formats either side of the path (host only) ------------------------- */
+
+/* Model template DSL (ModelTemplate.hs:78-145).  Writes a JSON description of the parsed template
+ * ({"branches", "events":[{"cmd","t","a","b","v","flag"}], "constraints", "params"}; "params" = getParamNames,
+ * ModelTemplate.hs:147-174) into out.  Returns 0, -RC_ERR_TEMPLATE (message in err), or the required buffer size
+ * when cap is too small.                                                                            */
+int rc_template_to_json(const char* text, char* out, int cap, char* err, int errCap);
+/* instantiateModel (ModelTemplate.hs:176-241): events of the ModelSpec for a parameter dictionary.  Returns the
+ * number of events (K = Join then SetPopSize), or -RC_ERR_TEMPLATE (parse error / missing parameter) /
+ * -RC_ERR_MODEL (unknown branch, violated constraint) with a message in err.                        */
+int rc_template_instantiate(const char* text, int nParams, const char* const* names, const double* values,
+                            rc_event* out, int cap, char* err, int errCap);
+/* makeParameterDict (ModelTemplate.hs:243-255): text of a maxl ("name value") or mcmc ('#' header, 3 lines skipped,
+ * MaxL column) output file.  namesOut receives the names separated by '\n'.  Returns the number of pairs.          */
+int rc_params_parse(const char* text, char* namesOut, int namesCap, double* values, int cap);
+
+/* Rare-allele histogram file (NAMES= / N= / MAX_M= / [MIN_M=] / TOTAL_SITES= header, then "m1,m2,.. count" rows;
+ * exampleData/fourPop.histogram.txt:1-5).                                                                       */
+typedef struct rc_hist rc_hist;
+rc_hist* rc_hist_read(const char* path, char* err, int errCap);
+void rc_hist_free(rc_hist* h);
+int rc_hist_info(const rc_hist* h, int32_t* nPops, int32_t* nRows, int32_t* minM, int32_t* maxM, int64_t* totalSites,
+                 int32_t* nVec, char* names, int namesCap);
+/* loadHistogram filters (Utils.hs:130-167), computeStandardOrder (Utils.hs:169-177) and the mapping of patterns and
+ * nVec to model-branch order (Utils.hs:114-119): the arguments of rc_set_problem.  maxAf == 0 keeps the file's
+ * MAX_M.  Returns the number of patterns (outputs filled up to cap rows) or -RC_ERR_HIST with a message in err.    */
+int rc_hist_problem(const rc_hist* h, int maxAf, int minAf, const int32_t* conditionOn, int nCond,
+                    const int32_t* exclude, int nExclude, int nModelBranches, const char* const* modelBranches,
+                    int32_t* patternsOut, int64_t* countsOut, int32_t* nVecOut, int cap, char* err, int errCap);
 
 const char* rc_version(void);
 

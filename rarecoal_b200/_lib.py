@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("RARECOAL_B200_LIB", os.path.join(HERE, "librarecoal_b200.so"))   # override: kernel A/B experiments
 
 RC_OK, RC_ERR_MODEL, RC_ERR_COMP, RC_ERR_ARG, RC_ERR_CUDA, RC_ERR_UNSUPPORTED = 0, 1, 2, -1, -2, -3
+RC_ERR_TEMPLATE, RC_ERR_HIST = 3, 4
 RC_EV_JOIN, RC_EV_SPLIT, RC_EV_POPSIZE, RC_EV_FREEZE = 0, 1, 2, 3
 
 
@@ -55,6 +56,14 @@ SIGNATURES = {
     "rc_ss_x1up": (C.c_int, [_vp, C.c_int, _ip]),
     "rc_ss_x1": (C.c_int, [_vp, C.c_int]),
     "rc_ss_fill_up": (C.c_int, [_vp, _ip, C.c_int, _ip, C.c_int]),
+    "rc_template_to_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
+    "rc_template_instantiate": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _dp, _evp, C.c_int, C.c_char_p, C.c_int]),
+    "rc_params_parse": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _dp, C.c_int]),
+    "rc_hist_read": (_vp, [C.c_char_p, C.c_char_p, C.c_int]),
+    "rc_hist_free": (None, [_vp]),
+    "rc_hist_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _lp, _ip, C.c_char_p, C.c_int]),
+    "rc_hist_problem": (C.c_int, [_vp, C.c_int, C.c_int, _ip, C.c_int, _ip, C.c_int, C.c_int, C.POINTER(C.c_char_p), _ip, _lp,
+                                  _ip, C.c_int, C.c_char_p, C.c_int]),
     "rc_version": (C.c_char_p, []),
 }
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librarecoal_b200.so")
-SOURCES = ["rc_api.cu", "rc_kernels.cu", "rc_plan.cpp"]
+SOURCES = ["rc_api.cu", "rc_kernels.cu", "rc_plan.cpp", "rc_frontend.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC,-O2,-Wall", "--fmad=true", "-cudart", "shared"]
 

@@ -101,7 +101,11 @@ def main():
                    "expected": [[1, 1, 0, 0, 0], [1, 2, 0, 0, 0], [2, 1, 0, 0, 0], [2, 2, 0, 0, 0],
                                 [0, 1, 1, 0, 0], [0, 1, 2, 0, 0], [0, 2, 1, 0, 0], [0, 2, 2, 0, 0]]},
     }, open(os.path.join(OUT, "fivepop_kat.json"), "w"))
-    print("wrote fourpop.json, fivepop_kat.json")
+    # the example DATA files themselves (formats of SURVEY.md Appendix B), for the front-end tests
+    import shutil
+    for name in ("fourPop.template.txt", "fourPop.histogram.txt", "fourPop.m4.mcmc.paramEstimates.txt"):
+        shutil.copyfile(os.path.join(ex, name), os.path.join(OUT, name))
+    print("wrote fourpop.json, fivepop_kat.json and the three example data files")
 
 
 if __name__ == "__main__":
