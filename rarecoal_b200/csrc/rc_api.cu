@@ -135,7 +135,7 @@ struct rc_ctx {
     // plans
     std::map<std::string, PlanEntry*> plans;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc;
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
@@ -365,9 +365,14 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     if ((rc = upload(ctx, pe, h.keyThrBase, &d.keyThrBase))) return rc;
     if ((rc = upload(ctx, pe, h.thrKey, &d.thrKey))) return rc;
     if ((rc = upload(ctx, pe, h.lastKeyId, &d.lastKeyId))) return rc;
-    if ((rc = upload(ctx, pe, h.fetchOff, &d.fetchOff))) return rc;
-    if ((rc = upload(ctx, pe, h.fetchRows, &d.fetchRows))) return rc;
-    if ((rc = upload(ctx, pe, h.rowBase, &d.rowBase))) return rc;
+    if ((rc = upload(ctx, pe, h.kBinBase, &d.kBinBase))) return rc;
+    if ((rc = upload(ctx, pe, h.nKBins, &d.nKBins))) return rc;
+    if ((rc = upload(ctx, pe, h.kBinPatOff, &d.kBinPatOff))) return rc;
+    if ((rc = upload(ctx, pe, h.kBinPats, &d.kBinPats))) return rc;
+    if ((rc = upload(ctx, pe, h.kFetchOff, &d.kFetchOff))) return rc;
+    if ((rc = upload(ctx, pe, h.kFetchRows, &d.kFetchRows))) return rc;
+    if ((rc = upload(ctx, pe, h.kRowBase, &d.kRowBase))) return rc;
+    d.maxEpochSlots = h.maxEpochSlots;
     if ((rc = upload(ctx, pe, h.binPatOff, &d.binPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.binPats, &d.binPats))) return rc;
     if ((rc = upload(ctx, pe, h.slotOff, &d.slotOff))) return rc;
@@ -476,7 +481,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     double* hW = (double*)(hb + oW);
     RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
     size_t mepPos = 0;
-    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0;
+    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0, carrySlots = 0;
     const long long ktabModelMax = (long long)(ctx->optKtabModelMB * 1048576.0 / 16.0);
     const long long ktabTotalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
 
@@ -521,6 +526,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
                 M.aShortOff = aShortDoubles;
                 aEndDoubles += hp.totalKeys;
                 aShortDoubles += hp.ep.back().nKeys;
+                carrySlots = std::max<long long>(carrySlots, hp.maxEpochSlots);
             }
             if (mh.sShort >= 0) {
                 size_t si = 0;
@@ -577,9 +583,13 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         size_t needK = (size_t)(std::max<long long>(ktabPairs, 1) + 8 * maxRowPairs + 64) * 16;
         size_t needA = (size_t)std::max<long long>(aEndDoubles, 1) * sizeof(double);
         size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
+        // b carried from one epoch's launch to the next (two buffers) and the per-pattern updateD accumulators
+        size_t needC = (size_t)std::max<long long>(2 * carrySlots * B, 1) * sizeof(double);
         if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap || needK > ctx->dKTab.cap || needA > ctx->dAEnd.cap ||
-            needS > ctx->dAShort.cap)
+            needS > ctx->dAShort.cap || needC > ctx->dBCarry.cap || needOut > ctx->dDAcc.cap)
             CK(cudaStreamSynchronize(st));
+        CK(ctx->dBCarry.ensure(needC));
+        CK(ctx->dDAcc.ensure(needOut));
         CK(ctx->dTab.ensure(needTab));
         CK(ctx->dPOut.ensure(needOut));
         CK(ctx->dKTab.ensure(needK));
@@ -624,9 +634,15 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
                     ++launches;
                 }
                 if (timeIt) { CK(cudaEventRecord(ctx->evt[7], st)); ctx->trajTimed = true; }
-                CK(rc_launch_propagate_keyed(pe->d, dM, dMep, dSev, (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW,
-                                             (double*)ctx->dPOut.p, pos, end - pos, st));
-                ++launches;
+                // one launch per structural epoch; b ping-pongs between the two carry buffers
+                for (int e = 0; e < pe->h.nEpochs; ++e) {
+                    double* c0 = (double*)ctx->dBCarry.p;
+                    double* c1 = c0 + (size_t)carrySlots * B;
+                    CK(rc_launch_propagate_keyed(pe->d, e, pe->h.nKBins[(size_t)e], dM, dMep, dSev, (const double*)ctx->dKTab.p,
+                                                 (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0, carrySlots,
+                                                 (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
+                    ++launches;
+                }
             }
             if (pe->d.nFastBins > 0 && anySelf) {
                 CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
@@ -753,7 +769,7 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
-                      &ctx->dAShort};
+                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();

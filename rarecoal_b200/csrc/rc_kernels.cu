@@ -986,209 +986,130 @@ __device__ __forceinline__ int rc_key_run(RcKeyRegs<NNZ>& R, const unsigned sBas
 #ifndef RC_KEYED_MINB
 #define RC_KEYED_MINB 4
 #endif
+// One launch per structural epoch `e`: block = (bin of that epoch, model).  b enters through the Join/Split
+// transition table of the event that opened the epoch (popJoinB / popSplitB as a gather, Core.hs:172-221) from the
+// previous launch's carry buffer and leaves through this launch's; the per-pattern updateD sums travel in dAcc.
+// The last epoch also does the shortcut (Core.hs:80-118) and the getProb epilogue (Core.hs:49-54).
 template <int NNZ>
 __global__ void __launch_bounds__(RC_BLOCK, RC_KEYED_MINB)
-rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
-                          const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab,
-                          const double* __restrict__ aShort, const double* __restrict__ wpool,
-                          double* __restrict__ pOut) {
+rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
+                          const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
+                          const double* __restrict__ ktab, const double* __restrict__ aShort,
+                          const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
+                          long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     typedef RcKeySmem SM;
     typedef RcKeyK K;
     const int tid = threadIdx.x;
-    const int bin = blockIdx.x, b = blockIdx.y;
+    const int b = blockIdx.y;
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
-    const int P = pl.P;
+    const int P = pl.P, nPat = pl.nPat, nnzw = pl.nnzw;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
-    const int pat0 = pl.fBinPatOff[bin];
-    const int np = pl.fBinPatOff[bin + 1] - pat0;
-    const int nSteps = models[b].nSteps, sShort = models[b].sShort, nSEv = models[b].nSEv;
-    const RcSEvDev* sev = sevs + models[b].sevOff;
-    const RcModelEpochDev* me = mep + models[b].mepOff;
-    const int nFP = pl.fBinPatOff[pl.nFastBins];
+    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int pat0 = pl.kBinPatOff[binIdx];
+    const int np = pl.kBinPatOff[binIdx + 1] - pat0;
+    const bool isLast = e + 1 == pl.nEpochs;
+    const int sShort = models[b].sShort;
+    const RcModelEpochDev mE = mep[models[b].mepOff + e];
 
     RcKeyRegs<NNZ> R;
     const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
     const unsigned zeroB = sBase + K::O_B + RC_BLOCK * 8u;
 #pragma unroll
     for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
-    R.nw = 0; R.unit = false; R.slotOn = false; R.fetchOn = false;
+    R.nw = 1; R.unit = false; R.slotOn = false; R.fetchOn = false;
     R.bv = 0.0; R.dacc = 0.0;
     R.fPtr = ktab;
 
+    // ---- set-up: patterns of the bin, slot layout of this epoch ----
+    const int* so = pl.slotOff + (size_t)e * (nPat + 1);
     if (tid < np) {
-        S.patId[tid] = pl.fBinPats[pat0 + tid];
+        const int pid = pl.kBinPats[pat0 + tid];
+        S.patId[tid] = pid;
         S.patDone[tid] = 0;
-        S.dpat[tid] = 0.0;
+        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + pid];
+        S.patOff2[tid] = so[pid + 1] - so[pid];
     }
     if (tid < 2 * RC_KDEPTH)                                                   // {1,0} padding pair of every ring slot
         S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
     if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                   // zero neighbours
     __syncthreads();
-
-    int epoch = 0, nextEv = 0;
-    int nextEvStep = nSEv > 0 ? sev[0].step : -1;
-    int s = 0;
-    int cp = 0;               // parity of the buffer that holds the current b when the slow path is entered
-    bool init = true;
-
-    for (;;) {
-        // ================= slow path: shortcut test, structural events, epoch set-up =================
-        // On exit everything is normalised: b in bbuf[0], pairs of steps s .. s+DEPTH-2 in (or on their way to) ring
-        // slots 0 .. DEPTH-2, fPtr at step s+DEPTH-1.
-        {
-            const int nnzw = pl.nnzw, nPat = pl.nPat;
-            rc_cp_wait<0>();
-            S.dslot[tid] = R.dacc;
-            R.dacc = 0.0;
-            __syncthreads();
-            if (tid < np && !S.patDone[tid] && !init) {       // updateD contributions so far (Core.hs:282-288)
-                const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
-                double acc = S.dpat[tid];
-                for (int i = 0; i < cnt; ++i)
-                    if (S.metaS[base + i] & RC_META_UNIT) acc = acc + S.dslot[base + i];
-                S.dpat[tid] = acc;
+    if (tid == 0) {
+        int run = 0;
+        for (int p = 0; p < np; ++p) { S.patOff[p] = run; run += S.patOff2[p]; }
+        S.patOff[np] = run;
+    }
+    __syncthreads();
+    const int nSlots = S.patOff[np];
+    R.slotOn = tid < nSlots;
+    int myLocal = 0, myPid = 0;
+    {
+        int n = 0;
+        if (R.slotOn) {
+            const int p = rc_find_owner(S.patOff, np, tid);
+            const int local = tid - S.patOff[p];
+            const int pid = S.patId[p];
+            const int gl = so[pid] + local;
+            const long long g = pl.epochBase[e] + gl;
+            myLocal = gl;
+            myPid = pid;
+            if (e > 0) {
+                // popJoinB / popSplitB as a gather over the previous epoch's live states of this pattern
+                const int* trOff = pl.trOff + pl.trBase[e - 1];
+                const uint32_t* trEnt = pl.trEnt + pl.trEntBase[e - 1];
+                const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
+                const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
+                const int e0 = trOff[gl], e1 = trOff[gl + 1];
+                double acc = 0.0;
+                for (int q = e0; q < e1; ++q) {
+                    const uint32_t en = trEnt[q];
+                    const uint32_t widx = en >> 16;
+                    const double old = bo[en & 0xFFFFu];
+                    acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
+                }
+                R.bv = acc;
+            } else {
+                // the seed state m is the last one fillUp emits (all components at their maximum), Core.hs:66
+                R.bv = (tid + 1 == S.patOff[p + 1]) ? 1.0 : 0.0;
             }
-            if (s == sShort && !init) {                       // canUseShortcut / propagateStateShortcut, Core.hs:80-118
-                int ok = 1;
-                if (tid < np && !S.patDone[tid]) {
-                    const int pid = S.patId[tid];
-                    if (pl.shortcutOK[pid]) {
-                        const double* aK = aShort + models[b].aShortOff;
-                        const int* kid = pl.lastKeyId + (size_t)pid * P;
-                        double nrA = 0.0;
-                        int popIndex = -1;
-                        for (int k = 0; k < P; ++k) {
-                            const double ak = aK[kid[k]];
-                            nrA = nrA + ak;
-                            if (popIndex < 0 && ak > 0.0) popIndex = k;
-                        }
-                        const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
-                        const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
-                        const double* bc = S.bbuf + cp * SM::BSTRIDE + base;
-                        double add = 0.0;
-                        for (int i = 0; i < cnt; ++i) {
-                            const int nd = (int)(S.metaS[base + i] >> 16);
-                            const double withComb = 2.0 * popSize / (double)nd;
-                            add = add + bc[i] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
-                        }
-                        S.dpat[tid] = S.dpat[tid] + add;
-                        S.patDone[tid] = 2;
-                    } else ok = 0;
-                }
-                if (__syncthreads_and(ok)) break;
-            }
-            // the initial state is handled as a pseudo-event that builds epoch 0 without a transition
-            bool first = init;
-            bool rebuilt = false;
-            while (first || (nextEv < nSEv && nextEvStep == s)) {
-                const double* W = wpool + models[b].wPool;
-                if (!first) {
-                    W += sev[nextEv].wOff;
-                    ++epoch;
-                    ++nextEv;
-                    nextEvStep = nextEv < nSEv ? sev[nextEv].step : -1;
-                }
-                // ---- per-thread structure of `epoch`; b is carried through the event's transition table
-                //      (popJoinB/popSplitB as a gather, Core.hs:172-221)
-                const int* so = pl.slotOff + (size_t)epoch * (nPat + 1);
-                if (tid < np) {
-                    const int pid = S.patId[tid];
-                    S.patOff2[tid] = so[pid + 1] - so[pid];
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    int run = 0;
-                    for (int p = 0; p < np; ++p) { int sz = S.patOff2[p]; S.patOff2[p] = run; run += sz; }
-                    S.patOff2[np] = run;
-                }
-                __syncthreads();
-                const int nNew = S.patOff2[np];
-                R.slotOn = tid < nNew;
-                int n = 0;
-                R.unit = false; R.bv = 0.0;
+            const uint32_t mt = pl.meta[g];
+            S.metaS[tid] = mt;
+            n = (int)(mt & 0xFFu);
+            R.unit = (mt & RC_META_UNIT) != 0;
+            const uint16_t* rb = pl.kRowBase + (size_t)(pat0 + p) * P;
+            const int bBase = S.patOff[p];
 #pragma unroll
-                for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
-                if (R.slotOn) {
-                    const int p = rc_find_owner(S.patOff2, np, tid);
-                    const int local = tid - S.patOff2[p];
-                    const int pid = S.patId[p];
-                    const int gl = so[pid] + local;
-                    const long long g = pl.epochBase[epoch] + gl;
-                    if (S.patDone[p]) R.slotOn = false;
-                    if (!first) {
-                        const int* trOff = pl.trOff + pl.trBase[epoch - 1];
-                        const uint32_t* trEnt = pl.trEnt + pl.trEntBase[epoch - 1];
-                        const double* bo = S.bbuf + cp * SM::BSTRIDE + S.patOff[p];
-                        const int e0 = trOff[gl], e1 = trOff[gl + 1];
-                        double acc = 0.0;
-                        for (int q = e0; q < e1; ++q) {
-                            const uint32_t en = trEnt[q];
-                            const uint32_t widx = en >> 16;
-                            const double old = bo[en & 0xFFFFu];
-                            acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
-                        }
-                        R.bv = acc;
-                    } else {
-                        // the seed state m is the last one fillUp emits (all components at their maximum)
-                        R.bv = (tid + 1 == S.patOff2[p + 1]) ? 1.0 : 0.0;
-                    }
-                    const uint32_t mt = pl.meta[g];
-                    S.metaS[tid] = mt;
-                    n = (int)(mt & 0xFFu);
-                    R.unit = (mt & RC_META_UNIT) != 0;
-                    const uint16_t* rb = pl.rowBase + ((size_t)epoch * nFP + pat0 + p) * P;
-                    const int bBase = S.patOff2[p];
-#pragma unroll
-                    for (int d = 0; d < NNZ; ++d) {
-                        if (d < n) {
-                            const uint32_t w = pl.words[g * nnzw + d];
-                            const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
-                            const uint32_t up = w >> 16;
-                            R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
-                            if (up != RC_NO_UP) R.aB[d] = sBase + K::O_B + (unsigned)(bBase + (int)up) * 8u;
-                        }
-                    }
-                }
-                R.nw = __reduce_max_sync(0xFFFFFFFFu, n);
-                __syncthreads();                      // every gather has read the old layout
-                S.bbuf[tid] = R.bv;                   // new layout lives at parity 0
-                cp = 0;
-                if (tid <= np) S.patOff[tid] = S.patOff2[tid];
-                first = false;
-                rebuilt = true;
-                __syncthreads();
-            }
-            init = false;
-            if (!rebuilt) {                           // no event: only move b to parity 0 and refresh activity
-                S.bbuf[tid] = R.bv;
-                if (R.slotOn) {
-                    const int p = rc_find_owner(S.patOff, np, tid);
-                    if (S.patDone[p]) {               // pattern took the shortcut: park the lane on the padding pair
-                        R.slotOn = false;
-                        R.unit = false;
-#pragma unroll
-                        for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
-                    }
+            for (int d = 0; d < NNZ; ++d) {
+                if (d < n) {
+                    const uint32_t w = pl.words[g * nnzw + d];
+                    const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                    const uint32_t up = w >> 16;
+                    R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
+                    if (up != RC_NO_UP) R.aB[d] = sBase + K::O_B + (unsigned)(bBase + (int)up) * 8u;
                 }
             }
-            if (R.nw < 1) R.nw = 1;
-            if (s >= nSteps) break;
         }
-        int nextStop = nSteps;
-        if (sShort > s && sShort < nextStop) nextStop = sShort;
-        if (nextEvStep > s && nextEvStep < nextStop) nextStop = nextEvStep;
-        {
-            // ---- start the ring: pairs of steps s .. s+DEPTH-2 into slots 0 .. DEPTH-2 ----
-            const RcModelEpochDev mE = me[epoch];
-            const int rowPairs = pl.ep[epoch].rowPairs;
-            const int* fo = pl.fetchOff + (size_t)epoch * (pl.nFastBins + 1) + bin;
-            const int nFetch = fo[1] - fo[0];
-            R.fetchOn = tid < nFetch;
-            const int fOff = R.fetchOn ? pl.fetchRows[fo[0] + tid] : 0;
+        R.nw = max(1, __reduce_max_sync(0xFFFFFFFFu, n));
+    }
+    S.bbuf[tid] = R.bv;
+    const int rowPairs = pl.ep[e].rowPairs;
+    const long long strideD = (long long)rowPairs * 2;
+    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
+    R.fetchOn = tid < nFetch;
+    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    __syncthreads();
+
+    int s = mE.beg;
+    int cp = 0;
+    bool finished = false;
+    // at most two runs: up to the end of the epoch (or to the shortcut step in the last epoch), then — only if some
+    // pattern of the bin cannot take the shortcut — on to the end of the grid
+    for (int phase = 0; phase < 2 && !finished; ++phase) {
+        int nextStop = mE.end;
+        if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
+        if (s < nextStop) {
             R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
-            const long long strideD = (long long)rowPairs * 2;
 #pragma unroll
             for (int u = 0; u < RC_KDEPTH - 1; ++u) {
                 rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
@@ -1197,7 +1118,6 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
             }
             rc_cp_wait<RC_KDEPTH - 2>();
             __syncthreads();
-            // ================================ fast path ================================
             switch (R.nw) {
                 case 1: cp = rc_key_run<NNZ, 1>(R, sBase, strideD, s, nextStop); break;
                 case 2: cp = rc_key_run<NNZ, 2>(R, sBase, strideD, s, nextStop); break;
@@ -1208,25 +1128,76 @@ rc_propagate_keyed_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, c
                 case 7: cp = rc_key_run<NNZ, (NNZ >= 7 ? 7 : NNZ)>(R, sBase, strideD, s, nextStop); break;
                 default: cp = rc_key_run<NNZ, NNZ>(R, sBase, strideD, s, nextStop); break;
             }
+            rc_cp_wait<0>();
         }
-        if (s >= nSteps && s != sShort) break;
+        // ---- updateD contributions of the run (Core.hs:282-288) ----
+        S.dslot[tid] = R.dacc;
+        R.dacc = 0.0;
+        __syncthreads();
+        if (tid < np && !S.patDone[tid]) {
+            const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+            double acc = S.dpat[tid];
+            for (int i = 0; i < cnt; ++i)
+                if (S.metaS[base + i] & RC_META_UNIT) acc = acc + S.dslot[base + i];
+            S.dpat[tid] = acc;
+        }
+        if (!(isLast && phase == 0 && s == sShort && s < models[b].nSteps)) { finished = true; break; }
+        // ---- canUseShortcut / propagateStateShortcut (Core.hs:80-118): the event queue is empty from here on ----
+        int ok = 1;
+        if (tid < np) {
+            const int pid = S.patId[tid];
+            if (pl.shortcutOK[pid]) {
+                const double* aK = aShort + models[b].aShortOff;
+                const int* kid = pl.lastKeyId + (size_t)pid * P;
+                double nrA = 0.0;
+                int popIndex = -1;
+                for (int k = 0; k < P; ++k) {
+                    const double ak = aK[kid[k]];
+                    nrA = nrA + ak;
+                    if (popIndex < 0 && ak > 0.0) popIndex = k;
+                }
+                const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
+                const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
+                const double* bc = S.bbuf + cp * SM::BSTRIDE + base;
+                double add = 0.0;
+                for (int i = 0; i < cnt; ++i) {
+                    const int nd = (int)(S.metaS[base + i] >> 16);
+                    const double withComb = 2.0 * popSize / (double)nd;
+                    add = add + bc[i] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
+                }
+                S.dpat[tid] = S.dpat[tid] + add;
+                S.patDone[tid] = 2;
+            } else ok = 0;
+        }
+        if (__syncthreads_and(ok)) { finished = true; break; }
+        // some pattern continues to the end of the grid: park the finished ones, move b to parity 0
+        if (R.slotOn) {
+            const int p = rc_find_owner(S.patOff, np, tid);
+            if (S.patDone[p]) {
+                R.slotOn = false;
+                R.unit = false;
+#pragma unroll
+                for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+            }
+        }
+        S.bbuf[tid] = R.bv;
+        cp = 0;
+        __syncthreads();
+    }
+    if (!isLast) {
+        // ---- hand b and the updateD sums to the next epoch's launch ----
+        if (tid < nSlots) bCur[(size_t)b * bStride + myLocal] = R.bv;
+        if (tid < np) dAcc[(size_t)b * nPat + S.patId[tid]] = S.dpat[tid];
+        (void)myPid;
+        return;
     }
     // ---- getProb epilogue (Core.hs:49-54) ----
-    rc_cp_wait<0>();
-    __syncthreads();
-    S.dslot[tid] = R.dacc;
-    __syncthreads();
     if (tid < np) {
         const int pid = S.patId[tid];
-        double d = S.dpat[tid];
-        if (S.patDone[tid] != 2) {
-            const int base = S.patOff[tid], cnt = S.patOff[tid + 1] - base;
-            for (int i = 0; i < cnt; ++i)
-                if (S.metaS[base + i] & RC_META_UNIT) d = d + S.dslot[base + i];
-        }
+        const double d = S.dpat[tid];
         double discFac = 1.0;
         for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
-        pOut[(size_t)b * pl.nPat + pid] = d * models[b].theta * pl.combFac[pid] * discFac;
+        pOut[(size_t)b * nPat + pid] = d * models[b].theta * pl.combFac[pid] * discFac;
     }
 }
 
@@ -1346,28 +1317,32 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
     return cudaGetLastError();
 }
 
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, const RcModelDev* models, const RcModelEpochDev* mep,
-                                      const RcSEvDev* sevs, const double* ktab, const double* aShort, const double* wpool,
-                                      double* pOut, int b0, int nB, cudaStream_t st) {
-    if (pl.nFastBins <= 0 || nB <= 0) return cudaSuccess;
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, const RcModelDev* models,
+                                      const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
+                                      const double* aShort, const double* wpool, const double* bPrev, double* bCur,
+                                      long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
+    if (nBins <= 0 || nB <= 0) return cudaSuccess;
     const size_t smem = (sizeof(RcKeySmem) + 15) & ~(size_t)15;
     static bool c4 = false, c8 = false;
-    dim3 grid((unsigned)pl.nFastBins, (unsigned)nB);
+    dim3 grid((unsigned)nBins, (unsigned)nB);
     double* out = pOut + (size_t)b0 * pl.nPat;
+    double* dac = dAcc + (size_t)b0 * pl.nPat;
+    const double* bp = bPrev + (size_t)b0 * bStride;
+    double* bc = bCur + (size_t)b0 * bStride;
     if (pl.nnzw <= 4) {
         if (!c4) {
-            cudaError_t e = cudaFuncSetAttribute(rc_propagate_keyed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
+            cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
             c4 = true;
         }
-        rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, mep, sevs, ktab, aShort, wpool, out);
+        rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     } else {
         if (!c8) {
-            cudaError_t e = cudaFuncSetAttribute(rc_propagate_keyed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
+            cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
             c8 = true;
         }
-        rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, mep, sevs, ktab, aShort, wpool, out);
+        rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     }
     return cudaGetLastError();
 }

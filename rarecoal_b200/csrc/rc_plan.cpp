@@ -428,7 +428,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     for (int i : fastIds)
         while (pps[(size_t)i].maxR > 2 * fastBlock - 2) fastBlock *= 2;
     out.fastBlock = fastBlock;
-    const int maxPatFast = std::max(1, std::min(RC_NPB, fastBlock / P));
+    const int maxPatFast = std::getenv("RC_MAXPAT") ? std::atoi(std::getenv("RC_MAXPAT")) : std::max(1, std::min(RC_NPB, fastBlock / P));
     int cap = ((std::max(maxLiveBig, 1) + RC_BLOCK - 1) / RC_BLOCK) * RC_BLOCK;
     // bytes per slot in the big-tier kernel: 2 b buffers + d accumulator (24) + words (4*nnzw) + meta (4) + owner (2)
     int perSlot = 24 + 4 * nnzw + 4 + 2;
@@ -548,8 +548,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         out.lastKeyId.assign(out.keyId.end() - (size_t)nPat * P, out.keyId.end());
     }
 
-    // ---- fast-tier bins: patterns in lexicographic order (neighbours share trajectory keys), packed sequentially under
-    //      the slot / pattern / pair-row limits; per bin and epoch the de-duplicated list of pair rows to fetch
+    // ---- fast-tier bins: patterns in lexicographic order (neighbours share trajectory keys), packed first-fit over a
+    //      short window of open bins under the slot / pattern / pair-row limits of the epochs the bins are used for.
+    //      Two sets: one spanning all epochs (self-contained kernel: events handled inside the block) and one per
+    //      epoch (keyed kernel: one launch per epoch, b carried through global memory, bins sized for that epoch only).
     {
         std::vector<int> order(fastIds);
         std::sort(order.begin(), order.end(), [&](int a, int b) {
@@ -559,65 +561,81 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             return a < b;
         });
         const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
-        out.fBinPatOff.assign(1, 0);
-        out.fBinPats.clear();
-        std::vector<std::unordered_map<int, int>> keyRows((size_t)nEpochs);   // key -> rows needed, current bin
-        std::vector<int> rowsUsed((size_t)nEpochs, 0), rowsSelf((size_t)nEpochs, 0);
-        int slots = 0, cnt = 0;
-        auto close_bin = [&]() {
-            if (cnt == 0) return;
-            out.fBinPatOff.push_back((int)out.fBinPats.size());
-            for (int e = 0; e < nEpochs; ++e) { keyRows[(size_t)e].clear(); rowsUsed[(size_t)e] = 0; rowsSelf[(size_t)e] = 0; }
-            slots = 0; cnt = 0;
+        struct OpenBin {
+            std::vector<int> ids, slotsE, rowsUsed, rowsSelf;
+            std::vector<std::unordered_map<int, int>> keyRows;   // per epoch: key -> pair rows needed
         };
-        for (int i : order) {
-            const PatPlan& pp = pps[(size_t)i];
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                bool fits = slots + pp.maxLive <= fastBlock && cnt + 1 <= maxPatFast;
-                std::vector<int> add((size_t)nEpochs, 0), addSelf((size_t)nEpochs, 0);
-                for (int e = 0; e < nEpochs && fits; ++e) {
+        auto pack_range = [&](int e0, int e1, int maxPats, std::vector<int>& patOff, std::vector<int>& pats) {
+            const int nE = e1 - e0 + 1;
+            const size_t WINDOW = 12;
+            std::vector<OpenBin> open;
+            auto flush = [&](OpenBin& ob) {
+                for (int i : ob.ids) pats.push_back(i);
+                patOff.push_back((int)pats.size());
+            };
+            auto try_add = [&](OpenBin& ob, int i) -> bool {
+                const PatPlan& pp = pps[(size_t)i];
+                if ((int)ob.ids.size() + 1 > maxPats) return false;
+                for (int q = 0; q < nE; ++q)
+                    if (ob.slotsE[(size_t)q] + pp.live[(size_t)(e0 + q)] > fastBlock) return false;
+                std::vector<int> add((size_t)nE, 0), addSelf((size_t)nE, 0);
+                for (int q = 0; q < nE; ++q) {
+                    const int e = e0 + q;
                     for (int k = 0; k < P; ++k) {
                         int mxk = pp.mx[(size_t)e * P + k];
                         if (!mxk) continue;
-                        addSelf[(size_t)e] += mxk;
+                        addSelf[(size_t)q] += mxk;
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
-                        auto it = keyRows[(size_t)e].find(key);
-                        int have = it == keyRows[(size_t)e].end() ? 0 : it->second;
-                        if (mxk > have) add[(size_t)e] += mxk - have;
+                        auto it = ob.keyRows[(size_t)q].find(key);
+                        int have = it == ob.keyRows[(size_t)q].end() ? 0 : it->second;
+                        if (mxk > have) add[(size_t)q] += mxk - have;
                     }
-                    fits = rowsUsed[(size_t)e] + add[(size_t)e] <= rowCap && rowsSelf[(size_t)e] + addSelf[(size_t)e] <= 2 * fastBlock - 2;
+                    if (ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
+                    if (ob.rowsSelf[(size_t)q] + addSelf[(size_t)q] > 2 * fastBlock - 2) return false;
                 }
-                if (!fits && cnt > 0) { close_bin(); continue; }
-                for (int e = 0; e < nEpochs; ++e) {
+                for (int q = 0; q < nE; ++q) {
+                    const int e = e0 + q;
                     for (int k = 0; k < P; ++k) {
                         int mxk = pp.mx[(size_t)e * P + k];
                         if (!mxk) continue;
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
-                        int& have = keyRows[(size_t)e][key];
-                        if (mxk > have) { rowsUsed[(size_t)e] += mxk - have; have = mxk; }
+                        int& have = ob.keyRows[(size_t)q][key];
+                        if (mxk > have) { ob.rowsUsed[(size_t)q] += mxk - have; have = mxk; }
                     }
-                    rowsSelf[(size_t)e] += addSelf[(size_t)e];
+                    ob.rowsSelf[(size_t)q] += addSelf[(size_t)q];
+                    ob.slotsE[(size_t)q] += pp.live[(size_t)e];
                 }
-                out.fBinPats.push_back(i);
-                slots += pp.maxLive;
-                ++cnt;
-                break;
+                ob.ids.push_back(i);
+                return true;
+            };
+            for (int i : order) {
+                bool placed = false;
+                for (size_t q = open.size(); q-- > 0 && !placed;) placed = try_add(open[q], i);
+                if (placed) continue;
+                if (open.size() >= WINDOW) {
+                    flush(open.front());
+                    open.erase(open.begin());
+                }
+                open.emplace_back();
+                OpenBin& ob = open.back();
+                ob.slotsE.assign((size_t)nE, 0);
+                ob.rowsUsed.assign((size_t)nE, 0);
+                ob.rowsSelf.assign((size_t)nE, 0);
+                ob.keyRows.resize((size_t)nE);
+                if (!try_add(ob, i)) ob.ids.push_back(i);     // a single pattern always fits its tier
             }
-        }
-        close_bin();
-        out.nFastBins = (int)out.fBinPatOff.size() - 1;
-        // fetch lists and per-(pattern, branch) pair-row bases
-        const int nFP = (int)out.fBinPats.size();
-        out.fetchOff.assign((size_t)nEpochs * (out.nFastBins + 1), 0);
-        out.rowBase.assign((size_t)nEpochs * nFP * P, 0xFFFF);
-        for (int e = 0; e < nEpochs; ++e) {
+            for (OpenBin& ob : open) flush(ob);
+        };
+        // de-duplicated pair rows a bin fetches in epoch e, and the first row of every (pattern, branch)
+        auto fetch_lists = [&](int e, const std::vector<int>& patOff, const std::vector<int>& pats, int b0, int b1,
+                               std::vector<int>& fOff, std::vector<int>& fRows, std::vector<uint16_t>& rBase, size_t rBaseOff) {
             const PlanHost::Epoch& E = out.ep[(size_t)e];
-            for (int bI = 0; bI < out.nFastBins; ++bI) {
-                out.fetchOff[(size_t)e * (out.nFastBins + 1) + bI] = (int)out.fetchRows.size();
+            for (int bI = b0; bI < b1; ++bI) {
+                fOff.push_back((int)fRows.size());
                 std::unordered_map<int, int> rowsOf, startOf;
                 std::vector<int> keyOrder;
-                for (int q = out.fBinPatOff[(size_t)bI]; q < out.fBinPatOff[(size_t)bI + 1]; ++q) {
-                    int i = out.fBinPats[(size_t)q];
+                for (int q = patOff[(size_t)bI]; q < patOff[(size_t)bI + 1]; ++q) {
+                    int i = pats[(size_t)q];
                     for (int k = 0; k < P; ++k) {
                         int mxk = pps[(size_t)i].mx[(size_t)e * P + k];
                         if (!mxk) continue;
@@ -627,33 +645,56 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         else if (mxk > it->second) it->second = mxk;
                     }
                 }
-                out.fetchRows.push_back(0);                 // smem pair row 0 <- {dt, 0}
+                fRows.push_back(0);                 // smem pair row 0 <- {dt, 0}
                 int row = 1;
                 for (int key : keyOrder) {
                     startOf[key] = row;
                     int n = rowsOf[key];
-                    for (int j = 0; j < n; ++j) out.fetchRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
+                    for (int j = 0; j < n; ++j) fRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
                     row += n;
                 }
-                for (int q = out.fBinPatOff[(size_t)bI]; q < out.fBinPatOff[(size_t)bI + 1]; ++q) {
-                    int i = out.fBinPats[(size_t)q];
+                for (int q = patOff[(size_t)bI]; q < patOff[(size_t)bI + 1]; ++q) {
+                    int i = pats[(size_t)q];
                     for (int k = 0; k < P; ++k) {
                         if (!pps[(size_t)i].mx[(size_t)e * P + k]) continue;
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
-                        out.rowBase[((size_t)e * nFP + q) * P + k] = (uint16_t)startOf[key];
+                        rBase[rBaseOff + (size_t)q * P + k] = (uint16_t)startOf[key];
                     }
                 }
             }
-            out.fetchOff[(size_t)e * (out.nFastBins + 1) + out.nFastBins] = (int)out.fetchRows.size();
+        };
+        // (1) bins spanning all epochs (self-contained fast kernel)
+        out.fBinPatOff.assign(1, 0);
+        out.fBinPats.clear();
+        pack_range(0, nEpochs - 1, maxPatFast, out.fBinPatOff, out.fBinPats);
+        out.nFastBins = (int)out.fBinPatOff.size() - 1;
+        // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
+        out.kBinBase.assign((size_t)nEpochs, 0);
+        out.nKBins.assign((size_t)nEpochs, 0);
+        for (int e = 0; e < nEpochs; ++e) {
+            out.kBinBase[(size_t)e] = (int)out.kBinPatOff.size();
+            out.kBinPatOff.push_back((int)out.kBinPats.size());
+            pack_range(e, e, RC_NPB, out.kBinPatOff, out.kBinPats);
+            out.nKBins[(size_t)e] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)e];
+        }
+        out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
+        for (int e = 0; e < nEpochs; ++e) {
+            const int b0 = out.kBinBase[(size_t)e];
+            // fetch offsets are stored at the same index as the bin offsets (one extra entry per epoch)
+            std::vector<int> fOff;
+            fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)e], fOff, out.kFetchRows, out.kRowBase, 0);
+            fOff.push_back((int)out.kFetchRows.size());
+            out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
         if (std::getenv("RC_PLAN_DEBUG")) {
             for (int e = 0; e < nEpochs; ++e) {
                 const PlanHost::Epoch& E = out.ep[(size_t)e];
-                int f0 = out.fetchOff[(size_t)e * (out.nFastBins + 1)], f1 = out.fetchOff[(size_t)e * (out.nFastBins + 1) + out.nFastBins];
-                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d fetch rows/bin %.1f\n", e, E.nKeys, E.nThr,
-                             E.rowPairs, out.nFastBins ? (double)(f1 - f0) / out.nFastBins : 0.0);
+                int b0 = out.kBinBase[(size_t)e], nb = out.nKBins[(size_t)e];
+                int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
+                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d slots %lld bins %d fetch rows/bin %.1f\n", e,
+                             E.nKeys, E.nThr, E.rowPairs, (long long)0, nb, nb ? (double)(f1 - f0) / nb : 0.0);
             }
-            std::fprintf(stderr, "[rc plan] fast bins %d (block %d), big bins %d (cap %d)\n", out.nFastBins, fastBlock, out.nBins, cap);
+            std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
         }
     }
     out.nBins = pack(bigIds, cap, RC_NPB, 1 << 30, out.binPatOff, out.binPats);
@@ -686,6 +727,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         total += tot;
     }
     out.totalSlots = total;
+    for (int e = 0; e < nEpochs; ++e) out.maxEpochSlots = std::max(out.maxEpochSlots, out.epochSlots[(size_t)e]);
     out.words.assign((size_t)total * nnzw, 0u);
     out.meta.assign((size_t)total, 0u);
     for (int i = 0; i < nPat; ++i) {

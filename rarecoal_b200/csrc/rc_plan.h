@@ -64,9 +64,13 @@ struct PlanHost {
     std::vector<int> keyId;                // [nEpochs][nPat][P] (host only)
     std::vector<int> lastKeyId;            // [nPat][P] keys of the final epoch (shortcut reads a from them)
     int totalKeys = 0;
-    std::vector<int> fetchOff;             // [nEpochs][nFastBins+1] -> fetchRows
-    std::vector<int> fetchRows;            // pair offsets inside a step row, one per shared-memory pair row
-    std::vector<uint16_t> rowBase;         // [nEpochs][fast pattern slot][P] first shared-memory pair row of (pattern, branch)
+    // per-epoch bins of the keyed kernel
+    std::vector<int> kBinBase, nKBins;     // [nEpochs] first entry of the epoch in kBinPatOff / number of bins
+    std::vector<int> kBinPatOff, kBinPats; // nKBins[e]+1 offsets per epoch into kBinPats (shard-local pattern ids)
+    std::vector<int> kFetchOff;            // same indexing as kBinPatOff -> kFetchRows
+    std::vector<int> kFetchRows;           // pair offsets inside a step row, one per shared-memory pair row of a bin
+    std::vector<uint16_t> kRowBase;        // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
+    long long maxEpochSlots = 0;           // largest number of live states in one epoch (stride of the b carry buffers)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]
     std::vector<uint32_t> words, meta;

@@ -80,9 +80,14 @@ struct RcPlanDev {
     const int* keyThrBase;       // first trajectory-kernel thread of the key
     const int* thrKey;           // trajectory-kernel thread -> key (RcEpochDev::thrOff)
     const int* lastKeyId;        // [nPat][P] keys of the final epoch
-    const int* fetchOff;         // [nEpochs][nFastBins+1] -> fetchRows
-    const int* fetchRows;        // pair offset inside a step row for every shared-memory pair row of a bin
-    const uint16_t* rowBase;     // [nEpochs][fast pattern slot][P] first shared-memory pair row of (pattern, branch)
+    const int* kBinBase;         // [nEpochs] first entry of the epoch in kBinPatOff / kFetchOff
+    const int* nKBins;           // [nEpochs] keyed bins of the epoch
+    const int* kBinPatOff;       // per epoch nKBins[e]+1 offsets into kBinPats
+    const int* kBinPats;         // shard-local pattern ids, epoch after epoch, bin after bin
+    const int* kFetchOff;        // same indexing as kBinPatOff -> kFetchRows
+    const int* kFetchRows;       // pair offset inside a step row for every shared-memory pair row of a bin
+    const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
+    long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
 };
 
 struct RcEpochDev {
