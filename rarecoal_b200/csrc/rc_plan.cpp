@@ -570,6 +570,16 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             const size_t WINDOW = 12;
             std::vector<OpenBin> open;
             auto flush = [&](OpenBin& ob) {
+                if (nE == 1) {
+                    // a warp visits as many components as its widest state: keep patterns with equally many non-zero
+                    // branches next to each other inside the bin
+                    auto nnzOf = [&](int i) {
+                        int c = 0;
+                        for (int k = 0; k < P; ++k) c += pps[(size_t)i].mx[(size_t)e0 * P + k] ? 1 : 0;
+                        return c;
+                    };
+                    std::stable_sort(ob.ids.begin(), ob.ids.end(), [&](int a, int b) { return nnzOf(a) > nnzOf(b); });
+                }
                 for (int i : ob.ids) pats.push_back(i);
                 patOff.push_back((int)pats.size());
             };
