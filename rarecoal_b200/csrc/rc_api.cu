@@ -373,6 +373,12 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     if ((rc = upload(ctx, pe, h.kFetchRows, &d.kFetchRows))) return rc;
     if ((rc = upload(ctx, pe, h.kRowBase, &d.kRowBase))) return rc;
     d.maxEpochSlots = h.maxEpochSlots;
+    if ((rc = upload(ctx, pe, h.epochMode, &d.epochMode))) return rc;
+    if ((rc = upload(ctx, pe, h.rowOff, &d.rowOff))) return rc;
+    if ((rc = upload(ctx, pe, h.rowEpochBase, &d.rowEpochBase))) return rc;
+    if ((rc = upload(ctx, pe, h.rowRefAll, &d.rowRefAll))) return rc;
+    if ((rc = upload(ctx, pe, h.rowWordsAll, &d.rowWordsAll))) return rc;
+    if ((rc = upload(ctx, pe, h.patRow, &d.patRow))) return rc;
     if ((rc = upload(ctx, pe, h.binPatOff, &d.binPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.binPats, &d.binPats))) return rc;
     if ((rc = upload(ctx, pe, h.slotOff, &d.slotOff))) return rc;
@@ -638,7 +644,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
-                    CK(rc_launch_propagate_keyed(pe->d, e, pe->h.nKBins[(size_t)e], dM, dMep, dSev, (const double*)ctx->dKTab.p,
+                    CK(rc_launch_propagate_keyed(pe->d, e, pe->h.nKBins[(size_t)e], pe->h.epochMode[(size_t)e], dM, dMep, dSev, (const double*)ctx->dKTab.p,
                                                  (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0, carrySlots,
                                                  (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
                     ++launches;

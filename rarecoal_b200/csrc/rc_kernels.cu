@@ -1202,6 +1202,349 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row mode of the keyed tier (epochs whose live sets are boxes with few non-zero branches): one thread owns the
+// row of states x_r = 1..M along the widest branch r of its pattern, the other coordinates fixed.  b of the row lives
+// in registers; the neighbour along r is the next register, the {G,E2} pairs of the other branches are loaded once per
+// row, and only the neighbouring rows and the row branch's own pairs come from shared memory:
+//     b'(j) = b(j) * [prod_{d != r} G_d(x_d)] * G_r(j) + sum_{d != r} b_{row+e_d}(j) * E2_d(x_d) + b(j+1) * E2_r(j)
+// (Core.hs:259).  Rows are stored row-major with an odd stride (M | 1), so a warp reading one column of consecutive
+// rows touches distinct banks.
+#define RC_RDEPTH 4
+struct RcRowSmem {
+    static constexpr int BPAR = RC_ROW_BCAP + 16;      // doubles per parity; the last 16 are the always-zero row
+    double bbuf[2 * BPAR];
+    double RE[RC_RDEPTH * 2 * RC_KROWS];               // [slot][row]{G, E2}; row 0 = {dt, 0}; last row = {1, 0}
+    double dslot[RC_BLOCK];
+    double dpat[RC_NPBR];
+    int patRowOff[RC_NPBR + 1];
+    int patBOff[RC_NPBR + 1];
+    int patId[RC_NPBR];
+    int patDone[RC_NPBR];
+};
+struct RcRowK {
+    static constexpr unsigned B_PAR = RcRowSmem::BPAR * 8u;
+    static constexpr unsigned RE_SLOT = RC_KROWS * 16u;
+    static constexpr unsigned RE_PAD = (RC_KROWS - 1) * 16u;
+    static constexpr unsigned O_B = (unsigned)offsetof(RcRowSmem, bbuf);
+    static constexpr unsigned O_RE = (unsigned)offsetof(RcRowSmem, RE);
+    static constexpr unsigned ZERO_B = RC_ROW_BCAP * 8u;
+    static_assert(O_RE % 16 == 0, "16-byte alignment of the pair table");
+};
+
+struct RcRowRegs {
+    double b[RC_ROW_MAXM];
+    unsigned aRE[RC_ROW_NO], aB[RC_ROW_NO];   // pair of (branch d, x_d) in ring slot 0 / neighbour row (parity 0)
+    unsigned aREr, myB;                        // pair of (row branch, j = 1) in ring slot 0 / own row (parity 0)
+    int M, NO;
+    bool unit, rowOn, fetchOn;
+    double dacc;
+    const double* fPtr;
+};
+
+// grid steps s .. nextStop-1 for a warp whose rows have at most NO other branches and length at most M
+template <int NO, int M>
+__device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
+                                          const int nextStop) {
+    typedef RcRowK K;
+    const unsigned myRE = sBase + K::O_RE + threadIdx.x * 16u;
+    const unsigned fetchPred = R.fetchOn ? 1u : 0u;
+    const bool warpOn = __any_sync(0xFFFFFFFFu, R.rowOn);
+    unsigned slot = 0, prev = (RC_RDEPTH - 1) * K::RE_SLOT;    // ring slot of step s / of step s-1
+    unsigned po = 0, qo = K::B_PAR;                            // parity offsets of the b buffer read / written
+    const int s0 = s;
+    for (; s < nextStop; ++s) {
+        rc_cp_async16_if(myRE + prev, R.fPtr, fetchPred);      // pairs of step s + DEPTH - 1 -> slot of step s - 1
+        rc_cp_commit();
+        R.fPtr += strideD;
+        if (warpOn) {
+            double D = 1.0, e2o[NO > 0 ? NO : 1];
+#pragma unroll
+            for (int d = 0; d < NO; ++d) {
+                double g;
+                rc_lds128(R.aRE[d] + slot, g, e2o[d]);
+                D *= g;
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const bool v = j < R.M;
+                double gj = 1.0, e2j = 0.0;
+                if (v) rc_lds128(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
+                double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
+#pragma unroll
+                for (int d = 0; d < NO; ++d) {
+                    double nb = 0.0;
+                    if (v) nb = rc_lds64(R.aB[d] + po + (unsigned)j * 8u);
+                    t2 = fma(nb, e2o[d], t2);
+                }
+                R.b[j] = fma(R.b[j], D * gj, t2);                            // updateB, Core.hs:259
+                if (v) rc_sts64(R.myB + qo + (unsigned)j * 8u, R.b[j]);
+            }
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.b[0], R.dacc);   // updateD, Core.hs:282-288
+        }
+        rc_cp_wait<RC_RDEPTH - 2>();
+        __syncthreads();
+        prev = slot;
+        slot = slot + K::RE_SLOT == RC_RDEPTH * K::RE_SLOT ? 0u : slot + K::RE_SLOT;
+        const unsigned t = po; po = qo; qo = t;
+    }
+    return (s - s0) & 1;
+}
+
+template <int NO>
+__device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
+                                                 const int nextStop, const int Mw) {
+    switch (Mw) {
+        case 1: return rc_row_run<NO, 1>(R, sBase, strideD, s, nextStop);
+        case 2: return rc_row_run<NO, 2>(R, sBase, strideD, s, nextStop);
+        case 3: return rc_row_run<NO, 3>(R, sBase, strideD, s, nextStop);
+        case 4: return rc_row_run<NO, 4>(R, sBase, strideD, s, nextStop);
+        case 5: return rc_row_run<NO, 5>(R, sBase, strideD, s, nextStop);
+        case 6: return rc_row_run<NO, 6>(R, sBase, strideD, s, nextStop);
+        case 7: case 8: return rc_row_run<NO, 8>(R, sBase, strideD, s, nextStop);
+        default: return rc_row_run<NO, RC_ROW_MAXM>(R, sBase, strideD, s, nextStop);
+    }
+}
+
+__global__ void __launch_bounds__(RC_BLOCK, 3)
+rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
+                         const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
+                         const double* __restrict__ ktab, const double* __restrict__ aShort,
+                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
+                         long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    typedef RcRowSmem SM;
+    typedef RcRowK K;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    if (models[b].nSteps < 0 || models[b].mode != 1) return;
+    const int P = pl.P, nPat = pl.nPat;
+    SM& S = *reinterpret_cast<SM*>(smemRaw);
+    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int pat0 = pl.kBinPatOff[binIdx];
+    const int np = pl.kBinPatOff[binIdx + 1] - pat0;
+    const bool isLast = e + 1 == pl.nEpochs;
+    const int sShort = models[b].sShort;
+    const RcModelEpochDev mE = mep[models[b].mepOff + e];
+    const int* ro = pl.rowOff + (size_t)e * (nPat + 1);
+    const int* so = pl.slotOff + (size_t)e * (nPat + 1);
+
+    RcRowRegs R;
+#pragma unroll
+    for (int j = 0; j < RC_ROW_MAXM; ++j) R.b[j] = 0.0;
+    const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
+    const unsigned zeroB = sBase + K::O_B + K::ZERO_B;
+#pragma unroll
+    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+    R.aREr = padRE; R.myB = zeroB; R.M = 0; R.NO = 0;
+    R.unit = false; R.rowOn = false; R.fetchOn = false; R.dacc = 0.0;
+    R.fPtr = ktab;
+
+    // ---- set-up ----
+    if (tid < np) {
+        const int pid = pl.kBinPats[pat0 + tid];
+        S.patId[tid] = pid;
+        S.patDone[tid] = 0;
+        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + pid];
+    }
+    if (tid < 2 * RC_RDEPTH)                                                   // {1,0} padding pair of every ring slot
+        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
+    if (tid < 32) S.bbuf[(tid >> 4) * SM::BPAR + RC_ROW_BCAP + (tid & 15)] = 0.0;   // zero rows
+    __syncthreads();
+    if (tid == 0) {
+        int rrun = 0, brun = 0;
+        for (int p = 0; p < np; ++p) {
+            const int pid = S.patId[p];
+            const int nr = ro[pid + 1] - ro[pid];
+            const int Mp = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
+            S.patRowOff[p] = rrun;
+            S.patBOff[p] = brun;
+            rrun += nr;
+            brun += nr * (Mp | 1);
+        }
+        S.patRowOff[np] = rrun;
+        S.patBOff[np] = brun;
+    }
+    __syncthreads();
+    const int nRows = S.patRowOff[np];
+    R.rowOn = tid < nRows;
+    const uint16_t* myRefs = pl.rowRefAll;
+    int myPid = 0;
+    if (R.rowOn) {
+        const int p = rc_find_owner(S.patRowOff, np, tid);
+        const int rl = tid - S.patRowOff[p];
+        const int pid = S.patId[p];
+        myPid = pid;
+        const uint32_t pr = pl.patRow[(size_t)e * nPat + pid];
+        R.M = (int)(pr & 0xFFu);
+        const int rk = (int)((pr >> 8) & 0xFFu);
+        R.NO = (int)((pr >> 16) & 0xFFu);
+        const int Mp = R.M | 1;
+        const long long grow = pl.rowEpochBase[e] + ro[pid] + rl;
+        myRefs = pl.rowRefAll + grow * RC_ROW_MAXM;
+        const uint32_t* rw = pl.rowWordsAll + grow * RC_ROW_NO;
+        const uint16_t* rb = pl.kRowBase + (size_t)(pat0 + p) * P;
+        const unsigned patB = sBase + K::O_B + (unsigned)S.patBOff[p] * 8u;
+        R.myB = patB + (unsigned)(rl * Mp) * 8u;
+        R.aREr = sBase + K::O_RE + (unsigned)rb[rk] * 16u;
+        R.unit = R.NO == 0;                                     // x = e_r is the j = 1 state of a single-branch pattern
+#pragma unroll
+        for (int d = 0; d < RC_ROW_NO; ++d) {
+            if (d < R.NO) {
+                const uint32_t w = rw[d];
+                const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                const uint32_t up = w >> 16;
+                R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
+                if (up != RC_NO_UP) R.aB[d] = patB + (unsigned)((int)up * Mp) * 8u;
+            }
+        }
+        // ---- b of the row: seed state (epoch 0) or gather through the event's transition table ----
+        const int live = so[pid + 1] - so[pid];
+        if (e > 0) {
+            const int* trOff = pl.trOff + pl.trBase[e - 1];
+            const uint32_t* trEnt = pl.trEnt + pl.trEntBase[e - 1];
+            const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
+            const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
+#pragma unroll
+            for (int j = 0; j < RC_ROW_MAXM; ++j) {
+                if (j < R.M) {
+                    const int gl = so[pid] + (int)myRefs[j];
+                    const int e0 = trOff[gl], e1 = trOff[gl + 1];
+                    double acc = 0.0;
+                    for (int q = e0; q < e1; ++q) {
+                        const uint32_t en = trEnt[q];
+                        const uint32_t widx = en >> 16;
+                        const double old = bo[en & 0xFFFFu];
+                        acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
+                    }
+                    R.b[j] = acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RC_ROW_MAXM; ++j)
+                if (j < R.M) R.b[j] = ((int)myRefs[j] == live - 1) ? 1.0 : 0.0;      // the seed state, Core.hs:66
+        }
+#pragma unroll
+        for (int j = 0; j < RC_ROW_MAXM; ++j)
+            if (j < R.M) rc_sts64(R.myB + (unsigned)j * 8u, R.b[j]);
+    }
+    const int NOw = __reduce_max_sync(0xFFFFFFFFu, R.NO);
+    const int Mw = max(1, __reduce_max_sync(0xFFFFFFFFu, R.M));
+    const int rowPairs = pl.ep[e].rowPairs;
+    const long long strideD = (long long)rowPairs * 2;
+    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
+    R.fetchOn = tid < nFetch;
+    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    __syncthreads();
+
+    int s = mE.beg;
+    int cp = 0;
+    bool finished = false;
+    for (int phase = 0; phase < 2 && !finished; ++phase) {
+        int nextStop = mE.end;
+        if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
+        if (s < nextStop) {
+            R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+#pragma unroll
+            for (int u = 0; u < RC_RDEPTH - 1; ++u) {
+                rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
+                rc_cp_commit();
+                R.fPtr += strideD;
+            }
+            rc_cp_wait<RC_RDEPTH - 2>();
+            __syncthreads();
+            int par;
+            switch (NOw) {
+                case 0: par = rc_row_dispatch_m<0>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 1: par = rc_row_dispatch_m<1>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 2: par = rc_row_dispatch_m<2>(R, sBase, strideD, s, nextStop, Mw); break;
+                default: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
+            }
+            cp ^= par;
+            rc_cp_wait<0>();
+        }
+        // ---- updateD contributions of the run ----
+        S.dslot[tid] = R.dacc;
+        R.dacc = 0.0;
+        __syncthreads();
+        if (tid < np && !S.patDone[tid]) {
+            const int r0 = S.patRowOff[tid], cnt = S.patRowOff[tid + 1] - r0;
+            double acc = S.dpat[tid];
+            for (int i = 0; i < cnt; ++i) acc = acc + S.dslot[r0 + i];       // non-unit rows carry 0
+            S.dpat[tid] = acc;
+        }
+        if (!(isLast && phase == 0 && s == sShort && s < models[b].nSteps)) { finished = true; break; }
+        // ---- canUseShortcut / propagateStateShortcut (Core.hs:80-118) ----
+        // a pattern that passes has single-branch states only: one row, |x| = j
+        __syncthreads();
+        if (R.rowOn && pl.shortcutOK[myPid]) {
+            const double* aK = aShort + models[b].aShortOff;
+            const int* kid = pl.lastKeyId + (size_t)myPid * P;
+            double nrA = 0.0;
+            int popIndex = -1;
+            for (int k = 0; k < P; ++k) {
+                const double ak = aK[kid[k]];
+                nrA = nrA + ak;
+                if (popIndex < 0 && ak > 0.0) popIndex = k;
+            }
+            const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
+            // sum in the reference's live-list order (fillUp order = ascending j for a single branch)
+            double add = 0.0;
+#pragma unroll
+            for (int j = 0; j < RC_ROW_MAXM; ++j) {
+                if (j < R.M) {
+                    const int nd = j + 1;
+                    const double withComb = 2.0 * popSize / (double)nd;
+                    add = add + R.b[j] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
+                }
+            }
+            S.dslot[tid] = add;
+        } else S.dslot[tid] = 0.0;
+        __syncthreads();
+        int ok = 1;
+        if (tid < np) {
+            if (pl.shortcutOK[S.patId[tid]]) {
+                S.dpat[tid] = S.dpat[tid] + S.dslot[S.patRowOff[tid]];
+                S.patDone[tid] = 2;
+            } else ok = 0;
+        }
+        if (__syncthreads_and(ok)) { finished = true; break; }
+        // some pattern continues to the end of the grid: park the finished rows
+        if (R.rowOn && pl.shortcutOK[myPid]) {
+            R.rowOn = false;
+            R.unit = false;
+            R.M = 0;
+        }
+        // b of the continuing rows must sit at parity 0 for the next run
+        if (cp) {
+#pragma unroll
+            for (int j = 0; j < RC_ROW_MAXM; ++j)
+                if (j < R.M) rc_sts64(R.myB + (unsigned)j * 8u, R.b[j]);
+            cp = 0;
+        }
+        __syncthreads();
+    }
+    if (!isLast) {
+        if (tid < nRows) {
+            double* out = bCur + (size_t)b * bStride + so[myPid];
+#pragma unroll
+            for (int j = 0; j < RC_ROW_MAXM; ++j)
+                if (j < R.M) out[myRefs[j]] = R.b[j];
+        }
+        if (tid < np) dAcc[(size_t)b * nPat + S.patId[tid]] = S.dpat[tid];
+        return;
+    }
+    if (tid < np) {
+        const int pid = S.patId[tid];
+        const double d = S.dpat[tid];
+        double discFac = 1.0;
+        for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
+        pOut[(size_t)b * nPat + pid] = d * models[b].theta * pl.combFac[pid] * discFac;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One block per model; fixed summation order (thread-strided partials, then a shared-memory tree),
 // so results are reproducible run to run.
 __global__ void __launch_bounds__(1024)
@@ -1317,7 +1660,7 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
     return cudaGetLastError();
 }
 
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int rowMode, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
@@ -1329,6 +1672,17 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, con
     double* dac = dAcc + (size_t)b0 * pl.nPat;
     const double* bp = bPrev + (size_t)b0 * bStride;
     double* bc = bCur + (size_t)b0 * bStride;
+    if (rowMode) {
+        static bool cr = false;
+        const size_t rsmem = (sizeof(RcRowSmem) + 15) & ~(size_t)15;
+        if (!cr) {
+            cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+            if (err != cudaSuccess) return err;
+            cr = true;
+        }
+        rc_propagate_rows_kernel<<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        return cudaGetLastError();
+    }
     if (pl.nnzw <= 4) {
         if (!c4) {
             cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -162,6 +162,12 @@ struct PatPlan {
     std::vector<int> trCnt;         // per transition: live_{e+1} counts
     std::vector<uint32_t> trEnt;
     std::vector<uint8_t> mx;        // per epoch: P bytes, largest x_k over the live states
+    // row view of a box-shaped live set (one thread per row along the widest branch), per epoch
+    std::vector<uint8_t> rowOK, rowM, rowK, rowNO;   // usable / row length / row branch / other non-zero branches
+    std::vector<int> rowStride, rowCnt;              // reference-order stride of the row branch / number of rows
+    std::vector<uint32_t> rowWords;                  // per row RC_ROW_NO words (k | x<<8 | neighbour row<<16)
+    std::vector<uint16_t> rowRef;                    // per row: reference-order index of its x_r = 1 state
+    std::vector<uint16_t> rowRefs;                   // per row RC_ROW_MAXM reference-order indices (x_r = 1 .. M)
     bool shortcutOK = false;
     int maxLive = 0;
     int maxNnz = 0;
@@ -239,6 +245,70 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     int r = 0;
     for (int k = 0; k < c.P; ++k) r += pp.mx[m0 + (size_t)k];
     pp.maxR = std::max(pp.maxR, r);
+    // ---- row view ----
+    long long box = 1;
+    int rk = -1, rm = 0, nz = 0;
+    for (int k = 0; k < c.P; ++k) {
+        int mk = pp.mx[m0 + (size_t)k];
+        if (!mk) continue;
+        ++nz;
+        box *= mk;
+        if (mk > rm) { rm = mk; rk = k; }
+    }
+    bool ok = box == (long long)L.size() && nz >= 1 && nz - 1 <= RC_ROW_NO && rm <= RC_ROW_MAXM;
+    int stride = 1;
+    for (int k = rk + 1; k < c.P && ok; ++k) if (pp.mx[m0 + (size_t)k]) stride *= pp.mx[m0 + (size_t)k];
+    size_t rowStart = pp.rowRef.size();
+    if (ok) {
+        std::unordered_map<int, int> rowOfRef;
+        for (size_t i = 0; i < L.size(); ++i)
+            if (L[i].x[rk] == 1) { rowOfRef.emplace((int)i, (int)(pp.rowRef.size() - rowStart)); pp.rowRef.push_back((uint16_t)i); }
+        for (size_t q = rowStart; q < pp.rowRef.size() && ok; ++q) {
+            St s = L[pp.rowRef[q]];
+            int no = 0;
+            uint32_t w[RC_ROW_NO];
+            for (int d = 0; d < RC_ROW_NO; ++d) w[d] = 0xFFFF0000u;     // k = 0, x = 0: unused entry
+            for (int k = 0; k < c.P; ++k) {
+                int xk = s.x[k];
+                if (!xk || k == rk) continue;
+                uint32_t up = RC_NO_UP;
+                s.x[k] = (uint8_t)(xk + 1);
+                auto it = idx.find(c.key(s));
+                s.x[k] = (uint8_t)xk;
+                if (it != idx.end()) {
+                    auto rt = rowOfRef.find(it->second);
+                    if (rt == rowOfRef.end()) { ok = false; break; }
+                    up = (uint32_t)rt->second;
+                }
+                w[no++] = (uint32_t)k | ((uint32_t)xk << 8) | (up << 16);
+            }
+            for (int d = 0; d < RC_ROW_NO; ++d) pp.rowWords.push_back(w[d]);
+        }
+        // every row must be complete (x_r = 1..rm live); the reference-order index of each of its states is kept, since
+        // after a Join the live list is no longer in mixed-radix order (fillUp over several seeds, Core.hs:188)
+        const size_t nRows = pp.rowRef.size() - rowStart;
+        std::vector<uint16_t> refs(nRows * RC_ROW_MAXM, 0xFFFF);
+        for (size_t q = 0; q < nRows && ok; ++q) {
+            St s = L[pp.rowRef[rowStart + q]];
+            for (int j = 0; j < rm && ok; ++j) {
+                s.x[rk] = (uint8_t)(j + 1);
+                auto it = idx.find(c.key(s));
+                ok = it != idx.end();
+                if (ok) refs[q * RC_ROW_MAXM + (size_t)j] = (uint16_t)it->second;
+            }
+        }
+        if (ok) pp.rowRefs.insert(pp.rowRefs.end(), refs.begin(), refs.end());
+    }
+    if (!ok) {
+        pp.rowRef.resize(rowStart);
+        pp.rowWords.resize(rowStart * RC_ROW_NO);
+    }
+    pp.rowOK.push_back(ok ? 1 : 0);
+    pp.rowM.push_back((uint8_t)(ok ? rm : 0));
+    pp.rowK.push_back((uint8_t)(ok ? rk : 0));
+    pp.rowNO.push_back((uint8_t)(ok ? nz - 1 : 0));
+    pp.rowStride.push_back(ok ? stride : 0);
+    pp.rowCnt.push_back(ok ? (int)(pp.rowRef.size() - rowStart) : 0);
 }
 
 void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std::vector<StructEv>& sev,
@@ -563,9 +633,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
         struct OpenBin {
             std::vector<int> ids, slotsE, rowsUsed, rowsSelf;
+            int rowStates = 0;
             std::vector<std::unordered_map<int, int>> keyRows;   // per epoch: key -> pair rows needed
         };
-        auto pack_range = [&](int e0, int e1, int maxPats, std::vector<int>& patOff, std::vector<int>& pats) {
+        auto pack_range = [&](int e0, int e1, int maxPats, bool rowMode, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
             const size_t WINDOW = 12;
             std::vector<OpenBin> open;
@@ -578,7 +649,14 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         for (int k = 0; k < P; ++k) c += pps[(size_t)i].mx[(size_t)e0 * P + k] ? 1 : 0;
                         return c;
                     };
-                    std::stable_sort(ob.ids.begin(), ob.ids.end(), [&](int a, int b) { return nnzOf(a) > nnzOf(b); });
+                    if (rowMode)
+                        std::stable_sort(ob.ids.begin(), ob.ids.end(), [&](int a, int b) {
+                            const PatPlan &x = pps[(size_t)a], &y = pps[(size_t)b];
+                            if (x.rowNO[(size_t)e0] != y.rowNO[(size_t)e0]) return x.rowNO[(size_t)e0] > y.rowNO[(size_t)e0];
+                            return x.rowM[(size_t)e0] > y.rowM[(size_t)e0];
+                        });
+                    else
+                        std::stable_sort(ob.ids.begin(), ob.ids.end(), [&](int a, int b) { return nnzOf(a) > nnzOf(b); });
                 }
                 for (int i : ob.ids) pats.push_back(i);
                 patOff.push_back((int)pats.size());
@@ -587,7 +665,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 const PatPlan& pp = pps[(size_t)i];
                 if ((int)ob.ids.size() + 1 > maxPats) return false;
                 for (int q = 0; q < nE; ++q)
-                    if (ob.slotsE[(size_t)q] + pp.live[(size_t)(e0 + q)] > fastBlock) return false;
+                    if (ob.slotsE[(size_t)q] + (rowMode ? pp.rowCnt[(size_t)(e0 + q)] : pp.live[(size_t)(e0 + q)]) > fastBlock) return false;
+                // padded states of the rows (odd stride) must fit the block's b buffer
+                const int padAdd = rowMode ? pp.rowCnt[(size_t)e0] * (pp.rowM[(size_t)e0] | 1) : 0;
+                if (ob.rowStates + padAdd > RC_ROW_BCAP) return false;
                 std::vector<int> add((size_t)nE, 0), addSelf((size_t)nE, 0);
                 for (int q = 0; q < nE; ++q) {
                     const int e = e0 + q;
@@ -613,8 +694,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         if (mxk > have) { ob.rowsUsed[(size_t)q] += mxk - have; have = mxk; }
                     }
                     ob.rowsSelf[(size_t)q] += addSelf[(size_t)q];
-                    ob.slotsE[(size_t)q] += pp.live[(size_t)e];
+                    ob.slotsE[(size_t)q] += rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e];
                 }
+                ob.rowStates += padAdd;
                 ob.ids.push_back(i);
                 return true;
             };
@@ -676,15 +758,58 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // (1) bins spanning all epochs (self-contained fast kernel)
         out.fBinPatOff.assign(1, 0);
         out.fBinPats.clear();
-        pack_range(0, nEpochs - 1, maxPatFast, out.fBinPatOff, out.fBinPats);
+        pack_range(0, nEpochs - 1, maxPatFast, false, out.fBinPatOff, out.fBinPats);
         out.nFastBins = (int)out.fBinPatOff.size() - 1;
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         out.kBinBase.assign((size_t)nEpochs, 0);
         out.nKBins.assign((size_t)nEpochs, 0);
+        // row mode per epoch: every fast-tier pattern is a box with at most RC_ROW_NO + 1 non-zero branches and the rows are
+        // long enough to pay for the per-row overhead
+        out.epochMode.assign((size_t)nEpochs, 0);
+        out.rowOff.assign((size_t)nEpochs * (nPat + 1), 0);
+        out.rowEpochBase.assign((size_t)nEpochs, 0);
+        out.patRow.assign((size_t)nEpochs * nPat, 0u);
+        out.patRowStride.assign((size_t)nEpochs * nPat, 0);
+        const char* rowEnv = std::getenv("RC_ROWMODE");
+        for (int e = 0; e < nEpochs; ++e) {
+            bool all = !order.empty();
+            long long rows = 0, states = 0;
+            for (int i : order) {
+                all = all && pps[(size_t)i].rowOK[(size_t)e];
+                rows += pps[(size_t)i].rowCnt[(size_t)e];
+                states += pps[(size_t)i].live[(size_t)e];
+            }
+            bool use = all && rows > 0 && (double)states / (double)rows >= 2.5;
+            if (rowEnv) use = all && std::atoi(rowEnv) != 0;
+            out.epochMode[(size_t)e] = use ? 1 : 0;
+            out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
+            if (use) {
+                int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
+                long long run = 0;
+                std::vector<size_t> rpos((size_t)nPat, 0);
+                for (int i = 0; i < nPat; ++i) {
+                    const PatPlan& pp = pps[(size_t)i];
+                    ro[i] = (int)run;
+                    size_t r0 = 0;
+                    for (int q = 0; q < e; ++q) r0 += (size_t)pp.rowCnt[(size_t)q];
+                    const int n = pp.rowOK[(size_t)e] ? pp.rowCnt[(size_t)e] : 0;
+                    for (int q = 0; q < n; ++q) {
+                        for (int j = 0; j < RC_ROW_MAXM; ++j) out.rowRefAll.push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
+                        for (int d = 0; d < RC_ROW_NO; ++d) out.rowWordsAll.push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
+                    }
+                    run += n;
+                    out.patRow[(size_t)e * nPat + i] = (uint32_t)pp.rowM[(size_t)e] | ((uint32_t)pp.rowK[(size_t)e] << 8) |
+                                                      ((uint32_t)pp.rowNO[(size_t)e] << 16);
+                    out.patRowStride[(size_t)e * nPat + i] = pp.rowStride[(size_t)e];
+                }
+                ro[nPat] = (int)run;
+            }
+        }
         for (int e = 0; e < nEpochs; ++e) {
             out.kBinBase[(size_t)e] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
-            pack_range(e, e, RC_NPB, out.kBinPatOff, out.kBinPats);
+            if (out.epochMode[(size_t)e]) pack_range(e, e, RC_NPBR, true, out.kBinPatOff, out.kBinPats);
+            else pack_range(e, e, RC_NPB, false, out.kBinPatOff, out.kBinPats);
             out.nKBins[(size_t)e] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)e];
         }
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
@@ -701,8 +826,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 const PlanHost::Epoch& E = out.ep[(size_t)e];
                 int b0 = out.kBinBase[(size_t)e], nb = out.nKBins[(size_t)e];
                 int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
-                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d slots %lld bins %d fetch rows/bin %.1f\n", e,
-                             E.nKeys, E.nThr, E.rowPairs, (long long)0, nb, nb ? (double)(f1 - f0) / nb : 0.0);
+                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s bins %d fetch rows/bin %.1f\n", e,
+                             E.nKeys, E.nThr, E.rowPairs, out.epochMode[(size_t)e] ? "rows" : "states", nb, nb ? (double)(f1 - f0) / nb : 0.0);
             }
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
         }

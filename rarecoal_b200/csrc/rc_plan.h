@@ -70,6 +70,14 @@ struct PlanHost {
     std::vector<int> kFetchOff;            // same indexing as kBinPatOff -> kFetchRows
     std::vector<int> kFetchRows;           // pair offsets inside a step row, one per shared-memory pair row of a bin
     std::vector<uint16_t> kRowBase;        // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
+    // row mode (per epoch): one thread per row of states along the widest branch of a box-shaped live set
+    std::vector<int> epochMode;            // [nEpochs] 0: one state per thread, 1: one row per thread
+    std::vector<int> rowOff;               // [nEpochs][nPat+1] rows before a pattern in the epoch's row arrays
+    std::vector<long long> rowEpochBase;   // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
+    std::vector<uint16_t> rowRefAll;       // per row RC_ROW_MAXM reference-order indices (inside the pattern) of x_r = 1..M
+    std::vector<uint32_t> rowWordsAll;     // per row RC_ROW_NO words: k | x_k << 8 | neighbour row << 16
+    std::vector<uint32_t> patRow;          // [nEpochs][nPat] row length | row branch << 8 | other branches << 16
+    std::vector<int> patRowStride;         // [nEpochs][nPat] reference-order stride of the row branch
     long long maxEpochSlots = 0;           // largest number of live states in one epoch (stride of the b carry buffers)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]

@@ -14,6 +14,11 @@
 // event type codes (same values as RC_EV_JOIN / RC_EV_SPLIT in include/rarecoal_b200.h)
 #define RC_EV_JOIN_D 0
 #define RC_EV_SPLIT_D 1
+// row mode of the keyed tier: one thread per row of states along the widest branch of a box-shaped live set
+#define RC_ROW_NO 3          // other non-zero branches of a row at most
+#define RC_ROW_MAXM 10       // longest row
+#define RC_ROW_BCAP 1536     // states per row-mode block at most (rows are stored with an odd stride: no bank conflicts)
+#define RC_NPBR 128          // patterns per row-mode bin at most
 // keyed fast tier: shared-memory pair rows per parity (row 0 = {dt,0}, last row = {1,0} padding)
 #define RC_KROWS 256
 // how a trajectory key obtains its starting a from the previous epoch (popJoinA / popSplitA, Core.hs:165-170,195-200)
@@ -88,6 +93,13 @@ struct RcPlanDev {
     const int* kFetchRows;       // pair offset inside a step row for every shared-memory pair row of a bin
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
+    // ---- row mode ----
+    const int* epochMode;        // [nEpochs] 0: one state per thread, 1: one row per thread
+    const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
+    const long long* rowEpochBase; // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
+    const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states
+    const uint32_t* rowWordsAll; // per row RC_ROW_NO words: k | x_k << 8 | neighbour row << 16
+    const uint32_t* patRow;      // [nEpochs][nPat] row length | row branch << 8 | other branches << 16
 };
 
 struct RcEpochDev {
