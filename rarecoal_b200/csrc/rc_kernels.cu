@@ -70,6 +70,52 @@ __device__ __forceinline__ int rc_find_owner(const int* off, int np, int slot) {
     return lo;
 }
 
+// Exclusive prefix sum of the values held by threads tid < n (n <= RC_BLOCK) into out[0..n] (out[n] = total).
+// Must be called by all threads of the block; `warpTot` is scratch for RC_BLOCK/32 ints.
+__device__ __forceinline__ void rc_block_scan(int v, int n, int* out, int* warpTot) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int x = tid < n ? v : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warpTot[wid] = x;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += warpTot[w];
+    if (tid < n) out[tid + 1] = base + x;
+    if (tid == 0) out[0] = 0;
+    __syncthreads();
+}
+
+// new_b = sum over the transition entries [e0, e1) of old_b[src] * w, with several loads in flight
+__device__ __forceinline__ double rc_gather(const uint32_t* __restrict__ trEnt, int e0, int e1, const double* __restrict__ bo,
+                                            const double* __restrict__ W) {
+    double acc = 0.0;
+    int q = e0;
+    for (; q + 4 <= e1; q += 4) {
+        uint32_t en[4];
+        double old[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) en[u] = trEnt[q + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            old[u] = bo[en[u] & 0xFFFFu];
+            w[u] = (en[u] >> 16) == RC_W_ONE ? 1.0 : W[en[u] >> 16];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = (en[u] >> 16) == RC_W_ONE ? acc + old[u] : acc + old[u] * w[u];
+    }
+    for (; q < e1; ++q) {
+        const uint32_t en = trEnt[q];
+        const uint32_t widx = en >> 16;
+        const double old = bo[en & 0xFFFFu];
+        acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
+    }
+    return acc;
+}
+
 struct RcSmem {
     double *bA, *bB, *dacc, *a, *r, *dpat, *tab;
     uint32_t *words, *meta;
@@ -886,6 +932,7 @@ struct RcKeySmem {
     int patOff2[RC_NPB + 1];
     int patId[RC_NPB];
     int patDone[RC_NPB];
+    int scanTmp[RC_BLOCK / 32];
 };
 struct RcKeyK {
     static constexpr unsigned B_PAR = RcKeySmem::BSTRIDE * 8u;
@@ -1035,12 +1082,25 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
     if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                   // zero neighbours
     __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int p = 0; p < np; ++p) { S.patOff[p] = run; run += S.patOff2[p]; }
-        S.patOff[np] = run;
+    rc_block_scan(tid < np ? S.patOff2[tid] : 0, np, S.patOff, S.scanTmp);
+    // start the pair ring right away: its latency overlaps the rest of the set-up
+    const int rowPairs = pl.ep[e].rowPairs;
+    const long long strideD = (long long)rowPairs * 2;
+    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
+    R.fetchOn = tid < nFetch;
+    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    int s = mE.beg;
+    bool ringStarted = false;
+    if (s < mE.end) {
+        R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+#pragma unroll
+        for (int u = 0; u < RC_KDEPTH - 1; ++u) {
+            rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
+            rc_cp_commit();
+            R.fPtr += strideD;
+        }
+        ringStarted = true;
     }
-    __syncthreads();
     const int nSlots = S.patOff[np];
     R.slotOn = tid < nSlots;
     int myLocal = 0, myPid = 0;
@@ -1060,15 +1120,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
                 const uint32_t* trEnt = pl.trEnt + pl.trEntBase[e - 1];
                 const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
                 const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
-                const int e0 = trOff[gl], e1 = trOff[gl + 1];
-                double acc = 0.0;
-                for (int q = e0; q < e1; ++q) {
-                    const uint32_t en = trEnt[q];
-                    const uint32_t widx = en >> 16;
-                    const double old = bo[en & 0xFFFFu];
-                    acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
-                }
-                R.bv = acc;
+                R.bv = rc_gather(trEnt, trOff[gl], trOff[gl + 1], bo, W);
             } else {
                 // the seed state m is the last one fillUp emits (all components at their maximum), Core.hs:66
                 R.bv = (tid + 1 == S.patOff[p + 1]) ? 1.0 : 0.0;
@@ -1093,14 +1145,8 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         R.nw = max(1, __reduce_max_sync(0xFFFFFFFFu, n));
     }
     S.bbuf[tid] = R.bv;
-    const int rowPairs = pl.ep[e].rowPairs;
-    const long long strideD = (long long)rowPairs * 2;
-    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
-    R.fetchOn = tid < nFetch;
-    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
     __syncthreads();
 
-    int s = mE.beg;
     int cp = 0;
     bool finished = false;
     // at most two runs: up to the end of the epoch (or to the shortcut step in the last epoch), then — only if some
@@ -1109,13 +1155,16 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         int nextStop = mE.end;
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
-            R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+            if (!ringStarted) {
+                R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
 #pragma unroll
-            for (int u = 0; u < RC_KDEPTH - 1; ++u) {
-                rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
-                rc_cp_commit();
-                R.fPtr += strideD;
+                for (int u = 0; u < RC_KDEPTH - 1; ++u) {
+                    rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
+                    rc_cp_commit();
+                    R.fPtr += strideD;
+                }
             }
+            ringStarted = false;
             rc_cp_wait<RC_KDEPTH - 2>();
             __syncthreads();
             switch (R.nw) {
@@ -1220,6 +1269,7 @@ struct RcRowSmem {
     int patBOff[RC_NPBR + 1];
     int patId[RC_NPBR];
     int patDone[RC_NPBR];
+    int scanTmp[RC_BLOCK / 32];
 };
 struct RcRowK {
     static constexpr unsigned B_PAR = RcRowSmem::BPAR * 8u;
@@ -1346,24 +1396,64 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
         S.patId[tid] = pid;
         S.patDone[tid] = 0;
         S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + pid];
+        const int nr = ro[pid + 1] - ro[pid];
+        const int Mp = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
+        S.patRowOff[tid] = nr;                                                 // counts; turned into offsets below
+        S.patBOff[tid] = nr * (Mp | 1);
     }
     if (tid < 2 * RC_RDEPTH)                                                   // {1,0} padding pair of every ring slot
         S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
     if (tid < 32) S.bbuf[(tid >> 4) * SM::BPAR + RC_ROW_BCAP + (tid & 15)] = 0.0;   // zero rows
     __syncthreads();
-    if (tid == 0) {
-        int rrun = 0, brun = 0;
-        for (int p = 0; p < np; ++p) {
-            const int pid = S.patId[p];
-            const int nr = ro[pid + 1] - ro[pid];
-            const int Mp = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
-            S.patRowOff[p] = rrun;
-            S.patBOff[p] = brun;
-            rrun += nr;
-            brun += nr * (Mp | 1);
+    {
+        const int nr = tid < np ? S.patRowOff[tid] : 0, nb = tid < np ? S.patBOff[tid] : 0;
+        __syncthreads();
+        rc_block_scan(nr, np, S.patRowOff, S.scanTmp);
+        rc_block_scan(nb, np, S.patBOff, S.scanTmp);
+    }
+    // start the pair ring right away: its latency overlaps the rest of the set-up
+    const int rowPairs = pl.ep[e].rowPairs;
+    const long long strideD = (long long)rowPairs * 2;
+    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
+    R.fetchOn = tid < nFetch;
+    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    int s = mE.beg;
+    bool ringStarted = false;
+    if (s < mE.end) {
+        R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+#pragma unroll
+        for (int u = 0; u < RC_RDEPTH - 1; ++u) {
+            rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
+            rc_cp_commit();
+            R.fPtr += strideD;
         }
-        S.patRowOff[np] = rrun;
-        S.patBOff[np] = brun;
+        ringStarted = true;
+    }
+    // ---- b of every state of the bin into shared memory (parity 0), all threads cooperating: the seed state (epoch 0)
+    //      or a gather through the event's transition table from the previous launch's carry buffer ----
+    {
+        const int nB = S.patBOff[np];
+        const int* trOff = e > 0 ? pl.trOff + pl.trBase[e - 1] : nullptr;
+        const uint32_t* trEnt = e > 0 ? pl.trEnt + pl.trEntBase[e - 1] : nullptr;
+        const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
+        for (int i = tid; i < nB; i += RC_BLOCK) {
+            const int p = rc_find_owner(S.patBOff, np, i);
+            const int pid = S.patId[p];
+            const int Mq = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
+            const int Mp = Mq | 1;
+            const int li = i - S.patBOff[p];
+            const int rl = li / Mp, j = li - rl * Mp;
+            double v = 0.0;
+            if (j < Mq) {
+                const int ref = (int)pl.rowRefAll[(pl.rowEpochBase[e] + ro[pid] + rl) * RC_ROW_MAXM + j];
+                if (e > 0) {
+                    const int gl = so[pid] + ref;
+                    const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
+                    v = rc_gather(trEnt, trOff[gl], trOff[gl + 1], bo, W);
+                } else v = (ref == so[pid + 1] - so[pid] - 1) ? 1.0 : 0.0;       // the seed state, Core.hs:66
+            }
+            S.bbuf[i] = v;
+        }
     }
     __syncthreads();
     const int nRows = S.patRowOff[np];
@@ -1398,60 +1488,31 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
                 if (up != RC_NO_UP) R.aB[d] = patB + (unsigned)((int)up * Mp) * 8u;
             }
         }
-        // ---- b of the row: seed state (epoch 0) or gather through the event's transition table ----
-        const int live = so[pid + 1] - so[pid];
-        if (e > 0) {
-            const int* trOff = pl.trOff + pl.trBase[e - 1];
-            const uint32_t* trEnt = pl.trEnt + pl.trEntBase[e - 1];
-            const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
-            const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
-#pragma unroll
-            for (int j = 0; j < RC_ROW_MAXM; ++j) {
-                if (j < R.M) {
-                    const int gl = so[pid] + (int)myRefs[j];
-                    const int e0 = trOff[gl], e1 = trOff[gl + 1];
-                    double acc = 0.0;
-                    for (int q = e0; q < e1; ++q) {
-                        const uint32_t en = trEnt[q];
-                        const uint32_t widx = en >> 16;
-                        const double old = bo[en & 0xFFFFu];
-                        acc = (widx == RC_W_ONE) ? acc + old : acc + old * W[widx];
-                    }
-                    R.b[j] = acc;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < RC_ROW_MAXM; ++j)
-                if (j < R.M) R.b[j] = ((int)myRefs[j] == live - 1) ? 1.0 : 0.0;      // the seed state, Core.hs:66
-        }
+        // b of the row from shared memory (filled cooperatively above)
 #pragma unroll
         for (int j = 0; j < RC_ROW_MAXM; ++j)
-            if (j < R.M) rc_sts64(R.myB + (unsigned)j * 8u, R.b[j]);
+            if (j < R.M) R.b[j] = rc_lds64(R.myB + (unsigned)j * 8u);
     }
     const int NOw = __reduce_max_sync(0xFFFFFFFFu, R.NO);
     const int Mw = max(1, __reduce_max_sync(0xFFFFFFFFu, R.M));
-    const int rowPairs = pl.ep[e].rowPairs;
-    const long long strideD = (long long)rowPairs * 2;
-    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
-    R.fetchOn = tid < nFetch;
-    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
     __syncthreads();
 
-    int s = mE.beg;
     int cp = 0;
     bool finished = false;
     for (int phase = 0; phase < 2 && !finished; ++phase) {
         int nextStop = mE.end;
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
-            R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
+            if (!ringStarted) {
+                R.fPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff) * 2;
 #pragma unroll
-            for (int u = 0; u < RC_RDEPTH - 1; ++u) {
-                rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
-                rc_cp_commit();
-                R.fPtr += strideD;
+                for (int u = 0; u < RC_RDEPTH - 1; ++u) {
+                    rc_cp_async16_if(sBase + K::O_RE + (unsigned)u * K::RE_SLOT + tid * 16u, R.fPtr, R.fetchOn ? 1u : 0u);
+                    rc_cp_commit();
+                    R.fPtr += strideD;
+                }
             }
+            ringStarted = false;
             rc_cp_wait<RC_RDEPTH - 2>();
             __syncthreads();
             int par;
