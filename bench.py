@@ -147,6 +147,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=44, help="models per GPU per step (44 = central differences, C4)")
+    ap.add_argument("--shard", choices=["models", "patterns"], default="models",
+                    help="N>1: models = every rank evaluates its own models on all patterns (no data-path collective, "
+                         "log-likelihoods gathered at the end); patterns = every rank evaluates a pattern shard of all "
+                         "models and the partial sums are all-reduced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -172,36 +176,44 @@ def main():
     times = R.defaultTimes()
     eng = R.Engine(local)
     eng.set_problem(nvec, MAXAF_C3, pats, cnt, Wk.TOTAL_SITES)
-    eng.set_shard(rank, world)
+    by_pattern = args.shard == "patterns" and world > 1
+    if by_pattern:
+        eng.set_shard(rank, world)
     eng.set_times(times)
-    B = args.batch * world
+    B = args.batch * world                     # models per step over all ranks (weak scaling)
     n_it = args.warmup + args.steps
     batches = make_batches(n_it, B)
+    if not by_pattern:                         # this rank's slice of every batch
+        batches = [evs[rank * args.batch:(rank + 1) * args.batch] for evs in batches]
+    Bl = len(batches[0])                       # models this rank evaluates per step
     packed = []
     for evs in batches:
         flat = [e for m in evs for e in m]
         off = np.cumsum([0] + [len(m) for m in evs]).astype(np.int32)
-        packed.append((R.api._events_array(flat), off, np.full(B, 0.0005), np.ones(B * P_C3)))
-    h2d = sum(len(m) for m in batches[0]) * ctypes.sizeof(R._lib.rc_event) + B * (4 + 8 + 8 * P_C3)
+        packed.append((R.api._events_array(flat), off, np.full(Bl, 0.0005), np.ones(Bl * P_C3)))
+    h2d = world * (sum(len(m) for m in batches[0]) * ctypes.sizeof(R._lib.rc_event) + Bl * (4 + 8 + 8 * P_C3))
     d2h = 8 * B
 
     stream = torch.cuda.current_stream()
-    partial = torch.zeros(2 * B, dtype=torch.float64, device="cuda")
+    partial = torch.zeros(2 * Bl, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(B, dtype=torch.float64, device="cuda")
 
     def step_device(i):
         ev, off, th, dc = packed[i]
         eng.eval_partial(ev, off, th, dc, False, partial.data_ptr(), None, stream.cuda_stream)
-        if world > 1:
+        if by_pattern:
             dist.all_reduce(partial)
 
     def step_e2e(i):
         ev, off, th, dc = packed[i]
-        if world == 1:
-            logl, _, _ = eng.eval_raw(ev, off, th, dc, False, 1.0)
+        if not by_pattern:
+            logl, _, _ = eng.eval_raw(ev, off, th, dc, False, 1.0)       # host buffers in, host log-likelihoods out
+            if world > 1:                                                # results of all ranks to every rank
+                dist.all_gather_into_tensor(gathered, torch.from_numpy(logl).cuda())
             return logl
         eng.eval_partial(ev, off, th, dc, False, partial.data_ptr(), None, stream.cuda_stream)
         dist.all_reduce(partial)
-        return eng.finalize(B, partial.data_ptr(), 1.0, stream.cuda_stream)
+        return eng.finalize(Bl, partial.data_ptr(), 1.0, stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -232,7 +244,7 @@ def main():
         st = eng.stats()
         kernel_ms.append(st["kernel_ms"] - st["traj_ms"])
         traj_ms.append(st["traj_ms"])
-        launches += st["launches"] + (1 if world > 1 else 0)
+        launches += st["launches"] + (1 if by_pattern else 0)
         w_steps = st["state_steps"]
     # ---- end-to-end timing (host buffers in, host logl out) ---------------------------------------------------
     for i in range(args.warmup):
@@ -277,7 +289,9 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": B,
-                       "parallelism": f"patterns sharded over {world} rank(s), all-reduce of 2*B doubles",
+                       "parallelism": (f"patterns sharded over {world} ranks, NCCL all-reduce of 2*B doubles per step" if by_pattern
+                                       else f"models sharded over {world} rank(s): {args.batch} models per rank and step on all patterns, "
+                                            "no data-path collective (log-likelihoods all-gathered in the e2e path)"),
                        "l2": "fresh parameter batch each step; the trajectory tables (~60 MB per model, larger than L2 for the "
                              "batch) are rewritten by rc_traj_kernel every step",
                        "single_logl_latency_ms": lat_ms,
