@@ -144,6 +144,7 @@ struct rc_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t evt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool trajTimed = false;
+    int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
     bool statsPending = false;
     bool blobInFlight = false;
     rc_stats stats;
@@ -420,12 +421,8 @@ long long count_state_steps(const ModelHost& mh, const rc::PlanHost& h, int T) {
 }
 
 // The whole evaluation up to the per-model partial sums (left on the device).
-int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
-              int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus) {
-    if (ctx->P == 0) { ctx->err = "rc_set_problem has not been called"; return RC_ERR_ARG; }
-    if (ctx->times.empty()) { ctx->err = "rc_set_times has not been called"; return RC_ERR_ARG; }
-    if (B <= 0) return RC_OK;
-    if (B > 32768) { ctx->err = "at most 32768 models per call; split the batch"; return RC_ERR_ARG; }
+int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
+               int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus, long long* maxPairsOut) {
     if (ctx->plans.size() >= 64) ctx->clear_plans();   // bounded plan cache
     const int P = ctx->P, A1 = ctx->maxAf + 1, T = (int)ctx->times.size();
     const int rowLen = rc_row_len(P, A1);
@@ -526,6 +523,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
                 maxRowPairs = std::max<long long>(maxRowPairs, hp.ep[(size_t)e].rowPairs);
             }
             M.mode = (ctx->optKeyed && hp.nFastBins > 0 && pairs <= ktabModelMax && ktabPairs + pairs <= ktabTotalMax) ? 1 : 0;
+            if (maxPairsOut && pairs > *maxPairsOut) *maxPairsOut = pairs;
             if (M.mode == 1) {
                 ktabPairs += pairs;
                 M.aEndOff = aEndDoubles;
@@ -668,6 +666,43 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     CK(cudaEventRecord(ctx->evt[4], st));
     ctx->stats.launches = launches;
     ctx->statsPending = true;
+    return RC_OK;
+}
+
+int collect_stats(rc_ctx* ctx);
+
+// Evaluates B models in chunks sized so that the trajectory tables of one chunk stay inside the memory budget
+// ("ktab_total_mb"); chunks run back to back on the same stream.
+int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
+              int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus) {
+    if (ctx->P == 0) { ctx->err = "rc_set_problem has not been called"; return RC_ERR_ARG; }
+    if (ctx->times.empty()) { ctx->err = "rc_set_times has not been called"; return RC_ERR_ARG; }
+    if (B <= 0) return RC_OK;
+    const long long totalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
+    rc_stats acc;
+    std::memset(&acc, 0, sizeof acc);
+    int done = 0, nChunks = 0;
+    while (done < B) {
+        int n = std::min(B - done, std::max(1, std::min(ctx->chunkHint, 32768)));
+        long long maxPairs = 0;
+        int rc = eval_chunk(ctx, n, ev, evOff + done, theta + done, disc + (size_t)done * ctx->P, noShortcut, dPartial + 2 * (size_t)done,
+                            dProbs ? dProbs + (size_t)done * ctx->nPatGlobal : nullptr, st, outStatus ? outStatus + done : nullptr,
+                            &maxPairs);
+        if (rc != RC_OK) return rc;
+        if (maxPairs > 0) ctx->chunkHint = (int)std::max<long long>(1, std::min<long long>(32768, totalMax / maxPairs));
+        done += n;
+        ++nChunks;
+        if (done < B || nChunks > 1) {      // several chunks: fold this chunk's counters into the running totals
+            rc = collect_stats(ctx);
+            if (rc != RC_OK) return rc;
+            acc.state_steps += ctx->stats.state_steps; acc.slots += ctx->stats.slots;
+            acc.kernel_ms += ctx->stats.kernel_ms; acc.traj_ms += ctx->stats.traj_ms; acc.tables_ms += ctx->stats.tables_ms;
+            acc.total_ms += ctx->stats.total_ms; acc.launches += ctx->stats.launches;
+            acc.plan_cache_hit = nChunks == 1 ? ctx->stats.plan_cache_hit : (acc.plan_cache_hit && ctx->stats.plan_cache_hit);
+            acc.n_epochs = ctx->stats.n_epochs; acc.n_steps = ctx->stats.n_steps;
+            if (done == B) ctx->stats = acc;
+        }
+    }
     return RC_OK;
 }
 
