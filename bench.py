@@ -3,15 +3,17 @@
 synthetic 8-population balanced tree, maxAf=10, 43 757 patterns, default 3043-point grid.
 
 A "step" = one batch of B_total = batch * n_gpus parameter vectors (C4-style single-coordinate perturbations of
-the C3 parameters; a fresh batch every step) evaluated against the resident histogram.  Patterns are sharded
-across ranks; each rank evaluates its slice for every model of the batch and the two partial sums per model are
-combined with one NCCL all-reduce (weak scaling: per-GPU work is fixed as N grows).
+the C3 parameters; a fresh batch every step) evaluated against the resident histogram.  Weak scaling: per-GPU work
+is fixed as N grows.  Default sharding is by MODEL (independent objects: every rank evaluates its own `batch` models
+on all patterns, no data-path collective; the log-likelihoods are all-gathered in the e2e path).  `--shard patterns`
+shards the patterns instead and all-reduces the two partial sums per model over NCCL.
 
   value  logl evals/s, parameter batch marshalled before the timed region, partials left on the device
   e2e    same metric through the C-ABI call with HOST buffers: per step the event arrays go host->device and
          the B log-likelihoods come back device->host
-  roofline  propagation kernel, FP64 FMA pipe: achieved = state-steps * (4P+27) flops / CUDA-event kernel time,
-         peak = DFMA rate measured on this GPU by rc_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)
+  roofline  propagation kernels (one launch per structural epoch), FP64 FMA pipe: achieved = state-steps * (4P+27)
+         flops / CUDA-event time of those launches, peak = DFMA rate measured on this GPU by rc_fp64_peak
+         (MEASURED_PEAKS.json has no FP64 figure); traffic = DRAM bytes of the same launches from the committed ncu capture
   cpu_baseline  the CPU oracle (port of the reference's algorithm; the Haskell reference cannot be built here)
          on a bounded pattern sample with all host cores, scaled to the full pattern set by state-steps
 
@@ -301,7 +303,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": TRAFFIC,
-                         "kernel": "rc_propagate_keyed_kernel", "kernel_ms": k_ms, "traj_kernels_ms": traj_mean,
+                         "kernel": "propagation launches, one per structural epoch: rc_propagate_keyed_kernel (epochs 0-3) + "
+                                   "rc_propagate_rows_kernel (epochs 4-7)",
+                         "kernel_ms": k_ms, "traj_kernels_ms": traj_mean,
                          "algorithmic": f"{w_steps} state-steps x {FLOPS_PER_STATE_STEP} flops per launch (rank 0)",
                          "peak_source": "rc_fp64_peak DFMA microbenchmark on this GPU (no FP64 figure in MEASURED_PEAKS.json)",
                          "hbm_note": "algorithmic HBM bytes ~24 B x patterns x models per launch: not the bound"},
