@@ -87,7 +87,8 @@ int rc_set_problem(rc_ctx* ctx, int P, int maxAf, int nPat, const int32_t* patte
                    const int32_t* nVec, const int64_t* counts, int64_t totalSites);
 
 /* Pattern sharding for the multi-GPU path: this context evaluates only the patterns dealt to `rank`
- * of `world` (work-sorted round-robin).  Call after rc_set_problem; default (0,1).                 */
+ * of `world` (contiguous chunks of equal work in lexicographic pattern order, so that a rank's patterns share
+ * their trajectory keys).  Call after rc_set_problem; default (0,1).                                */
 int rc_set_shard(rc_ctx* ctx, int rank, int world);
 
 /* mTimeSteps (StateSpace.hs:44; Utils.hs:64-73).  t[0..T) strictly increasing, > 0.               */

@@ -719,21 +719,37 @@ int collect_stats(rc_ctx* ctx) {
     return RC_OK;
 }
 
-// Work-sorted round-robin deal of patterns to ranks (host only).  Work proxy: live states at t=0 = prod max(1, m_k).
+// Deal of patterns to ranks (host only).  Patterns are ordered lexicographically and cut into `world` contiguous
+// chunks of (nearly) equal work, so that the patterns of a rank share their trajectory keys (each rank then needs about
+// 1/world of the keys instead of all of them).  Work proxy: live states at t=0 = prod max(1, m_k).
 std::vector<int> shard_patterns(int P, int n, const int32_t* pats, int rank, int world) {
     std::vector<int> order((size_t)n);
     std::vector<long long> work((size_t)n);
+    long long total = 0;
     for (int i = 0; i < n; ++i) {
         long long w = 1;
         for (int k = 0; k < P; ++k) w *= std::max(1, pats[(size_t)i * P + k]);
         work[(size_t)i] = w;
+        total += w;
         order[(size_t)i] = i;
     }
     if (world > 1)
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[(size_t)a] > work[(size_t)b]; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int32_t* x = pats + (size_t)a * P;
+            const int32_t* y = pats + (size_t)b * P;
+            for (int k = 0; k < P; ++k) if (x[k] != y[k]) return x[k] < y[k];
+            return false;
+        });
     std::vector<int> mine;
-    for (int j = 0; j < n; ++j)
-        if (j % world == rank) mine.push_back(order[(size_t)j]);
+    long long run = 0;
+    for (int j = 0; j < n; ++j) {
+        // pattern j belongs to the rank whose work interval contains the midpoint of its own work
+        const long long mid = run + work[(size_t)order[(size_t)j]] / 2;
+        int r = total > 0 ? (int)((__int128)mid * world / total) : 0;
+        if (r >= world) r = world - 1;
+        if (r == rank) mine.push_back(order[(size_t)j]);
+        run += work[(size_t)order[(size_t)j]];
+    }
     std::sort(mine.begin(), mine.end());
     return mine;
 }
