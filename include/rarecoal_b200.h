@@ -167,7 +167,8 @@ int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int wo
 
 /* Runs the host planner only (no device): executed state-steps (one unit = one iteration of the
  * updateB loop, Core.hs:248), live states at t=0, largest live set of a pattern, structural epochs and
- * kernel bins for this problem/model.  Used for roofline accounting and to check the planner on CPU. */
+ * kernel bins for this problem/model, after a bounds / capacity self-check of the compiled plan (RC_ERR_UNSUPPORTED
+ * if it fails).  Used for roofline accounting and to check the planner on CPU.                       */
 int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T,
                   const double* times, const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps,
                   int64_t* slots0, int32_t* maxLive, int32_t* nEpochs, int32_t* nBins);

@@ -1114,6 +1114,8 @@ int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int
     rc::PlanHost h;
     std::string e = rc::build_plan(P, maxAf, nPat, patterns, nVec, mh.sev, mh.gaps, mh.hasSplit, 227 * 1024, h);
     if (!e.empty()) return RC_ERR_UNSUPPORTED;
+    e = rc::check_plan(h);
+    if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
     if (stateSteps) *stateSteps = count_state_steps(mh, h, T);
     if (slots0) *slots0 = h.epochSlots[0];
     if (maxLive) *maxLive = h.maxLive;

@@ -911,4 +911,128 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     return "";
 }
 
+
+// Structural self-check of a plan: every index a kernel dereferences is inside its array and every bin respects the
+// shared-memory limits of the kernel that runs it.  Returns "" or a description of the first violation.  (The pool's
+// compute-sanitizer is closed, so the bounds are verified on the host — tests/test_host_cpu.py runs this on every
+// workload shape.)
+std::string check_plan(const PlanHost& h) {
+    const int P = h.P, nPat = h.nPat, nE = h.nEpochs;
+    auto fail = [](const std::string& m) { return std::string("plan check: ") + m; };
+    if ((int)h.slotOff.size() != nE * (nPat + 1)) return fail("slotOff size");
+    for (int e = 0; e < nE; ++e) {
+        const int* so = &h.slotOff[(size_t)e * (nPat + 1)];
+        for (int i = 0; i < nPat; ++i) {
+            const int live = so[i + 1] - so[i];
+            if (live < 1) return fail("empty live set");
+            const long long g0 = h.epochBase[(size_t)e] + so[i];
+            for (int s = 0; s < live; ++s) {
+                const uint32_t mt = h.meta[(size_t)(g0 + s)];
+                const int nnz = (int)(mt & 0xFFu);
+                if (nnz < 1 || nnz > h.nnzw) return fail("nnz out of range");
+                for (int d = 0; d < nnz; ++d) {
+                    const uint32_t w = h.words[(size_t)(g0 + s) * h.nnzw + d];
+                    const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                    const uint32_t up = w >> 16;
+                    if (k >= P || x < 1 || x > h.maxAf) return fail("word k/x out of range");
+                    if (x > h.maxX[((size_t)e * nPat + i) * P + k]) return fail("x above maxX");
+                    if (up != RC_NO_UP && (int)up >= live) return fail("neighbour slot out of range");
+                }
+            }
+            if (e > 0) {
+                const int livePrev = h.slotOff[(size_t)(e - 1) * (nPat + 1) + i + 1] - h.slotOff[(size_t)(e - 1) * (nPat + 1) + i];
+                const int* trOff = &h.trOff[(size_t)h.trBase[(size_t)e - 1]];
+                for (int s = 0; s < live; ++s) {
+                    const int a = trOff[so[i] + s], b = trOff[so[i] + s + 1];
+                    if (a > b) return fail("transition offsets not monotone");
+                    for (int q = a; q < b; ++q) {
+                        const uint32_t en = h.trEnt[(size_t)(h.trEntBase[(size_t)e - 1] + q)];
+                        if ((int)(en & 0xFFFFu) >= livePrev) return fail("transition source out of range");
+                        const uint32_t widx = en >> 16;
+                        if (widx != RC_W_ONE && (int)widx >= (h.maxAf + 1) * (h.maxAf + 1)) return fail("weight index out of range");
+                    }
+                }
+            }
+        }
+    }
+    // keyed per-epoch bins
+    if (!h.kBinBase.empty()) {
+        std::vector<char> seen;
+        for (int e = 0; e < nE; ++e) {
+            const PlanHost::Epoch& E = h.ep[(size_t)e];
+            const bool rows = h.epochMode[(size_t)e] != 0;
+            seen.assign((size_t)nPat, 0);
+            const int b0 = h.kBinBase[(size_t)e];
+            for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
+                const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
+                if (p1 - p0 < 1 || p1 - p0 > (rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
+                const int f0 = h.kFetchOff[(size_t)bI], f1 = h.kFetchOff[(size_t)bI + 1];
+                if (f1 - f0 < 1 || f1 - f0 > RC_KROWS - 1) return fail("pair rows per keyed bin");
+                for (int q = f0; q < f1; ++q)
+                    if (h.kFetchRows[(size_t)q] < 0 || h.kFetchRows[(size_t)q] >= E.rowPairs) return fail("fetch row out of range");
+                long long lanes = 0, padded = 0;
+                for (int q = p0; q < p1; ++q) {
+                    const int i = h.kBinPats[(size_t)q];
+                    if (i < 0 || i >= nPat || seen[(size_t)i]) return fail("pattern missing or repeated in keyed bins");
+                    seen[(size_t)i] = 1;
+                    const int live = h.slotOff[(size_t)e * (nPat + 1) + i + 1] - h.slotOff[(size_t)e * (nPat + 1) + i];
+                    for (int k = 0; k < P; ++k) {
+                        const int mxk = h.maxX[((size_t)e * nPat + i) * P + k];
+                        if (!mxk) continue;
+                        const int rb = h.kRowBase[(size_t)q * P + k];
+                        if (rb < 1 || rb + mxk - 1 > f1 - f0 - 1) return fail("pair-row base out of range");
+                    }
+                    if (rows) {
+                        const uint32_t pr = h.patRow[(size_t)e * nPat + i];
+                        const int M = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
+                        const int nr = h.rowOff[(size_t)e * (nPat + 1) + i + 1] - h.rowOff[(size_t)e * (nPat + 1) + i];
+                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || rk >= P || nr * M != live) return fail("row shape");
+                        lanes += nr;
+                        padded += (long long)nr * (M | 1);
+                        for (int r = 0; r < nr; ++r) {
+                            const long long gr = h.rowEpochBase[(size_t)e] + h.rowOff[(size_t)e * (nPat + 1) + i] + r;
+                            for (int j = 0; j < M; ++j)
+                                if ((int)h.rowRefAll[(size_t)gr * RC_ROW_MAXM + j] >= live) return fail("row state index out of range");
+                            for (int d = 0; d < NO; ++d) {
+                                const uint32_t w = h.rowWordsAll[(size_t)gr * RC_ROW_NO + d];
+                                const uint32_t up = w >> 16;
+                                if ((int)(w & 0xFFu) >= P || (up != RC_NO_UP && (int)up >= nr)) return fail("row word out of range");
+                            }
+                        }
+                    } else lanes += live;
+                }
+                if (lanes > RC_BLOCK) return fail("lanes per keyed bin");
+                if (padded > RC_ROW_BCAP) return fail("padded states per row bin");
+            }
+        }
+    }
+    // all-epoch fast bins and big bins
+    for (int bI = 0; bI < h.nFastBins; ++bI) {
+        const int p0 = h.fBinPatOff[(size_t)bI], p1 = h.fBinPatOff[(size_t)bI + 1];
+        if (p1 - p0 < 1 || (p1 - p0) * P > h.fastBlock || p1 - p0 > RC_NPB) return fail("patterns per fast bin");
+        for (int e = 0; e < nE; ++e) {
+            long long slots = 0, rr = 0;
+            for (int q = p0; q < p1; ++q) {
+                const int i = h.fBinPats[(size_t)q];
+                slots += h.slotOff[(size_t)e * (nPat + 1) + i + 1] - h.slotOff[(size_t)e * (nPat + 1) + i];
+                for (int k = 0; k < P; ++k) rr += h.maxX[((size_t)e * nPat + i) * P + k];
+            }
+            if (slots > h.fastBlock || rr > 2 * h.fastBlock - 2) return fail("fast bin over capacity");
+        }
+    }
+    for (int bI = 0; bI < h.nBins; ++bI) {
+        const int p0 = h.binPatOff[(size_t)bI], p1 = h.binPatOff[(size_t)bI + 1];
+        if (p1 - p0 < 1 || p1 - p0 > RC_NPB) return fail("patterns per big bin");
+        for (int e = 0; e < nE; ++e) {
+            long long slots = 0;
+            for (int q = p0; q < p1; ++q) {
+                const int i = h.binPats[(size_t)q];
+                slots += h.slotOff[(size_t)e * (nPat + 1) + i + 1] - h.slotOff[(size_t)e * (nPat + 1) + i];
+            }
+            if (slots > h.cap) return fail("big bin over capacity");
+        }
+    }
+    return "";
+}
+
 }  // namespace rc

@@ -98,4 +98,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                        const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
                        int smemBudgetBytes, PlanHost& out);
 
+// Bounds / capacity self-check of a built plan ("" if consistent).
+std::string check_plan(const PlanHost& h);
+
 }  // namespace rc

@@ -118,6 +118,19 @@ def test_planner_state_steps_match_oracle_on_edge_models(events, no_shortcut, T)
     assert st["state_steps"] == w
 
 
+def test_plan_self_check_on_every_workload_shape(fourpop):
+    # rc_plan_stats also runs the planner's bounds / capacity self-check (every index a kernel dereferences, every
+    # bin against the shared-memory limits of its kernel): trees (state and row mode), admixture, big-tier patterns
+    T = R.defaultTimes()
+    nv10 = [100] * 10
+    assert R.planStats(nv10, 4, R.computeStandardOrder(nv10, 4), T, Wk.c5_events())["n_epochs"] == 13
+    nvec, pats, _ = Wk.c3_problem(max_af=6)
+    assert R.planStats(nvec, 6, pats, T, Wk.c3_events())["max_live"] <= 16
+    std8 = R.computeStandardOrder(fourpop["nVec"], 8)
+    assert R.planStats(fourpop["nVec"], 8, std8, T, fourpop["events"])["max_live"] > 256      # big tier engaged
+    assert R.planStats([5, 5], 3, R.computeStandardOrder([5, 5], 3), T[:50], [], True)["n_epochs"] == 1
+
+
 def test_c_abi_rejects_bad_arguments_without_device():
     lib = L.load()
     assert lib.rc_all_configs(0, 3, None, None, 0) == L.RC_ERR_ARG
