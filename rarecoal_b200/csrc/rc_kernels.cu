@@ -1355,7 +1355,10 @@ __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sB
     }
 }
 
-__global__ void __launch_bounds__(RC_BLOCK, 3)
+#ifndef RC_ROWS_MINB
+#define RC_ROWS_MINB 3
+#endif
+__global__ void __launch_bounds__(RC_BLOCK, RC_ROWS_MINB)
 rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
                          const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
                          const double* __restrict__ ktab, const double* __restrict__ aShort,

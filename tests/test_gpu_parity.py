@@ -264,3 +264,27 @@ def test_large_batches_are_chunked_by_table_budget(default_times):
     # a model whose own table exceeds the budget falls back to the self-contained kernel: same answers to rounding
     assert _relerr(probs2, probs) < 1e-12 and np.max(np.abs(logl2 - logl) / np.abs(logl)) < 1e-13 and not status2.any()
     e.close()
+
+
+@pytest.mark.parametrize("P,max_af,n", [(2, 12, 20), (3, 14, 15), (12, 3, 6), (9, 9, 4), (6, 11, 12), (1, 6, 9)])
+def test_tier_selection_on_odd_shapes(eng, default_times, P, max_af, n):
+    # shapes that exercise the tier choices: rows longer than the row kernel holds (state mode), more than 8 non-zero
+    # branches (general tier), many branches with few alleles, a single population
+    nvec = [n] * P
+    pats = R.computeStandardOrder(nvec, max_af)
+    if len(pats) > 1200:
+        pats = pats[np.sort(np.random.default_rng(P * 100 + max_af).choice(len(pats), 1200, replace=False))]
+    cnt = Wk.synthetic_counts(pats, total_sites=10 ** 8, seed=3)
+    eng.set_problem(nvec, max_af, pats, cnt, 10 ** 8)
+    times = default_times[:700]
+    ev = [(0.0, 2, k, 0, 0.6 + 0.3 * k) for k in range(P)]
+    t = 0.002
+    for k in range(P - 1, 0, -1):                 # caterpillar: branch k joins k-1
+        ev += Wk.k_event(t, k - 1, k, 0.8 + 0.1 * k)
+        t += 0.0015
+    logl, probs, status = eng.eval_models([_spec(P, times, ev, 0.001)], want_probs=True)
+    assert status[0] == 0
+    ll_o, probs_o, w_o = O.logl(P, max_af, times, 0.001, [1.0] * P, False, ev, nvec, pats, cnt, 10 ** 8)
+    assert _relerr(probs[0], probs_o) < PROB_RTOL
+    assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert eng.stats()["state_steps"] == w_o
