@@ -373,6 +373,10 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     if ((rc = upload(ctx, pe, h.kFetchOff, &d.kFetchOff))) return rc;
     if ((rc = upload(ctx, pe, h.kFetchRows, &d.kFetchRows))) return rc;
     if ((rc = upload(ctx, pe, h.kRowBase, &d.kRowBase))) return rc;
+    if ((rc = upload(ctx, pe, h.kBinHdr, &d.kBinHdr))) return rc;
+    if ((rc = upload(ctx, pe, h.kPatRec, &d.kPatRec))) return rc;
+    if ((rc = upload(ctx, pe, h.kLane, &d.kLane))) return rc;
+    if ((rc = upload(ctx, pe, h.kElem, &d.kElem))) return rc;
     d.maxEpochSlots = h.maxEpochSlots;
     if ((rc = upload(ctx, pe, h.epochMode, &d.epochMode))) return rc;
     if ((rc = upload(ctx, pe, h.rowOff, &d.rowOff))) return rc;

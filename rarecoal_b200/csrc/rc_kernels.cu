@@ -929,10 +929,8 @@ struct RcKeySmem {
     double dpat[RC_NPB];
     uint32_t metaS[RC_BLOCK];
     int patOff[RC_NPB + 1];
-    int patOff2[RC_NPB + 1];
     int patId[RC_NPB];
     int patDone[RC_NPB];
-    int scanTmp[RC_BLOCK / 32];
 };
 struct RcKeyK {
     static constexpr unsigned B_PAR = RcKeySmem::BSTRIDE * 8u;
@@ -1050,12 +1048,14 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
-    const int P = pl.P, nPat = pl.nPat, nnzw = pl.nnzw;
+    const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
     const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
-    const int pat0 = pl.kBinPatOff[binIdx];
-    const int np = pl.kBinPatOff[binIdx + 1] - pat0;
+    // bin image (rc_types.h): header -> pattern / lane records -> transition entries
+    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
+    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
+    const int pat0 = hdrA.x, np = hdrA.y, nSlots = hdrA.z;
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
     const RcModelEpochDev mE = mep[models[b].mepOff + e];
@@ -1063,32 +1063,17 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
     RcKeyRegs<NNZ> R;
     const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
     const unsigned zeroB = sBase + K::O_B + RC_BLOCK * 8u;
-#pragma unroll
-    for (int d = 0; d < NNZ; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
-    R.nw = 1; R.unit = false; R.slotOn = false; R.fetchOn = false;
+    R.nw = 1; R.unit = false; R.fetchOn = false;
     R.bv = 0.0; R.dacc = 0.0;
     R.fPtr = ktab;
+    R.slotOn = tid < nSlots;
 
-    // ---- set-up: patterns of the bin, slot layout of this epoch ----
-    const int* so = pl.slotOff + (size_t)e * (nPat + 1);
-    if (tid < np) {
-        const int pid = pl.kBinPats[pat0 + tid];
-        S.patId[tid] = pid;
-        S.patDone[tid] = 0;
-        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + pid];
-        S.patOff2[tid] = so[pid + 1] - so[pid];
-    }
-    if (tid < 2 * RC_KDEPTH)                                                   // {1,0} padding pair of every ring slot
-        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
-    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                   // zero neighbours
-    __syncthreads();
-    rc_block_scan(tid < np ? S.patOff2[tid] : 0, np, S.patOff, S.scanTmp);
+    // ---- set-up ----
     // start the pair ring right away: its latency overlaps the rest of the set-up
     const int rowPairs = pl.ep[e].rowPairs;
     const long long strideD = (long long)rowPairs * 2;
-    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
-    R.fetchOn = tid < nFetch;
-    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    R.fetchOn = tid < hdrB.y;
+    const int fOff = R.fetchOn ? pl.kFetchRows[hdrB.x + tid] : 0;
     int s = mE.beg;
     bool ringStarted = false;
     if (s < mE.end) {
@@ -1101,46 +1086,48 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         }
         ringStarted = true;
     }
-    const int nSlots = S.patOff[np];
-    R.slotOn = tid < nSlots;
-    int myLocal = 0, myPid = 0;
+    if (tid < np) {
+        const int2 rec = reinterpret_cast<const int2*>(pl.kPatRec)[pat0 + tid];
+        S.patId[tid] = rec.x;
+        S.patOff[tid] = rec.y & 0xFFFF;
+        S.patDone[tid] = 0;
+        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + rec.x];
+    }
+    if (tid == 0) S.patOff[np] = nSlots;
+    if (tid < 2 * RC_KDEPTH)                                                   // {1,0} padding pair of every ring slot
+        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
+    if (tid < 2) S.bbuf[tid * SM::BSTRIDE + RC_BLOCK] = 0.0;                   // zero neighbours
+    int myLocal = 0;
     {
         int n = 0;
+        uint32_t mt = 0u;
+        uint4 la = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), lb = make_uint4(0u, 0u, 0u, 0u);
         if (R.slotOn) {
-            const int p = rc_find_owner(S.patOff, np, tid);
-            const int local = tid - S.patOff[p];
-            const int pid = S.patId[p];
-            const int gl = so[pid] + local;
-            const long long g = pl.epochBase[e] + gl;
-            myLocal = gl;
-            myPid = pid;
-            if (e > 0) {
-                // popJoinB / popSplitB as a gather over the previous epoch's live states of this pattern
-                const int* trOff = pl.trOff + pl.trBase[e - 1];
-                const uint32_t* trEnt = pl.trEnt + pl.trEntBase[e - 1];
-                const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
-                const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
-                R.bv = rc_gather(trEnt, trOff[gl], trOff[gl + 1], bo, W);
-            } else {
-                // the seed state m is the last one fillUp emits (all components at their maximum), Core.hs:66
-                R.bv = (tid + 1 == S.patOff[p + 1]) ? 1.0 : 0.0;
-            }
-            const uint32_t mt = pl.meta[g];
-            S.metaS[tid] = mt;
+            const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + 2 * (size_t)(hdrB.z + tid);
+            la = lane[0];
+            lb = lane[1];
+            mt = lb.x;
+            myLocal = (int)lb.y;
             n = (int)(mt & 0xFFu);
             R.unit = (mt & RC_META_UNIT) != 0;
-            const uint16_t* rb = pl.kRowBase + (size_t)(pat0 + p) * P;
-            const int bBase = S.patOff[p];
-#pragma unroll
-            for (int d = 0; d < NNZ; ++d) {
-                if (d < n) {
-                    const uint32_t w = pl.words[g * nnzw + d];
-                    const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
-                    const uint32_t up = w >> 16;
-                    R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
-                    if (up != RC_NO_UP) R.aB[d] = sBase + K::O_B + (unsigned)(bBase + (int)up) * 8u;
+            if (lb.z == RC_IMG_SEED) R.bv = 1.0;                                // makeInitCoalState, Core.hs:66
+            else {
+                // popJoinB / popSplitB as a gather over the previous epoch's live states of this pattern
+                const int cnt = (int)(lb.w >> RC_IMG_CNT_SHIFT);
+                if (cnt) {
+                    const double* W = wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff;
+                    const double* bo = bPrev + (size_t)b * bStride + (lb.w & ((1u << RC_IMG_CNT_SHIFT) - 1u));
+                    R.bv = rc_gather(pl.trEnt + lb.z, 0, cnt, bo, W);
                 }
             }
+        }
+        S.metaS[tid] = mt;
+#pragma unroll
+        for (int d = 0; d < NNZ; ++d) {
+            const uint32_t rw = d < 4 ? la.x : la.y, uw = d < 4 ? la.z : la.w;
+            const unsigned row = (rw >> (8 * (d & 3))) & 0xFFu, up = (uw >> (8 * (d & 3))) & 0xFFu;
+            R.aRE[d] = sBase + K::O_RE + row * 16u;
+            R.aB[d] = (!R.slotOn || up == (unsigned)tid) ? zeroB : sBase + K::O_B + up * 8u;
         }
         R.nw = max(1, __reduce_max_sync(0xFFFFFFFFu, n));
     }
@@ -1153,6 +1140,9 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
     // pattern of the bin cannot take the shortcut — on to the end of the grid
     for (int phase = 0; phase < 2 && !finished; ++phase) {
         int nextStop = mE.end;
+#ifdef RC_PROBE_NOLOOP
+        nextStop = s;      // timing probe only (tools/setup_probe.py): set-up and hand-over without the grid steps
+#endif
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
             if (!ringStarted) {
@@ -1237,7 +1227,6 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         // ---- hand b and the updateD sums to the next epoch's launch ----
         if (tid < nSlots) bCur[(size_t)b * bStride + myLocal] = R.bv;
         if (tid < np) dAcc[(size_t)b * nPat + S.patId[tid]] = S.dpat[tid];
-        (void)myPid;
         return;
     }
     // ---- getProb epilogue (Core.hs:49-54) ----
@@ -1266,10 +1255,8 @@ struct RcRowSmem {
     double dslot[RC_BLOCK];
     double dpat[RC_NPBR];
     int patRowOff[RC_NPBR + 1];
-    int patBOff[RC_NPBR + 1];
     int patId[RC_NPBR];
     int patDone[RC_NPBR];
-    int scanTmp[RC_BLOCK / 32];
 };
 struct RcRowK {
     static constexpr unsigned B_PAR = RcRowSmem::BPAR * 8u;
@@ -1374,13 +1361,13 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
     const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
-    const int pat0 = pl.kBinPatOff[binIdx];
-    const int np = pl.kBinPatOff[binIdx + 1] - pat0;
+    // bin image (rc_types.h): header -> pattern / row / element records -> transition entries
+    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
+    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
+    const int pat0 = hdrA.x, np = hdrA.y, nRows = hdrA.z, nB = hdrA.w;
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
     const RcModelEpochDev mE = mep[models[b].mepOff + e];
-    const int* ro = pl.rowOff + (size_t)e * (nPat + 1);
-    const int* so = pl.slotOff + (size_t)e * (nPat + 1);
 
     RcRowRegs R;
 #pragma unroll
@@ -1390,36 +1377,16 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
 #pragma unroll
     for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
     R.aREr = padRE; R.myB = zeroB; R.M = 0; R.NO = 0;
-    R.unit = false; R.rowOn = false; R.fetchOn = false; R.dacc = 0.0;
+    R.unit = false; R.fetchOn = false; R.dacc = 0.0;
     R.fPtr = ktab;
+    R.rowOn = tid < nRows;
 
     // ---- set-up ----
-    if (tid < np) {
-        const int pid = pl.kBinPats[pat0 + tid];
-        S.patId[tid] = pid;
-        S.patDone[tid] = 0;
-        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + pid];
-        const int nr = ro[pid + 1] - ro[pid];
-        const int Mp = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
-        S.patRowOff[tid] = nr;                                                 // counts; turned into offsets below
-        S.patBOff[tid] = nr * (Mp | 1);
-    }
-    if (tid < 2 * RC_RDEPTH)                                                   // {1,0} padding pair of every ring slot
-        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
-    if (tid < 32) S.bbuf[(tid >> 4) * SM::BPAR + RC_ROW_BCAP + (tid & 15)] = 0.0;   // zero rows
-    __syncthreads();
-    {
-        const int nr = tid < np ? S.patRowOff[tid] : 0, nb = tid < np ? S.patBOff[tid] : 0;
-        __syncthreads();
-        rc_block_scan(nr, np, S.patRowOff, S.scanTmp);
-        rc_block_scan(nb, np, S.patBOff, S.scanTmp);
-    }
     // start the pair ring right away: its latency overlaps the rest of the set-up
     const int rowPairs = pl.ep[e].rowPairs;
     const long long strideD = (long long)rowPairs * 2;
-    const int nFetch = pl.kFetchOff[binIdx + 1] - pl.kFetchOff[binIdx];
-    R.fetchOn = tid < nFetch;
-    const int fOff = R.fetchOn ? pl.kFetchRows[pl.kFetchOff[binIdx] + tid] : 0;
+    R.fetchOn = tid < hdrB.y;
+    const int fOff = R.fetchOn ? pl.kFetchRows[hdrB.x + tid] : 0;
     int s = mE.beg;
     bool ringStarted = false;
     if (s < mE.end) {
@@ -1432,65 +1399,59 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
         }
         ringStarted = true;
     }
+    // the row's record; its loads are in flight while the block gathers b
+    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = make_uint4(0u, 0u, 0u, 0u);
+    if (R.rowOn) {
+        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + 2 * (size_t)(hdrB.z + tid);
+        la = lane[0];
+        lb = lane[1];
+    }
+    if (tid < np) {
+        const int2 rec = reinterpret_cast<const int2*>(pl.kPatRec)[pat0 + tid];
+        S.patId[tid] = rec.x;
+        S.patRowOff[tid] = rec.y & 0xFFFF;
+        S.patDone[tid] = 0;
+        S.dpat[tid] = e == 0 ? 0.0 : dAcc[(size_t)b * nPat + rec.x];
+    }
+    if (tid == 0) S.patRowOff[np] = nRows;
+    if (tid < 2 * RC_RDEPTH)                                                   // {1,0} padding pair of every ring slot
+        S.RE[(tid >> 1) * 2 * RC_KROWS + 2 * (RC_KROWS - 1) + (tid & 1)] = (tid & 1) ? 0.0 : 1.0;
+    if (tid < 32) S.bbuf[(tid >> 4) * SM::BPAR + RC_ROW_BCAP + (tid & 15)] = 0.0;   // zero rows
     // ---- b of every state of the bin into shared memory (parity 0), all threads cooperating: the seed state (epoch 0)
     //      or a gather through the event's transition table from the previous launch's carry buffer ----
     {
-        const int nB = S.patBOff[np];
-        const int* trOff = e > 0 ? pl.trOff + pl.trBase[e - 1] : nullptr;
-        const uint32_t* trEnt = e > 0 ? pl.trEnt + pl.trEntBase[e - 1] : nullptr;
+        const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
+        const double* bp = bPrev + (size_t)b * bStride;
         for (int i = tid; i < nB; i += RC_BLOCK) {
-            const int p = rc_find_owner(S.patBOff, np, i);
-            const int pid = S.patId[p];
-            const int Mq = (int)(pl.patRow[(size_t)e * nPat + pid] & 0xFFu);
-            const int Mp = Mq | 1;
-            const int li = i - S.patBOff[p];
-            const int rl = li / Mp, j = li - rl * Mp;
+            const uint2 g = el[i];
             double v = 0.0;
-            if (j < Mq) {
-                const int ref = (int)pl.rowRefAll[(pl.rowEpochBase[e] + ro[pid] + rl) * RC_ROW_MAXM + j];
-                if (e > 0) {
-                    const int gl = so[pid] + ref;
-                    const double* bo = bPrev + (size_t)b * bStride + pl.slotOff[(size_t)(e - 1) * (nPat + 1) + pid];
-                    v = rc_gather(trEnt, trOff[gl], trOff[gl + 1], bo, W);
-                } else v = (ref == so[pid + 1] - so[pid] - 1) ? 1.0 : 0.0;       // the seed state, Core.hs:66
+            if (g.x == RC_IMG_SEED) v = 1.0;                                    // makeInitCoalState, Core.hs:66
+            else {
+                const int cnt = (int)(g.y >> RC_IMG_CNT_SHIFT);
+                if (cnt) v = rc_gather(pl.trEnt + g.x, 0, cnt, bp + (g.y & ((1u << RC_IMG_CNT_SHIFT) - 1u)), W);
             }
             S.bbuf[i] = v;
         }
     }
     __syncthreads();
-    const int nRows = S.patRowOff[np];
-    R.rowOn = tid < nRows;
     const uint16_t* myRefs = pl.rowRefAll;
-    int myPid = 0;
+    int myPid = 0, myOut = 0;
     if (R.rowOn) {
-        const int p = rc_find_owner(S.patRowOff, np, tid);
-        const int rl = tid - S.patRowOff[p];
-        const int pid = S.patId[p];
-        myPid = pid;
-        const uint32_t pr = pl.patRow[(size_t)e * nPat + pid];
-        R.M = (int)(pr & 0xFFu);
-        const int rk = (int)((pr >> 8) & 0xFFu);
-        R.NO = (int)((pr >> 16) & 0xFFu);
-        const int Mp = R.M | 1;
-        const long long grow = pl.rowEpochBase[e] + ro[pid] + rl;
-        myRefs = pl.rowRefAll + grow * RC_ROW_MAXM;
-        const uint32_t* rw = pl.rowWordsAll + grow * RC_ROW_NO;
-        const uint16_t* rb = pl.kRowBase + (size_t)(pat0 + p) * P;
-        const unsigned patB = sBase + K::O_B + (unsigned)S.patBOff[p] * 8u;
-        R.myB = patB + (unsigned)(rl * Mp) * 8u;
-        R.aREr = sBase + K::O_RE + (unsigned)rb[rk] * 16u;
+        R.M = (int)(la.y & 0xFFu);
+        R.NO = (int)((la.y >> 8) & 0xFFu);
         R.unit = R.NO == 0;                                     // x = e_r is the j = 1 state of a single-branch pattern
+        R.aREr = sBase + K::O_RE + (la.x >> 24) * 16u;
+        R.myB = sBase + K::O_B + (la.z & 0xFFFFu) * 8u;
+        const unsigned nb[RC_ROW_NO] = {la.z >> 16, la.w & 0xFFFFu, la.w >> 16};
 #pragma unroll
         for (int d = 0; d < RC_ROW_NO; ++d) {
-            if (d < R.NO) {
-                const uint32_t w = rw[d];
-                const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
-                const uint32_t up = w >> 16;
-                R.aRE[d] = sBase + K::O_RE + (unsigned)((int)rb[k] + x - 1) * 16u;
-                if (up != RC_NO_UP) R.aB[d] = patB + (unsigned)((int)up * Mp) * 8u;
-            }
+            R.aRE[d] = sBase + K::O_RE + ((la.x >> (8 * d)) & 0xFFu) * 16u;
+            R.aB[d] = sBase + K::O_B + nb[d] * 8u;
         }
+        myOut = (int)lb.x;
+        myRefs = pl.rowRefAll + (size_t)lb.y * RC_ROW_MAXM;
+        myPid = (int)lb.z;
         // b of the row from shared memory (filled cooperatively above)
 #pragma unroll
         for (int j = 0; j < RC_ROW_MAXM; ++j)
@@ -1504,6 +1465,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     bool finished = false;
     for (int phase = 0; phase < 2 && !finished; ++phase) {
         int nextStop = mE.end;
+#ifdef RC_PROBE_NOLOOP
+        nextStop = s;      // timing probe only (tools/setup_probe.py): set-up and hand-over without the grid steps
+#endif
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
             if (!ringStarted) {
@@ -1591,7 +1555,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     }
     if (!isLast) {
         if (tid < nRows) {
-            double* out = bCur + (size_t)b * bStride + so[myPid];
+            double* out = bCur + (size_t)b * bStride + myOut;
 #pragma unroll
             for (int j = 0; j < RC_ROW_MAXM; ++j)
                 if (j < R.M) out[myRefs[j]] = R.b[j];

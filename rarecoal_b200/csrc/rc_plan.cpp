@@ -437,6 +437,134 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
 
 }  // namespace
 
+// Bin images of the keyed tier (record layouts in rc_types.h).  Everything the set-up of a block used to look up through
+// pattern ids, slot offsets, packed words and transition offsets is resolved here once, in the order the lanes of the
+// block consume it: the block reads its header, every lane one 32-byte record, and the gather goes straight to the
+// transition entries.
+static std::string build_bin_images(PlanHost& out) {
+    const int P = out.P, nPat = out.nPat, nE = out.nEpochs, nnzw = out.nnzw;
+    out.kBinHdr.assign(out.kBinPatOff.size() * (size_t)RC_HDR_N, 0);
+    out.kPatRec.assign(out.kBinPats.size() * 2, 0);
+    out.kLane.clear();
+    out.kElem.clear();
+    if (out.kBinBase.empty()) return "";
+    if (out.maxEpochSlots >= (1LL << RC_IMG_CNT_SHIFT)) return "too many live states in one epoch for the keyed tier";
+    if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
+    // gather record of the state with reference index `ref` of pattern i in epoch e
+    auto gather_rec = [&](int e, int i, int ref, int live, uint32_t& r0, uint32_t& r1) -> bool {
+        if (e == 0) {
+            // the seed state m is the last one fillUp emits (Core.hs:66)
+            r0 = ref == live - 1 ? RC_IMG_SEED : 0u;
+            r1 = 0u;
+            return true;
+        }
+        const int* trOff = &out.trOff[(size_t)out.trBase[(size_t)e - 1]];
+        const int sl = out.slotOff[(size_t)e * (nPat + 1) + i] + ref;
+        const int a = trOff[sl], b = trOff[sl + 1];
+        if (b - a >= (1 << (32 - RC_IMG_CNT_SHIFT))) return false;
+        r0 = (uint32_t)(out.trEntBase[(size_t)e - 1] + a);
+        r1 = (uint32_t)out.slotOff[(size_t)(e - 1) * (nPat + 1) + i] | ((uint32_t)(b - a) << RC_IMG_CNT_SHIFT);
+        return true;
+    };
+    for (int e = 0; e < nE; ++e) {
+        const bool rows = out.epochMode[(size_t)e] != 0;
+        const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
+        const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
+        const int b0 = out.kBinBase[(size_t)e];
+        for (int bI = b0; bI < b0 + out.nKBins[(size_t)e]; ++bI) {
+            const int p0 = out.kBinPatOff[(size_t)bI], p1 = out.kBinPatOff[(size_t)bI + 1];
+            if (out.kLane.size() / RC_LANE_N > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
+            int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
+            hdr[0] = p0;
+            hdr[1] = p1 - p0;
+            hdr[4] = out.kFetchOff[(size_t)bI];
+            hdr[5] = out.kFetchOff[(size_t)bI + 1] - out.kFetchOff[(size_t)bI];
+            hdr[6] = (int)(out.kLane.size() / RC_LANE_N);
+            hdr[7] = (int)(out.kElem.size() / 2);
+            int lanes = 0, bOff = 0;
+            for (int q = p0; q < p1; ++q) {
+                const int i = out.kBinPats[(size_t)q];
+                const int live = so[i + 1] - so[i];
+                const uint16_t* rb = &out.kRowBase[(size_t)q * P];
+                out.kPatRec[(size_t)q * 2] = i;
+                out.kPatRec[(size_t)q * 2 + 1] = lanes | (bOff << 16);
+                if (!rows) {
+                    for (int s = 0; s < live; ++s) {
+                        const long long g = out.epochBase[(size_t)e] + so[i] + s;
+                        const uint32_t mt = out.meta[(size_t)g];
+                        const int n = (int)(mt & 0xFFu);
+                        if (n > 8) return "keyed bin with more than 8 components";
+                        uint32_t rec[RC_LANE_N] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        for (int d = 0; d < 8; ++d) {
+                            uint32_t row = RC_KROWS - 1, up = (uint32_t)(lanes + s);
+                            if (d < n) {
+                                const uint32_t w = out.words[(size_t)g * nnzw + d];
+                                const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                                row = (uint32_t)((int)rb[k] + x - 1);
+                                if ((w >> 16) != RC_NO_UP) up = (uint32_t)(lanes + (int)(w >> 16));
+                            }
+                            if (row > 0xFFu || up > 0xFFu) return "keyed bin image out of range";
+                            rec[d >> 2] |= row << (8 * (d & 3));
+                            rec[2 + (d >> 2)] |= up << (8 * (d & 3));
+                        }
+                        rec[4] = mt;
+                        rec[5] = (uint32_t)(so[i] + s);
+                        if (!gather_rec(e, i, s, live, rec[6], rec[7])) return "too many transition entries per state";
+                        out.kLane.insert(out.kLane.end(), rec, rec + RC_LANE_N);
+                    }
+                    lanes += live;
+                } else {
+                    const uint32_t pr = out.patRow[(size_t)e * nPat + i];
+                    const int M = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
+                    const int Mp = M | 1, nr = ro[i + 1] - ro[i];
+                    for (int r = 0; r < nr; ++r) {
+                        const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
+                        uint32_t rec[RC_LANE_N] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        uint32_t nb[RC_ROW_NO];
+                        for (int d = 0; d < RC_ROW_NO; ++d) {
+                            uint32_t row = RC_KROWS - 1;
+                            nb[d] = RC_ROW_BCAP;
+                            if (d < NO) {
+                                const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
+                                const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                                row = (uint32_t)((int)rb[k] + x - 1);
+                                if ((w >> 16) != RC_NO_UP) nb[d] = (uint32_t)(bOff + (int)(w >> 16) * Mp);
+                            }
+                            if (row > 0xFFu || nb[d] > RC_ROW_BCAP) return "row bin image out of range";
+                            rec[0] |= row << (8 * d);
+                        }
+                        static_assert(RC_ROW_NO == 3, "lane record packs three other branches");
+                        if (rb[rk] > 0xFFu) return "row bin image out of range";
+                        rec[0] |= (uint32_t)rb[rk] << 24;
+                        rec[1] = (uint32_t)M | ((uint32_t)NO << 8);
+                        rec[2] = (uint32_t)(bOff + r * Mp) | (nb[0] << 16);
+                        rec[3] = nb[1] | (nb[2] << 16);
+                        rec[4] = (uint32_t)so[i];
+                        if (grow > 0xFFFFFFFFLL) return "bin images too large";
+                        rec[5] = (uint32_t)grow;
+                        rec[6] = (uint32_t)i;
+                        out.kLane.insert(out.kLane.end(), rec, rec + RC_LANE_N);
+                        for (int j = 0; j < Mp; ++j) {
+                            uint32_t g0 = 0u, g1 = 0u;
+                            if (j < M) {
+                                const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + j];
+                                if (!gather_rec(e, i, ref, live, g0, g1)) return "too many transition entries per state";
+                            }
+                            out.kElem.push_back(g0);
+                            out.kElem.push_back(g1);
+                        }
+                    }
+                    lanes += nr;
+                    bOff += nr * Mp;
+                }
+            }
+            hdr[2] = lanes;
+            hdr[3] = bOff;
+        }
+    }
+    return "";
+}
+
 std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
                        const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
                        int smemBudgetBytes, PlanHost& out) {
@@ -908,7 +1036,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         tb += nNew + 1;
         te += run;
     }
-    return "";
+    return build_bin_images(out);
 }
 
 
@@ -1003,6 +1131,67 @@ std::string check_plan(const PlanHost& h) {
                 }
                 if (lanes > RC_BLOCK) return fail("lanes per keyed bin");
                 if (padded > RC_ROW_BCAP) return fail("padded states per row bin");
+            }
+        }
+    }
+    // bin images
+    if (!h.kBinBase.empty()) {
+        if (h.kBinHdr.size() != h.kBinPatOff.size() * (size_t)RC_HDR_N || h.kPatRec.size() != h.kBinPats.size() * 2)
+            return fail("bin image sizes");
+        const long long nLaneRec = (long long)(h.kLane.size() / RC_LANE_N), nElemRec = (long long)(h.kElem.size() / 2);
+        auto gather_ok = [&](int e, uint32_t r0, uint32_t r1) {
+            if (e == 0) return (r0 == 0u || r0 == RC_IMG_SEED) && r1 == 0u;
+            const long long cnt = r1 >> RC_IMG_CNT_SHIFT, prev = r1 & ((1u << RC_IMG_CNT_SHIFT) - 1u);
+            if (cnt == 0) return true;                       // no sources: the value is 0 (padding of a row, or a dead state)
+            const long long lo = h.trEntBase[(size_t)e - 1];
+            const long long hi = e < nE - 1 ? h.trEntBase[(size_t)e] : (long long)h.trEnt.size();
+            return (long long)r0 >= lo && (long long)r0 + cnt <= hi && prev < h.epochSlots[(size_t)e - 1];
+        };
+        for (int e = 0; e < nE; ++e) {
+            const bool rows = h.epochMode[(size_t)e] != 0;
+            const int b0 = h.kBinBase[(size_t)e];
+            for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
+                const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
+                const int np = hdr[1], lanes = hdr[2], nB = hdr[3], nFetch = hdr[5];
+                if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
+                if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
+                if (lanes < 1 || lanes > RC_BLOCK || nB < 0 || nB > RC_ROW_BCAP) return fail("image header lanes");
+                if (hdr[6] < 0 || hdr[6] + lanes > nLaneRec || hdr[7] < 0 || hdr[7] + nB > nElemRec) return fail("image record range");
+                for (int q = 0; q < np; ++q) {
+                    const int rec = h.kPatRec[(size_t)(hdr[0] + q) * 2 + 1];
+                    if (h.kPatRec[(size_t)(hdr[0] + q) * 2] != h.kBinPats[(size_t)(hdr[0] + q)]) return fail("image pattern id");
+                    if ((rec & 0xFFFF) >= lanes || (rec >> 16) > nB) return fail("image pattern offsets");
+                }
+                for (int t = 0; t < lanes; ++t) {
+                    const uint32_t* r = &h.kLane[(size_t)(hdr[6] + t) * RC_LANE_N];
+                    if (!rows) {
+                        for (int d = 0; d < 8; ++d) {
+                            const int row = (int)((r[d >> 2] >> (8 * (d & 3))) & 0xFFu), up = (int)((r[2 + (d >> 2)] >> (8 * (d & 3))) & 0xFFu);
+                            if (row != RC_KROWS - 1 && (row < 1 || row >= nFetch)) return fail("image pair row");
+                            if (up >= lanes) return fail("image neighbour lane");
+                        }
+                        if ((long long)r[5] >= h.epochSlots[(size_t)e]) return fail("image carry slot");
+                        if (!gather_ok(e, r[6], r[7])) return fail("image gather record");
+                    } else {
+                        const int M = (int)(r[1] & 0xFFu), NO = (int)((r[1] >> 8) & 0xFFu);
+                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO) return fail("image row shape");
+                        const int rr = (int)(r[0] >> 24);
+                        if (rr < 1 || rr + M - 1 >= nFetch) return fail("image row-branch pair rows");
+                        for (int d = 0; d < RC_ROW_NO; ++d) {
+                            const int row = (int)((r[0] >> (8 * d)) & 0xFFu);
+                            if (row != RC_KROWS - 1 && (row < 1 || row >= nFetch)) return fail("image pair row");
+                        }
+                        const int offs[4] = {(int)(r[2] & 0xFFFFu), (int)(r[2] >> 16), (int)(r[3] & 0xFFFFu), (int)(r[3] >> 16)};
+                        if (offs[0] + M > nB) return fail("image own row");
+                        for (int d = 1; d < 4; ++d)
+                            if (offs[d] != RC_ROW_BCAP && offs[d] + M > nB) return fail("image neighbour row");
+                        if ((long long)r[4] >= h.epochSlots[(size_t)e] || (long long)(r[5] + 1) * RC_ROW_MAXM > (long long)h.rowRefAll.size() ||
+                            (int)r[6] >= nPat)
+                            return fail("image row hand-over");
+                    }
+                }
+                for (int q = 0; q < nB; ++q)
+                    if (!gather_ok(e, h.kElem[(size_t)(hdr[7] + q) * 2], h.kElem[(size_t)(hdr[7] + q) * 2 + 1])) return fail("image element record");
             }
         }
     }

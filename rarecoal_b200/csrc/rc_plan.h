@@ -78,6 +78,10 @@ struct PlanHost {
     std::vector<uint32_t> rowWordsAll;     // per row RC_ROW_NO words: k | x_k << 8 | neighbour row << 16
     std::vector<uint32_t> patRow;          // [nEpochs][nPat] row length | row branch << 8 | other branches << 16
     std::vector<int> patRowStride;         // [nEpochs][nPat] reference-order stride of the row branch
+    // bin images (layouts in rc_types.h): the set-up data of every keyed bin in lane order, so that a block reads
+    // header -> lane record -> transition entries instead of chasing pattern / slot / word / offset tables
+    std::vector<int> kBinHdr, kPatRec;
+    std::vector<uint32_t> kLane, kElem;
     long long maxEpochSlots = 0;           // largest number of live states in one epoch (stride of the b carry buffers)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]

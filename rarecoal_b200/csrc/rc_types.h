@@ -100,7 +100,30 @@ struct RcPlanDev {
     const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states
     const uint32_t* rowWordsAll; // per row RC_ROW_NO words: k | x_k << 8 | neighbour row << 16
     const uint32_t* patRow;      // [nEpochs][nPat] row length | row branch << 8 | other branches << 16
+    // ---- bin images: what a block's set-up needs, already resolved to lane order (rc_plan.h, build_bin_images) ----
+    const int* kBinHdr;          // [bin][RC_HDR_N], same bin indexing as kBinPatOff
+    const int* kPatRec;          // [position in kBinPats][2]: pattern id, first lane | first b double << 16
+    const uint32_t* kLane;       // [lane][RC_LANE_N] (layout per mode below)
+    const uint32_t* kElem;       // [element][2], row mode: gather record of every b double of a bin
 };
+
+// Bin header (ints): 0 first entry in kBinPats/kPatRec, 1 patterns, 2 lanes (states or rows), 3 b doubles (row mode, padded
+// rows), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record, 7 first element record.
+#define RC_HDR_N 8
+// Lane record (8 x u32).
+//   state mode: [0..1] pair row of component d (8 x u8; RC_KROWS-1 = the {1,0} padding pair)
+//               [2..3] lane of the neighbour x + e_k (8 x u8; own lane = no such state)
+//               [4] meta word  [5] slot inside the epoch (carry buffer)  [6..7] gather record
+//   row mode:   [0] pair rows of the other branches (3 x u8) | pair row of (row branch, j = 1) << 24
+//               [1] M | NO << 8
+//               [2] own row | neighbour row 0 << 16    [3] neighbour rows 1 | 2 << 16   (b offsets in doubles;
+//                   RC_ROW_BCAP = the always-zero row)
+//               [4] first slot of the pattern in the epoch  [5] row index in rowRefAll  [6] pattern id  [7] 0
+// Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
+// and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
+#define RC_LANE_N 8
+#define RC_IMG_SEED 0xFFFFFFFFu
+#define RC_IMG_CNT_SHIFT 26
 
 struct RcEpochDev {
     int nKeys, nThr, rowPairs, keyOff, thrOff;
