@@ -421,6 +421,21 @@ __device__ __forceinline__ double rc_lds64(unsigned addr) {
 __device__ __forceinline__ void rc_lds128(unsigned addr, double& a, double& b) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
+// {G, E2} pair of the keyed kernels.  A 128-bit shared load is served quarter-warp by quarter-warp (about 3 wavefronts per
+// warp here) even when the lanes read a handful of distinct rows.  Two 64-bit loads (RC_PAIR_SPLIT=1) were measured 10 %
+// slower on C3 (41.1 vs 37.2 ms per 44 models), so the pair stays one LDS.128.
+#ifndef RC_PAIR_SPLIT
+#define RC_PAIR_SPLIT 0
+#endif
+__device__ __forceinline__ void rc_lds_pair(unsigned addr, double& a, double& b) {
+#if RC_PAIR_SPLIT
+    // volatile: ptxas would fuse the two loads back into one LDS.128
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
+    asm volatile("ld.volatile.shared.f64 %0, [%1+8];" : "=d"(b) : "r"(addr));
+#else
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+#endif
+}
 __device__ __forceinline__ void rc_sts64(unsigned addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
@@ -950,12 +965,16 @@ struct RcKeyRegs {
     const double* fPtr;           // this lane's pair in the step row to be copied next
 };
 
+// the pairs are read once per block: no L1 allocation
+#ifndef RC_CP_MODE
+#define RC_CP_MODE "cg"
+#endif
 __device__ __forceinline__ void rc_cp_async16(unsigned dst, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async." RC_CP_MODE ".shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 // predicated form: no branch around the copy
 __device__ __forceinline__ void rc_cp_async16_if(unsigned dst, const double* src, unsigned pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"(pred)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async." RC_CP_MODE ".shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"(pred)
                  : "memory");
 }
 __device__ __forceinline__ void rc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -976,12 +995,12 @@ __device__ __forceinline__ void rc_key_step(RcKeyRegs<NNZ>& R, const unsigned sB
     R.fPtr += strideD;
     if (warpOn) {      // warp-uniform; lanes without a state run on the padding pair / zero neighbour and keep b = 0
         double g, e2;
-        rc_lds128(R.aRE[0] + slot, g, e2);
+        rc_lds_pair(R.aRE[0] + slot, g, e2);
         double D = g;
         double t2 = rc_lds64(R.aB[0] + PH * K::B_PAR) * e2;
 #pragma unroll
         for (int d = 1; d < N; ++d) {
-            rc_lds128(R.aRE[d] + slot, g, e2);
+            rc_lds_pair(R.aRE[d] + slot, g, e2);
             D *= g;
             t2 = fma(rc_lds64(R.aB[d] + PH * K::B_PAR), e2, t2);
         }
@@ -1298,14 +1317,14 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
 #pragma unroll
             for (int d = 0; d < NO; ++d) {
                 double g;
-                rc_lds128(R.aRE[d] + slot, g, e2o[d]);
+                rc_lds_pair(R.aRE[d] + slot, g, e2o[d]);
                 D *= g;
             }
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 const bool v = j < R.M;
                 double gj = 1.0, e2j = 0.0;
-                if (v) rc_lds128(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
+                if (v) rc_lds_pair(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
                 double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
 #pragma unroll
                 for (int d = 0; d < NO; ++d) {
