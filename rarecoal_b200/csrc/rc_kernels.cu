@@ -1267,6 +1267,9 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
 // (Core.hs:259).  Rows are stored row-major with an odd stride (M | 1), so a warp reading one column of consecutive
 // rows touches distinct banks.
 #define RC_RDEPTH 4
+#ifndef RC_ROW_NBPRED
+#define RC_ROW_NBPRED 0
+#endif
 struct RcRowSmem {
     static constexpr int BPAR = RC_ROW_BCAP + 16;      // doubles per parity; the last 16 are the always-zero row
     double bbuf[2 * BPAR];
@@ -1291,6 +1294,7 @@ struct RcRowRegs {
     double b[RC_ROW_MAXM];
     unsigned aRE[RC_ROW_NO], aB[RC_ROW_NO];   // pair of (branch d, x_d) in ring slot 0 / neighbour row (parity 0)
     unsigned aREr, myB;                        // pair of (row branch, j = 1) in ring slot 0 / own row (parity 0)
+    int Mnb[RC_ROW_NO];                        // M if the neighbouring row along branch d exists, else 0
     int M, NO;
     bool unit, rowOn, fetchOn;
     double dacc;
@@ -1328,8 +1332,14 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
                 double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
 #pragma unroll
                 for (int d = 0; d < NO; ++d) {
+                    // rows at the upper face of branch d have no neighbour there: the load is predicated off rather than
+                    // pointed at a zero row, whose bank would collide with some other lane's
                     double nb = 0.0;
+#if RC_ROW_NBPRED
+                    if (j < R.Mnb[d]) nb = rc_lds64(R.aB[d] + po + (unsigned)j * 8u);
+#else
                     if (v) nb = rc_lds64(R.aB[d] + po + (unsigned)j * 8u);
+#endif
                     t2 = fma(nb, e2o[d], t2);
                 }
                 R.b[j] = fma(R.b[j], D * gj, t2);                            // updateB, Core.hs:259
@@ -1394,7 +1404,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
     const unsigned zeroB = sBase + K::O_B + K::ZERO_B;
 #pragma unroll
-    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; R.Mnb[d] = 0; }
     R.aREr = padRE; R.myB = zeroB; R.M = 0; R.NO = 0;
     R.unit = false; R.fetchOn = false; R.dacc = 0.0;
     R.fPtr = ktab;
@@ -1467,6 +1477,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
         for (int d = 0; d < RC_ROW_NO; ++d) {
             R.aRE[d] = sBase + K::O_RE + ((la.x >> (8 * d)) & 0xFFu) * 16u;
             R.aB[d] = sBase + K::O_B + nb[d] * 8u;
+            R.Mnb[d] = nb[d] == RC_ROW_BCAP ? 0 : R.M;
         }
         myOut = (int)lb.x;
         myRefs = pl.rowRefAll + (size_t)lb.y * RC_ROW_MAXM;
@@ -1537,13 +1548,15 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
             }
             const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
             // sum in the reference's live-list order (fillUp order = ascending j for a single branch)
-            double add = 0.0;
+            // chooseCont (nrA + nd) nd = chooseCont (nrA + nd - 1) (nd - 1) * (nrA + nd) / nd  (Utils.hs:213-215 as a recurrence
+            // along the row; the factors are the same, multiplied in ascending instead of descending order)
+            double add = 0.0, cc = 1.0;
 #pragma unroll
             for (int j = 0; j < RC_ROW_MAXM; ++j) {
                 if (j < R.M) {
-                    const int nd = j + 1;
-                    const double withComb = 2.0 * popSize / (double)nd;
-                    add = add + R.b[j] * (withComb / rc_choose_cont(nrA + (double)nd, nd));
+                    const double nd = (double)(j + 1);
+                    cc = cc * ((nrA + nd) / nd);
+                    add = add + R.b[j] * (2.0 * popSize / nd / cc);
                 }
             }
             S.dslot[tid] = add;
@@ -1562,6 +1575,8 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
             R.rowOn = false;
             R.unit = false;
             R.M = 0;
+#pragma unroll
+            for (int d = 0; d < RC_ROW_NO; ++d) R.Mnb[d] = 0;
         }
         // b of the continuing rows must sit at parity 0 for the next run
         if (cp) {
