@@ -764,6 +764,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             int rowStates = 0;
             std::vector<std::unordered_map<int, int>> keyRows;   // per epoch: key -> pair rows needed
         };
+        // measured on C3 (44 models): 36.7 ms with lexicographic bins, 33.4 ms with cost-class bins; RC_BINSORT=0 restores the former
+        const bool binSort = std::getenv("RC_BINSORT") ? std::atoi(std::getenv("RC_BINSORT")) != 0 : true;
         auto pack_range = [&](int e0, int e1, int maxPats, bool rowMode, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
             const size_t WINDOW = 12;
@@ -828,7 +830,22 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ob.ids.push_back(i);
                 return true;
             };
-            for (int i : order) {
+            // One-epoch bins: a block advances at the pace of its slowest warp (one barrier per grid step), and a warp at
+            // the pace of its widest lane.  Patterns of equal cost class (row mode: other branches, row length; state
+            // mode: non-zero branches) are therefore binned together; inside a class the lexicographic order keeps
+            // patterns that share trajectory keys next to each other.
+            std::vector<int> ord(order);
+            if (nE == 1 && binSort) {
+                auto cls = [&](int i) {
+                    const PatPlan& pp = pps[(size_t)i];
+                    if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
+                    int c = 0;
+                    for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
+                    return c;
+                };
+                std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return cls(a) > cls(b); });
+            }
+            for (int i : ord) {
                 bool placed = false;
                 for (size_t q = open.size(); q-- > 0 && !placed;) placed = try_add(open[q], i);
                 if (placed) continue;
