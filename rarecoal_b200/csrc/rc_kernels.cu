@@ -1302,7 +1302,8 @@ struct RcRowRegs {
 };
 
 // grid steps s .. nextStop-1 for a warp whose rows have at most NO other branches and length at most M
-template <int NO, int M>
+// EX: every lane of the warp owns a row of exactly M states — no per-state predicates
+template <int NO, int M, bool EX>
 __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
                                           const int nextStop) {
     typedef RcRowK K;
@@ -1326,7 +1327,7 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
             }
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                const bool v = j < R.M;
+                const bool v = EX || j < R.M;
                 double gj = 1.0, e2j = 0.0;
                 if (v) rc_lds_pair(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
                 double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
@@ -1359,15 +1360,30 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
 template <int NO>
 __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
                                                  const int nextStop, const int Mw) {
+    // bins hold rows of one length (rc_plan.cpp, cost classes), so most warps take the predicate-free variant
+    if (__all_sync(0xFFFFFFFFu, R.rowOn && R.M == Mw)) {
+        switch (Mw) {
+            case 1: return rc_row_run<NO, 1, true>(R, sBase, strideD, s, nextStop);
+            case 2: return rc_row_run<NO, 2, true>(R, sBase, strideD, s, nextStop);
+            case 3: return rc_row_run<NO, 3, true>(R, sBase, strideD, s, nextStop);
+            case 4: return rc_row_run<NO, 4, true>(R, sBase, strideD, s, nextStop);
+            case 5: return rc_row_run<NO, 5, true>(R, sBase, strideD, s, nextStop);
+            case 6: return rc_row_run<NO, 6, true>(R, sBase, strideD, s, nextStop);
+            case 7: return rc_row_run<NO, 7, true>(R, sBase, strideD, s, nextStop);
+            case 8: return rc_row_run<NO, 8, true>(R, sBase, strideD, s, nextStop);
+            case 9: return rc_row_run<NO, 9, true>(R, sBase, strideD, s, nextStop);
+            default: return rc_row_run<NO, RC_ROW_MAXM, true>(R, sBase, strideD, s, nextStop);
+        }
+    }
     switch (Mw) {
-        case 1: return rc_row_run<NO, 1>(R, sBase, strideD, s, nextStop);
-        case 2: return rc_row_run<NO, 2>(R, sBase, strideD, s, nextStop);
-        case 3: return rc_row_run<NO, 3>(R, sBase, strideD, s, nextStop);
-        case 4: return rc_row_run<NO, 4>(R, sBase, strideD, s, nextStop);
-        case 5: return rc_row_run<NO, 5>(R, sBase, strideD, s, nextStop);
-        case 6: return rc_row_run<NO, 6>(R, sBase, strideD, s, nextStop);
-        case 7: case 8: return rc_row_run<NO, 8>(R, sBase, strideD, s, nextStop);
-        default: return rc_row_run<NO, RC_ROW_MAXM>(R, sBase, strideD, s, nextStop);
+        case 1: return rc_row_run<NO, 1, false>(R, sBase, strideD, s, nextStop);
+        case 2: return rc_row_run<NO, 2, false>(R, sBase, strideD, s, nextStop);
+        case 3: return rc_row_run<NO, 3, false>(R, sBase, strideD, s, nextStop);
+        case 4: return rc_row_run<NO, 4, false>(R, sBase, strideD, s, nextStop);
+        case 5: return rc_row_run<NO, 5, false>(R, sBase, strideD, s, nextStop);
+        case 6: return rc_row_run<NO, 6, false>(R, sBase, strideD, s, nextStop);
+        case 7: case 8: return rc_row_run<NO, 8, false>(R, sBase, strideD, s, nextStop);
+        default: return rc_row_run<NO, RC_ROW_MAXM, false>(R, sBase, strideD, s, nextStop);
     }
 }
 
