@@ -542,8 +542,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 for (int k = 0; k < P; ++k) M.Nshort[k] = mh.segs[si].N[k];
             }
         }
-        // table rows are needed by the self-contained tiers only
-        M.rowsAvail = (M.mode == 1 && hp.nBins == 0) ? 0 : ((mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T);
+        // per-step table rows: read by the self-contained tiers and by the trajectory kernel of the keyed tier
+        M.rowsAvail = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
         M.tabOff = tabDoubles;
         M.wPool = 0;
         M.theta = theta[b];
@@ -637,7 +637,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 const bool timeIt = !ctx->trajTimed;      // trajectory kernels of the first plan group are timed
                 if (timeIt) CK(cudaEventRecord(ctx->evt[6], st));
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
-                    CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, dSegs, dSegOff, (const double*)ctx->dDts.p,
+                    CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
                                       (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, st));
                     ++launches;
                 }

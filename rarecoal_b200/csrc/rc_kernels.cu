@@ -427,14 +427,17 @@ __device__ __forceinline__ void rc_lds128(unsigned addr, double& a, double& b) {
 #ifndef RC_PAIR_SPLIT
 #define RC_PAIR_SPLIT 0
 #endif
-__device__ __forceinline__ void rc_lds_pair(unsigned addr, double& a, double& b) {
-#if RC_PAIR_SPLIT
+template <int SPLIT = RC_PAIR_SPLIT>
+__device__ __forceinline__ void rc_lds_pair(unsigned addr, double& a, double& b);
+template <>
+__device__ __forceinline__ void rc_lds_pair<0>(unsigned addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+template <>
+__device__ __forceinline__ void rc_lds_pair<1>(unsigned addr, double& a, double& b) {
     // volatile: ptxas would fuse the two loads back into one LDS.128
     asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
     asm volatile("ld.volatile.shared.f64 %0, [%1+8];" : "=d"(b) : "r"(addr));
-#else
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
-#endif
 }
 __device__ __forceinline__ void rc_sts64(unsigned addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
@@ -853,7 +856,7 @@ rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, co
 // b(x+e_k) (Core.hs:279).  All patterns that share the key read the same pairs.
 __global__ void __launch_bounds__(128)
 rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
-               const RcSEvDev* __restrict__ sevs, const RcSegDev* __restrict__ segs, const int* __restrict__ segOff,
+               const RcSEvDev* __restrict__ sevs, const double* __restrict__ tab,
                const double* __restrict__ dts, double* __restrict__ ktab, double* __restrict__ aEnd,
                double* __restrict__ aShort) {
     const int b = blockIdx.y;
@@ -893,35 +896,30 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
             else a = (1.0 - m) * aPrev[pa];                                // (1 - m) * al
         }
     }
-    // ---- (popSize, freeze) segment of the first step ----
-    int si = segOff[b];
-    const int sEnd = segOff[b + 1];
-    while (si + 1 < sEnd && segs[si + 1].sBegin <= me.beg) ++si;
-    double N = segs[si].N[k];
-    bool frozen = (segs[si].frozenMask >> k) & 1u;
-    int nextSeg = si + 1 < sEnd ? segs[si + 1].sBegin : 0x7fffffff;
+    // The key-independent factors of a step — EA = exp(-dt/2N_k) (Core.hs:240), 1/N_k, CN = j(j-1)/2N_k (Core.hs:270) and
+    // E2 (Core.hs:279) — come from the per-step table rc_tables_kernel has already written for this model (rc_types.h, table
+    // row layout); only the a-dependent exponential is left per (key, j, step).
     const double xx = (double)j;
     double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2;
     const long long stride = (long long)E.rowPairs * 2;
-    for (int s = me.beg; s < me.end; ++s, out += stride) {
-        while (s >= nextSeg) {
-            ++si;
-            N = segs[si].N[k];
-            frozen = (segs[si].frozenMask >> k) & 1u;
-            nextSeg = si + 1 < sEnd ? segs[si + 1].sBegin : 0x7fffffff;
-        }
+    const int rowLen = rc_row_len(pl.P, pl.A1);
+    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
+    const int jOff = hasPair ? 2 * j : 0;
+    for (int s = me.beg; s < me.end; ++s, out += stride, row += rowLen) {
         if (lastEpoch && s == M.sShort && j == 1) aShort[M.aShortOff + key] = a;
+        const double2 p0 = *reinterpret_cast<const double2*>(row);            // {EA, 1/N}; 1/N == 0: frozen
+        const double2 pj = *reinterpret_cast<const double2*>(row + jOff);     // {CN, E2}
         const double dt = dts[s];
         double G = 1.0, E2 = 0.0;
-        if (dt > 0.0 && !frozen) {
-            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * exp(-(0.5 * dt / N)));     // propagateA, Core.hs:239-240
+        if (dt > 0.0 && p0.y != 0.0) {
+            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * p0.x);         // propagateA, Core.hs:239-240
             if (hasPair) {
-                const double t1k = xx * (xx - 1.0) / 2.0 * (1.0 / N) + xx * a * (1.0 / N);  // Core.hs:270 (new a)
+                const double t1k = pj.x + xx * a * p0.y;                       // Core.hs:270 (new a)
                 G = exp(-(t1k * dt));
-                E2 = 1.0 - exp(-(xx * (xx + 1.0) / 2.0 * (1.0 / N) * dt));                   // Core.hs:279
+                E2 = pj.y;
             }
         }
-        if (hasPair) { out[0] = G; out[1] = E2; }
+        if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
     }
     if (j == 1) {
         aEnd[M.aEndOff + kk] = a;
@@ -1267,6 +1265,12 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
 // (Core.hs:259).  Rows are stored row-major with an odd stride (M | 1), so a warp reading one column of consecutive
 // rows touches distinct banks.
 #define RC_RDEPTH 4
+#ifndef RC_ROW_SPLIT_O
+#define RC_ROW_SPLIT_O 0
+#endif
+#ifndef RC_ROW_SPLIT_R
+#define RC_ROW_SPLIT_R 0
+#endif
 #ifndef RC_ROW_NBPRED
 #define RC_ROW_NBPRED 0
 #endif
@@ -1322,14 +1326,14 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
 #pragma unroll
             for (int d = 0; d < NO; ++d) {
                 double g;
-                rc_lds_pair(R.aRE[d] + slot, g, e2o[d]);
+                rc_lds_pair<RC_ROW_SPLIT_O>(R.aRE[d] + slot, g, e2o[d]);
                 D *= g;
             }
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 const bool v = EX || j < R.M;
                 double gj = 1.0, e2j = 0.0;
-                if (v) rc_lds_pair(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
+                if (v) rc_lds_pair<RC_ROW_SPLIT_R>(R.aREr + slot + (unsigned)j * 16u, gj, e2j);
                 double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
 #pragma unroll
                 for (int d = 0; d < NO; ++d) {
@@ -1730,11 +1734,11 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
 }
 
 cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
-                           const RcSEvDev* sevs, const RcSegDev* segs, const int* segOff, const double* dts, double* ktab,
+                           const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
                            double* aEnd, double* aShort, int b0, int nB, cudaStream_t st) {
     if (nB <= 0) return cudaSuccess;
     dim3 grid((unsigned)((nThr + 127) / 128), (unsigned)nB);
-    rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, segs, segOff + b0, dts, ktab, aEnd, aShort);
+    rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, ktab, aEnd, aShort);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
                                      cudaStream_t st);
 size_t rc_fast_smem_bytes(int block);
 cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
-                           const RcSEvDev* sevs, const RcSegDev* segs, const int* segOff, const double* dts, double* ktab,
+                           const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
                            double* aEnd, double* aShort, int b0, int nB, cudaStream_t st);
 cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int rowMode, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
