@@ -1120,7 +1120,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
         uint32_t mt = 0u;
         uint4 la = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), lb = make_uint4(0u, 0u, 0u, 0u);
         if (R.slotOn) {
-            const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + 2 * (size_t)(hdrB.z + tid);
+            const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + 2 * (size_t)tid;
             la = lane[0];
             lb = lane[1];
             mt = lb.x;
@@ -1271,9 +1271,6 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
 #ifndef RC_ROW_SPLIT_R
 #define RC_ROW_SPLIT_R 0
 #endif
-#ifndef RC_ROW_NBPRED
-#define RC_ROW_NBPRED 0
-#endif
 struct RcRowSmem {
     static constexpr int BPAR = RC_ROW_BCAP + 16;      // doubles per parity; the last 16 are the always-zero row
     double bbuf[2 * BPAR];
@@ -1298,7 +1295,6 @@ struct RcRowRegs {
     double b[RC_ROW_MAXM];
     unsigned aRE[RC_ROW_NO], aB[RC_ROW_NO];   // pair of (branch d, x_d) in ring slot 0 / neighbour row (parity 0)
     unsigned aREr, myB;                        // pair of (row branch, j = 1) in ring slot 0 / own row (parity 0)
-    int Mnb[RC_ROW_NO];                        // M if the neighbouring row along branch d exists, else 0
     int M, NO;
     bool unit, rowOn, fetchOn;
     double dacc;
@@ -1337,14 +1333,10 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
                 double t2 = (j + 1 < M) ? R.b[j + 1] * e2j : 0.0;             // old b(j+1): not yet overwritten
 #pragma unroll
                 for (int d = 0; d < NO; ++d) {
-                    // rows at the upper face of branch d have no neighbour there: the load is predicated off rather than
-                    // pointed at a zero row, whose bank would collide with some other lane's
+                    // (predicating off the loads of rows without a neighbour along d, instead of pointing them at the zero
+                    // row, was measured: fewer bank conflicts, but 5 % slower for the extra predicate arithmetic)
                     double nb = 0.0;
-#if RC_ROW_NBPRED
-                    if (j < R.Mnb[d]) nb = rc_lds64(R.aB[d] + po + (unsigned)j * 8u);
-#else
                     if (v) nb = rc_lds64(R.aB[d] + po + (unsigned)j * 8u);
-#endif
                     t2 = fma(nb, e2o[d], t2);
                 }
                 R.b[j] = fma(R.b[j], D * gj, t2);                            // updateB, Core.hs:259
@@ -1361,6 +1353,13 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, co
     return (s - s0) & 1;
 }
 
+// Row lengths that occur with NO other branches: any up to RC_ROW_MAXM for NO <= 3, else NO + M <= RC_ROW_SUM (planner rule).
+// A length the planner never produces maps onto the longest variant that exists, so no dead variants are compiled.
+template <int NO, int M>
+struct RcRowLen {
+    static constexpr int MAXM = NO <= 3 ? RC_ROW_MAXM : (RC_ROW_SUM - NO < 1 ? 1 : RC_ROW_SUM - NO);
+    static constexpr int value = M <= MAXM ? M : MAXM;
+};
 template <int NO>
 __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
                                                  const int nextStop, const int Mw) {
@@ -1368,26 +1367,26 @@ __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sB
     if (__all_sync(0xFFFFFFFFu, R.rowOn && R.M == Mw)) {
         switch (Mw) {
             case 1: return rc_row_run<NO, 1, true>(R, sBase, strideD, s, nextStop);
-            case 2: return rc_row_run<NO, 2, true>(R, sBase, strideD, s, nextStop);
-            case 3: return rc_row_run<NO, 3, true>(R, sBase, strideD, s, nextStop);
-            case 4: return rc_row_run<NO, 4, true>(R, sBase, strideD, s, nextStop);
-            case 5: return rc_row_run<NO, 5, true>(R, sBase, strideD, s, nextStop);
-            case 6: return rc_row_run<NO, 6, true>(R, sBase, strideD, s, nextStop);
-            case 7: return rc_row_run<NO, 7, true>(R, sBase, strideD, s, nextStop);
-            case 8: return rc_row_run<NO, 8, true>(R, sBase, strideD, s, nextStop);
-            case 9: return rc_row_run<NO, 9, true>(R, sBase, strideD, s, nextStop);
-            default: return rc_row_run<NO, RC_ROW_MAXM, true>(R, sBase, strideD, s, nextStop);
+            case 2: return rc_row_run<NO, RcRowLen<NO, 2>::value, true>(R, sBase, strideD, s, nextStop);
+            case 3: return rc_row_run<NO, RcRowLen<NO, 3>::value, true>(R, sBase, strideD, s, nextStop);
+            case 4: return rc_row_run<NO, RcRowLen<NO, 4>::value, true>(R, sBase, strideD, s, nextStop);
+            case 5: return rc_row_run<NO, RcRowLen<NO, 5>::value, true>(R, sBase, strideD, s, nextStop);
+            case 6: return rc_row_run<NO, RcRowLen<NO, 6>::value, true>(R, sBase, strideD, s, nextStop);
+            case 7: return rc_row_run<NO, RcRowLen<NO, 7>::value, true>(R, sBase, strideD, s, nextStop);
+            case 8: return rc_row_run<NO, RcRowLen<NO, 8>::value, true>(R, sBase, strideD, s, nextStop);
+            case 9: return rc_row_run<NO, RcRowLen<NO, 9>::value, true>(R, sBase, strideD, s, nextStop);
+            default: return rc_row_run<NO, RcRowLen<NO, RC_ROW_MAXM>::value, true>(R, sBase, strideD, s, nextStop);
         }
     }
     switch (Mw) {
         case 1: return rc_row_run<NO, 1, false>(R, sBase, strideD, s, nextStop);
-        case 2: return rc_row_run<NO, 2, false>(R, sBase, strideD, s, nextStop);
-        case 3: return rc_row_run<NO, 3, false>(R, sBase, strideD, s, nextStop);
-        case 4: return rc_row_run<NO, 4, false>(R, sBase, strideD, s, nextStop);
-        case 5: return rc_row_run<NO, 5, false>(R, sBase, strideD, s, nextStop);
-        case 6: return rc_row_run<NO, 6, false>(R, sBase, strideD, s, nextStop);
-        case 7: case 8: return rc_row_run<NO, 8, false>(R, sBase, strideD, s, nextStop);
-        default: return rc_row_run<NO, RC_ROW_MAXM, false>(R, sBase, strideD, s, nextStop);
+        case 2: return rc_row_run<NO, RcRowLen<NO, 2>::value, false>(R, sBase, strideD, s, nextStop);
+        case 3: return rc_row_run<NO, RcRowLen<NO, 3>::value, false>(R, sBase, strideD, s, nextStop);
+        case 4: return rc_row_run<NO, RcRowLen<NO, 4>::value, false>(R, sBase, strideD, s, nextStop);
+        case 5: return rc_row_run<NO, RcRowLen<NO, 5>::value, false>(R, sBase, strideD, s, nextStop);
+        case 6: return rc_row_run<NO, RcRowLen<NO, 6>::value, false>(R, sBase, strideD, s, nextStop);
+        case 7: case 8: return rc_row_run<NO, RcRowLen<NO, 8>::value, false>(R, sBase, strideD, s, nextStop);
+        default: return rc_row_run<NO, RcRowLen<NO, RC_ROW_MAXM>::value, false>(R, sBase, strideD, s, nextStop);
     }
 }
 
@@ -1424,7 +1423,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
     const unsigned zeroB = sBase + K::O_B + K::ZERO_B;
 #pragma unroll
-    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; R.Mnb[d] = 0; }
+    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
     R.aREr = padRE; R.myB = zeroB; R.M = 0; R.NO = 0;
     R.unit = false; R.fetchOn = false; R.dacc = 0.0;
     R.fPtr = ktab;
@@ -1449,11 +1448,12 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
         ringStarted = true;
     }
     // the row's record; its loads are in flight while the block gathers b
-    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = make_uint4(0u, 0u, 0u, 0u);
+    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = make_uint4(0u, 0u, 0u, 0u), lc = make_uint4(0u, 0u, 0u, 0u);
     if (R.rowOn) {
-        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + 2 * (size_t)(hdrB.z + tid);
+        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + 3 * (size_t)tid;
         la = lane[0];
         lb = lane[1];
+        lc = lane[2];
     }
     if (tid < np) {
         const int2 rec = reinterpret_cast<const int2*>(pl.kPatRec)[pat0 + tid];
@@ -1487,21 +1487,21 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     const uint16_t* myRefs = pl.rowRefAll;
     int myPid = 0, myOut = 0;
     if (R.rowOn) {
-        R.M = (int)(la.y & 0xFFu);
-        R.NO = (int)((la.y >> 8) & 0xFFu);
+        R.M = (int)(la.z & 0xFFu);
+        R.NO = (int)((la.z >> 8) & 0xFFu);
         R.unit = R.NO == 0;                                     // x = e_r is the j = 1 state of a single-branch pattern
-        R.aREr = sBase + K::O_RE + (la.x >> 24) * 16u;
-        R.myB = sBase + K::O_B + (la.z & 0xFFFFu) * 8u;
-        const unsigned nb[RC_ROW_NO] = {la.z >> 16, la.w & 0xFFFFu, la.w >> 16};
+        R.aREr = sBase + K::O_RE + (la.y >> 24) * 16u;
+        R.myB = sBase + K::O_B + (la.w & 0xFFFFu) * 8u;
+        const unsigned rowsW[2] = {la.x, la.y};
+        const unsigned offW[4] = {la.w, lb.x, lb.y, lb.z};       // 8 x u16: own row, neighbour rows
 #pragma unroll
         for (int d = 0; d < RC_ROW_NO; ++d) {
-            R.aRE[d] = sBase + K::O_RE + ((la.x >> (8 * d)) & 0xFFu) * 16u;
-            R.aB[d] = sBase + K::O_B + nb[d] * 8u;
-            R.Mnb[d] = nb[d] == RC_ROW_BCAP ? 0 : R.M;
+            R.aRE[d] = sBase + K::O_RE + ((rowsW[d >> 2] >> (8 * (d & 3))) & 0xFFu) * 16u;
+            R.aB[d] = sBase + K::O_B + ((offW[(d + 1) >> 1] >> (16 * ((d + 1) & 1))) & 0xFFFFu) * 8u;
         }
-        myOut = (int)lb.x;
-        myRefs = pl.rowRefAll + (size_t)lb.y * RC_ROW_MAXM;
-        myPid = (int)lb.z;
+        myOut = (int)lb.w;
+        myRefs = pl.rowRefAll + (size_t)lc.x * RC_ROW_MAXM;
+        myPid = (int)lc.y;
         // b of the row from shared memory (filled cooperatively above)
 #pragma unroll
         for (int j = 0; j < RC_ROW_MAXM; ++j)
@@ -1533,11 +1533,19 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
             rc_cp_wait<RC_RDEPTH - 2>();
             __syncthreads();
             int par;
-            switch (NOw) {
+            static_assert(RC_ROW_NO == 7, "dispatch over the number of other branches");
+            // a warp at the border of two cost classes can combine many other branches (one lane) with a long row (another
+            // lane): no specialised variant exists for that (RcRowLen), the general one covers it
+            if (NOw > 3 && NOw + Mw > RC_ROW_SUM) par = rc_row_run<RC_ROW_NO, RC_ROW_MAXM, false>(R, sBase, strideD, s, nextStop);
+            else switch (NOw) {
                 case 0: par = rc_row_dispatch_m<0>(R, sBase, strideD, s, nextStop, Mw); break;
                 case 1: par = rc_row_dispatch_m<1>(R, sBase, strideD, s, nextStop, Mw); break;
                 case 2: par = rc_row_dispatch_m<2>(R, sBase, strideD, s, nextStop, Mw); break;
-                default: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 3: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 4: par = rc_row_dispatch_m<4>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 5: par = rc_row_dispatch_m<5>(R, sBase, strideD, s, nextStop, Mw); break;
+                case 6: par = rc_row_dispatch_m<6>(R, sBase, strideD, s, nextStop, Mw); break;
+                default: par = rc_row_dispatch_m<7>(R, sBase, strideD, s, nextStop, Mw); break;
             }
             cp ^= par;
             rc_cp_wait<0>();
@@ -1595,8 +1603,6 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
             R.rowOn = false;
             R.unit = false;
             R.M = 0;
-#pragma unroll
-            for (int d = 0; d < RC_ROW_NO; ++d) R.Mnb[d] = 0;
         }
         // b of the continuing rows must sit at parity 0 for the next run
         if (cp) {

@@ -255,7 +255,8 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
         box *= mk;
         if (mk > rm) { rm = mk; rk = k; }
     }
-    bool ok = box == (long long)L.size() && nz >= 1 && nz - 1 <= RC_ROW_NO && rm <= RC_ROW_MAXM;
+    bool ok = box == (long long)L.size() && nz >= 1 && nz - 1 <= RC_ROW_NO && rm <= RC_ROW_MAXM &&
+              (nz - 1 <= 3 || nz - 1 + rm <= RC_ROW_SUM);
     int stride = 1;
     for (int k = rk + 1; k < c.P && ok; ++k) if (pp.mx[m0 + (size_t)k]) stride *= pp.mx[m0 + (size_t)k];
     size_t rowStart = pp.rowRef.size();
@@ -473,13 +474,13 @@ static std::string build_bin_images(PlanHost& out) {
         const int b0 = out.kBinBase[(size_t)e];
         for (int bI = b0; bI < b0 + out.nKBins[(size_t)e]; ++bI) {
             const int p0 = out.kBinPatOff[(size_t)bI], p1 = out.kBinPatOff[(size_t)bI + 1];
-            if (out.kLane.size() / RC_LANE_N > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
+            if (out.kLane.size() / 4 > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
             int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
             hdr[0] = p0;
             hdr[1] = p1 - p0;
             hdr[4] = out.kFetchOff[(size_t)bI];
             hdr[5] = out.kFetchOff[(size_t)bI + 1] - out.kFetchOff[(size_t)bI];
-            hdr[6] = (int)(out.kLane.size() / RC_LANE_N);
+            hdr[6] = (int)(out.kLane.size() / 4);
             hdr[7] = (int)(out.kElem.size() / 2);
             int lanes = 0, bOff = 0;
             for (int q = p0; q < p1; ++q) {
@@ -519,31 +520,31 @@ static std::string build_bin_images(PlanHost& out) {
                     const int Mp = M | 1, nr = ro[i + 1] - ro[i];
                     for (int r = 0; r < nr; ++r) {
                         const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
-                        uint32_t rec[RC_LANE_N] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        uint32_t nb[RC_ROW_NO];
+                        uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                        uint32_t off[RC_ROW_NO + 1];
+                        off[0] = (uint32_t)(bOff + r * Mp);
+                        static_assert(RC_ROW_NO == 7, "row lane record packs seven other branches");
                         for (int d = 0; d < RC_ROW_NO; ++d) {
                             uint32_t row = RC_KROWS - 1;
-                            nb[d] = RC_ROW_BCAP;
+                            off[d + 1] = RC_ROW_BCAP;
                             if (d < NO) {
                                 const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
                                 const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
                                 row = (uint32_t)((int)rb[k] + x - 1);
-                                if ((w >> 16) != RC_NO_UP) nb[d] = (uint32_t)(bOff + (int)(w >> 16) * Mp);
+                                if ((w >> 16) != RC_NO_UP) off[d + 1] = (uint32_t)(bOff + (int)(w >> 16) * Mp);
                             }
-                            if (row > 0xFFu || nb[d] > RC_ROW_BCAP) return "row bin image out of range";
-                            rec[0] |= row << (8 * d);
+                            if (row > 0xFFu || off[d + 1] > RC_ROW_BCAP) return "row bin image out of range";
+                            rec[d >> 2] |= row << (8 * (d & 3));
                         }
-                        static_assert(RC_ROW_NO == 3, "lane record packs three other branches");
-                        if (rb[rk] > 0xFFu) return "row bin image out of range";
-                        rec[0] |= (uint32_t)rb[rk] << 24;
-                        rec[1] = (uint32_t)M | ((uint32_t)NO << 8);
-                        rec[2] = (uint32_t)(bOff + r * Mp) | (nb[0] << 16);
-                        rec[3] = nb[1] | (nb[2] << 16);
-                        rec[4] = (uint32_t)so[i];
+                        if (rb[rk] > 0xFFu || off[0] > RC_ROW_BCAP) return "row bin image out of range";
+                        rec[1] |= (uint32_t)rb[rk] << 24;
+                        rec[2] = (uint32_t)M | ((uint32_t)NO << 8);
+                        for (int q = 0; q < RC_ROW_NO + 1; ++q) rec[3 + (q >> 1)] |= off[q] << (16 * (q & 1));
+                        rec[7] = (uint32_t)so[i];
                         if (grow > 0xFFFFFFFFLL) return "bin images too large";
-                        rec[5] = (uint32_t)grow;
-                        rec[6] = (uint32_t)i;
-                        out.kLane.insert(out.kLane.end(), rec, rec + RC_LANE_N);
+                        rec[8] = (uint32_t)grow;
+                        rec[9] = (uint32_t)i;
+                        out.kLane.insert(out.kLane.end(), rec, rec + RC_RLANE_N);
                         for (int j = 0; j < Mp; ++j) {
                             uint32_t g0 = 0u, g1 = 0u;
                             if (j < M) {
@@ -924,7 +925,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 rows += pps[(size_t)i].rowCnt[(size_t)e];
                 states += pps[(size_t)i].live[(size_t)e];
             }
-            bool use = all && rows > 0 && (double)states / (double)rows >= 2.5;
+            static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
+            bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
             if (rowEnv) use = all && std::atoi(rowEnv) != 0;
             out.epochMode[(size_t)e] = use ? 1 : 0;
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
@@ -1155,7 +1157,7 @@ std::string check_plan(const PlanHost& h) {
     if (!h.kBinBase.empty()) {
         if (h.kBinHdr.size() != h.kBinPatOff.size() * (size_t)RC_HDR_N || h.kPatRec.size() != h.kBinPats.size() * 2)
             return fail("bin image sizes");
-        const long long nLaneRec = (long long)(h.kLane.size() / RC_LANE_N), nElemRec = (long long)(h.kElem.size() / 2);
+        const long long nLaneQ = (long long)(h.kLane.size() / 4), nElemRec = (long long)(h.kElem.size() / 2);
         auto gather_ok = [&](int e, uint32_t r0, uint32_t r1) {
             if (e == 0) return (r0 == 0u || r0 == RC_IMG_SEED) && r1 == 0u;
             const long long cnt = r1 >> RC_IMG_CNT_SHIFT, prev = r1 & ((1u << RC_IMG_CNT_SHIFT) - 1u);
@@ -1173,14 +1175,15 @@ std::string check_plan(const PlanHost& h) {
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
                 if (lanes < 1 || lanes > RC_BLOCK || nB < 0 || nB > RC_ROW_BCAP) return fail("image header lanes");
-                if (hdr[6] < 0 || hdr[6] + lanes > nLaneRec || hdr[7] < 0 || hdr[7] + nB > nElemRec) return fail("image record range");
+                if (hdr[6] < 0 || hdr[6] + (long long)lanes * (rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)
+                    return fail("image record range");
                 for (int q = 0; q < np; ++q) {
                     const int rec = h.kPatRec[(size_t)(hdr[0] + q) * 2 + 1];
                     if (h.kPatRec[(size_t)(hdr[0] + q) * 2] != h.kBinPats[(size_t)(hdr[0] + q)]) return fail("image pattern id");
                     if ((rec & 0xFFFF) >= lanes || (rec >> 16) > nB) return fail("image pattern offsets");
                 }
                 for (int t = 0; t < lanes; ++t) {
-                    const uint32_t* r = &h.kLane[(size_t)(hdr[6] + t) * RC_LANE_N];
+                    const uint32_t* r = &h.kLane[(size_t)hdr[6] * 4 + (size_t)t * (rows ? RC_RLANE_N : RC_LANE_N)];
                     if (!rows) {
                         for (int d = 0; d < 8; ++d) {
                             const int row = (int)((r[d >> 2] >> (8 * (d & 3))) & 0xFFu), up = (int)((r[2 + (d >> 2)] >> (8 * (d & 3))) & 0xFFu);
@@ -1190,20 +1193,21 @@ std::string check_plan(const PlanHost& h) {
                         if ((long long)r[5] >= h.epochSlots[(size_t)e]) return fail("image carry slot");
                         if (!gather_ok(e, r[6], r[7])) return fail("image gather record");
                     } else {
-                        const int M = (int)(r[1] & 0xFFu), NO = (int)((r[1] >> 8) & 0xFFu);
-                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO) return fail("image row shape");
-                        const int rr = (int)(r[0] >> 24);
+                        const int M = (int)(r[2] & 0xFFu), NO = (int)((r[2] >> 8) & 0xFFu);
+                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || (NO > 3 && NO + M > RC_ROW_SUM)) return fail("image row shape");
+                        const int rr = (int)(r[1] >> 24);
                         if (rr < 1 || rr + M - 1 >= nFetch) return fail("image row-branch pair rows");
                         for (int d = 0; d < RC_ROW_NO; ++d) {
-                            const int row = (int)((r[0] >> (8 * d)) & 0xFFu);
+                            const int row = (int)((r[d >> 2] >> (8 * (d & 3))) & 0xFFu);
                             if (row != RC_KROWS - 1 && (row < 1 || row >= nFetch)) return fail("image pair row");
+                            if (d >= NO && row != RC_KROWS - 1) return fail("image unused pair row");
                         }
-                        const int offs[4] = {(int)(r[2] & 0xFFFFu), (int)(r[2] >> 16), (int)(r[3] & 0xFFFFu), (int)(r[3] >> 16)};
-                        if (offs[0] + M > nB) return fail("image own row");
-                        for (int d = 1; d < 4; ++d)
-                            if (offs[d] != RC_ROW_BCAP && offs[d] + M > nB) return fail("image neighbour row");
-                        if ((long long)r[4] >= h.epochSlots[(size_t)e] || (long long)(r[5] + 1) * RC_ROW_MAXM > (long long)h.rowRefAll.size() ||
-                            (int)r[6] >= nPat)
+                        for (int q = 0; q < RC_ROW_NO + 1; ++q) {
+                            const int off = (int)((r[3 + (q >> 1)] >> (16 * (q & 1))) & 0xFFFFu);
+                            if (q == 0 ? off + M > nB : (off != RC_ROW_BCAP && off + M > nB)) return fail("image row offsets");
+                        }
+                        if ((long long)r[7] >= h.epochSlots[(size_t)e] || (long long)(r[8] + 1) * RC_ROW_MAXM > (long long)h.rowRefAll.size() ||
+                            (int)r[9] >= nPat)
                             return fail("image row hand-over");
                     }
                 }

@@ -15,7 +15,8 @@
 #define RC_EV_JOIN_D 0
 #define RC_EV_SPLIT_D 1
 // row mode of the keyed tier: one thread per row of states along the widest branch of a box-shaped live set
-#define RC_ROW_NO 3          // other non-zero branches of a row at most
+#define RC_ROW_NO 7          // other non-zero branches of a row at most
+#define RC_ROW_SUM 11        // with more than 3 other branches: other branches + row length <= RC_ROW_SUM (bounds the kernel variants)
 #define RC_ROW_MAXM 10       // longest row
 #define RC_ROW_BCAP 1536     // states per row-mode block at most (rows are stored with an odd stride: no bank conflicts)
 #define RC_NPBR 128          // patterns per row-mode bin at most
@@ -103,25 +104,28 @@ struct RcPlanDev {
     // ---- bin images: what a block's set-up needs, already resolved to lane order (rc_plan.h, build_bin_images) ----
     const int* kBinHdr;          // [bin][RC_HDR_N], same bin indexing as kBinPatOff
     const int* kPatRec;          // [position in kBinPats][2]: pattern id, first lane | first b double << 16
-    const uint32_t* kLane;       // [lane][RC_LANE_N] (layout per mode below)
+    const uint32_t* kLane;       // lane records, RC_LANE_N (state mode) or RC_RLANE_N (row mode) words each
     const uint32_t* kElem;       // [element][2], row mode: gather record of every b double of a bin
 };
 
 // Bin header (ints): 0 first entry in kBinPats/kPatRec, 1 patterns, 2 lanes (states or rows), 3 b doubles (row mode, padded
-// rows), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record, 7 first element record.
+// rows), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first element record.
 #define RC_HDR_N 8
 // Lane record (8 x u32).
 //   state mode: [0..1] pair row of component d (8 x u8; RC_KROWS-1 = the {1,0} padding pair)
 //               [2..3] lane of the neighbour x + e_k (8 x u8; own lane = no such state)
 //               [4] meta word  [5] slot inside the epoch (carry buffer)  [6..7] gather record
-//   row mode:   [0] pair rows of the other branches (3 x u8) | pair row of (row branch, j = 1) << 24
-//               [1] M | NO << 8
-//               [2] own row | neighbour row 0 << 16    [3] neighbour rows 1 | 2 << 16   (b offsets in doubles;
-//                   RC_ROW_BCAP = the always-zero row)
-//               [4] first slot of the pattern in the epoch  [5] row index in rowRefAll  [6] pattern id  [7] 0
+//   row mode (RC_RLANE_N = 12 x u32):
+//               [0..1] pair rows of the other branches (7 x u8) | pair row of (row branch, j = 1) << 24 in [1]
+//               [2] M | NO << 8
+//               [3..6] b offsets in doubles (8 x u16): own row, then the neighbour row along each other branch
+//                      (RC_ROW_BCAP = the always-zero row)
+//               [7] first slot of the pattern in the epoch  [8] row index in rowRefAll  [9] pattern id  [10..11] 0
+//   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row lane).
 // Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
 // and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
 #define RC_LANE_N 8
+#define RC_RLANE_N 12
 #define RC_IMG_SEED 0xFFFFFFFFu
 #define RC_IMG_CNT_SHIFT 26
 
