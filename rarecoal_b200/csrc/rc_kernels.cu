@@ -1291,9 +1291,10 @@ struct RcRowK {
     static_assert(O_RE % 16 == 0, "16-byte alignment of the pair table");
 };
 
+template <int NOCAP>
 struct RcRowRegs {
     double b[RC_ROW_MAXM];
-    unsigned aRE[RC_ROW_NO], aB[RC_ROW_NO];   // pair of (branch d, x_d) in ring slot 0 / neighbour row (parity 0)
+    unsigned aRE[NOCAP], aB[NOCAP];   // pair of (branch d, x_d) in ring slot 0 / neighbour row (parity 0)
     unsigned aREr, myB;                        // pair of (row branch, j = 1) in ring slot 0 / own row (parity 0)
     int M, NO;
     bool unit, rowOn, fetchOn;
@@ -1303,8 +1304,8 @@ struct RcRowRegs {
 
 // grid steps s .. nextStop-1 for a warp whose rows have at most NO other branches and length at most M
 // EX: every lane of the warp owns a row of exactly M states — no per-state predicates
-template <int NO, int M, bool EX>
-__device__ __forceinline__ int rc_row_run(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
+template <int NO, int M, bool EX, int NOCAP>
+__device__ __forceinline__ int rc_row_run(RcRowRegs<NOCAP>& R, const unsigned sBase, const long long strideD, int& s,
                                           const int nextStop) {
     typedef RcRowK K;
     const unsigned myRE = sBase + K::O_RE + threadIdx.x * 16u;
@@ -1360,8 +1361,8 @@ struct RcRowLen {
     static constexpr int MAXM = NO <= 3 ? RC_ROW_MAXM : (RC_ROW_SUM - NO < 1 ? 1 : RC_ROW_SUM - NO);
     static constexpr int value = M <= MAXM ? M : MAXM;
 };
-template <int NO>
-__device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sBase, const long long strideD, int& s,
+template <int NO, int NOCAP>
+__device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs<NOCAP>& R, const unsigned sBase, const long long strideD, int& s,
                                                  const int nextStop, const int Mw) {
     // bins hold rows of one length (rc_plan.cpp, cost classes), so most warps take the predicate-free variant
     if (__all_sync(0xFFFFFFFFu, R.rowOn && R.M == Mw)) {
@@ -1393,6 +1394,8 @@ __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs& R, const unsigned sB
 #ifndef RC_ROWS_MINB
 #define RC_ROWS_MINB 3
 #endif
+// NOCAP = 3 for epochs whose rows all have at most 3 other branches (fewer registers, smaller code), else RC_ROW_NO
+template <int NOCAP>
 __global__ void __launch_bounds__(RC_BLOCK, RC_ROWS_MINB)
 rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
                          const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
@@ -1417,13 +1420,13 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     const int sShort = models[b].sShort;
     const RcModelEpochDev mE = mep[models[b].mepOff + e];
 
-    RcRowRegs R;
+    RcRowRegs<NOCAP> R;
 #pragma unroll
     for (int j = 0; j < RC_ROW_MAXM; ++j) R.b[j] = 0.0;
     const unsigned padRE = sBase + K::O_RE + K::RE_PAD;
     const unsigned zeroB = sBase + K::O_B + K::ZERO_B;
 #pragma unroll
-    for (int d = 0; d < RC_ROW_NO; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
+    for (int d = 0; d < NOCAP; ++d) { R.aRE[d] = padRE; R.aB[d] = zeroB; }
     R.aREr = padRE; R.myB = zeroB; R.M = 0; R.NO = 0;
     R.unit = false; R.fetchOn = false; R.dacc = 0.0;
     R.fPtr = ktab;
@@ -1495,7 +1498,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
         const unsigned rowsW[2] = {la.x, la.y};
         const unsigned offW[4] = {la.w, lb.x, lb.y, lb.z};       // 8 x u16: own row, neighbour rows
 #pragma unroll
-        for (int d = 0; d < RC_ROW_NO; ++d) {
+        for (int d = 0; d < NOCAP; ++d) {
             R.aRE[d] = sBase + K::O_RE + ((rowsW[d >> 2] >> (8 * (d & 3))) & 0xFFu) * 16u;
             R.aB[d] = sBase + K::O_B + ((offW[(d + 1) >> 1] >> (16 * ((d + 1) & 1))) & 0xFFFFu) * 8u;
         }
@@ -1534,18 +1537,28 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
             __syncthreads();
             int par;
             static_assert(RC_ROW_NO == 7, "dispatch over the number of other branches");
-            // a warp at the border of two cost classes can combine many other branches (one lane) with a long row (another
-            // lane): no specialised variant exists for that (RcRowLen), the general one covers it
-            if (NOw > 3 && NOw + Mw > RC_ROW_SUM) par = rc_row_run<RC_ROW_NO, RC_ROW_MAXM, false>(R, sBase, strideD, s, nextStop);
-            else switch (NOw) {
-                case 0: par = rc_row_dispatch_m<0>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 1: par = rc_row_dispatch_m<1>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 2: par = rc_row_dispatch_m<2>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 3: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 4: par = rc_row_dispatch_m<4>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 5: par = rc_row_dispatch_m<5>(R, sBase, strideD, s, nextStop, Mw); break;
-                case 6: par = rc_row_dispatch_m<6>(R, sBase, strideD, s, nextStop, Mw); break;
-                default: par = rc_row_dispatch_m<7>(R, sBase, strideD, s, nextStop, Mw); break;
+            if constexpr (NOCAP <= 3) {
+                switch (NOw) {
+                    case 0: par = rc_row_dispatch_m<0>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 1: par = rc_row_dispatch_m<1>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 2: par = rc_row_dispatch_m<2>(R, sBase, strideD, s, nextStop, Mw); break;
+                    default: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
+                }
+            } else {
+                // a warp at the border of two cost classes can combine many other branches (one lane) with a long row
+                // (another lane): no specialised variant exists for that (RcRowLen), the general one covers it
+                if (NOw > 3 && NOw + Mw > RC_ROW_SUM)
+                    par = rc_row_run<RC_ROW_NO, RC_ROW_MAXM, false>(R, sBase, strideD, s, nextStop);
+                else switch (NOw) {
+                    case 0: par = rc_row_dispatch_m<0>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 1: par = rc_row_dispatch_m<1>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 2: par = rc_row_dispatch_m<2>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 3: par = rc_row_dispatch_m<3>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 4: par = rc_row_dispatch_m<4>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 5: par = rc_row_dispatch_m<5>(R, sBase, strideD, s, nextStop, Mw); break;
+                    case 6: par = rc_row_dispatch_m<6>(R, sBase, strideD, s, nextStop, Mw); break;
+                    default: par = rc_row_dispatch_m<7>(R, sBase, strideD, s, nextStop, Mw); break;
+                }
             }
             cp ^= par;
             rc_cp_wait<0>();
@@ -1761,14 +1774,23 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int
     const double* bp = bPrev + (size_t)b0 * bStride;
     double* bc = bCur + (size_t)b0 * bStride;
     if (rowMode) {
-        static bool cr = false;
+        static bool cr3 = false, cr7 = false;
         const size_t rsmem = (sizeof(RcRowSmem) + 15) & ~(size_t)15;
-        if (!cr) {
-            cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-            if (err != cudaSuccess) return err;
-            cr = true;
+        if (rowMode == 1) {
+            if (!cr3) {
+                cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+                if (err != cudaSuccess) return err;
+                cr3 = true;
+            }
+            rc_propagate_rows_kernel<3><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        } else {
+            if (!cr7) {
+                cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel<RC_ROW_NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+                if (err != cudaSuccess) return err;
+                cr7 = true;
+            }
+            rc_propagate_rows_kernel<RC_ROW_NO><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         }
-        rc_propagate_rows_kernel<<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return cudaGetLastError();
     }
     if (pl.nnzw <= 4) {

@@ -928,7 +928,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
             bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
             if (rowEnv) use = all && std::atoi(rowEnv) != 0;
-            out.epochMode[(size_t)e] = use ? 1 : 0;
+            int maxNO = 0;
+            for (int i : order) maxNO = std::max(maxNO, (int)pps[(size_t)i].rowNO[(size_t)e]);
+            out.epochMode[(size_t)e] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
             if (use) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];

@@ -95,7 +95,7 @@ struct RcPlanDev {
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
     // ---- row mode ----
-    const int* epochMode;        // [nEpochs] 0: one state per thread, 1: one row per thread
+    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches
     const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
     const long long* rowEpochBase; // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states

@@ -5,8 +5,11 @@ launches of one evaluation, read by bench.py -> roofline.traffic) and prints the
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+rep = sys.argv[1]          # .ncu-rep, or the raw page already exported on the GPU box (ncu -i X --page raw --csv)
+if rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 raw = raw[raw.index('"ID"'):]
 open(os.path.join(ROOT, "profiles", "r01_propagate_raw.csv"), "w").write(raw)
 rows = list(csv.reader(io.StringIO(raw)))
