@@ -1646,6 +1646,262 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pattern mode of the keyed tier (epochs in which every pattern has at most two non-zero branches A, B and at most
+// RC_PAT_MAXS live states — the last epochs of a tree model): one thread owns a whole pattern.  b(x_A, x_B) lives in
+// registers, so both neighbours of a state are registers too and shared memory only carries the {G,E2} pairs:
+//     b'(i,j) = b(i,j) G_A(i) G_B(j) + b(i+1,j) E2_A(i) + b(i,j+1) E2_B(j)                        (Core.hs:259)
+// with MA + MB pair loads per pattern and step instead of one per state and branch.  Blocks are small (RC_PBLOCK threads,
+// several resident per SM) and hold patterns of one shape (MA, MB) only (rc_plan.cpp), so the update is fully unrolled
+// without predicates; every thread fetches up to four pair rows per grid step into the ring.
+#define RC_PDEPTH 4
+#define RC_PFETCH (RC_KROWS / RC_PBLOCK)
+struct RcPatSmem {
+    double RE[RC_PDEPTH * 2 * RC_KROWS];               // [slot][row]{G, E2}; row 0 = {dt, 0}
+    double bb[RC_PBLOCK * RC_PAT_MAXS];                // gathered b of the bin, pattern after pattern
+};
+static_assert(offsetof(RcPatSmem, RE) % 16 == 0, "16-byte alignment of the pair table");
+
+struct RcPatRegs {
+    double b[RC_PAT_MAXS];
+    unsigned aA, aB;              // pair of (A, x = 1) / (B, x = 1) in ring slot 0
+    bool on, unit;
+    double dacc;
+    const double* fp[RC_PFETCH];  // this thread's pairs in the step row to be copied next
+    unsigned fmask;               // bit q: the thread fetches pair row q * RC_PBLOCK + tid
+};
+
+template <int MA, int MB>
+__device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
+                                           unsigned& slot) {
+    constexpr unsigned RE_SLOT = RC_KROWS * 16u;
+    constexpr int MBp = MB ? MB : 1;
+    const unsigned myRE = sBase + threadIdx.x * 16u;
+    for (; s < nextStop; ++s) {
+        const unsigned prev = slot == 0 ? (RC_PDEPTH - 1) * RE_SLOT : slot - RE_SLOT;      // slot of step s - 1: free again
+#pragma unroll
+        for (int q = 0; q < RC_PFETCH; ++q) {
+            rc_cp_async16_if(myRE + prev + (unsigned)q * RC_PBLOCK * 16u, R.fp[q], (R.fmask >> q) & 1u);
+            R.fp[q] += strideD;
+        }
+        rc_cp_commit();
+        if (R.on) {
+            double gB[MBp], eB[MBp];
+            if (MB) {
+#pragma unroll
+                for (int j = 0; j < MBp; ++j) rc_lds128(R.aB + slot + (unsigned)j * 16u, gB[j], eB[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < MA; ++i) {
+                double gA, eA;
+                rc_lds128(R.aA + slot + (unsigned)i * 16u, gA, eA);
+#pragma unroll
+                for (int j = 0; j < MBp; ++j) {
+                    const int x = i * MBp + j;
+                    double t2 = (i + 1 < MA) ? R.b[x + MBp] * eA : 0.0;          // old values: not yet overwritten
+                    if (MB && j + 1 < MB) t2 = fma(R.b[x + 1], eB[j], t2);
+                    const double D = MB ? gA * gB[j] : gA;
+                    R.b[x] = fma(R.b[x], D, t2);                                 // updateB, Core.hs:259
+                }
+            }
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);    // updateD, Core.hs:282-288
+        }
+        rc_cp_wait<RC_PDEPTH - 2>();
+        __syncthreads();
+        slot = slot + RE_SLOT == RC_PDEPTH * RE_SLOT ? 0u : slot + RE_SLOT;
+    }
+}
+
+// (MA, MB) shapes the planner admits: MB <= MA <= RC_ROW_MAXM and MA * max(MB, 1) <= RC_PAT_MAXS
+template <int MB>
+__device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
+                                                  unsigned& slot, const int MA) {
+    constexpr int MBp = MB ? MB : 1;
+#define RC_PAT_CASE(A) \
+    case A: if constexpr (A >= MBp && A * MBp <= RC_PAT_MAXS) { rc_pat_run<A, MB>(R, sBase, strideD, s, nextStop, slot); } break;
+    switch (MA) {
+        RC_PAT_CASE(1) RC_PAT_CASE(2) RC_PAT_CASE(3) RC_PAT_CASE(4) RC_PAT_CASE(5)
+        RC_PAT_CASE(6) RC_PAT_CASE(7) RC_PAT_CASE(8) RC_PAT_CASE(9) RC_PAT_CASE(10)
+        default: break;
+    }
+#undef RC_PAT_CASE
+    static_assert(RC_ROW_MAXM == 10, "cases above");
+}
+
+__global__ void __launch_bounds__(RC_PBLOCK, 8)
+rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+                        const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
+                        const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
+                        long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    typedef RcPatSmem SM;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    if (models[b].nSteps < 0 || models[b].mode != 1) return;
+    const int P = pl.P, nPat = pl.nPat;
+    SM& S = *reinterpret_cast<SM*>(smemRaw);
+    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
+    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
+    const int np = hdrA.y, nB = hdrA.w;
+    const bool isLast = e + 1 == pl.nEpochs;
+    const int sShort = models[b].sShort;
+    const RcModelEpochDev mE = mep[models[b].mepOff + e];
+
+    RcPatRegs R;
+#pragma unroll
+    for (int x = 0; x < RC_PAT_MAXS; ++x) R.b[x] = 0.0;
+    R.on = tid < np;
+    R.unit = false;
+    R.dacc = 0.0;
+    R.fmask = 0u;
+    // ---- pair ring: every thread copies the pair rows tid, tid + RC_PBLOCK, ... of the bin ----
+    const int rowPairs = pl.ep[e].rowPairs;
+    const long long strideD = (long long)rowPairs * 2;
+    int fOff[RC_PFETCH];
+#pragma unroll
+    for (int q = 0; q < RC_PFETCH; ++q) {
+        const int r = q * RC_PBLOCK + tid;
+        fOff[q] = 0;
+        if (r < hdrB.y) { fOff[q] = pl.kFetchRows[hdrB.x + r]; R.fmask |= 1u << q; }
+    }
+    int s = mE.beg;
+    unsigned slot = 0;
+    auto ring_start = [&]() {
+#pragma unroll
+        for (int q = 0; q < RC_PFETCH; ++q) R.fp[q] = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff[q]) * 2;
+#pragma unroll
+        for (int u = 0; u < RC_PDEPTH - 1; ++u) {
+#pragma unroll
+            for (int q = 0; q < RC_PFETCH; ++q) {
+                rc_cp_async16_if(sBase + (unsigned)u * RC_KROWS * 16u + (unsigned)(q * RC_PBLOCK + tid) * 16u, R.fp[q], (R.fmask >> q) & 1u);
+                R.fp[q] += strideD;
+            }
+            rc_cp_commit();
+        }
+        slot = 0;
+    };
+    bool ringStarted = false;
+    if (s < mE.end) { ring_start(); ringStarted = true; }
+    // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory ----
+    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la;
+    if (R.on) {
+        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + 3 * (size_t)tid;
+        la = lane[0];
+        lb = lane[1];
+        lc = lane[2];
+    }
+    {
+        const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
+        const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
+        const double* bp = bPrev + (size_t)b * bStride;
+        for (int i = tid; i < nB; i += RC_PBLOCK) {
+            const uint2 g = el[i];
+            double v = 0.0;
+            if (g.x == RC_IMG_SEED) v = 1.0;                                    // makeInitCoalState, Core.hs:66
+            else {
+                const int cnt = (int)(g.y >> RC_IMG_CNT_SHIFT);
+                if (cnt) v = rc_gather(pl.trEnt + g.x, 0, cnt, bp + (g.y & ((1u << RC_IMG_CNT_SHIFT) - 1u)), W);
+            }
+            S.bb[i] = v;
+        }
+    }
+    const int MA = (int)((la.x >> 16) & 0xFFu), MB = (int)(la.x >> 24), n = MA * (MB ? MB : 1);
+    const int pid = (int)la.w;
+    double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
+    R.aA = sBase + (la.x & 0xFFu) * 16u;
+    R.aB = sBase + ((la.x >> 8) & 0xFFu) * 16u;
+    R.unit = R.on && MB == 0;                       // x = e_A is the first state of a single-branch pattern
+    __syncthreads();
+    if (R.on) {
+        const double* mine = S.bb + la.z;
+#pragma unroll
+        for (int x = 0; x < RC_PAT_MAXS; ++x)
+            if (x < n) R.b[x] = mine[x];
+    }
+    // the block's shape: bins hold one (MA, MB) class
+    const int MAb = __shfl_sync(0xFFFFFFFFu, MA, 0), MBb = __shfl_sync(0xFFFFFFFFu, MB, 0);
+    __shared__ int shape[2];
+    if (tid == 0) { shape[0] = MAb; shape[1] = MBb; }
+    __syncthreads();
+    const int MAw = shape[0], MBw = shape[1];
+
+    bool finished = false, parked = false;
+    for (int phase = 0; phase < 2 && !finished; ++phase) {
+        int nextStop = mE.end;
+#ifdef RC_PROBE_NOLOOP
+        nextStop = s;
+#endif
+        if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
+        if (s < nextStop) {
+            if (!ringStarted) ring_start();
+            ringStarted = false;
+            rc_cp_wait<RC_PDEPTH - 2>();
+            __syncthreads();
+            switch (MBw) {
+                case 0: rc_pat_dispatch_a<0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 1: rc_pat_dispatch_a<1>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 2: rc_pat_dispatch_a<2>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 3: rc_pat_dispatch_a<3>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 4: rc_pat_dispatch_a<4>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                default: rc_pat_dispatch_a<5>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+            }
+            static_assert(RC_PAT_MAXS == 25, "MB <= 5 above");
+            rc_cp_wait<0>();
+            __syncthreads();
+        }
+        if (!parked) dp = dp + R.dacc;                                           // updateD contributions of the run
+        R.dacc = 0.0;
+        if (!(isLast && phase == 0 && s == sShort && s < models[b].nSteps)) { finished = true; break; }
+        // ---- canUseShortcut / propagateStateShortcut (Core.hs:80-118): a pattern that passes has single-branch states only ----
+        int ok = 1;
+        if (R.on) {
+            if (pl.shortcutOK[pid]) {
+                const double* aK = aShort + models[b].aShortOff;
+                const int* kid = pl.lastKeyId + (size_t)pid * P;
+                double nrA = 0.0;
+                int popIndex = -1;
+                for (int k = 0; k < P; ++k) {
+                    const double ak = aK[kid[k]];
+                    nrA = nrA + ak;
+                    if (popIndex < 0 && ak > 0.0) popIndex = k;
+                }
+                const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
+                // chooseCont (nrA + nd) nd as a recurrence along the states (Utils.hs:213-215, ascending order of factors)
+                double add = 0.0, cc = 1.0;
+#pragma unroll
+                for (int x = 0; x < RC_ROW_MAXM; ++x) {
+                    if (x < n) {
+                        const double nd = (double)(x + 1);
+                        cc = cc * ((nrA + nd) / nd);
+                        add = add + R.b[x] * (2.0 * popSize / nd / cc);
+                    }
+                }
+                dp = dp + add;
+                R.on = false;          // parked: b stays, nothing more is accumulated
+                R.unit = false;
+                parked = true;
+            } else ok = 0;
+        }
+        if (__syncthreads_and(ok)) { finished = true; break; }
+    }
+    if (tid >= np) return;
+    if (!isLast) {
+        // ---- hand b and the updateD sums to the next epoch's launch ----
+        double* out = bCur + (size_t)b * bStride + la.y;
+        const unsigned refW[7] = {lb.x, lb.y, lb.z, lb.w, lc.x, lc.y, lc.z};
+#pragma unroll
+        for (int x = 0; x < RC_PAT_MAXS; ++x)
+            if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
+        dAcc[(size_t)b * nPat + pid] = dp;
+        return;
+    }
+    double discFac = 1.0;
+    for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
+    pOut[(size_t)b * nPat + pid] = dp * models[b].theta * pl.combFac[pid] * discFac;
+}
+
+// ------------------------------------------------------------------------------------------------
 // One block per model; fixed summation order (thread-strided partials, then a shared-memory tree),
 // so results are reproducible run to run.
 __global__ void __launch_bounds__(1024)
@@ -1773,6 +2029,17 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int
     double* dac = dAcc + (size_t)b0 * pl.nPat;
     const double* bp = bPrev + (size_t)b0 * bStride;
     double* bc = bCur + (size_t)b0 * bStride;
+    if (rowMode == 3) {
+        static bool cp = false;
+        const size_t psmem = (sizeof(RcPatSmem) + 15) & ~(size_t)15;
+        if (!cp) {
+            cudaError_t err = cudaFuncSetAttribute(rc_propagate_pat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (err != cudaSuccess) return err;
+            cp = true;
+        }
+        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        return cudaGetLastError();
+    }
     if (rowMode) {
         static bool cr3 = false, cr7 = false;
         const size_t rsmem = (sizeof(RcRowSmem) + 15) & ~(size_t)15;

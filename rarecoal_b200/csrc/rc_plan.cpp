@@ -468,7 +468,7 @@ static std::string build_bin_images(PlanHost& out) {
         return true;
     };
     for (int e = 0; e < nE; ++e) {
-        const bool rows = out.epochMode[(size_t)e] != 0;
+        const bool rows = out.epochMode[(size_t)e] != 0, patM = out.epochMode[(size_t)e] == 3;
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
         const int b0 = out.kBinBase[(size_t)e];
@@ -489,7 +489,42 @@ static std::string build_bin_images(PlanHost& out) {
                 const uint16_t* rb = &out.kRowBase[(size_t)q * P];
                 out.kPatRec[(size_t)q * 2] = i;
                 out.kPatRec[(size_t)q * 2 + 1] = lanes | (bOff << 16);
-                if (!rows) {
+                if (patM) {
+                    // pattern mode: one lane per pattern; state (x_A = i + 1, x_B = j + 1) sits at position i * max(MB, 1) + j
+                    const uint32_t pr = out.patRow[(size_t)e * nPat + i];
+                    const int MA = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
+                    const int nr = ro[i + 1] - ro[i], MB = NO ? nr : 0, MBp = NO ? nr : 1;
+                    if (NO > 1 || MA * MBp != live || live > RC_PAT_MAXS) return "pattern-mode bin with an unsuitable pattern";
+                    uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t rowB = RC_KROWS - 1;
+                    std::vector<uint32_t> el((size_t)live * 2, 0u);
+                    for (int r = 0; r < nr; ++r) {
+                        const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
+                        int j = 0;
+                        if (NO) {
+                            const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO];
+                            const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
+                            rowB = rb[k];
+                            j = x - 1;
+                            if (j < 0 || j >= MB) return "pattern-mode image out of range";
+                        }
+                        for (int a = 0; a < MA; ++a) {
+                            const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + a], idx = a * MBp + j;
+                            if (ref > 0xFF) return "pattern-mode image out of range";
+                            rec[4 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
+                            if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
+                        }
+                    }
+                    if (rb[rk] > 0xFFu || rowB > 0xFFu) return "pattern-mode image out of range";
+                    rec[0] = (uint32_t)rb[rk] | (rowB << 8) | ((uint32_t)MA << 16) | ((uint32_t)MB << 24);
+                    rec[1] = (uint32_t)so[i];
+                    rec[2] = (uint32_t)bOff;
+                    rec[3] = (uint32_t)i;
+                    out.kLane.insert(out.kLane.end(), rec, rec + RC_RLANE_N);
+                    out.kElem.insert(out.kElem.end(), el.begin(), el.end());
+                    lanes += 1;
+                    bOff += live;
+                } else if (!rows) {
                     for (int s = 0; s < live; ++s) {
                         const long long g = out.epochBase[(size_t)e] + so[i] + s;
                         const uint32_t mt = out.meta[(size_t)g];
@@ -762,13 +797,23 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
         struct OpenBin {
             std::vector<int> ids, slotsE, rowsUsed, rowsSelf;
-            int rowStates = 0;
+            int rowStates = 0, cls = 0;
             std::vector<std::unordered_map<int, int>> keyRows;   // per epoch: key -> pair rows needed
         };
         // measured on C3 (44 models): 36.7 ms with lexicographic bins, 33.4 ms with cost-class bins; RC_BINSORT=0 restores the former
         const bool binSort = std::getenv("RC_BINSORT") ? std::atoi(std::getenv("RC_BINSORT")) != 0 : true;
-        auto pack_range = [&](int e0, int e1, int maxPats, bool rowMode, std::vector<int>& patOff, std::vector<int>& pats) {
+        // mode: 0 one state per lane, 1 one row per lane, 3 one pattern per lane (bins of one cost class only)
+        auto pack_range = [&](int e0, int e1, int maxPats, int mode, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
+            const bool rowMode = mode != 0, patMode = mode == 3;
+            auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
+            auto clsOf = [&](int i) {
+                const PatPlan& pp = pps[(size_t)i];
+                if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0] + (patMode ? 1024 * pp.rowCnt[(size_t)e0] : 0);
+                int c = 0;
+                for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
+                return c;
+            };
             const size_t WINDOW = 12;
             std::vector<OpenBin> open;
             auto flush = [&](OpenBin& ob) {
@@ -780,7 +825,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         for (int k = 0; k < P; ++k) c += pps[(size_t)i].mx[(size_t)e0 * P + k] ? 1 : 0;
                         return c;
                     };
-                    if (rowMode)
+                    if (patMode) {
+                    } else if (rowMode)
                         std::stable_sort(ob.ids.begin(), ob.ids.end(), [&](int a, int b) {
                             const PatPlan &x = pps[(size_t)a], &y = pps[(size_t)b];
                             if (x.rowNO[(size_t)e0] != y.rowNO[(size_t)e0]) return x.rowNO[(size_t)e0] > y.rowNO[(size_t)e0];
@@ -796,9 +842,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 const PatPlan& pp = pps[(size_t)i];
                 if ((int)ob.ids.size() + 1 > maxPats) return false;
                 for (int q = 0; q < nE; ++q)
-                    if (ob.slotsE[(size_t)q] + (rowMode ? pp.rowCnt[(size_t)(e0 + q)] : pp.live[(size_t)(e0 + q)]) > fastBlock) return false;
+                    if (ob.slotsE[(size_t)q] + lanesOf(pp, e0 + q) > fastBlock) return false;
+                if (patMode && !ob.ids.empty() && ob.cls != clsOf(i)) return false;
                 // padded states of the rows (odd stride) must fit the block's b buffer
-                const int padAdd = rowMode ? pp.rowCnt[(size_t)e0] * (pp.rowM[(size_t)e0] | 1) : 0;
+                const int padAdd = (rowMode && !patMode) ? pp.rowCnt[(size_t)e0] * (pp.rowM[(size_t)e0] | 1) : 0;
                 if (ob.rowStates + padAdd > RC_ROW_BCAP) return false;
                 std::vector<int> add((size_t)nE, 0), addSelf((size_t)nE, 0);
                 for (int q = 0; q < nE; ++q) {
@@ -825,9 +872,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         if (mxk > have) { ob.rowsUsed[(size_t)q] += mxk - have; have = mxk; }
                     }
                     ob.rowsSelf[(size_t)q] += addSelf[(size_t)q];
-                    ob.slotsE[(size_t)q] += rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e];
+                    ob.slotsE[(size_t)q] += lanesOf(pp, e);
                 }
                 ob.rowStates += padAdd;
+                if (ob.ids.empty()) ob.cls = clsOf(i);
                 ob.ids.push_back(i);
                 return true;
             };
@@ -836,15 +884,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             // mode: non-zero branches) are therefore binned together; inside a class the lexicographic order keeps
             // patterns that share trajectory keys next to each other.
             std::vector<int> ord(order);
-            if (nE == 1 && binSort) {
-                auto cls = [&](int i) {
-                    const PatPlan& pp = pps[(size_t)i];
-                    if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
-                    int c = 0;
-                    for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
-                    return c;
-                };
-                std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return cls(a) > cls(b); });
+            if (nE == 1 && (binSort || patMode)) {
+                std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return clsOf(a) > clsOf(b); });
             }
             for (int i : ord) {
                 bool placed = false;
@@ -904,7 +945,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // (1) bins spanning all epochs (self-contained fast kernel)
         out.fBinPatOff.assign(1, 0);
         out.fBinPats.clear();
-        pack_range(0, nEpochs - 1, maxPatFast, false, out.fBinPatOff, out.fBinPats);
+        pack_range(0, nEpochs - 1, maxPatFast, 0, out.fBinPatOff, out.fBinPats);
         out.nFastBins = (int)out.fBinPatOff.size() - 1;
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         out.kBinBase.assign((size_t)nEpochs, 0);
@@ -931,6 +972,12 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             int maxNO = 0;
             for (int i : order) maxNO = std::max(maxNO, (int)pps[(size_t)i].rowNO[(size_t)e]);
             out.epochMode[(size_t)e] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
+            // pattern mode: at most two non-zero branches everywhere and few enough states to keep a whole pattern in the
+            // registers of one thread
+            static const bool patEnv = std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true;
+            bool pat = all && patEnv && maxNO <= 1;
+            for (int i : order) pat = pat && pps[(size_t)i].live[(size_t)e] <= RC_PAT_MAXS;
+            if (pat) { use = true; out.epochMode[(size_t)e] = 3; }
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
             if (use) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
@@ -957,8 +1004,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         for (int e = 0; e < nEpochs; ++e) {
             out.kBinBase[(size_t)e] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
-            if (out.epochMode[(size_t)e]) pack_range(e, e, RC_NPBR, true, out.kBinPatOff, out.kBinPats);
-            else pack_range(e, e, RC_NPB, false, out.kBinPatOff, out.kBinPats);
+            if (out.epochMode[(size_t)e] == 3) pack_range(e, e, RC_PBLOCK, 3, out.kBinPatOff, out.kBinPats);
+            else if (out.epochMode[(size_t)e]) pack_range(e, e, RC_NPBR, 1, out.kBinPatOff, out.kBinPats);
+            else pack_range(e, e, RC_NPB, 0, out.kBinPatOff, out.kBinPats);
             out.nKBins[(size_t)e] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)e];
         }
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
@@ -976,7 +1024,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 int b0 = out.kBinBase[(size_t)e], nb = out.nKBins[(size_t)e];
                 int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
                 std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s bins %d fetch rows/bin %.1f\n", e,
-                             E.nKeys, E.nThr, E.rowPairs, out.epochMode[(size_t)e] ? "rows" : "states", nb, nb ? (double)(f1 - f0) / nb : 0.0);
+                             E.nKeys, E.nThr, E.rowPairs, out.epochMode[(size_t)e] == 3 ? "patterns" : out.epochMode[(size_t)e] ? "rows" : "states", nb, nb ? (double)(f1 - f0) / nb : 0.0);
             }
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
         }
@@ -1109,12 +1157,12 @@ std::string check_plan(const PlanHost& h) {
         std::vector<char> seen;
         for (int e = 0; e < nE; ++e) {
             const PlanHost::Epoch& E = h.ep[(size_t)e];
-            const bool rows = h.epochMode[(size_t)e] != 0;
+            const bool rows = h.epochMode[(size_t)e] != 0, patM = h.epochMode[(size_t)e] == 3;
             seen.assign((size_t)nPat, 0);
             const int b0 = h.kBinBase[(size_t)e];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
                 const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
-                if (p1 - p0 < 1 || p1 - p0 > (rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
+                if (p1 - p0 < 1 || p1 - p0 > (patM ? RC_PBLOCK : rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
                 const int f0 = h.kFetchOff[(size_t)bI], f1 = h.kFetchOff[(size_t)bI + 1];
                 if (f1 - f0 < 1 || f1 - f0 > RC_KROWS - 1) return fail("pair rows per keyed bin");
                 for (int q = f0; q < f1; ++q)
@@ -1136,8 +1184,8 @@ std::string check_plan(const PlanHost& h) {
                         const int M = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
                         const int nr = h.rowOff[(size_t)e * (nPat + 1) + i + 1] - h.rowOff[(size_t)e * (nPat + 1) + i];
                         if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || rk >= P || nr * M != live) return fail("row shape");
-                        lanes += nr;
-                        padded += (long long)nr * (M | 1);
+                        lanes += patM ? 1 : nr;
+                        padded += patM ? 0 : (long long)nr * (M | 1);
                         for (int r = 0; r < nr; ++r) {
                             const long long gr = h.rowEpochBase[(size_t)e] + h.rowOff[(size_t)e * (nPat + 1) + i] + r;
                             for (int j = 0; j < M; ++j)
@@ -1169,14 +1217,15 @@ std::string check_plan(const PlanHost& h) {
             return (long long)r0 >= lo && (long long)r0 + cnt <= hi && prev < h.epochSlots[(size_t)e - 1];
         };
         for (int e = 0; e < nE; ++e) {
-            const bool rows = h.epochMode[(size_t)e] != 0;
+            const bool rows = h.epochMode[(size_t)e] != 0, patM = h.epochMode[(size_t)e] == 3;
             const int b0 = h.kBinBase[(size_t)e];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
                 const int np = hdr[1], lanes = hdr[2], nB = hdr[3], nFetch = hdr[5];
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
-                if (lanes < 1 || lanes > RC_BLOCK || nB < 0 || nB > RC_ROW_BCAP) return fail("image header lanes");
+                if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * RC_PAT_MAXS : RC_ROW_BCAP))
+                    return fail("image header lanes");
                 if (hdr[6] < 0 || hdr[6] + (long long)lanes * (rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)
                     return fail("image record range");
                 for (int q = 0; q < np; ++q) {
@@ -1186,7 +1235,22 @@ std::string check_plan(const PlanHost& h) {
                 }
                 for (int t = 0; t < lanes; ++t) {
                     const uint32_t* r = &h.kLane[(size_t)hdr[6] * 4 + (size_t)t * (rows ? RC_RLANE_N : RC_LANE_N)];
-                    if (!rows) {
+                    if (patM) {
+                        const int rowA = (int)(r[0] & 0xFFu), rowB = (int)((r[0] >> 8) & 0xFFu), MA = (int)((r[0] >> 16) & 0xFFu), MB = (int)(r[0] >> 24);
+                        const int n = MA * (MB ? MB : 1);
+                        if (MA < 1 || MA > RC_ROW_MAXM || n > RC_PAT_MAXS) return fail("image pattern shape");
+                        if (rowA < 1 || rowA + MA - 1 >= nFetch) return fail("image pattern pair rows (A)");
+                        if (MB ? (rowB < 1 || rowB + MB - 1 >= nFetch) : rowB != RC_KROWS - 1) return fail("image pattern pair rows (B)");
+                        if ((int)r[3] >= nPat || (long long)r[1] + n > h.epochSlots[(size_t)e] || (int)r[2] + n > nB) return fail("image pattern hand-over");
+                        const int live = h.slotOff[(size_t)e * (nPat + 1) + r[3] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[3]];
+                        if (live != n || (int)r[1] != h.slotOff[(size_t)e * (nPat + 1) + r[3]]) return fail("image pattern states");
+                        std::vector<char> hit((size_t)n, 0);
+                        for (int q = 0; q < n; ++q) {
+                            const int ref = (int)((r[4 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
+                            if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
+                            hit[(size_t)ref] = 1;
+                        }
+                    } else if (!rows) {
                         for (int d = 0; d < 8; ++d) {
                             const int row = (int)((r[d >> 2] >> (8 * (d & 3))) & 0xFFu), up = (int)((r[2 + (d >> 2)] >> (8 * (d & 3))) & 0xFFu);
                             if (row != RC_KROWS - 1 && (row < 1 || row >= nFetch)) return fail("image pair row");

@@ -16,6 +16,8 @@
 #define RC_EV_SPLIT_D 1
 // row mode of the keyed tier: one thread per row of states along the widest branch of a box-shaped live set
 #define RC_ROW_NO 7          // other non-zero branches of a row at most
+#define RC_PBLOCK 64         // pattern mode: threads (= patterns) per block
+#define RC_PAT_MAXS 25       // pattern mode: live states of a pattern at most (all in the registers of one thread)
 #define RC_ROW_SUM 11        // with more than 3 other branches: other branches + row length <= RC_ROW_SUM (bounds the kernel variants)
 #define RC_ROW_MAXM 10       // longest row
 #define RC_ROW_BCAP 1536     // states per row-mode block at most (rows are stored with an odd stride: no bank conflicts)
@@ -95,7 +97,7 @@ struct RcPlanDev {
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
     // ---- row mode ----
-    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches
+    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; 3: one pattern per thread
     const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
     const long long* rowEpochBase; // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states
