@@ -646,10 +646,14 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
-                    CK(rc_launch_propagate_keyed(pe->d, e, pe->h.nKBins[(size_t)e], pe->h.epochMode[(size_t)e], dM, dMep, dSev, (const double*)ctx->dKTab.p,
-                                                 (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0, carrySlots,
-                                                 (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
-                    ++launches;
+                    // two bin groups per epoch: patterns small enough for one thread each, and the rest (rows or states)
+                    for (int v = 2 * e; v < 2 * e + 2; ++v) {
+                        if (pe->h.nKBins[(size_t)v] == 0) continue;
+                        CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], dM, dMep, dSev,
+                                                     (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
+                                                     carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
+                        ++launches;
+                    }
                 }
             }
             if (pe->d.nFastBins > 0 && anySelf) {
@@ -1117,7 +1121,7 @@ int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int
     if (mh.status != RC_OK) return mh.status;
     rc::PlanHost h;
     std::string e = rc::build_plan(P, maxAf, nPat, patterns, nVec, mh.sev, mh.gaps, mh.hasSplit, 227 * 1024, h);
-    if (!e.empty()) return RC_ERR_UNSUPPORTED;
+    if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
     e = rc::check_plan(h);
     if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
     if (stateSteps) *stateSteps = count_state_steps(mh, h, T);

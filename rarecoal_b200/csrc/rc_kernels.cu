@@ -1054,7 +1054,7 @@ __device__ __forceinline__ int rc_key_run(RcKeyRegs<NNZ>& R, const unsigned sBas
 // The last epoch also does the shortcut (Core.hs:80-118) and the getProb epilogue (Core.hs:49-54).
 template <int NNZ>
 __global__ void __launch_bounds__(RC_BLOCK, RC_KEYED_MINB)
-rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
+rc_propagate_keyed_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __restrict__ models,
                           const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
                           const double* __restrict__ ktab, const double* __restrict__ aShort,
                           const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
@@ -1068,7 +1068,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mo
     const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
-    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / lane records -> transition entries
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
@@ -1397,7 +1397,7 @@ __device__ __forceinline__ int rc_row_dispatch_m(RcRowRegs<NOCAP>& R, const unsi
 // NOCAP = 3 for epochs whose rows all have at most 3 other branches (fewer registers, smaller code), else RC_ROW_NO
 template <int NOCAP>
 __global__ void __launch_bounds__(RC_BLOCK, RC_ROWS_MINB)
-rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models,
+rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __restrict__ models,
                          const RcModelEpochDev* __restrict__ mep, const RcSEvDev* __restrict__ sevs,
                          const double* __restrict__ ktab, const double* __restrict__ aShort,
                          const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
@@ -1411,7 +1411,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
     const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
-    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / row / element records -> transition entries
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
@@ -1646,13 +1646,14 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mod
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pattern mode of the keyed tier (epochs in which every pattern has at most two non-zero branches A, B and at most
-// RC_PAT_MAXS live states — the last epochs of a tree model): one thread owns a whole pattern.  b(x_A, x_B) lives in
-// registers, so both neighbours of a state are registers too and shared memory only carries the {G,E2} pairs:
-//     b'(i,j) = b(i,j) G_A(i) G_B(j) + b(i+1,j) E2_A(i) + b(i,j+1) E2_B(j)                        (Core.hs:259)
-// with MA + MB pair loads per pattern and step instead of one per state and branch.  Blocks are small (RC_PBLOCK threads,
-// several resident per SM) and hold patterns of one shape (MA, MB) only (rc_plan.cpp), so the update is fully unrolled
-// without predicates; every thread fetches up to four pair rows per grid step into the ring.
+// Pattern mode of the keyed tier: one thread owns a whole pattern whose live set is a box of at most RC_PAT_MAXS states —
+// the row branch A, up to three more branches with m >= 2 (B, C, D; the shape is a template parameter) and any number of
+// branches with m = 1, which only contribute a decay factor.  b lives in registers, so every neighbour of a state is a
+// register too and shared memory only carries the {G,E2} pairs:
+//     b'(x) = b(x) prod_k G_k(x_k) + sum_{k in A..D} b(x + e_k) E2_k(x_k)                          (Core.hs:259)
+// with sum_k m_k pair loads per pattern and step instead of one per state and branch.  Blocks are small (RC_PBLOCK threads,
+// several resident per SM) and hold patterns of one shape only (rc_plan.cpp), so the update is fully unrolled without
+// predicates; every thread fetches up to four pair rows per grid step into the ring.
 #define RC_PDEPTH 4
 #define RC_PFETCH (RC_KROWS / RC_PBLOCK)
 struct RcPatSmem {
@@ -1663,19 +1664,27 @@ static_assert(offsetof(RcPatSmem, RE) % 16 == 0, "16-byte alignment of the pair 
 
 struct RcPatRegs {
     double b[RC_PAT_MAXS];
-    unsigned aA, aB;              // pair of (A, x = 1) / (B, x = 1) in ring slot 0
+    unsigned rowsW[2];            // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
+    int nU;                       // number of m = 1 branches
     bool on, unit;
     double dacc;
     const double* fp[RC_PFETCH];  // this thread's pairs in the step row to be copied next
     unsigned fmask;               // bit q: the thread fetches pair row q * RC_PBLOCK + tid
 };
 
-template <int MA, int MB>
+__device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs& R, int q) { return (R.rowsW[q >> 2] >> (8 * (q & 3))) & 0xFFu; }
+
+template <int MA, int MB, int MC, int MD>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                            unsigned& slot) {
     constexpr unsigned RE_SLOT = RC_KROWS * 16u;
-    constexpr int MBp = MB ? MB : 1;
+    constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1;
+    constexpr int SA = MBp * MCp * MDp, SB = MCp * MDp, SC = MDp;
+    constexpr int NS = (MB ? 1 : 0) + (MC ? 1 : 0) + (MD ? 1 : 0);
+    static_assert(MA * SA <= RC_PAT_MAXS, "shape");
     const unsigned myRE = sBase + threadIdx.x * 16u;
+    const unsigned aA = sBase + rc_pat_row(R, 0) * 16u, aB = sBase + rc_pat_row(R, 1) * 16u, aC = sBase + rc_pat_row(R, 2) * 16u,
+                   aD = sBase + rc_pat_row(R, 3) * 16u;
     for (; s < nextStop; ++s) {
         const unsigned prev = slot == 0 ? (RC_PDEPTH - 1) * RE_SLOT : slot - RE_SLOT;      // slot of step s - 1: free again
 #pragma unroll
@@ -1685,25 +1694,48 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
         }
         rc_cp_commit();
         if (R.on) {
-            double gB[MBp], eB[MBp];
+            double gB[MBp], eB[MBp], gC[MCp], eC[MCp], gD[MDp], eD[MDp];
             if (MB) {
 #pragma unroll
-                for (int j = 0; j < MBp; ++j) rc_lds128(R.aB + slot + (unsigned)j * 16u, gB[j], eB[j]);
+                for (int j = 0; j < MBp; ++j) rc_lds128(aB + slot + (unsigned)j * 16u, gB[j], eB[j]);
             }
+            if (MC) {
+#pragma unroll
+                for (int j = 0; j < MCp; ++j) rc_lds128(aC + slot + (unsigned)j * 16u, gC[j], eC[j]);
+            }
+            if (MD) {
+#pragma unroll
+                for (int j = 0; j < MDp; ++j) rc_lds128(aD + slot + (unsigned)j * 16u, gD[j], eD[j]);
+            }
+            double D1 = 1.0;                     // branches with m = 1: G_k(1) only
+#pragma unroll
+            for (int u = 0; u < 8 - 1 - NS; ++u)
+                if (u < R.nU) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
                 double gA, eA;
-                rc_lds128(R.aA + slot + (unsigned)i * 16u, gA, eA);
+                rc_lds128(aA + slot + (unsigned)i * 16u, gA, eA);
+                const double dA = D1 * gA;
 #pragma unroll
                 for (int j = 0; j < MBp; ++j) {
-                    const int x = i * MBp + j;
-                    double t2 = (i + 1 < MA) ? R.b[x + MBp] * eA : 0.0;          // old values: not yet overwritten
-                    if (MB && j + 1 < MB) t2 = fma(R.b[x + 1], eB[j], t2);
-                    const double D = MB ? gA * gB[j] : gA;
-                    R.b[x] = fma(R.b[x], D, t2);                                 // updateB, Core.hs:259
+                    const double dB = MB ? dA * gB[j] : dA;
+#pragma unroll
+                    for (int k = 0; k < MCp; ++k) {
+                        const double dC = MC ? dB * gC[k] : dB;
+#pragma unroll
+                        for (int l = 0; l < MDp; ++l) {
+                            const double dD = MD ? dC * gD[l] : dC;
+                            const int x = i * SA + j * SB + k * SC + l;
+                            double t2 = (i + 1 < MA) ? R.b[x + SA] * eA : 0.0;      // old values: not yet overwritten
+                            if (MB && j + 1 < MB) t2 = fma(R.b[x + SB], eB[j], t2);
+                            if (MC && k + 1 < MC) t2 = fma(R.b[x + SC], eC[k], t2);
+                            if (MD && l + 1 < MD) t2 = fma(R.b[x + 1], eD[l], t2);
+                            R.b[x] = fma(R.b[x], dD, t2);                           // updateB, Core.hs:259
+                        }
+                    }
                 }
             }
-            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);    // updateD, Core.hs:282-288
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);       // updateD, Core.hs:282-288
         }
         rc_cp_wait<RC_PDEPTH - 2>();
         __syncthreads();
@@ -1711,13 +1743,14 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
     }
 }
 
-// (MA, MB) shapes the planner admits: MB <= MA <= RC_ROW_MAXM and MA * max(MB, 1) <= RC_PAT_MAXS
-template <int MB>
+// shapes the planner admits (pat_shape in rc_plan.cpp): MA >= MB >= MC >= MD, each of B, C, D absent (0) or >= 2, product of
+// the present ones <= RC_PAT_MAXS
+template <int MB, int MC, int MD>
 __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                                   unsigned& slot, const int MA) {
-    constexpr int MBp = MB ? MB : 1;
+    constexpr int SA = (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
 #define RC_PAT_CASE(A) \
-    case A: if constexpr (A >= MBp && A * MBp <= RC_PAT_MAXS) { rc_pat_run<A, MB>(R, sBase, strideD, s, nextStop, slot); } break;
+    case A: if constexpr (A >= MB && A * SA <= RC_PAT_MAXS) { rc_pat_run<A, MB, MC, MD>(R, sBase, strideD, s, nextStop, slot); } break;
     switch (MA) {
         RC_PAT_CASE(1) RC_PAT_CASE(2) RC_PAT_CASE(3) RC_PAT_CASE(4) RC_PAT_CASE(5)
         RC_PAT_CASE(6) RC_PAT_CASE(7) RC_PAT_CASE(8) RC_PAT_CASE(9) RC_PAT_CASE(10)
@@ -1728,7 +1761,7 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned s
 }
 
 __global__ void __launch_bounds__(RC_PBLOCK, 8)
-rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                         const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
                         long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
@@ -1740,7 +1773,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mode
     const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
-    const int binIdx = pl.kBinBase[e] + (int)blockIdx.x;
+    const int binIdx = binBase + (int)blockIdx.x;
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
     const int np = hdrA.y, nB = hdrA.w;
@@ -1806,25 +1839,28 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mode
             S.bb[i] = v;
         }
     }
-    const int MA = (int)((la.x >> 16) & 0xFFu), MB = (int)(la.x >> 24), n = MA * (MB ? MB : 1);
-    const int pid = (int)la.w;
+    const unsigned shape = la.z & 0xFFFFu;          // MA | MB << 4 | MC << 8 | MD << 12
+    const int MA = (int)(shape & 0xFu), MB = (int)((shape >> 4) & 0xFu), MC = (int)((shape >> 8) & 0xFu), MD = (int)((shape >> 12) & 0xFu);
+    const int n = MA * (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
+    const int pid = (int)lb.x;
     double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
-    R.aA = sBase + (la.x & 0xFFu) * 16u;
-    R.aB = sBase + ((la.x >> 8) & 0xFFu) * 16u;
-    R.unit = R.on && MB == 0;                       // x = e_A is the first state of a single-branch pattern
+    R.rowsW[0] = la.x;
+    R.rowsW[1] = la.y;
+    R.nU = (int)((la.z >> 16) & 0xFu);
+    R.unit = R.on && MB == 0 && R.nU == 0;          // x = e_A is the first state of a single-branch pattern
     __syncthreads();
     if (R.on) {
-        const double* mine = S.bb + la.z;
+        const double* mine = S.bb + (la.z >> 20);
 #pragma unroll
         for (int x = 0; x < RC_PAT_MAXS; ++x)
             if (x < n) R.b[x] = mine[x];
     }
     // the block's shape: bins hold one (MA, MB) class
-    const int MAb = __shfl_sync(0xFFFFFFFFu, MA, 0), MBb = __shfl_sync(0xFFFFFFFFu, MB, 0);
-    __shared__ int shape[2];
-    if (tid == 0) { shape[0] = MAb; shape[1] = MBb; }
+    __shared__ unsigned shapeS;
+    if (tid == 0) shapeS = shape;
     __syncthreads();
-    const int MAw = shape[0], MBw = shape[1];
+    const unsigned shapeB = shapeS;
+    const int MAw = (int)(shapeB & 0xFu);
 
     bool finished = false, parked = false;
     for (int phase = 0; phase < 2 && !finished; ++phase) {
@@ -1838,15 +1874,18 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mode
             ringStarted = false;
             rc_cp_wait<RC_PDEPTH - 2>();
             __syncthreads();
-            switch (MBw) {
-                case 0: rc_pat_dispatch_a<0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 1: rc_pat_dispatch_a<1>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 2: rc_pat_dispatch_a<2>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 3: rc_pat_dispatch_a<3>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 4: rc_pat_dispatch_a<4>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                default: rc_pat_dispatch_a<5>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+            switch (shapeB >> 4) {          // MB | MC << 4 | MD << 8
+                case 0x000: rc_pat_dispatch_a<0, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x002: rc_pat_dispatch_a<2, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x003: rc_pat_dispatch_a<3, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x004: rc_pat_dispatch_a<4, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x005: rc_pat_dispatch_a<5, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x022: rc_pat_dispatch_a<2, 2, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x023: rc_pat_dispatch_a<3, 2, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x222: rc_pat_dispatch_a<2, 2, 2>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                default: break;             // no other shape has a product <= RC_PAT_MAXS
             }
-            static_assert(RC_PAT_MAXS == 25, "MB <= 5 above");
+            static_assert(RC_PAT_MAXS == 25, "shape list above");
             rc_cp_wait<0>();
             __syncthreads();
         }
@@ -1888,8 +1927,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ mode
     if (tid >= np) return;
     if (!isLast) {
         // ---- hand b and the updateD sums to the next epoch's launch ----
-        double* out = bCur + (size_t)b * bStride + la.y;
-        const unsigned refW[7] = {lb.x, lb.y, lb.z, lb.w, lc.x, lc.y, lc.z};
+        double* out = bCur + (size_t)b * bStride + la.w;
+        const unsigned refW[7] = {lb.y, lb.z, lb.w, lc.x, lc.y, lc.z, lc.w};
 #pragma unroll
         for (int x = 0; x < RC_PAT_MAXS; ++x)
             if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
@@ -2017,7 +2056,7 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
     return cudaGetLastError();
 }
 
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int rowMode, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
@@ -2037,7 +2076,7 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int
             if (err != cudaSuccess) return err;
             cp = true;
         }
-        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return cudaGetLastError();
     }
     if (rowMode) {
@@ -2049,14 +2088,14 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int
                 if (err != cudaSuccess) return err;
                 cr3 = true;
             }
-            rc_propagate_rows_kernel<3><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+            rc_propagate_rows_kernel<3><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         } else {
             if (!cr7) {
                 cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel<RC_ROW_NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
                 if (err != cudaSuccess) return err;
                 cr7 = true;
             }
-            rc_propagate_rows_kernel<RC_ROW_NO><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+            rc_propagate_rows_kernel<RC_ROW_NO><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         }
         return cudaGetLastError();
     }
@@ -2066,14 +2105,14 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int nBins, int
             if (err != cudaSuccess) return err;
             c4 = true;
         }
-        rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     } else {
         if (!c8) {
             cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return err;
             c8 = true;
         }
-        rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, e, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     }
     return cudaGetLastError();
 }

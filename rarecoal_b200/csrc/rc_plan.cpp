@@ -164,6 +164,7 @@ struct PatPlan {
     std::vector<uint8_t> mx;        // per epoch: P bytes, largest x_k over the live states
     // row view of a box-shaped live set (one thread per row along the widest branch), per epoch
     std::vector<uint8_t> rowOK, rowM, rowK, rowNO;   // usable / row length / row branch / other non-zero branches
+    std::vector<uint8_t> fullBox;                    // per epoch: the live set is exactly prod_k {1..mx_k} (every state has every live branch)
     std::vector<int> rowStride, rowCnt;              // reference-order stride of the row branch / number of rows
     std::vector<uint32_t> rowWords;                  // per row RC_ROW_NO words (k | x<<8 | neighbour row<<16)
     std::vector<uint16_t> rowRef;                    // per row: reference-order index of its x_r = 1 state
@@ -304,6 +305,11 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
         pp.rowRef.resize(rowStart);
         pp.rowWords.resize(rowStart * RC_ROW_NO);
     }
+    bool full = box == (long long)L.size();
+    for (size_t i = 0; i < L.size() && full; ++i)
+        for (int k = 0; k < c.P && full; ++k)
+            if (pp.mx[m0 + (size_t)k] && !L[i].x[k]) full = false;
+    pp.fullBox.push_back(full ? 1 : 0);
     pp.rowOK.push_back(ok ? 1 : 0);
     pp.rowM.push_back((uint8_t)(ok ? rm : 0));
     pp.rowK.push_back((uint8_t)(ok ? rk : 0));
@@ -438,6 +444,36 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
 
 }  // namespace
 
+// Pattern mode: shape of a box-shaped live set whose states all fit the registers of one thread.  A = the row branch (the
+// widest), then up to three more branches with m >= 2 in descending order (B, C, D); every other non-zero branch has
+// m = 1 and only contributes a decay factor.  Returns MA | MB << 4 | MC << 8 | MD << 12, or 0 if the pattern does not
+// qualify; dims (optional) receives the branch ids in the kernel's order: A, B.., then the m = 1 branches.
+static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int* dims = nullptr, int* nShaped = nullptr, int* nUnit = nullptr) {
+    const int MA = mx[rk];
+    if (MA < 1 || MA > RC_ROW_MAXM) return 0;
+    int sh[3] = {0, 0, 0}, shK[3] = {0, 0, 0}, nS = 0, nU = 0, un[RC_MAX_P];
+    for (int k = 0; k < P; ++k) {
+        if (k == rk || !mx[k]) continue;
+        if (mx[k] == 1) { un[nU++] = k; continue; }
+        if (nS == 3) return 0;
+        int q = nS++;
+        while (q > 0 && sh[q - 1] < mx[k]) { sh[q] = sh[q - 1]; shK[q] = shK[q - 1]; --q; }     // descending, stable in k
+        sh[q] = mx[k];
+        shK[q] = k;
+    }
+    long long prod = MA;
+    for (int q = 0; q < nS; ++q) prod *= sh[q];
+    if (prod > RC_PAT_MAXS || 1 + nS + nU > 8 || (nS && sh[0] > MA)) return 0;
+    if (dims) {
+        dims[0] = rk;
+        for (int q = 0; q < nS; ++q) dims[1 + q] = shK[q];
+        for (int q = 0; q < nU; ++q) dims[1 + nS + q] = un[q];
+    }
+    if (nShaped) *nShaped = nS;
+    if (nUnit) *nUnit = nU;
+    return (uint32_t)MA | ((uint32_t)sh[0] << 4) | ((uint32_t)sh[1] << 8) | ((uint32_t)sh[2] << 12);
+}
+
 // Bin images of the keyed tier (record layouts in rc_types.h).  Everything the set-up of a block used to look up through
 // pattern ids, slot offsets, packed words and transition offsets is resolved here once, in the order the lanes of the
 // block consume it: the block reads its header, every lane one 32-byte record, and the gather goes straight to the
@@ -467,12 +503,13 @@ static std::string build_bin_images(PlanHost& out) {
         r1 = (uint32_t)out.slotOff[(size_t)(e - 1) * (nPat + 1) + i] | ((uint32_t)(b - a) << RC_IMG_CNT_SHIFT);
         return true;
     };
-    for (int e = 0; e < nE; ++e) {
-        const bool rows = out.epochMode[(size_t)e] != 0, patM = out.epochMode[(size_t)e] == 3;
+    for (int v = 0; v < nE * 2; ++v) {
+        const int e = v / 2;
+        const bool rows = out.epochMode[(size_t)v] != 0, patM = out.epochMode[(size_t)v] == 3;
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
-        const int b0 = out.kBinBase[(size_t)e];
-        for (int bI = b0; bI < b0 + out.nKBins[(size_t)e]; ++bI) {
+        const int b0 = out.kBinBase[(size_t)v];
+        for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
             const int p0 = out.kBinPatOff[(size_t)bI], p1 = out.kBinPatOff[(size_t)bI + 1];
             if (out.kLane.size() / 4 > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
             int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
@@ -490,36 +527,45 @@ static std::string build_bin_images(PlanHost& out) {
                 out.kPatRec[(size_t)q * 2] = i;
                 out.kPatRec[(size_t)q * 2 + 1] = lanes | (bOff << 16);
                 if (patM) {
-                    // pattern mode: one lane per pattern; state (x_A = i + 1, x_B = j + 1) sits at position i * max(MB, 1) + j
+                    // pattern mode: one lane per pattern; state (x_A, x_B, x_C, x_D) sits at the mixed-radix position
+                    // (((x_A - 1) MB' + x_B - 1) MC' + x_C - 1) MD' + x_D - 1 with M' = max(M, 1)
                     const uint32_t pr = out.patRow[(size_t)e * nPat + i];
-                    const int MA = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
-                    const int nr = ro[i + 1] - ro[i], MB = NO ? nr : 0, MBp = NO ? nr : 1;
-                    if (NO > 1 || MA * MBp != live || live > RC_PAT_MAXS) return "pattern-mode bin with an unsuitable pattern";
+                    const int rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
+                    int dims[8], nS = 0, nU = 0;
+                    const uint32_t shape = pat_shape(&out.maxX[((size_t)e * nPat + i) * P], P, rk, dims, &nS, &nU);
+                    if (!shape) return "pattern-mode bin with an unsuitable pattern";
+                    const int MA = (int)(shape & 0xFu);
+                    const int Mp[3] = {std::max(1, (int)((shape >> 4) & 0xFu)), std::max(1, (int)((shape >> 8) & 0xFu)), std::max(1, (int)((shape >> 12) & 0xFu))};
+                    const int SA = Mp[0] * Mp[1] * Mp[2], nr = ro[i + 1] - ro[i];
+                    if (MA * SA != live || nr != SA || NO != nS + nU) return "pattern-mode image: shape does not match the live set";
                     uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    uint32_t rowB = RC_KROWS - 1;
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t row = q < 1 + nS + nU ? (uint32_t)rb[dims[q]] : (uint32_t)(RC_KROWS - 1);
+                        if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
+                        rec[q >> 2] |= row << (8 * (q & 3));
+                    }
                     std::vector<uint32_t> el((size_t)live * 2, 0u);
                     for (int r = 0; r < nr; ++r) {
                         const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
-                        int j = 0;
-                        if (NO) {
-                            const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO];
+                        int xs[3] = {1, 1, 1};
+                        for (int d = 0; d < NO; ++d) {
+                            const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
                             const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
-                            rowB = rb[k];
-                            j = x - 1;
-                            if (j < 0 || j >= MB) return "pattern-mode image out of range";
+                            for (int q = 0; q < nS; ++q) if (dims[1 + q] == k) xs[q] = x;
                         }
+                        const int other = ((xs[0] - 1) * Mp[1] + (xs[1] - 1)) * Mp[2] + (xs[2] - 1);
+                        if (other < 0 || other >= SA) return "pattern-mode image out of range (other index)";
                         for (int a = 0; a < MA; ++a) {
-                            const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + a], idx = a * MBp + j;
-                            if (ref > 0xFF) return "pattern-mode image out of range";
-                            rec[4 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
+                            const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + a], idx = a * SA + other;
+                            if (ref > 0xFF) return "pattern-mode image out of range (state index)";
+                            rec[5 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
                             if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
                         }
                     }
-                    if (rb[rk] > 0xFFu || rowB > 0xFFu) return "pattern-mode image out of range";
-                    rec[0] = (uint32_t)rb[rk] | (rowB << 8) | ((uint32_t)MA << 16) | ((uint32_t)MB << 24);
-                    rec[1] = (uint32_t)so[i];
-                    rec[2] = (uint32_t)bOff;
-                    rec[3] = (uint32_t)i;
+                    if (bOff >= (1 << 12)) return "pattern-mode image out of range (element offset)";
+                    rec[2] = shape | ((uint32_t)nU << 16) | ((uint32_t)bOff << 20);
+                    rec[3] = (uint32_t)so[i];
+                    rec[4] = (uint32_t)i;
                     out.kLane.insert(out.kLane.end(), rec, rec + RC_RLANE_N);
                     out.kElem.insert(out.kElem.end(), el.begin(), el.end());
                     lanes += 1;
@@ -803,13 +849,14 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // measured on C3 (44 models): 36.7 ms with lexicographic bins, 33.4 ms with cost-class bins; RC_BINSORT=0 restores the former
         const bool binSort = std::getenv("RC_BINSORT") ? std::atoi(std::getenv("RC_BINSORT")) != 0 : true;
         // mode: 0 one state per lane, 1 one row per lane, 3 one pattern per lane (bins of one cost class only)
-        auto pack_range = [&](int e0, int e1, int maxPats, int mode, std::vector<int>& patOff, std::vector<int>& pats) {
+        auto pack_range = [&](int e0, int e1, int maxPats, int mode, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
             const bool rowMode = mode != 0, patMode = mode == 3;
             auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
             auto clsOf = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
-                if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0] + (patMode ? 1024 * pp.rowCnt[(size_t)e0] : 0);
+                if (patMode) return (int)pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0]);
+                if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
                 int c = 0;
                 for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
                 return c;
@@ -883,7 +930,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             // the pace of its widest lane.  Patterns of equal cost class (row mode: other branches, row length; state
             // mode: non-zero branches) are therefore binned together; inside a class the lexicographic order keeps
             // patterns that share trajectory keys next to each other.
-            std::vector<int> ord(order);
+            std::vector<int> ord(ids);
             if (nE == 1 && (binSort || patMode)) {
                 std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return clsOf(a) > clsOf(b); });
             }
@@ -945,44 +992,46 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // (1) bins spanning all epochs (self-contained fast kernel)
         out.fBinPatOff.assign(1, 0);
         out.fBinPats.clear();
-        pack_range(0, nEpochs - 1, maxPatFast, 0, out.fBinPatOff, out.fBinPats);
+        pack_range(0, nEpochs - 1, maxPatFast, 0, order, out.fBinPatOff, out.fBinPats);
         out.nFastBins = (int)out.fBinPatOff.size() - 1;
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
-        out.kBinBase.assign((size_t)nEpochs, 0);
-        out.nKBins.assign((size_t)nEpochs, 0);
-        // row mode per epoch: every fast-tier pattern is a box with at most RC_ROW_NO + 1 non-zero branches and the rows are
-        // long enough to pay for the per-row overhead
-        out.epochMode.assign((size_t)nEpochs, 0);
+        // Two bin groups per epoch (index 2e + g): g = 0 the patterns small enough for one thread each (pattern mode), g = 1
+        // the rest in row mode (all boxes with rows long enough) or state mode.
+        out.kBinBase.assign((size_t)nEpochs * 2, 0);
+        out.nKBins.assign((size_t)nEpochs * 2, 0);
+        out.epochMode.assign((size_t)nEpochs * 2, 0);
         out.rowOff.assign((size_t)nEpochs * (nPat + 1), 0);
         out.rowEpochBase.assign((size_t)nEpochs, 0);
         out.patRow.assign((size_t)nEpochs * nPat, 0u);
         out.patRowStride.assign((size_t)nEpochs * nPat, 0);
         const char* rowEnv = std::getenv("RC_ROWMODE");
+        static const bool patEnv = std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true;
+        std::vector<std::vector<int>> groupIds((size_t)nEpochs * 2);
         for (int e = 0; e < nEpochs; ++e) {
-            bool all = !order.empty();
-            long long rows = 0, states = 0;
+            std::vector<int>& patIds = groupIds[(size_t)e * 2];
+            std::vector<int>& restIds = groupIds[(size_t)e * 2 + 1];
             for (int i : order) {
+                const bool small = patEnv && pps[(size_t)i].rowOK[(size_t)e] && pps[(size_t)i].fullBox[(size_t)e] && pat_shape(&pps[(size_t)i].mx[(size_t)e * P], P, pps[(size_t)i].rowK[(size_t)e]) != 0;
+                (small ? patIds : restIds).push_back(i);
+            }
+            bool all = !restIds.empty();
+            long long rows = 0, states = 0;
+            int maxNO = 0;
+            for (int i : restIds) {
                 all = all && pps[(size_t)i].rowOK[(size_t)e];
                 rows += pps[(size_t)i].rowCnt[(size_t)e];
                 states += pps[(size_t)i].live[(size_t)e];
+                maxNO = std::max(maxNO, (int)pps[(size_t)i].rowNO[(size_t)e]);
             }
             static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
             bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
             if (rowEnv) use = all && std::atoi(rowEnv) != 0;
-            int maxNO = 0;
-            for (int i : order) maxNO = std::max(maxNO, (int)pps[(size_t)i].rowNO[(size_t)e]);
-            out.epochMode[(size_t)e] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
-            // pattern mode: at most two non-zero branches everywhere and few enough states to keep a whole pattern in the
-            // registers of one thread
-            static const bool patEnv = std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true;
-            bool pat = all && patEnv && maxNO <= 1;
-            for (int i : order) pat = pat && pps[(size_t)i].live[(size_t)e] <= RC_PAT_MAXS;
-            if (pat) { use = true; out.epochMode[(size_t)e] = 3; }
+            out.epochMode[(size_t)e * 2] = 3;
+            out.epochMode[(size_t)e * 2 + 1] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
-            if (use) {
+            if (use || !patIds.empty()) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
                 long long run = 0;
-                std::vector<size_t> rpos((size_t)nPat, 0);
                 for (int i = 0; i < nPat; ++i) {
                     const PatPlan& pp = pps[(size_t)i];
                     ro[i] = (int)run;
@@ -1001,30 +1050,36 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ro[nPat] = (int)run;
             }
         }
-        for (int e = 0; e < nEpochs; ++e) {
-            out.kBinBase[(size_t)e] = (int)out.kBinPatOff.size();
+        for (int v = 0; v < nEpochs * 2; ++v) {
+            const int e = v / 2, mode = out.epochMode[(size_t)v];
+            out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
-            if (out.epochMode[(size_t)e] == 3) pack_range(e, e, RC_PBLOCK, 3, out.kBinPatOff, out.kBinPats);
-            else if (out.epochMode[(size_t)e]) pack_range(e, e, RC_NPBR, 1, out.kBinPatOff, out.kBinPats);
-            else pack_range(e, e, RC_NPB, 0, out.kBinPatOff, out.kBinPats);
-            out.nKBins[(size_t)e] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)e];
+            if (!groupIds[(size_t)v].empty()) {
+                if (mode == 3) pack_range(e, e, RC_PBLOCK, 3, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                else if (mode) pack_range(e, e, RC_NPBR, 1, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                else pack_range(e, e, RC_NPB, 0, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+            }
+            out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
         }
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
-        for (int e = 0; e < nEpochs; ++e) {
-            const int b0 = out.kBinBase[(size_t)e];
-            // fetch offsets are stored at the same index as the bin offsets (one extra entry per epoch)
+        for (int v = 0; v < nEpochs * 2; ++v) {
+            const int e = v / 2, b0 = out.kBinBase[(size_t)v];
+            // fetch offsets are stored at the same index as the bin offsets (one extra entry per group)
             std::vector<int> fOff;
-            fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)e], fOff, out.kFetchRows, out.kRowBase, 0);
+            fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0);
             fOff.push_back((int)out.kFetchRows.size());
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
         if (std::getenv("RC_PLAN_DEBUG")) {
-            for (int e = 0; e < nEpochs; ++e) {
+            for (int v = 0; v < nEpochs * 2; ++v) {
+                const int e = v / 2, m = out.epochMode[(size_t)v];
                 const PlanHost::Epoch& E = out.ep[(size_t)e];
-                int b0 = out.kBinBase[(size_t)e], nb = out.nKBins[(size_t)e];
+                int b0 = out.kBinBase[(size_t)v], nb = out.nKBins[(size_t)v];
+                if (!nb) continue;
                 int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
-                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s bins %d fetch rows/bin %.1f\n", e,
-                             E.nKeys, E.nThr, E.rowPairs, out.epochMode[(size_t)e] == 3 ? "patterns" : out.epochMode[(size_t)e] ? "rows" : "states", nb, nb ? (double)(f1 - f0) / nb : 0.0);
+                std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s patterns %d bins %d fetch rows/bin %.1f\n", e,
+                             E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
+                             (double)(f1 - f0) / nb);
             }
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
         }
@@ -1155,12 +1210,13 @@ std::string check_plan(const PlanHost& h) {
     // keyed per-epoch bins
     if (!h.kBinBase.empty()) {
         std::vector<char> seen;
-        for (int e = 0; e < nE; ++e) {
+        for (int v = 0; v < nE * 2; ++v) {
+            const int e = v / 2;
             const PlanHost::Epoch& E = h.ep[(size_t)e];
-            const bool rows = h.epochMode[(size_t)e] != 0, patM = h.epochMode[(size_t)e] == 3;
-            seen.assign((size_t)nPat, 0);
-            const int b0 = h.kBinBase[(size_t)e];
-            for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
+            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] == 3;
+            if (v % 2 == 0) seen.assign((size_t)nPat, 0);
+            const int b0 = h.kBinBase[(size_t)v];
+            for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
                 if (p1 - p0 < 1 || p1 - p0 > (patM ? RC_PBLOCK : rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
                 const int f0 = h.kFetchOff[(size_t)bI], f1 = h.kFetchOff[(size_t)bI + 1];
@@ -1216,10 +1272,11 @@ std::string check_plan(const PlanHost& h) {
             const long long hi = e < nE - 1 ? h.trEntBase[(size_t)e] : (long long)h.trEnt.size();
             return (long long)r0 >= lo && (long long)r0 + cnt <= hi && prev < h.epochSlots[(size_t)e - 1];
         };
-        for (int e = 0; e < nE; ++e) {
-            const bool rows = h.epochMode[(size_t)e] != 0, patM = h.epochMode[(size_t)e] == 3;
-            const int b0 = h.kBinBase[(size_t)e];
-            for (int bI = b0; bI < b0 + h.nKBins[(size_t)e]; ++bI) {
+        for (int v = 0; v < nE * 2; ++v) {
+            const int e = v / 2;
+            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] == 3;
+            const int b0 = h.kBinBase[(size_t)v];
+            for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
                 const int np = hdr[1], lanes = hdr[2], nB = hdr[3], nFetch = hdr[5];
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
@@ -1236,17 +1293,22 @@ std::string check_plan(const PlanHost& h) {
                 for (int t = 0; t < lanes; ++t) {
                     const uint32_t* r = &h.kLane[(size_t)hdr[6] * 4 + (size_t)t * (rows ? RC_RLANE_N : RC_LANE_N)];
                     if (patM) {
-                        const int rowA = (int)(r[0] & 0xFFu), rowB = (int)((r[0] >> 8) & 0xFFu), MA = (int)((r[0] >> 16) & 0xFFu), MB = (int)(r[0] >> 24);
-                        const int n = MA * (MB ? MB : 1);
-                        if (MA < 1 || MA > RC_ROW_MAXM || n > RC_PAT_MAXS) return fail("image pattern shape");
-                        if (rowA < 1 || rowA + MA - 1 >= nFetch) return fail("image pattern pair rows (A)");
-                        if (MB ? (rowB < 1 || rowB + MB - 1 >= nFetch) : rowB != RC_KROWS - 1) return fail("image pattern pair rows (B)");
-                        if ((int)r[3] >= nPat || (long long)r[1] + n > h.epochSlots[(size_t)e] || (int)r[2] + n > nB) return fail("image pattern hand-over");
-                        const int live = h.slotOff[(size_t)e * (nPat + 1) + r[3] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[3]];
-                        if (live != n || (int)r[1] != h.slotOff[(size_t)e * (nPat + 1) + r[3]]) return fail("image pattern states");
+                        const int M[4] = {(int)(r[2] & 0xFu), (int)((r[2] >> 4) & 0xFu), (int)((r[2] >> 8) & 0xFu), (int)((r[2] >> 12) & 0xFu)};
+                        const int nU = (int)((r[2] >> 16) & 0xFu), eOff = (int)(r[2] >> 20);
+                        int n = M[0], nS = 0;
+                        for (int q = 1; q < 4; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1]) return fail("image pattern shape order"); }
+                        if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > RC_PAT_MAXS || 1 + nS + nU > 8) return fail("image pattern shape");
+                        for (int q = 0; q < 8; ++q) {
+                            const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                            const int len = q <= nS ? M[q] : 1;
+                            if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != RC_KROWS - 1) return fail("image pattern pair rows");
+                        }
+                        if ((int)r[4] >= nPat || (long long)r[3] + n > h.epochSlots[(size_t)e] || eOff + n > nB) return fail("image pattern hand-over");
+                        const int live = h.slotOff[(size_t)e * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[4]];
+                        if (live != n || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
                         std::vector<char> hit((size_t)n, 0);
                         for (int q = 0; q < n; ++q) {
-                            const int ref = (int)((r[4 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
+                            const int ref = (int)((r[5 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
                             if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
                             hit[(size_t)ref] = 1;
                         }
