@@ -649,7 +649,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     // two bin groups per epoch: patterns small enough for one thread each, and the rest (rows or states)
                     for (int v = 2 * e; v < 2 * e + 2; ++v) {
                         if (pe->h.nKBins[(size_t)v] == 0) continue;
-                        CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], dM, dMep, dSev,
+                        CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v],
+                                                     dM, dMep, dSev,
                                                      (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
                                                      carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
                         ++launches;

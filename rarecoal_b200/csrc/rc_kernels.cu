@@ -1656,12 +1656,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 // predicates; every thread fetches up to four pair rows per grid step into the ring.
 #define RC_PDEPTH 4
 #define RC_PFETCH (RC_KROWS / RC_PBLOCK)
-struct RcPatSmem {
-    double RE[RC_PDEPTH * 2 * RC_KROWS];               // [slot][row]{G, E2}; row 0 = {dt, 0}
-    double bb[RC_PBLOCK * RC_PAT_MAXS];                // gathered b of the bin, pattern after pattern
-};
-static_assert(offsetof(RcPatSmem, RE) % 16 == 0, "16-byte alignment of the pair table");
-
+// Shared memory of a pattern-mode block (dynamic, sized per bin group by the host): the pair ring, RC_PDEPTH slots of
+// `ringRows` pairs — [slot][row]{G, E2}, row 0 = {dt, 0} — and, aliased onto it, the b values of the bin gathered before the
+// ring starts (pattern after pattern).
 struct RcPatRegs {
     double b[RC_PAT_MAXS];
     unsigned rowsW[2];            // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
@@ -1676,8 +1673,7 @@ __device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs& R, int q) { retu
 
 template <int MA, int MB, int MC, int MD>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
-                                           unsigned& slot) {
-    constexpr unsigned RE_SLOT = RC_KROWS * 16u;
+                                           unsigned& slot, const unsigned RE_SLOT) {
     constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1;
     constexpr int SA = MBp * MCp * MDp, SB = MCp * MDp, SC = MDp;
     constexpr int NS = (MB ? 1 : 0) + (MC ? 1 : 0) + (MD ? 1 : 0);
@@ -1747,10 +1743,10 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
 // the present ones <= RC_PAT_MAXS
 template <int MB, int MC, int MD>
 __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
-                                                  unsigned& slot, const int MA) {
+                                                  unsigned& slot, const unsigned reSlot, const int MA) {
     constexpr int SA = (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
 #define RC_PAT_CASE(A) \
-    case A: if constexpr (A >= MB && A * SA <= RC_PAT_MAXS) { rc_pat_run<A, MB, MC, MD>(R, sBase, strideD, s, nextStop, slot); } break;
+    case A: if constexpr (A >= MB && A * SA <= RC_PAT_MAXS) { rc_pat_run<A, MB, MC, MD>(R, sBase, strideD, s, nextStop, slot, reSlot); } break;
     switch (MA) {
         RC_PAT_CASE(1) RC_PAT_CASE(2) RC_PAT_CASE(3) RC_PAT_CASE(4) RC_PAT_CASE(5)
         RC_PAT_CASE(6) RC_PAT_CASE(7) RC_PAT_CASE(8) RC_PAT_CASE(9) RC_PAT_CASE(10)
@@ -1760,19 +1756,22 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned s
     static_assert(RC_ROW_MAXM == 10, "cases above");
 }
 
-__global__ void __launch_bounds__(RC_PBLOCK, 8)
-rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+#ifndef RC_PAT_MINB
+#define RC_PAT_MINB 8
+#endif
+__global__ void __launch_bounds__(RC_PBLOCK, RC_PAT_MINB)
+rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                         const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
                         long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    typedef RcPatSmem SM;
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
-    SM& S = *reinterpret_cast<SM*>(smemRaw);
+    double* bb = reinterpret_cast<double*>(smemRaw);
     const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned reSlot = (unsigned)ringRows * 16u;
     const int binIdx = binBase + (int)blockIdx.x;
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
@@ -1807,16 +1806,15 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __re
         for (int u = 0; u < RC_PDEPTH - 1; ++u) {
 #pragma unroll
             for (int q = 0; q < RC_PFETCH; ++q) {
-                rc_cp_async16_if(sBase + (unsigned)u * RC_KROWS * 16u + (unsigned)(q * RC_PBLOCK + tid) * 16u, R.fp[q], (R.fmask >> q) & 1u);
+                rc_cp_async16_if(sBase + (unsigned)u * reSlot + (unsigned)(q * RC_PBLOCK + tid) * 16u, R.fp[q], (R.fmask >> q) & 1u);
                 R.fp[q] += strideD;
             }
             rc_cp_commit();
         }
         slot = 0;
     };
-    bool ringStarted = false;
-    if (s < mE.end) { ring_start(); ringStarted = true; }
-    // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory ----
+    // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory (the ring starts
+    //      afterwards: it lives in the same bytes) ----
     uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la;
     if (R.on) {
         const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + 3 * (size_t)tid;
@@ -1836,7 +1834,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __re
                 const int cnt = (int)(g.y >> RC_IMG_CNT_SHIFT);
                 if (cnt) v = rc_gather(pl.trEnt + g.x, 0, cnt, bp + (g.y & ((1u << RC_IMG_CNT_SHIFT) - 1u)), W);
             }
-            S.bb[i] = v;
+            bb[i] = v;
         }
     }
     const unsigned shape = la.z & 0xFFFFu;          // MA | MB << 4 | MC << 8 | MD << 12
@@ -1850,7 +1848,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __re
     R.unit = R.on && MB == 0 && R.nU == 0;          // x = e_A is the first state of a single-branch pattern
     __syncthreads();
     if (R.on) {
-        const double* mine = S.bb + (la.z >> 20);
+        const double* mine = bb + (la.z >> 20);
 #pragma unroll
         for (int x = 0; x < RC_PAT_MAXS; ++x)
             if (x < n) R.b[x] = mine[x];
@@ -1870,19 +1868,18 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __re
 #endif
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
-            if (!ringStarted) ring_start();
-            ringStarted = false;
+            ring_start();
             rc_cp_wait<RC_PDEPTH - 2>();
             __syncthreads();
             switch (shapeB >> 4) {          // MB | MC << 4 | MD << 8
-                case 0x000: rc_pat_dispatch_a<0, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x002: rc_pat_dispatch_a<2, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x003: rc_pat_dispatch_a<3, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x004: rc_pat_dispatch_a<4, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x005: rc_pat_dispatch_a<5, 0, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x022: rc_pat_dispatch_a<2, 2, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x023: rc_pat_dispatch_a<3, 2, 0>(R, sBase, strideD, s, nextStop, slot, MAw); break;
-                case 0x222: rc_pat_dispatch_a<2, 2, 2>(R, sBase, strideD, s, nextStop, slot, MAw); break;
+                case 0x000: rc_pat_dispatch_a<0, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x002: rc_pat_dispatch_a<2, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x003: rc_pat_dispatch_a<3, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x004: rc_pat_dispatch_a<4, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x005: rc_pat_dispatch_a<5, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x022: rc_pat_dispatch_a<2, 2, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x023: rc_pat_dispatch_a<3, 2, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+                case 0x222: rc_pat_dispatch_a<2, 2, 2>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
                 default: break;             // no other shape has a product <= RC_PAT_MAXS
             }
             static_assert(RC_PAT_MAXS == 25, "shape list above");
@@ -2056,7 +2053,7 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
     return cudaGetLastError();
 }
 
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
@@ -2069,14 +2066,10 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
     const double* bp = bPrev + (size_t)b0 * bStride;
     double* bc = bCur + (size_t)b0 * bStride;
     if (rowMode == 3) {
-        static bool cp = false;
-        const size_t psmem = (sizeof(RcPatSmem) + 15) & ~(size_t)15;
-        if (!cp) {
-            cudaError_t err = cudaFuncSetAttribute(rc_propagate_pat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-            if (err != cudaSuccess) return err;
-            cp = true;
-        }
-        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        // ring of RC_PDEPTH slots sized for the group's largest fetch list, aliased with the gathered b of the largest bin
+        const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
+        const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
+        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return cudaGetLastError();
     }
     if (rowMode) {

@@ -19,7 +19,7 @@ size_t rc_fast_smem_bytes(int block);
 cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
                            const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
                            double* aEnd, double* aShort, int b0, int nB, cudaStream_t st);
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st);

@@ -484,6 +484,8 @@ static std::string build_bin_images(PlanHost& out) {
     out.kPatRec.assign(out.kBinPats.size() * 2, 0);
     out.kLane.clear();
     out.kElem.clear();
+    out.grpMaxFetch.assign((size_t)out.nEpochs * 2, 0);
+    out.grpMaxB.assign((size_t)out.nEpochs * 2, 0);
     if (out.kBinBase.empty()) return "";
     if (out.maxEpochSlots >= (1LL << RC_IMG_CNT_SHIFT)) return "too many live states in one epoch for the keyed tier";
     if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
@@ -642,6 +644,8 @@ static std::string build_bin_images(PlanHost& out) {
             }
             hdr[2] = lanes;
             hdr[3] = bOff;
+            out.grpMaxFetch[(size_t)v] = std::max(out.grpMaxFetch[(size_t)v], hdr[5]);
+            out.grpMaxB[(size_t)v] = std::max(out.grpMaxB[(size_t)v], bOff);
         }
     }
     return "";
