@@ -303,8 +303,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": TRAFFIC,
-                         "kernel": "propagation launches, one per structural epoch: rc_propagate_keyed_kernel (epochs 0-3) + "
-                                   "rc_propagate_rows_kernel (epochs 4-7)",
+                         "kernel": (TRAFFIC or {}).get("kernels", "propagation launches (rc_propagate_pat_kernel / rc_propagate_rows_kernel)"),
+                         "pipes": (TRAFFIC or {}).get("pipes_pct_of_peak_time_weighted"),
+                         "frac_note": "achieved counts the reference's 4P+27 flops per state-step (SURVEY.md 8d); the factorised update "
+                                      "executes fewer DP instructions, so frac can exceed 1 - the pipes measured by ncu are in `pipes`",
                          "kernel_ms": k_ms, "traj_kernels_ms": traj_mean,
                          "algorithmic": f"{w_steps} state-steps x {FLOPS_PER_STATE_STEP} flops per launch (rank 0)",
                          "peak_source": "rc_fp64_peak DFMA microbenchmark on this GPU (no FP64 figure in MEASURED_PEAKS.json)",

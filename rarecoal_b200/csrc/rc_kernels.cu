@@ -1654,7 +1654,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 // with sum_k m_k pair loads per pattern and step instead of one per state and branch.  Blocks are small (RC_PBLOCK threads,
 // several resident per SM) and hold patterns of one shape only (rc_plan.cpp), so the update is fully unrolled without
 // predicates; every thread fetches up to four pair rows per grid step into the ring.
+#ifndef RC_PDEPTH
 #define RC_PDEPTH 4
+#endif
 #define RC_PFETCH (RC_KROWS / RC_PBLOCK)
 // Shared memory of a pattern-mode block (dynamic, sized per bin group by the host): the pair ring, RC_PDEPTH slots of
 // `ringRows` pairs — [slot][row]{G, E2}, row 0 = {dt, 0} — and, aliased onto it, the b values of the bin gathered before the
@@ -1757,7 +1759,7 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned s
 }
 
 #ifndef RC_PAT_MINB
-#define RC_PAT_MINB 8
+#define RC_PAT_MINB 7      // measured on C3: 6 -> 16.9 ms, 7 -> 16.2, 8 -> 16.6, 10 -> 18.2 (spills)
 #endif
 __global__ void __launch_bounds__(RC_PBLOCK, RC_PAT_MINB)
 rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,

@@ -30,25 +30,38 @@ def scale(v, u):
 rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
 tot_r = sum(scale(r[rd], units[rd]) for r in body)
 tot_w = sum(scale(r[wr], units[wr]) for r in body)
-json.dump({
-    "kernels": "rc_propagate_keyed_kernel<8> (epochs 0-3) + rc_propagate_rows_kernel (epochs 4-7): the 8 propagation launches of one evaluation",
-    "launch": "C3, 44 models per evaluation (bench.py default)",
-    "dram_bytes_read": int(tot_r), "dram_bytes_write": int(tot_w), "dram_bytes_total": int(tot_r + tot_w),
-    "algorithmic_hbm_bytes": 46207392,
-    "source": "profiles/r01_propagate_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 launches)",
-    "note": "trajectory tables (~60 MB per model) written by rc_traj_kernel and read here, bin images re-read per model, b carried between epoch launches (2 x 5.9 MB per model and epoch); a few hundred GB/s against the measured 6539 GB/s copy bandwidth - not the bound",
-}, open(os.path.join(ROOT, "profiles", "r01_keyed_traffic.json"), "w"))
 names = {"ms": "gpu__time_duration.sum", "smem": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
          "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active", "fp64": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
          "warps": "sm__warps_active.avg.pct_of_peak_sustained_active", "regs": "launch__registers_per_thread", "grid": "launch__grid_size"}
-print("| epoch | kernel | grid | ms | smem pipe % | issue % | FP64 % | warps % | regs | DRAM rd / wr |")
+
+
+def kind(r):
+    n = r[ix["Kernel Name"]]
+    return "pattern" if "_pat_" in n else "rows" if "rows" in n else "states"
+
+
+ms = [float(r[col(names["ms"])]) for r in body]
+tms = sum(ms)
+pipes = {k: sum(float(r[col(names[k])]) * m for r, m in zip(body, ms)) / tms for k in ("smem", "issue", "fp64", "warps")}
+share = {}
+for r, m in zip(body, ms):
+    share[kind(r)] = share.get(kind(r), 0.0) + m / tms
+json.dump({
+    "kernels": "the propagation launches of one evaluation: per structural epoch rc_propagate_pat_kernel (one pattern per thread) and, "
+               "for the patterns with more than 25 live states, rc_propagate_rows_kernel",
+    "launch": "C3, 44 models per evaluation (bench.py default); %d launches" % len(body),
+    "dram_bytes_read": int(tot_r), "dram_bytes_write": int(tot_w), "dram_bytes_total": int(tot_r + tot_w),
+    "algorithmic_hbm_bytes": 46207392,
+    "time_share": {k: round(v, 3) for k, v in share.items()},
+    "pipes_pct_of_peak_time_weighted": {"shared_memory_wavefronts": round(pipes["smem"], 1), "fp64_pipe": round(pipes["fp64"], 1),
+                                        "issue_slots": round(pipes["issue"], 1), "warps_active": round(pipes["warps"], 1)},
+    "source": "profiles/r01_propagate_raw.csv (ncu --set full, per-launch metrics; DRAM = dram__bytes_read.sum + dram__bytes_write.sum summed)",
+    "note": "trajectory tables (~60 MB per model) written by rc_traj_kernel and read here, bin images re-read per model, b carried "
+            "between epoch launches; a few hundred GB/s against the measured 6539 GB/s copy bandwidth - not the bound",
+}, open(os.path.join(ROOT, "profiles", "r01_keyed_traffic.json"), "w"))
+print("| launch | kernel | grid | ms | smem pipe % | issue % | FP64 pipe % | warps % | regs | DRAM rd / wr |")
 for e, r in enumerate(body):
-    kn = "rows" if "rows" in r[ix["Kernel Name"]] else "keyed"
     g = lambda k: r[col(names[k])]
-    try:
-        f64 = "%.1f" % float(g("fp64"))
-    except Exception:
-        f64 = "-"
-    print(f"| {e} | {kn} | {g('grid')} | {float(g('ms')):.2f} | {float(g('smem')):.1f} | {float(g('issue')):.1f} | {f64} | "
+    print(f"| {e} | {kind(r)} | {g('grid')} | {float(g('ms')):.2f} | {float(g('smem')):.1f} | {float(g('issue')):.1f} | {float(g('fp64')):.1f} | "
           f"{float(g('warps')):.1f} | {g('regs')} | {scale(r[rd], units[rd]) / 1e9:.2f} GB / {scale(r[wr], units[wr]) / 1e6:.0f} MB |")
-print("sum ms", sum(float(r[col(names['ms'])]) for r in body), "dram GB", (tot_r + tot_w) / 1e9)
+print("sum ms", tms, "dram GB", (tot_r + tot_w) / 1e9, "pipes", pipes, "share", share)
