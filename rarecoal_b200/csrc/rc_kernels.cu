@@ -116,6 +116,43 @@ __device__ __forceinline__ double rc_gather(const uint32_t* __restrict__ trEnt, 
     return acc;
 }
 
+// The same gather for U states of a bin at once (records of rc_types.h, "gather record"): all entry words first, then all
+// carried b values and weights, then the sums in entry order — three dependent loads per batch instead of per state.
+template <int U, int E>
+__device__ __forceinline__ void rc_gather_batch(const uint2 (&g)[U], const uint32_t* __restrict__ trEnt, const double* __restrict__ bp,
+                                                const double* __restrict__ W, double (&v)[U]) {
+    int cnt[U], maxCnt = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool seed = g[u].x == RC_IMG_SEED;                              // makeInitCoalState, Core.hs:66
+        cnt[u] = seed ? 0 : (int)(g[u].y >> RC_IMG_CNT_SHIFT);
+        v[u] = seed ? 1.0 : 0.0;
+        maxCnt = max(maxCnt, cnt[u]);
+    }
+    for (int base = 0; base < maxCnt; base += E) {
+        uint32_t en[U][E];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < E; ++q) en[u][q] = base + q < cnt[u] ? trEnt[(size_t)g[u].x + base + q] : (RC_W_ONE << 16);
+        double old[U][E], w[U][E];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const bool on = base + q < cnt[u];
+                const uint32_t widx = en[u][q] >> 16;
+                old[u][q] = on ? bp[(size_t)(g[u].y & ((1u << RC_IMG_CNT_SHIFT) - 1u)) + (en[u][q] & 0xFFFFu)] : 0.0;
+                w[u][q] = (on && widx != RC_W_ONE) ? W[widx] : 1.0;
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < E; ++q)
+                if (base + q < cnt[u]) v[u] = (en[u][q] >> 16) == RC_W_ONE ? v[u] + old[u][q] : v[u] + old[u][q] * w[u][q];
+    }
+}
+
 struct RcSmem {
     double *bA, *bB, *dacc, *a, *r, *dpat, *tab;
     uint32_t *words, *meta;
@@ -1265,6 +1302,9 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __
 // (Core.hs:259).  Rows are stored row-major with an odd stride (M | 1), so a warp reading one column of consecutive
 // rows touches distinct banks.
 #define RC_RDEPTH 4
+#ifndef RC_ROW_GU
+#define RC_ROW_GU 2
+#endif
 #ifndef RC_ROW_SPLIT_O
 #define RC_ROW_SPLIT_O 0
 #endif
@@ -1475,15 +1515,16 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        for (int i = tid; i < nB; i += RC_BLOCK) {
-            const uint2 g = el[i];
-            double v = 0.0;
-            if (g.x == RC_IMG_SEED) v = 1.0;                                    // makeInitCoalState, Core.hs:66
-            else {
-                const int cnt = (int)(g.y >> RC_IMG_CNT_SHIFT);
-                if (cnt) v = rc_gather(pl.trEnt + g.x, 0, cnt, bp + (g.y & ((1u << RC_IMG_CNT_SHIFT) - 1u)), W);
-            }
-            S.bbuf[i] = v;
+        constexpr int GU = RC_ROW_GU;
+        for (int i = tid; i < nB; i += GU * RC_BLOCK) {
+            uint2 g[GU];
+            double v[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) g[u] = i + u * RC_BLOCK < nB ? el[i + u * RC_BLOCK] : make_uint2(0u, 0u);
+            rc_gather_batch<GU, 4>(g, pl.trEnt, bp, W, v);
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
+                if (i + u * RC_BLOCK < nB) S.bbuf[i + u * RC_BLOCK] = v[u];
         }
     }
     __syncthreads();
@@ -1654,6 +1695,12 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 // with sum_k m_k pair loads per pattern and step instead of one per state and branch.  Blocks are small (RC_PBLOCK threads,
 // several resident per SM) and hold patterns of one shape only (rc_plan.cpp), so the update is fully unrolled without
 // predicates; every thread fetches up to four pair rows per grid step into the ring.
+#ifndef RC_PAT_GU
+#define RC_PAT_GU 4
+#endif
+#ifndef RC_PAT_NU_MODE
+#define RC_PAT_NU_MODE 1      // 0: loop over the unit branches (16.8 ms on C3), 1: loads unrolled, tree product (15.6 ms)
+#endif
 #ifndef RC_PDEPTH
 #define RC_PDEPTH 4
 #endif
@@ -1663,7 +1710,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 // ring starts (pattern after pattern).
 struct RcPatRegs {
     double b[RC_PAT_MAXS];
-    unsigned rowsW[2];            // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
+    unsigned long long rows64;    // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
     int nU;                       // number of m = 1 branches
     bool on, unit;
     double dacc;
@@ -1671,7 +1718,7 @@ struct RcPatRegs {
     unsigned fmask;               // bit q: the thread fetches pair row q * RC_PBLOCK + tid
 };
 
-__device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs& R, int q) { return (R.rowsW[q >> 2] >> (8 * (q & 3))) & 0xFFu; }
+__device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs& R, int q) { return (unsigned)(R.rows64 >> (8 * q)) & 0xFFu; }
 
 template <int MA, int MB, int MC, int MD>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
@@ -1705,10 +1752,17 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
 #pragma unroll
                 for (int j = 0; j < MDp; ++j) rc_lds128(aD + slot + (unsigned)j * 16u, gD[j], eD[j]);
             }
-            double D1 = 1.0;                     // branches with m = 1: G_k(1) only
+            double D1 = 1.0;                     // branches with m = 1: G_k(1) only; nU is the same for the whole block
+#if RC_PAT_NU_MODE == 0
+            for (int u = 0; u < R.nU; ++u) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
+#else
+            if (R.nU) {
+                double g[7];
 #pragma unroll
-            for (int u = 0; u < 8 - 1 - NS; ++u)
-                if (u < R.nU) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
+                for (int u = 0; u < 7 - NS; ++u) g[u] = u < R.nU ? rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot) : 1.0;
+                D1 = ((g[0] * g[1]) * (g[2] * g[3])) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
+            }
+#endif
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
                 double gA, eA;
@@ -1828,15 +1882,16 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        for (int i = tid; i < nB; i += RC_PBLOCK) {
-            const uint2 g = el[i];
-            double v = 0.0;
-            if (g.x == RC_IMG_SEED) v = 1.0;                                    // makeInitCoalState, Core.hs:66
-            else {
-                const int cnt = (int)(g.y >> RC_IMG_CNT_SHIFT);
-                if (cnt) v = rc_gather(pl.trEnt + g.x, 0, cnt, bp + (g.y & ((1u << RC_IMG_CNT_SHIFT) - 1u)), W);
-            }
-            bb[i] = v;
+        constexpr int GU = RC_PAT_GU;
+        for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
+            uint2 g[GU];
+            double v[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) g[u] = i + u * RC_PBLOCK < nB ? el[i + u * RC_PBLOCK] : make_uint2(0u, 0u);
+            rc_gather_batch<GU, 4>(g, pl.trEnt, bp, W, v);
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
+                if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
         }
     }
     const unsigned shape = la.z & 0xFFFFu;          // MA | MB << 4 | MC << 8 | MD << 12
@@ -1844,8 +1899,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int n = MA * (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
     const int pid = (int)lb.x;
     double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
-    R.rowsW[0] = la.x;
-    R.rowsW[1] = la.y;
+    R.rows64 = (unsigned long long)la.x | ((unsigned long long)la.y << 32);
     R.nU = (int)((la.z >> 16) & 0xFu);
     R.unit = R.on && MB == 0 && R.nU == 0;          // x = e_A is the first state of a single-branch pattern
     __syncthreads();
@@ -1857,9 +1911,10 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     }
     // the block's shape: bins hold one (MA, MB) class
     __shared__ unsigned shapeS;
-    if (tid == 0) shapeS = shape;
+    if (tid == 0) shapeS = la.z & 0xFFFFFu;         // shape and number of unit branches: one class per bin
     __syncthreads();
-    const unsigned shapeB = shapeS;
+    const unsigned shapeB = shapeS & 0xFFFFu;
+    R.nU = (int)(shapeS >> 16);
     const int MAw = (int)(shapeB & 0xFu);
 
     bool finished = false, parked = false;

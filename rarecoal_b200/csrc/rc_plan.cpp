@@ -859,7 +859,11 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
             auto clsOf = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
-                if (patMode) return (int)pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0]);
+                if (patMode) {
+                    int nU = 0;
+                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0], nullptr, nullptr, &nU);
+                    return (int)(sh | ((uint32_t)nU << 16));      // blocks are uniform in shape and in the number of unit branches
+                }
                 if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
                 int c = 0;
                 for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
