@@ -123,7 +123,13 @@ struct RcPlanDev {
 //               [3..6] b offsets in doubles (8 x u16): own row, then the neighbour row along each other branch
 //                      (RC_ROW_BCAP = the always-zero row)
 //               [7] first slot of the pattern in the epoch  [8] row index in rowRefAll  [9] pattern id  [10..11] 0
-//   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row lane).
+//   pattern mode (RC_RLANE_N words; one lane = one pattern, its states at the mixed-radix position
+//               (((x_A - 1) MB' + x_B - 1) MC' + x_C - 1) MD' + x_D - 1, M' = max(M, 1)):
+//               [0..1] pair row of x = 1 of every non-zero branch (8 x u8): A, the shaped branches B.., then the m = 1 branches
+//               [2] MA | MB << 4 | MC << 8 | MD << 12 | number of m = 1 branches << 16 | first b double of the pattern in the bin << 20
+//               [3] first slot of the pattern in the epoch  [4] pattern id
+//               [5..11] reference-order index of every state (25 x u8)
+//   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row or pattern lane).
 // Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
 // and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
 #define RC_LANE_N 8
