@@ -143,6 +143,11 @@ struct rc_ctx {
     PinBuf hBlob, hOut;
     cudaStream_t stream = nullptr;
     cudaEvent_t evt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // side stream of the trajectory kernels: rc_traj_kernel(e) depends only on rc_traj_kernel(e-1), so the chain runs beside
+    // the propagation launches, each of which waits for the trajectory of its own epoch
+    cudaStream_t trajStream = nullptr;
+    cudaEvent_t evFork = nullptr;
+    std::vector<cudaEvent_t> evTraj;
     bool trajTimed = false;
     int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
     bool statsPending = false;
@@ -635,17 +640,27 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
             for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
             if (pe->d.nFastBins > 0 && anyKeyed) {
                 const bool timeIt = !ctx->trajTimed;      // trajectory kernels of the first plan group are timed
-                if (timeIt) CK(cudaEventRecord(ctx->evt[6], st));
+                cudaStream_t ts = ctx->trajStream;
+                while ((int)ctx->evTraj.size() < pe->h.nEpochs) {
+                    cudaEvent_t ev = nullptr;
+                    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    ctx->evTraj.push_back(ev);
+                }
+                CK(cudaEventRecord(ctx->evFork, st));     // tables written, previous work on st finished
+                CK(cudaStreamWaitEvent(ts, ctx->evFork, 0));
+                if (timeIt) CK(cudaEventRecord(ctx->evt[6], ts));
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
-                                      (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, st));
+                                      (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, ts));
+                    CK(cudaEventRecord(ctx->evTraj[(size_t)e], ts));
                     ++launches;
                 }
-                if (timeIt) { CK(cudaEventRecord(ctx->evt[7], st)); ctx->trajTimed = true; }
+                if (timeIt) { CK(cudaEventRecord(ctx->evt[7], ts)); ctx->trajTimed = true; }
                 // one launch per structural epoch; b ping-pongs between the two carry buffers
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
+                    CK(cudaStreamWaitEvent(st, ctx->evTraj[(size_t)e], 0));
                     // two bin groups per epoch: patterns small enough for one thread each, and the rest (rows or states)
                     for (int v = 2 * e; v < 2 * e + 2; ++v) {
                         if (pe->h.nKBins[(size_t)v] == 0) continue;
@@ -821,6 +836,8 @@ int rc_create(int device, rc_ctx** out) {
     cudaDeviceGetAttribute(&ctx->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->trajStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     for (auto& e : ctx->evt)
         if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -841,6 +858,9 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->hOut.release();
     for (auto& e : ctx->evt) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->trajStream) cudaStreamDestroy(ctx->trajStream);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    for (cudaEvent_t ev : ctx->evTraj) cudaEventDestroy(ev);
     delete ctx;
 }
 
