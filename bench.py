@@ -244,7 +244,9 @@ def main():
         step_device(i)
         torch.cuda.synchronize()
         st = eng.stats()
-        kernel_ms.append(st["kernel_ms"] - st["traj_ms"])
+        # span of the propagation launches on the main stream; the trajectory kernels run beside them on a side stream
+        # (each epoch's launch waits for its own trajectory), so their time is not subtracted — the conservative reading
+        kernel_ms.append(st["kernel_ms"])
         traj_ms.append(st["traj_ms"])
         launches += st["launches"] + (1 if by_pattern else 0)
         w_steps = st["state_steps"]
@@ -307,7 +309,7 @@ def main():
                          "pipes": (TRAFFIC or {}).get("pipes_pct_of_peak_time_weighted"),
                          "frac_note": "achieved counts the reference's 4P+27 flops per state-step (SURVEY.md 8d); the factorised update "
                                       "executes fewer DP instructions, so frac can exceed 1 - the pipes measured by ncu are in `pipes`",
-                         "kernel_ms": k_ms, "traj_kernels_ms": traj_mean,
+                         "kernel_ms": k_ms, "traj_kernels_ms_side_stream": traj_mean,
                          "algorithmic": f"{w_steps} state-steps x {FLOPS_PER_STATE_STEP} flops per launch (rank 0)",
                          "peak_source": "rc_fp64_peak DFMA microbenchmark on this GPU (no FP64 figure in MEASURED_PEAKS.json)",
                          "hbm_note": "algorithmic HBM bytes ~24 B x patterns x models per launch: not the bound"},

@@ -58,8 +58,9 @@ typedef struct {
 typedef struct {
     int64_t state_steps;     /* executed b(x) updates over all models (SURVEY.md §8d unit, Core.hs:248) */
     int64_t slots;           /* live states resident at t=0 over all models                            */
-    double kernel_ms;        /* CUDA-event time of trajectory + propagation kernels on the eval stream   */
-    double traj_ms;          /* of which: trajectory kernels (first plan group)                          */
+    double kernel_ms;        /* CUDA-event span of the propagation launches on the eval stream           */
+    double traj_ms;          /* trajectory kernels (first plan group): elapsed on their side stream,     */
+                             /* concurrent with the propagation launches                                 */
     double tables_ms;        /* CUDA-event time of the per-model table kernel                           */
     double total_ms;         /* CUDA-event time first launch -> last launch of the call                 */
     int32_t launches;        /* kernels launched by the call                                            */
