@@ -661,8 +661,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
                     CK(cudaStreamWaitEvent(st, ctx->evTraj[(size_t)e], 0));
-                    // two bin groups per epoch: patterns small enough for one thread each, and the rest (rows or states)
-                    for (int v = 2 * e; v < 2 * e + 2; ++v) {
+                    // bin groups of the epoch: small / large patterns (one thread each), and the rest (rows or states)
+                    for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
                         if (pe->h.nKBins[(size_t)v] == 0) continue;
                         CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v],
                                                      dM, dMep, dSev,

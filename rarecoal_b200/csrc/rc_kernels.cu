@@ -1687,8 +1687,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pattern mode of the keyed tier: one thread owns a whole pattern whose live set is a box of at most RC_PAT_MAXS states —
-// the row branch A, up to three more branches with m >= 2 (B, C, D; the shape is a template parameter) and any number of
+// Pattern mode of the keyed tier: one thread owns a whole pattern whose live set is a box of at most MAXS states (two
+// instantiations: RC_PAT_MAXS, and RC_PAT_MAXL with fewer resident blocks for the larger boxes) —
+// the row branch A, up to four more branches with m >= 2 (B..E; the shape is a template parameter) and any number of
 // branches with m = 1, which only contribute a decay factor.  b lives in registers, so every neighbour of a state is a
 // register too and shared memory only carries the {G,E2} pairs:
 //     b'(x) = b(x) prod_k G_k(x_k) + sum_{k in A..D} b(x + e_k) E2_k(x_k)                          (Core.hs:259)
@@ -1708,8 +1709,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 // Shared memory of a pattern-mode block (dynamic, sized per bin group by the host): the pair ring, RC_PDEPTH slots of
 // `ringRows` pairs — [slot][row]{G, E2}, row 0 = {dt, 0} — and, aliased onto it, the b values of the bin gathered before the
 // ring starts (pattern after pattern).
+template <int MAXS>
 struct RcPatRegs {
-    double b[RC_PAT_MAXS];
+    double b[MAXS];
     unsigned long long rows64;    // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
     int nU;                       // number of m = 1 branches
     bool on, unit;
@@ -1718,18 +1720,19 @@ struct RcPatRegs {
     unsigned fmask;               // bit q: the thread fetches pair row q * RC_PBLOCK + tid
 };
 
-__device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs& R, int q) { return (unsigned)(R.rows64 >> (8 * q)) & 0xFFu; }
+template <int MAXS>
+__device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs<MAXS>& R, int q) { return (unsigned)(R.rows64 >> (8 * q)) & 0xFFu; }
 
-template <int MA, int MB, int MC, int MD>
-__device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
+template <int MA, int MB, int MC, int MD, int ME, int MAXS>
+__device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                            unsigned& slot, const unsigned RE_SLOT) {
-    constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1;
-    constexpr int SA = MBp * MCp * MDp, SB = MCp * MDp, SC = MDp;
-    constexpr int NS = (MB ? 1 : 0) + (MC ? 1 : 0) + (MD ? 1 : 0);
-    static_assert(MA * SA <= RC_PAT_MAXS, "shape");
+    constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1, MEp = ME ? ME : 1;
+    constexpr int SA = MBp * MCp * MDp * MEp, SB = MCp * MDp * MEp, SC = MDp * MEp, SD = MEp;
+    constexpr int NS = (MB ? 1 : 0) + (MC ? 1 : 0) + (MD ? 1 : 0) + (ME ? 1 : 0);
+    static_assert(MA * SA <= MAXS, "shape");
     const unsigned myRE = sBase + threadIdx.x * 16u;
     const unsigned aA = sBase + rc_pat_row(R, 0) * 16u, aB = sBase + rc_pat_row(R, 1) * 16u, aC = sBase + rc_pat_row(R, 2) * 16u,
-                   aD = sBase + rc_pat_row(R, 3) * 16u;
+                   aD = sBase + rc_pat_row(R, 3) * 16u, aE = sBase + rc_pat_row(R, 4) * 16u;
     for (; s < nextStop; ++s) {
         const unsigned prev = slot == 0 ? (RC_PDEPTH - 1) * RE_SLOT : slot - RE_SLOT;      // slot of step s - 1: free again
 #pragma unroll
@@ -1739,7 +1742,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
         }
         rc_cp_commit();
         if (R.on) {
-            double gB[MBp], eB[MBp], gC[MCp], eC[MCp], gD[MDp], eD[MDp];
+            double gB[MBp], eB[MBp], gC[MCp], eC[MCp], gD[MDp], eD[MDp], gE[MEp], eE[MEp];
             if (MB) {
 #pragma unroll
                 for (int j = 0; j < MBp; ++j) rc_lds128(aB + slot + (unsigned)j * 16u, gB[j], eB[j]);
@@ -1752,6 +1755,10 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
 #pragma unroll
                 for (int j = 0; j < MDp; ++j) rc_lds128(aD + slot + (unsigned)j * 16u, gD[j], eD[j]);
             }
+            if (ME) {
+#pragma unroll
+                for (int j = 0; j < MEp; ++j) rc_lds128(aE + slot + (unsigned)j * 16u, gE[j], eE[j]);
+            }
             double D1 = 1.0;                     // branches with m = 1: G_k(1) only; nU is the same for the whole block
 #if RC_PAT_NU_MODE == 0
             for (int u = 0; u < R.nU; ++u) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
@@ -1760,7 +1767,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
                 double g[7];
 #pragma unroll
                 for (int u = 0; u < 7 - NS; ++u) g[u] = u < R.nU ? rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot) : 1.0;
-                D1 = ((g[0] * g[1]) * (g[2] * g[3])) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
+                D1 = ((g[0] * g[1]) * (g[2] * (NS < 4 ? g[3] : 1.0))) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
             }
 #endif
 #pragma unroll
@@ -1777,17 +1784,22 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
 #pragma unroll
                         for (int l = 0; l < MDp; ++l) {
                             const double dD = MD ? dC * gD[l] : dC;
-                            const int x = i * SA + j * SB + k * SC + l;
-                            double t2 = (i + 1 < MA) ? R.b[x + SA] * eA : 0.0;      // old values: not yet overwritten
-                            if (MB && j + 1 < MB) t2 = fma(R.b[x + SB], eB[j], t2);
-                            if (MC && k + 1 < MC) t2 = fma(R.b[x + SC], eC[k], t2);
-                            if (MD && l + 1 < MD) t2 = fma(R.b[x + 1], eD[l], t2);
-                            R.b[x] = fma(R.b[x], dD, t2);                           // updateB, Core.hs:259
+#pragma unroll
+                            for (int m = 0; m < MEp; ++m) {
+                                const double dE = ME ? dD * gE[m] : dD;
+                                const int x = i * SA + j * SB + k * SC + l * SD + m;
+                                double t2 = (i + 1 < MA) ? R.b[x + SA] * eA : 0.0;      // old values: not yet overwritten
+                                if (MB && j + 1 < MB) t2 = fma(R.b[x + SB], eB[j], t2);
+                                if (MC && k + 1 < MC) t2 = fma(R.b[x + SC], eC[k], t2);
+                                if (MD && l + 1 < MD) t2 = fma(R.b[x + SD], eD[l], t2);
+                                if (ME && m + 1 < ME) t2 = fma(R.b[x + 1], eE[m], t2);
+                                R.b[x] = fma(R.b[x], dE, t2);                           // updateB, Core.hs:259
+                            }
                         }
                     }
                 }
             }
-            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);       // updateD, Core.hs:282-288
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);           // updateD, Core.hs:282-288
         }
         rc_cp_wait<RC_PDEPTH - 2>();
         __syncthreads();
@@ -1795,14 +1807,18 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs& R, const unsigned sBase, c
     }
 }
 
-// shapes the planner admits (pat_shape in rc_plan.cpp): MA >= MB >= MC >= MD, each of B, C, D absent (0) or >= 2, product of
-// the present ones <= RC_PAT_MAXS
-template <int MB, int MC, int MD>
-__device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
+// shapes the planner admits (pat_shape in rc_plan.cpp): MA >= MB >= MC >= MD >= ME, each of B..E absent (0) or >= 2, product
+// of the present ones <= MAXS; the large-pattern instantiation only receives the shapes the small one does not hold
+template <int MB, int MC, int MD, int ME, int MAXS>
+__device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                                   unsigned& slot, const unsigned reSlot, const int MA) {
-    constexpr int SA = (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
-#define RC_PAT_CASE(A) \
-    case A: if constexpr (A >= MB && A * SA <= RC_PAT_MAXS) { rc_pat_run<A, MB, MC, MD>(R, sBase, strideD, s, nextStop, slot, reSlot); } break;
+    constexpr int SA = (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1) * (ME ? ME : 1);
+#define RC_PAT_CASE(A)                                                                                         \
+    case A:                                                                                                    \
+        if constexpr (A >= MB && A * SA <= MAXS && (MAXS == RC_PAT_MAXS || A * SA > RC_PAT_MAXS)) {            \
+            rc_pat_run<A, MB, MC, MD, ME>(R, sBase, strideD, s, nextStop, slot, reSlot);                       \
+        }                                                                                                      \
+        break;
     switch (MA) {
         RC_PAT_CASE(1) RC_PAT_CASE(2) RC_PAT_CASE(3) RC_PAT_CASE(4) RC_PAT_CASE(5)
         RC_PAT_CASE(6) RC_PAT_CASE(7) RC_PAT_CASE(8) RC_PAT_CASE(9) RC_PAT_CASE(10)
@@ -1815,7 +1831,11 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs& R, const unsigned s
 #ifndef RC_PAT_MINB
 #define RC_PAT_MINB 7      // measured on C3: 6 -> 16.9 ms, 7 -> 16.2, 8 -> 16.6, 10 -> 18.2 (spills)
 #endif
-__global__ void __launch_bounds__(RC_PBLOCK, RC_PAT_MINB)
+#ifndef RC_PATL_MINB
+#define RC_PATL_MINB 5
+#endif
+template <int MAXS>
+__global__ void __launch_bounds__(RC_PBLOCK, MAXS <= RC_PAT_MAXS ? RC_PAT_MINB : RC_PATL_MINB)
 rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                         const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
@@ -1836,9 +1856,9 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int sShort = models[b].sShort;
     const RcModelEpochDev mE = mep[models[b].mepOff + e];
 
-    RcPatRegs R;
+    RcPatRegs<MAXS> R;
 #pragma unroll
-    for (int x = 0; x < RC_PAT_MAXS; ++x) R.b[x] = 0.0;
+    for (int x = 0; x < MAXS; ++x) R.b[x] = 0.0;
     R.on = tid < np;
     R.unit = false;
     R.dacc = 0.0;
@@ -1871,12 +1891,13 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     };
     // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory (the ring starts
     //      afterwards: it lives in the same bytes) ----
-    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la;
+    uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la, ld = la;
     if (R.on) {
-        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + 3 * (size_t)tid;
+        const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + (RC_PLANE_N / 4) * (size_t)tid;
         la = lane[0];
         lb = lane[1];
         lc = lane[2];
+        ld = lane[3];
     }
     {
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
@@ -1894,27 +1915,27 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
                 if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
         }
     }
-    const unsigned shape = la.z & 0xFFFFu;          // MA | MB << 4 | MC << 8 | MD << 12
-    const int MA = (int)(shape & 0xFu), MB = (int)((shape >> 4) & 0xFu), MC = (int)((shape >> 8) & 0xFu), MD = (int)((shape >> 12) & 0xFu);
-    const int n = MA * (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1);
+    const unsigned shape = la.z & 0xFFFFFu;         // MA | MB << 4 | MC << 8 | MD << 12 | ME << 16
+    int n = (int)(shape & 0xFu);
+#pragma unroll
+    for (int q = 1; q < 5; ++q) n *= max(1, (int)((shape >> (4 * q)) & 0xFu));
     const int pid = (int)lb.x;
     double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
     R.rows64 = (unsigned long long)la.x | ((unsigned long long)la.y << 32);
-    R.nU = (int)((la.z >> 16) & 0xFu);
-    R.unit = R.on && MB == 0 && R.nU == 0;          // x = e_A is the first state of a single-branch pattern
     __syncthreads();
     if (R.on) {
-        const double* mine = bb + (la.z >> 20);
+        const double* mine = bb + lb.y;
 #pragma unroll
-        for (int x = 0; x < RC_PAT_MAXS; ++x)
+        for (int x = 0; x < MAXS; ++x)
             if (x < n) R.b[x] = mine[x];
     }
-    // the block's shape: bins hold one (MA, MB) class
+    // the block's shape and number of unit branches: bins hold one class
     __shared__ unsigned shapeS;
-    if (tid == 0) shapeS = la.z & 0xFFFFFu;         // shape and number of unit branches: one class per bin
+    if (tid == 0) shapeS = la.z;
     __syncthreads();
-    const unsigned shapeB = shapeS & 0xFFFFu;
-    R.nU = (int)(shapeS >> 16);
+    const unsigned shapeB = shapeS & 0xFFFFFu;
+    R.nU = (int)((shapeS >> 20) & 0xFu);
+    R.unit = R.on && (shapeB >> 4) == 0 && R.nU == 0;        // x = e_A is the first state of a single-branch pattern
     const int MAw = (int)(shapeB & 0xFu);
 
     bool finished = false, parked = false;
@@ -1928,18 +1949,18 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
             ring_start();
             rc_cp_wait<RC_PDEPTH - 2>();
             __syncthreads();
-            switch (shapeB >> 4) {          // MB | MC << 4 | MD << 8
-                case 0x000: rc_pat_dispatch_a<0, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x002: rc_pat_dispatch_a<2, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x003: rc_pat_dispatch_a<3, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x004: rc_pat_dispatch_a<4, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x005: rc_pat_dispatch_a<5, 0, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x022: rc_pat_dispatch_a<2, 2, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x023: rc_pat_dispatch_a<3, 2, 0>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                case 0x222: rc_pat_dispatch_a<2, 2, 2>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
-                default: break;             // no other shape has a product <= RC_PAT_MAXS
+#define RC_PAT_SHAPE(code, B, C, D, E) \
+    case code: rc_pat_dispatch_a<B, C, D, E>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
+            switch (shapeB >> 4) {          // MB | MC << 4 | MD << 8 | ME << 12
+                RC_PAT_SHAPE(0x0000, 0, 0, 0, 0) RC_PAT_SHAPE(0x0002, 2, 0, 0, 0) RC_PAT_SHAPE(0x0003, 3, 0, 0, 0)
+                RC_PAT_SHAPE(0x0004, 4, 0, 0, 0) RC_PAT_SHAPE(0x0005, 5, 0, 0, 0) RC_PAT_SHAPE(0x0006, 6, 0, 0, 0)
+                RC_PAT_SHAPE(0x0022, 2, 2, 0, 0) RC_PAT_SHAPE(0x0023, 3, 2, 0, 0) RC_PAT_SHAPE(0x0024, 4, 2, 0, 0)
+                RC_PAT_SHAPE(0x0033, 3, 3, 0, 0) RC_PAT_SHAPE(0x0222, 2, 2, 2, 0) RC_PAT_SHAPE(0x0223, 3, 2, 2, 0)
+                RC_PAT_SHAPE(0x2222, 2, 2, 2, 2)
+                default: break;             // no other shape has a product <= RC_PAT_MAXL
             }
-            static_assert(RC_PAT_MAXS == 25, "shape list above");
+#undef RC_PAT_SHAPE
+            static_assert(RC_PAT_MAXS == 25 && RC_PAT_MAXL == 36, "shape list above");
             rc_cp_wait<0>();
             __syncthreads();
         }
@@ -1982,9 +2003,9 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (!isLast) {
         // ---- hand b and the updateD sums to the next epoch's launch ----
         double* out = bCur + (size_t)b * bStride + la.w;
-        const unsigned refW[7] = {lb.y, lb.z, lb.w, lc.x, lc.y, lc.z, lc.w};
+        const unsigned refW[9] = {lb.z, lb.w, lc.x, lc.y, lc.z, lc.w, ld.x, ld.y, ld.z};
 #pragma unroll
-        for (int x = 0; x < RC_PAT_MAXS; ++x)
+        for (int x = 0; x < MAXS; ++x)
             if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
         dAcc[(size_t)b * nPat + pid] = dp;
         return;
@@ -2126,7 +2147,13 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
         // ring of RC_PDEPTH slots sized for the group's largest fetch list, aliased with the gathered b of the largest bin
         const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
         const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
-        rc_propagate_pat_kernel<<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        rc_propagate_pat_kernel<RC_PAT_MAXS><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        return cudaGetLastError();
+    }
+    if (rowMode == 4) {
+        const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
+        const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
+        rc_propagate_pat_kernel<RC_PAT_MAXL><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return cudaGetLastError();
     }
     if (rowMode) {

@@ -445,17 +445,18 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
 }  // namespace
 
 // Pattern mode: shape of a box-shaped live set whose states all fit the registers of one thread.  A = the row branch (the
-// widest), then up to three more branches with m >= 2 in descending order (B, C, D); every other non-zero branch has
-// m = 1 and only contributes a decay factor.  Returns MA | MB << 4 | MC << 8 | MD << 12, or 0 if the pattern does not
-// qualify; dims (optional) receives the branch ids in the kernel's order: A, B.., then the m = 1 branches.
-static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int* dims = nullptr, int* nShaped = nullptr, int* nUnit = nullptr) {
+// widest), then up to four more branches with m >= 2 in descending order (B, C, D, E); every other non-zero branch has
+// m = 1 and only contributes a decay factor.  Returns MA | MB << 4 | MC << 8 | MD << 12 | ME << 16, or 0 if the pattern has
+// more than maxStates states or does not qualify; dims (optional) receives the branch ids in the kernel's order: A, B..,
+// then the m = 1 branches.
+static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int maxStates, int* dims = nullptr, int* nShaped = nullptr, int* nUnit = nullptr) {
     const int MA = mx[rk];
     if (MA < 1 || MA > RC_ROW_MAXM) return 0;
-    int sh[3] = {0, 0, 0}, shK[3] = {0, 0, 0}, nS = 0, nU = 0, un[RC_MAX_P];
+    int sh[4] = {0, 0, 0, 0}, shK[4] = {0, 0, 0, 0}, nS = 0, nU = 0, un[RC_MAX_P];
     for (int k = 0; k < P; ++k) {
         if (k == rk || !mx[k]) continue;
         if (mx[k] == 1) { un[nU++] = k; continue; }
-        if (nS == 3) return 0;
+        if (nS == 4) return 0;
         int q = nS++;
         while (q > 0 && sh[q - 1] < mx[k]) { sh[q] = sh[q - 1]; shK[q] = shK[q - 1]; --q; }     // descending, stable in k
         sh[q] = mx[k];
@@ -463,7 +464,7 @@ static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int* dims = nullptr,
     }
     long long prod = MA;
     for (int q = 0; q < nS; ++q) prod *= sh[q];
-    if (prod > RC_PAT_MAXS || 1 + nS + nU > 8 || (nS && sh[0] > MA)) return 0;
+    if (prod > maxStates || 1 + nS + nU > 8 || (nS && sh[0] > MA)) return 0;
     if (dims) {
         dims[0] = rk;
         for (int q = 0; q < nS; ++q) dims[1 + q] = shK[q];
@@ -471,7 +472,7 @@ static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int* dims = nullptr,
     }
     if (nShaped) *nShaped = nS;
     if (nUnit) *nUnit = nU;
-    return (uint32_t)MA | ((uint32_t)sh[0] << 4) | ((uint32_t)sh[1] << 8) | ((uint32_t)sh[2] << 12);
+    return (uint32_t)MA | ((uint32_t)sh[0] << 4) | ((uint32_t)sh[1] << 8) | ((uint32_t)sh[2] << 12) | ((uint32_t)sh[3] << 16);
 }
 
 // Bin images of the keyed tier (record layouts in rc_types.h).  Everything the set-up of a block used to look up through
@@ -484,8 +485,8 @@ static std::string build_bin_images(PlanHost& out) {
     out.kPatRec.assign(out.kBinPats.size() * 2, 0);
     out.kLane.clear();
     out.kElem.clear();
-    out.grpMaxFetch.assign((size_t)out.nEpochs * 2, 0);
-    out.grpMaxB.assign((size_t)out.nEpochs * 2, 0);
+    out.grpMaxFetch.assign((size_t)out.nEpochs * RC_NGROUP, 0);
+    out.grpMaxB.assign((size_t)out.nEpochs * RC_NGROUP, 0);
     if (out.kBinBase.empty()) return "";
     if (out.maxEpochSlots >= (1LL << RC_IMG_CNT_SHIFT)) return "too many live states in one epoch for the keyed tier";
     if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
@@ -505,9 +506,10 @@ static std::string build_bin_images(PlanHost& out) {
         r1 = (uint32_t)out.slotOff[(size_t)(e - 1) * (nPat + 1) + i] | ((uint32_t)(b - a) << RC_IMG_CNT_SHIFT);
         return true;
     };
-    for (int v = 0; v < nE * 2; ++v) {
-        const int e = v / 2;
-        const bool rows = out.epochMode[(size_t)v] != 0, patM = out.epochMode[(size_t)v] == 3;
+    for (int v = 0; v < nE * RC_NGROUP; ++v) {
+        const int e = v / RC_NGROUP;
+        const bool rows = out.epochMode[(size_t)v] != 0, patM = out.epochMode[(size_t)v] >= 3;
+        const int patMax = out.epochMode[(size_t)v] == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
         const int b0 = out.kBinBase[(size_t)v];
@@ -529,18 +531,19 @@ static std::string build_bin_images(PlanHost& out) {
                 out.kPatRec[(size_t)q * 2] = i;
                 out.kPatRec[(size_t)q * 2 + 1] = lanes | (bOff << 16);
                 if (patM) {
-                    // pattern mode: one lane per pattern; state (x_A, x_B, x_C, x_D) sits at the mixed-radix position
-                    // (((x_A - 1) MB' + x_B - 1) MC' + x_C - 1) MD' + x_D - 1 with M' = max(M, 1)
+                    // pattern mode: one lane per pattern; its states in mixed-radix order over (A, B, C, D, E), see rc_types.h
                     const uint32_t pr = out.patRow[(size_t)e * nPat + i];
                     const int rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
                     int dims[8], nS = 0, nU = 0;
-                    const uint32_t shape = pat_shape(&out.maxX[((size_t)e * nPat + i) * P], P, rk, dims, &nS, &nU);
+                    const uint32_t shape = pat_shape(&out.maxX[((size_t)e * nPat + i) * P], P, rk, patMax, dims, &nS, &nU);
                     if (!shape) return "pattern-mode bin with an unsuitable pattern";
                     const int MA = (int)(shape & 0xFu);
-                    const int Mp[3] = {std::max(1, (int)((shape >> 4) & 0xFu)), std::max(1, (int)((shape >> 8) & 0xFu)), std::max(1, (int)((shape >> 12) & 0xFu))};
-                    const int SA = Mp[0] * Mp[1] * Mp[2], nr = ro[i + 1] - ro[i];
+                    int Mp[4];
+                    for (int q = 0; q < 4; ++q) Mp[q] = std::max(1, (int)((shape >> (4 * (q + 1))) & 0xFu));
+                    const int SA = Mp[0] * Mp[1] * Mp[2] * Mp[3], nr = ro[i + 1] - ro[i];
                     if (MA * SA != live || nr != SA || NO != nS + nU) return "pattern-mode image: shape does not match the live set";
-                    uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t rec[RC_PLANE_N];
+                    for (int q = 0; q < RC_PLANE_N; ++q) rec[q] = 0u;
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t row = q < 1 + nS + nU ? (uint32_t)rb[dims[q]] : (uint32_t)(RC_KROWS - 1);
                         if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
@@ -549,26 +552,27 @@ static std::string build_bin_images(PlanHost& out) {
                     std::vector<uint32_t> el((size_t)live * 2, 0u);
                     for (int r = 0; r < nr; ++r) {
                         const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
-                        int xs[3] = {1, 1, 1};
+                        int xs[4] = {1, 1, 1, 1};
                         for (int d = 0; d < NO; ++d) {
                             const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
                             const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
                             for (int q = 0; q < nS; ++q) if (dims[1 + q] == k) xs[q] = x;
                         }
-                        const int other = ((xs[0] - 1) * Mp[1] + (xs[1] - 1)) * Mp[2] + (xs[2] - 1);
+                        const int other = (((xs[0] - 1) * Mp[1] + (xs[1] - 1)) * Mp[2] + (xs[2] - 1)) * Mp[3] + (xs[3] - 1);
                         if (other < 0 || other >= SA) return "pattern-mode image out of range (other index)";
                         for (int a = 0; a < MA; ++a) {
                             const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + a], idx = a * SA + other;
                             if (ref > 0xFF) return "pattern-mode image out of range (state index)";
-                            rec[5 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
+                            rec[6 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
                             if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
                         }
                     }
-                    if (bOff >= (1 << 12)) return "pattern-mode image out of range (element offset)";
-                    rec[2] = shape | ((uint32_t)nU << 16) | ((uint32_t)bOff << 20);
+                    static_assert(6 * 4 + RC_PAT_MAXL <= RC_PLANE_N * 4, "state indices fit the lane record");
+                    rec[2] = shape | ((uint32_t)nU << 20);
                     rec[3] = (uint32_t)so[i];
                     rec[4] = (uint32_t)i;
-                    out.kLane.insert(out.kLane.end(), rec, rec + RC_RLANE_N);
+                    rec[5] = (uint32_t)bOff;
+                    out.kLane.insert(out.kLane.end(), rec, rec + RC_PLANE_N);
                     out.kElem.insert(out.kElem.end(), el.begin(), el.end());
                     lanes += 1;
                     bOff += live;
@@ -855,14 +859,15 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // mode: 0 one state per lane, 1 one row per lane, 3 one pattern per lane (bins of one cost class only)
         auto pack_range = [&](int e0, int e1, int maxPats, int mode, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
-            const bool rowMode = mode != 0, patMode = mode == 3;
+            const bool rowMode = mode != 0, patMode = mode >= 3;
+            const int patMaxStates = mode == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
             auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
             auto clsOf = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
                 if (patMode) {
                     int nU = 0;
-                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0], nullptr, nullptr, &nU);
-                    return (int)(sh | ((uint32_t)nU << 16));      // blocks are uniform in shape and in the number of unit branches
+                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0], patMaxStates, nullptr, nullptr, &nU);
+                    return (int)(sh | ((uint32_t)nU << 20));      // blocks are uniform in shape and in the number of unit branches
                 }
                 if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
                 int c = 0;
@@ -1005,22 +1010,27 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         // Two bin groups per epoch (index 2e + g): g = 0 the patterns small enough for one thread each (pattern mode), g = 1
         // the rest in row mode (all boxes with rows long enough) or state mode.
-        out.kBinBase.assign((size_t)nEpochs * 2, 0);
-        out.nKBins.assign((size_t)nEpochs * 2, 0);
-        out.epochMode.assign((size_t)nEpochs * 2, 0);
+        out.kBinBase.assign((size_t)nEpochs * RC_NGROUP, 0);
+        out.nKBins.assign((size_t)nEpochs * RC_NGROUP, 0);
+        out.epochMode.assign((size_t)nEpochs * RC_NGROUP, 0);
         out.rowOff.assign((size_t)nEpochs * (nPat + 1), 0);
         out.rowEpochBase.assign((size_t)nEpochs, 0);
         out.patRow.assign((size_t)nEpochs * nPat, 0u);
         out.patRowStride.assign((size_t)nEpochs * nPat, 0);
         const char* rowEnv = std::getenv("RC_ROWMODE");
         static const bool patEnv = std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true;
-        std::vector<std::vector<int>> groupIds((size_t)nEpochs * 2);
+        static const bool patLEnv = std::getenv("RC_PATLARGE") ? std::atoi(std::getenv("RC_PATLARGE")) != 0 : true;
+        std::vector<std::vector<int>> groupIds((size_t)nEpochs * RC_NGROUP);
         for (int e = 0; e < nEpochs; ++e) {
-            std::vector<int>& patIds = groupIds[(size_t)e * 2];
-            std::vector<int>& restIds = groupIds[(size_t)e * 2 + 1];
+            std::vector<int>& patIds = groupIds[(size_t)e * RC_NGROUP];
+            std::vector<int>& patLIds = groupIds[(size_t)e * RC_NGROUP + 1];
+            std::vector<int>& restIds = groupIds[(size_t)e * RC_NGROUP + 2];
             for (int i : order) {
-                const bool small = patEnv && pps[(size_t)i].rowOK[(size_t)e] && pps[(size_t)i].fullBox[(size_t)e] && pat_shape(&pps[(size_t)i].mx[(size_t)e * P], P, pps[(size_t)i].rowK[(size_t)e]) != 0;
-                (small ? patIds : restIds).push_back(i);
+                const PatPlan& pp = pps[(size_t)i];
+                const bool box = patEnv && pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
+                if (box && pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], RC_PAT_MAXS) != 0) patIds.push_back(i);
+                else if (box && patLEnv && pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], RC_PAT_MAXL) != 0) patLIds.push_back(i);
+                else restIds.push_back(i);
             }
             bool all = !restIds.empty();
             long long rows = 0, states = 0;
@@ -1034,10 +1044,11 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
             bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
             if (rowEnv) use = all && std::atoi(rowEnv) != 0;
-            out.epochMode[(size_t)e * 2] = 3;
-            out.epochMode[(size_t)e * 2 + 1] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
+            out.epochMode[(size_t)e * RC_NGROUP] = 3;
+            out.epochMode[(size_t)e * RC_NGROUP + 1] = 4;
+            out.epochMode[(size_t)e * RC_NGROUP + 2] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
-            if (use || !patIds.empty()) {
+            if (use || !patIds.empty() || !patLIds.empty()) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
                 long long run = 0;
                 for (int i = 0; i < nPat; ++i) {
@@ -1058,20 +1069,20 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ro[nPat] = (int)run;
             }
         }
-        for (int v = 0; v < nEpochs * 2; ++v) {
-            const int e = v / 2, mode = out.epochMode[(size_t)v];
+        for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
+            const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
             out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
             if (!groupIds[(size_t)v].empty()) {
-                if (mode == 3) pack_range(e, e, RC_PBLOCK, 3, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
                 else if (mode) pack_range(e, e, RC_NPBR, 1, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
                 else pack_range(e, e, RC_NPB, 0, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
             }
             out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
         }
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
-        for (int v = 0; v < nEpochs * 2; ++v) {
-            const int e = v / 2, b0 = out.kBinBase[(size_t)v];
+        for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
+            const int e = v / RC_NGROUP, b0 = out.kBinBase[(size_t)v];
             // fetch offsets are stored at the same index as the bin offsets (one extra entry per group)
             std::vector<int> fOff;
             fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0);
@@ -1079,14 +1090,14 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
         if (std::getenv("RC_PLAN_DEBUG")) {
-            for (int v = 0; v < nEpochs * 2; ++v) {
-                const int e = v / 2, m = out.epochMode[(size_t)v];
+            for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
+                const int e = v / RC_NGROUP, m = out.epochMode[(size_t)v];
                 const PlanHost::Epoch& E = out.ep[(size_t)e];
                 int b0 = out.kBinBase[(size_t)v], nb = out.nKBins[(size_t)v];
                 if (!nb) continue;
                 int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
                 std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s patterns %d bins %d fetch rows/bin %.1f\n", e,
-                             E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
+                             E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns" : m == 4 ? "patterns (large)" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
                              (double)(f1 - f0) / nb);
             }
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
@@ -1218,11 +1229,11 @@ std::string check_plan(const PlanHost& h) {
     // keyed per-epoch bins
     if (!h.kBinBase.empty()) {
         std::vector<char> seen;
-        for (int v = 0; v < nE * 2; ++v) {
-            const int e = v / 2;
+        for (int v = 0; v < nE * RC_NGROUP; ++v) {
+            const int e = v / RC_NGROUP;
             const PlanHost::Epoch& E = h.ep[(size_t)e];
-            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] == 3;
-            if (v % 2 == 0) seen.assign((size_t)nPat, 0);
+            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] >= 3;
+            if (v % RC_NGROUP == 0) seen.assign((size_t)nPat, 0);
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
@@ -1280,18 +1291,19 @@ std::string check_plan(const PlanHost& h) {
             const long long hi = e < nE - 1 ? h.trEntBase[(size_t)e] : (long long)h.trEnt.size();
             return (long long)r0 >= lo && (long long)r0 + cnt <= hi && prev < h.epochSlots[(size_t)e - 1];
         };
-        for (int v = 0; v < nE * 2; ++v) {
-            const int e = v / 2;
-            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] == 3;
+        for (int v = 0; v < nE * RC_NGROUP; ++v) {
+            const int e = v / RC_NGROUP;
+            const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] >= 3;
+            const int patMax = h.epochMode[(size_t)v] == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
                 const int np = hdr[1], lanes = hdr[2], nB = hdr[3], nFetch = hdr[5];
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
-                if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * RC_PAT_MAXS : RC_ROW_BCAP))
+                if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * patMax : RC_ROW_BCAP))
                     return fail("image header lanes");
-                if (hdr[6] < 0 || hdr[6] + (long long)lanes * (rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)
+                if (hdr[6] < 0 || hdr[6] + (long long)lanes * (patM ? RC_PLANE_N / 4 : rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)
                     return fail("image record range");
                 for (int q = 0; q < np; ++q) {
                     const int rec = h.kPatRec[(size_t)(hdr[0] + q) * 2 + 1];
@@ -1299,13 +1311,15 @@ std::string check_plan(const PlanHost& h) {
                     if ((rec & 0xFFFF) >= lanes || (rec >> 16) > nB) return fail("image pattern offsets");
                 }
                 for (int t = 0; t < lanes; ++t) {
-                    const uint32_t* r = &h.kLane[(size_t)hdr[6] * 4 + (size_t)t * (rows ? RC_RLANE_N : RC_LANE_N)];
+                    const uint32_t* r = &h.kLane[(size_t)hdr[6] * 4 + (size_t)t * (patM ? RC_PLANE_N : rows ? RC_RLANE_N : RC_LANE_N)];
                     if (patM) {
-                        const int M[4] = {(int)(r[2] & 0xFu), (int)((r[2] >> 4) & 0xFu), (int)((r[2] >> 8) & 0xFu), (int)((r[2] >> 12) & 0xFu)};
-                        const int nU = (int)((r[2] >> 16) & 0xFu), eOff = (int)(r[2] >> 20);
+                        int M[5];
+                        for (int q = 0; q < 5; ++q) M[q] = (int)((r[2] >> (4 * q)) & 0xFu);
+                        const int nU = (int)((r[2] >> 20) & 0xFu), eOff = (int)r[5];
                         int n = M[0], nS = 0;
-                        for (int q = 1; q < 4; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1]) return fail("image pattern shape order"); }
-                        if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > RC_PAT_MAXS || 1 + nS + nU > 8) return fail("image pattern shape");
+                        for (int q = 1; q < 5; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1] || nS != q) return fail("image pattern shape order"); }
+                        if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > patMax || 1 + nS + nU > 8) return fail("image pattern shape");
+                        if (patMax == RC_PAT_MAXL && n <= RC_PAT_MAXS) return fail("small pattern in the large-pattern group");
                         for (int q = 0; q < 8; ++q) {
                             const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
                             const int len = q <= nS ? M[q] : 1;
@@ -1316,7 +1330,7 @@ std::string check_plan(const PlanHost& h) {
                         if (live != n || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
                         std::vector<char> hit((size_t)n, 0);
                         for (int q = 0; q < n; ++q) {
-                            const int ref = (int)((r[5 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
+                            const int ref = (int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
                             if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
                             hit[(size_t)ref] = 1;
                         }

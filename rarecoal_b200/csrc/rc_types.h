@@ -18,6 +18,9 @@
 #define RC_ROW_NO 7          // other non-zero branches of a row at most
 #define RC_PBLOCK 64         // pattern mode: threads (= patterns) per block
 #define RC_PAT_MAXS 25       // pattern mode: live states of a pattern at most (all in the registers of one thread)
+#define RC_PAT_MAXL 36       // same, second instantiation of the pattern kernel for the larger boxes (fewer resident blocks)
+#define RC_NGROUP 3          // bin groups per epoch: small patterns, large patterns (one thread each), the rest (rows or states)
+#define RC_PLANE_N 16        // words of a pattern-mode lane record
 #define RC_ROW_SUM 11        // with more than 3 other branches: other branches + row length <= RC_ROW_SUM (bounds the kernel variants)
 #define RC_ROW_MAXM 10       // longest row
 #define RC_ROW_BCAP 1536     // states per row-mode block at most (rows are stored with an odd stride: no bank conflicts)
@@ -97,7 +100,7 @@ struct RcPlanDev {
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
     // ---- row mode ----
-    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; 3: one pattern per thread
+    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXS (3) or <= RC_PAT_MAXL (4) states
     const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
     const long long* rowEpochBase; // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states
@@ -123,13 +126,13 @@ struct RcPlanDev {
 //               [3..6] b offsets in doubles (8 x u16): own row, then the neighbour row along each other branch
 //                      (RC_ROW_BCAP = the always-zero row)
 //               [7] first slot of the pattern in the epoch  [8] row index in rowRefAll  [9] pattern id  [10..11] 0
-//   pattern mode (RC_RLANE_N words; one lane = one pattern, its states at the mixed-radix position
-//               (((x_A - 1) MB' + x_B - 1) MC' + x_C - 1) MD' + x_D - 1, M' = max(M, 1)):
+//   pattern mode (RC_PLANE_N words; one lane = one pattern, its states at the mixed-radix position
+//               ((((x_A - 1) MB' + x_B - 1) MC' + x_C - 1) MD' + x_D - 1) ME' + x_E - 1, M' = max(M, 1)):
 //               [0..1] pair row of x = 1 of every non-zero branch (8 x u8): A, the shaped branches B.., then the m = 1 branches
-//               [2] MA | MB << 4 | MC << 8 | MD << 12 | number of m = 1 branches << 16 | first b double of the pattern in the bin << 20
-//               [3] first slot of the pattern in the epoch  [4] pattern id
-//               [5..11] reference-order index of every state (25 x u8)
-//   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row or pattern lane).
+//               [2] MA | MB << 4 | MC << 8 | MD << 12 | ME << 16 | number of m = 1 branches << 20
+//               [3] first slot of the pattern in the epoch  [4] pattern id  [5] first b double of the pattern in the bin
+//               [6..14] reference-order index of every state (36 x u8)
+//   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row lane, 4 per pattern lane).
 // Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
 // and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
 #define RC_LANE_N 8
