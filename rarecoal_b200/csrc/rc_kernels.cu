@@ -1832,7 +1832,7 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsi
 #define RC_PAT_MINB 7      // measured on C3: 6 -> 16.9 ms, 7 -> 16.2, 8 -> 16.6, 10 -> 18.2 (spills)
 #endif
 #ifndef RC_PATL_MINB
-#define RC_PATL_MINB 5
+#define RC_PATL_MINB 6
 #endif
 template <int MAXS>
 __global__ void __launch_bounds__(RC_PBLOCK, MAXS <= RC_PAT_MAXS ? RC_PAT_MINB : RC_PATL_MINB)
