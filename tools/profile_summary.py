@@ -11,9 +11,14 @@ if rep.endswith(".csv"):
 else:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 raw = raw[raw.index('"ID"'):]
-open(os.path.join(ROOT, "profiles", "r01_propagate_raw.csv"), "w").write(raw)
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, body = rows[0], rows[1], rows[2:]
+if len(sys.argv) > 2:      # e.g. "10-13,0-9": the launches of one evaluation when the capture window straddles two
+    pick = []
+    for part in sys.argv[2].split(","):
+        a, _, b = part.partition("-")
+        pick += list(range(int(a), int(b or a) + 1))
+    body = [body[i] for i in pick]
 ix = {h: i for i, h in enumerate(hdr)}
 
 
@@ -27,6 +32,9 @@ def scale(v, u):
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
 
+with open(os.path.join(ROOT, "profiles", "r01_propagate_raw.csv"), "w", newline="") as f:
+    w = csv.writer(f, quoting=csv.QUOTE_ALL)
+    w.writerows([hdr, units] + body)
 rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
 tot_r = sum(scale(r[rd], units[rd]) for r in body)
 tot_w = sum(scale(r[wr], units[wr]) for r in body)
@@ -37,7 +45,7 @@ names = {"ms": "gpu__time_duration.sum", "smem": "l1tex__data_pipe_lsu_wavefront
 
 def kind(r):
     n = r[ix["Kernel Name"]]
-    return "pattern" if "_pat_" in n else "rows" if "rows" in n else "states"
+    return ("pattern<36>" if "168" == r[col(names["regs"])] else "pattern<25>") if "_pat_" in n else "rows" if "rows" in n else "states"
 
 
 ms = [float(r[col(names["ms"])]) for r in body]
@@ -47,8 +55,9 @@ share = {}
 for r, m in zip(body, ms):
     share[kind(r)] = share.get(kind(r), 0.0) + m / tms
 json.dump({
-    "kernels": "the propagation launches of one evaluation: per structural epoch rc_propagate_pat_kernel (one pattern per thread) and, "
-               "for the patterns with more than 25 live states, rc_propagate_rows_kernel",
+    "kernels": "the propagation launches of one evaluation: per structural epoch rc_propagate_pat_kernel<25> (one pattern per thread, "
+               "boxes of at most 25 live states) and rc_propagate_pat_kernel<36> (26-36 states); rc_propagate_rows_kernel / "
+               "rc_propagate_keyed_kernel take what is left (nothing on C3)",
     "launch": "C3, 44 models per evaluation (bench.py default); %d launches" % len(body),
     "dram_bytes_read": int(tot_r), "dram_bytes_write": int(tot_w), "dram_bytes_total": int(tot_r + tot_w),
     "algorithmic_hbm_bytes": 46207392,
