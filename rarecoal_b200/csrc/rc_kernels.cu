@@ -1759,7 +1759,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
 #pragma unroll
                 for (int j = 0; j < MEp; ++j) rc_lds128(aE + slot + (unsigned)j * 16u, gE[j], eE[j]);
             }
-            double D1 = 1.0;                     // branches with m = 1: G_k(1) only; nU is the same for the whole block
+            double D1 = 1.0;                     // branches with m = 1: G_k(1) only
 #if RC_PAT_NU_MODE == 0
             for (int u = 0; u < R.nU; ++u) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
 #else
@@ -1934,7 +1934,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (tid == 0) shapeS = la.z;
     __syncthreads();
     const unsigned shapeB = shapeS & 0xFFFFFu;
-    R.nU = (int)((shapeS >> 20) & 0xFu);
+    R.nU = (int)((la.z >> 20) & 0xFu);                       // per lane: the unit branches are loaded under a predicate
     R.unit = R.on && (shapeB >> 4) == 0 && R.nU == 0;        // x = e_A is the first state of a single-branch pattern
     const int MAw = (int)(shapeB & 0xFu);
 

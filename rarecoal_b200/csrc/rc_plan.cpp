@@ -857,7 +857,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // measured on C3 (44 models): 36.7 ms with lexicographic bins, 33.4 ms with cost-class bins; RC_BINSORT=0 restores the former
         const bool binSort = std::getenv("RC_BINSORT") ? std::atoi(std::getenv("RC_BINSORT")) != 0 : true;
         // mode: 0 one state per lane, 1 one row per lane, 3 one pattern per lane (bins of one cost class only)
-        auto pack_range = [&](int e0, int e1, int maxPats, int mode, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
+        auto pack_range = [&](int e0, int e1, int maxPats, int mode, bool keyedBins, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
             const bool rowMode = mode != 0, patMode = mode >= 3;
             const int patMaxStates = mode == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
@@ -867,7 +867,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 if (patMode) {
                     int nU = 0;
                     const uint32_t sh = pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0], patMaxStates, nullptr, nullptr, &nU);
-                    return (int)(sh | ((uint32_t)nU << 20));      // blocks are uniform in shape and in the number of unit branches
+                    static const bool nuClass = std::getenv("RC_PAT_NUCLASS") ? std::atoi(std::getenv("RC_PAT_NUCLASS")) != 0 : false;
+                    return (int)(sh | (nuClass ? (uint32_t)nU << 20 : 0u));   // blocks are uniform in shape (the unrolled update)
                 }
                 if (rowMode) return pp.rowNO[(size_t)e0] * 64 + pp.rowM[(size_t)e0];
                 int c = 0;
@@ -920,7 +921,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         if (mxk > have) add[(size_t)q] += mxk - have;
                     }
                     if (ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
-                    if (ob.rowsSelf[(size_t)q] + addSelf[(size_t)q] > 2 * fastBlock - 2) return false;
+                    // (pair rows without de-duplication: a limit of the self-contained kernel's rate table only)
+                    if (!keyedBins && ob.rowsSelf[(size_t)q] + addSelf[(size_t)q] > 2 * fastBlock - 2) return false;
                 }
                 for (int q = 0; q < nE; ++q) {
                     const int e = e0 + q;
@@ -946,6 +948,35 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             std::vector<int> ord(ids);
             if (nE == 1 && (binSort || patMode)) {
                 std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return clsOf(a) > clsOf(b); });
+                // Patterns with exactly two live branches (the last epochs of a tree): inside a shape class every pattern is a
+                // pair (key of A, key of B).  Lexicographic order keeps A fixed and walks through all B keys, so a bin of 64
+                // patterns needs ~64 distinct B keys; 8 x 8 tiles of the (A key, B key) grid need 16 keys.
+                static const bool tile = std::getenv("RC_PAT_TILE") ? std::atoi(std::getenv("RC_PAT_TILE")) != 0 : true;
+                if (patMode && tile) {
+                    auto two = [&](int i, int& ka, int& kb) {
+                        const PatPlan& pp = pps[(size_t)i];
+                        const int rk = pp.rowK[(size_t)e0];
+                        int other = -1, n = 0;
+                        for (int k = 0; k < P; ++k)
+                            if (pp.mx[(size_t)e0 * P + k] && k != rk) { other = k; ++n; }
+                        if (n != 1) return false;
+                        ka = out.keyId[((size_t)e0 * nPat + i) * P + rk];
+                        kb = out.keyId[((size_t)e0 * nPat + i) * P + other];
+                        return true;
+                    };
+                    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+                        const int ca = clsOf(a), cb = clsOf(b);
+                        if (ca != cb) return ca > cb;
+                        int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+                        const bool ta = two(a, a1, a2), tb = two(b, b1, b2);
+                        if (ta != tb) return ta;                        // a consistent order: two-branch patterns first,
+                        if (!ta) return false;                          // the others keep their lexicographic order
+                        if ((a1 >> 3) != (b1 >> 3)) return (a1 >> 3) < (b1 >> 3);
+                        if ((a2 >> 3) != (b2 >> 3)) return (a2 >> 3) < (b2 >> 3);
+                        if (a1 != b1) return a1 < b1;
+                        return a2 < b2;
+                    });
+                }
             }
             for (int i : ord) {
                 bool placed = false;
@@ -1005,7 +1036,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // (1) bins spanning all epochs (self-contained fast kernel)
         out.fBinPatOff.assign(1, 0);
         out.fBinPats.clear();
-        pack_range(0, nEpochs - 1, maxPatFast, 0, order, out.fBinPatOff, out.fBinPats);
+        pack_range(0, nEpochs - 1, maxPatFast, 0, false, order, out.fBinPatOff, out.fBinPats);
         out.nFastBins = (int)out.fBinPatOff.size() - 1;
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         // Two bin groups per epoch (index 2e + g): g = 0 the patterns small enough for one thread each (pattern mode), g = 1
@@ -1074,9 +1105,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
             if (!groupIds[(size_t)v].empty()) {
-                if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
-                else if (mode) pack_range(e, e, RC_NPBR, 1, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
-                else pack_range(e, e, RC_NPB, 0, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                else if (mode) pack_range(e, e, RC_NPBR, 1, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+                else pack_range(e, e, RC_NPB, 0, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
             }
             out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
         }
