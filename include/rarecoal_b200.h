@@ -141,6 +141,8 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
 /* Tuning switches (defaults in parentheses):
  *   "keyed" (1)            patterns of the fast tier go through the trajectory-key kernels when the table fits;
  *                          0 forces the self-contained kernels (used by the parity tests to cover both)
+ *   "pattern_mode" (1)     box-shaped live sets of at most 36 states run one pattern per thread; 0 sends every pattern
+ *                          to the row / state kernels (used by the parity tests to cover those kernels too)
  *   "ktab_model_mb" (1024) largest trajectory table of one model; a model above it uses the self-contained kernels
  *   "ktab_total_mb" (12288) largest trajectory table memory of one call                                   */
 int rc_set_option(rc_ctx* ctx, const char* name, double value);

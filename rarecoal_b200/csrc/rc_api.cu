@@ -138,6 +138,7 @@ struct rc_ctx {
     DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc;
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
+    int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
     double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
     PinBuf hBlob, hOut;
@@ -336,7 +337,7 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     *hit = false;
     PlanEntry* pe = new PlanEntry();
     std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
-                                   mh.hasSplit, ctx->smemOptin, pe->h);
+                                   mh.hasSplit, ctx->smemOptin, pe->h, ctx->optPattern);
     if (!e.empty()) {
         delete pe;
         ctx->err = e;
@@ -1038,6 +1039,17 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
     ctx->err.clear();
     std::string n(name);
     if (n == "keyed") ctx->optKeyed = value != 0.0;
+    else if (n == "pattern_mode") {
+        const int v = value != 0.0;
+        if (v != ctx->optPattern) {
+            // plans depend on it: finish what is queued, then drop them
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->trajStream);
+            ctx->clear_plans();
+            ctx->optPattern = v;
+        }
+    }
     else if (n == "ktab_model_mb") ctx->optKtabModelMB = value;
     else if (n == "ktab_total_mb") ctx->optKtabTotalMB = value;
     else { ctx->err = "rc_set_option: unknown option " + n; return RC_ERR_ARG; }

@@ -657,7 +657,7 @@ static std::string build_bin_images(PlanHost& out) {
 
 std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
                        const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
-                       int smemBudgetBytes, PlanHost& out) {
+                       int smemBudgetBytes, PlanHost& out, int patternMode) {
     if (!key_fits(P, maxAf)) return "state key (maxAf+1)^P does not fit 63 bits";
     Ctx c;
     c.P = P;
@@ -1049,7 +1049,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         out.patRow.assign((size_t)nEpochs * nPat, 0u);
         out.patRowStride.assign((size_t)nEpochs * nPat, 0);
         const char* rowEnv = std::getenv("RC_ROWMODE");
-        static const bool patEnv = std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true;
+        const bool patEnv = patternMode != 0 && (std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true);
         static const bool patLEnv = std::getenv("RC_PATLARGE") ? std::atoi(std::getenv("RC_PATLARGE")) != 0 : true;
         std::vector<std::vector<int>> groupIds((size_t)nEpochs * RC_NGROUP);
         for (int e = 0; e < nEpochs; ++e) {

@@ -101,7 +101,9 @@ struct PlanHost {
 // success, else an error message (RC_ERR_UNSUPPORTED).
 std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
                        const std::vector<StructEv>& sev, const std::vector<GapInfo>& gaps, bool hasSplit,
-                       int smemBudgetBytes, PlanHost& out);
+                       int smemBudgetBytes, PlanHost& out, int patternMode = 1);
+// patternMode: 1 (default) boxes of at most RC_PAT_MAXL states run one pattern per thread; 0 every pattern goes to the row /
+// state bins (the "pattern_mode" option of rc_set_option; the parity tests cover both)
 
 // Bounds / capacity self-check of a built plan ("" if consistent).
 std::string check_plan(const PlanHost& h);

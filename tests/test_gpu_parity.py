@@ -15,11 +15,13 @@ PROB_RTOL = 1e-10
 LOGL_RTOL = 1e-9
 
 
-@pytest.fixture(scope="module", params=["keyed", "selfcontained"])
+@pytest.fixture(scope="module", params=["keyed", "keyed-rows", "selfcontained"])
 def eng(request):
-    # both fast-tier code paths: trajectory-key kernels (default) and the self-contained kernel
+    # every fast-tier code path: trajectory-key kernels with one pattern per thread (default), the same with pattern mode
+    # off (row / state kernels), and the self-contained kernel
     e = R.Engine(0)
-    e.set_option("keyed", 1.0 if request.param == "keyed" else 0.0)
+    e.set_option("keyed", 0.0 if request.param == "selfcontained" else 1.0)
+    e.set_option("pattern_mode", 0.0 if request.param == "keyed-rows" else 1.0)
     yield e
     e.close()
 
