@@ -849,6 +849,7 @@ int rc_create(int device, rc_ctx** out) {
 void rc_destroy(rc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();          // launches queued by rc_eval_partial on a caller's stream may still read the buffers
     if (ctx->child) rc_destroy(ctx->child);
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
