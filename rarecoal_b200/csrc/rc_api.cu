@@ -665,6 +665,21 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     // bin groups of the epoch: small / large patterns (one thread each), and the rest (rows or states)
                     for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
                         if (pe->h.nKBins[(size_t)v] == 0) continue;
+                        // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then run
+                        // in the same launch as the small-pattern bins (their headers are contiguous but for one unused entry).
+                        const int nb0 = pe->h.nKBins[(size_t)v], nb1 = v + 1 < RC_NGROUP * (e + 1) ? pe->h.nKBins[(size_t)v + 1] : 0;
+                        if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
+                            pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
+                            (long long)(nb0 + nb1) * (end - pos) < 3LL * 7 * ctx->smCount) {
+                            CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
+                                                         std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
+                                                         std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1]), dM, dMep, dSev,
+                                                         (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
+                                                         carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
+                            ++launches;
+                            ++v;
+                            continue;
+                        }
                         CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v],
                                                      dM, dMep, dSev,
                                                      (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,

@@ -1808,14 +1808,15 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
 }
 
 // shapes the planner admits (pat_shape in rc_plan.cpp): MA >= MB >= MC >= MD >= ME, each of B..E absent (0) or >= 2, product
-// of the present ones <= MAXS; the large-pattern instantiation only receives the shapes the small one does not hold
+// of the present ones <= MAXS; <RC_PAT_MAXS> also holds the shapes of <RC_PAT_MAXT> (small batches run both groups in one
+// launch, see rc_api.cu), <RC_PAT_MAXL> only those the others do not hold
 template <int MB, int MC, int MD, int ME, int MAXS>
 __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                                   unsigned& slot, const unsigned reSlot, const int MA) {
     constexpr int SA = (MB ? MB : 1) * (MC ? MC : 1) * (MD ? MD : 1) * (ME ? ME : 1);
 #define RC_PAT_CASE(A)                                                                                         \
     case A:                                                                                                    \
-        if constexpr (A >= MB && A * SA <= MAXS && (MAXS == RC_PAT_MAXS || A * SA > RC_PAT_MAXS)) {            \
+        if constexpr (A >= MB && A * SA <= MAXS && (MAXS <= RC_PAT_MAXS || A * SA > RC_PAT_MAXS)) {            \
             rc_pat_run<A, MB, MC, MD, ME>(R, sBase, strideD, s, nextStop, slot, reSlot);                       \
         }                                                                                                      \
         break;
@@ -1835,7 +1836,10 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsi
 #define RC_PATL_MINB 6
 #endif
 template <int MAXS>
-__global__ void __launch_bounds__(RC_PBLOCK, MAXS <= RC_PAT_MAXS ? RC_PAT_MINB : RC_PATL_MINB)
+#ifndef RC_PATT_MINB
+#define RC_PATT_MINB 8      // measured on C3: 8 -> 11.0 ms, 10 -> 11.2, 12 -> 11.6 (without this instantiation 11.5)
+#endif
+__global__ void __launch_bounds__(RC_PBLOCK, MAXS <= RC_PAT_MAXT ? RC_PATT_MINB : MAXS <= RC_PAT_MAXS ? RC_PAT_MINB : RC_PATL_MINB)
 rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                         const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
@@ -1852,6 +1856,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
     const int np = hdrA.y, nB = hdrA.w;
+    if (np == 0) return;              // the unused header between two bin groups launched together
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
     const RcModelEpochDev mE = mep[models[b].mepOff + e];
@@ -2143,17 +2148,16 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
     double* dac = dAcc + (size_t)b0 * pl.nPat;
     const double* bp = bPrev + (size_t)b0 * bStride;
     double* bc = bCur + (size_t)b0 * bStride;
-    if (rowMode == 3) {
+    if (rowMode >= RC_MODE_PAT) {
         // ring of RC_PDEPTH slots sized for the group's largest fetch list, aliased with the gathered b of the largest bin
         const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
         const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
-        rc_propagate_pat_kernel<RC_PAT_MAXS><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
-        return cudaGetLastError();
-    }
-    if (rowMode == 4) {
-        const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
-        const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
-        rc_propagate_pat_kernel<RC_PAT_MAXL><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        if (rowMode == RC_MODE_PAT)
+            rc_propagate_pat_kernel<RC_PAT_MAXT><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        else if (rowMode == RC_MODE_PAT + 1)
+            rc_propagate_pat_kernel<RC_PAT_MAXS><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        else
+            rc_propagate_pat_kernel<RC_PAT_MAXL><<<grid, RC_PBLOCK, psmem, st>>>(pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return cudaGetLastError();
     }
     if (rowMode) {

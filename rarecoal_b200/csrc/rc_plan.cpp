@@ -509,7 +509,7 @@ static std::string build_bin_images(PlanHost& out) {
     for (int v = 0; v < nE * RC_NGROUP; ++v) {
         const int e = v / RC_NGROUP;
         const bool rows = out.epochMode[(size_t)v] != 0, patM = out.epochMode[(size_t)v] >= 3;
-        const int patMax = out.epochMode[(size_t)v] == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
+        const int patMax = rc_pat_cap(out.epochMode[(size_t)v]);
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
         const int b0 = out.kBinBase[(size_t)v];
@@ -860,7 +860,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         auto pack_range = [&](int e0, int e1, int maxPats, int mode, bool keyedBins, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
             const int nE = e1 - e0 + 1;
             const bool rowMode = mode != 0, patMode = mode >= 3;
-            const int patMaxStates = mode == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
+            const int patMaxStates = rc_pat_cap(mode);
             auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
             auto clsOf = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
@@ -1053,15 +1053,19 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         static const bool patLEnv = std::getenv("RC_PATLARGE") ? std::atoi(std::getenv("RC_PATLARGE")) != 0 : true;
         std::vector<std::vector<int>> groupIds((size_t)nEpochs * RC_NGROUP);
         for (int e = 0; e < nEpochs; ++e) {
-            std::vector<int>& patIds = groupIds[(size_t)e * RC_NGROUP];
-            std::vector<int>& patLIds = groupIds[(size_t)e * RC_NGROUP + 1];
-            std::vector<int>& restIds = groupIds[(size_t)e * RC_NGROUP + 2];
+            std::vector<int>& restIds = groupIds[(size_t)e * RC_NGROUP + RC_NGROUP - 1];
+            bool anyPat = false;
             for (int i : order) {
                 const PatPlan& pp = pps[(size_t)i];
                 const bool box = patEnv && pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
-                if (box && pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], RC_PAT_MAXS) != 0) patIds.push_back(i);
-                else if (box && patLEnv && pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], RC_PAT_MAXL) != 0) patLIds.push_back(i);
-                else restIds.push_back(i);
+                int g = RC_NGROUP - 1;
+                if (box)
+                    for (int q = 0; q < RC_NGROUP - 1; ++q) {
+                        if (q > 0 && !patLEnv && rc_pat_cap(RC_MODE_PAT + q) > RC_PAT_MAXS) break;
+                        if (pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], rc_pat_cap(RC_MODE_PAT + q)) != 0) { g = q; break; }
+                    }
+                groupIds[(size_t)e * RC_NGROUP + g].push_back(i);
+                anyPat = anyPat || g < RC_NGROUP - 1;
             }
             bool all = !restIds.empty();
             long long rows = 0, states = 0;
@@ -1075,11 +1079,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
             bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
             if (rowEnv) use = all && std::atoi(rowEnv) != 0;
-            out.epochMode[(size_t)e * RC_NGROUP] = 3;
-            out.epochMode[(size_t)e * RC_NGROUP + 1] = 4;
-            out.epochMode[(size_t)e * RC_NGROUP + 2] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
+            for (int q = 0; q < RC_NGROUP - 1; ++q) out.epochMode[(size_t)e * RC_NGROUP + q] = RC_MODE_PAT + q;
+            out.epochMode[(size_t)e * RC_NGROUP + RC_NGROUP - 1] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
-            if (use || !patIds.empty() || !patLIds.empty()) {
+            if (use || anyPat) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
                 long long run = 0;
                 for (int i = 0; i < nPat; ++i) {
@@ -1128,7 +1131,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 if (!nb) continue;
                 int f0 = out.kFetchOff[(size_t)b0], f1 = out.kFetchOff[(size_t)(b0 + nb)];
                 std::fprintf(stderr, "[rc plan] epoch %d: keys %d threads %d rowPairs %d mode %s patterns %d bins %d fetch rows/bin %.1f\n", e,
-                             E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns" : m == 4 ? "patterns (large)" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
+                             E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns<12>" : m == 4 ? "patterns<25>" : m == 5 ? "patterns<36>" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
                              (double)(f1 - f0) / nb);
             }
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
@@ -1325,7 +1328,7 @@ std::string check_plan(const PlanHost& h) {
         for (int v = 0; v < nE * RC_NGROUP; ++v) {
             const int e = v / RC_NGROUP;
             const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] >= 3;
-            const int patMax = h.epochMode[(size_t)v] == 4 ? RC_PAT_MAXL : RC_PAT_MAXS;
+            const int patMax = rc_pat_cap(h.epochMode[(size_t)v]), patMin = rc_pat_floor(h.epochMode[(size_t)v]);
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
@@ -1350,7 +1353,7 @@ std::string check_plan(const PlanHost& h) {
                         int n = M[0], nS = 0;
                         for (int q = 1; q < 5; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1] || nS != q) return fail("image pattern shape order"); }
                         if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > patMax || 1 + nS + nU > 8) return fail("image pattern shape");
-                        if (patMax == RC_PAT_MAXL && n <= RC_PAT_MAXS) return fail("small pattern in the large-pattern group");
+                        if (n <= patMin) return fail("pattern in the group of a larger kernel instantiation");
                         for (int q = 0; q < 8; ++q) {
                             const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
                             const int len = q <= nS ? M[q] : 1;

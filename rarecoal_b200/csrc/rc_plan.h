@@ -71,7 +71,7 @@ struct PlanHost {
     std::vector<int> kFetchRows;           // pair offsets inside a step row, one per shared-memory pair row of a bin
     std::vector<uint16_t> kRowBase;        // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     // row mode (per epoch): one thread per row of states along the widest branch of a box-shaped live set
-    std::vector<int> epochMode;            // [nEpochs] 0: one state per thread; indexed RC_NGROUP * e + g: 0 one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXS (3) or <= RC_PAT_MAXL (4) states
+    std::vector<int> epochMode;            // [nEpochs] 0: one state per thread; indexed RC_NGROUP * e + g: 0 one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXT (3), <= RC_PAT_MAXS (4) or <= RC_PAT_MAXL (5) states
     std::vector<int> rowOff;               // [nEpochs][nPat+1] rows before a pattern in the epoch's row arrays
     std::vector<long long> rowEpochBase;   // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     std::vector<uint16_t> rowRefAll;       // per row RC_ROW_MAXM reference-order indices (inside the pattern) of x_r = 1..M

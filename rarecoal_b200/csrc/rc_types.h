@@ -17,9 +17,14 @@
 // row mode of the keyed tier: one thread per row of states along the widest branch of a box-shaped live set
 #define RC_ROW_NO 7          // other non-zero branches of a row at most
 #define RC_PBLOCK 64         // pattern mode: threads (= patterns) per block
-#define RC_PAT_MAXS 25       // pattern mode: live states of a pattern at most (all in the registers of one thread)
-#define RC_PAT_MAXL 36       // same, second instantiation of the pattern kernel for the larger boxes (fewer resident blocks)
-#define RC_NGROUP 3          // bin groups per epoch: small patterns, large patterns (one thread each), the rest (rows or states)
+#define RC_PAT_MAXT 12       // pattern mode: three instantiations of the kernel by the live states of a pattern (all in the
+#define RC_PAT_MAXS 25       //   registers of one thread) — the fewer states, the fewer registers and the more resident blocks
+#define RC_PAT_MAXL 36
+#define RC_NGROUP 4          // bin groups per epoch: tiny, small, large patterns (one thread each), the rest (rows or states)
+// epochMode of a pattern group = RC_MODE_PAT + index of its capacity in {RC_PAT_MAXT, RC_PAT_MAXS, RC_PAT_MAXL}
+#define RC_MODE_PAT 3
+static inline __host__ __device__ int rc_pat_cap(int mode) { return mode == RC_MODE_PAT ? RC_PAT_MAXT : mode == RC_MODE_PAT + 1 ? RC_PAT_MAXS : RC_PAT_MAXL; }
+static inline __host__ __device__ int rc_pat_floor(int mode) { return mode == RC_MODE_PAT ? 0 : mode == RC_MODE_PAT + 1 ? RC_PAT_MAXT : RC_PAT_MAXS; }
 #define RC_PLANE_N 16        // words of a pattern-mode lane record
 #define RC_ROW_SUM 11        // with more than 3 other branches: other branches + row length <= RC_ROW_SUM (bounds the kernel variants)
 #define RC_ROW_MAXM 10       // longest row
@@ -100,7 +105,7 @@ struct RcPlanDev {
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
     // ---- row mode ----
-    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXS (3) or <= RC_PAT_MAXL (4) states
+    const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXT (3), <= RC_PAT_MAXS (4) or <= RC_PAT_MAXL (5) states
     const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
     const long long* rowEpochBase; // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     const uint16_t* rowRefAll;   // per row RC_ROW_MAXM reference-order indices of its states
