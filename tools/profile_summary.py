@@ -45,7 +45,10 @@ names = {"ms": "gpu__time_duration.sum", "smem": "l1tex__data_pipe_lsu_wavefront
 
 def kind(r):
     n = r[ix["Kernel Name"]]
-    return ("pattern<36>" if "168" == r[col(names["regs"])] else "pattern<25>") if "_pat_" in n else "rows" if "rows" in n else "states"
+    for cap in ("12", "25", "36"):
+        if "_pat_kernel<%s>" % cap in n:
+            return "pattern<%s>" % cap
+    return "rows" if "rows" in n else "states"
 
 
 ms = [float(r[col(names["ms"])]) for r in body]
@@ -55,9 +58,9 @@ share = {}
 for r, m in zip(body, ms):
     share[kind(r)] = share.get(kind(r), 0.0) + m / tms
 json.dump({
-    "kernels": "the propagation launches of one evaluation: per structural epoch rc_propagate_pat_kernel<25> (one pattern per thread, "
-               "boxes of at most 25 live states) and rc_propagate_pat_kernel<36> (26-36 states); rc_propagate_rows_kernel / "
-               "rc_propagate_keyed_kernel take what is left (nothing on C3)",
+    "kernels": "the propagation launches of one evaluation: per structural epoch rc_propagate_pat_kernel<12>, <25>, <36> (one pattern "
+               "per thread; boxes of at most 12 / 13-25 / 26-36 live states); rc_propagate_rows_kernel / rc_propagate_keyed_kernel "
+               "take what is left (nothing on C3)",
     "launch": "C3, 44 models per evaluation (bench.py default); %d launches" % len(body),
     "dram_bytes_read": int(tot_r), "dram_bytes_write": int(tot_w), "dram_bytes_total": int(tot_r + tot_w),
     "algorithmic_hbm_bytes": 46207392,
