@@ -118,7 +118,8 @@ __device__ __forceinline__ double rc_gather(const uint32_t* __restrict__ trEnt, 
 
 // The same gather for U states of a bin at once (records of rc_types.h, "gather record"): all entry words first, then all
 // carried b values and weights, then the sums in entry order — three dependent loads per batch instead of per state.
-template <int U, int E>
+// HASW = false: every weight is 1 (a Join, Core.hs:172-189) — no weight loads and half the registers, so twice the states.
+template <int U, int E, bool HASW = true>
 __device__ __forceinline__ void rc_gather_batch(const uint2 (&g)[U], const uint32_t* __restrict__ trEnt, const double* __restrict__ bp,
                                                 const double* __restrict__ W, double (&v)[U]) {
     int cnt[U], maxCnt = 0;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void rc_gather_batch(const uint2 (&g)[U], const uint3
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int q = 0; q < E; ++q) en[u][q] = base + q < cnt[u] ? trEnt[(size_t)g[u].x + base + q] : (RC_W_ONE << 16);
-        double old[U][E], w[U][E];
+        double old[U][E], w[HASW ? U : 1][HASW ? E : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -143,13 +144,16 @@ __device__ __forceinline__ void rc_gather_batch(const uint2 (&g)[U], const uint3
                 const bool on = base + q < cnt[u];
                 const uint32_t widx = en[u][q] >> 16;
                 old[u][q] = on ? bp[(size_t)(g[u].y & ((1u << RC_IMG_CNT_SHIFT) - 1u)) + (en[u][q] & 0xFFFFu)] : 0.0;
-                w[u][q] = (on && widx != RC_W_ONE) ? W[widx] : 1.0;
+                if (HASW) w[u][q] = (on && widx != RC_W_ONE) ? W[widx] : 1.0;
             }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int q = 0; q < E; ++q)
-                if (base + q < cnt[u]) v[u] = (en[u][q] >> 16) == RC_W_ONE ? v[u] + old[u][q] : v[u] + old[u][q] * w[u][q];
+                if (base + q < cnt[u]) {
+                    if (HASW) v[u] = (en[u][q] >> 16) == RC_W_ONE ? v[u] + old[u][q] : v[u] + old[u][q] * w[u][q];
+                    else v[u] = v[u] + old[u][q];
+                }
     }
 }
 
@@ -1908,16 +1912,31 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        constexpr int GU = RC_PAT_GU;
-        for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
-            uint2 g[GU];
-            double v[GU];
+        if (e > 0 && sevs[models[b].sevOff + e - 1].type == RC_EV_JOIN_D) {
+            // a Join: all weights are 1, twice as many states per batch
+            constexpr int GU = 2 * RC_PAT_GU;
+            for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
+                uint2 g[GU];
+                double v[GU];
 #pragma unroll
-            for (int u = 0; u < GU; ++u) g[u] = i + u * RC_PBLOCK < nB ? el[i + u * RC_PBLOCK] : make_uint2(0u, 0u);
-            rc_gather_batch<GU, 4>(g, pl.trEnt, bp, W, v);
+                for (int u = 0; u < GU; ++u) g[u] = i + u * RC_PBLOCK < nB ? el[i + u * RC_PBLOCK] : make_uint2(0u, 0u);
+                rc_gather_batch<GU, 4, false>(g, pl.trEnt, bp, W, v);
 #pragma unroll
-            for (int u = 0; u < GU; ++u)
-                if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
+                for (int u = 0; u < GU; ++u)
+                    if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
+            }
+        } else {
+            constexpr int GU = RC_PAT_GU;
+            for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
+                uint2 g[GU];
+                double v[GU];
+#pragma unroll
+                for (int u = 0; u < GU; ++u) g[u] = i + u * RC_PBLOCK < nB ? el[i + u * RC_PBLOCK] : make_uint2(0u, 0u);
+                rc_gather_batch<GU, 4>(g, pl.trEnt, bp, W, v);
+#pragma unroll
+                for (int u = 0; u < GU; ++u)
+                    if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
+            }
         }
     }
     const unsigned shape = la.z & 0xFFFFFu;         // MA | MB << 4 | MC << 8 | MD << 12 | ME << 16
