@@ -16,7 +16,9 @@
 #define RC_EV_SPLIT_D 1
 // row mode of the keyed tier: one thread per row of states along the widest branch of a box-shaped live set
 #define RC_ROW_NO 7          // other non-zero branches of a row at most
+#ifndef RC_PBLOCK
 #define RC_PBLOCK 64         // pattern mode: threads (= patterns) per block
+#endif
 #define RC_PAT_MAXT 12       // pattern mode: three instantiations of the kernel by the live states of a pattern (all in the
 #define RC_PAT_MAXS 25       //   registers of one thread) — the fewer states, the fewer registers and the more resident blocks
 #define RC_PAT_MAXL 36
