@@ -1718,6 +1718,9 @@ struct RcPatRegs {
     double b[MAXS];
     unsigned long long rows64;    // pair rows (bytes): A, then the shaped branches, then the m = 1 branches
     int nU;                       // number of m = 1 branches
+    const double* dptr;           // direct bins (no ring): the pattern's first pair in the step row to be read next, else null
+    int dPairBase;                // ... and its pair index inside the step row (pair 0 of the row is {dt, 0})
+    bool direct;                  // block-uniform
     bool on, unit;
     double dacc;
     const double* fp[RC_PFETCH];  // this thread's pairs in the step row to be copied next
@@ -1734,6 +1737,26 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
     constexpr int SA = MBp * MCp * MDp * MEp, SB = MCp * MDp * MEp, SC = MDp * MEp, SD = MEp;
     constexpr int NS = (MB ? 1 : 0) + (MC ? 1 : 0) + (MD ? 1 : 0) + (ME ? 1 : 0);
     static_assert(MA * SA <= MAXS, "shape");
+    if constexpr (NS == 0) {
+        // Direct bin (every pattern of the group has one live branch and its own trajectory key — the root epoch of a tree):
+        // nothing is shared between threads, the pairs come straight from the table, no ring, no barrier.
+        if (R.direct) {
+            for (; s < nextStop; ++s) {
+                if (R.on) {
+                    const double2* row = reinterpret_cast<const double2*>(R.dptr);
+#pragma unroll
+                    for (int i = 0; i < MA; ++i) {
+                        const double2 p = row[i];
+                        const double t2 = (i + 1 < MA) ? R.b[i + 1] * p.y : 0.0;
+                        R.b[i] = fma(R.b[i], p.x, t2);                                      // updateB, Core.hs:259
+                    }
+                    if (R.unit) R.dacc = fma(*(R.dptr - 2 * (long long)R.dPairBase), R.b[0], R.dacc);   // updateD, Core.hs:282-288
+                    R.dptr += strideD;
+                }
+            }
+            return;
+        }
+    }
     const unsigned myRE = sBase + threadIdx.x * 16u;
     const unsigned aA = sBase + rc_pat_row(R, 0) * 16u, aB = sBase + rc_pat_row(R, 1) * 16u, aC = sBase + rc_pat_row(R, 2) * 16u,
                    aD = sBase + rc_pat_row(R, 3) * 16u, aE = sBase + rc_pat_row(R, 4) * 16u;
@@ -1946,6 +1969,10 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int pid = (int)lb.x;
     double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
     R.rows64 = (unsigned long long)la.x | ((unsigned long long)la.y << 32);
+    // direct bin: no pair rows to fetch; the pattern reads its own key's pairs from the table
+    R.dPairBase = (int)ld.w;
+    R.direct = hdrB.y == 0;
+    R.dptr = ktab + (mE.tabBase + (long long)R.dPairBase) * 2;
     __syncthreads();
     if (R.on) {
         const double* mine = bb + lb.y;

@@ -544,10 +544,16 @@ static std::string build_bin_images(PlanHost& out) {
                     if (MA * SA != live || nr != SA || NO != nS + nU) return "pattern-mode image: shape does not match the live set";
                     uint32_t rec[RC_PLANE_N];
                     for (int q = 0; q < RC_PLANE_N; ++q) rec[q] = 0u;
+                    const bool direct = out.grpDirect[(size_t)v] != 0;
                     for (int q = 0; q < 8; ++q) {
-                        const uint32_t row = q < 1 + nS + nU ? (uint32_t)rb[dims[q]] : (uint32_t)(RC_KROWS - 1);
+                        const uint32_t row = (!direct && q < 1 + nS + nU) ? (uint32_t)rb[dims[q]] : (uint32_t)(RC_KROWS - 1);
                         if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
                         rec[q >> 2] |= row << (8 * (q & 3));
+                    }
+                    if (direct) {
+                        // first pair of the pattern's only key inside a step row of the trajectory table
+                        if (nS + nU != 0) return "direct group with a multi-branch pattern";
+                        rec[15] = (uint32_t)out.keyPairBase[(size_t)out.ep[(size_t)e].keyOff + out.keyId[((size_t)e * nPat + i) * P + rk]];
                     }
                     std::vector<uint32_t> el((size_t)live * 2, 0u);
                     for (int r = 0; r < nr; ++r) {
@@ -849,6 +855,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             return a < b;
         });
         const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
+        bool packDirect = false;                  // set around the packing of a direct group: no pair rows in shared memory
         struct OpenBin {
             std::vector<int> ids, slotsE, rowsUsed, rowsSelf;
             int rowStates = 0, cls = 0;
@@ -920,7 +927,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         int have = it == ob.keyRows[(size_t)q].end() ? 0 : it->second;
                         if (mxk > have) add[(size_t)q] += mxk - have;
                     }
-                    if (ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
+                    if (!packDirect && ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
                     // (pair rows without de-duplication: a limit of the self-contained kernel's rate table only)
                     if (!keyedBins && ob.rowsSelf[(size_t)q] + addSelf[(size_t)q] > 2 * fastBlock - 2) return false;
                 }
@@ -1103,15 +1110,23 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ro[nPat] = (int)run;
             }
         }
+        out.grpDirect.assign((size_t)nEpochs * RC_NGROUP, 0);
+        static const bool directEnv = std::getenv("RC_PAT_DIRECT") ? std::atoi(std::getenv("RC_PAT_DIRECT")) != 0 : true;
         for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
             const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
             out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
             out.kBinPatOff.push_back((int)out.kBinPats.size());
+            // a pattern group in which every pattern has one live branch (the root epoch of a tree)
+            bool direct = directEnv && mode >= RC_MODE_PAT && !groupIds[(size_t)v].empty();
+            for (int i : groupIds[(size_t)v]) direct = direct && pps[(size_t)i].rowNO[(size_t)e] == 0;
+            out.grpDirect[(size_t)v] = direct ? 1 : 0;
+            packDirect = direct;
             if (!groupIds[(size_t)v].empty()) {
                 if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
                 else if (mode) pack_range(e, e, RC_NPBR, 1, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
                 else pack_range(e, e, RC_NPB, 0, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
             }
+            packDirect = false;
             out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
         }
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
@@ -1119,7 +1134,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             const int e = v / RC_NGROUP, b0 = out.kBinBase[(size_t)v];
             // fetch offsets are stored at the same index as the bin offsets (one extra entry per group)
             std::vector<int> fOff;
-            fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0);
+            if (out.grpDirect[(size_t)v]) fOff.assign((size_t)out.nKBins[(size_t)v], (int)out.kFetchRows.size());     // nothing to fetch
+            else fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0);
             fOff.push_back((int)out.kFetchRows.size());
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
@@ -1273,7 +1289,8 @@ std::string check_plan(const PlanHost& h) {
                 const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
                 if (p1 - p0 < 1 || p1 - p0 > (patM ? RC_PBLOCK : rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
                 const int f0 = h.kFetchOff[(size_t)bI], f1 = h.kFetchOff[(size_t)bI + 1];
-                if (f1 - f0 < 1 || f1 - f0 > RC_KROWS - 1) return fail("pair rows per keyed bin");
+                const bool direct = !h.grpDirect.empty() && h.grpDirect[(size_t)v] != 0;
+                if (direct ? f1 != f0 : (f1 - f0 < 1 || f1 - f0 > RC_KROWS - 1)) return fail("pair rows per keyed bin");
                 for (int q = f0; q < f1; ++q)
                     if (h.kFetchRows[(size_t)q] < 0 || h.kFetchRows[(size_t)q] >= E.rowPairs) return fail("fetch row out of range");
                 long long lanes = 0, padded = 0;
@@ -1286,7 +1303,7 @@ std::string check_plan(const PlanHost& h) {
                         const int mxk = h.maxX[((size_t)e * nPat + i) * P + k];
                         if (!mxk) continue;
                         const int rb = h.kRowBase[(size_t)q * P + k];
-                        if (rb < 1 || rb + mxk - 1 > f1 - f0 - 1) return fail("pair-row base out of range");
+                        if (!direct && (rb < 1 || rb + mxk - 1 > f1 - f0 - 1)) return fail("pair-row base out of range");
                     }
                     if (rows) {
                         const uint32_t pr = h.patRow[(size_t)e * nPat + i];
@@ -1329,6 +1346,7 @@ std::string check_plan(const PlanHost& h) {
             const int e = v / RC_NGROUP;
             const bool rows = h.epochMode[(size_t)v] != 0, patM = h.epochMode[(size_t)v] >= 3;
             const int patMax = rc_pat_cap(h.epochMode[(size_t)v]), patMin = rc_pat_floor(h.epochMode[(size_t)v]);
+            const bool directG = !h.grpDirect.empty() && h.grpDirect[(size_t)v] != 0;
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
@@ -1354,10 +1372,12 @@ std::string check_plan(const PlanHost& h) {
                         for (int q = 1; q < 5; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1] || nS != q) return fail("image pattern shape order"); }
                         if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > patMax || 1 + nS + nU > 8) return fail("image pattern shape");
                         if (n <= patMin) return fail("pattern in the group of a larger kernel instantiation");
+                        if (directG && (nS + nU != 0 || (int)r[15] < 1 || (int)r[15] + M[0] > h.ep[(size_t)e].rowPairs)) return fail("image direct pair base");
                         for (int q = 0; q < 8; ++q) {
                             const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
                             const int len = q <= nS ? M[q] : 1;
-                            if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != RC_KROWS - 1) return fail("image pattern pair rows");
+                            if (directG) { if (row != RC_KROWS - 1) return fail("image pattern pair rows (direct)"); }
+                            else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != RC_KROWS - 1) return fail("image pattern pair rows");
                         }
                         if ((int)r[4] >= nPat || (long long)r[3] + n > h.epochSlots[(size_t)e] || eOff + n > nB) return fail("image pattern hand-over");
                         const int live = h.slotOff[(size_t)e * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[4]];

@@ -81,6 +81,8 @@ struct PlanHost {
     // bin images (layouts in rc_types.h): the set-up data of every keyed bin in lane order, so that a block reads
     // header -> lane record -> transition entries instead of chasing pattern / slot / word / offset tables
     std::vector<int> kBinHdr, kPatRec;
+    std::vector<int> grpDirect;            // per bin group: 1 if every pattern has a single live branch — such patterns share no
+                                           // trajectory keys, so their pairs are read straight from the table (no ring, no row limit)
     std::vector<int> grpMaxFetch, grpMaxB;   // per bin group: most pair rows / most b doubles of one bin (sizes the pattern kernel's shared memory)
     std::vector<uint32_t> kLane, kElem;
     long long maxEpochSlots = 0;           // largest number of live states in one epoch (stride of the b carry buffers)
