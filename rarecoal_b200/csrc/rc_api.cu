@@ -148,6 +148,10 @@ struct rc_ctx {
     // the propagation launches, each of which waits for the trajectory of its own epoch
     cudaStream_t trajStream = nullptr;
     cudaEvent_t evFork = nullptr;
+    // the bin groups of one epoch touch disjoint patterns: their launches run side by side (group streams), so the few long
+    // blocks of the large-pattern group do not leave the GPU idle in their tail; joined before the next epoch
+    cudaStream_t grpStream[RC_NGROUP - 1] = {};
+    cudaEvent_t evEpoch = nullptr, evGrp[RC_NGROUP - 1] = {};
     std::vector<cudaEvent_t> evTraj;
     bool trajTimed = false;
     int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
@@ -662,7 +666,11 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
                     CK(cudaStreamWaitEvent(st, ctx->evTraj[(size_t)e], 0));
-                    // bin groups of the epoch: small / large patterns (one thread each), and the rest (rows or states)
+                    // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
+                    // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
+                    struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
+                    Launch L[RC_NGROUP];
+                    int nL = 0;
                     for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
                         if (pe->h.nKBins[(size_t)v] == 0) continue;
                         // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then run
@@ -671,21 +679,25 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                         if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
                             pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
                             (long long)(nb0 + nb1) * (end - pos) < 3LL * 7 * ctx->smCount) {
-                            CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
-                                                         std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
-                                                         std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1]), dM, dMep, dSev,
-                                                         (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
-                                                         carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
-                            ++launches;
+                            L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
+                                       std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
+                                       std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
                             ++v;
                             continue;
                         }
-                        CK(rc_launch_propagate_keyed(pe->d, e, pe->h.kBinBase[(size_t)v], pe->h.nKBins[(size_t)v], pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v],
-                                                     dM, dMep, dSev,
+                        L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
+                    }
+                    if (nL > 1) CK(cudaEventRecord(ctx->evEpoch, st));
+                    for (int q = nL - 1; q >= 0; --q) {
+                        cudaStream_t gs = q == 0 ? st : ctx->grpStream[q - 1];
+                        if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch, 0));
+                        CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
                                                      (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
-                                                     carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, st));
+                                                     carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, gs));
+                        if (q > 0) CK(cudaEventRecord(ctx->evGrp[q - 1], gs));
                         ++launches;
                     }
+                    for (int q = 1; q < nL; ++q) CK(cudaStreamWaitEvent(st, ctx->evGrp[q - 1], 0));
                 }
             }
             if (pe->d.nFastBins > 0 && anySelf) {
@@ -853,7 +865,11 @@ int rc_create(int device, rc_ctx** out) {
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->trajStream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evEpoch, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    for (int g = 0; g < RC_NGROUP - 1; ++g)
+        if (cudaStreamCreateWithFlags(&ctx->grpStream[g], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->evGrp[g], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     for (auto& e : ctx->evt)
         if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -877,6 +893,11 @@ void rc_destroy(rc_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->trajStream) cudaStreamDestroy(ctx->trajStream);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evEpoch) cudaEventDestroy(ctx->evEpoch);
+    for (int g = 0; g < RC_NGROUP - 1; ++g) {
+        if (ctx->grpStream[g]) cudaStreamDestroy(ctx->grpStream[g]);
+        if (ctx->evGrp[g]) cudaEventDestroy(ctx->evGrp[g]);
+    }
     for (cudaEvent_t ev : ctx->evTraj) cudaEventDestroy(ev);
     delete ctx;
 }
