@@ -110,6 +110,7 @@ struct rc_statespace {
     rc::StateSpace* ss;
 };
 
+#define RC_NCHAIN 2
 struct rc_ctx {
     int device = 0;
     int smemOptin = 0;
@@ -150,8 +151,11 @@ struct rc_ctx {
     cudaEvent_t evFork = nullptr;
     // the bin groups of one epoch touch disjoint patterns: their launches run side by side (group streams), so the few long
     // blocks of the large-pattern group do not leave the GPU idle in their tail; joined before the next epoch
-    cudaStream_t grpStream[RC_NGROUP - 1] = {};
-    cudaEvent_t evEpoch = nullptr, evGrp[RC_NGROUP - 1] = {};
+    // ... and a large batch is cut into RC_NCHAIN model ranges whose epoch chains run side by side, so that the tail of one
+    // range's launch is filled by the other's
+    cudaStream_t chainStream[RC_NCHAIN] = {};                 // [0] unused: chain 0 runs on the caller's stream
+    cudaStream_t grpStream[RC_NCHAIN][RC_NGROUP - 1] = {};
+    cudaEvent_t evEpoch[RC_NCHAIN] = {}, evGrp[RC_NCHAIN][RC_NGROUP - 1] = {}, evChain[RC_NCHAIN] = {};
     std::vector<cudaEvent_t> evTraj;
     bool trajTimed = false;
     int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
@@ -661,43 +665,59 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     ++launches;
                 }
                 if (timeIt) { CK(cudaEventRecord(ctx->evt[7], ts)); ctx->trajTimed = true; }
-                // one launch per structural epoch; b ping-pongs between the two carry buffers
+                // one launch per structural epoch and bin group; b ping-pongs between the two carry buffers.  A batch large
+                // enough is cut into RC_NCHAIN model ranges, each with its own chain of streams.
+                const int nModels = end - pos;
+                const int nChains = nModels >= 16 ? RC_NCHAIN : 1;
+                if (nChains > 1) {
+                    CK(cudaEventRecord(ctx->evChain[0], st));         // everything queued so far (blob, tables) precedes the chains
+                    for (int c = 1; c < nChains; ++c) CK(cudaStreamWaitEvent(ctx->chainStream[c], ctx->evChain[0], 0));
+                }
                 for (int e = 0; e < pe->h.nEpochs; ++e) {
                     double* c0 = (double*)ctx->dBCarry.p;
                     double* c1 = c0 + (size_t)carrySlots * B;
-                    CK(cudaStreamWaitEvent(st, ctx->evTraj[(size_t)e], 0));
-                    // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
-                    // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
-                    struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
-                    Launch L[RC_NGROUP];
-                    int nL = 0;
-                    for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
-                        if (pe->h.nKBins[(size_t)v] == 0) continue;
-                        // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then run
-                        // in the same launch as the small-pattern bins (their headers are contiguous but for one unused entry).
-                        const int nb0 = pe->h.nKBins[(size_t)v], nb1 = v + 1 < RC_NGROUP * (e + 1) ? pe->h.nKBins[(size_t)v + 1] : 0;
-                        if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
-                            pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
-                            (long long)(nb0 + nb1) * (end - pos) < 3LL * 7 * ctx->smCount) {
-                            L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
-                                       std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
-                                       std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
-                            ++v;
-                            continue;
+                    for (int c = 0; c < nChains; ++c) {
+                        cudaStream_t cs = c == 0 ? st : ctx->chainStream[c];
+                        const int p0 = pos + (int)((long long)nModels * c / nChains), p1 = pos + (int)((long long)nModels * (c + 1) / nChains);
+                        CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)e], 0));
+                        // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
+                        // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
+                        struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
+                        Launch L[RC_NGROUP];
+                        int nL = 0;
+                        for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
+                            if (pe->h.nKBins[(size_t)v] == 0) continue;
+                            // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then
+                            // run in the same launch as the small-pattern bins (their headers are contiguous but for one unused
+                            // entry).
+                            const int nb0 = pe->h.nKBins[(size_t)v], nb1 = v + 1 < RC_NGROUP * (e + 1) ? pe->h.nKBins[(size_t)v + 1] : 0;
+                            if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
+                                pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
+                                (long long)(nb0 + nb1) * nModels < 3LL * 7 * ctx->smCount) {
+                                L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
+                                           std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
+                                           std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
+                                ++v;
+                                continue;
+                            }
+                            L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
                         }
-                        L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
+                        if (nL > 1) CK(cudaEventRecord(ctx->evEpoch[c], cs));
+                        for (int q = nL - 1; q >= 0; --q) {
+                            cudaStream_t gs = q == 0 ? cs : ctx->grpStream[c][q - 1];
+                            if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch[c], 0));
+                            CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
+                                                         (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1,
+                                                         (e & 1) ? c1 : c0, carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, p0, p1 - p0, gs));
+                            if (q > 0) CK(cudaEventRecord(ctx->evGrp[c][q - 1], gs));
+                            ++launches;
+                        }
+                        for (int q = 1; q < nL; ++q) CK(cudaStreamWaitEvent(cs, ctx->evGrp[c][q - 1], 0));
                     }
-                    if (nL > 1) CK(cudaEventRecord(ctx->evEpoch, st));
-                    for (int q = nL - 1; q >= 0; --q) {
-                        cudaStream_t gs = q == 0 ? st : ctx->grpStream[q - 1];
-                        if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch, 0));
-                        CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
-                                                     (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1, (e & 1) ? c1 : c0,
-                                                     carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, pos, end - pos, gs));
-                        if (q > 0) CK(cudaEventRecord(ctx->evGrp[q - 1], gs));
-                        ++launches;
-                    }
-                    for (int q = 1; q < nL; ++q) CK(cudaStreamWaitEvent(st, ctx->evGrp[q - 1], 0));
+                }
+                for (int c = 1; c < nChains; ++c) {
+                    CK(cudaEventRecord(ctx->evChain[c], ctx->chainStream[c]));
+                    CK(cudaStreamWaitEvent(st, ctx->evChain[c], 0));
                 }
             }
             if (pe->d.nFastBins > 0 && anySelf) {
@@ -865,11 +885,15 @@ int rc_create(int device, rc_ctx** out) {
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->trajStream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->evEpoch, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
-    for (int g = 0; g < RC_NGROUP - 1; ++g)
-        if (cudaStreamCreateWithFlags(&ctx->grpStream[g], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->evGrp[g], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    for (int c = 0; c < RC_NCHAIN; ++c) {
+        if ((c > 0 && cudaStreamCreateWithFlags(&ctx->chainStream[c], cudaStreamNonBlocking) != cudaSuccess) ||
+            cudaEventCreateWithFlags(&ctx->evEpoch[c], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->evChain[c], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+        for (int g = 0; g < RC_NGROUP - 1; ++g)
+            if (cudaStreamCreateWithFlags(&ctx->grpStream[c][g], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->evGrp[c][g], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
+    }
     for (auto& e : ctx->evt)
         if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -893,10 +917,14 @@ void rc_destroy(rc_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->trajStream) cudaStreamDestroy(ctx->trajStream);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
-    if (ctx->evEpoch) cudaEventDestroy(ctx->evEpoch);
-    for (int g = 0; g < RC_NGROUP - 1; ++g) {
-        if (ctx->grpStream[g]) cudaStreamDestroy(ctx->grpStream[g]);
-        if (ctx->evGrp[g]) cudaEventDestroy(ctx->evGrp[g]);
+    for (int c = 0; c < RC_NCHAIN; ++c) {
+        if (ctx->chainStream[c]) cudaStreamDestroy(ctx->chainStream[c]);
+        if (ctx->evEpoch[c]) cudaEventDestroy(ctx->evEpoch[c]);
+        if (ctx->evChain[c]) cudaEventDestroy(ctx->evChain[c]);
+        for (int g = 0; g < RC_NGROUP - 1; ++g) {
+            if (ctx->grpStream[c][g]) cudaStreamDestroy(ctx->grpStream[c][g]);
+            if (ctx->evGrp[c][g]) cudaEventDestroy(ctx->evGrp[c][g]);
+        }
     }
     for (cudaEvent_t ev : ctx->evTraj) cudaEventDestroy(ev);
     delete ctx;
