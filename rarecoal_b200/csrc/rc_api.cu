@@ -110,7 +110,9 @@ struct rc_statespace {
     rc::StateSpace* ss;
 };
 
+#ifndef RC_NCHAIN
 #define RC_NCHAIN 2
+#endif
 struct rc_ctx {
     int device = 0;
     int smemOptin = 0;
