@@ -1111,8 +1111,7 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
         if (v != ctx->optPattern) {
             // plans depend on it: finish what is queued, then drop them
             cudaSetDevice(ctx->device);
-            cudaStreamSynchronize(ctx->stream);
-            cudaStreamSynchronize(ctx->trajStream);
+            cudaDeviceSynchronize();
             ctx->clear_plans();
             ctx->optPattern = v;
         }
