@@ -74,7 +74,26 @@ class ClockSampler(threading.Thread):
         self.rows = []
         self.stop_flag = False
 
+    def _run_nvml(self):
+        """NVML directly: a sample every 20 ms (nvidia-smi takes ~0.2 s per call, too coarse for a sub-second timed region)."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop_flag:
+            r = get_reasons(h)
+            self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), str(N.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                             ["Active" if r & b else "Not Active" for _, b in bits])
+            time.sleep(0.02)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
