@@ -886,7 +886,10 @@ int rc_create(int device, rc_ctx** out) {
     cudaDeviceGetAttribute(&ctx->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->trajStream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the trajectory chain feeds every propagation launch: its blocks go first when both are runnable
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    if (cudaStreamCreateWithPriority(&ctx->trajStream, cudaStreamNonBlocking, prHi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     for (int c = 0; c < RC_NCHAIN; ++c) {
         if ((c > 0 && cudaStreamCreateWithFlags(&ctx->chainStream[c], cudaStreamNonBlocking) != cudaSuccess) ||
