@@ -1,5 +1,5 @@
 """Randomised differential test: random models (random join orders, admixture pulses, size changes, freezes) on random
-problem shapes, GPU (through the C ABI) against the CPU oracle, with pattern mode on and off.
+problem shapes, GPU (through the C ABI) against the CPU oracle, in the three kernel configurations of the parity suite.
     python tools/fuzz_parity.py [cases] [seed]"""
 import os, sys
 import numpy as np
@@ -39,8 +39,9 @@ def run(n_cases=40, seed=1, verbose=True):
     rng = np.random.default_rng(seed)
     times = R.defaultTimes()
     engs = []
-    for pm in (1.0, 0.0):
+    for keyed, pm in ((1.0, 1.0), (1.0, 0.0), (0.0, 1.0)):      # pattern kernels; row / state kernels; self-contained kernels
         e = R.Engine(0)
+        e.set_option("keyed", keyed)
         e.set_option("pattern_mode", pm)
         engs.append(e)
     worst = 0.0
