@@ -46,8 +46,12 @@ def run(n_cases=40, seed=1, verbose=True):
         engs.append(e)
     worst = 0.0
     for case in range(n_cases):
-        P = int(rng.integers(1, 7))
-        max_af = int(rng.integers(2, 11 if P <= 4 else 8))
+        if os.environ.get("FUZZ_BIG"):                 # many branches, many alleles: the multi-branch shapes of the pattern kernels
+            P = int(rng.integers(5, 9))
+            max_af = int(rng.integers(8, 11))
+        else:
+            P = int(rng.integers(1, 7))
+            max_af = int(rng.integers(2, 11 if P <= 4 else 8))
         nvec = [int(rng.integers(max_af, 60)) for _ in range(P)]
         pats = R.computeStandardOrder(nvec, max_af)
         if len(pats) > 600:
