@@ -44,6 +44,16 @@ def _traffic():
 
 
 TRAFFIC = _traffic()
+
+
+def _hbm_peak():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6539.2, "fallback (value measured on this pool earlier in the round)"
+
+
 METRIC = "logl_evals_per_sec"
 UNIT = "logl evals/s"
 WORKLOAD = "C3: synthetic 8-pop balanced tree, maxAf=10, 43757 patterns, nVec=[100]*8, 3043-step grid"
@@ -331,7 +341,10 @@ def main():
                          "kernel_ms": k_ms, "traj_kernels_ms_side_stream": traj_mean,
                          "algorithmic": f"{w_steps} state-steps x {FLOPS_PER_STATE_STEP} flops per launch (rank 0)",
                          "peak_source": "rc_fp64_peak DFMA microbenchmark on this GPU (no FP64 figure in MEASURED_PEAKS.json)",
-                         "hbm_note": "algorithmic HBM bytes ~24 B x patterns x models per launch: not the bound"},
+                         "hbm_note": "algorithmic HBM bytes ~24 B x patterns x models per launch: not the bound",
+                         "hbm_view": (lambda pk: {"dram_gbs_measured_traffic": (TRAFFIC or {}).get("dram_bytes_total", 0) / (k_ms * 1e-3) / 1e9,
+                                                  "peak_gbs": pk[0], "peak_source": pk[1],
+                                                  "frac": (TRAFFIC or {}).get("dram_bytes_total", 0) / (k_ms * 1e-3) / 1e9 / pk[0]})(_hbm_peak())},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
