@@ -19,7 +19,9 @@
 #ifndef RC_PBLOCK
 #define RC_PBLOCK 64         // pattern mode: threads (= patterns) per block
 #endif
+#ifndef RC_PAT_MAXT
 #define RC_PAT_MAXT 12       // pattern mode: three instantiations of the kernel by the live states of a pattern (all in the
+#endif
 #define RC_PAT_MAXS 25       //   registers of one thread) — the fewer states, the fewer registers and the more resident blocks
 #define RC_PAT_MAXL 36
 #define RC_NGROUP 4          // bin groups per epoch: tiny, small, large patterns (one thread each), the rest (rows or states)
