@@ -162,7 +162,10 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_gpu": 1},
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                   "parallelism": "host thread pool over patterns, one model after the other (the rate does not depend on the batch); "
+                                  "every step times every second pattern of one model and scales by executed state-steps"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; the Haskell reference cannot be built in this image (no ghc), "
                                             "the timed code is the C++ oracle port with a thread pool over patterns"},
