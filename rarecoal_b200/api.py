@@ -342,8 +342,25 @@ class Engine:
             self.set_times(t)
 
     def eval_models(self, models: Sequence[ModelSpec], siteRed=1.0, want_probs=False):
-        """Batch of ModelSpecs (same grid, same noShortcut) -> (logl[B], probs[B][nPat] or None, status[B])."""
+        """Batch of ModelSpecs (same grid) -> (logl[B], probs[B][nPat] or None, status[B]).  mNoShortcut is one flag per
+        rc_eval call: a batch that mixes both values is evaluated as two calls."""
         B = len(models)
+        flags = [bool(m.mNoShortcut) for m in models]
+        if any(flags) and not all(flags):
+            logl = np.zeros(B)
+            status = np.zeros(B, dtype=np.int32)
+            probs = np.zeros((B, self.nPat)) if want_probs else None
+            steps = 0
+            for f in (False, True):
+                idx = [i for i, g in enumerate(flags) if g == f]
+                l, p, st = self.eval_models([models[i] for i in idx], siteRed, want_probs)
+                logl[idx], status[idx] = l, st
+                if want_probs:
+                    probs[idx] = p
+                steps += self.stats()["state_steps"]
+            self._mixed_state_steps = steps
+            return logl, probs, status
+        self._mixed_state_steps = None
         self._ensure_times(models)
         ev, off, theta, disc = self._pack(models)
         logl = np.zeros(B)
@@ -387,7 +404,10 @@ class Engine:
     def stats(self):
         st = L.rc_stats()
         self._check(self._lib.rc_last_stats(self._h, C.byref(st)))
-        return {f: getattr(st, f) for f, _ in L.rc_stats._fields_}
+        d = {f: getattr(st, f) for f, _ in L.rc_stats._fields_}
+        if getattr(self, "_mixed_state_steps", None) is not None:      # eval_models ran as two calls: the sum of both
+            d["state_steps"] = self._mixed_state_steps
+        return d
 
     def fp64_peak_tflops(self):
         out = C.c_double(0.0)

@@ -516,6 +516,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         const int b = order[(size_t)pos];
         ModelHost& mh = mhs[(size_t)b];
         RcModelDev& M = hM[pos];
+        std::memset(&M, 0, sizeof M);      // the staging buffer is reused: a rejected model must not keep a previous call's
+                                           // table offsets (rc_tables_kernel would write its rows over another model's)
         hSegOff[pos] = (int)segPos;
         M.pad = b;   // original model index: rows of partial / dProbs
         if (mh.status != RC_OK || ctx->nPat == 0) {

@@ -290,3 +290,24 @@ def test_tier_selection_on_odd_shapes(eng, default_times, P, max_af, n):
     assert _relerr(probs[0], probs_o) < PROB_RTOL
     assert abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
     assert eng.stats()["state_steps"] == w_o
+
+
+def test_batch_mixing_shortcut_and_noshortcut_models(eng, fivepop, default_times):
+    # mNoShortcut is a field of every ModelSpec (StateSpace.hs:49) but one flag per rc_eval call: the host layer must not
+    # apply the first model's flag to the whole batch
+    nvec = fivepop["nVec"]
+    pats = R.computeStandardOrder(nvec, 3)
+    cnt = Wk.synthetic_counts(pats, total_sites=10 ** 8, seed=5)
+    eng.set_problem(nvec, 3, pats, cnt, 10 ** 8)
+    times = default_times[:600]
+    specs = [_spec(5, times, fivepop["events"], 0.001, no_shortcut=ns) for ns in (True, False, True, False)]
+    logl, probs, status = eng.eval_models(specs, want_probs=True)
+    assert not status.any()
+    total = 0
+    for m, ns in enumerate((True, False, True, False)):
+        ll_o, probs_o, w_o = O.logl(5, 3, times, 0.001, [1.0] * 5, ns, fivepop["events"], nvec, pats, cnt, 10 ** 8)
+        total += w_o
+        assert _relerr(probs[m], probs_o) < PROB_RTOL
+        assert abs(logl[m] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert logl[0] != logl[1]
+    assert eng.stats()["state_steps"] == total

@@ -57,37 +57,43 @@ def run(n_cases=40, seed=1, verbose=True):
         if len(pats) > 600:
             pats = pats[np.sort(rng.choice(len(pats), 600, replace=False))]
         cnt = Wk.synthetic_counts(pats, total_sites=10 ** 8, seed=case)
-        ev = random_model(rng, P)
-        no_sc = bool(rng.random() < 0.15)
+        # a batch of models with different event structures, thetas and discovery rates in one call
         T = times[: int(rng.choice([400, 900, len(times)]))]
-        spec = R.ModelSpec(P, T, 0.001, [1.0] * P, 0.0, no_sc, [R.ModelEvent.from_tuple(x) for x in ev])
-        try:
-            ll_o, probs_o, w_o = O.logl(P, max_af, T, 0.001, [1.0] * P, no_sc, ev, nvec, pats, cnt, 10 ** 8)
-        except O.OracleError as ex:                 # validateModel rejects it: the engine must reject it too
-            for e in engs:
-                e.set_problem(nvec, max_af, pats, cnt, 10 ** 8)
-                _, _, status = e.eval_models([spec])
-                assert status[0] != 0, (case, str(ex))
-            if verbose:
-                print(f"case {case:3d}: rejected by both ({ex})", flush=True)
-            continue
+        specs, want = [], []
+        for _ in range(int(rng.integers(1, 5))):
+            ev = random_model(rng, P)
+            no_sc = bool(rng.random() < 0.15)
+            theta = float(rng.choice([0.0005, 0.001, 0.002]))
+            disc = [float(rng.choice([1.0, rng.uniform(0.5, 1.0)])) for _ in range(P)]
+            specs.append(R.ModelSpec(P, T, theta, disc, 0.0, no_sc, [R.ModelEvent.from_tuple(x) for x in ev]))
+            try:
+                want.append(O.logl(P, max_af, T, theta, disc, no_sc, ev, nvec, pats, cnt, 10 ** 8))
+            except O.OracleError:                   # validateModel rejects it: the engine must reject it too
+                want.append(None)
         for e in engs:
             e.set_problem(nvec, max_af, pats, cnt, 10 ** 8)
-            logl, probs, status = e.eval_models([spec, spec], want_probs=True)
-            assert status[0] == 0, (case, status)
-            nz = probs_o != 0
-            assert np.array_equal(probs[0][~nz], probs_o[~nz]), case
-            err = float(np.max(np.abs(probs[0][nz] - probs_o[nz]) / np.abs(probs_o[nz]))) if nz.any() else 0.0
-            worst = max(worst, err)
-            assert err < 1e-10, (case, P, max_af, err, ev)
-            if np.isfinite(ll_o):
-                assert abs(logl[0] - ll_o) <= 1e-9 * abs(ll_o), (case, logl[0], ll_o)
-            else:                                   # a pattern with count > 0 is unreachable under the model: log 0
-                assert logl[0] == ll_o or (np.isnan(logl[0]) and np.isnan(ll_o)), (case, logl[0], ll_o)
-            assert logl[0] == logl[1] or (np.isnan(logl[0]) and np.isnan(logl[1])), case
-            assert e.stats()["state_steps"] == 2 * w_o, (case, e.stats()["state_steps"], w_o)
+            logl, probs, status = e.eval_models(specs, want_probs=True)
+            steps = 0
+            for m, w in enumerate(want):
+                if w is None:
+                    assert status[m] != 0, (case, m)
+                    continue
+                ll_o, probs_o, w_o = w
+                steps += w_o
+                assert status[m] == 0, (case, m, status)
+                nz = probs_o != 0
+                assert np.array_equal(probs[m][~nz], probs_o[~nz]), (case, m)
+                err = float(np.max(np.abs(probs[m][nz] - probs_o[nz]) / np.abs(probs_o[nz]))) if nz.any() else 0.0
+                worst = max(worst, err)
+                assert err < 1e-10, (case, m, P, max_af, err)
+                if np.isfinite(ll_o):
+                    assert abs(logl[m] - ll_o) <= 1e-9 * abs(ll_o), (case, m, logl[m], ll_o)
+                else:                               # a pattern with count > 0 is unreachable under the model: log 0
+                    assert logl[m] == ll_o or (np.isnan(logl[m]) and np.isnan(ll_o)), (case, m, logl[m], ll_o)
+            assert e.stats()["state_steps"] == steps, (case, e.stats()["state_steps"], steps)
+        ev, no_sc = specs, any(w is None for w in want)
         if verbose:
-            print(f"case {case:3d}: P={P} maxAf={max_af} patterns={len(pats):4d} events={len(ev):2d} noShortcut={int(no_sc)} steps={len(T)} ok", flush=True)
+            print(f"case {case:3d}: P={P} maxAf={max_af} patterns={len(pats):4d} models={len(ev)} rejected={int(no_sc)} steps={len(T)} ok", flush=True)
     for e in engs:
         e.close()
     return worst
