@@ -44,6 +44,10 @@ def run(n_cases=40, seed=1, verbose=True):
         e.set_option("keyed", keyed)
         e.set_option("pattern_mode", pm)
         engs.append(e)
+    e = R.Engine(0)                                   # a trajectory-table budget so small that calls are cut into chunks and
+    e.set_option("ktab_total_mb", 1.0)                # models fall back to the self-contained kernels
+    e.set_option("ktab_model_mb", 0.5)
+    engs.append(e)
     worst = 0.0
     for case in range(n_cases):
         if os.environ.get("FUZZ_BIG"):                 # many branches, many alleles: the multi-branch shapes of the pattern kernels
