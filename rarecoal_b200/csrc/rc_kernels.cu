@@ -1857,7 +1857,7 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsi
 }
 
 #ifndef RC_PAT_MINB
-#define RC_PAT_MINB 7      // measured on C3: 6 -> 16.9 ms, 7 -> 16.2, 8 -> 16.6, 10 -> 18.2 (spills)
+#define RC_PAT_MINB 6      // measured on C3 with the final launch scheme: 5 -> 10.19 ms, 6 -> 10.07, 7 -> 10.22, 8 -> 10.35
 #endif
 #ifndef RC_PATL_MINB
 #define RC_PATL_MINB 6
