@@ -53,8 +53,9 @@ foreign import ccall safe "rc_last_error"  c_rc_last_error  :: Ptr RcCtx -> IO C
 foreign import ccall safe "rc_set_problem" c_rc_set_problem ::
     Ptr RcCtx -> CInt -> CInt -> CInt -> Ptr Int32 -> Ptr Int32 -> Ptr Int64 -> Int64 -> IO CInt
 foreign import ccall safe "rc_set_times"   c_rc_set_times   :: Ptr RcCtx -> CInt -> Ptr Double -> IO CInt
-foreign import ccall safe "rc_eval"        c_rc_eval        ::
-    Ptr RcCtx -> CInt -> Ptr RcEvent -> Ptr Int32 -> Ptr Double -> Ptr Double -> CInt -> Double
+-- mNoShortcut is a field of every ModelSpec (StateSpace.hs:49): rc_eval_models takes one flag per model
+foreign import ccall safe "rc_eval_models" c_rc_eval_models ::
+    Ptr RcCtx -> CInt -> Ptr RcEvent -> Ptr Int32 -> Ptr Double -> Ptr Double -> Ptr Int32 -> Double
     -> Ptr Double -> Ptr Double -> Ptr Int32 -> IO CInt
 
 check :: Ptr RcCtx -> CInt -> IO ()
@@ -103,15 +104,16 @@ evalModels (B200Context ctx) nPat siteRed specs = do
         offs   = scanl (+) 0 (map (length . mEvents) specs)
         thetas = map mTheta specs
         discs  = concatMap mDiscoveryRates specs
-        noSc   = if any mNoShortcut specs then 1 else 0
+        noScs  = map (\m -> if mNoShortcut m then 1 else 0) specs :: [Int32]
     VS.unsafeWith (VS.fromList evs) $ \pev ->
       VS.unsafeWith (VS.fromList (map fromIntegral offs :: [Int32])) $ \poff ->
       VS.unsafeWith (VS.fromList thetas) $ \pth ->
       VS.unsafeWith (VS.fromList discs) $ \pdi ->
+      VS.unsafeWith (VS.fromList noScs) $ \pns ->
       allocaArray (b * nPat) $ \pprobs ->
       allocaArray b $ \plogl ->
       allocaArray b $ \pstat -> do
-        c_rc_eval ctx (fromIntegral b) pev poff pth pdi noSc siteRed pprobs plogl pstat >>= check ctx
+        c_rc_eval_models ctx (fromIntegral b) pev poff pth pdi pns siteRed pprobs plogl pstat >>= check ctx
         probs <- VS.fromList <$> peekArray (b * nPat) pprobs
         logls <- peekArray b plogl
         stats <- peekArray b pstat

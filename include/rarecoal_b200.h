@@ -117,6 +117,12 @@ int rc_eval(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const 
             const double* disc, int noShortcut, double siteRed, double* outProbs, double* outLogl,
             int32_t* outStatus);
 
+/* rc_eval with mNoShortcut per model (StateSpace.hs:49 makes it a field of every ModelSpec): noShortcut[b] != 0 disables
+ * the closed-form tail (Core.hs:80-118) for model b only.                                          */
+int rc_eval_models(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta,
+                   const double* disc, const int32_t* noShortcut /*[B]*/, double siteRed, double* outProbs,
+                   double* outLogl, int32_t* outStatus);
+
 /* Sharded path: like rc_eval, but leaves this rank's partial sums on the DEVICE.
  *   dPartial   : device pointer, [2*B] doubles: (sum cnt_i log p_i, sum p_i) per model, this shard
  *   dProbs     : device pointer or NULL, [B][nPat]; entries of patterns owned by other ranks are 0

@@ -35,6 +35,7 @@ SIGNATURES = {
     "rc_set_times": (C.c_int, [_vp, C.c_int, _dp]),
     "rc_time_steps": (C.c_int, [C.c_int, C.c_int, C.c_double, _dp, C.c_int]),
     "rc_eval": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, C.c_int, C.c_double, _dp, _dp, _ip]),
+    "rc_eval_models": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, _ip, C.c_double, _dp, _dp, _ip]),
     "rc_eval_partial": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, C.c_int, _vp, _vp, _vp, _ip]),
     "rc_finalize": (C.c_int, [_vp, C.c_int, _vp, C.c_double, _vp, _dp]),
     "rc_get_prob": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _evp, C.c_int, C.c_double, _dp, C.c_int, _dp]),

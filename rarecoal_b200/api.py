@@ -342,32 +342,17 @@ class Engine:
             self.set_times(t)
 
     def eval_models(self, models: Sequence[ModelSpec], siteRed=1.0, want_probs=False):
-        """Batch of ModelSpecs (same grid) -> (logl[B], probs[B][nPat] or None, status[B]).  mNoShortcut is one flag per
-        rc_eval call: a batch that mixes both values is evaluated as two calls."""
+        """Batch of ModelSpecs (same grid) -> (logl[B], probs[B][nPat] or None, status[B]).  mNoShortcut is passed per
+        model (rc_eval_models)."""
         B = len(models)
-        flags = [bool(m.mNoShortcut) for m in models]
-        if any(flags) and not all(flags):
-            logl = np.zeros(B)
-            status = np.zeros(B, dtype=np.int32)
-            probs = np.zeros((B, self.nPat)) if want_probs else None
-            steps = 0
-            for f in (False, True):
-                idx = [i for i, g in enumerate(flags) if g == f]
-                l, p, st = self.eval_models([models[i] for i in idx], siteRed, want_probs)
-                logl[idx], status[idx] = l, st
-                if want_probs:
-                    probs[idx] = p
-                steps += self.stats()["state_steps"]
-            self._mixed_state_steps = steps
-            return logl, probs, status
-        self._mixed_state_steps = None
         self._ensure_times(models)
         ev, off, theta, disc = self._pack(models)
+        ns = _i32([1 if m.mNoShortcut else 0 for m in models])
         logl = np.zeros(B)
         status = np.zeros(B, dtype=np.int32)
         probs = np.zeros((B, self.nPat)) if want_probs else None
-        rc = self._lib.rc_eval(self._h, B, ev, _ip(off), _dp(theta), _dp(disc), int(models[0].mNoShortcut),
-                               float(siteRed), _dp(probs) if want_probs else None, _dp(logl), _ip(status))
+        rc = self._lib.rc_eval_models(self._h, B, ev, _ip(off), _dp(theta), _dp(disc), _ip(ns), float(siteRed),
+                                      _dp(probs) if want_probs else None, _dp(logl), _ip(status))
         self._check(rc)
         return logl, probs, status
 
@@ -404,10 +389,7 @@ class Engine:
     def stats(self):
         st = L.rc_stats()
         self._check(self._lib.rc_last_stats(self._h, C.byref(st)))
-        d = {f: getattr(st, f) for f, _ in L.rc_stats._fields_}
-        if getattr(self, "_mixed_state_steps", None) is not None:      # eval_models ran as two calls: the sum of both
-            d["state_steps"] = self._mixed_state_steps
-        return d
+        return {f: getattr(st, f) for f, _ in L.rc_stats._fields_}
 
     def fp64_peak_tflops(self):
         out = C.c_double(0.0)

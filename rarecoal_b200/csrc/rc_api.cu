@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -78,9 +79,12 @@ struct PlanEntry {
     RcPlanDev d;
     std::vector<void*> allocs;
     bool allShortcut = false;
+    size_t allocBytes = 0, bytes = 0;    // device bytes uploaded so far / accounted in the cache
+    long long lastUse = 0;               // serial of the last eval call that used the plan (LRU)
     void release() {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
+        allocBytes = 0;
     }
 };
 
@@ -137,6 +141,13 @@ struct rc_ctx {
     DevBuf dDts;
     // plans
     std::map<std::string, PlanEntry*> plans;
+    size_t planBytes = 0;                // device memory held by cached plans
+    long long evalSerial = 0;            // incremented per eval_chunk
+    int optPlanCacheMax = 64;            // "plan_cache_max"
+    double optPlanCacheMB = 49152.0;     // "plan_cache_mb"
+    // counters since rc_create (rc_stats reports the per-call deltas)
+    long long planMisses = 0, planEvictions = 0;
+    double planBuildMs = 0.0;
     // eval scratch
     DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc;
     // options (rc_set_option)
@@ -172,6 +183,7 @@ struct rc_ctx {
             delete kv.second;
         }
         plans.clear();
+        planBytes = 0;
     }
 };
 
@@ -333,26 +345,14 @@ int upload(rc_ctx* ctx, PlanEntry* pe, const std::vector<T>& v, const T** out) {
     size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
     CK(cudaMalloc(&p, n));
     pe->allocs.push_back(p);
+    pe->allocBytes += n;
     if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<const T*>(p);
     return RC_OK;
 }
 
-int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
-    auto it = ctx->plans.find(mh.sig);
-    if (it != ctx->plans.end()) {
-        mh.plan = it->second;
-        return RC_OK;
-    }
-    *hit = false;
-    PlanEntry* pe = new PlanEntry();
-    std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
-                                   mh.hasSplit, ctx->smemOptin, pe->h, ctx->optPattern);
-    if (!e.empty()) {
-        delete pe;
-        ctx->err = e;
-        return RC_ERR_UNSUPPORTED;
-    }
+// Device copy of a built plan.  On failure the caller releases what was uploaded so far.
+int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     RcPlanDev& d = pe->d;
     std::memset(&d, 0, sizeof d);
     const rc::PlanHost& h = pe->h;
@@ -417,8 +417,73 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     d.patGlobal = (const int32_t*)ctx->dPatGlobal.p;
     pe->allShortcut = true;
     for (uint8_t f : h.shortcutOK) pe->allShortcut = pe->allShortcut && f;
+    return RC_OK;
+}
+
+// Plan cache: least-recently-used eviction (an optimiser that crosses event orders keeps its working set; the plans of
+// the batch being resolved are never evicted).  Limits: "plan_cache_max" plans and "plan_cache_mb" MiB of device memory.
+void evict_plans(rc_ctx* ctx, size_t needBytes) {
+    auto over = [&]() {
+        return (int)ctx->plans.size() >= ctx->optPlanCacheMax ||
+               (double)(ctx->planBytes + needBytes) > ctx->optPlanCacheMB * 1048576.0;
+    };
+    bool synced = false;
+    while (!ctx->plans.empty() && over()) {
+        auto victim = ctx->plans.end();
+        for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it)
+            if (it->second->lastUse < ctx->evalSerial && (victim == ctx->plans.end() || it->second->lastUse < victim->second->lastUse))
+                victim = it;
+        if (victim == ctx->plans.end()) break;          // everything left belongs to the current batch
+        if (!synced) { cudaDeviceSynchronize(); synced = true; }   // launches of earlier calls may still read the plan
+        ctx->planBytes -= victim->second->bytes;
+        victim->second->release();
+        delete victim->second;
+        ctx->plans.erase(victim);
+        ++ctx->planEvictions;
+    }
+}
+
+int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
+    auto it = ctx->plans.find(mh.sig);
+    if (it != ctx->plans.end()) {
+        mh.plan = it->second;
+        mh.plan->lastUse = ctx->evalSerial;
+        return RC_OK;
+    }
+    *hit = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    PlanEntry* pe = new PlanEntry();
+    std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
+                                   mh.hasSplit, ctx->smemOptin, pe->h, ctx->optPattern);
+    if (!e.empty()) {
+        delete pe;
+        ctx->err = e;
+        return RC_ERR_UNSUPPORTED;
+    }
+    evict_plans(ctx, 0);
+    int rc = upload_plan(ctx, pe);
+    if (rc != RC_OK && cudaPeekAtLastError() == cudaErrorMemoryAllocation) {
+        // out of device memory: drop every plan no model of this batch uses and try once more
+        cudaGetLastError();
+        pe->release();
+        const int keepMax = ctx->optPlanCacheMax;
+        ctx->optPlanCacheMax = 1;
+        evict_plans(ctx, 0);
+        ctx->optPlanCacheMax = keepMax;
+        rc = upload_plan(ctx, pe);
+    }
+    if (rc != RC_OK) {
+        pe->release();
+        delete pe;
+        return rc;
+    }
+    pe->bytes = pe->allocBytes;
+    ctx->planBytes += pe->bytes;
+    pe->lastUse = ctx->evalSerial;
     ctx->plans[mh.sig] = pe;
     mh.plan = pe;
+    ++ctx->planMisses;
+    ctx->planBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return RC_OK;
 }
 
@@ -442,8 +507,8 @@ long long count_state_steps(const ModelHost& mh, const rc::PlanHost& h, int T) {
 
 // The whole evaluation up to the per-model partial sums (left on the device).
 int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
-               int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus, long long* maxPairsOut) {
-    if (ctx->plans.size() >= 64) ctx->clear_plans();   // bounded plan cache
+               const int32_t* noShortcut /*[B]*/, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus, long long* maxPairsOut) {
+    ++ctx->evalSerial;
     const int P = ctx->P, A1 = ctx->maxAf + 1, T = (int)ctx->times.size();
     const int rowLen = rc_row_len(P, A1);
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -457,7 +522,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
             mh.status = RC_ERR_COMP;
             mh.err = ctx->compErrMsg;
         } else {
-            resolve_model(ctx, ev + evOff[b], evOff[b + 1] - evOff[b], disc + (size_t)b * P, noShortcut, mh);
+            resolve_model(ctx, ev + evOff[b], evOff[b + 1] - evOff[b], disc + (size_t)b * P, noShortcut[b], mh);
             if (mh.status == RC_OK && ctx->nPat > 0) {
                 int rc = get_plan(ctx, mh, &hit);
                 if (rc != RC_OK) return rc;
@@ -545,8 +610,9 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 maxRowPairs = std::max<long long>(maxRowPairs, hp.ep[(size_t)e].rowPairs);
             }
             M.mode = (ctx->optKeyed && hp.nFastBins > 0 && pairs <= ktabModelMax && ktabPairs + pairs <= ktabTotalMax) ? 1 : 0;
-            if (maxPairsOut && pairs > *maxPairsOut) *maxPairsOut = pairs;
             if (M.mode == 1) {
+                // only models that own a slice of the trajectory table bound the chunk size
+                if (maxPairsOut && pairs > *maxPairsOut) *maxPairsOut = pairs;
                 ktabPairs += pairs;
                 M.aEndOff = aEndDoubles;
                 M.aShortOff = aShortDoubles;
@@ -750,7 +816,7 @@ int collect_stats(rc_ctx* ctx);
 // Evaluates B models in chunks sized so that the trajectory tables of one chunk stay inside the memory budget
 // ("ktab_total_mb"); chunks run back to back on the same stream.
 int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
-              int noShortcut, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus) {
+              const int32_t* noShortcut /*[B]*/, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus) {
     if (ctx->P == 0) { ctx->err = "rc_set_problem has not been called"; return RC_ERR_ARG; }
     if (ctx->times.empty()) { ctx->err = "rc_set_times has not been called"; return RC_ERR_ARG; }
     if (B <= 0) return RC_OK;
@@ -761,11 +827,13 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     while (done < B) {
         int n = std::min(B - done, std::max(1, std::min(ctx->chunkHint, 32768)));
         long long maxPairs = 0;
-        int rc = eval_chunk(ctx, n, ev, evOff + done, theta + done, disc + (size_t)done * ctx->P, noShortcut, dPartial + 2 * (size_t)done,
+        int rc = eval_chunk(ctx, n, ev, evOff + done, theta + done, disc + (size_t)done * ctx->P, noShortcut + done, dPartial + 2 * (size_t)done,
                             dProbs ? dProbs + (size_t)done * ctx->nPatGlobal : nullptr, st, outStatus ? outStatus + done : nullptr,
                             &maxPairs);
         if (rc != RC_OK) return rc;
+        // a chunk without a keyed model says nothing about the table: let the hint grow back
         if (maxPairs > 0) ctx->chunkHint = (int)std::max<long long>(1, std::min<long long>(32768, totalMax / maxPairs));
+        else ctx->chunkHint = std::min(32768, std::max(ctx->chunkHint, 256));
         done += n;
         ++nChunks;
         if (done < B || nChunks > 1) {      // several chunks: fold this chunk's counters into the running totals
@@ -1002,18 +1070,22 @@ int rc_set_times(rc_ctx* ctx, int T, const double* t) {
     ctx->err.clear();
     if (T < 1 || !t) { ctx->err = "rc_set_times: empty grid"; return RC_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
-    ctx->times.assign(t, t + T);
-    ctx->dts.resize((size_t)T);
+    // validate the whole grid before anything in the context changes
+    std::vector<double> dts((size_t)T);
     // deltaT = nextTime - t; t += deltaT (Core.hs:129,135) — the running clock is kept as the reference keeps it
     double clock = 0.0;
     for (int s = 0; s < T; ++s) {
-        double dt = t[s] - clock;
-        ctx->dts[(size_t)s] = dt;
-        if (dt > 0) clock = clock + dt;
+        if (!std::isfinite(t[s])) { ctx->err = "rc_set_times: grid must be finite"; return RC_ERR_ARG; }
         if (s > 0 && !(t[s] >= t[s - 1])) { ctx->err = "rc_set_times: grid must be non-decreasing"; return RC_ERR_ARG; }
+        double dt = t[s] - clock;
+        dts[(size_t)s] = dt;
+        if (dt > 0) clock = clock + dt;
     }
+    CK(cudaDeviceSynchronize());        // launches of an earlier call may still read the old grid
     CK(ctx->dDts.ensure((size_t)T * sizeof(double)));
-    CK(cudaMemcpy(ctx->dDts.p, ctx->dts.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->dDts.p, dts.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->times.assign(t, t + T);
+    ctx->dts.swap(dts);
     ctx->clear_plans();
     return RC_OK;
 }
@@ -1037,7 +1109,8 @@ int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff
     ctx->err.clear();
     if (B < 0 || !evOff || !theta || !disc || !dPartial) { ctx->err = "rc_eval_partial: null argument"; return RC_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
-    return eval_impl(ctx, B, ev, evOff, theta, disc, noShortcut, dPartial, dProbs, (cudaStream_t)stream, outStatus);
+    std::vector<int32_t> ns((size_t)std::max(B, 1), noShortcut ? 1 : 0);
+    return eval_impl(ctx, B, ev, evOff, theta, disc, ns.data(), dPartial, dProbs, (cudaStream_t)stream, outStatus);
 }
 
 int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRed, void* stream, double* outLogl) {
@@ -1060,9 +1133,15 @@ int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRe
 
 int rc_eval(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
             int noShortcut, double siteRed, double* outProbs, double* outLogl, int32_t* outStatus) {
+    std::vector<int32_t> ns((size_t)std::max(B, 1), noShortcut ? 1 : 0);
+    return rc_eval_models(ctx, B, ev, evOff, theta, disc, ns.data(), siteRed, outProbs, outLogl, outStatus);
+}
+
+int rc_eval_models(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
+                   const int32_t* noShortcut, double siteRed, double* outProbs, double* outLogl, int32_t* outStatus) {
     if (!ctx) return RC_ERR_ARG;
     ctx->err.clear();
-    if (B < 0 || !evOff || !theta || !disc || !outLogl) { ctx->err = "rc_eval: null argument"; return RC_ERR_ARG; }
+    if (B < 0 || !evOff || !theta || !disc || !outLogl || !noShortcut) { ctx->err = "rc_eval: null argument"; return RC_ERR_ARG; }
     if (B == 0) return RC_OK;
     CK(cudaSetDevice(ctx->device));
     CK(ctx->dPartial.ensure((size_t)2 * B * sizeof(double)));
@@ -1121,6 +1200,8 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
             ctx->optPattern = v;
         }
     }
+    else if (n == "plan_cache_max") ctx->optPlanCacheMax = std::max(1, (int)value);
+    else if (n == "plan_cache_mb") ctx->optPlanCacheMB = std::max(1.0, value);
     else if (n == "ktab_model_mb") ctx->optKtabModelMB = value;
     else if (n == "ktab_total_mb") ctx->optKtabTotalMB = value;
     else { ctx->err = "rc_set_option: unknown option " + n; return RC_ERR_ARG; }
@@ -1182,6 +1263,7 @@ int rc_validate_model(int P, const double* disc, const rc_event* ev, int nEv, ch
 
 double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv) {
     // getRegularizationPenalty (StateSpace.hs:199-221): sizes tracked through SetPopSize events only
+    if (P < 1 || nEv < 0 || (nEv > 0 && !ev)) return std::nan("");
     std::vector<rc_event> s = sort_events(ev, nEv);
     std::vector<double> size((size_t)std::max(P, 1), 1.0);
     auto term = [reg](double from, double to) {
@@ -1189,7 +1271,12 @@ double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv) {
         return reg * ((ratio - 1.0) * (ratio - 1.0));
     };
     double total = 0.0;
+    // the reference indexes its size vector with V.! / V.// and fails on a bad branch (StateSpace.hs:205-215); here a bad index
+    // yields NaN, which minFunc turns into the 1e20 penalty (MaxUtils.hs:72-75) and the Python layer into RarecoalModelException
+    auto bad = [P](int i) { return i < 0 || i >= P; };
     for (const rc_event& e : s) {
+        if ((e.type == RC_EV_POPSIZE && bad(e.k)) || (e.type == RC_EV_JOIN && (bad(e.k) || bad(e.l))))
+            return std::nan("");
         if (e.type == RC_EV_POPSIZE) {
             if (e.t != 0.0) total = total + term(size[(size_t)e.k], e.v);
             size[(size_t)e.k] = e.v;

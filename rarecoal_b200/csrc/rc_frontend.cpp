@@ -430,17 +430,23 @@ int rc_hist_problem(const rc_hist* H, int maxAf, int minAf, const int32_t* condi
     int useMax = maxAf == 0 ? h.maxM : maxAf;
     if (useMax > h.maxM || useMax < h.minM) { copy_out("illegal maxAF", err, errCap); return -RC_ERR_HIST; }      // Utils.hs:153
     if (minAf > useMax || minAf < h.minM) { copy_out("illegal minAf", err, errCap); return -RC_ERR_HIST; }         // Utils.hs:162
-    std::vector<int> cond(h.conditionOn);
-    for (int i = 0; i < nCond; ++i) {
-        if (conditionOn[i] < 0 || conditionOn[i] >= P) { copy_out("illegal conditionOn indices", err, errCap); return -RC_ERR_HIST; }
-        cond.push_back(conditionOn[i]);
-    }
-    std::vector<std::vector<int>> excl(h.exclude);
-    for (int i = 0; i < nExclude; ++i) excl.emplace_back(exclude + (size_t)i * P, exclude + (size_t)(i + 1) * P);
+    // filterConditionOn / filterExcludePatterns (Utils.hs:129-149) REPLACE raConditionOn / raExcludePatterns when the option
+    // is given; the lists of the file's header are kept only when the option is empty
+    std::vector<int> cond;
+    if (nCond > 0) {
+        for (int i = 0; i < nCond; ++i) {
+            if (conditionOn[i] < 0 || conditionOn[i] >= P) { copy_out("illegal conditionOn indices", err, errCap); return -RC_ERR_HIST; }
+            cond.push_back(conditionOn[i]);
+        }
+    } else cond = h.conditionOn;
+    std::vector<std::vector<int>> excl;
+    if (nExclude > 0)
+        for (int i = 0; i < nExclude; ++i) excl.emplace_back(exclude + (size_t)i * P, exclude + (size_t)(i + 1) * P);
+    else excl = h.exclude;
     // validateBranchNameCongruency (Utils.hs:199-206)
     std::vector<int> src((size_t)nModelBranches, -1);
     for (int b = 0; b < nModelBranches; ++b)
-        for (int q = 0; q < P; ++q) if (h.names[(size_t)q] == modelBranches[b]) src[(size_t)b] = q;
+        for (int q = 0; q < P; ++q) if (h.names[(size_t)q] == modelBranches[b]) { src[(size_t)b] = q; break; }   // elemIndex: first match (Utils.hs:118)
     for (int q = 0; q < P; ++q) {
         bool found = false;
         for (int b = 0; b < nModelBranches; ++b) found = found || h.names[(size_t)q] == modelBranches[b];

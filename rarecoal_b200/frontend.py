@@ -234,6 +234,8 @@ def loadHistogram(histOpts: HistogramOptions, modelBranches: Sequence[str]) -> H
         max_af = histOpts.optMaxAf if histOpts.optMaxAf else mx.value
         nB = len(modelBranches)
         mb = (C.c_char_p * nB)(*[b.encode() for b in modelBranches])
+        if any(len(x) != nP.value for x in histOpts.optExcludePatterns):                 # Utils.hs:143
+            raise RarecoalHistogramException("illegal excludePattern(s)" + str(list(histOpts.optExcludePatterns)))
         cond = np.array(list(histOpts.optConditionOn) or [0], dtype=np.int32)
         excl = np.array(list(histOpts.optExcludePatterns) or [[0] * nP.value], dtype=np.int32)
         ip = C.POINTER(C.c_int32)

@@ -114,6 +114,32 @@ def test_histogram_filters_and_branch_mapping(fourpop):
         F.loadHistogram(F.HistogramOptions("/nonexistent/file", 1, 4), fourpop["branches"])
 
 
+def test_histogram_header_lists_are_replaced_by_options(tmp_path):
+    # filterConditionOn / filterExcludePatterns (Utils.hs:129-149) replace raConditionOn / raExcludePatterns when the
+    # option is given; computeStandardOrder (Utils.hs:169-177) then uses the option's lists only.  elemIndex takes the
+    # first of two equal histogram names (Utils.hs:118).
+    path = tmp_path / "h.txt"
+    path.write_text("NAMES=A,B,A\nN=4,4,4\nMAX_M=3\nTOTAL_SITES=1000\nCONDITION_ON=0\nEXCLUDE_PATTERNS=1,1,0;1,0,0\n"
+                    "1,0,0 5\n0,1,0 7\n1,1,0 3\n0,1,1 2\n")
+    std = R.computeAllConfigs(3, [4, 4, 4])
+
+    def expect(cond, excl):
+        keep = [p for p in std.tolist() if all(p[i] > 0 for i in cond) and p not in excl]
+        return [[p[0], p[1]] for p in keep]            # model branches [A, B]: A maps to the FIRST histogram column
+
+    file_lists = F.loadHistogram(F.HistogramOptions(str(path), 1, 3), ["A", "B"])
+    assert file_lists.patterns.tolist() == expect([0], [[1, 1, 0], [1, 0, 0]])
+    cli_cond = F.loadHistogram(F.HistogramOptions(str(path), 1, 3, [1]), ["A", "B"])
+    assert cli_cond.patterns.tolist() == expect([1], [[1, 1, 0], [1, 0, 0]])          # header's [0] is gone
+    cli_excl = F.loadHistogram(F.HistogramOptions(str(path), 1, 3, [], [[0, 1, 1]]), ["A", "B"])
+    assert cli_excl.patterns.tolist() == expect([0], [[0, 1, 1]])                     # header's exclusions are gone
+    assert cli_excl.nVec.tolist() == [4, 4]
+    with pytest.raises(R.RarecoalHistogramException):
+        F.loadHistogram(F.HistogramOptions(str(path), 1, 3, [], [[0, 1]]), ["A", "B"])  # Utils.hs:143: wrong length
+    with pytest.raises(R.RarecoalHistogramException):
+        F.loadHistogram(F.HistogramOptions(str(path), 1, 3, [3]), ["A", "B"])           # Utils.hs:133
+
+
 def test_haskell_show():
     for x, s in ((5.503134217048233e7, "5.503134217048233e7"), (1.9060110218875406, "1.9060110218875406"),
                  (1.5951118620536157e-2, "1.5951118620536157e-2"), (0.1, "0.1"), (1.0, "1.0"), (100.0, "100.0"),
