@@ -44,8 +44,14 @@ enum {
  *   type 0  Join k l        : branch l merges into k                       (v unused)
  *   type 1  Split k l m     : fraction v=m of branch l moves to k
  *   type 2  SetPopSize k p  : v = p                                        (l unused)
- *   type 3  SetFreeze k b   : v != 0 -> frozen                             (l unused)            */
-enum { RC_EV_JOIN = 0, RC_EV_SPLIT = 1, RC_EV_POPSIZE = 2, RC_EV_FREEZE = 3 };
+ *   type 3  SetFreeze k b   : v != 0 -> frozen                             (l unused)
+ *   type 4  SetGrowthRate k r : v = r                                      (l unused)
+ *           NOT a reference constructor (StateSpace.hs:36-40 has four); BASELINE.json's north_star names it.  It is sugar:
+ *           from its time t0 on, N_k(t) = N_k(t0) exp(-r (t - t0)) (t = time into the past) until the next SetPopSize /
+ *           SetGrowthRate on k or the Join that removes k, realised as one `SetPopSize k N_k(t_s)` at every grid point
+ *           t0 < t_s < tStop (rc_desugar_growth returns that list).  r = 0 ends a growth phase at the current size.
+ *           It contributes nothing to the regularisation penalty.                                                  */
+enum { RC_EV_JOIN = 0, RC_EV_SPLIT = 1, RC_EV_POPSIZE = 2, RC_EV_FREEZE = 3, RC_EV_GROWTH = 4 };
 typedef struct {
     double t;
     int32_t type;
@@ -67,6 +73,11 @@ typedef struct {
     int32_t plan_cache_hit;  /* 1 if every model reused a cached transition plan                        */
     int32_t n_epochs;        /* structural epochs of the last model                                     */
     int32_t n_steps;         /* grid steps executed by the last model                                   */
+    int64_t fp64_instr;      /* FP64 instructions (DMUL / DFMA, thread level) the propagation kernels of the trajectory-key */
+                             /* tier executed for these models: numerator of the pipe-level roofline      */
+    double plan_build_ms;    /* host time spent building and uploading transition plans in this call                     */
+    int32_t plan_misses;     /* event structures of this call that were not in the plan cache                            */
+    int32_t plan_evictions;  /* plans evicted (least recently used first) to make room                                   */
 } rc_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -138,6 +149,30 @@ int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff
 int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRed, void* stream,
                 double* outLogl);
 
+/* ---- multi-GPU (the reference's fan-out over one machine's cores, MaxUtils.hs:108-110, taken across GPUs) ---------- */
+
+/* One context that drives nDevices GPUs of this process (devices == NULL: 0 .. nDevices-1).  Every call of this header
+ * works on it; rc_eval / rc_eval_models shard the batch over the devices themselves:
+ *   - B >= nDevices: models sharded — device d evaluates a contiguous slice of the models on all patterns, no collective;
+ *   - B <  nDevices: patterns sharded — every device evaluates its pattern shard of all models, the 2*B partial sums
+ *     (and the probabilities when outProbs != NULL) are summed with ncclAllReduce over NVLink, device 0 finalises.
+ * rc_set_option(ctx, "multi_shard", 0 auto | 1 models | 2 patterns) forces one.  NCCL is bound at run time (libnccl.so.2);
+ * without it the pattern-sharded path fails with RC_ERR_CUDA — there is no substitute path.  rc_eval_partial /
+ * rc_finalize / rc_set_shard return RC_ERR_ARG on such a context (their device pointers belong to one device).          */
+int rc_create_multi(int nDevices, const int32_t* devices, rc_ctx** out);
+/* Devices behind a context (1 for rc_create).                                                       */
+int rc_device_count(rc_ctx* ctx);
+
+/* One process per GPU (MPI / torchrun style): rank 0 obtains a 128-byte NCCL unique id (ncclGetUniqueId), the launcher
+ * hands it to every rank, and each rank joins its context to the communicator.  rc_comm_init also fixes the pattern shard
+ * (rc_set_shard(rank, nRanks)); from then on rc_eval / rc_eval_models evaluate the rank's shard, all-reduce the partial
+ * sums (and probabilities) with ncclAllReduce on the context's stream, and return the full result on EVERY rank — all
+ * ranks must make the same calls with the same models.  rc_comm_allreduce is the same sum for callers of rc_eval_partial
+ * (in place, device pointer, `stream` as in rc_eval_partial).                                                         */
+int rc_comm_unique_id(void* out128);
+int rc_comm_init(rc_ctx* ctx, int nRanks, int rank, const void* uniqueId128);
+int rc_comm_allreduce(rc_ctx* ctx, double* dBuf, int64_t n, void* stream);
+
 /* getProb for ONE pattern (Core.hs:38-56; the `rarecoal prob` command, Prob.hs:28): builds a
  * one-pattern problem on a scratch context state.  nVec/config have length P.                      */
 int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_t* config,
@@ -150,7 +185,9 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
  *   "pattern_mode" (1)     box-shaped live sets of at most 36 states run one pattern per thread; 0 sends every pattern
  *                          to the row / state kernels (used by the parity tests to cover those kernels too)
  *   "ktab_model_mb" (1024) largest trajectory table of one model; a model above it uses the self-contained kernels
- *   "ktab_total_mb" (12288) largest trajectory table memory of one call                                   */
+ *   "ktab_total_mb" (12288) largest trajectory table memory of one call
+ *   "plan_cache_max" (64)  transition plans (one per event structure) kept per context, least recently used evicted first
+ *   "plan_cache_mb" (49152) device memory the cached plans may hold                                        */
 int rc_set_option(rc_ctx* ctx, const char* name, double value);
 
 int rc_last_stats(rc_ctx* ctx, rc_stats* out);
@@ -169,6 +206,9 @@ int rc_validate_model(int P, const double* disc, const rc_event* ev, int nEv, ch
 double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv);
 /* choose n k (Utils.hs:208-210).                                                                   */
 double rc_choose(int n, int k);
+/* The model's events with every SetGrowthRate (RC_EV_GROWTH) rewritten into per-grid-step SetPopSize events, stably
+ * sorted by time — what rc_eval evaluates.  Returns the number of events, fills out up to cap.                     */
+int rc_desugar_growth(int T, const double* times, const rc_event* ev, int nEv, rc_event* out, int cap);
 
 /* The pattern indices rc_set_shard(rank, world) assigns to `rank` (host only): returns the count, fills out up to cap.
  * Shards of all ranks are disjoint and cover every pattern.                                                     */

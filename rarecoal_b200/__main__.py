@@ -20,6 +20,9 @@ def _general(ap):
     ap.add_argument("--lingen", type=int, default=400)
     ap.add_argument("--tMax", type=float, default=20.0)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--nrGpus", type=int, default=1,
+                    help="GPUs of this machine to use (rc_create_multi): a batch of models is sharded by model, a single "
+                         "likelihood by pattern with an NCCL all-reduce of the partial sums")
 
 
 def _model(ap):
@@ -58,7 +61,7 @@ def _params(a):
 def _load(a, mt):
     ho = F.HistogramOptions(a.histogram, a.minAf, a.maxAf, a.conditionOn, a.excludePattern, a.effectiveSitesReduction)
     hp = F.loadHistogram(ho, mt.mtBranchNames)
-    eng = Engine(a.device)
+    eng = Engine(a.device) if a.nrGpus <= 1 else Engine(nrGpus=a.nrGpus)
     eng.set_problem(hp.nVec, hp.maxAf, hp.patterns, hp.counts, hp.totalSites)
     return hp, eng
 

@@ -8,7 +8,7 @@ SO = os.environ.get("RARECOAL_B200_LIB", os.path.join(HERE, "librarecoal_b200.so
 
 RC_OK, RC_ERR_MODEL, RC_ERR_COMP, RC_ERR_ARG, RC_ERR_CUDA, RC_ERR_UNSUPPORTED = 0, 1, 2, -1, -2, -3
 RC_ERR_TEMPLATE, RC_ERR_HIST = 3, 4
-RC_EV_JOIN, RC_EV_SPLIT, RC_EV_POPSIZE, RC_EV_FREEZE = 0, 1, 2, 3
+RC_EV_JOIN, RC_EV_SPLIT, RC_EV_POPSIZE, RC_EV_FREEZE, RC_EV_GROWTH = 0, 1, 2, 3, 4
 
 
 class rc_event(C.Structure):
@@ -18,7 +18,9 @@ class rc_event(C.Structure):
 class rc_stats(C.Structure):
     _fields_ = [("state_steps", C.c_int64), ("slots", C.c_int64), ("kernel_ms", C.c_double),
                 ("traj_ms", C.c_double), ("tables_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32),
-                ("plan_cache_hit", C.c_int32), ("n_epochs", C.c_int32), ("n_steps", C.c_int32)]
+                ("plan_cache_hit", C.c_int32), ("n_epochs", C.c_int32), ("n_steps", C.c_int32),
+                ("fp64_instr", C.c_int64), ("plan_build_ms", C.c_double), ("plan_misses", C.c_int32),
+                ("plan_evictions", C.c_int32)]
 
 
 _dp, _ip, _lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
@@ -38,6 +40,11 @@ SIGNATURES = {
     "rc_eval_models": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, _ip, C.c_double, _dp, _dp, _ip]),
     "rc_eval_partial": (C.c_int, [_vp, C.c_int, _evp, _ip, _dp, _dp, C.c_int, _vp, _vp, _vp, _ip]),
     "rc_finalize": (C.c_int, [_vp, C.c_int, _vp, C.c_double, _vp, _dp]),
+    "rc_create_multi": (C.c_int, [C.c_int, _ip, C.POINTER(_vp)]),
+    "rc_device_count": (C.c_int, [_vp]),
+    "rc_comm_unique_id": (C.c_int, [_vp]),
+    "rc_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "rc_comm_allreduce": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "rc_get_prob": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _evp, C.c_int, C.c_double, _dp, C.c_int, _dp]),
     "rc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "rc_last_stats": (C.c_int, [_vp, C.POINTER(rc_stats)]),
@@ -46,6 +53,7 @@ SIGNATURES = {
     "rc_validate_model": (C.c_int, [C.c_int, _dp, _evp, C.c_int, C.c_char_p, C.c_int]),
     "rc_reg_penalty": (C.c_double, [C.c_int, C.c_double, _evp, C.c_int]),
     "rc_choose": (C.c_double, [C.c_int, C.c_int]),
+    "rc_desugar_growth": (C.c_int, [C.c_int, _dp, _evp, C.c_int, _evp, C.c_int]),
     "rc_shard_patterns": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.c_int, _ip, C.c_int]),
     "rc_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp, _evp, C.c_int, C.c_int,
                                 _lp, _lp, _ip, _ip, _ip]),

@@ -74,6 +74,14 @@ class SetFreeze:
 
 
 @dataclass(frozen=True)
+class SetGrowthRate:
+    """Not a reference constructor (StateSpace.hs:36-40): sugar for one SetPopSize per grid step, see
+    include/rarecoal_b200.h (RC_EV_GROWTH) and desugarGrowth."""
+    k: int
+    r: float
+
+
+@dataclass(frozen=True)
 class ModelEvent:
     meTime: float
     meEventType: object
@@ -88,6 +96,8 @@ class ModelEvent:
             return (self.meTime, L.RC_EV_POPSIZE, e.k, 0, e.p)
         if isinstance(e, SetFreeze):
             return (self.meTime, L.RC_EV_FREEZE, e.k, 0, 1.0 if e.b else 0.0)
+        if isinstance(e, SetGrowthRate):
+            return (self.meTime, L.RC_EV_GROWTH, e.k, 0, e.r)
         raise TypeError(e)
 
     @staticmethod
@@ -95,7 +105,8 @@ class ModelEvent:
         tt, ty, k, l, v = t
         et = {L.RC_EV_JOIN: lambda: Join(int(k), int(l)), L.RC_EV_SPLIT: lambda: Split(int(k), int(l), float(v)),
               L.RC_EV_POPSIZE: lambda: SetPopSize(int(k), float(v)),
-              L.RC_EV_FREEZE: lambda: SetFreeze(int(k), bool(v))}[int(ty)]()
+              L.RC_EV_FREEZE: lambda: SetFreeze(int(k), bool(v)),
+              L.RC_EV_GROWTH: lambda: SetGrowthRate(int(k), float(v))}[int(ty)]()
         return ModelEvent(float(tt), et)
 
 
@@ -189,7 +200,25 @@ def validateModel(modelSpec: ModelSpec):
 def getRegularizationPenalty(modelSpec: ModelSpec):
     """StateSpace.hs:199-221."""
     ev = _events_array(modelSpec.mEvents)
-    return L.load().rc_reg_penalty(modelSpec.mNrPops, modelSpec.mPopSizeRegularization, ev, len(modelSpec.mEvents))
+    v = L.load().rc_reg_penalty(modelSpec.mNrPops, modelSpec.mPopSizeRegularization, ev, len(modelSpec.mEvents))
+    if v != v and not any(e.as_tuple()[4] != e.as_tuple()[4] for e in modelSpec.mEvents):
+        # a branch index outside [0, nrPops): the reference's V.! / V.// fails here (StateSpace.hs:205-215)
+        raise RarecoalModelException("illegal branch index in getRegularizationPenalty")
+    return v
+
+
+def desugarGrowth(times, events):
+    """Events (ModelEvents or (t, type, k, l, v) tuples) with every SetGrowthRate rewritten into per-grid-step SetPopSize
+    events, stably sorted by time (rc_desugar_growth) — the model the likelihood path actually evaluates."""
+    t = _f64(times)
+    ev = _events_array(events)
+    lib = L.load()
+    n = lib.rc_desugar_growth(len(t), _dp(t), ev, len(events), None, 0)
+    if n < 0:
+        raise ValueError("rc_desugar_growth: bad arguments")
+    out = (L.rc_event * max(1, n))()
+    lib.rc_desugar_growth(len(t), _dp(t), ev, len(events), out, n)
+    return [(out[i].t, out[i].type, out[i].k, out[i].l, out[i].v) for i in range(n)]
 
 
 def shardPatterns(patterns, rank, world):
@@ -273,16 +302,26 @@ class SpectrumEntry:
 
 
 class Engine:
-    """One CUDA context bound to one GPU (rc_ctx).  Holds the histogram-side problem
-    (patterns, nVec, counts, total sites) and evaluates ModelSpecs against it."""
+    """One rc_ctx: bound to one GPU (`Engine(device)`), or driving several GPUs of this process (`Engine(devices=[0, 1, ..])`
+    / `Engine(nrGpus=N)`, rc_create_multi).  Holds the histogram-side problem (patterns, nVec, counts, total sites) and
+    evaluates ModelSpecs against it."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None, nrGpus=None):
         self._lib = L.load()
         h = C.c_void_p()
-        rc = self._lib.rc_create(int(device), C.byref(h))
+        if nrGpus is not None and devices is None and nrGpus > 1:
+            devices = list(range(int(nrGpus)))
+        if devices is not None and len(devices) > 1:
+            dv = _i32(devices)
+            rc = self._lib.rc_create_multi(len(dv), _ip(dv), C.byref(h))
+            device = int(dv[0])
+        else:
+            if devices is not None and len(devices) == 1:
+                device = int(devices[0])
+            rc = self._lib.rc_create(int(device), C.byref(h))
         if rc != L.RC_OK:
             raise RarecoalDeviceError(
-                f"rc_create(device={device}) failed with {rc}: no usable CUDA device. "
+                f"rc_create(device={device}, devices={devices}) failed with {rc}: no usable CUDA device. "
                 "rarecoal_b200 has no CPU fallback.")
         self._h = h
         self.device = device
@@ -314,6 +353,28 @@ class Engine:
                                              cnt.ctypes.data_as(C.POINTER(C.c_int64)), int(totalSites)))
         self.P, self.maxAf, self.nPat = len(nv), int(maxAf), len(pats)
         self.patterns, self.counts, self.totalSites, self.nVec = pats, cnt, int(totalSites), nv
+
+    @property
+    def nrDevices(self):
+        return self._lib.rc_device_count(self._h)
+
+    # -- one process per GPU: NCCL communicator inside the library --------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it, the launcher hands it to every rank)."""
+        buf = C.create_string_buffer(128)
+        rc = L.load().rc_comm_unique_id(buf)
+        if rc != L.RC_OK:
+            raise RarecoalDeviceError("rc_comm_unique_id failed: NCCL (libnccl.so.2) is not available")
+        return buf.raw
+
+    def comm_init(self, nRanks, rank, unique_id):
+        """Joins the communicator and fixes this context's pattern shard; eval_* then return the all-reduced result."""
+        assert len(unique_id) == 128
+        self._check(self._lib.rc_comm_init(self._h, int(nRanks), int(rank), C.c_char_p(unique_id)))
+
+    def comm_allreduce(self, dPtr, n, stream=None):
+        self._check(self._lib.rc_comm_allreduce(self._h, C.c_void_p(dPtr), int(n), C.c_void_p(stream) if stream else None))
 
     def set_shard(self, rank, world):
         self._check(self._lib.rc_set_shard(self._h, int(rank), int(world)))

@@ -15,12 +15,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/rarecoal_b200.h"
 #include "rc_kernels.h"
+#include "rc_multi.h"
+#include "rc_nccl.h"
 #include "rc_plan.h"
 
 namespace {
@@ -146,8 +149,8 @@ struct rc_ctx {
     int optPlanCacheMax = 64;            // "plan_cache_max"
     double optPlanCacheMB = 49152.0;     // "plan_cache_mb"
     // counters since rc_create (rc_stats reports the per-call deltas)
-    long long planMisses = 0, planEvictions = 0;
-    double planBuildMs = 0.0;
+    long long planMisses = 0, planEvictions = 0, planMissesAtCall = 0, planEvictionsAtCall = 0;
+    double planBuildMs = 0.0, planBuildMsAtCall = 0.0;
     // eval scratch
     DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc;
     // options (rc_set_option)
@@ -176,6 +179,11 @@ struct rc_ctx {
     bool blobInFlight = false;
     rc_stats stats;
     rc_ctx* child = nullptr;
+    // multi-GPU: this context is one rank of an NCCL communicator (rc_comm_init), or the front of a single-process
+    // multi-device context (rc_create_multi, rc_multi.cpp) whose calls are forwarded
+    rc::NcclComm comm = nullptr;
+    int commRanks = 1, commRank = 0;
+    RcMulti* multi = nullptr;
 
     void clear_plans() {
         for (auto& kv : plans) {
@@ -223,6 +231,9 @@ int validate_model(int P, const double* disc, const std::vector<rc_event>& sorte
             if (e.k == e.l) { err = "Illegal split of a branch into itself"; return RC_ERR_MODEL; }
         } else if (e.type == RC_EV_FREEZE) {
             if (bad_idx(e.k)) { err = "illegal branch indices in event SetFreeze"; return RC_ERR_MODEL; }
+        } else if (e.type == RC_EV_GROWTH) {
+            if (bad_idx(e.k)) { err = "illegal branch indices in event SetGrowthRate"; return RC_ERR_MODEL; }
+            if (!std::isfinite(e.v)) { err = "Illegal growth rate"; return RC_ERR_MODEL; }
         } else {
             err = "unknown event type";
             return RC_ERR_MODEL;
@@ -236,6 +247,58 @@ std::vector<rc_event> sort_events(const rc_event* ev, int n) {
     // sortBy time is stable (Core.hs:292-294): template order survives for equal times
     std::stable_sort(v.begin(), v.end(), [](const rc_event& a, const rc_event& b) { return a.t < b.t; });
     return v;
+}
+
+// SetGrowthRate is sugar (include/rarecoal_b200.h, RC_EV_GROWTH): from its time t0 on, the size of branch k follows
+// N(t) = N(t0) * exp(-r (t - t0)) (t runs backwards in time, so r > 0 is a population that grew towards the present) until
+// the next SetPopSize / SetGrowthRate on k or the Join that removes k.  It is rewritten into the reference's own events —
+// one `SetPopSize k N(t_s)` at every grid point t0 < t_s < tStop (so grid step s+1 runs with the size at its recent end)
+// — before anything else looks at the model; N(t0) is the size set by earlier events (1.0 initially, Core.hs:296).
+// `sorted` must be stably sorted by time; so is the result (generated events after the explicit ones of the same time).
+std::vector<rc_event> desugar_growth(const std::vector<double>& times, const std::vector<rc_event>& sorted) {
+    bool any = false;
+    for (const rc_event& e : sorted) any = any || e.type == RC_EV_GROWTH;
+    if (!any) return sorted;
+    struct G { bool on = false; double t0 = 0, n0 = 1, r = 0; };
+    std::vector<G> g(RC_MAX_P);
+    std::vector<double> size(RC_MAX_P, 1.0);
+    std::vector<rc_event> out, gen;
+    auto valid = [](int k) { return k >= 0 && k < RC_MAX_P; };
+    auto at = [](const G& s, double t) { return s.n0 * std::exp(-(s.r * (t - s.t0))); };
+    // per-step sizes of a growth phase of branch k that ends (exclusively) at tStop
+    auto flush = [&](int k, double tStop) {
+        G& s = g[(size_t)k];
+        if (!s.on) return;
+        auto it = std::upper_bound(times.begin(), times.end(), s.t0);
+        for (; it != times.end() && *it < tStop; ++it) {
+            rc_event e;
+            e.t = *it; e.type = RC_EV_POPSIZE; e.k = k; e.l = 0; e.v = at(s, *it);
+            gen.push_back(e);
+        }
+        size[(size_t)k] = at(s, tStop);
+        s.on = false;
+    };
+    for (const rc_event& e : sorted) {
+        if (e.type == RC_EV_GROWTH) {
+            if (!valid(e.k)) continue;                       // rejected by validateModel
+            flush(e.k, e.t);                                 // N is continuous across a change of rate
+            G& s = g[(size_t)e.k];
+            if (e.v == 0.0) {                                // rate 0: a plain size from here on
+                rc_event p;
+                p.t = e.t; p.type = RC_EV_POPSIZE; p.k = e.k; p.l = 0; p.v = size[(size_t)e.k];
+                gen.push_back(p);
+            } else { s.on = true; s.t0 = e.t; s.n0 = size[(size_t)e.k]; s.r = e.v; }
+            continue;
+        }
+        if (e.type == RC_EV_POPSIZE && valid(e.k)) { flush(e.k, e.t); size[(size_t)e.k] = e.v; }
+        if (e.type == RC_EV_JOIN && valid(e.l)) flush(e.l, e.t);   // the joined-away branch ends here
+        out.push_back(e);
+    }
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int k = 0; k < RC_MAX_P; ++k) flush(k, inf);
+    out.insert(out.end(), gen.begin(), gen.end());
+    std::stable_sort(out.begin(), out.end(), [](const rc_event& a, const rc_event& b) { return a.t < b.t; });
+    return out;
 }
 
 // GHC's (^): square-and-multiply with the accumulator order of GHC.Real.powImpl / powImplAcc, so the
@@ -270,6 +333,7 @@ void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double*
     std::vector<rc_event> sorted = sort_events(ev, nEv);
     mh.status = validate_model(P, disc, sorted, mh.err);
     if (mh.status != RC_OK) return;
+    sorted = desugar_growth(ctx->times, sorted);
     SegHost cur;
     cur.sBegin = 0;
     cur.mask = 0;
@@ -505,10 +569,30 @@ long long count_state_steps(const ModelHost& mh, const rc::PlanHost& h, int T) {
     return W;
 }
 
+// FP64 instructions executed by the propagation kernels of the keyed tier (rc_plan.h, epochFp64), counted like the
+// state-steps above.
+long long count_fp64_instr(const ModelHost& mh, const rc::PlanHost& h, int T) {
+    if (h.epochFp64.empty()) return 0;
+    long long W = 0;
+    int prev = 0;
+    for (int e = 0; e < h.nEpochs; ++e) {
+        bool last = e + 1 == h.nEpochs;
+        int endFull = last ? T : mh.sevStep[(size_t)e];
+        int endShort = last ? (mh.sShort >= 0 ? mh.sShort : T) : endFull;
+        W += h.epochFp64Short[(size_t)e] * (long long)(endShort - prev) +
+             (h.epochFp64[(size_t)e] - h.epochFp64Short[(size_t)e]) * (long long)(endFull - prev);
+        prev = endFull;
+    }
+    return W;
+}
+
 // The whole evaluation up to the per-model partial sums (left on the device).
 int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
                const int32_t* noShortcut /*[B]*/, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus, long long* maxPairsOut) {
     ++ctx->evalSerial;
+    ctx->planMissesAtCall = ctx->planMisses;
+    ctx->planEvictionsAtCall = ctx->planEvictions;
+    ctx->planBuildMsAtCall = ctx->planBuildMs;
     const int P = ctx->P, A1 = ctx->maxAf + 1, T = (int)ctx->times.size();
     const int rowLen = rc_row_len(P, A1);
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -576,7 +660,9 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     long long tabDoubles = 0;
     int rowsMax = 0;
     size_t sevPos = 0, segPos = 0, wPos = 0;
-    long long W = 0, slots0 = 0;
+    long long W = 0, slots0 = 0, Wfp = 0;
+    const long long miss0 = ctx->planMissesAtCall, evict0 = ctx->planEvictionsAtCall;
+    const double build0 = ctx->planBuildMsAtCall;
     for (int pos = 0; pos < B; ++pos) {
         const int b = order[(size_t)pos];
         ModelHost& mh = mhs[(size_t)b];
@@ -659,6 +745,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         }
         const rc::PlanHost& h = pe->h;
         W += count_state_steps(mh, h, T);
+        if (M.mode == 1) Wfp += count_fp64_instr(mh, h, T);
         slots0 += h.epochSlots[0];
         ctx->stats.n_epochs = h.nEpochs;
         ctx->stats.n_steps = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
@@ -667,6 +754,10 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     ctx->stats.state_steps = W;
     ctx->stats.slots = slots0;
     ctx->stats.plan_cache_hit = hit ? 1 : 0;
+    ctx->stats.fp64_instr = Wfp;
+    ctx->stats.plan_misses = (int32_t)(ctx->planMisses - miss0);
+    ctx->stats.plan_evictions = (int32_t)(ctx->planEvictions - evict0);
+    ctx->stats.plan_build_ms = ctx->planBuildMs - build0;
 
     {
         size_t needTab = (size_t)std::max<long long>(tabDoubles, 1) * sizeof(double);
@@ -842,6 +933,8 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
             acc.state_steps += ctx->stats.state_steps; acc.slots += ctx->stats.slots;
             acc.kernel_ms += ctx->stats.kernel_ms; acc.traj_ms += ctx->stats.traj_ms; acc.tables_ms += ctx->stats.tables_ms;
             acc.total_ms += ctx->stats.total_ms; acc.launches += ctx->stats.launches;
+            acc.fp64_instr += ctx->stats.fp64_instr; acc.plan_misses += ctx->stats.plan_misses;
+            acc.plan_evictions += ctx->stats.plan_evictions; acc.plan_build_ms += ctx->stats.plan_build_ms;
             acc.plan_cache_hit = nChunks == 1 ? ctx->stats.plan_cache_hit : (acc.plan_cache_hit && ctx->stats.plan_cache_hit);
             acc.n_epochs = ctx->stats.n_epochs; acc.n_steps = ctx->stats.n_steps;
             if (done == B) ctx->stats = acc;
@@ -978,9 +1071,19 @@ int rc_create(int device, rc_ctx** out) {
 
 void rc_destroy(rc_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->multi) {
+        rc_multi_destroy(ctx->multi);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();          // launches queued by rc_eval_partial on a caller's stream may still read the buffers
     if (ctx->child) rc_destroy(ctx->child);
+    if (ctx->comm) {
+        std::string e;
+        if (const rc::NcclApi* api = rc::nccl_api(e)) api->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
@@ -1005,11 +1108,16 @@ void rc_destroy(rc_ctx* ctx) {
     delete ctx;
 }
 
-const char* rc_last_error(rc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* rc_last_error(rc_ctx* ctx) {
+    if (!ctx) return "null context";
+    if (ctx->multi) return rc_multi_last_error(ctx->multi);
+    return ctx->err.c_str();
+}
 
 int rc_set_problem(rc_ctx* ctx, int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec,
                    const int64_t* counts, int64_t totalSites) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_set_problem(ctx->multi, P, maxAf, nPat, patterns, nVec, counts, totalSites);
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
     if (P < 1 || P > RC_MAX_P || maxAf < 1 || maxAf > RC_MAX_AF || nPat < 0 || !nVec || (nPat > 0 && !patterns)) {
@@ -1049,14 +1157,19 @@ int rc_set_problem(rc_ctx* ctx, int P, int maxAf, int nPat, const int32_t* patte
             ctx->sumCounts += counts[i];
         }
     ctx->totalSites = totalSites;
-    ctx->rank = 0;
-    ctx->world = 1;
+    ctx->rank = ctx->comm ? ctx->commRank : 0;          // a context that joined a communicator keeps its shard
+    ctx->world = ctx->comm ? ctx->commRanks : 1;
     return build_shard(ctx);
 }
 
 int rc_set_shard(rc_ctx* ctx, int rank, int world) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return RC_ERR_ARG;                   // a multi-device context shards by itself
     ctx->err.clear();
+    if (ctx->comm && (rank != ctx->commRank || world != ctx->commRanks)) {
+        ctx->err = "rc_set_shard: the context's shard is fixed by rc_comm_init";
+        return RC_ERR_ARG;
+    }
     if (ctx->P == 0) { ctx->err = "rc_set_shard: call rc_set_problem first"; return RC_ERR_ARG; }
     if (world < 1 || rank < 0 || rank >= world) { ctx->err = "rc_set_shard: bad rank/world"; return RC_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -1067,6 +1180,7 @@ int rc_set_shard(rc_ctx* ctx, int rank, int world) {
 
 int rc_set_times(rc_ctx* ctx, int T, const double* t) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_set_times(ctx->multi, T, t);
     ctx->err.clear();
     if (T < 1 || !t) { ctx->err = "rc_set_times: empty grid"; return RC_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -1106,6 +1220,7 @@ int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff
                     const double* disc, int noShortcut, double* dPartial, double* dProbs, void* stream,
                     int32_t* outStatus) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return RC_ERR_ARG;                   // device pointers belong to one device: use rc_eval on a multi-device context
     ctx->err.clear();
     if (B < 0 || !evOff || !theta || !disc || !dPartial) { ctx->err = "rc_eval_partial: null argument"; return RC_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -1115,6 +1230,7 @@ int rc_eval_partial(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff
 
 int rc_finalize(rc_ctx* ctx, int B, const double* dPartialReduced, double siteRed, void* stream, double* outLogl) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return RC_ERR_ARG;
     ctx->err.clear();
     if (B <= 0) return RC_OK;
     if (!dPartialReduced || !outLogl) { ctx->err = "rc_finalize: null argument"; return RC_ERR_ARG; }
@@ -1140,6 +1256,7 @@ int rc_eval(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const 
 int rc_eval_models(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
                    const int32_t* noShortcut, double siteRed, double* outProbs, double* outLogl, int32_t* outStatus) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_eval_models(ctx->multi, B, ev, evOff, theta, disc, noShortcut, siteRed, outProbs, outLogl, outStatus);
     ctx->err.clear();
     if (B < 0 || !evOff || !theta || !disc || !outLogl || !noShortcut) { ctx->err = "rc_eval: null argument"; return RC_ERR_ARG; }
     if (B == 0) return RC_OK;
@@ -1152,6 +1269,24 @@ int rc_eval_models(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff,
         dProbs = (double*)ctx->dProbs.p;
     }
     int rc = eval_impl(ctx, B, ev, evOff, theta, disc, noShortcut, (double*)ctx->dPartial.p, dProbs, ctx->stream, outStatus);
+    if (ctx->comm) {
+        // one rank of a communicator: the partial sums (and probabilities) of all pattern shards are summed by NCCL on the
+        // evaluation stream.  A rank whose evaluation failed still takes part — with NaNs — so that its peers do not wait
+        // for it forever; it then reports its own error.
+        std::string nerr;
+        const rc::NcclApi* api = rc::nccl_api(nerr);
+        if (!api) { ctx->err = nerr; return RC_ERR_CUDA; }
+        if (rc != RC_OK) {
+            std::vector<double> nanv((size_t)2 * B, std::nan(""));
+            cudaMemcpyAsync(ctx->dPartial.p, nanv.data(), nanv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        int nr = api->AllReduce(ctx->dPartial.p, ctx->dPartial.p, (size_t)2 * B, rc::kNcclFloat64, rc::kNcclSum, ctx->comm, ctx->stream);
+        if (nr == 0 && dProbs && ctx->nPatGlobal > 0)
+            nr = api->AllReduce(dProbs, dProbs, (size_t)B * ctx->nPatGlobal, rc::kNcclFloat64, rc::kNcclSum, ctx->comm, ctx->stream);
+        if (nr != 0 && rc == RC_OK) { ctx->err = std::string("ncclAllReduce: ") + api->GetErrorString(nr); rc = RC_ERR_CUDA; }
+        ctx->stats.launches += dProbs ? 2 : 1;
+    }
     if (rc != RC_OK) return rc;
     if (outProbs && ctx->nPatGlobal > 0) {
         CK(ctx->hOut.ensure(std::max(probBytes, (size_t)B * sizeof(double))));
@@ -1165,6 +1300,7 @@ int rc_eval_models(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff,
 int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_t* config, const rc_event* ev, int nEv,
                 double theta, const double* disc, int noShortcut, double* outProb) {
     if (!ctx) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_get_prob(ctx->multi, P, maxAf, nVec, config, ev, nEv, theta, disc, noShortcut, outProb);
     ctx->err.clear();
     if (ctx->times.empty()) { ctx->err = "rc_get_prob: rc_set_times has not been called"; return RC_ERR_ARG; }
     if (!ctx->child) {
@@ -1187,6 +1323,7 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
 
 int rc_set_option(rc_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_set_option(ctx->multi, name, value);
     ctx->err.clear();
     std::string n(name);
     if (n == "keyed") ctx->optKeyed = value != 0.0;
@@ -1210,6 +1347,7 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
 
 int rc_last_stats(rc_ctx* ctx, rc_stats* out) {
     if (!ctx || !out) return RC_ERR_ARG;
+    if (ctx->multi) return rc_multi_last_stats(ctx->multi, out);
     int rc = collect_stats(ctx);
     *out = ctx->stats;
     return rc;
@@ -1217,6 +1355,7 @@ int rc_last_stats(rc_ctx* ctx, rc_stats* out) {
 
 int rc_fp64_peak(rc_ctx* ctx, double* outTflops) {
     if (!ctx || !outTflops) return RC_ERR_ARG;
+    if (ctx->multi) return rc_fp64_peak(rc_multi_first(ctx->multi), outTflops);
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
     const int blocks = ctx->smCount * 16, iters = 4096;
@@ -1241,6 +1380,70 @@ int rc_fp64_peak(rc_ctx* ctx, double* outTflops) {
     cudaFree(d);
     *outTflops = best;
     return RC_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+int rc_comm_unique_id(void* out128) {
+    if (!out128) return RC_ERR_ARG;
+    std::string e;
+    const rc::NcclApi* api = rc::nccl_api(e);
+    if (!api) return RC_ERR_CUDA;
+    rc::NcclUniqueId id;
+    if (api->GetUniqueId(&id) != 0) return RC_ERR_CUDA;
+    std::memcpy(out128, id.internal, sizeof id.internal);
+    return RC_OK;
+}
+
+int rc_comm_init(rc_ctx* ctx, int nRanks, int rank, const void* uniqueId128) {
+    if (!ctx || ctx->multi) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (nRanks < 1 || rank < 0 || rank >= nRanks || !uniqueId128) { ctx->err = "rc_comm_init: bad rank / size / id"; return RC_ERR_ARG; }
+    if (ctx->comm) { ctx->err = "rc_comm_init: the context already belongs to a communicator"; return RC_ERR_ARG; }
+    const rc::NcclApi* api = rc::nccl_api(ctx->err);
+    if (!api) return RC_ERR_CUDA;
+    CK(cudaSetDevice(ctx->device));
+    rc::NcclUniqueId id;
+    std::memcpy(id.internal, uniqueId128, sizeof id.internal);
+    rc::NcclComm comm = nullptr;
+    int nr = api->CommInitRank(&comm, nRanks, id, rank);
+    if (nr != 0) { ctx->err = std::string("ncclCommInitRank: ") + api->GetErrorString(nr); return RC_ERR_CUDA; }
+    ctx->comm = comm;
+    ctx->commRanks = nRanks;
+    ctx->commRank = rank;
+    ctx->rank = rank;
+    ctx->world = nRanks;
+    return ctx->P > 0 ? build_shard(ctx) : RC_OK;
+}
+
+int rc_comm_allreduce(rc_ctx* ctx, double* dBuf, int64_t n, void* stream) {
+    if (!ctx || ctx->multi) return RC_ERR_ARG;
+    ctx->err.clear();
+    if (!ctx->comm) { ctx->err = "rc_comm_allreduce: rc_comm_init has not been called"; return RC_ERR_ARG; }
+    if (n <= 0) return RC_OK;
+    if (!dBuf) { ctx->err = "rc_comm_allreduce: null buffer"; return RC_ERR_ARG; }
+    const rc::NcclApi* api = rc::nccl_api(ctx->err);
+    if (!api) return RC_ERR_CUDA;
+    CK(cudaSetDevice(ctx->device));
+    int nr = api->AllReduce(dBuf, dBuf, (size_t)n, rc::kNcclFloat64, rc::kNcclSum, ctx->comm, (cudaStream_t)stream);
+    if (nr != 0) { ctx->err = std::string("ncclAllReduce: ") + api->GetErrorString(nr); return RC_ERR_CUDA; }
+    return RC_OK;
+}
+
+int rc_create_multi(int nDevices, const int32_t* devices, rc_ctx** out) {
+    if (!out) return RC_ERR_ARG;
+    *out = nullptr;
+    RcMulti* m = nullptr;
+    int rc = rc_multi_create(nDevices, devices, &m);
+    if (rc != RC_OK) return rc;
+    rc_ctx* ctx = new rc_ctx();
+    ctx->multi = m;
+    *out = ctx;
+    return RC_OK;
+}
+
+int rc_device_count(rc_ctx* ctx) {
+    if (!ctx) return RC_ERR_ARG;
+    return ctx->multi ? rc_multi_count(ctx->multi) : 1;
 }
 
 // ---- host-side mirrors -------------------------------------------------------------------------
@@ -1288,6 +1491,13 @@ double rc_reg_penalty(int P, double reg, const rc_event* ev, int nEv) {
 }
 
 double rc_choose(int n, int k) { return rc::choose(n, k); }
+
+int rc_desugar_growth(int T, const double* times, const rc_event* ev, int nEv, rc_event* out, int cap) {
+    if (T < 0 || (T > 0 && !times) || nEv < 0 || (nEv > 0 && !ev)) return RC_ERR_ARG;
+    std::vector<rc_event> r = desugar_growth(std::vector<double>(times, times + T), sort_events(ev, nEv));
+    if (out) for (size_t i = 0; i < r.size() && (int)i < cap; ++i) out[i] = r[i];
+    return (int)r.size();
+}
 
 int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int world, int32_t* out, int cap) {
     if (P < 1 || nPat < 0 || (nPat > 0 && !patterns) || world < 1 || rank < 0 || rank >= world) return RC_ERR_ARG;

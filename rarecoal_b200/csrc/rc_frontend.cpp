@@ -31,7 +31,7 @@ struct ParamSpec {
 };
 
 struct MTEvent {
-    char cmd = 'P';              // P, J, K, S, F
+    char cmd = 'P';              // P, J, K, S, F, G
     ParamSpec t;
     std::string a, b;            // branch / to, from
     ParamSpec v;                 // size / rate
@@ -129,10 +129,11 @@ bool parse_template(const std::string& text, Template& t, std::string& err) {
     while (p.i < text.size() && text[p.i] != ']') {
         MTEvent e;
         e.cmd = text[p.i];
-        if (std::strchr("PJKSF", e.cmd) == nullptr) { p.fail("unknown event command"); err = p.err; return false; }
+        // G t branch rate: SetGrowthRate, an extension of the reference grammar (include/rarecoal_b200.h, RC_EV_GROWTH)
+        if (std::strchr("PJKSFG", e.cmd) == nullptr) { p.fail("unknown event command"); err = p.err; return false; }
         ++p.i;
         bool ok = p.spaces1() && p.param(e.t) && p.spaces1() && p.ident(e.a);
-        if (ok && e.cmd == 'P') ok = p.spaces1() && p.param(e.v);
+        if (ok && (e.cmd == 'P' || e.cmd == 'G')) ok = p.spaces1() && p.param(e.v);
         if (ok && e.cmd == 'J') ok = p.spaces1() && p.ident(e.b);
         if (ok && (e.cmd == 'K' || e.cmd == 'S')) ok = p.spaces1() && p.ident(e.b) && p.spaces1() && p.param(e.v);
         if (ok && e.cmd == 'F') {
@@ -306,6 +307,7 @@ int rc_template_instantiate(const char* text, int nParams, const char* const* na
                 ev.type = RC_EV_POPSIZE; ev.l = 0; ev.v = get(m.v); evs.push_back(ev);
                 break;
             case 'S': ev.type = RC_EV_SPLIT; ev.l = b; ev.v = get(m.v); evs.push_back(ev); break;
+            case 'G': ev.type = RC_EV_GROWTH; ev.v = get(m.v); evs.push_back(ev); break;
             default: ev.type = RC_EV_FREEZE; ev.v = m.flag ? 1.0 : 0.0; evs.push_back(ev); break;
         }
     }

@@ -2118,6 +2118,30 @@ __global__ void __launch_bounds__(256) rc_fp64_peak_kernel(double* out, int iter
 
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
+//
+// cudaFuncSetAttribute applies to the CURRENT device and the library may drive several devices from several threads
+// (rc_create_multi): the opt-in to large dynamic shared memory is tracked per (kernel, device).
+#include <map>
+#include <mutex>
+#include <utility>
+static cudaError_t rc_ensure_smem(const void* kernel, size_t smem, bool carveout = false) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = done[std::make_pair(kernel, dev)];
+    if (smem <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (carveout) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+    }
+    have = smem;
+    return cudaSuccess;
+}
 cudaError_t rc_launch_tables(const RcModelDev* models, const RcSegDev* segs, const int* segOff, const double* dts,
                              double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st) {
     if (rowsMax <= 0 || B <= 0) return cudaSuccess;
@@ -2131,12 +2155,8 @@ cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, c
                                 cudaStream_t st) {
     if (pl.nBins <= 0 || nB <= 0) return cudaSuccess;
     size_t smem = rc_propagate_smem_bytes(pl.cap, pl.nnzw, pl.P, rc_row_len(pl.P, pl.A1));
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(rc_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = rc_ensure_smem((const void*)rc_propagate_kernel, smem);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)pl.nBins, (unsigned)nB);
     rc_propagate_kernel<<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, sevs, tab, wpool, pOut + (size_t)b0 * pl.nPat);
     return cudaGetLastError();
@@ -2145,15 +2165,9 @@ cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, c
 template <int NNZ, int BLOCK>
 static cudaError_t rc_launch_fast_t(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs, const double* tab,
                                     const double* wpool, double* pOut, int nB, cudaStream_t st) {
-    static bool configured = false;
     const size_t smem = rc_fast_smem_bytes(BLOCK);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rc_propagate_fast_kernel<NNZ, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(rc_propagate_fast_kernel<NNZ, BLOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    cudaError_t e = rc_ensure_smem((const void*)rc_propagate_fast_kernel<NNZ, BLOCK>, smem, true);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)pl.nFastBins, (unsigned)nB);
     rc_propagate_fast_kernel<NNZ, BLOCK><<<grid, BLOCK, smem, st>>>(pl, models, sevs, tab, wpool, pOut);
     return cudaGetLastError();
@@ -2188,7 +2202,6 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
     if (nBins <= 0 || nB <= 0) return cudaSuccess;
     const size_t smem = (sizeof(RcKeySmem) + 15) & ~(size_t)15;
-    static bool c4 = false, c8 = false;
     dim3 grid((unsigned)nBins, (unsigned)nB);
     double* out = pOut + (size_t)b0 * pl.nPat;
     double* dac = dAcc + (size_t)b0 * pl.nPat;
@@ -2207,38 +2220,25 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
         return cudaGetLastError();
     }
     if (rowMode) {
-        static bool cr3 = false, cr7 = false;
         const size_t rsmem = (sizeof(RcRowSmem) + 15) & ~(size_t)15;
         if (rowMode == 1) {
-            if (!cr3) {
-                cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-                if (err != cudaSuccess) return err;
-                cr3 = true;
-            }
+            cudaError_t err = rc_ensure_smem((const void*)rc_propagate_rows_kernel<3>, rsmem);
+            if (err != cudaSuccess) return err;
             rc_propagate_rows_kernel<3><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         } else {
-            if (!cr7) {
-                cudaError_t err = cudaFuncSetAttribute(rc_propagate_rows_kernel<RC_ROW_NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-                if (err != cudaSuccess) return err;
-                cr7 = true;
-            }
+            cudaError_t err = rc_ensure_smem((const void*)rc_propagate_rows_kernel<RC_ROW_NO>, rsmem);
+            if (err != cudaSuccess) return err;
             rc_propagate_rows_kernel<RC_ROW_NO><<<grid, RC_BLOCK, rsmem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         }
         return cudaGetLastError();
     }
     if (pl.nnzw <= 4) {
-        if (!c4) {
-            cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err != cudaSuccess) return err;
-            c4 = true;
-        }
+        cudaError_t err = rc_ensure_smem((const void*)rc_propagate_keyed_kernel<4>, smem);
+        if (err != cudaSuccess) return err;
         rc_propagate_keyed_kernel<4><<<grid, RC_BLOCK, smem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     } else {
-        if (!c8) {
-            cudaError_t err = cudaFuncSetAttribute(rc_propagate_keyed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err != cudaSuccess) return err;
-            c8 = true;
-        }
+        cudaError_t err = rc_ensure_smem((const void*)rc_propagate_keyed_kernel<8>, smem);
+        if (err != cudaSuccess) return err;
         rc_propagate_keyed_kernel<8><<<grid, RC_BLOCK, smem, st>>>(pl, e, binBase, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     }
     return cudaGetLastError();

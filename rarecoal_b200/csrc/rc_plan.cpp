@@ -1110,6 +1110,46 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ro[nPat] = (int)run;
             }
         }
+        // ---- executed FP64 instructions per grid step (rc_kernels.cu, the update of each tier as written) ----
+        out.epochFp64.assign((size_t)nEpochs, 0);
+        out.epochFp64Short.assign((size_t)nEpochs, 0);
+        for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
+            const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
+            bool direct = mode >= RC_MODE_PAT && !groupIds[(size_t)v].empty();
+            for (int i : groupIds[(size_t)v]) direct = direct && pps[(size_t)i].rowNO[(size_t)e] == 0;
+            for (int i : groupIds[(size_t)v]) {
+                const PatPlan& pp = pps[(size_t)i];
+                long long n = 0;
+                if (mode >= RC_MODE_PAT) {
+                    // rc_pat_run: D1 tree over the m = 1 branches, one DMUL per prefix of the shaped branches, per state one
+                    // DMUL / DFMA per existing neighbour and the combining DFMA; updateD for a single-branch pattern
+                    int nS = 0, nU = 0;
+                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], rc_pat_cap(mode), nullptr, &nS, &nU);
+                    int M[5];
+                    for (int q = 0; q < 5; ++q) M[q] = (int)((sh >> (4 * q)) & 0xFu);
+                    long long pre = M[0], states = M[0];
+                    n += nU ? 6 - nS : 0;
+                    n += pre;                                               // dA = D1 * gA
+                    for (int q = 1; q <= nS; ++q) { pre *= M[q]; n += pre; states *= M[q]; }
+                    n += states;                                            // b = fma(b, d, t2)
+                    for (int q = 0; q <= nS; ++q) n += states / M[q] * (M[q] - 1);   // neighbours along each shaped branch
+                    if (nS + nU == 0) n += 1;                               // updateD
+                    if (direct) n = 2LL * M[0] - 1 + 1;
+                } else if (mode) {
+                    // rc_row_run: per row NO DMUL (D), per state DMUL (D * G_r), DMUL (row neighbour), NO DFMA, DFMA
+                    const long long rows = pp.rowCnt[(size_t)e], Mr = pp.rowM[(size_t)e], NO = pp.rowNO[(size_t)e];
+                    n = rows * (NO + Mr * (NO + 2) + (Mr - 1) + (NO == 0 ? 1 : 0));
+                } else {
+                    // rc_key_step: per state and non-zero branch one DMUL into the decay factor (the first is a move) and one
+                    // DMUL / DFMA of the neighbour, then the combining DFMA
+                    size_t m0 = 0;
+                    for (int q = 0; q < e; ++q) m0 += (size_t)pp.live[(size_t)q];
+                    for (int sI = 0; sI < pp.live[(size_t)e]; ++sI) n += 2LL * (long long)(pp.meta[m0 + (size_t)sI] & 0xFFu);
+                }
+                out.epochFp64[(size_t)e] += n;
+                if (pp.shortcutOK) out.epochFp64Short[(size_t)e] += n;
+            }
+        }
         out.grpDirect.assign((size_t)nEpochs * RC_NGROUP, 0);
         static const bool directEnv = std::getenv("RC_PAT_DIRECT") ? std::atoi(std::getenv("RC_PAT_DIRECT")) != 0 : true;
         for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {

@@ -95,6 +95,9 @@ struct PlanHost {
     std::vector<uint8_t> shortcutOK;       // [nPat]
     std::vector<long long> epochSlots;     // [nEpochs] total live states per epoch
     std::vector<long long> epochSlotsShort;// [nEpochs] same, restricted to patterns that take the shortcut
+    // FP64 instructions (DMUL / DFMA, one issue slot of the FP64 pipe each) the keyed kernels execute per grid step of
+    // epoch e, summed over the patterns (all / those that take the shortcut): the numerator of the pipe-level roofline
+    std::vector<long long> epochFp64, epochFp64Short;
     int maxLive = 0;
     long long totalSlots = 0;
 };

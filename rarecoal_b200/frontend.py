@@ -81,6 +81,14 @@ class MTFreeze:
 
 
 @dataclass(frozen=True)
+class MTGrowthRate:
+    """`G t branch rate` — SetGrowthRate, an extension of the reference grammar (see api.SetGrowthRate)."""
+    t: object
+    branch: str
+    rate: object
+
+
+@dataclass(frozen=True)
 class MTConstraint:
     lhs: object
     rhs: object
@@ -116,7 +124,7 @@ def parseModelTemplate(text: str) -> ModelTemplate:
         t, v = _spec(e["t"]), _spec(e["v"])
         evs.append({"P": lambda: MTPopSizeChange(t, e["a"], v), "J": lambda: MTJoin(t, e["a"], e["b"]),
                     "K": lambda: MTJoinPopSizeChange(t, e["a"], e["b"], v), "S": lambda: MTSplit(t, e["a"], e["b"], v),
-                    "F": lambda: MTFreeze(t, e["a"], e["flag"])}[e["cmd"]]())
+                    "F": lambda: MTFreeze(t, e["a"], e["flag"]), "G": lambda: MTGrowthRate(t, e["a"], v)}[e["cmd"]]())
     cons = [MTConstraint(_spec(c["lhs"]), _spec(c["rhs"]),
                          "ConstraintOpGreater" if c["op"] == ">" else "ConstraintOpSmaller") for c in d["constraints"]]
     return ModelTemplate(d["branches"], evs, cons, text, d["params"])

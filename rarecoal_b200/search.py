@@ -81,7 +81,7 @@ class Objective:
                                                 self.opts.optNoShortcut, self.hp.siteRed)
             self.n_launches += 1
             for b in range(B):
-                if ok[b] and status[b] == 0 and np.isfinite(logl[b]):
+                if ok[b] and status[b] == 0 and np.isfinite(logl[b]) and np.isfinite(pen[b]):
                     scores[b] = -logl[b] + self.hp.siteRed * pen[b]
         self.n_evals += B
         return scores

@@ -165,3 +165,21 @@ def test_batched_simplex_on_a_known_function(par):
     assert np.allclose(x, target, atol=1e-6)
     assert calls[0] == 5 and max(calls) >= 4 * par            # start simplex in one batch, 4 speculative points per vertex
     assert trace[-1][2] < 1e-8 or len(trace) == 2000
+
+
+def test_workload_templates_instantiate_to_the_written_out_events(fourpop):
+    # bench.py's reference arm builds events without the library; they must be what the template front-end produces
+    from rarecoal_b200 import workloads as Wk
+    for wl in (Wk.get("c2"), Wk.get("c3"), Wk.get("c5")):
+        mt = F.parseModelTemplate(wl.template)
+        assert len(mt.mtBranchNames) == wl.P
+        x = wl.x0 * (1.0 + 0.001 * np.arange(len(wl.x0)))
+        d = list(zip(wl.names, x.tolist()))
+        assert sorted(F.getParamNames(mt)) == sorted(wl.names)
+        got = F.instantiateEvents(mt, d)
+        assert [tuple(e) for e in got] == [tuple(map(float, e)) if False else (float(e[0]), e[1], e[2], e[3], float(e[4]))
+                                           for e in wl.events(x)]
+    mt = F.parseModelTemplate(Wk.get("c5").template)
+    assert F.getParamNames(mt) == [n for n, _ in Wk.c5_param_dict()]           # optimiser-vector order
+    assert any(isinstance(e, F.MTGrowthRate) for e in mt.mtEvents)
+    assert F.getParamNames(F.parseModelTemplate(Wk.C3_TEMPLATE)) == Wk.c3_param_names()

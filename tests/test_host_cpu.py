@@ -83,6 +83,11 @@ def test_validate_and_regularization_match_oracle(fourpop):
         R.validateModel(bad)
     with pytest.raises(R.RarecoalModelException):
         R.validateModel(R.ModelSpec(2, [], 0.1, [1.0, 1.5], 0.0, False, []))
+    # branch indices outside [0, nrPops) must not touch the size vector (the reference's V.! / V.// fail cleanly)
+    for ev in (R.SetPopSize(50000000, 2.0), R.SetPopSize(-1, 2.0), R.Join(0, 7), R.Join(9, 1)):
+        with pytest.raises(R.RarecoalModelException):
+            R.getRegularizationPenalty(R.ModelSpec(2, R.defaultTimes(), 0.0005, [1.0, 1.0], 10.0, False,
+                                                   [R.ModelEvent(0.1, ev)]))
 
 
 @pytest.mark.parametrize("max_af,want", [(4, 224261), (10, 26379903)])
@@ -123,7 +128,7 @@ def test_plan_self_check_on_every_workload_shape(fourpop):
     # bin against the shared-memory limits of its kernel): trees (state and row mode), admixture, big-tier patterns
     T = R.defaultTimes()
     nv10 = [100] * 10
-    assert R.planStats(nv10, 4, R.computeStandardOrder(nv10, 4), T, Wk.c5_events())["n_epochs"] == 13
+    assert R.planStats(nv10, 4, R.computeStandardOrder(nv10, 4), T, Wk.c5_events())["n_epochs"] == 13   # 9 joins + 3 pulses
     nvec, pats, _ = Wk.c3_problem(max_af=6)
     assert R.planStats(nvec, 6, pats, T, Wk.c3_events())["max_live"] <= 16
     std8 = R.computeStandardOrder(fourpop["nVec"], 8)
@@ -137,3 +142,33 @@ def test_c_abi_rejects_bad_arguments_without_device():
     assert lib.rc_ss_create(3, 0) is None
     assert lib.rc_last_error(None) == b"null context"
     assert lib.rc_version().startswith(b"rarecoal_b200")
+
+
+def test_growth_rate_desugaring_matches_the_numpy_statement():
+    # SetGrowthRate (RC_EV_GROWTH) is sugar: rc_desugar_growth must produce exactly the per-grid-step SetPopSize list of the
+    # independent numpy statement (workloads.desugar_growth_py), which is what the oracle is given in the GPU tests
+    T = R.defaultTimes()
+    cases = [Wk.c5_events(),
+             [(0.0, 2, 0, 0, 2.0), (0.0, 4, 0, 0, 30.0), (0.003, 4, 0, 0, -10.0), (0.006, 4, 0, 0, 0.0), (0.01, 0, 1, 0, 0.0)],
+             [(0.001, 4, 1, 0, 5.0), (0.002, 0, 0, 1, 0.0)],                       # growth ended by the Join that removes the branch
+             [(0.0, 4, 0, 0, 1.0)]]                                                # growth to the end of the grid
+    for ev in cases:
+        got = R.desugarGrowth(T[:800], ev)
+        want = Wk.desugar_growth_py(T[:800], ev)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert a[:4] == tuple(b[:4]) and abs(a[4] - b[4]) <= 4e-16 * abs(b[4])
+        assert all(e[1] != 4 for e in got)
+    assert len(R.desugarGrowth(T[:800], cases[3])) == 800 - 0    # one SetPopSize per grid point after t0 = 0
+    # validateModel: bad branch / non-finite rate
+    for bad in (R.SetGrowthRate(5, 1.0), R.SetGrowthRate(0, float("nan"))):
+        with pytest.raises(R.RarecoalModelException):
+            R.validateModel(R.ModelSpec(2, T, 0.0005, [1.0, 1.0], 0.0, False, [R.ModelEvent(0.1, bad)]))
+    # a grown branch used after it was joined away is still an illegal join (StateSpace.hs:176-180)
+    with pytest.raises(R.RarecoalModelException):
+        R.validateModel(R.ModelSpec(2, T, 0.0005, [1.0, 1.0], 0.0, False,
+                                    [R.ModelEvent(0.1, R.Join(0, 1)), R.ModelEvent(0.2, R.SetGrowthRate(1, 2.0))]))
+    # no penalty term and no tracked-size update from a growth phase
+    spec = lambda evs: R.ModelSpec(2, T, 0.0005, [1.0, 1.0], 10.0, False, [R.ModelEvent.from_tuple(e) for e in evs])
+    assert R.getRegularizationPenalty(spec([(0.0, 4, 0, 0, 3.0), (0.1, 0, 0, 1, 0.0)])) == \
+        R.getRegularizationPenalty(spec([(0.1, 0, 0, 1, 0.0)]))
