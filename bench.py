@@ -227,17 +227,20 @@ def measure(R, Wk, wl, eng, batches, steps, warmup, stream, torch, sync_all, aft
         sync_all()
         long_ms = e0.elapsed_time(e1)
     kernel_ms, traj_ms, launches, w_steps, fp64_instr, misses = [], [], 0, 0, 0, 0
+    host_ms, total_ms, tables_ms = [], [], []
     for i in range(warmup, warmup + steps):
         step(i)
         torch.cuda.synchronize()
         st = eng.stats()
         kernel_ms.append(st["kernel_ms"])
         traj_ms.append(st["traj_ms"])
+        host_ms.append(st["host_ms"]); total_ms.append(st["total_ms"]); tables_ms.append(st["tables_ms"])
         launches += st["launches"]
         misses += st["plan_misses"]
         w_steps, fp64_instr = st["state_steps"], st["fp64_instr"]
     return {"dev_ms": dev_ms, "long_ms": long_ms, "long_steps": long_steps, "kernel_ms": float(np.mean(kernel_ms)),
-            "traj_ms": float(np.mean(traj_ms)), "launches": launches, "state_steps": w_steps, "fp64_instr": fp64_instr,
+            "traj_ms": float(np.mean(traj_ms)), "host_ms": float(np.mean(host_ms)), "gpu_total_ms": float(np.mean(total_ms)),
+            "tables_ms": float(np.mean(tables_ms)), "ktab_mb": st["ktab_mb"], "launches": launches, "state_steps": w_steps, "fp64_instr": fp64_instr,
             "plan_build_s": st0["plan_build_ms"] * 1e-3, "first_call_s": first_call_s, "plan_misses_first_call": st0["plan_misses"],
             "plan_misses_timed": misses, "packed": packed}
 
@@ -315,6 +318,9 @@ def single_gpu_record(R, Wk, wl, device, batch, steps, warmup, torch, with_cpu=T
                 "h2d_bytes_per_step": int(sum(len(x) for x in batches[0]) * ctypes.sizeof(R._lib.rc_event) + batch * (4 + 8 + 8 * wl.P)),
                 "d2h_bytes_per_step": 8 * batch},
         "gpu_launches": int(m["launches"]),
+        "per_step_ms": {"host_resolve_pack_enqueue": m["host_ms"], "gpu_first_to_last_launch": m["gpu_total_ms"],
+                        "tables_kernel": m["tables_ms"], "propagation_launches": m["kernel_ms"], "traj_kernels_side_stream": m["traj_ms"],
+                        "trajectory_table_mb": m["ktab_mb"]},
         "plan": {"build_s_first_call": m["plan_build_s"], "first_call_s": m["first_call_s"],
                  "cache_misses_first_call": m["plan_misses_first_call"], "cache_misses_timed": m["plan_misses_timed"]},
         "roofline": {
@@ -511,7 +517,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "parallelism": f"one GPU: {batch} models per step in one launch chain on all patterns"}
     for k in ("e2e", "gpu_launches", "roofline", "cpu_baseline", "parity", "clocks", "plan", "timed_region_s", "value_long_run",
-              "long_run_s", "pattern_probs_per_sec", "state_steps_per_sec", "single_logl_latency_ms", "single_logl_launches"):
+              "long_run_s", "per_step_ms", "pattern_probs_per_sec", "state_steps_per_sec", "single_logl_latency_ms", "single_logl_launches"):
         if k in rec:
             line[k] = rec[k]
     if not args.no_sub and args.workload == "c3":

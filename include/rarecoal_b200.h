@@ -78,6 +78,11 @@ typedef struct {
     double plan_build_ms;    /* host time spent building and uploading transition plans in this call                     */
     int32_t plan_misses;     /* event structures of this call that were not in the plan cache                            */
     int32_t plan_evictions;  /* plans evicted (least recently used first) to make room                                   */
+    double ktab_mb;          /* MiB of trajectory tables written by the call (all chunks)                                */
+    int32_t chunks;          /* chunks the batch was cut into to respect "ktab_total_mb"                                 */
+    int32_t models_selfcontained; /* models whose table exceeded the budget and ran the self-contained kernels          */
+    double host_ms;          /* host time of the call up to its last launch: model resolution (validateModel, events to   */
+                             /* grid steps), plan lookup, packing and enqueueing                                         */
 } rc_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -18,6 +18,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rarecoal_b200.h"
@@ -91,16 +92,33 @@ struct PlanEntry {
     }
 };
 
-struct SegHost {
+// piecewise-constant sizes per branch and frozen masks per model, by firing step (layouts of rc_types.h)
+struct SizeStep {
+    int sBegin;
+    double N;
+};
+struct MaskStep {
     int sBegin;
     unsigned mask;
-    double N[RC_MAX_P];
 };
 
 struct ModelHost {
     int status = RC_OK;
     std::string err;
-    std::vector<SegHost> segs;
+    std::vector<std::vector<SizeStep>> sizes;   // [P]
+    std::vector<MaskStep> masks;
+    double size_at(int k, int s) const {
+        const std::vector<SizeStep>& v = sizes[(size_t)k];
+        size_t i = 0, lo = 0, hi = v.size() - 1;
+        while (lo < hi) { size_t mid = (lo + hi + 1) / 2; if (v[mid].sBegin <= s) lo = mid; else hi = mid - 1; }
+        i = lo;
+        return v[i].N;
+    }
+    unsigned mask_at(int s) const {
+        size_t i = 0;
+        while (i + 1 < masks.size() && masks[i + 1].sBegin <= s) ++i;
+        return masks[i].mask;
+    }
     std::vector<rc::StructEv> sev;
     std::vector<int> sevStep;
     std::vector<double> sevM;
@@ -320,12 +338,6 @@ double ghc_pow(double x, int n) {
     }
 }
 
-unsigned seg_mask_at(const std::vector<SegHost>& segs, int s) {
-    size_t i = 0;
-    while (i + 1 < segs.size() && segs[i + 1].sBegin <= s) ++i;
-    return segs[i].mask;
-}
-
 // Resolves one ModelSpec against the grid: event firing steps, (popSize, freeze) segments,
 // structural events and the structural signature.
 void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double* disc, int noShortcut, ModelHost& mh) {
@@ -334,11 +346,8 @@ void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double*
     mh.status = validate_model(P, disc, sorted, mh.err);
     if (mh.status != RC_OK) return;
     sorted = desugar_growth(ctx->times, sorted);
-    SegHost cur;
-    cur.sBegin = 0;
-    cur.mask = 0;
-    for (int k = 0; k < RC_MAX_P; ++k) cur.N[k] = 1.0;       // Core.hs:296-297
-    mh.segs.assign(1, cur);
+    mh.sizes.assign((size_t)P, std::vector<SizeStep>(1, SizeStep{0, 1.0}));     // Core.hs:296-297
+    mh.masks.assign(1, MaskStep{0, 0u});
     bool allFire = true;
     int lastFire = -1;
     for (const rc_event& e : sorted) {
@@ -346,16 +355,16 @@ void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double*
         int f = (int)(std::upper_bound(ctx->times.begin(), ctx->times.end(), e.t) - ctx->times.begin());
         if (f >= T) { allFire = false; continue; }
         lastFire = f;
-        if (e.type == RC_EV_POPSIZE || e.type == RC_EV_FREEZE) {
-            if (mh.segs.back().sBegin != f) {
-                cur.sBegin = f;
-                mh.segs.push_back(cur);
-            }
-            SegHost& sg = mh.segs.back();
-            if (e.type == RC_EV_POPSIZE) sg.N[e.k] = e.v;
-            else if (e.v != 0.0) sg.mask |= (1u << e.k);
-            else sg.mask &= ~(1u << e.k);
-            cur = sg;
+        if (e.type == RC_EV_POPSIZE) {
+            // the last SetPopSize that fires before a step's update is the size of that step
+            std::vector<SizeStep>& v = mh.sizes[(size_t)e.k];
+            if (v.back().sBegin == f) v.back().N = e.v;
+            else v.push_back(SizeStep{f, e.v});
+        } else if (e.type == RC_EV_FREEZE) {
+            if (mh.masks.back().sBegin != f) mh.masks.push_back(MaskStep{f, mh.masks.back().mask});
+            unsigned& m = mh.masks.back().mask;
+            if (e.v != 0.0) m |= (1u << e.k);
+            else m &= ~(1u << e.k);
         } else {
             rc::StructEv se;
             se.type = e.type;
@@ -394,7 +403,7 @@ void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double*
             sig.push_back('|');
             sig.push_back((char)cnt);
             for (int s = 0; s < cnt; ++s) {
-                unsigned m = seg_mask_at(mh.segs, prev + s);
+                unsigned m = mh.mask_at(prev + s);
                 mh.gaps[g].masks.push_back(m);
                 sig.append(reinterpret_cast<const char*>(&m), sizeof m);
             }
@@ -590,6 +599,7 @@ long long count_fp64_instr(const ModelHost& mh, const rc::PlanHost& h, int T) {
 int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, const double* theta, const double* disc,
                const int32_t* noShortcut /*[B]*/, double* dPartial, double* dProbs, cudaStream_t st, int32_t* outStatus, long long* maxPairsOut) {
     ++ctx->evalSerial;
+    const auto tHost0 = std::chrono::steady_clock::now();
     ctx->planMissesAtCall = ctx->planMisses;
     ctx->planEvictionsAtCall = ctx->planEvictions;
     ctx->planBuildMsAtCall = ctx->planBuildMs;
@@ -600,17 +610,34 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
 
     std::vector<ModelHost> mhs((size_t)B);
     bool hit = true;
+    // models are resolved against the grid independently of each other: a large batch (mcmc proposals, possibly with
+    // hundreds of per-step size changes each) is spread over a few host threads; the plan cache is then consulted serially
+    {
+        auto resolve_range = [&](int b0, int b1) {
+            for (int b = b0; b < b1; ++b) {
+                ModelHost& mh = mhs[(size_t)b];
+                if (ctx->compErr) {
+                    mh.status = RC_ERR_COMP;
+                    mh.err = ctx->compErrMsg;
+                } else resolve_model(ctx, ev + evOff[b], evOff[b + 1] - evOff[b], disc + (size_t)b * P, noShortcut[b], mh);
+            }
+        };
+        long long nEvTotal = (long long)evOff[B] - evOff[0];
+        int nThr = (int)std::min<long long>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), nEvTotal / 2048);
+        nThr = std::min(nThr, B / 8);
+        if (nThr <= 1) resolve_range(0, B);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nThr; ++t) pool.emplace_back(resolve_range, (int)((long long)B * t / nThr), (int)((long long)B * (t + 1) / nThr));
+            resolve_range(0, B / nThr);
+            for (auto& th : pool) th.join();
+        }
+    }
     for (int b = 0; b < B; ++b) {
         ModelHost& mh = mhs[(size_t)b];
-        if (ctx->compErr) {
-            mh.status = RC_ERR_COMP;
-            mh.err = ctx->compErrMsg;
-        } else {
-            resolve_model(ctx, ev + evOff[b], evOff[b + 1] - evOff[b], disc + (size_t)b * P, noShortcut[b], mh);
-            if (mh.status == RC_OK && ctx->nPat > 0) {
-                int rc = get_plan(ctx, mh, &hit);
-                if (rc != RC_OK) return rc;
-            }
+        if (mh.status == RC_OK && ctx->nPat > 0) {
+            int rc = get_plan(ctx, mh, &hit);
+            if (rc != RC_OK) return rc;
         }
         if (outStatus) outStatus[b] = mh.status;
         if (mh.status != RC_OK && ctx->err.empty()) ctx->err = mh.err;
@@ -621,19 +648,22 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mhs[(size_t)x].plan < mhs[(size_t)y].plan; });
 
     // ---- pack the per-call blob: headers | structural events | segment offsets | segments | weights
-    size_t nSev = 0, nSeg = 0, nW = 0, nMep = 0;
+    size_t nSev = 0, nSize = 0, nMask = 0, nW = 0, nMep = 0;
     for (auto& mh : mhs) {
         if (mh.status != RC_OK) continue;
         nMep += mh.sev.size() + 1;
         nSev += mh.sev.size();
-        nSeg += mh.segs.size();
+        for (auto& v : mh.sizes) nSize += v.size();
+        nMask += mh.masks.size();
         for (auto& se : mh.sev) if (se.type == RC_EV_SPLIT) nW += (size_t)A1 * A1;
     }
     size_t oModels = 0;
     size_t oSev = align16(oModels + (size_t)B * sizeof(RcModelDev));
-    size_t oSegOff = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
-    size_t oSegs = align16(oSegOff + (size_t)(B + 1) * sizeof(int));
-    size_t oW = align16(oSegs + std::max<size_t>(nSeg, 1) * sizeof(RcSegDev));
+    size_t oSizeOff = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
+    size_t oMaskOff = align16(oSizeOff + ((size_t)B * P + 1) * sizeof(int));
+    size_t oSizes = align16(oMaskOff + (size_t)(B + 1) * sizeof(int));
+    size_t oMasks = align16(oSizes + std::max<size_t>(nSize, 1) * sizeof(RcSizeStepDev));
+    size_t oW = align16(oMasks + std::max<size_t>(nMask, 1) * sizeof(RcMaskStepDev));
     size_t oMep = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
     size_t blobBytes = align16(oMep + std::max<size_t>(nMep, 1) * sizeof(RcModelEpochDev));
     // the pinned staging buffer is reused: wait until the previous call's upload has left it
@@ -648,8 +678,10 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     std::memset(hb, 0, blobBytes);
     RcModelDev* hM = (RcModelDev*)(hb + oModels);
     RcSEvDev* hSev = (RcSEvDev*)(hb + oSev);
-    int* hSegOff = (int*)(hb + oSegOff);
-    RcSegDev* hSegs = (RcSegDev*)(hb + oSegs);
+    int* hSizeOff = (int*)(hb + oSizeOff);
+    int* hMaskOff = (int*)(hb + oMaskOff);
+    RcSizeStepDev* hSizes = (RcSizeStepDev*)(hb + oSizes);
+    RcMaskStepDev* hMasks = (RcMaskStepDev*)(hb + oMasks);
     double* hW = (double*)(hb + oW);
     RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
     size_t mepPos = 0;
@@ -659,7 +691,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
 
     long long tabDoubles = 0;
     int rowsMax = 0;
-    size_t sevPos = 0, segPos = 0, wPos = 0;
+    size_t sevPos = 0, sizePos = 0, maskPos = 0, wPos = 0;
     long long W = 0, slots0 = 0, Wfp = 0;
     const long long miss0 = ctx->planMissesAtCall, evict0 = ctx->planEvictionsAtCall;
     const double build0 = ctx->planBuildMsAtCall;
@@ -669,7 +701,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         RcModelDev& M = hM[pos];
         std::memset(&M, 0, sizeof M);      // the staging buffer is reused: a rejected model must not keep a previous call's
                                            // table offsets (rc_tables_kernel would write its rows over another model's)
-        hSegOff[pos] = (int)segPos;
+        hMaskOff[pos] = (int)maskPos;
+        for (int k = 0; k < P; ++k) hSizeOff[(size_t)pos * P + k] = (int)sizePos;   // overwritten below for a valid model
         M.pad = b;   // original model index: rows of partial / dProbs
         if (mh.status != RC_OK || ctx->nPat == 0) {
             M.nSteps = mh.status != RC_OK ? -1 : 0;
@@ -707,9 +740,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 carrySlots = std::max<long long>(carrySlots, hp.maxEpochSlots);
             }
             if (mh.sShort >= 0) {
-                size_t si = 0;
-                while (si + 1 < mh.segs.size() && mh.segs[si + 1].sBegin <= mh.sShort) ++si;
-                for (int k = 0; k < P; ++k) M.Nshort[k] = mh.segs[si].N[k];
+                for (int k = 0; k < P; ++k) M.Nshort[k] = mh.size_at(k, mh.sShort);
             }
         }
         // per-step table rows: read by the self-contained tiers and by the trajectory kernel of the keyed tier
@@ -737,11 +768,19 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 wPos += (size_t)A1 * A1;
             }
         }
-        for (const SegHost& sg : mh.segs) {
-            RcSegDev& d = hSegs[segPos++];
-            d.sBegin = sg.sBegin;
-            d.frozenMask = sg.mask;
-            std::memcpy(d.N, sg.N, sizeof d.N);
+        for (int k = 0; k < P; ++k) {
+            hSizeOff[(size_t)pos * P + k] = (int)sizePos;
+            for (const SizeStep& z : mh.sizes[(size_t)k]) {
+                RcSizeStepDev& d = hSizes[sizePos++];
+                d.sBegin = z.sBegin;
+                d.pad = 0;
+                d.N = z.N;
+            }
+        }
+        for (const MaskStep& z : mh.masks) {
+            RcMaskStepDev& d = hMasks[maskPos++];
+            d.sBegin = z.sBegin;
+            d.frozenMask = z.mask;
         }
         const rc::PlanHost& h = pe->h;
         W += count_state_steps(mh, h, T);
@@ -750,11 +789,15 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         ctx->stats.n_epochs = h.nEpochs;
         ctx->stats.n_steps = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort + 1 : T;
     }
-    hSegOff[B] = (int)segPos;
+    hSizeOff[(size_t)B * P] = (int)sizePos;
+    hMaskOff[B] = (int)maskPos;
     ctx->stats.state_steps = W;
     ctx->stats.slots = slots0;
     ctx->stats.plan_cache_hit = hit ? 1 : 0;
     ctx->stats.fp64_instr = Wfp;
+    ctx->stats.ktab_mb = (double)ktabPairs * 16.0 / 1048576.0;
+    ctx->stats.chunks = 1;
+    for (int pos = 0; pos < B; ++pos) ctx->stats.models_selfcontained += hM[pos].nSteps > 0 && hM[pos].mode == 0;
     ctx->stats.plan_misses = (int32_t)(ctx->planMisses - miss0);
     ctx->stats.plan_evictions = (int32_t)(ctx->planEvictions - evict0);
     ctx->stats.plan_build_ms = ctx->planBuildMs - build0;
@@ -783,8 +826,10 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     unsigned char* db = (unsigned char*)ctx->dBlob.p;
     const RcModelDev* dM = (const RcModelDev*)(db + oModels);
     const RcSEvDev* dSev = (const RcSEvDev*)(db + oSev);
-    const int* dSegOff = (const int*)(db + oSegOff);
-    const RcSegDev* dSegs = (const RcSegDev*)(db + oSegs);
+    const int* dSizeOff = (const int*)(db + oSizeOff);
+    const int* dMaskOff = (const int*)(db + oMaskOff);
+    const RcSizeStepDev* dSizes = (const RcSizeStepDev*)(db + oSizes);
+    const RcMaskStepDev* dMasks = (const RcMaskStepDev*)(db + oMasks);
     const double* dW = (const double*)(db + oW);
     const RcModelEpochDev* dMep = (const RcModelEpochDev*)(db + oMep);
 
@@ -796,7 +841,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     CK(cudaEventRecord(ctx->evt[1], st));
     int launches = 0;
     if (rowsMax > 0) {
-        CK(rc_launch_tables(dM, dSegs, dSegOff, (const double*)ctx->dDts.p, (double*)ctx->dTab.p, P, A1, rowsMax, B, st));
+        CK(rc_launch_tables(dM, dSizes, dSizeOff, dMasks, dMaskOff, (const double*)ctx->dDts.p, (double*)ctx->dTab.p, P, A1, rowsMax, B, st));
         ++launches;
     }
     CK(cudaEventRecord(ctx->evt[2], st));
@@ -898,6 +943,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     ++launches;
     CK(cudaEventRecord(ctx->evt[4], st));
     ctx->stats.launches = launches;
+    ctx->stats.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count();
     ctx->statsPending = true;
     return RC_OK;
 }
@@ -933,6 +979,7 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
             acc.state_steps += ctx->stats.state_steps; acc.slots += ctx->stats.slots;
             acc.kernel_ms += ctx->stats.kernel_ms; acc.traj_ms += ctx->stats.traj_ms; acc.tables_ms += ctx->stats.tables_ms;
             acc.total_ms += ctx->stats.total_ms; acc.launches += ctx->stats.launches;
+            acc.host_ms += ctx->stats.host_ms; acc.ktab_mb += ctx->stats.ktab_mb; acc.chunks += 1; acc.models_selfcontained += ctx->stats.models_selfcontained;
             acc.fp64_instr += ctx->stats.fp64_instr; acc.plan_misses += ctx->stats.plan_misses;
             acc.plan_evictions += ctx->stats.plan_evictions; acc.plan_build_ms += ctx->stats.plan_build_ms;
             acc.plan_cache_hit = nChunks == 1 ? ctx->stats.plan_cache_hit : (acc.plan_cache_hit && ctx->stats.plan_cache_hit);

@@ -15,20 +15,30 @@
 
 // ------------------------------------------------------------------------------------------------
 // Per-step tables.  Formulas keep the reference's operation order (Core.hs:240,270,279).
-__global__ void rc_tables_kernel(const RcModelDev* __restrict__ models, const RcSegDev* __restrict__ segs,
-                                 const int* __restrict__ segOff, const double* __restrict__ dts,
+__global__ void rc_tables_kernel(const RcModelDev* __restrict__ models, const RcSizeStepDev* __restrict__ sizes,
+                                 const int* __restrict__ sizeOff, const RcMaskStepDev* __restrict__ masks,
+                                 const int* __restrict__ maskOff, const double* __restrict__ dts,
                                  double* __restrict__ tab, int P, int A1) {
     const int b = blockIdx.y;
     const int s = blockIdx.x;
     const RcModelDev& M = models[b];
     if (s >= M.rowsAvail) return;
-    // last segment with sBegin <= s
-    int lo = segOff[b], hi = segOff[b + 1] - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (segs[mid].sBegin <= s) lo = mid; else hi = mid - 1;
+    __shared__ double Ns[RC_MAX_P];
+    __shared__ unsigned maskS;
+    // last entry with sBegin <= s: thread k for branch k's sizes, thread P for the frozen mask
+    if ((int)threadIdx.x <= P) {
+        const bool isMask = (int)threadIdx.x == P;
+        int lo = isMask ? maskOff[b] : sizeOff[b * P + threadIdx.x];
+        int hi = (isMask ? maskOff[b + 1] : sizeOff[b * P + threadIdx.x + 1]) - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((isMask ? masks[mid].sBegin : sizes[mid].sBegin) <= s) lo = mid; else hi = mid - 1;
+        }
+        if (isMask) maskS = masks[lo].frozenMask;
+        else Ns[threadIdx.x] = sizes[lo].N;
     }
-    const RcSegDev& sg = segs[lo];
+    __syncthreads();
+    const unsigned frozenMask = maskS;
     const double dt = dts[s];
     const int rowLen = rc_row_len(P, A1);
     double* row = tab + M.tabOff + (long long)s * rowLen;
@@ -36,19 +46,19 @@ __global__ void rc_tables_kernel(const RcModelDev* __restrict__ models, const Rc
     for (int i = threadIdx.x; i < rowLen; i += blockDim.x) {
         double v = 0.0;
         if (i == 0) v = dt;
-        else if (i == 1) v = (double)sg.frozenMask;
+        else if (i == 1) v = (double)frozenMask;
         else if (i < RC_ROW_PAIRS + 2 * nE) {
             const int q = i - RC_ROW_PAIRS;
             const int pi = q >> 1, k = pi / A1, j = pi - k * A1;
-            const bool frozen = (sg.frozenMask >> k) & 1u;
-            const double xx = (double)j, pp = sg.N[k];
+            const bool frozen = (frozenMask >> k) & 1u;
+            const double xx = (double)j, pp = Ns[k];
             if (j == 0) {
                 if (q & 1) v = frozen ? 0.0 : 1.0 / pp;
                 else v = (frozen || !(dt > 0.0)) ? 1.0 : exp(-(0.5 * dt / pp));
             } else if (frozen) v = 0.0;
             else if (q & 1) v = 1.0 - exp(-(xx * (xx + 1.0) / 2.0 * (1.0 / pp) * dt));
             else v = xx * (xx - 1.0) / 2.0 * (1.0 / pp);
-        } else if (i < RC_ROW_PAIRS + 2 * nE + P) v = sg.N[i - RC_ROW_PAIRS - 2 * nE];
+        } else if (i < RC_ROW_PAIRS + 2 * nE + P) v = Ns[i - RC_ROW_PAIRS - 2 * nE];
         row[i] = v;
     }
 }
@@ -2142,11 +2152,11 @@ static cudaError_t rc_ensure_smem(const void* kernel, size_t smem, bool carveout
     have = smem;
     return cudaSuccess;
 }
-cudaError_t rc_launch_tables(const RcModelDev* models, const RcSegDev* segs, const int* segOff, const double* dts,
-                             double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st) {
+cudaError_t rc_launch_tables(const RcModelDev* models, const RcSizeStepDev* sizes, const int* sizeOff, const RcMaskStepDev* masks,
+                             const int* maskOff, const double* dts, double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st) {
     if (rowsMax <= 0 || B <= 0) return cudaSuccess;
     dim3 grid((unsigned)rowsMax, (unsigned)B);
-    rc_tables_kernel<<<grid, 128, 0, st>>>(models, segs, segOff, dts, tab, P, A1);
+    rc_tables_kernel<<<grid, 128, 0, st>>>(models, sizes, sizeOff, masks, maskOff, dts, tab, P, A1);
     return cudaGetLastError();
 }
 

@@ -7,8 +7,8 @@
 
 size_t rc_propagate_smem_bytes(int cap, int nnzw, int P, int rowLen);
 
-cudaError_t rc_launch_tables(const RcModelDev* models, const RcSegDev* segs, const int* segOff, const double* dts,
-                             double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st);
+cudaError_t rc_launch_tables(const RcModelDev* models, const RcSizeStepDev* sizes, const int* sizeOff, const RcMaskStepDev* masks,
+                             const int* maskOff, const double* dts, double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st);
 cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
                                 const double* tab, const double* wpool, double* pOut, int b0, int nB,
                                 cudaStream_t st);

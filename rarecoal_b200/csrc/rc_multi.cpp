@@ -224,6 +224,7 @@ static void fold_stats(RcMulti* m, const std::vector<rc_ctx*>& ctxs, const std::
         acc.kernel_ms = std::max(acc.kernel_ms, s.kernel_ms); acc.traj_ms = std::max(acc.traj_ms, s.traj_ms);
         acc.tables_ms = std::max(acc.tables_ms, s.tables_ms); acc.total_ms = std::max(acc.total_ms, s.total_ms);
         acc.plan_build_ms = std::max(acc.plan_build_ms, s.plan_build_ms);
+        acc.host_ms = std::max(acc.host_ms, s.host_ms); acc.ktab_mb += s.ktab_mb; acc.chunks = std::max(acc.chunks, s.chunks); acc.models_selfcontained += s.models_selfcontained;
         acc.launches += s.launches; acc.plan_misses += s.plan_misses; acc.plan_evictions += s.plan_evictions;
         acc.plan_cache_hit = acc.plan_cache_hit && s.plan_cache_hit;
         acc.n_epochs = s.n_epochs; acc.n_steps = s.n_steps;

@@ -189,11 +189,18 @@ struct RcModelDev {
     double Nshort[RC_MAX_P];   // population sizes at the shortcut step
 };
 
-// Piecewise-constant (popSize, freeze) segments used by the table kernel.
-struct RcSegDev {
+// Piecewise-constant population sizes and freeze flags used by the table kernel: per (model, branch) the grid steps at
+// which the size changes (SetPopSize, Core.hs:152-153; many entries under SetGrowthRate), per model the steps at which the
+// frozen mask changes (SetFreeze, Core.hs:154-157).  Both lists start with an entry for step 0 (N = 1, nothing frozen,
+// Core.hs:296-297) and are sorted by step.
+struct RcSizeStepDev {
+    int sBegin;
+    int pad;
+    double N;
+};
+struct RcMaskStepDev {
     int sBegin;
     unsigned frozenMask;
-    double N[RC_MAX_P];
 };
 
 // Table row layout (doubles), one row per (model, grid step):

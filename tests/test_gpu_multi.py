@@ -50,6 +50,7 @@ def test_multi_context_models_sharded_on_one_device(default_times):
     nvec, pats, cnt = wl.problem()
     m = R.Engine(devices=[0, 0])
     assert m.nrDevices == 2
+    m.set_option("multi_shard", 1)                # both contexts sit on ONE device here: NCCL would refuse the pattern split
     m.set_problem(nvec, wl.max_af, pats, cnt, wl.total_sites)
     logl2, probs2, status2 = m.eval_models(specs, want_probs=True)
     assert np.array_equal(logl2, logl) and np.array_equal(probs2, probs) and np.array_equal(status2, status)

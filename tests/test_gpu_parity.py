@@ -262,21 +262,29 @@ def test_sharded_partials_sum_to_whole(default_times, fourpop):
 
 
 def test_large_batches_are_chunked_by_table_budget(default_times):
-    # a batch whose trajectory tables exceed "ktab_total_mb" runs in chunks and gives the same answers
+    # a batch whose trajectory tables exceed "ktab_total_mb" runs in chunks and gives the same answers; a model whose own
+    # table exceeds the budget runs the self-contained kernels and does not shrink the chunks of the others
     e = R.Engine(0)
     nvec, pats, cnt = Wk.c3_problem(max_af=5)
     e.set_problem(nvec, 5, pats, cnt, Wk.TOTAL_SITES)
     specs = [_spec(8, default_times, ev) for ev in Wk.c4_batch(9)]
     logl, probs, status = e.eval_models(specs, want_probs=True)
     one_chunk = e.stats()
-    e.set_option("ktab_total_mb", 1.5)
-    e.eval_models(specs[:1])                       # adapts the chunk size to the table of one model
+    assert one_chunk["chunks"] == 1 and one_chunk["models_selfcontained"] == 0
+    per_model = one_chunk["ktab_mb"] / 9
+    e.set_option("ktab_total_mb", 3.5 * per_model)          # three models per chunk
+    e.eval_models(specs[:1])                                 # adapts the chunk size to the table of one model
     logl2, probs2, status2 = e.eval_models(specs, want_probs=True)
     st = e.stats()
-    assert st["launches"] > one_chunk["launches"]  # several chunks
+    assert st["chunks"] == 3 and st["models_selfcontained"] == 0 and st["launches"] > one_chunk["launches"]
     assert st["state_steps"] == one_chunk["state_steps"]
-    # a model whose own table exceeds the budget falls back to the self-contained kernel: same answers to rounding
-    assert _relerr(probs2, probs) < 1e-12 and np.max(np.abs(logl2 - logl) / np.abs(logl)) < 1e-13 and not status2.any()
+    assert np.array_equal(probs2, probs) and np.array_equal(logl2, logl) and not status2.any()
+    # budget below one model's table: every model falls back to the self-contained kernel, in ONE chunk
+    e.set_option("ktab_total_mb", 0.5 * per_model)
+    logl3, probs3, status3 = e.eval_models(specs, want_probs=True)
+    st = e.stats()
+    assert st["chunks"] == 1 and st["models_selfcontained"] == 9 and st["state_steps"] == one_chunk["state_steps"]
+    assert _relerr(probs3, probs) < 1e-12 and np.max(np.abs(logl3 - logl) / np.abs(logl)) < 1e-13 and not status3.any()
     e.close()
 
 
