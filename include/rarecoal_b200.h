@@ -81,6 +81,8 @@ typedef struct {
     double ktab_mb;          /* MiB of trajectory tables written by the call (all chunks)                                */
     int32_t chunks;          /* chunks the batch was cut into to respect "ktab_total_mb"                                 */
     int32_t models_selfcontained; /* models whose table exceeded the budget and ran the self-contained kernels          */
+    int32_t graph_replay;    /* 1 if the launch chain of the (last chunk of the) call was replayed as a CUDA graph        */
+    int32_t pad_;
     double host_ms;          /* host time of the call up to its last launch: model resolution (validateModel, events to   */
                              /* grid steps), plan lookup, packing and enqueueing                                         */
 } rc_stats;
@@ -191,6 +193,8 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
  *                          to the row / state kernels (used by the parity tests to cover those kernels too)
  *   "ktab_model_mb" (1024) largest trajectory table of one model; a model above it uses the self-contained kernels
  *   "ktab_total_mb" (12288) largest trajectory table memory of one call
+ *   "graphs" (1)           the launch chain of a call is captured as a CUDA graph the second time the same launch signature
+ *                          (batch size, event structures, buffers) is seen and replayed from then on; 0 = plain launches
  *   "plan_cache_max" (64)  transition plans (one per event structure) kept per context, least recently used evicted first
  *   "plan_cache_mb" (49152) device memory the cached plans may hold                                        */
 int rc_set_option(rc_ctx* ctx, const char* name, double value);

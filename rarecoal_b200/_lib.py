@@ -21,7 +21,7 @@ class rc_stats(C.Structure):
                 ("plan_cache_hit", C.c_int32), ("n_epochs", C.c_int32), ("n_steps", C.c_int32),
                 ("fp64_instr", C.c_int64), ("plan_build_ms", C.c_double), ("plan_misses", C.c_int32),
                 ("plan_evictions", C.c_int32), ("ktab_mb", C.c_double), ("chunks", C.c_int32),
-                ("models_selfcontained", C.c_int32), ("host_ms", C.c_double)]
+                ("models_selfcontained", C.c_int32), ("graph_replay", C.c_int32), ("pad_", C.c_int32), ("host_ms", C.c_double)]
 
 
 _dp, _ip, _lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -195,6 +196,17 @@ struct rc_ctx {
     int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
     bool statsPending = false;
     bool blobInFlight = false;
+    // launch graphs by launch signature ("graphs" option); dropped whenever a plan or a buffer they point to goes away
+    int optGraphs = 1;
+    std::map<std::string, cudaGraphExec_t> graphs;
+    std::map<std::string, int> graphLaunches;
+    std::set<std::string> graphSeen;
+    void clear_graphs() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+        graphLaunches.clear();
+        graphSeen.clear();
+    }
     rc_stats stats;
     rc_ctx* child = nullptr;
     // multi-GPU: this context is one rank of an NCCL communicator (rc_comm_init), or the front of a single-process
@@ -204,6 +216,7 @@ struct rc_ctx {
     RcMulti* multi = nullptr;
 
     void clear_plans() {
+        clear_graphs();
         for (auto& kv : plans) {
             kv.second->release();
             delete kv.second;
@@ -507,7 +520,7 @@ void evict_plans(rc_ctx* ctx, size_t needBytes) {
             if (it->second->lastUse < ctx->evalSerial && (victim == ctx->plans.end() || it->second->lastUse < victim->second->lastUse))
                 victim = it;
         if (victim == ctx->plans.end()) break;          // everything left belongs to the current batch
-        if (!synced) { cudaDeviceSynchronize(); synced = true; }   // launches of earlier calls may still read the plan
+        if (!synced) { cudaDeviceSynchronize(); synced = true; ctx->clear_graphs(); }   // launches of earlier calls may still read the plan
         ctx->planBytes -= victim->second->bytes;
         victim->second->release();
         delete victim->second;
@@ -623,6 +636,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
             }
         };
         long long nEvTotal = (long long)evOff[B] - evOff[0];
+        for (int q = evOff[0]; q < evOff[B]; ++q) nEvTotal += ev[q].type == RC_EV_GROWTH ? 512 : 0;   // rewritten into per-step events
         int nThr = (int)std::min<long long>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), nEvTotal / 2048);
         nThr = std::min(nThr, B / 8);
         if (nThr <= 1) resolve_range(0, B);
@@ -657,15 +671,18 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         nMask += mh.masks.size();
         for (auto& se : mh.sev) if (se.type == RC_EV_SPLIT) nW += (size_t)A1 * A1;
     }
+    // Layout: everything whose size follows from (B, structures) first, the per-step size lists — whose length moves with
+    // the parameters under SetGrowthRate — last: the device addresses the kernels are launched with then stay the same from
+    // call to call and a captured launch graph (below) can be replayed.
     size_t oModels = 0;
     size_t oSev = align16(oModels + (size_t)B * sizeof(RcModelDev));
-    size_t oSizeOff = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
+    size_t oMep = align16(oSev + std::max<size_t>(nSev, 1) * sizeof(RcSEvDev));
+    size_t oW = align16(oMep + std::max<size_t>(nMep, 1) * sizeof(RcModelEpochDev));
+    size_t oSizeOff = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
     size_t oMaskOff = align16(oSizeOff + ((size_t)B * P + 1) * sizeof(int));
-    size_t oSizes = align16(oMaskOff + (size_t)(B + 1) * sizeof(int));
-    size_t oMasks = align16(oSizes + std::max<size_t>(nSize, 1) * sizeof(RcSizeStepDev));
-    size_t oW = align16(oMasks + std::max<size_t>(nMask, 1) * sizeof(RcMaskStepDev));
-    size_t oMep = align16(oW + std::max<size_t>(nW, 1) * sizeof(double));
-    size_t blobBytes = align16(oMep + std::max<size_t>(nMep, 1) * sizeof(RcModelEpochDev));
+    size_t oMasks = align16(oMaskOff + (size_t)(B + 1) * sizeof(int));
+    size_t oSizes = align16(oMasks + std::max<size_t>(nMask, 1) * sizeof(RcMaskStepDev));
+    size_t blobBytes = align16(oSizes + std::max<size_t>(nSize, 1) * sizeof(RcSizeStepDev));
     // the pinned staging buffer is reused: wait until the previous call's upload has left it
     if (ctx->blobInFlight) {
         CK(cudaEventSynchronize(ctx->evt[5]));
@@ -838,110 +855,181 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     CK(cudaEventRecord(ctx->evt[5], st));
     ctx->blobInFlight = true;
     if (dProbs && ctx->world > 1) CK(cudaMemsetAsync(dProbs, 0, (size_t)B * ctx->nPatGlobal * sizeof(double), st));
-    CK(cudaEventRecord(ctx->evt[1], st));
+    // ---- the launch chain.  Enqueued on the stream directly, or — from the second call with the same launch signature on —
+    //      replayed as a CUDA graph captured from the same code: a step is 25 to 60 short launches over up to 8 streams
+    //      with event joins, and for a small batch (a single `logl`) the host-side launch cost is most of the call.
+    const int rowsGrid = rowsMax > 0 ? ((rowsMax + 63) / 64) * 64 : 0;      // the table kernel skips rows >= rowsAvail
     int launches = 0;
-    if (rowsMax > 0) {
-        CK(rc_launch_tables(dM, dSizes, dSizeOff, dMasks, dMaskOff, (const double*)ctx->dDts.p, (double*)ctx->dTab.p, P, A1, rowsMax, B, st));
-        ++launches;
-    }
-    CK(cudaEventRecord(ctx->evt[2], st));
-    ctx->trajTimed = false;
-    for (int pos = 0; pos < B;) {
-        const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
-        int end = pos + 1;
-        while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
-        if (pe && ctx->nPat > 0) {
-            bool anyKeyed = false, anySelf = false;
-            for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
-            if (pe->d.nFastBins > 0 && anyKeyed) {
-                const bool timeIt = !ctx->trajTimed;      // trajectory kernels of the first plan group are timed
-                cudaStream_t ts = ctx->trajStream;
-                while ((int)ctx->evTraj.size() < pe->h.nEpochs) {
-                    cudaEvent_t ev = nullptr;
-                    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                    ctx->evTraj.push_back(ev);
-                }
-                CK(cudaEventRecord(ctx->evFork, st));     // tables written, previous work on st finished
-                CK(cudaStreamWaitEvent(ts, ctx->evFork, 0));
-                if (timeIt) CK(cudaEventRecord(ctx->evt[6], ts));
-                for (int e = 0; e < pe->h.nEpochs; ++e) {
-                    CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
-                                      (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, ts));
-                    CK(cudaEventRecord(ctx->evTraj[(size_t)e], ts));
-                    ++launches;
-                }
-                if (timeIt) { CK(cudaEventRecord(ctx->evt[7], ts)); ctx->trajTimed = true; }
-                // one launch per structural epoch and bin group; b ping-pongs between the two carry buffers.  A batch large
-                // enough is cut into RC_NCHAIN model ranges, each with its own chain of streams.
-                const int nModels = end - pos;
-                const int nChains = nModels >= 16 ? RC_NCHAIN : 1;
-                if (nChains > 1) {
-                    CK(cudaEventRecord(ctx->evChain[0], st));         // everything queued so far (blob, tables) precedes the chains
-                    for (int c = 1; c < nChains; ++c) CK(cudaStreamWaitEvent(ctx->chainStream[c], ctx->evChain[0], 0));
-                }
-                for (int e = 0; e < pe->h.nEpochs; ++e) {
-                    double* c0 = (double*)ctx->dBCarry.p;
-                    double* c1 = c0 + (size_t)carrySlots * B;
-                    for (int c = 0; c < nChains; ++c) {
-                        cudaStream_t cs = c == 0 ? st : ctx->chainStream[c];
-                        const int p0 = pos + (int)((long long)nModels * c / nChains), p1 = pos + (int)((long long)nModels * (c + 1) / nChains);
-                        CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)e], 0));
-                        // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
-                        // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
-                        struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
-                        Launch L[RC_NGROUP];
-                        int nL = 0;
-                        for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
-                            if (pe->h.nKBins[(size_t)v] == 0) continue;
-                            // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then
-                            // run in the same launch as the small-pattern bins (their headers are contiguous but for one unused
-                            // entry).
-                            const int nb0 = pe->h.nKBins[(size_t)v], nb1 = v + 1 < RC_NGROUP * (e + 1) ? pe->h.nKBins[(size_t)v + 1] : 0;
-                            if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
-                                pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
-                                (long long)(nb0 + nb1) * nModels < 3LL * 7 * ctx->smCount) {
-                                L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
-                                           std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
-                                           std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
-                                ++v;
-                                continue;
+    bool capturing = false;
+    auto rec_timing = [&](cudaEvent_t e, cudaStream_t s2) {
+        // under capture a timing event must be an event-record NODE (it is recorded when the graph runs)
+        return capturing ? cudaEventRecordWithFlags(e, s2, cudaEventRecordExternal) : cudaEventRecord(e, s2);
+    };
+    auto enqueue = [&](cudaStream_t st) -> int {
+        launches = 0;
+        CK(rec_timing(ctx->evt[1], st));
+        if (rowsGrid > 0) {
+            CK(rc_launch_tables(dM, dSizes, dSizeOff, dMasks, dMaskOff, (const double*)ctx->dDts.p, (double*)ctx->dTab.p, P, A1, rowsGrid, B, st));
+            ++launches;
+        }
+        CK(rec_timing(ctx->evt[2], st));
+        ctx->trajTimed = false;
+        for (int pos = 0; pos < B;) {
+            const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
+            int end = pos + 1;
+            while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
+            if (pe && ctx->nPat > 0) {
+                bool anyKeyed = false, anySelf = false;
+                for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
+                if (pe->d.nFastBins > 0 && anyKeyed) {
+                    const bool timeIt = !ctx->trajTimed;      // trajectory kernels of the first plan group are timed
+                    cudaStream_t ts = ctx->trajStream;
+                    while ((int)ctx->evTraj.size() < pe->h.nEpochs) {
+                        cudaEvent_t ev = nullptr;
+                        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                        ctx->evTraj.push_back(ev);
+                    }
+                    CK(cudaEventRecord(ctx->evFork, st));     // tables written, previous work on st finished
+                    CK(cudaStreamWaitEvent(ts, ctx->evFork, 0));
+                    if (timeIt) CK(rec_timing(ctx->evt[6], ts));
+                    for (int e = 0; e < pe->h.nEpochs; ++e) {
+                        CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
+                                          (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, ts));
+                        // (the timing record precedes the epoch's join event: a captured side stream must end in a join)
+                        if (timeIt && e + 1 == pe->h.nEpochs) { CK(rec_timing(ctx->evt[7], ts)); ctx->trajTimed = true; }
+                        CK(cudaEventRecord(ctx->evTraj[(size_t)e], ts));
+                        ++launches;
+                    }
+                    // one launch per structural epoch and bin group; b ping-pongs between the two carry buffers.  A batch large
+                    // enough is cut into RC_NCHAIN model ranges, each with its own chain of streams.
+                    const int nModels = end - pos;
+                    const int nChains = nModels >= 16 ? RC_NCHAIN : 1;
+                    if (nChains > 1) {
+                        CK(cudaEventRecord(ctx->evChain[0], st));         // everything queued so far (blob, tables) precedes the chains
+                        for (int c = 1; c < nChains; ++c) CK(cudaStreamWaitEvent(ctx->chainStream[c], ctx->evChain[0], 0));
+                    }
+                    for (int e = 0; e < pe->h.nEpochs; ++e) {
+                        double* c0 = (double*)ctx->dBCarry.p;
+                        double* c1 = c0 + (size_t)carrySlots * B;
+                        for (int c = 0; c < nChains; ++c) {
+                            cudaStream_t cs = c == 0 ? st : ctx->chainStream[c];
+                            const int p0 = pos + (int)((long long)nModels * c / nChains), p1 = pos + (int)((long long)nModels * (c + 1) / nChains);
+                            CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)e], 0));
+                            // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
+                            // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
+                            struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
+                            Launch L[RC_NGROUP];
+                            int nL = 0;
+                            for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
+                                if (pe->h.nKBins[(size_t)v] == 0) continue;
+                                // A batch too small to fill the GPU cares about launches, not occupancy: the tiny-pattern bins then
+                                // run in the same launch as the small-pattern bins (their headers are contiguous but for one unused
+                                // entry).
+                                const int nb0 = pe->h.nKBins[(size_t)v], nb1 = v + 1 < RC_NGROUP * (e + 1) ? pe->h.nKBins[(size_t)v + 1] : 0;
+                                if (pe->h.epochMode[(size_t)v] == RC_MODE_PAT && nb1 > 0 && pe->h.epochMode[(size_t)v + 1] == RC_MODE_PAT + 1 &&
+                                    pe->h.kBinBase[(size_t)v + 1] == pe->h.kBinBase[(size_t)v] + nb0 + 1 &&
+                                    (long long)(nb0 + nb1) * nModels < 3LL * 7 * ctx->smCount) {
+                                    L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
+                                               std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
+                                               std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
+                                    ++v;
+                                    continue;
+                                }
+                                L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
                             }
-                            L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
+                            if (nL > 1) CK(cudaEventRecord(ctx->evEpoch[c], cs));
+                            for (int q = nL - 1; q >= 0; --q) {
+                                cudaStream_t gs = q == 0 ? cs : ctx->grpStream[c][q - 1];
+                                if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch[c], 0));
+                                CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
+                                                             (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1,
+                                                             (e & 1) ? c1 : c0, carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, p0, p1 - p0, gs));
+                                ++launches;
+                                if (q > 0) CK(cudaEventRecord(ctx->evGrp[c][q - 1], gs));
+                            }
+                            for (int q = 1; q < nL; ++q) CK(cudaStreamWaitEvent(cs, ctx->evGrp[c][q - 1], 0));
                         }
-                        if (nL > 1) CK(cudaEventRecord(ctx->evEpoch[c], cs));
-                        for (int q = nL - 1; q >= 0; --q) {
-                            cudaStream_t gs = q == 0 ? cs : ctx->grpStream[c][q - 1];
-                            if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch[c], 0));
-                            CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
-                                                         (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1,
-                                                         (e & 1) ? c1 : c0, carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, p0, p1 - p0, gs));
-                            if (q > 0) CK(cudaEventRecord(ctx->evGrp[c][q - 1], gs));
-                            ++launches;
-                        }
-                        for (int q = 1; q < nL; ++q) CK(cudaStreamWaitEvent(cs, ctx->evGrp[c][q - 1], 0));
+                    }
+                    for (int c = 1; c < nChains; ++c) {
+                        CK(cudaEventRecord(ctx->evChain[c], ctx->chainStream[c]));
+                        CK(cudaStreamWaitEvent(st, ctx->evChain[c], 0));
                     }
                 }
-                for (int c = 1; c < nChains; ++c) {
-                    CK(cudaEventRecord(ctx->evChain[c], ctx->chainStream[c]));
-                    CK(cudaStreamWaitEvent(st, ctx->evChain[c], 0));
+                if (pe->d.nFastBins > 0 && anySelf) {
+                    CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+                    ++launches;
+                }
+                if (pe->d.nBins > 0) {
+                    CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+                    ++launches;
                 }
             }
-            if (pe->d.nFastBins > 0 && anySelf) {
-                CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
-                ++launches;
-            }
-            if (pe->d.nBins > 0) {
-                CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
-                ++launches;
+            pos = end;
+        }
+        CK(rec_timing(ctx->evt[3], st));
+        CK(rc_launch_reduce((const double*)ctx->dPOut.p, (const long long*)ctx->dCounts.p, (const int*)ctx->dPatGlobal.p, dM,
+                            ctx->nPat, ctx->nPatGlobal, B, dPartial, dProbs, st));
+        ++launches;
+        CK(rec_timing(ctx->evt[4], st));
+        return RC_OK;
+    };
+    {
+        // launch signature: everything baked into the kernel parameters and grid sizes of the chain
+        std::string key;
+        auto put = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
+        auto putv = [&](long long v) { put(&v, sizeof v); };
+        putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat);
+        const void* ptrs[] = {db + oModels, db + oSev, db + oMep, db + oW, db + oSizeOff, db + oMaskOff, db + oMasks, db + oSizes,
+                              ctx->dTab.p, ctx->dPOut.p, ctx->dKTab.p, ctx->dAEnd.p, ctx->dAShort.p, ctx->dBCarry.p, ctx->dDAcc.p,
+                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p};
+        put(ptrs, sizeof ptrs);
+        for (int pos = 0; pos < B;) {
+            const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
+            int end = pos + 1;
+            while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
+            bool anyKeyed = false, anySelf = false;
+            for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
+            putv((long long)(uintptr_t)pe); putv(end); putv(anyKeyed); putv(anySelf);
+            pos = end;
+        }
+        cudaGraphExec_t exec = nullptr;
+        if (ctx->optGraphs) {
+            auto it = ctx->graphs.find(key);
+            if (it != ctx->graphs.end()) exec = it->second;
+            else if (ctx->graphSeen.count(key)) {
+                // second sighting: capture the chain on the context's own stream (the caller's may be the legacy default
+                // stream, which cannot capture) and keep the executable graph
+                if (ctx->graphs.size() >= 48) ctx->clear_graphs();
+                cudaGraph_t g = nullptr;
+                capturing = true;
+                cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+                int rcq = ce == cudaSuccess ? enqueue(ctx->stream) : RC_ERR_CUDA;
+                cudaError_t ee = cudaStreamEndCapture(ctx->stream, &g);
+                capturing = false;
+                if (rcq == RC_OK && ee == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+                    ctx->graphs[key] = exec;
+                    ctx->graphLaunches[key] = launches | (ctx->trajTimed ? 1 << 30 : 0);
+                } else {
+                    exec = nullptr;
+                    cudaGetLastError();
+                    ctx->optGraphs = 0;                       // capture is not usable here: stay on plain launches
+                }
+                if (g) cudaGraphDestroy(g);
+            } else {
+                if (ctx->graphSeen.size() >= 4096) ctx->graphSeen.clear();
+                ctx->graphSeen.insert(key);
             }
         }
-        pos = end;
+        if (exec) {
+            CK(cudaGraphLaunch(exec, st));
+            launches = ctx->graphLaunches[key] & ((1 << 30) - 1);
+            ctx->trajTimed = (ctx->graphLaunches[key] >> 30) & 1;
+            ctx->stats.graph_replay = 1;
+        } else {
+            int rcq = enqueue(st);
+            if (rcq != RC_OK) return rcq;
+        }
     }
-    CK(cudaEventRecord(ctx->evt[3], st));
-    CK(rc_launch_reduce((const double*)ctx->dPOut.p, (const long long*)ctx->dCounts.p, (const int*)ctx->dPatGlobal.p, dM,
-                        ctx->nPat, ctx->nPatGlobal, B, dPartial, dProbs, st));
-    ++launches;
-    CK(cudaEventRecord(ctx->evt[4], st));
     ctx->stats.launches = launches;
     ctx->stats.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count();
     ctx->statsPending = true;
@@ -992,13 +1080,17 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
 
 int collect_stats(rc_ctx* ctx) {
     if (!ctx->statsPending) return RC_OK;
-    float ms = 0;
     CK(cudaEventSynchronize(ctx->evt[4]));
-    CK(cudaEventElapsedTime(&ms, ctx->evt[1], ctx->evt[2])); ctx->stats.tables_ms = ms;
-    CK(cudaEventElapsedTime(&ms, ctx->evt[2], ctx->evt[3])); ctx->stats.kernel_ms = ms;
-    ctx->stats.traj_ms = 0.0;
-    if (ctx->trajTimed) { CK(cudaEventElapsedTime(&ms, ctx->evt[6], ctx->evt[7])); ctx->stats.traj_ms = ms; }
-    CK(cudaEventElapsedTime(&ms, ctx->evt[0], ctx->evt[4])); ctx->stats.total_ms = ms;
+    // a span that cannot be read (it never fails the evaluation) is reported as 0
+    auto span = [](cudaEvent_t a, cudaEvent_t b) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+        return (double)ms;
+    };
+    ctx->stats.tables_ms = span(ctx->evt[1], ctx->evt[2]);
+    ctx->stats.kernel_ms = span(ctx->evt[2], ctx->evt[3]);
+    ctx->stats.traj_ms = ctx->trajTimed ? span(ctx->evt[6], ctx->evt[7]) : 0.0;
+    ctx->stats.total_ms = span(ctx->evt[0], ctx->evt[4]);
     ctx->statsPending = false;
     return RC_OK;
 }
@@ -1126,6 +1218,7 @@ void rc_destroy(rc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();          // launches queued by rc_eval_partial on a caller's stream may still read the buffers
     if (ctx->child) rc_destroy(ctx->child);
+    ctx->clear_graphs();
     if (ctx->comm) {
         std::string e;
         if (const rc::NcclApi* api = rc::nccl_api(e)) api->CommDestroy(ctx->comm);
@@ -1384,10 +1477,11 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
             ctx->optPattern = v;
         }
     }
+    else if (n == "graphs") { ctx->optGraphs = value != 0.0; if (!ctx->optGraphs) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->clear_graphs(); } }
     else if (n == "plan_cache_max") ctx->optPlanCacheMax = std::max(1, (int)value);
     else if (n == "plan_cache_mb") ctx->optPlanCacheMB = std::max(1.0, value);
-    else if (n == "ktab_model_mb") ctx->optKtabModelMB = value;
-    else if (n == "ktab_total_mb") ctx->optKtabTotalMB = value;
+    else if (n == "ktab_model_mb") { ctx->optKtabModelMB = value; ctx->chunkHint = 256; }
+    else if (n == "ktab_total_mb") { ctx->optKtabTotalMB = value; ctx->chunkHint = 256; }
     else { ctx->err = "rc_set_option: unknown option " + n; return RC_ERR_ARG; }
     return RC_OK;
 }

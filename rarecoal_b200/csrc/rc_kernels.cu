@@ -464,6 +464,14 @@ size_t rc_fast_smem_bytes(int block) {
     return (n + 15) & ~(size_t)15;
 }
 
+// Shared-window address of the dynamic shared memory, made opaque to the compiler: left as a plain cvta it is "cheap to
+// rematerialise", and ptxas then re-derives it (S2R SR_CgaCtaId + MOV + LEA) inside the grid-step loops instead of keeping
+// it in a register (profiles/r01_pat_kernel_loop.sass.txt).
+__device__ __forceinline__ unsigned rc_smem_base(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
 __device__ __forceinline__ double rc_lds64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -637,7 +645,7 @@ rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, co
     typedef RcFastSmem<BLOCK> SM;
     typedef RcFastK<BLOCK> K;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
-    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned sBase = rc_smem_base(smemRaw);
     const int pat0 = pl.fBinPatOff[bin];
     const int np = pl.fBinPatOff[bin + 1] - pat0;
     const int rowsAvail = models[b].rowsAvail, nSteps = models[b].nSteps, sShort = models[b].sShort;
@@ -1118,7 +1126,7 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
-    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned sBase = rc_smem_base(smemRaw);
     const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / lane records -> transition entries
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
@@ -1464,7 +1472,7 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
     SM& S = *reinterpret_cast<SM*>(smemRaw);
-    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned sBase = rc_smem_base(smemRaw);
     const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / row / element records -> transition entries
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
@@ -1887,7 +1895,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (models[b].nSteps < 0 || models[b].mode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
     double* bb = reinterpret_cast<double*>(smemRaw);
-    const unsigned sBase = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned sBase = rc_smem_base(smemRaw);
     const unsigned reSlot = (unsigned)ringRows * 16u;
     const int binIdx = binBase + (int)blockIdx.x;
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];

@@ -1,37 +1,33 @@
-"""Times rc_eval (host buffers in, host logl out) on the small configurations, keyed vs self-contained kernels."""
-import json, os, sys, time
+"""Single-model latency and small-batch cost through the host-buffer call, with and without launch graphs.
+    python tools/latency_probe.py [c3|c2|c5|c1 ...]"""
+import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rarecoal_b200 as R
 from rarecoal_b200 import workloads as Wk
 
-f = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "fourpop.json")))
-T = R.defaultTimes()
-
-def spec(P, ev):
-    return R.ModelSpec(P, T, 0.0005, [1.0] * P, 0.0, False, [R.ModelEvent.from_tuple(e) for e in ev])
-
-cases = []
-for maxaf in (4, 10):
-    std = R.computeStandardOrder(f["nVec"], maxaf)
-    cases.append((f"fourPop m={maxaf}", f["nVec"], maxaf, std, spec(4, f["events"])))
-nv = [100] * 10
-cases.append(("C5 10-pop m=4", nv, 4, R.computeStandardOrder(nv, 4), spec(10, Wk.c5_events())))
-nvec, pats, _ = Wk.c3_problem(max_af=6)
-cases.append(("8-pop tree m=6", nvec, 6, pats, spec(8, Wk.c3_events())))
-for name, nvec, maxaf, pats, sp in cases:
-    for keyed in (1, 0):
+for key in (sys.argv[1:] or ["c3", "c2", "c5", "c1"]):
+    wl = Wk.get(key)
+    nvec, pats, cnt = wl.problem()
+    for graphs in (0, 1):
         eng = R.Engine(0)
-        eng.set_option("keyed", keyed)
-        eng.set_problem(nvec, maxaf, pats, np.ones(len(pats), dtype=np.int64), 10 ** 9)
-        for B in (1, 32):
-            specs = [sp] * B
-            eng.eval_models(specs)
+        eng.set_option("graphs", graphs)
+        eng.set_problem(nvec, wl.max_af, pats, cnt, wl.total_sites)
+        eng.set_times(R.defaultTimes())
+        for B in (1, 4, 16, 64):
+            batches = wl.proposal_batches(30, B, seed=5)
+            packed = []
+            for evs in batches:
+                flat = [e for m in evs for e in m]
+                off = np.cumsum([0] + [len(m) for m in evs]).astype(np.int32)
+                packed.append((R.api._events_array(flat), off, np.full(B, wl.theta), np.ones(B * wl.P)))
+            for i in range(5):
+                eng.eval_raw(*packed[i], False, 1.0)
             t0 = time.perf_counter()
-            n = 20
-            for _ in range(n):
-                eng.eval_models(specs)
-            dt = (time.perf_counter() - t0) / n
+            for i in range(5, 30):
+                eng.eval_raw(*packed[i], False, 1.0)
+            ms = (time.perf_counter() - t0) * 1e3 / 25
             st = eng.stats()
-            print(f"{name:16s} patterns {len(pats):6d} keyed={keyed} B={B:3d}: {dt*1e3:8.3f} ms/call  launches {st['launches']:3d} kernel {st['kernel_ms']:.3f} ms")
+            print(f"{key} graphs={graphs} B={B:3d}: {ms:7.3f} ms/call  host {st['host_ms']:.3f} gpu {st['total_ms']:.3f} kernel {st['kernel_ms']:.3f} "
+                  f"traj {st['traj_ms']:.3f} launches {st['launches']} replay {st['graph_replay']}", flush=True)
         eng.close()
