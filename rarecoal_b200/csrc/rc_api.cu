@@ -443,7 +443,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     std::memset(&d, 0, sizeof d);
     const rc::PlanHost& h = pe->h;
     d.P = h.P; d.maxAf = h.maxAf; d.A1 = h.maxAf + 1; d.nPat = h.nPat; d.nEpochs = h.nEpochs; d.nnzw = h.nnzw;
-    d.nBins = h.nBins; d.cap = h.cap; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
+    d.nBins = h.nBins; d.nBinsKB = h.nBinsKB; d.cap = h.cap; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
     int rc;
     if ((rc = upload(ctx, pe, h.fBinPatOff, &d.fBinPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
@@ -959,7 +959,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     CK(rc_launch_propagate_fast(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
                     ++launches;
                 }
-                if (pe->d.nBins > 0) {
+                if (pe->d.nBins > 0 && (anySelf || pe->d.nBins > pe->d.nBinsKB)) {
                     CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
                     ++launches;
                 }

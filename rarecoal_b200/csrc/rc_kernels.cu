@@ -216,6 +216,7 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
     const int bin = blockIdx.x, b = blockIdx.y;
     const RcModelDev& M = models[b];
     if (M.nSteps < 0) return;   // model failed validation on the host
+    if (M.mode == 1 && bin < pl.nBinsKB) return;   // these patterns run in row mode on the trajectory-key tier for this model
     const int P = pl.P, A1 = pl.A1, nnzw = pl.nnzw, nPat = pl.nPat, cap = pl.cap;
     const int rowLen = rc_row_len(P, A1);
     RcSmem S = rc_carve(smemRaw, pl.cap, nnzw, P, rowLen);
@@ -1548,6 +1549,9 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
             for (int u = 0; u < GU; ++u)
                 if (i + u * RC_BLOCK < nB) S.bbuf[i + u * RC_BLOCK] = v[u];
         }
+        // the other parity starts as zeros: a row may be longer than its neighbour row (the staircase a Split leaves), and
+        // the elements the neighbour does not own — states that are not live — must read as b = 0 in both parities
+        for (int i = tid; i < nB; i += RC_BLOCK) S.bbuf[SM::BPAR + i] = 0.0;
     }
     __syncthreads();
     const uint16_t* myRefs = pl.rowRefAll;
@@ -1669,7 +1673,10 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
         int ok = 1;
         if (tid < np) {
             if (pl.shortcutOK[S.patId[tid]]) {
-                S.dpat[tid] = S.dpat[tid] + S.dslot[S.patRowOff[tid]];
+                // single-branch states only: one row per live branch (several after a Split)
+                double acc = S.dpat[tid];
+                for (int r = S.patRowOff[tid]; r < S.patRowOff[tid + 1]; ++r) acc = acc + S.dslot[r];
+                S.dpat[tid] = acc;
                 S.patDone[tid] = 2;
             } else ok = 0;
         }

@@ -168,7 +168,8 @@ struct PatPlan {
     std::vector<int> rowStride, rowCnt;              // reference-order stride of the row branch / number of rows
     std::vector<uint32_t> rowWords;                  // per row RC_ROW_NO words (k | x<<8 | neighbour row<<16)
     std::vector<uint16_t> rowRef;                    // per row: reference-order index of its x_r = 1 state
-    std::vector<uint16_t> rowRefs;                   // per row RC_ROW_MAXM reference-order indices (x_r = 1 .. M)
+    std::vector<uint16_t> rowRefs;                   // per row RC_ROW_MAXM reference-order indices (x_r = 1 .. M; 0xFFFF beyond the row)
+    std::vector<uint8_t> rowBr;                      // per row: its row branch (the widest branch of the row's part)
     bool shortcutOK = false;
     int maxLive = 0;
     int maxNnz = 0;
@@ -247,26 +248,53 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     for (int k = 0; k < c.P; ++k) r += pp.mx[m0 + (size_t)k];
     pp.maxR = std::max(pp.maxR, r);
     // ---- row view ----
-    long long box = 1;
-    int rk = -1, rm = 0, nz = 0;
-    for (int k = 0; k < c.P; ++k) {
-        int mk = pp.mx[m0 + (size_t)k];
-        if (!mk) continue;
-        ++nz;
-        box *= mk;
-        if (mk > rm) { rm = mk; rk = k; }
+    // updateB couples a state only to x + e_k for its NON-ZERO components (Core.hs:272-280: a zero component contributes
+    // nothing to t1 or t2), so the live set falls apart into independent parts by SUPPORT (the set of non-zero branches).
+    // fillUp makes every part down-closed (with x every y <= x of the same support): a box for a tree model, a union of
+    // boxes — a staircase — after a Split (Core.hs:220-221).  Every part is cut into rows along its own widest branch, x_r =
+    // 1 .. the row's own length; a neighbouring row may be shorter, the states it lacks are not live, i.e. b = 0.
+    // One thread of the row kernel owns a row.
+    std::map<uint32_t, std::vector<int>> parts;          // support mask -> states (reference order)
+    for (size_t i = 0; i < L.size(); ++i) {
+        uint32_t m = 0;
+        for (int k = 0; k < c.P; ++k) if (L[i].x[k]) m |= 1u << k;
+        parts[m].push_back((int)i);
     }
-    bool ok = box == (long long)L.size() && nz >= 1 && nz - 1 <= RC_ROW_NO && rm <= RC_ROW_MAXM &&
-              (nz - 1 <= 3 || nz - 1 + rm <= RC_ROW_SUM);
-    int stride = 1;
-    for (int k = rk + 1; k < c.P && ok; ++k) if (pp.mx[m0 + (size_t)k]) stride *= pp.mx[m0 + (size_t)k];
-    size_t rowStart = pp.rowRef.size();
-    if (ok) {
-        std::unordered_map<int, int> rowOfRef;
-        for (size_t i = 0; i < L.size(); ++i)
-            if (L[i].x[rk] == 1) { rowOfRef.emplace((int)i, (int)(pp.rowRef.size() - rowStart)); pp.rowRef.push_back((uint16_t)i); }
+    bool ok = !L.empty();
+    int maxM = 0, maxNO = 0, firstRk = 0, nz = 0;
+    long long box = 1;
+    for (int k = 0; k < c.P; ++k) { int mk = pp.mx[m0 + (size_t)k]; if (mk) { ++nz; box *= mk; } }
+    const size_t rowStart = pp.rowRef.size();
+    std::vector<uint16_t> refsAll;
+    std::vector<uint8_t> brAll;
+    {
+        std::unordered_map<int, int> rowOfRef;           // reference index of a row's first state -> row (inside the pattern)
+        struct Part { uint32_t mask; int rk, rm; };
+        std::vector<Part> plist;
+        // rows of all parts first (neighbour rows are looked up across the whole pattern's row list)
+        for (auto& kv : parts) {
+            if (!ok) break;
+            int ext[RC_MAX_P] = {0}, rk = -1, rm = 0, no = -1;
+            long long cnt = 1;
+            for (int st : kv.second) for (int k = 0; k < c.P; ++k) ext[k] = std::max(ext[k], (int)L[(size_t)st].x[k]);
+            for (int k = 0; k < c.P; ++k) if (ext[k]) { ++no; cnt *= ext[k]; if (ext[k] > rm) { rm = ext[k]; rk = k; } }
+            (void)cnt;
+            ok = no <= RC_ROW_NO && rm <= RC_ROW_MAXM && (no <= 3 || no + rm <= RC_ROW_SUM);
+            if (!ok) break;
+            plist.push_back({kv.first, rk, rm});
+            if (plist.size() == 1) firstRk = rk;
+            maxM = std::max(maxM, rm);
+            maxNO = std::max(maxNO, no);
+            for (int st : kv.second)
+                if (L[(size_t)st].x[rk] == 1) {
+                    rowOfRef.emplace(st, (int)(pp.rowRef.size() - rowStart));
+                    pp.rowRef.push_back((uint16_t)st);
+                    brAll.push_back((uint8_t)rk);
+                }
+        }
         for (size_t q = rowStart; q < pp.rowRef.size() && ok; ++q) {
             St s = L[pp.rowRef[q]];
+            const int rk = brAll[q - rowStart];
             int no = 0;
             uint32_t w[RC_ROW_NO];
             for (int d = 0; d < RC_ROW_NO; ++d) w[d] = 0xFFFF0000u;     // k = 0, x = 0: unused entry
@@ -286,36 +314,47 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
             }
             for (int d = 0; d < RC_ROW_NO; ++d) pp.rowWords.push_back(w[d]);
         }
-        // every row must be complete (x_r = 1..rm live); the reference-order index of each of its states is kept, since
-        // after a Join the live list is no longer in mixed-radix order (fillUp over several seeds, Core.hs:188)
+        // every row must be complete (x_r = 1 .. the extent of its part); the reference-order index of each of its states is
+        // kept, since after a Join the live list is no longer in mixed-radix order (fillUp over several seeds, Core.hs:188)
         const size_t nRows = pp.rowRef.size() - rowStart;
-        std::vector<uint16_t> refs(nRows * RC_ROW_MAXM, 0xFFFF);
+        refsAll.assign(nRows * RC_ROW_MAXM, 0xFFFF);
+        size_t covered = 0;
         for (size_t q = 0; q < nRows && ok; ++q) {
             St s = L[pp.rowRef[rowStart + q]];
-            for (int j = 0; j < rm && ok; ++j) {
+            const int rk = brAll[q];
+            uint32_t m = 0;
+            for (int k = 0; k < c.P; ++k) if (s.x[k]) m |= 1u << k;
+            int rm = 0;
+            for (const Part& pt : plist) if (pt.mask == m) rm = pt.rm;
+            for (int j = 0; j < rm; ++j) {                     // the row ends at its first state that is not live
                 s.x[rk] = (uint8_t)(j + 1);
                 auto it = idx.find(c.key(s));
-                ok = it != idx.end();
-                if (ok) refs[q * RC_ROW_MAXM + (size_t)j] = (uint16_t)it->second;
+                if (it == idx.end()) break;
+                refsAll[q * RC_ROW_MAXM + (size_t)j] = (uint16_t)it->second;
+                ++covered;
             }
         }
-        if (ok) pp.rowRefs.insert(pp.rowRefs.end(), refs.begin(), refs.end());
+        ok = ok && covered == L.size();
     }
-    if (!ok) {
+    if (ok) {
+        pp.rowRefs.insert(pp.rowRefs.end(), refsAll.begin(), refsAll.end());
+        pp.rowBr.insert(pp.rowBr.end(), brAll.begin(), brAll.end());
+    } else {
         pp.rowRef.resize(rowStart);
         pp.rowWords.resize(rowStart * RC_ROW_NO);
     }
-    bool full = box == (long long)L.size();
-    for (size_t i = 0; i < L.size() && full; ++i)
-        for (int k = 0; k < c.P && full; ++k)
-            if (pp.mx[m0 + (size_t)k] && !L[i].x[k]) full = false;
+    // a single part whose support is every live branch: the box of pattern mode
+    bool full = ok && parts.size() == 1 && box == (long long)L.size();
+    int stride = 1;
+    for (int k = firstRk + 1; k < c.P && full; ++k) if (pp.mx[m0 + (size_t)k]) stride *= pp.mx[m0 + (size_t)k];
     pp.fullBox.push_back(full ? 1 : 0);
     pp.rowOK.push_back(ok ? 1 : 0);
-    pp.rowM.push_back((uint8_t)(ok ? rm : 0));
-    pp.rowK.push_back((uint8_t)(ok ? rk : 0));
-    pp.rowNO.push_back((uint8_t)(ok ? nz - 1 : 0));
-    pp.rowStride.push_back(ok ? stride : 0);
+    pp.rowM.push_back((uint8_t)(ok ? maxM : 0));
+    pp.rowK.push_back((uint8_t)(ok ? firstRk : 0));
+    pp.rowNO.push_back((uint8_t)(ok ? maxNO : 0));
+    pp.rowStride.push_back(full ? stride : 0);
     pp.rowCnt.push_back(ok ? (int)(pp.rowRef.size() - rowStart) : 0);
+    (void)nz;
 }
 
 void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std::vector<StructEv>& sev,
@@ -608,11 +647,17 @@ static std::string build_bin_images(PlanHost& out) {
                     }
                     lanes += live;
                 } else {
+                    // rows of one pattern share the stride of its longest row; length, row branch and other branches are per row
+                    // (the parts of a live set left by a Split differ in all three)
                     const uint32_t pr = out.patRow[(size_t)e * nPat + i];
-                    const int M = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
-                    const int Mp = M | 1, nr = ro[i + 1] - ro[i];
+                    const int Mmax = (int)(pr & 0xFFu);
+                    const int Mp = Mmax | 1, nr = ro[i + 1] - ro[i];
                     for (int r = 0; r < nr; ++r) {
                         const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
+                        const int rk = out.rowBrAll[(size_t)grow];
+                        int M = 0, NO = 0;
+                        while (M < RC_ROW_MAXM && out.rowRefAll[(size_t)grow * RC_ROW_MAXM + M] != 0xFFFF) ++M;
+                        while (NO < RC_ROW_NO && ((out.rowWordsAll[(size_t)grow * RC_ROW_NO + NO] >> 8) & 0xFFu) != 0) ++NO;
                         uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                         uint32_t off[RC_ROW_NO + 1];
                         off[0] = (uint32_t)(bOff + r * Mp);
@@ -706,7 +751,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     // Two tiers.  Fast tier (rc_propagate_fast_kernel): one live state per thread, <= RC_BLOCK states per
     // pattern, <= 8 non-zero components per state.  Big tier (rc_propagate_kernel): several states per thread,
     // block capacity = the largest pattern rounded up to the block size, bounded by shared memory.
-    std::vector<int> fastIds, bigIds;
+    // A pattern too large for one state per thread can still run on the trajectory-key tier if in EVERY epoch its live set
+    // cuts into rows that fit one row-mode bin (`keyedBig`; live sets of several hundred states after admixture pulses).
+    std::vector<int> fastIds, bigIds, keyedBig;
+    std::vector<char> isKeyedBig((size_t)nPat, 0);
     int maxLiveBig = 0, maxLiveFast = 1;
     const bool fastOK = nnzw <= 8 && rc_row_len(P, maxAf + 1) <= RC_ROWCAP;
     for (int i = 0; i < nPat; ++i) {
@@ -714,7 +762,18 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         if (fastOK && pp.maxLive <= RC_BLOCK && pp.maxR <= 2 * RC_BLOCK - 2) {
             fastIds.push_back(i);
             maxLiveFast = std::max(maxLiveFast, pp.maxLive);
-        } else { bigIds.push_back(i); maxLiveBig = std::max(maxLiveBig, pp.maxLive); }
+        } else {
+            bigIds.push_back(i);
+            maxLiveBig = std::max(maxLiveBig, pp.maxLive);
+            bool rowsFit = fastOK && patternMode >= 0;
+            for (int e = 0; e < nEpochs && rowsFit; ++e) {
+                int rr = 0;
+                for (int k = 0; k < P; ++k) rr += pp.mx[(size_t)e * P + k];
+                rowsFit = pp.rowOK[(size_t)e] && pp.rowCnt[(size_t)e] <= RC_BLOCK &&
+                          pp.rowCnt[(size_t)e] * (pp.rowM[(size_t)e] | 1) <= RC_ROW_BCAP && rr <= RC_KROWS - 2;
+            }
+            if (rowsFit) { keyedBig.push_back(i); isKeyedBig[(size_t)i] = 1; }
+        }
     }
     // smallest block that holds the largest fast-tier pattern: fewer warps per barrier, finer packing
     (void)maxLiveFast;
@@ -849,6 +908,15 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     {
         std::vector<int> order(fastIds);
         std::sort(order.begin(), order.end(), [&](int a, int b) {
+            const int32_t* x = patterns + (size_t)a * P;
+            const int32_t* y = patterns + (size_t)b * P;
+            for (int k = 0; k < P; ++k) if (x[k] != y[k]) return x[k] < y[k];
+            return a < b;
+        });
+        // per-epoch (keyed) bins also hold the big patterns that run in row mode
+        std::vector<int> orderK(order);
+        orderK.insert(orderK.end(), keyedBig.begin(), keyedBig.end());
+        std::sort(orderK.begin(), orderK.end(), [&](int a, int b) {
             const int32_t* x = patterns + (size_t)a * P;
             const int32_t* y = patterns + (size_t)b * P;
             for (int k = 0; k < P; ++k) if (x[k] != y[k]) return x[k] < y[k];
@@ -1059,35 +1127,40 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         const bool patEnv = patternMode != 0 && (std::getenv("RC_PATMODE") ? std::atoi(std::getenv("RC_PATMODE")) != 0 : true);
         static const bool patLEnv = std::getenv("RC_PATLARGE") ? std::atoi(std::getenv("RC_PATLARGE")) != 0 : true;
         std::vector<std::vector<int>> groupIds((size_t)nEpochs * RC_NGROUP);
+        static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.0;
         for (int e = 0; e < nEpochs; ++e) {
-            std::vector<int>& restIds = groupIds[(size_t)e * RC_NGROUP + RC_NGROUP - 1];
-            bool anyPat = false;
-            for (int i : order) {
+            bool anyPat = false, use = false;
+            int maxNO = 0;
+            for (int i : orderK) {
                 const PatPlan& pp = pps[(size_t)i];
                 const bool box = patEnv && pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
-                int g = RC_NGROUP - 1;
+                int g = RC_NGROUP - 1;                               // one state per thread
                 if (box)
-                    for (int q = 0; q < RC_NGROUP - 1; ++q) {
+                    for (int q = 0; q < RC_NPATG; ++q) {
                         if (q > 0 && !patLEnv && rc_pat_cap(RC_MODE_PAT + q) > RC_PAT_MAXS) break;
                         if (pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], rc_pat_cap(RC_MODE_PAT + q)) != 0) { g = q; break; }
                     }
+                if (g == RC_NGROUP - 1) {
+                    // row mode: a big pattern always (that is why it is here); a small one when its rows are long enough to pay
+                    // for themselves and it fits one row bin
+                    int rr = 0;
+                    for (int k = 0; k < P; ++k) rr += pp.mx[(size_t)e * P + k];
+                    const bool fits = pp.rowOK[(size_t)e] && pp.rowCnt[(size_t)e] > 0 && pp.rowCnt[(size_t)e] <= fastBlock &&
+                                      pp.rowCnt[(size_t)e] * (pp.rowM[(size_t)e] | 1) <= RC_ROW_BCAP && rr <= rowCap;
+                    bool rowsWanted = fits && (double)pp.live[(size_t)e] / (double)pp.rowCnt[(size_t)e] >= minLen;
+                    if (rowEnv) rowsWanted = fits && std::atoi(rowEnv) != 0;
+                    if (isKeyedBig[(size_t)i] || rowsWanted) {
+                        g = RC_NPATG;
+                        use = true;
+                        maxNO = std::max(maxNO, (int)pp.rowNO[(size_t)e]);
+                    }
+                }
                 groupIds[(size_t)e * RC_NGROUP + g].push_back(i);
-                anyPat = anyPat || g < RC_NGROUP - 1;
+                anyPat = anyPat || g < RC_NPATG;
             }
-            bool all = !restIds.empty();
-            long long rows = 0, states = 0;
-            int maxNO = 0;
-            for (int i : restIds) {
-                all = all && pps[(size_t)i].rowOK[(size_t)e];
-                rows += pps[(size_t)i].rowCnt[(size_t)e];
-                states += pps[(size_t)i].live[(size_t)e];
-                maxNO = std::max(maxNO, (int)pps[(size_t)i].rowNO[(size_t)e]);
-            }
-            static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.5;
-            bool use = all && rows > 0 && (double)states / (double)rows >= minLen;
-            if (rowEnv) use = all && std::atoi(rowEnv) != 0;
-            for (int q = 0; q < RC_NGROUP - 1; ++q) out.epochMode[(size_t)e * RC_NGROUP + q] = RC_MODE_PAT + q;
-            out.epochMode[(size_t)e * RC_NGROUP + RC_NGROUP - 1] = use ? (maxNO <= 3 ? 1 : 2) : 0;     // 1 / 2: row kernel for <= 3 / <= RC_ROW_NO other branches
+            for (int q = 0; q < RC_NPATG; ++q) out.epochMode[(size_t)e * RC_NGROUP + q] = RC_MODE_PAT + q;
+            out.epochMode[(size_t)e * RC_NGROUP + RC_NPATG] = maxNO <= 3 ? 1 : 2;     // row kernel for <= 3 / <= RC_ROW_NO other branches
+            out.epochMode[(size_t)e * RC_NGROUP + RC_NGROUP - 1] = 0;
             out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
             if (use || anyPat) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
@@ -1101,6 +1174,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     for (int q = 0; q < n; ++q) {
                         for (int j = 0; j < RC_ROW_MAXM; ++j) out.rowRefAll.push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
                         for (int d = 0; d < RC_ROW_NO; ++d) out.rowWordsAll.push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
+                        out.rowBrAll.push_back(pp.rowBr[r0 + (size_t)q]);
                     }
                     run += n;
                     out.patRow[(size_t)e * nPat + i] = (uint32_t)pp.rowM[(size_t)e] | ((uint32_t)pp.rowK[(size_t)e] << 8) |
@@ -1137,8 +1211,14 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     if (direct) n = 2LL * M[0] - 1 + 1;
                 } else if (mode) {
                     // rc_row_run: per row NO DMUL (D), per state DMUL (D * G_r), DMUL (row neighbour), NO DFMA, DFMA
-                    const long long rows = pp.rowCnt[(size_t)e], Mr = pp.rowM[(size_t)e], NO = pp.rowNO[(size_t)e];
-                    n = rows * (NO + Mr * (NO + 2) + (Mr - 1) + (NO == 0 ? 1 : 0));
+                    size_t r0 = 0;
+                    for (int q = 0; q < e; ++q) r0 += (size_t)pp.rowCnt[(size_t)q];
+                    for (int r = 0; r < pp.rowCnt[(size_t)e]; ++r) {
+                        long long Mr = 0, NO = 0;
+                        while (Mr < RC_ROW_MAXM && pp.rowRefs[(r0 + (size_t)r) * RC_ROW_MAXM + (size_t)Mr] != 0xFFFF) ++Mr;
+                        while (NO < RC_ROW_NO && ((pp.rowWords[(r0 + (size_t)r) * RC_ROW_NO + (size_t)NO] >> 8) & 0xFFu) != 0) ++NO;
+                        n += NO + Mr * (NO + 2) + (Mr - 1) + (NO == 0 ? 1 : 0);
+                    }
                 } else {
                     // rc_key_step: per state and non-zero branch one DMUL into the decay factor (the first is a move) and one
                     // DMUL / DFMA of the neighbour, then the combining DFMA
@@ -1193,7 +1273,20 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
         }
     }
-    out.nBins = pack(bigIds, cap, RC_NPB, 1 << 30, out.binPatOff, out.binPats);
+    {
+        // big-tier bins (self-contained general kernel): first those of the patterns that the trajectory-key tier runs in row
+        // mode — a model on that tier skips them (rc_propagate_kernel) —, then the patterns only this tier can run
+        std::vector<int> rest, off2, pats2;
+        for (int i : bigIds) if (!isKeyedBig[(size_t)i]) rest.push_back(i);
+        out.nBinsKB = keyedBig.empty() ? 0 : pack(keyedBig, cap, RC_NPB, 1 << 30, out.binPatOff, out.binPats);
+        if (keyedBig.empty()) { out.binPatOff.assign(1, 0); out.binPats.clear(); }
+        const int nRest = rest.empty() ? 0 : pack(rest, cap, RC_NPB, 1 << 30, off2, pats2);
+        for (int b = 0; b < nRest; ++b) {
+            for (int q = off2[(size_t)b]; q < off2[(size_t)b + 1]; ++q) out.binPats.push_back(pats2[(size_t)q]);
+            out.binPatOff.push_back((int)out.binPats.size());
+        }
+        out.nBins = out.nBinsKB + nRest;
+    }
     out.maxX.assign((size_t)nEpochs * nPat * P, 0);
     for (int e = 0; e < nEpochs; ++e)
         for (int i = 0; i < nPat; ++i)
@@ -1349,19 +1442,26 @@ std::string check_plan(const PlanHost& h) {
                         const uint32_t pr = h.patRow[(size_t)e * nPat + i];
                         const int M = (int)(pr & 0xFFu), rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
                         const int nr = h.rowOff[(size_t)e * (nPat + 1) + i + 1] - h.rowOff[(size_t)e * (nPat + 1) + i];
-                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || rk >= P || nr * M != live) return fail("row shape");
+                        if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || rk >= P) return fail("row shape");
                         lanes += patM ? 1 : nr;
                         padded += patM ? 0 : (long long)nr * (M | 1);
+                        long long covered = 0;
                         for (int r = 0; r < nr; ++r) {
                             const long long gr = h.rowEpochBase[(size_t)e] + h.rowOff[(size_t)e * (nPat + 1) + i] + r;
-                            for (int j = 0; j < M; ++j)
+                            int Mr = 0, NOr = 0;         // length and other branches of this row (<= the pattern's maxima)
+                            while (Mr < RC_ROW_MAXM && h.rowRefAll[(size_t)gr * RC_ROW_MAXM + Mr] != 0xFFFF) ++Mr;
+                            while (NOr < RC_ROW_NO && ((h.rowWordsAll[(size_t)gr * RC_ROW_NO + NOr] >> 8) & 0xFFu) != 0) ++NOr;
+                            if (Mr < 1 || Mr > M || NOr > NO || (int)h.rowBrAll[(size_t)gr] >= P) return fail("row shape (row)");
+                            covered += Mr;
+                            for (int j = 0; j < Mr; ++j)
                                 if ((int)h.rowRefAll[(size_t)gr * RC_ROW_MAXM + j] >= live) return fail("row state index out of range");
-                            for (int d = 0; d < NO; ++d) {
+                            for (int d = 0; d < NOr; ++d) {
                                 const uint32_t w = h.rowWordsAll[(size_t)gr * RC_ROW_NO + d];
                                 const uint32_t up = w >> 16;
                                 if ((int)(w & 0xFFu) >= P || (up != RC_NO_UP && (int)up >= nr)) return fail("row word out of range");
                             }
                         }
+                        if (covered != live) return fail("rows do not cover the live set");
                     } else lanes += live;
                 }
                 if (lanes > RC_BLOCK) return fail("lanes per keyed bin");

@@ -24,7 +24,8 @@
 #endif
 #define RC_PAT_MAXS 25       //   registers of one thread) — the fewer states, the fewer registers and the more resident blocks
 #define RC_PAT_MAXL 36
-#define RC_NGROUP 4          // bin groups per epoch: tiny, small, large patterns (one thread each), the rest (rows or states)
+#define RC_NGROUP 5          // bin groups per epoch: tiny, small, large patterns (one thread each), rows (one thread per row), states
+#define RC_NPATG 3           // ... of which the first RC_NPATG are the pattern groups
 // epochMode of a pattern group = RC_MODE_PAT + index of its capacity in {RC_PAT_MAXT, RC_PAT_MAXS, RC_PAT_MAXL}
 #define RC_MODE_PAT 3
 static inline __host__ __device__ int rc_pat_cap(int mode) { return mode == RC_MODE_PAT ? RC_PAT_MAXT : mode == RC_MODE_PAT + 1 ? RC_PAT_MAXS : RC_PAT_MAXL; }
@@ -65,6 +66,7 @@ struct RcPlanDev {
     int nEpochs;                 // structural epochs = fired Join/Split events + 1
     int nnzw;                    // words per slot
     int nBins;
+    int nBinsKB;                 // the first nBinsKB big-tier bins hold patterns that models on the trajectory-key tier run in row mode
     int cap;                     // slots per block
     const int* binPatOff;        // [nBins+1]          big-tier bins (several states per thread)
     const int* binPats;          // shard-local pattern ids, bin after bin
