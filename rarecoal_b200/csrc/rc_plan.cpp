@@ -170,6 +170,8 @@ struct PatPlan {
     std::vector<uint16_t> rowRef;                    // per row: reference-order index of its x_r = 1 state
     std::vector<uint16_t> rowRefs;                   // per row RC_ROW_MAXM reference-order indices (x_r = 1 .. M; 0xFFFF beyond the row)
     std::vector<uint8_t> rowBr;                      // per row: its row branch (the widest branch of the row's part)
+    std::vector<uint8_t> rowPm;                      // per row: longest row of its part (rows of a part are stored with one stride)
+    std::vector<int> rowPad;                         // per epoch: sum over the rows of (rowPm | 1) — b doubles the pattern needs in a row bin
     bool shortcutOK = false;
     int maxLive = 0;
     int maxNnz = 0;
@@ -266,7 +268,8 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     for (int k = 0; k < c.P; ++k) { int mk = pp.mx[m0 + (size_t)k]; if (mk) { ++nz; box *= mk; } }
     const size_t rowStart = pp.rowRef.size();
     std::vector<uint16_t> refsAll;
-    std::vector<uint8_t> brAll;
+    std::vector<uint8_t> brAll, pmAll;
+    int padSum = 0;
     {
         std::unordered_map<int, int> rowOfRef;           // reference index of a row's first state -> row (inside the pattern)
         struct Part { uint32_t mask; int rk, rm; };
@@ -290,6 +293,8 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
                     rowOfRef.emplace(st, (int)(pp.rowRef.size() - rowStart));
                     pp.rowRef.push_back((uint16_t)st);
                     brAll.push_back((uint8_t)rk);
+                    pmAll.push_back((uint8_t)rm);
+                    padSum += rm | 1;
                 }
         }
         for (size_t q = rowStart; q < pp.rowRef.size() && ok; ++q) {
@@ -339,6 +344,7 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     if (ok) {
         pp.rowRefs.insert(pp.rowRefs.end(), refsAll.begin(), refsAll.end());
         pp.rowBr.insert(pp.rowBr.end(), brAll.begin(), brAll.end());
+        pp.rowPm.insert(pp.rowPm.end(), pmAll.begin(), pmAll.end());
     } else {
         pp.rowRef.resize(rowStart);
         pp.rowWords.resize(rowStart * RC_ROW_NO);
@@ -354,6 +360,7 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     pp.rowNO.push_back((uint8_t)(ok ? maxNO : 0));
     pp.rowStride.push_back(full ? stride : 0);
     pp.rowCnt.push_back(ok ? (int)(pp.rowRef.size() - rowStart) : 0);
+    pp.rowPad.push_back(ok ? padSum : 0);
     (void)nz;
 }
 
@@ -649,18 +656,22 @@ static std::string build_bin_images(PlanHost& out) {
                 } else {
                     // rows of one pattern share the stride of its longest row; length, row branch and other branches are per row
                     // (the parts of a live set left by a Split differ in all three)
-                    const uint32_t pr = out.patRow[(size_t)e * nPat + i];
-                    const int Mmax = (int)(pr & 0xFFu);
-                    const int Mp = Mmax | 1, nr = ro[i + 1] - ro[i];
+                    const int nr = ro[i + 1] - ro[i];
+                    // rows of one part share a stride (its longest row, made odd): a row reads its neighbour rows — always
+                    // of its own part — at its own element index, and finds zeros where the neighbour is shorter
+                    std::vector<int> rOff((size_t)nr + 1, 0);
+                    for (int r = 0; r < nr; ++r)
+                        rOff[(size_t)r + 1] = rOff[(size_t)r] + (out.rowPmAll[(size_t)(out.rowEpochBase[(size_t)e] + ro[i] + r)] | 1);
                     for (int r = 0; r < nr; ++r) {
                         const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
                         const int rk = out.rowBrAll[(size_t)grow];
+                        const int Mp = out.rowPmAll[(size_t)grow] | 1;
                         int M = 0, NO = 0;
                         while (M < RC_ROW_MAXM && out.rowRefAll[(size_t)grow * RC_ROW_MAXM + M] != 0xFFFF) ++M;
                         while (NO < RC_ROW_NO && ((out.rowWordsAll[(size_t)grow * RC_ROW_NO + NO] >> 8) & 0xFFu) != 0) ++NO;
                         uint32_t rec[RC_RLANE_N] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                         uint32_t off[RC_ROW_NO + 1];
-                        off[0] = (uint32_t)(bOff + r * Mp);
+                        off[0] = (uint32_t)(bOff + rOff[(size_t)r]);
                         static_assert(RC_ROW_NO == 7, "row lane record packs seven other branches");
                         for (int d = 0; d < RC_ROW_NO; ++d) {
                             uint32_t row = RC_KROWS - 1;
@@ -669,7 +680,7 @@ static std::string build_bin_images(PlanHost& out) {
                                 const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
                                 const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
                                 row = (uint32_t)((int)rb[k] + x - 1);
-                                if ((w >> 16) != RC_NO_UP) off[d + 1] = (uint32_t)(bOff + (int)(w >> 16) * Mp);
+                                if ((w >> 16) != RC_NO_UP) off[d + 1] = (uint32_t)(bOff + rOff[(size_t)(w >> 16)]);
                             }
                             if (row > 0xFFu || off[d + 1] > RC_ROW_BCAP) return "row bin image out of range";
                             rec[d >> 2] |= row << (8 * (d & 3));
@@ -694,7 +705,7 @@ static std::string build_bin_images(PlanHost& out) {
                         }
                     }
                     lanes += nr;
-                    bOff += nr * Mp;
+                    bOff += rOff[(size_t)nr];
                 }
             }
             hdr[2] = lanes;
@@ -769,8 +780,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             for (int e = 0; e < nEpochs && rowsFit; ++e) {
                 int rr = 0;
                 for (int k = 0; k < P; ++k) rr += pp.mx[(size_t)e * P + k];
-                rowsFit = pp.rowOK[(size_t)e] && pp.rowCnt[(size_t)e] <= RC_BLOCK &&
-                          pp.rowCnt[(size_t)e] * (pp.rowM[(size_t)e] | 1) <= RC_ROW_BCAP && rr <= RC_KROWS - 2;
+                rowsFit = pp.rowOK[(size_t)e] && pp.rowCnt[(size_t)e] <= RC_BLOCK && pp.rowPad[(size_t)e] <= RC_ROW_BCAP && rr <= RC_KROWS - 2;
             }
             if (rowsFit) { keyedBig.push_back(i); isKeyedBig[(size_t)i] = 1; }
         }
@@ -981,7 +991,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     if (ob.slotsE[(size_t)q] + lanesOf(pp, e0 + q) > fastBlock) return false;
                 if (patMode && !ob.ids.empty() && ob.cls != clsOf(i)) return false;
                 // padded states of the rows (odd stride) must fit the block's b buffer
-                const int padAdd = (rowMode && !patMode) ? pp.rowCnt[(size_t)e0] * (pp.rowM[(size_t)e0] | 1) : 0;
+                const int padAdd = (rowMode && !patMode) ? pp.rowPad[(size_t)e0] : 0;
                 if (ob.rowStates + padAdd > RC_ROW_BCAP) return false;
                 std::vector<int> add((size_t)nE, 0), addSelf((size_t)nE, 0);
                 for (int q = 0; q < nE; ++q) {
@@ -1146,7 +1156,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     int rr = 0;
                     for (int k = 0; k < P; ++k) rr += pp.mx[(size_t)e * P + k];
                     const bool fits = pp.rowOK[(size_t)e] && pp.rowCnt[(size_t)e] > 0 && pp.rowCnt[(size_t)e] <= fastBlock &&
-                                      pp.rowCnt[(size_t)e] * (pp.rowM[(size_t)e] | 1) <= RC_ROW_BCAP && rr <= rowCap;
+                                      pp.rowPad[(size_t)e] <= RC_ROW_BCAP && rr <= rowCap;
                     bool rowsWanted = fits && (double)pp.live[(size_t)e] / (double)pp.rowCnt[(size_t)e] >= minLen;
                     if (rowEnv) rowsWanted = fits && std::atoi(rowEnv) != 0;
                     if (isKeyedBig[(size_t)i] || rowsWanted) {
@@ -1175,6 +1185,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         for (int j = 0; j < RC_ROW_MAXM; ++j) out.rowRefAll.push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
                         for (int d = 0; d < RC_ROW_NO; ++d) out.rowWordsAll.push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
                         out.rowBrAll.push_back(pp.rowBr[r0 + (size_t)q]);
+                        out.rowPmAll.push_back(pp.rowPm[r0 + (size_t)q]);
                     }
                     run += n;
                     out.patRow[(size_t)e * nPat + i] = (uint32_t)pp.rowM[(size_t)e] | ((uint32_t)pp.rowK[(size_t)e] << 8) |
@@ -1270,7 +1281,8 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                              E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns<12>" : m == 4 ? "patterns<25>" : m == 5 ? "patterns<36>" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
                              (double)(f1 - f0) / nb);
             }
-            std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d)\n", out.nFastBins, fastBlock);
+            std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d); big patterns %d, of which %d in row mode on the key tier\n",
+                         out.nFastBins, fastBlock, (int)bigIds.size(), (int)keyedBig.size());
         }
     }
     {
@@ -1444,7 +1456,8 @@ std::string check_plan(const PlanHost& h) {
                         const int nr = h.rowOff[(size_t)e * (nPat + 1) + i + 1] - h.rowOff[(size_t)e * (nPat + 1) + i];
                         if (M < 1 || M > RC_ROW_MAXM || NO > RC_ROW_NO || rk >= P) return fail("row shape");
                         lanes += patM ? 1 : nr;
-                        padded += patM ? 0 : (long long)nr * (M | 1);
+                        for (int r = 0; r < nr && !patM; ++r)
+                            padded += h.rowPmAll[(size_t)(h.rowEpochBase[(size_t)e] + h.rowOff[(size_t)e * (nPat + 1) + i] + r)] | 1;
                         long long covered = 0;
                         for (int r = 0; r < nr; ++r) {
                             const long long gr = h.rowEpochBase[(size_t)e] + h.rowOff[(size_t)e * (nPat + 1) + i] + r;

@@ -76,6 +76,7 @@ struct PlanHost {
     std::vector<long long> rowEpochBase;   // [nEpochs] first row of the epoch in rowRefAll / rowWordsAll
     std::vector<uint16_t> rowRefAll;       // per row RC_ROW_MAXM reference-order indices (inside the pattern) of x_r = 1..M
     std::vector<uint32_t> rowWordsAll;     // per row RC_ROW_NO words: k | x_k << 8 | neighbour row << 16
+    std::vector<uint8_t> rowPmAll;         // per row: longest row of its part (the stride its part's rows are stored with)
     std::vector<uint8_t> rowBrAll;         // per row: its row branch (host only; a live set left by a Split has parts with different ones)
     std::vector<uint32_t> patRow;          // [nEpochs][nPat] row length | row branch << 8 | other branches << 16
     std::vector<int> patRowStride;         // [nEpochs][nPat] reference-order stride of the row branch
