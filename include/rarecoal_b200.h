@@ -64,7 +64,8 @@ typedef struct {
 typedef struct {
     int64_t state_steps;     /* executed b(x) updates over all models (SURVEY.md §8d unit, Core.hs:248) */
     int64_t slots;           /* live states resident at t=0 over all models                            */
-    double kernel_ms;        /* CUDA-event span of the propagation launches on the eval stream           */
+    double kernel_ms;        /* CUDA-event span of the propagation launches on the eval stream (a call cut into chunks: of */
+                             /* its last chunk; likewise traj_ms and tables_ms)                                            */
     double traj_ms;          /* trajectory kernels (first plan group): elapsed on their side stream,     */
                              /* concurrent with the propagation launches                                 */
     double tables_ms;        /* CUDA-event time of the per-model table kernel                           */

@@ -196,6 +196,7 @@ struct rc_ctx {
     int chunkHint = 256;              // models per chunk; adapted to the trajectory-table size after every call
     bool statsPending = false;
     bool blobInFlight = false;
+    bool firstChunk = true;
     // launch graphs by launch signature ("graphs" option); dropped whenever a plan or a buffer they point to goes away
     int optGraphs = 1;
     std::map<std::string, cudaGraphExec_t> graphs;
@@ -850,7 +851,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     const double* dW = (const double*)(db + oW);
     const RcModelEpochDev* dMep = (const RcModelEpochDev*)(db + oMep);
 
-    CK(cudaEventRecord(ctx->evt[0], st));
+    if (ctx->firstChunk) CK(cudaEventRecord(ctx->evt[0], st));
     CK(cudaMemcpyAsync(db, hb, blobBytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->evt[5], st));
     ctx->blobInFlight = true;
@@ -1046,12 +1047,18 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
     if (ctx->times.empty()) { ctx->err = "rc_set_times has not been called"; return RC_ERR_ARG; }
     if (B <= 0) return RC_OK;
     const long long totalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
+    // A batch is cut into chunks when its trajectory tables would not fit ("ktab_total_mb").  Chunks are queued back to back on
+    // the stream; nothing waits for the device in between.  (Cutting host-heavy batches into chunks to overlap the host side
+    // of one with the kernels of the previous was measured and dropped: the small workloads it targets are latency-bound on
+    // the GPU, a chunk of 32 models takes about as long as one of 128 — C5 fell from 110k to 62k evaluations/s.)
     rc_stats acc;
     std::memset(&acc, 0, sizeof acc);
+    acc.plan_cache_hit = 1;
     int done = 0, nChunks = 0;
     while (done < B) {
         int n = std::min(B - done, std::max(1, std::min(ctx->chunkHint, 32768)));
         long long maxPairs = 0;
+        ctx->firstChunk = nChunks == 0;
         int rc = eval_chunk(ctx, n, ev, evOff + done, theta + done, disc + (size_t)done * ctx->P, noShortcut + done, dPartial + 2 * (size_t)done,
                             dProbs ? dProbs + (size_t)done * ctx->nPatGlobal : nullptr, st, outStatus ? outStatus + done : nullptr,
                             &maxPairs);
@@ -1061,20 +1068,18 @@ int eval_impl(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, cons
         else ctx->chunkHint = std::min(32768, std::max(ctx->chunkHint, 256));
         done += n;
         ++nChunks;
-        if (done < B || nChunks > 1) {      // several chunks: fold this chunk's counters into the running totals
-            rc = collect_stats(ctx);
-            if (rc != RC_OK) return rc;
-            acc.state_steps += ctx->stats.state_steps; acc.slots += ctx->stats.slots;
-            acc.kernel_ms += ctx->stats.kernel_ms; acc.traj_ms += ctx->stats.traj_ms; acc.tables_ms += ctx->stats.tables_ms;
-            acc.total_ms += ctx->stats.total_ms; acc.launches += ctx->stats.launches;
-            acc.host_ms += ctx->stats.host_ms; acc.ktab_mb += ctx->stats.ktab_mb; acc.chunks += 1; acc.models_selfcontained += ctx->stats.models_selfcontained;
-            acc.fp64_instr += ctx->stats.fp64_instr; acc.plan_misses += ctx->stats.plan_misses;
-            acc.plan_evictions += ctx->stats.plan_evictions; acc.plan_build_ms += ctx->stats.plan_build_ms;
-            acc.plan_cache_hit = nChunks == 1 ? ctx->stats.plan_cache_hit : (acc.plan_cache_hit && ctx->stats.plan_cache_hit);
-            acc.n_epochs = ctx->stats.n_epochs; acc.n_steps = ctx->stats.n_steps;
-            if (done == B) ctx->stats = acc;
-        }
+        // counters of the chunks add up; the CUDA-event spans are read once, at the end of the call: tables / propagation /
+        // trajectory spans are those of the LAST chunk, total_ms runs from the first chunk's upload to the last chunk's reduction
+        acc.state_steps += ctx->stats.state_steps; acc.slots += ctx->stats.slots; acc.launches += ctx->stats.launches;
+        acc.host_ms += ctx->stats.host_ms; acc.ktab_mb += ctx->stats.ktab_mb; acc.chunks += 1;
+        acc.models_selfcontained += ctx->stats.models_selfcontained;
+        acc.fp64_instr += ctx->stats.fp64_instr; acc.plan_misses += ctx->stats.plan_misses;
+        acc.plan_evictions += ctx->stats.plan_evictions; acc.plan_build_ms += ctx->stats.plan_build_ms;
+        acc.plan_cache_hit = acc.plan_cache_hit && ctx->stats.plan_cache_hit;
+        acc.n_epochs = ctx->stats.n_epochs; acc.n_steps = ctx->stats.n_steps; acc.graph_replay = ctx->stats.graph_replay;
     }
+    ctx->stats = acc;
+    ctx->statsPending = true;
     return RC_OK;
 }
 
