@@ -101,6 +101,9 @@ def minimize_batched(f, x0, max_cycles, par=1, tol=1.0e-8):
     S = np.vstack([x0] + [x0 + steps[j] * np.eye(n)[j] for j in range(n)])
     fv = f(S)                                                         # n+1 models, one launch
     par = max(1, min(par, n))
+    # dimension-dependent coefficients (Gao & Han 2012): with the classical 2 / 0.5 / 0.5 the simplex collapses long before
+    # the optimum in 15+ dimensions; the reference's GSL simplex has the same weakness and relies on its restarts
+    k_exp, k_con, k_shr = 1.0 + 2.0 / n, 0.75 - 0.5 / n, 1.0 - 1.0 / n
     trace = []
     for it in range(1, max_cycles + 1):
         order = np.argsort(fv, kind="stable")
@@ -112,7 +115,7 @@ def minimize_batched(f, x0, max_cycles, par=1, tol=1.0e-8):
         keep = n + 1 - par
         c = S[:keep].mean(axis=0)
         worst = S[keep:]
-        cand = np.vstack([c + (c - worst), c + 2.0 * (c - worst), c + 0.5 * (c - worst), c - 0.5 * (c - worst)])
+        cand = np.vstack([c + (c - worst), c + k_exp * (c - worst), c + k_con * (c - worst), c - k_con * (c - worst)])
         fc = f(cand).reshape(4, par)                                  # reflection, expansion, outside, inside
         shrink = False
         for i in range(par):
@@ -132,10 +135,120 @@ def minimize_batched(f, x0, max_cycles, par=1, tol=1.0e-8):
         if shrink:
             best = S[np.argmin(fv)].copy()
             idx = [j for j in range(n + 1) if not np.array_equal(S[j], best)]
-            S[idx] = best + 0.5 * (S[idx] - best)
+            S[idx] = best + k_shr * (S[idx] - best)
             fv[idx] = f(S[idx])                                       # all moved vertices, one launch
     j = int(np.argmin(fv))
     return S[j].copy(), trace
+
+
+def polish_batched(f, x, fx, max_iter=400, rel_tol=1.0e-7):
+    """Batched coordinate pattern search, run after the simplex: the likelihood is piecewise constant in every time
+    parameter (events fire on the grid, Core.hs:120-135), which stalls a collapsing simplex on a ridge.  Every iteration is
+    ONE launch: x +- delta_j e_j for every parameter (the central-difference batch of SURVEY.md 8d, C4) plus a few combinations
+    of the moves that improved in the previous iteration; the best point is taken, deltas halve when nothing improves."""
+    n = len(x)
+    delta = np.maximum(1.0e-4, np.abs(0.01 * x))
+    combos = []
+    trace = []
+    for it in range(max_iter):
+        if np.all(delta <= np.maximum(1.0e-12, rel_tol * np.abs(x))):
+            break
+        eye = np.eye(n) * delta
+        cand = np.vstack([x + eye, x - eye] + combos)
+        fc = f(cand)
+        gain_p, gain_m = fx - fc[:n], fx - fc[n:2 * n]
+        j = int(np.argmin(fc))
+        move = np.where(gain_p > np.maximum(gain_m, 0.0), delta, np.where(gain_m > 0.0, -delta, 0.0))
+        if fc[j] < fx:
+            x, fx = cand[j].copy(), float(fc[j])
+            # next launch also tries all improving moves at once, at three scales
+            combos = [x + sc * move for sc in (1.0, 0.5, 0.25)] if np.count_nonzero(move) > 1 else []
+            grow = np.zeros(n, dtype=bool)
+            if j < 2 * n:
+                grow[j % n] = True
+            delta = np.where(grow, delta * 1.5, delta)
+        else:
+            combos = []
+            delta = delta * 0.5
+        trace.append([float(it + 1), fx, float(np.max(delta / np.maximum(np.abs(x), 1e-300)))] + x.tolist())
+    return x, fx, trace
+
+
+def bfgs_batched(f, x, fx, max_iter=200, fd_rel=0.01):
+    """Quasi-Newton descent on batches: the central-difference gradient is ONE launch of 2n models (44
+    models for the 22 parameters of the 8-population template), the line search along the BFGS direction a second launch
+    of a dozen step lengths.  Works in relative coordinates z = x / scale; the finite-difference step (1 % by default, the
+    simplex's own start step, Maxl.hs:84) spans a few cells of the time grid, on which the likelihood is piecewise constant
+    in every event time (Core.hs:120-135).  Follows the narrow diagonal valleys (size / time trade-offs) in which both the
+    simplex and a coordinate search stall."""
+    n = len(x)
+    scale = np.maximum(np.abs(x), 1.0e-4)
+    H = np.eye(n)
+    alphas = np.array([4.0, 2.0, 1.0, 0.5, 0.25, 0.1, 0.05, 0.02, 0.01, 0.003, 0.001])
+    trace = []
+    g_prev, z_prev = None, None
+    h = fd_rel
+    for it in range(max_iter):
+        z = x / scale
+        E = np.eye(n) * h
+        fc = f(np.vstack([(z + E) * scale, (z - E) * scale]))
+        g = (fc[:n] - fc[n:]) / (2.0 * h)
+        # the probes themselves are candidates
+        jb = int(np.argmin(fc))
+        if g_prev is not None:
+            sk, yk = z - z_prev, g - g_prev
+            sy = float(sk @ yk)
+            if sy > 1.0e-12 * np.linalg.norm(sk) * np.linalg.norm(yk):
+                rho = 1.0 / sy
+                V = np.eye(n) - rho * np.outer(sk, yk)
+                H = V @ H @ V.T + rho * np.outer(sk, sk)
+        p = -H @ g
+        if g @ p >= 0.0:                       # not a descent direction: restart from steepest descent
+            H = np.eye(n)
+            p = -g
+        p = p / max(1.0, np.max(np.abs(p)) / 0.2)          # no coordinate moves by more than 20 % at unit step
+        cand = (z + np.outer(alphas, p)) * scale
+        fl = f(cand)
+        ib = int(np.argmin(fl))
+        g_prev, z_prev = g, z
+        f_new, x_new = (float(fl[ib]), cand[ib]) if fl[ib] <= fc[jb] else (float(fc[jb]), np.vstack([(z + E) * scale, (z - E) * scale])[jb])
+        if f_new < fx - 1.0e-9 * abs(fx) * 1.0e-3:
+            x, fx = x_new.copy(), f_new
+        else:
+            if h <= 1.0e-4:
+                break
+            h *= 0.5                            # nothing improved: look closer, forget the curvature
+            H = np.eye(n)
+            g_prev = None
+        trace.append([float(it + 1), fx, h] + x.tolist())
+    return x, fx, trace
+
+
+def random_polish_batched(f, x, fx, seed=1, batch=64, max_launches=300, rel_tol=1.0e-6):
+    """Last stage of the batched search: `batch` random perturbations of one to three parameters per launch, the best one
+    kept; the width shrinks when a launch brings nothing and grows when it does.  The event times make the objective a
+    staircase (Core.hs:120-135), and moving a time to the next grid cell only pays off together with a size or rate change —
+    moves that neither finite differences nor single-coordinate probes see, and that a sampler finds by chance."""
+    rng = np.random.default_rng(seed)
+    n = len(x)
+    w = 0.01
+    trace = []
+    for it in range(max_launches):
+        if w < rel_tol:
+            break
+        cand = np.tile(x, (batch, 1))
+        for c in range(batch):
+            js = rng.choice(n, size=int(rng.integers(1, 4)), replace=False)
+            cand[c, js] *= 1.0 + rng.uniform(-w, w, size=len(js))
+        fc = f(cand)
+        j = int(np.argmin(fc))
+        if fc[j] < fx:
+            x, fx = cand[j].copy(), float(fc[j])
+            w = min(0.05, w * 1.3)
+        else:
+            w *= 0.7
+        trace.append([float(it + 1), fx, w] + x.tolist())
+    return x, fx, trace
 
 
 def run_maxl(a, opts, mt, params, hp, eng):
@@ -151,6 +264,13 @@ def run_maxl(a, opts, mt, params, hp, eng):
         print("minimizing from point " + str(x.tolist()), file=sys.stderr)
         x, tr = minimize_batched(f, x, a.maxCycles, a.parallel)
         trace += tr
+        if not a.noPolish:
+            x, fx, tr = bfgs_batched(f, x, float(f(x)[0]))
+            trace += tr
+            x, fx, tr = polish_batched(f, x, fx)
+            trace += tr
+            x, fx, tr = random_polish_batched(f, x, fx, seed=len(trace))
+            trace += tr
     score = float(f(x)[0])
     names = f.names
     with open(a.prefix + ".paramEstimates.txt", "w") as h:            # reportMaxResult, Maxl.hs:99-102
@@ -254,6 +374,74 @@ def run_mcmc(a, opts, mt, params, hp, eng):
     return best, float(pv[mi])
 
 
+# ---- find ----------------------------------------------------------------------------------------------------------
+def find_grid(events, nrPops, l, branchAge, deltaTime, maxTime):
+    """allParamPairs of Find.hs:49-58: every (branch, join time) at which the free branch `l` could join the tree.
+    `events` are (t, type, k, l, v) tuples in model order."""
+    joins = [(t, k, frm) for (t, ty, k, frm, _) in events if ty == L.RC_EV_JOIN]
+
+    def is_empty(branch):                                                       # isEmptyBranch, Find.hs:79-82
+        return any(frm == branch and t < branchAge for t, _, frm in joins)
+
+    def join_times(k):                                                          # getJoinTimes, Find.hs:84-89
+        times, i = [], 1.0
+        while i * deltaTime + branchAge <= maxTime:                             # map ((+branchAge) . (*deltaT)) [1.0, 2.0 ..]
+            times.append(i * deltaTime + branchAge)
+            i += 1.0
+        leave = [t for t, _, frm in joins if frm == k]
+        return times if not leave else [t for t in times if t < leave[0]]
+
+    return [(k, t) for k in range(nrPops) if k != l and not is_empty(k) for t in join_times(k)]
+
+
+def run_find(a, opts, mt, params, hp, eng):
+    """Find.hs:29-63: where does the free branch join the tree?  The reference evaluates the (branch, time) grid one
+    likelihood after the other (Find.hs:59-61); here the whole grid is ONE batch of models for rc_eval."""
+    spec = F.instantiateModel(opts, mt, params)
+    if a.queryName not in mt.mtBranchNames:
+        raise RarecoalException("could not find branch name " + a.queryName)    # findQueryIndex, Find.hs:73-76
+    l = mt.mtBranchNames.index(a.queryName)
+    ev = [e.as_tuple() for e in spec.mEvents]
+    if any(ty == L.RC_EV_JOIN and l in (k, frm) for (_, ty, k, frm, _) in ev):  # hasFreeBranch, Find.hs:66-69
+        from .api import RarecoalModelException
+        raise RarecoalModelException(f"model must have free branch {l}")
+    if a.branchAge > 0.0:                                                       # an ancient sample: frozen until its age
+        ev = [(0.0, L.RC_EV_FREEZE, l, 0, 1.0), (a.branchAge, L.RC_EV_FREEZE, l, 0, 0.0)] + ev
+    pairs = find_grid(ev, spec.mNrPops, l, a.branchAge, a.deltaTime, a.maxTime)
+    if not pairs:
+        raise RarecoalException("find: empty (branch, time) grid")
+    eng.set_times(spec.mTimeSteps)
+    P = spec.mNrPops
+    lls = np.zeros(len(pairs))
+    step = max(1, a.batch)
+    launches = 0
+    for i0 in range(0, len(pairs), step):
+        chunk = pairs[i0:i0 + step]
+        evs, off = [], [0]
+        for k, t in chunk:
+            evs += [(t, L.RC_EV_JOIN, k, l, 0.0)] + ev                          # newE : e, Find.hs:94-96
+            off.append(len(evs))
+        logl, _, status = eng.eval_raw(_events_array(evs), np.array(off, dtype=np.int32), np.full(len(chunk), spec.mTheta),
+                                       np.ones(len(chunk) * P), spec.mNoShortcut, hp.siteRed)
+        launches += 1
+        if status.any():                                                        # tryEither: the first failure is fatal
+            from .api import _raise
+            b = int(np.nonzero(status)[0][0])
+            _raise(int(status[b]), f"find: model for branch {chunk[b][0]}, time {chunk[b][1]} is invalid")
+        lls[i0:i0 + len(chunk)] = logl
+    for (k, t), ll in zip(pairs, lls):
+        print(f"branch={k}, time={hs_show(t)}, ll={hs_show(ll)}", file=sys.stderr)
+    with open(a.evalFile, "w") as h:                                            # writeResult, Find.hs:98-103
+        h.write("Branch\tTime\tLikelihood\n")
+        for (k, t), ll in zip(pairs, lls):
+            h.write(f"{k}\t{hs_show(t)}\t{hs_show(ll)}\n")
+    # maximumBy keeps the LAST of equal maxima
+    best = max(range(len(pairs)), key=lambda i: (lls[i], i))
+    print(f"highest likelihood point:\nbranch {pairs[best][0]}\ntime {hs_show(pairs[best][1])}\nlog-likelihood {hs_show(lls[best])}")
+    print(f"find: {len(pairs)} likelihoods in {launches} launches", file=sys.stderr)
+    return pairs, lls
+
+
 # ---- fit tables (MaxUtils.hs:125-195; patterns and names in model-branch order, no jackknife columns) ----------------
 def _write_fit_tables(prefix, opts, mt, params, hp, eng):
     spec = F.instantiateModel(opts, mt, params)
@@ -307,9 +495,19 @@ def add_parsers(sub, _general, _model, _hist, _opts, _template, _params, _load):
     p.add_argument("--maxCycles", type=int, default=10000)
     p.add_argument("--nrRestarts", type=int, default=5)
     p.add_argument("-o", "--prefix", required=True)
+    p.add_argument("--noPolish", action="store_true", help="skip the batched quasi-Newton and coordinate searches that follow every simplex run")
     p.add_argument("--parallel", type=int, default=4,
                    help="vertices reflected per iteration; each costs 4 speculative likelihoods in the same launch")
     p.set_defaults(fn=wrap(run_maxl))
+    p = sub.add_parser("find", help="Explore where a branch joins the tree")
+    _general(p); _model(p); _hist(p)
+    p.add_argument("-n", "--queryName", required=True, help="model branch that does not merge onto the tree at any time")
+    p.add_argument("-f", "--evalFile", required=True, help="file to write the list of computed likelihoods to")
+    p.add_argument("-b", "--branchAge", type=float, default=0.0, help="sampling age of the query sample")
+    p.add_argument("--deltaTime", type=float, default=0.0005)
+    p.add_argument("--maxTime", type=float, default=0.025)
+    p.add_argument("--batch", type=int, default=512, help="grid points evaluated per launch")
+    p.set_defaults(fn=wrap(run_find))
     p = sub.add_parser("mcmc", help="Run MCMC on the model and the data")
     _general(p); _model(p); _hist(p)
     p.add_argument("--cycles", type=int, default=1000)
