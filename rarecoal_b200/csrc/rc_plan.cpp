@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <thread>
 
@@ -728,6 +729,15 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     c.base = (uint64_t)(maxAf + 1);
     const int nEpochs = (int)sev.size() + 1;
     std::vector<PatPlan> pps((size_t)nPat);
+    // RC_PLAN_TIMING=1: wall time of the planner's phases on stderr
+    static const bool timing = std::getenv("RC_PLAN_TIMING") != nullptr;
+    auto tPhase = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rc plan] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tPhase).count());
+        tPhase = now;
+    };
 
     int nThreads = (int)std::thread::hardware_concurrency();
     if (nThreads < 1) nThreads = 1;
@@ -749,6 +759,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         for (int t = 0; t < nThreads; ++t) pool.emplace_back(worker);
         for (auto& th : pool) th.join();
     }
+    lap("live sets per pattern");
     int nnzw = 1, maxLive = 1;
     for (auto& pp : pps) {
         if (!pp.err.empty()) return pp.err;
@@ -911,6 +922,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         out.lastKeyId.assign(out.keyId.end() - (size_t)nPat * P, out.keyId.end());
     }
 
+    lap("trajectory keys");
     // ---- fast-tier bins: patterns in lexicographic order (neighbours share trajectory keys), packed first-fit over a
     //      short window of open bins under the slot / pattern / pair-row limits of the epochs the bins are used for.
     //      Two sets: one spanning all epochs (self-contained kernel: events handled inside the block) and one per
@@ -933,7 +945,6 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             return a < b;
         });
         const int rowCap = RC_KROWS - 2;          // smem pair rows per parity minus the dt row and the padding row
-        bool packDirect = false;                  // set around the packing of a direct group: no pair rows in shared memory
         struct OpenBin {
             std::vector<int> ids, slotsE, rowsUsed, rowsSelf;
             int rowStates = 0, cls = 0;
@@ -942,7 +953,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         // measured on C3 (44 models): 36.7 ms with lexicographic bins, 33.4 ms with cost-class bins; RC_BINSORT=0 restores the former
         const bool binSort = std::getenv("RC_BINSORT") ? std::atoi(std::getenv("RC_BINSORT")) != 0 : true;
         // mode: 0 one state per lane, 1 one row per lane, 3 one pattern per lane (bins of one cost class only)
-        auto pack_range = [&](int e0, int e1, int maxPats, int mode, bool keyedBins, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats) {
+        // packDirect: a direct group needs no pair rows in shared memory (no row limit)
+        auto pack_range = [&](int e0, int e1, int maxPats, int mode, bool keyedBins, const std::vector<int>& ids, std::vector<int>& patOff, std::vector<int>& pats,
+                              bool packDirect = false) {
             const int nE = e1 - e0 + 1;
             const bool rowMode = mode != 0, patMode = mode >= 3;
             const int patMaxStates = rc_pat_cap(mode);
@@ -1123,6 +1136,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         out.fBinPats.clear();
         pack_range(0, nEpochs - 1, maxPatFast, 0, false, order, out.fBinPatOff, out.fBinPats);
         out.nFastBins = (int)out.fBinPatOff.size() - 1;
+        lap("all-epoch bins");
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         // Two bin groups per epoch (index 2e + g): g = 0 the patterns small enough for one thread each (pattern mode), g = 1
         // the rest in row mode (all boxes with rows long enough) or state mode.
@@ -1195,6 +1209,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 ro[nPat] = (int)run;
             }
         }
+        lap("groups and row arrays");
         // ---- executed FP64 instructions per grid step (rc_kernels.cu, the update of each tier as written) ----
         out.epochFp64.assign((size_t)nEpochs, 0);
         out.epochFp64Short.assign((size_t)nEpochs, 0);
@@ -1241,25 +1256,51 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 if (pp.shortcutOK) out.epochFp64Short[(size_t)e] += n;
             }
         }
+        lap("instruction counts");
         out.grpDirect.assign((size_t)nEpochs * RC_NGROUP, 0);
         static const bool directEnv = std::getenv("RC_PAT_DIRECT") ? std::atoi(std::getenv("RC_PAT_DIRECT")) != 0 : true;
-        for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
-            const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
-            out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
-            out.kBinPatOff.push_back((int)out.kBinPats.size());
-            // a pattern group in which every pattern has one live branch (the root epoch of a tree)
-            bool direct = directEnv && mode >= RC_MODE_PAT && !groupIds[(size_t)v].empty();
-            for (int i : groupIds[(size_t)v]) direct = direct && pps[(size_t)i].rowNO[(size_t)e] == 0;
-            out.grpDirect[(size_t)v] = direct ? 1 : 0;
-            packDirect = direct;
-            if (!groupIds[(size_t)v].empty()) {
-                if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
-                else if (mode) pack_range(e, e, RC_NPBR, 1, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
-                else pack_range(e, e, RC_NPB, 0, true, groupIds[(size_t)v], out.kBinPatOff, out.kBinPats);
+        {
+            // the bin groups are packed independently of each other: one task per (epoch, group) over a few host threads, the
+            // results appended in order
+            const int nV = nEpochs * RC_NGROUP;
+            std::vector<std::vector<int>> offV((size_t)nV), patsV((size_t)nV);
+            for (int v = 0; v < nV; ++v) {
+                const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
+                // a pattern group in which every pattern has one live branch (the root epoch of a tree)
+                bool direct = directEnv && mode >= RC_MODE_PAT && !groupIds[(size_t)v].empty();
+                for (int i : groupIds[(size_t)v]) direct = direct && pps[(size_t)i].rowNO[(size_t)e] == 0;
+                out.grpDirect[(size_t)v] = direct ? 1 : 0;
             }
-            packDirect = false;
-            out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
+            std::atomic<int> nextV(0);
+            auto packer = [&]() {
+                for (;;) {
+                    const int v = nextV.fetch_add(1);
+                    if (v >= nV) break;
+                    if (groupIds[(size_t)v].empty()) continue;
+                    const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
+                    const bool direct = out.grpDirect[(size_t)v] != 0;
+                    if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
+                    else if (mode) pack_range(e, e, RC_NPBR, 1, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
+                    else pack_range(e, e, RC_NPB, 0, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
+                }
+            };
+            const int nT = nPat < 2048 ? 1 : std::min(nThreads, nV);
+            if (nT <= 1) packer();
+            else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nT; ++t) pool.emplace_back(packer);
+                for (auto& th : pool) th.join();
+            }
+            for (int v = 0; v < nV; ++v) {
+                out.kBinBase[(size_t)v] = (int)out.kBinPatOff.size();
+                const int base = (int)out.kBinPats.size();
+                out.kBinPatOff.push_back(base);
+                for (int o : offV[(size_t)v]) out.kBinPatOff.push_back(base + o);       // cumulative counts after every bin
+                out.kBinPats.insert(out.kBinPats.end(), patsV[(size_t)v].begin(), patsV[(size_t)v].end());
+                out.nKBins[(size_t)v] = (int)out.kBinPatOff.size() - 1 - out.kBinBase[(size_t)v];
+            }
         }
+        lap("per-epoch bins");
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
         for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
             const int e = v / RC_NGROUP, b0 = out.kBinBase[(size_t)v];
@@ -1270,6 +1311,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             fOff.push_back((int)out.kFetchRows.size());
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
+        lap("fetch lists");
         if (std::getenv("RC_PLAN_DEBUG")) {
             for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
                 const int e = v / RC_NGROUP, m = out.epochMode[(size_t)v];
@@ -1374,7 +1416,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         tb += nNew + 1;
         te += run;
     }
-    return build_bin_images(out);
+    lap("concatenation");
+    std::string r = build_bin_images(out);
+    lap("bin images");
+    return r;
 }
 
 
