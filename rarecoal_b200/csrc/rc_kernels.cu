@@ -931,8 +931,9 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
         const double dt = dts[me.beg + i];
         double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
-        p0[0] = dt > 0.0 ? dt : 0.0;
-        p0[1] = 0.0;
+        // pair 0 = {1, dt}: its first half doubles as the neutral decay factor of the pattern kernel's unused unit-branch slots
+        p0[0] = 1.0;
+        p0[1] = dt > 0.0 ? dt : 0.0;
     }
     if (t >= E.nThr) return;
     const int key = pl.thrKey[E.thrOff + t];
@@ -965,11 +966,26 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     const int rowLen = rc_row_len(pl.P, pl.A1);
     const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
     const int jOff = hasPair ? 2 * j : 0;
+    // The chain of a-values is sequential and every step costs two divisions and an exp; the step's table entries do not
+    // depend on it, so the loads of step s+1 are issued before the arithmetic of step s (the warp issues in order: left in
+    // program order they would sit behind it and their L2 latency would be added to every step).
+    double2 p0n = make_double2(1.0, 0.0), pjn = p0n;
+    double dtn = 0.0;
+    if (me.beg < me.end) {
+        p0n = *reinterpret_cast<const double2*>(row);
+        pjn = *reinterpret_cast<const double2*>(row + jOff);
+        dtn = dts[me.beg];
+    }
     for (int s = me.beg; s < me.end; ++s, out += stride, row += rowLen) {
         if (lastEpoch && s == M.sShort && j == 1) aShort[M.aShortOff + key] = a;
-        const double2 p0 = *reinterpret_cast<const double2*>(row);            // {EA, 1/N}; 1/N == 0: frozen
-        const double2 pj = *reinterpret_cast<const double2*>(row + jOff);     // {CN, E2}
-        const double dt = dts[s];
+        const double2 p0 = p0n;                                               // {EA, 1/N}; 1/N == 0: frozen
+        const double2 pj = pjn;                                               // {CN, E2}
+        const double dt = dtn;
+        if (s + 1 < me.end) {
+            p0n = *reinterpret_cast<const double2*>(row + rowLen);
+            pjn = *reinterpret_cast<const double2*>(row + rowLen + jOff);
+            dtn = dts[s + 1];
+        }
         double G = 1.0, E2 = 0.0;
         if (dt > 0.0 && p0.y != 0.0) {
             if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * p0.x);         // propagateA, Core.hs:239-240
@@ -1064,7 +1080,7 @@ __device__ __forceinline__ void rc_key_step(RcKeyRegs<NNZ>& R, const unsigned sB
         }
         R.bv = fma(R.bv, D, t2);                                               // updateB, Core.hs:259
         rc_sts64(myB + QH * K::B_PAR, R.bv);
-        if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.bv, R.dacc);   // updateD, Core.hs:282-288
+        if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot + 8u), R.bv, R.dacc);   // updateD, Core.hs:282-288
     }
     rc_cp_wait<RC_KDEPTH - 2>();       // the pairs of the next step have landed
     __syncthreads();
@@ -1406,7 +1422,7 @@ __device__ __forceinline__ int rc_row_run(RcRowRegs<NOCAP>& R, const unsigned sB
                 R.b[j] = fma(R.b[j], D * gj, t2);                            // updateB, Core.hs:259
                 if (v) rc_sts64(R.myB + qo + (unsigned)j * 8u, R.b[j]);
             }
-            if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot), R.b[0], R.dacc);   // updateD, Core.hs:282-288
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + K::O_RE + slot + 8u), R.b[0], R.dacc);   // updateD, Core.hs:282-288
         }
         rc_cp_wait<RC_RDEPTH - 2>();
         __syncthreads();
@@ -1728,9 +1744,6 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 #ifndef RC_PAT_GU
 #define RC_PAT_GU 4
 #endif
-#ifndef RC_PAT_NU_MODE
-#define RC_PAT_NU_MODE 1      // 0: loop over the unit branches (16.8 ms on C3), 1: loads unrolled, tree product (15.6 ms)
-#endif
 #ifndef RC_PDEPTH
 #define RC_PDEPTH 4
 #endif
@@ -1775,7 +1788,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
                         const double t2 = (i + 1 < MA) ? R.b[i + 1] * p.y : 0.0;
                         R.b[i] = fma(R.b[i], p.x, t2);                                      // updateB, Core.hs:259
                     }
-                    if (R.unit) R.dacc = fma(*(R.dptr - 2 * (long long)R.dPairBase), R.b[0], R.dacc);   // updateD, Core.hs:282-288
+                    if (R.unit) R.dacc = fma(*(R.dptr - 2 * (long long)R.dPairBase + 1), R.b[0], R.dacc);   // updateD, Core.hs:282-288
                     R.dptr += strideD;
                 }
             }
@@ -1783,6 +1796,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
         }
     }
     const unsigned myRE = sBase + threadIdx.x * 16u;
+    const unsigned long long unitRows = R.rows64 >> (8 * (1 + NS));      // pair rows of the m = 1 branches, one byte each
     const unsigned aA = sBase + rc_pat_row(R, 0) * 16u, aB = sBase + rc_pat_row(R, 1) * 16u, aC = sBase + rc_pat_row(R, 2) * 16u,
                    aD = sBase + rc_pat_row(R, 3) * 16u, aE = sBase + rc_pat_row(R, 4) * 16u;
     for (; s < nextStop; ++s) {
@@ -1811,17 +1825,12 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
 #pragma unroll
                 for (int j = 0; j < MEp; ++j) rc_lds128(aE + slot + (unsigned)j * 16u, gE[j], eE[j]);
             }
-            double D1 = 1.0;                     // branches with m = 1: G_k(1) only
-#if RC_PAT_NU_MODE == 0
-            for (int u = 0; u < R.nU; ++u) D1 *= rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot);
-#else
-            if (R.nU) {
-                double g[7];
+            // branches with m = 1 contribute G_k(1) only.  Every lane multiplies all 7 - NS slots: a spare slot points at pair
+            // row 0, whose first half is 1.0 — no predicates, no constants to materialise, a balanced product
+            double g[7];
 #pragma unroll
-                for (int u = 0; u < 7 - NS; ++u) g[u] = u < R.nU ? rc_lds64(sBase + rc_pat_row(R, 1 + NS + u) * 16u + slot) : 1.0;
-                D1 = ((g[0] * g[1]) * (g[2] * (NS < 4 ? g[3] : 1.0))) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
-            }
-#endif
+            for (int u = 0; u < 7 - NS; ++u) g[u] = rc_lds64(sBase + slot + ((unsigned)(unitRows >> (8 * u)) & 0xFFu) * 16u);
+            const double D1 = ((g[0] * g[1]) * (g[2] * (NS < 4 ? g[3] : 1.0))) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
                 double gA, eA;
@@ -1851,7 +1860,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
                     }
                 }
             }
-            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot), R.b[0], R.dacc);           // updateD, Core.hs:282-288
+            if (R.unit) R.dacc = fma(rc_lds64(sBase + slot + 8u), R.b[0], R.dacc);      // updateD, Core.hs:282-288
         }
         rc_cp_wait<RC_PDEPTH - 2>();
         __syncthreads();
@@ -2010,7 +2019,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (tid == 0) shapeS = la.z;
     __syncthreads();
     const unsigned shapeB = shapeS & 0xFFFFFu;
-    R.nU = (int)((la.z >> 20) & 0xFu);                       // per lane: the unit branches are loaded under a predicate
+    R.nU = (int)((la.z >> 20) & 0xFu);
+
     R.unit = R.on && (shapeB >> 4) == 0 && R.nU == 0;        // x = e_A is the first state of a single-branch pattern
     const int MAw = (int)(shapeB & 0xFu);
 

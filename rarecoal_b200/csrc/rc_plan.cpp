@@ -593,7 +593,8 @@ static std::string build_bin_images(PlanHost& out) {
                     for (int q = 0; q < RC_PLANE_N; ++q) rec[q] = 0u;
                     const bool direct = out.grpDirect[(size_t)v] != 0;
                     for (int q = 0; q < 8; ++q) {
-                        const uint32_t row = (!direct && q < 1 + nS + nU) ? (uint32_t)rb[dims[q]] : (uint32_t)(RC_KROWS - 1);
+                        // an unused slot points at pair row 0, {1, dt}: a neutral decay factor (direct bins have no ring: marker)
+                        const uint32_t row = direct ? (uint32_t)(RC_KROWS - 1) : q < 1 + nS + nU ? (uint32_t)rb[dims[q]] : 0u;
                         if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
                         rec[q >> 2] |= row << (8 * (q & 3));
                     }
@@ -1575,7 +1576,7 @@ std::string check_plan(const PlanHost& h) {
                             const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
                             const int len = q <= nS ? M[q] : 1;
                             if (directG) { if (row != RC_KROWS - 1) return fail("image pattern pair rows (direct)"); }
-                            else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != RC_KROWS - 1) return fail("image pattern pair rows");
+                            else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != 0) return fail("image pattern pair rows");
                         }
                         if ((int)r[4] >= nPat || (long long)r[3] + n > h.epochSlots[(size_t)e] || eOff + n > nB) return fail("image pattern hand-over");
                         const int live = h.slotOff[(size_t)e * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[4]];
