@@ -331,3 +331,41 @@ def test_batch_mixing_shortcut_and_noshortcut_models(eng, fivepop, default_times
         assert abs(logl[m] - ll_o) / abs(ll_o) < LOGL_RTOL
     assert logl[0] != logl[1]
     assert eng.stats()["state_steps"] == total
+
+
+def test_c3_batch_mixing_join_orders_uses_one_plan_per_order(default_times):
+    # an optimiser or sampler over the seven join times of the 8-population tree crosses event orders: a batch that mixes
+    # four orders is evaluated plan by plan (one transition plan per order, built once and kept in the LRU cache), every
+    # model equal to its own single evaluation and — two of them, in full — to the oracle
+    nvec, pats, cnt = Wk.c3_problem(max_af=6)
+    e = R.Engine(0)
+    e.set_problem(nvec, 6, pats, cnt, Wk.TOTAL_SITES)
+    base = Wk.c3_params()
+    orders = []
+    for swap in (None, (8, 9), (9, 10), (12, 13)):           # indices of join times in the parameter vector
+        x = base.copy()
+        if swap:
+            x[swap[0]], x[swap[1]] = x[swap[1]], x[swap[0]]
+        orders.append(x)
+    batch = [Wk.c3_events_from_params(orders[i % 4] * (1.0 + 0.001 * (i // 4))) for i in range(12)]
+    specs = [_spec(8, default_times, ev) for ev in batch]
+    logl, probs, status = e.eval_models(specs, want_probs=True)
+    st = e.stats()
+    assert not status.any() and st["plan_misses"] == 4
+    for b in (1, 6, 11):
+        l1, p1, _ = e.eval_models([specs[b]], want_probs=True)
+        assert np.array_equal(p1[0], probs[b]) and l1[0] == logl[b]
+        assert e.stats()["plan_misses"] == 0               # cached
+    for b in (2, 3):
+        ll_o, probs_o, _ = O.logl(8, 6, default_times, 0.0005, [1.0] * 8, False, batch[b], nvec, pats, cnt, Wk.TOTAL_SITES)
+        assert _relerr(probs[b], probs_o) < PROB_RTOL and abs(logl[b] - ll_o) / abs(ll_o) < LOGL_RTOL
+    # the cache keeps the most recently used plans when it is full
+    e.set_option("plan_cache_max", 2)
+    x5 = base.copy()
+    x5[10], x5[11] = x5[11], x5[10]
+    e.eval_models([_spec(8, default_times, Wk.c3_events_from_params(x5))])       # a fifth order: the least recently used plans go
+    st = e.stats()
+    assert st["plan_misses"] == 1 and st["plan_evictions"] == 3
+    logl2, _, _ = e.eval_models(specs[:4])                                       # rebuilt on demand, same answers
+    assert np.array_equal(logl2, logl[:4]) and e.stats()["plan_misses"] >= 3
+    e.close()

@@ -5,6 +5,7 @@ launches of one evaluation, read by bench.py -> roofline.traffic) and prints the
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = os.environ.get("RC_PROFILE_TAG", "r02")
 rep = sys.argv[1]          # .ncu-rep, or the raw page already exported on the GPU box (ncu -i X --page raw --csv)
 if rep.endswith(".csv"):
     raw = open(rep).read()
@@ -32,7 +33,7 @@ def scale(v, u):
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
 
-with open(os.path.join(ROOT, "profiles", "r01_propagate_raw.csv"), "w", newline="") as f:
+with open(os.path.join(ROOT, "profiles", TAG + "_propagate_raw.csv"), "w", newline="") as f:
     w = csv.writer(f, quoting=csv.QUOTE_ALL)
     w.writerows([hdr, units] + body)
 rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
@@ -67,10 +68,10 @@ json.dump({
     "time_share": {k: round(v, 3) for k, v in share.items()},
     "pipes_pct_of_peak_time_weighted": {"shared_memory_wavefronts": round(pipes["smem"], 1), "fp64_pipe": round(pipes["fp64"], 1),
                                         "issue_slots": round(pipes["issue"], 1), "warps_active": round(pipes["warps"], 1)},
-    "source": "profiles/r01_propagate_raw.csv (ncu --set full, per-launch metrics; DRAM = dram__bytes_read.sum + dram__bytes_write.sum summed)",
+    "source": "profiles/" + TAG + "_propagate_raw.csv (ncu --set full, per-launch metrics; DRAM = dram__bytes_read.sum + dram__bytes_write.sum summed)",
     "note": "trajectory tables (~60 MB per model) written by rc_traj_kernel and read here, bin images re-read per model, b carried "
             "between epoch launches; a few hundred GB/s against the measured 6539 GB/s copy bandwidth - not the bound",
-}, open(os.path.join(ROOT, "profiles", "r01_keyed_traffic.json"), "w"))
+}, open(os.path.join(ROOT, "profiles", TAG + "_traffic.json"), "w"))
 print("| launch | kernel | grid | ms | smem pipe % | issue % | FP64 pipe % | warps % | regs | DRAM rd / wr |")
 for e, r in enumerate(body):
     g = lambda k: r[col(names[k])]
