@@ -1827,6 +1827,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
             }
             // branches with m = 1 contribute G_k(1) only.  Every lane multiplies all 7 - NS slots: a spare slot points at pair
             // row 0, whose first half is 1.0 — no predicates, no constants to materialise, a balanced product
+            // (skipping the loads with one uniform branch in bins without any such branch measured slower: 10.21 against 10.13 ms)
             double g[7];
 #pragma unroll
             for (int u = 0; u < 7 - NS; ++u) g[u] = rc_lds64(sBase + slot + ((unsigned)(unitRows >> (8 * u)) & 0xFFu) * 16u);
@@ -1956,7 +1957,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         slot = 0;
     };
     // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory (the ring starts
-    //      afterwards: it lives in the same bytes) ----
+    //      afterwards: it lives in the same bytes; starting it before the gather, in bytes of its own, keeps the fetch
+    //      pointers live across the gather and measured slower — spills, 9.96 -> 10.26 ms on C3) ----
     uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la, ld = la;
     if (R.on) {
         const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + (RC_PLANE_N / 4) * (size_t)tid;

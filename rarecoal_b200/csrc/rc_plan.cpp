@@ -1097,7 +1097,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         };
         // de-duplicated pair rows a bin fetches in epoch e, and the first row of every (pattern, branch)
         auto fetch_lists = [&](int e, const std::vector<int>& patOff, const std::vector<int>& pats, int b0, int b1,
-                               std::vector<int>& fOff, std::vector<int>& fRows, std::vector<uint16_t>& rBase, size_t rBaseOff) {
+                               std::vector<int>& fOff, std::vector<int>& fRows, std::vector<uint16_t>& rBase, size_t rBaseOff, bool pad) {
             const PlanHost::Epoch& E = out.ep[(size_t)e];
             for (int bI = b0; bI < b1; ++bI) {
                 fOff.push_back((int)fRows.size());
@@ -1115,12 +1115,22 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     }
                 }
                 fRows.push_back(0);                 // smem pair row 0 <- {dt, 0}
+                // Pattern mode: the lanes of a quarter warp read the pairs {G, E2} of eight consecutive keys with one LDS.128
+                // (row j of each key at the same time).  A key of even length puts every second or fourth of them on the same
+                // 16-byte bank group: keys of two or more rows are padded to an odd stride when the bin's ring has room.
+                bool padBin = false;
+                if (pad) {
+                    int rowsPadded = 1;
+                    for (int key : keyOrder) { const int n = rowsOf[key]; rowsPadded += n >= 2 ? (n | 1) : n; }
+                    padBin = rowsPadded <= RC_KROWS - 1;
+                }
                 int row = 1;
                 for (int key : keyOrder) {
                     startOf[key] = row;
                     int n = rowsOf[key];
                     for (int j = 0; j < n; ++j) fRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
                     row += n;
+                    if (padBin && n >= 2 && !(n & 1)) { fRows.push_back(0); ++row; }
                 }
                 for (int q = patOff[(size_t)bI]; q < patOff[(size_t)bI + 1]; ++q) {
                     int i = pats[(size_t)q];
@@ -1308,7 +1318,11 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             // fetch offsets are stored at the same index as the bin offsets (one extra entry per group)
             std::vector<int> fOff;
             if (out.grpDirect[(size_t)v]) fOff.assign((size_t)out.nKBins[(size_t)v], (int)out.kFetchRows.size());     // nothing to fetch
-            else fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0);
+            else {
+                static const bool padEnv = std::getenv("RC_PAT_PAD") ? std::atoi(std::getenv("RC_PAT_PAD")) != 0 : true;
+                fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0,
+                            padEnv && out.epochMode[(size_t)v] >= RC_MODE_PAT);
+            }
             fOff.push_back((int)out.kFetchRows.size());
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
         }
