@@ -453,7 +453,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
         std::vector<RcEpochDev> eps(h.ep.size());
         for (size_t e = 0; e < h.ep.size(); ++e) {
             eps[e].nKeys = h.ep[e].nKeys; eps[e].nThr = h.ep[e].nThr; eps[e].rowPairs = h.ep[e].rowPairs;
-            eps[e].keyOff = h.ep[e].keyOff; eps[e].thrOff = h.ep[e].thrOff;
+            eps[e].keyOff = h.ep[e].keyOff; eps[e].thrOff = h.ep[e].thrOff; eps[e].elBase = h.ep[e].elBase;
         }
         if ((rc = upload(ctx, pe, eps, &d.ep))) return rc;
     }
@@ -481,6 +481,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     if ((rc = upload(ctx, pe, h.kLane, &d.kLane))) return rc;
     if ((rc = upload(ctx, pe, h.kElem, &d.kElem))) return rc;
     d.maxEpochSlots = h.maxEpochSlots;
+    d.dirOff = h.dirOff;
     if ((rc = upload(ctx, pe, h.epochMode, &d.epochMode))) return rc;
     if ((rc = upload(ctx, pe, h.rowOff, &d.rowOff))) return rc;
     if ((rc = upload(ctx, pe, h.rowEpochBase, &d.rowEpochBase))) return rc;

@@ -1917,7 +1917,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int binIdx = binBase + (int)blockIdx.x;
     const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
     const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
-    const int np = hdrA.y, nB = hdrA.w;
+    const int np = hdrA.y, nB = hdrA.w & ~RC_HDR_DIRIN;
+    const bool dirIn = (hdrA.w & RC_HDR_DIRIN) != 0;      // b arrives in lane order (the previous epoch's lanes applied the Join)
     if (np == 0) return;              // the unused header between two bin groups launched together
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
@@ -1971,7 +1972,19 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        if (e > 0 && sevs[models[b].sevOff + e - 1].type == RC_EV_JOIN_D) {
+        if (dirIn) {
+            // direct hand-over: the bin's b is one contiguous run of the lane-ordered region
+            const double* src = bp + pl.dirOff + (hdrB.w - pl.ep[e].elBase);
+            constexpr int GU = 2 * RC_PAT_GU;
+            for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
+                double v[GU];
+#pragma unroll
+                for (int u = 0; u < GU; ++u) v[u] = i + u * RC_PBLOCK < nB ? src[i + u * RC_PBLOCK] : 0.0;
+#pragma unroll
+                for (int u = 0; u < GU; ++u)
+                    if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
+            }
+        } else if (e > 0 && sevs[models[b].sevOff + e - 1].type == RC_EV_JOIN_D) {
             // a Join: all weights are 1, twice as many states per batch
             constexpr int GU = 2 * RC_PAT_GU;
             for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
@@ -2090,11 +2103,28 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (tid >= np) return;
     if (!isLast) {
         // ---- hand b and the updateD sums to the next epoch's launch ----
-        double* out = bCur + (size_t)b * bStride + la.w;
         const unsigned refW[9] = {lb.z, lb.w, lc.x, lc.y, lc.z, lc.w, ld.x, ld.y, ld.z};
+        if (la.z & RC_PLANE_DIROUT) {
+            // direct hand-over: the lane applies the Join itself, new_b[J(x)] += b(x) (Core.hs:172-188), summing in its own
+            // [state][lane] column of shared memory (the ring is drained), and writes the pattern's new states where its lane
+            // of the next epoch reads them
+            const int nOut = (int)((la.z >> 24) & 0x3Fu);
+            double* col = bb + tid;
+            for (int y = 0; y < nOut; ++y) col[y * RC_PBLOCK] = 0.0;
 #pragma unroll
-        for (int x = 0; x < MAXS; ++x)
-            if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
+            for (int x = 0; x < MAXS; ++x)
+                if (x < n) {
+                    double* t = col + ((refW[x >> 2] >> (8 * (x & 3))) & 0xFFu) * RC_PBLOCK;
+                    *t = *t + R.b[x];
+                }
+            double* out = bCur + (size_t)b * bStride + pl.dirOff + la.w;
+            for (int y = 0; y < nOut; ++y) out[y] = col[y * RC_PBLOCK];
+        } else {
+            double* out = bCur + (size_t)b * bStride + la.w;
+#pragma unroll
+            for (int x = 0; x < MAXS; ++x)
+                if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
+        }
         dAcc[(size_t)b * nPat + pid] = dp;
         return;
     }

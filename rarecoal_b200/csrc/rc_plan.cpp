@@ -526,7 +526,7 @@ static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int maxStates, int* 
 // pattern ids, slot offsets, packed words and transition offsets is resolved here once, in the order the lanes of the
 // block consume it: the block reads its header, every lane one 32-byte record, and the gather goes straight to the
 // transition entries.
-static std::string build_bin_images(PlanHost& out) {
+static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& sev) {
     const int P = out.P, nPat = out.nPat, nE = out.nEpochs, nnzw = out.nnzw;
     out.kBinHdr.assign(out.kBinPatOff.size() * (size_t)RC_HDR_N, 0);
     out.kPatRec.assign(out.kBinPats.size() * 2, 0);
@@ -537,6 +537,10 @@ static std::string build_bin_images(PlanHost& out) {
     if (out.kBinBase.empty()) return "";
     if (out.maxEpochSlots >= (1LL << RC_IMG_CNT_SHIFT)) return "too many live states in one epoch for the keyed tier";
     if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
+    // pattern-mode lanes: where the record of (epoch, pattern) went, its group and its first element record
+    std::vector<long long> recPos((size_t)nE * nPat, -1);
+    std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0);
+    std::vector<long long> patElemEnd((size_t)nE, 0);
     // gather record of the state with reference index `ref` of pattern i in epoch e
     auto gather_rec = [&](int e, int i, int ref, int live, uint32_t& r0, uint32_t& r1) -> bool {
         if (e == 0) {
@@ -560,6 +564,7 @@ static std::string build_bin_images(PlanHost& out) {
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
         const int b0 = out.kBinBase[(size_t)v];
+        if (v % RC_NGROUP == 0) out.ep[(size_t)e].elBase = (int)(out.kElem.size() / 2);
         for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
             const int p0 = out.kBinPatOff[(size_t)bI], p1 = out.kBinPatOff[(size_t)bI + 1];
             if (out.kLane.size() / 4 > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
@@ -626,6 +631,9 @@ static std::string build_bin_images(PlanHost& out) {
                     rec[3] = (uint32_t)so[i];
                     rec[4] = (uint32_t)i;
                     rec[5] = (uint32_t)bOff;
+                    recPos[(size_t)e * nPat + i] = (long long)out.kLane.size();
+                    elPos[(size_t)e * nPat + i] = hdr[7] + bOff;
+                    grpOf[(size_t)e * nPat + i] = v;
                     out.kLane.insert(out.kLane.end(), rec, rec + RC_PLANE_N);
                     out.kElem.insert(out.kElem.end(), el.begin(), el.end());
                     lanes += 1;
@@ -715,6 +723,75 @@ static std::string build_bin_images(PlanHost& out) {
             out.grpMaxFetch[(size_t)v] = std::max(out.grpMaxFetch[(size_t)v], hdr[5]);
             out.grpMaxB[(size_t)v] = std::max(out.grpMaxB[(size_t)v], bOff);
         }
+        if (patM) patElemEnd[(size_t)e] = (long long)(out.kElem.size() / 2);
+    }
+    // ---- direct hand-over across a Join between pattern-mode epochs.  The lane that owns a pattern holds all its b(x): it
+    //      applies the Join itself (new_b[J(x)] += b(x), Core.hs:172-188) and writes the result where the pattern's lane of the
+    //      next epoch reads it — contiguous, in that lane's own state order — instead of writing slots that the next block
+    //      gathers through element records and transition entries (three dependent loads per state at the start of every block).
+    //      A bin group reads this way if every pattern of it was in pattern mode in the previous epoch. ----
+    out.grpDirIn.assign((size_t)nE * RC_NGROUP, 0);
+    out.dirOff = out.maxEpochSlots;
+    out.dirSize = 0;
+    static const bool dirEnv = std::getenv("RC_PAT_DIRHAND") ? std::atoi(std::getenv("RC_PAT_DIRHAND")) != 0 : true;
+    for (int e = 1; e < nE && dirEnv; ++e) {
+        if (sev[(size_t)e - 1].type != RC_EV_JOIN_D) continue;
+        const int* trOff = &out.trOff[(size_t)out.trBase[(size_t)e - 1]];
+        for (int g = 0; g < RC_NPATG; ++g) {
+            const int v = e * RC_NGROUP + g;
+            if (out.epochMode[(size_t)v] < RC_MODE_PAT || out.nKBins[(size_t)v] == 0) continue;
+            const int b0 = out.kBinBase[(size_t)v];
+            const int q0 = out.kBinPatOff[(size_t)b0], q1 = out.kBinPatOff[(size_t)(b0 + out.nKBins[(size_t)v])];
+            std::vector<uint8_t> maps((size_t)(q1 - q0) * RC_PAT_MAXL, 0);
+            bool ok = true;
+            for (int q = q0; q < q1 && ok; ++q) {
+                const int i = out.kBinPats[(size_t)q];
+                const long long rpN = recPos[(size_t)e * nPat + i], rpO = recPos[(size_t)(e - 1) * nPat + i];
+                if (rpN < 0 || rpO < 0) { ok = false; break; }
+                const uint32_t* rn = &out.kLane[(size_t)rpN];
+                const uint32_t* ro = &out.kLane[(size_t)rpO];
+                const int liveN = out.slotOff[(size_t)e * (nPat + 1) + i + 1] - out.slotOff[(size_t)e * (nPat + 1) + i];
+                const int liveO = out.slotOff[(size_t)(e - 1) * (nPat + 1) + i + 1] - out.slotOff[(size_t)(e - 1) * (nPat + 1) + i];
+                if (liveN > RC_PAT_MAXL || liveO > RC_PAT_MAXL) { ok = false; break; }
+                uint8_t localOfRef[RC_PAT_MAXL];
+                for (int x = 0; x < liveO; ++x) localOfRef[(ro[6 + (x >> 2)] >> (8 * (x & 3))) & 0xFFu] = (uint8_t)x;
+                uint8_t* mp = &maps[(size_t)(q - q0) * RC_PAT_MAXL];
+                for (int x = 0; x < liveO; ++x) mp[x] = 0xFF;
+                for (int y = 0; y < liveN && ok; ++y) {
+                    const int ref = (int)((rn[6 + (y >> 2)] >> (8 * (y & 3))) & 0xFFu);
+                    const int sl = out.slotOff[(size_t)e * (nPat + 1) + i] + ref;
+                    for (int t = trOff[sl]; t < trOff[sl + 1]; ++t) {
+                        const uint32_t ent = out.trEnt[(size_t)(out.trEntBase[(size_t)e - 1] + t)];
+                        const int src = (int)(ent & 0xFFFFu);
+                        if ((ent >> 16) != RC_W_ONE || src >= liveO || mp[localOfRef[src]] != 0xFF) { ok = false; break; }
+                        mp[localOfRef[src]] = (uint8_t)y;
+                    }
+                }
+                for (int x = 0; x < liveO && ok; ++x) if (mp[x] == 0xFF) ok = false;     // a Join maps every state somewhere
+            }
+            if (!ok) continue;
+            out.grpDirIn[(size_t)v] = 1;
+            for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) out.kBinHdr[(size_t)bI * RC_HDR_N + 3] |= RC_HDR_DIRIN;
+            for (int q = q0; q < q1; ++q) {
+                const int i = out.kBinPats[(size_t)q];
+                uint32_t* ro = &out.kLane[(size_t)recPos[(size_t)(e - 1) * nPat + i]];
+                const int liveN = out.slotOff[(size_t)e * (nPat + 1) + i + 1] - out.slotOff[(size_t)e * (nPat + 1) + i];
+                const int liveO = out.slotOff[(size_t)(e - 1) * (nPat + 1) + i + 1] - out.slotOff[(size_t)(e - 1) * (nPat + 1) + i];
+                const uint8_t* mp = &maps[(size_t)(q - q0) * RC_PAT_MAXL];
+                for (int w = 6; w < 15; ++w) ro[w] = 0u;
+                for (int x = 0; x < liveO; ++x) ro[6 + (x >> 2)] |= (uint32_t)mp[x] << (8 * (x & 3));
+                ro[2] |= RC_PLANE_DIROUT | ((uint32_t)liveN << 24);
+                ro[3] = (uint32_t)(elPos[(size_t)e * nPat + i] - out.ep[(size_t)e].elBase);
+                // the lane sums into [state][lane] doubles of its block's shared memory
+                int& mb = out.grpMaxB[(size_t)grpOf[(size_t)(e - 1) * nPat + i]];
+                mb = std::max(mb, RC_PBLOCK * liveN);
+            }
+            out.dirSize = std::max(out.dirSize, patElemEnd[(size_t)e] - out.ep[(size_t)e].elBase);
+        }
+    }
+    if (out.dirSize > 0) {
+        out.dirOff = (out.maxEpochSlots + 1) & ~1LL;
+        out.maxEpochSlots = out.dirOff + out.dirSize;
     }
     return "";
 }
@@ -1432,7 +1509,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         te += run;
     }
     lap("concatenation");
-    std::string r = build_bin_images(out);
+    std::string r = build_bin_images(out, sev);
     lap("bin images");
     return r;
 }
@@ -1563,7 +1640,11 @@ std::string check_plan(const PlanHost& h) {
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
-                const int np = hdr[1], lanes = hdr[2], nB = hdr[3], nFetch = hdr[5];
+                const int np = hdr[1], lanes = hdr[2], nB = hdr[3] & ~RC_HDR_DIRIN, nFetch = hdr[5];
+                const bool dirIn = (hdr[3] & RC_HDR_DIRIN) != 0;
+                if (dirIn && (!patM || e == 0 || h.grpDirIn.empty() || !h.grpDirIn[(size_t)v] ||
+                              hdr[7] - h.ep[(size_t)e].elBase < 0 || hdr[7] - h.ep[(size_t)e].elBase + nB > h.dirSize))
+                    return fail("image header direct hand-over");
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
                 if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * patMax : RC_ROW_BCAP))
@@ -1592,14 +1673,24 @@ std::string check_plan(const PlanHost& h) {
                             if (directG) { if (row != RC_KROWS - 1) return fail("image pattern pair rows (direct)"); }
                             else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != 0) return fail("image pattern pair rows");
                         }
-                        if ((int)r[4] >= nPat || (long long)r[3] + n > h.epochSlots[(size_t)e] || eOff + n > nB) return fail("image pattern hand-over");
+                        if ((int)r[4] >= nPat || eOff + n > nB) return fail("image pattern hand-over");
                         const int live = h.slotOff[(size_t)e * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[4]];
-                        if (live != n || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
-                        std::vector<char> hit((size_t)n, 0);
-                        for (int q = 0; q < n; ++q) {
-                            const int ref = (int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
-                            if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
-                            hit[(size_t)ref] = 1;
+                        if (live != n) return fail("image pattern states");
+                        if (r[2] & RC_PLANE_DIROUT) {
+                            // the lane applies the next Join itself: next-epoch state index per state, lane-ordered destination
+                            const int nOut = (int)((r[2] >> 24) & 0x3Fu);
+                            if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + nOut > h.dirSize) return fail("image direct hand-over");
+                            if (nOut != h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4]]) return fail("image direct hand-over states");
+                            for (int q = 0; q < n; ++q)
+                                if ((int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu) >= nOut) return fail("image direct hand-over map");
+                        } else {
+                            if ((long long)r[3] + n > h.epochSlots[(size_t)e] || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
+                            std::vector<char> hit((size_t)n, 0);
+                            for (int q = 0; q < n; ++q) {
+                                const int ref = (int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
+                                if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
+                                hit[(size_t)ref] = 1;
+                            }
                         }
                     } else if (!rows) {
                         for (int d = 0; d < 8; ++d) {

@@ -56,6 +56,7 @@ struct PlanHost {
     // each key once and all patterns sharing it read the result.
     struct Epoch {
         int nKeys = 0, nThr = 0, rowPairs = 0, keyOff = 0, thrOff = 0;
+        int elBase = 0;                    // first element record (kElem) of the epoch: origin of its lane-ordered b region
     };
     std::vector<Epoch> ep;                 // [nEpochs]
     std::vector<uint8_t> keyBranch, keyMaxJ, keyOp;       // concatenated over epochs (Epoch::keyOff)
@@ -87,7 +88,10 @@ struct PlanHost {
                                            // trajectory keys, so their pairs are read straight from the table (no ring, no row limit)
     std::vector<int> grpMaxFetch, grpMaxB;   // per bin group: most pair rows / most b doubles of one bin (sizes the pattern kernel's shared memory)
     std::vector<uint32_t> kLane, kElem;
-    long long maxEpochSlots = 0;           // largest number of live states in one epoch (stride of the b carry buffers)
+    long long maxEpochSlots = 0;           // largest number of live states in one epoch; after the bin images are built: stride
+                                           // of the b carry buffers = that (slot order) + the lane-ordered region behind it
+    long long dirOff = 0, dirSize = 0;     // lane-ordered region of the carry buffers (direct hand-over between pattern-mode epochs)
+    std::vector<int> grpDirIn;             // per bin group: 1 if its blocks read b in lane order (written by the previous epoch's lanes)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]
     std::vector<uint32_t> words, meta;

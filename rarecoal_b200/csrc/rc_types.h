@@ -110,6 +110,7 @@ struct RcPlanDev {
     const int* kFetchRows;       // pair offset inside a step row for every shared-memory pair row of a bin
     const uint16_t* kRowBase;    // [position in kBinPats][P] first shared-memory pair row of (pattern, branch)
     long long maxEpochSlots;     // stride (doubles per model) of the b carry buffers
+    long long dirOff;            // ... whose doubles [dirOff, maxEpochSlots) are the lane-ordered region (direct hand-over)
     // ---- row mode ----
     const int* epochMode;        // [nEpochs] 0: one state per thread; one row per thread with <= 3 (1) or <= RC_ROW_NO (2) other branches; one pattern per thread with <= RC_PAT_MAXT (3), <= RC_PAT_MAXS (4) or <= RC_PAT_MAXL (5) states
     const int* rowOff;           // [nEpochs][nPat+1] rows before a pattern
@@ -125,7 +126,11 @@ struct RcPlanDev {
 };
 
 // Bin header (ints): 0 first entry in kBinPats/kPatRec, 1 patterns, 2 lanes (states or rows), 3 b doubles (row mode, padded
-// rows), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first element record.
+// rows; pattern mode: | RC_HDR_DIRIN if the bin's b arrives in lane order at element index [7] - RcEpochDev::elBase of the
+// lane-ordered region), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first
+// element record.
+#define RC_HDR_DIRIN 0x40000000
+#define RC_PLANE_DIROUT 0x80000000u
 #define RC_HDR_N 8
 // Lane record (8 x u32).
 //   state mode: [0..1] pair row of component d (8 x u8; RC_KROWS-1 = the {1,0} padding pair)
@@ -143,6 +148,9 @@ struct RcPlanDev {
 //               [2] MA | MB << 4 | MC << 8 | MD << 12 | ME << 16 | number of m = 1 branches << 20
 //               [3] first slot of the pattern in the epoch  [4] pattern id  [5] first b double of the pattern in the bin
 //               [6..14] reference-order index of every state (36 x u8)
+//               Direct hand-over (bit 31 of [2]): the next event is a Join and the pattern's next bin reads b in lane order.
+//               The lane then applies the Join itself: [6..14] hold the next epoch's lane-local index of every state, bits
+//               24..29 of [2] the number of states there and [3] the first double of the pattern in the lane-ordered region.
 //   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row lane, 4 per pattern lane).
 // Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
 // and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
@@ -153,6 +161,7 @@ struct RcPlanDev {
 
 struct RcEpochDev {
     int nKeys, nThr, rowPairs, keyOff, thrOff;
+    int elBase;                  // first element record of the epoch
 };
 
 // Per (model, epoch): grid steps [beg, end) executed in that epoch and where its first step row starts in the
