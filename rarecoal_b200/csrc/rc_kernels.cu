@@ -1909,20 +1909,24 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    if (models[b].nSteps < 0 || models[b].mode != 1) return;
+    // every load of the first level (model header, bin header, epoch record) is issued before the first branch: a warp issues
+    // in order, so a branch on one of them would keep the others from starting until it has arrived
+    const int mSteps = models[b].nSteps, mMode = models[b].mode, mSShort = models[b].sShort, mMepOff = models[b].mepOff;
+    const int binIdx0 = binBase + (int)blockIdx.x;
+    const int4 hdrA = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + 2 * binIdx0);
+    const int4 hdrB = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + 2 * binIdx0 + 1);
+    const RcEpochDev epd = pl.ep[e];
+    if (mSteps < 0 || mMode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
     double* bb = reinterpret_cast<double*>(smemRaw);
     const unsigned sBase = rc_smem_base(smemRaw);
     const unsigned reSlot = (unsigned)ringRows * 16u;
-    const int binIdx = binBase + (int)blockIdx.x;
-    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
-    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
     const int np = hdrA.y, nB = hdrA.w & ~RC_HDR_DIRIN;
     const bool dirIn = (hdrA.w & RC_HDR_DIRIN) != 0;      // b arrives in lane order (the previous epoch's lanes applied the Join)
     if (np == 0) return;              // the unused header between two bin groups launched together
     const bool isLast = e + 1 == pl.nEpochs;
-    const int sShort = models[b].sShort;
-    const RcModelEpochDev mE = mep[models[b].mepOff + e];
+    const int sShort = mSShort;
+    const RcModelEpochDev mE = mep[mMepOff + e];
 
     RcPatRegs<MAXS> R;
 #pragma unroll
@@ -1932,7 +1936,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     R.dacc = 0.0;
     R.fmask = 0u;
     // ---- pair ring: every thread copies the pair rows tid, tid + RC_PBLOCK, ... of the bin ----
-    const int rowPairs = pl.ep[e].rowPairs;
+    const int rowPairs = epd.rowPairs;
     const long long strideD = (long long)rowPairs * 2;
     int fOff[RC_PFETCH];
 #pragma unroll
@@ -1974,16 +1978,14 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const double* bp = bPrev + (size_t)b * bStride;
         if (dirIn) {
             // direct hand-over: the bin's b is one contiguous run of the lane-ordered region
-            const double* src = bp + pl.dirOff + (hdrB.w - pl.ep[e].elBase);
-            constexpr int GU = 2 * RC_PAT_GU;
-            for (int i = tid; i < nB; i += GU * RC_PBLOCK) {
-                double v[GU];
+            // (all loads of a thread in flight at once: one round trip)
+            const double* src = bp + pl.dirOff + (hdrB.w - epd.elBase);
+            double v[MAXS];
 #pragma unroll
-                for (int u = 0; u < GU; ++u) v[u] = i + u * RC_PBLOCK < nB ? src[i + u * RC_PBLOCK] : 0.0;
+            for (int u = 0; u < MAXS; ++u) v[u] = tid + u * RC_PBLOCK < nB ? src[tid + u * RC_PBLOCK] : 0.0;
 #pragma unroll
-                for (int u = 0; u < GU; ++u)
-                    if (i + u * RC_PBLOCK < nB) bb[i + u * RC_PBLOCK] = v[u];
-            }
+            for (int u = 0; u < MAXS; ++u)
+                if (tid + u * RC_PBLOCK < nB) bb[tid + u * RC_PBLOCK] = v[u];
         } else if (e > 0 && sevs[models[b].sevOff + e - 1].type == RC_EV_JOIN_D) {
             // a Join: all weights are 1, twice as many states per batch
             constexpr int GU = 2 * RC_PAT_GU;
