@@ -480,6 +480,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     if ((rc = upload(ctx, pe, h.kPatRec, &d.kPatRec))) return rc;
     if ((rc = upload(ctx, pe, h.kLane, &d.kLane))) return rc;
     if ((rc = upload(ctx, pe, h.kElem, &d.kElem))) return rc;
+    if ((rc = upload(ctx, pe, h.kSegs, &d.kSegs))) return rc;
     d.maxEpochSlots = h.maxEpochSlots;
     d.dirOff = h.dirOff;
     if ((rc = upload(ctx, pe, h.epochMode, &d.epochMode))) return rc;

@@ -1146,8 +1146,8 @@ rc_propagate_keyed_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __
     const unsigned sBase = rc_smem_base(smemRaw);
     const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / lane records -> transition entries
-    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
-    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
+    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[(RC_HDR_N / 4) * binIdx];
+    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[(RC_HDR_N / 4) * binIdx + 1];
     const int pat0 = hdrA.x, np = hdrA.y, nSlots = hdrA.z;
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
@@ -1492,8 +1492,8 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
     const unsigned sBase = rc_smem_base(smemRaw);
     const int binIdx = binBase + (int)blockIdx.x;
     // bin image (rc_types.h): header -> pattern / row / element records -> transition entries
-    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx];
-    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[2 * binIdx + 1];
+    const int4 hdrA = reinterpret_cast<const int4*>(pl.kBinHdr)[(RC_HDR_N / 4) * binIdx];
+    const int4 hdrB = reinterpret_cast<const int4*>(pl.kBinHdr)[(RC_HDR_N / 4) * binIdx + 1];
     const int pat0 = hdrA.x, np = hdrA.y, nRows = hdrA.z, nB = hdrA.w;
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = models[b].sShort;
@@ -1748,6 +1748,32 @@ rc_propagate_rows_kernel(RcPlanDev pl, int e, int binBase, const RcModelDev* __r
 #define RC_PDEPTH 4
 #endif
 #define RC_PFETCH (RC_KROWS / RC_PBLOCK)
+// RC_PAT_TMA 0 (default): every thread copies up to RC_PFETCH pairs per grid step with cp.async.cg.  1: the ring is filled by
+// bulk copies (cp.async.bulk, one per segment of the bin and grid step, issued by the first lanes) that complete on one mbarrier
+// per slot.  Measured on C3 (44 models): 11.01 ms against 9.03 ms — UBLKCP takes its operands from uniform registers, so the
+// per-lane copies become a serial loop over the active lanes (ELECT, 5 x R2UR, UBLKCP per segment: profiles/
+// r02_tma_ring_waterfall.sass.txt), and a bin has 10 - 60 segments; the waiting on the slot's mbarrier adds a dependent ~90 cycles
+// per step.  Kept for reproduction: python tools/build_variant.py tma -DRC_PAT_TMA=1.
+#ifndef RC_PAT_TMA
+#define RC_PAT_TMA 0
+#endif
+__device__ __forceinline__ void rc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void rc_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // Shared memory of a pattern-mode block (dynamic, sized per bin group by the host): the pair ring, RC_PDEPTH slots of
 // `ringRows` pairs — [slot][row]{G, E2}, row 0 = {dt, 0} — and, aliased onto it, the b values of the bin gathered before the
 // ring starts (pattern after pattern).
@@ -1761,12 +1787,40 @@ struct RcPatRegs {
     bool direct;                  // block-uniform
     bool on, unit;
     double dacc;
+#if RC_PAT_TMA
+    const double* rowPtr;         // step row of the trajectory table the next fill reads (block-uniform)
+    unsigned segSrc, segDL;       // this lane's segment: first pair in a step row; first ring row | pair rows << 16 (0: none)
+    int nSeg;                     // segments of the bin (lanes beyond the 64th read theirs from shared memory)
+    unsigned stepBytes;           // bytes all segments bring in per grid step
+    unsigned mb0, segS;           // shared-memory addresses: the RC_PDEPTH mbarriers, the segment table
+    unsigned k;                   // grid steps consumed so far: slot k % RC_PDEPTH, mbarrier phase parity (k / RC_PDEPTH) & 1
+#else
     const double* fp[RC_PFETCH];  // this thread's pairs in the step row to be copied next
     unsigned fmask;               // bit q: the thread fetches pair row q * RC_PBLOCK + tid
+#endif
 };
 
 template <int MAXS>
 __device__ __forceinline__ unsigned rc_pat_row(const RcPatRegs<MAXS>& R, int q) { return (unsigned)(R.rows64 >> (8 * q)) & 0xFFu; }
+
+#if RC_PAT_TMA
+// one grid step's pairs into ring slot `idx`: thread 0 arms the slot's mbarrier with the byte count, the first lanes issue one
+// bulk copy per segment
+template <int MAXS>
+__device__ __forceinline__ void rc_pat_fill(RcPatRegs<MAXS>& R, const unsigned sBase, const unsigned idx, const unsigned RE_SLOT, const long long strideD) {
+    const unsigned bar = R.mb0 + idx * 8u, dst0 = sBase + idx * RE_SLOT;
+    if (threadIdx.x == 0) rc_mbar_expect_tx(bar, R.stepBytes);
+    if (R.segDL) rc_bulk_g2s(dst0 + (R.segDL & 0xFFFFu) * 16u, R.rowPtr + 2 * (size_t)R.segSrc, (R.segDL >> 16) * 16u, bar);
+    if (R.nSeg > RC_PBLOCK) {
+        for (int i = RC_PBLOCK + (int)threadIdx.x; i < R.nSeg; i += RC_PBLOCK) {
+            unsigned sg, dl;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sg), "=r"(dl) : "r"(R.segS + (unsigned)i * 8u));
+            rc_bulk_g2s(dst0 + (dl & 0xFFFFu) * 16u, R.rowPtr + 2 * (size_t)sg, (dl >> 16) * 16u, bar);
+        }
+    }
+    R.rowPtr += strideD;
+}
+#endif
 
 template <int MA, int MB, int MC, int MD, int ME, int MAXS>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
@@ -1795,11 +1849,17 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
             return;
         }
     }
+#if !RC_PAT_TMA
     const unsigned myRE = sBase + threadIdx.x * 16u;
+#endif
     const unsigned long long unitRows = R.rows64 >> (8 * (1 + NS));      // pair rows of the m = 1 branches, one byte each
     const unsigned aA = sBase + rc_pat_row(R, 0) * 16u, aB = sBase + rc_pat_row(R, 1) * 16u, aC = sBase + rc_pat_row(R, 2) * 16u,
                    aD = sBase + rc_pat_row(R, 3) * 16u, aE = sBase + rc_pat_row(R, 4) * 16u;
     for (; s < nextStop; ++s) {
+#if RC_PAT_TMA
+        rc_pat_fill(R, sBase, (R.k + RC_PDEPTH - 1) & (RC_PDEPTH - 1), RE_SLOT, strideD);      // the slot of step s - 1 is free again
+        const unsigned slot = (R.k & (RC_PDEPTH - 1)) * RE_SLOT;
+#else
         const unsigned prev = slot == 0 ? (RC_PDEPTH - 1) * RE_SLOT : slot - RE_SLOT;      // slot of step s - 1: free again
 #pragma unroll
         for (int q = 0; q < RC_PFETCH; ++q) {
@@ -1807,6 +1867,7 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
             R.fp[q] += strideD;
         }
         rc_cp_commit();
+#endif
         if (R.on) {
             double gB[MBp], eB[MBp], gC[MCp], eC[MCp], gD[MDp], eD[MDp], gE[MEp], eE[MEp];
             if (MB) {
@@ -1863,9 +1924,15 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
             }
             if (R.unit) R.dacc = fma(rc_lds64(sBase + slot + 8u), R.b[0], R.dacc);      // updateD, Core.hs:282-288
         }
+#if RC_PAT_TMA
+        ++R.k;
+        rc_mbar_wait(R.mb0 + (R.k & (RC_PDEPTH - 1)) * 8u, (R.k / RC_PDEPTH) & 1u);      // the pairs of the next step have landed
+        __syncthreads();       // ... and every thread is done with the slot the next fill overwrites
+#else
         rc_cp_wait<RC_PDEPTH - 2>();
         __syncthreads();       // (probe: with a warp-level sync here instead — results undefined — C3 ran 3.8 % faster: the barrier is not the bound)
         slot = slot + RE_SLOT == RC_PDEPTH * RE_SLOT ? 0u : slot + RE_SLOT;
+#endif
     }
 }
 
@@ -1913,8 +1980,9 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     // in order, so a branch on one of them would keep the others from starting until it has arrived
     const int mSteps = models[b].nSteps, mMode = models[b].mode, mSShort = models[b].sShort, mMepOff = models[b].mepOff;
     const int binIdx0 = binBase + (int)blockIdx.x;
-    const int4 hdrA = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + 2 * binIdx0);
-    const int4 hdrB = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + 2 * binIdx0 + 1);
+    const int4 hdrA = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0);
+    const int4 hdrB = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0 + 1);
+    const int4 hdrC = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0 + 2);      // x first segment, y segments, z bytes per step
     const RcEpochDev epd = pl.ep[e];
     if (mSteps < 0 || mMode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
@@ -1934,10 +2002,48 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     R.on = tid < np;
     R.unit = false;
     R.dacc = 0.0;
-    R.fmask = 0u;
-    // ---- pair ring: every thread copies the pair rows tid, tid + RC_PBLOCK, ... of the bin ----
     const int rowPairs = epd.rowPairs;
     const long long strideD = (long long)rowPairs * 2;
+    int s = mE.beg;
+    unsigned slot = 0;
+#if RC_PAT_TMA
+    // ---- pair ring: one bulk copy per segment of the bin and grid step, completing on the slot's mbarrier ----
+    __shared__ __align__(8) unsigned long long mbarS[RC_PDEPTH];
+    __shared__ uint2 segTab[RC_KROWS];
+    R.mb0 = rc_smem_base(mbarS);
+    R.segS = rc_smem_base(segTab);
+    R.nSeg = hdrC.y;
+    R.stepBytes = (unsigned)hdrC.z;
+    R.segSrc = 0u;
+    R.segDL = 0u;
+    R.k = 0u;
+    {
+        const uint2* segs = reinterpret_cast<const uint2*>(pl.kSegs) + hdrC.x;
+        if (tid < R.nSeg) { const uint2 sg = segs[tid]; R.segSrc = sg.x; R.segDL = sg.y; }
+        for (int i = RC_PBLOCK + tid; i < R.nSeg; i += RC_PBLOCK) segTab[i] = segs[i];
+        if (tid == 0) {
+#pragma unroll
+            for (int u = 0; u < RC_PDEPTH; ++u) rc_mbar_init(R.mb0 + (unsigned)u * 8u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    // (re)start: the RC_PDEPTH - 1 slots after the last one consumed; the generic-proxy accesses to these bytes (the gathered b)
+    // are ordered before the bulk copies by the fence
+    auto ring_start = [&]() {
+        R.rowPtr = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs) * 2;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < RC_PDEPTH - 1; ++u) rc_pat_fill(R, sBase, (R.k + (unsigned)u) & (RC_PDEPTH - 1), reSlot, strideD);
+    };
+    // all fills under way have landed (the loop waited for the first of them already); they count as consumed
+    auto ring_drain = [&]() {
+#pragma unroll
+        for (unsigned u = 1; u < RC_PDEPTH - 1; ++u) rc_mbar_wait(R.mb0 + ((R.k + u) & (RC_PDEPTH - 1)) * 8u, ((R.k + u) / RC_PDEPTH) & 1u);
+        R.k += RC_PDEPTH - 1;
+    };
+#else
+    // ---- pair ring: every thread copies the pair rows tid, tid + RC_PBLOCK, ... of the bin ----
+    R.fmask = 0u;
     int fOff[RC_PFETCH];
 #pragma unroll
     for (int q = 0; q < RC_PFETCH; ++q) {
@@ -1945,8 +2051,6 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         fOff[q] = 0;
         if (r < hdrB.y) { fOff[q] = pl.kFetchRows[hdrB.x + r]; R.fmask |= 1u << q; }
     }
-    int s = mE.beg;
-    unsigned slot = 0;
     auto ring_start = [&]() {
 #pragma unroll
         for (int q = 0; q < RC_PFETCH; ++q) R.fp[q] = ktab + (mE.tabBase + (long long)(s - mE.beg) * rowPairs + fOff[q]) * 2;
@@ -1961,6 +2065,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         }
         slot = 0;
     };
+#endif
     // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory (the ring starts
     //      afterwards: it lives in the same bytes; starting it before the gather, in bytes of its own, keeps the fetch
     //      pointers live across the gather and measured slower — spills, 9.96 -> 10.26 ms on C3) ----
@@ -2050,7 +2155,11 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         if (isLast && sShort >= s && phase == 0) nextStop = min(nextStop, sShort);
         if (s < nextStop) {
             ring_start();
+#if RC_PAT_TMA
+            rc_mbar_wait(R.mb0 + (R.k & (RC_PDEPTH - 1)) * 8u, (R.k / RC_PDEPTH) & 1u);
+#else
             rc_cp_wait<RC_PDEPTH - 2>();
+#endif
             __syncthreads();
 #define RC_PAT_SHAPE(code, B, C, D, E) \
     case code: rc_pat_dispatch_a<B, C, D, E>(R, sBase, strideD, s, nextStop, slot, reSlot, MAw); break;
@@ -2064,7 +2173,11 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
             }
 #undef RC_PAT_SHAPE
             static_assert(RC_PAT_MAXS == 25 && RC_PAT_MAXL == 36, "shape list above");
+#if RC_PAT_TMA
+            ring_drain();
+#else
             rc_cp_wait<0>();
+#endif
             __syncthreads();
         }
         if (!parked) dp = dp + R.dacc;                                           // updateD contributions of the run

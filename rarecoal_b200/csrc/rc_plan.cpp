@@ -575,6 +575,9 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             hdr[5] = out.kFetchOff[(size_t)bI + 1] - out.kFetchOff[(size_t)bI];
             hdr[6] = (int)(out.kLane.size() / 4);
             hdr[7] = (int)(out.kElem.size() / 2);
+            hdr[8] = out.binSegOff[(size_t)bI];
+            hdr[9] = out.binSegCnt[(size_t)bI];
+            hdr[10] = out.binSegBytes[(size_t)bI];
             int lanes = 0, bOff = 0;
             for (int q = p0; q < p1; ++q) {
                 const int i = out.kBinPats[(size_t)q];
@@ -990,7 +993,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 int mj = out.keyMaxJ[(size_t)E.keyOff + q];
                 out.keyThrBase.push_back((int)out.thrKey.size() - E.thrOff);
                 out.keyPairBase.push_back(pairs);
-                pairs += mj;
+                pairs += rc_pair_stride(mj);        // odd stride: see rc_types.h (RC_HDR_N)
                 for (int t = 0; t < std::max(1, mj); ++t) out.thrKey.push_back(q);
             }
             E.nThr = (int)out.thrKey.size() - E.thrOff;
@@ -1094,7 +1097,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
                         auto it = ob.keyRows[(size_t)q].find(key);
                         int have = it == ob.keyRows[(size_t)q].end() ? 0 : it->second;
-                        if (mxk > have) add[(size_t)q] += mxk - have;
+                        if (mxk > have) add[(size_t)q] += patMode ? rc_pair_stride(mxk) - rc_pair_stride(have) : mxk - have;
                     }
                     if (!packDirect && ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
                     // (pair rows without de-duplication: a limit of the self-contained kernel's rate table only)
@@ -1107,7 +1110,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         if (!mxk) continue;
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
                         int& have = ob.keyRows[(size_t)q][key];
-                        if (mxk > have) { ob.rowsUsed[(size_t)q] += mxk - have; have = mxk; }
+                        if (mxk > have) { ob.rowsUsed[(size_t)q] += patMode ? rc_pair_stride(mxk) - rc_pair_stride(have) : mxk - have; have = mxk; }
                     }
                     ob.rowsSelf[(size_t)q] += addSelf[(size_t)q];
                     ob.slotsE[(size_t)q] += lanesOf(pp, e);
@@ -1192,22 +1195,40 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     }
                 }
                 fRows.push_back(0);                 // smem pair row 0 <- {dt, 0}
-                // Pattern mode: the lanes of a quarter warp read the pairs {G, E2} of eight consecutive keys with one LDS.128
-                // (row j of each key at the same time).  A key of even length puts every second or fourth of them on the same
-                // 16-byte bank group: keys of two or more rows are padded to an odd stride when the bin's ring has room.
-                bool padBin = false;
-                if (pad) {
-                    int rowsPadded = 1;
-                    for (int key : keyOrder) { const int n = rowsOf[key]; rowsPadded += n >= 2 ? (n | 1) : n; }
-                    padBin = rowsPadded <= RC_KROWS - 1;
-                }
                 int row = 1;
-                for (int key : keyOrder) {
-                    startOf[key] = row;
-                    int n = rowsOf[key];
-                    for (int j = 0; j < n; ++j) fRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
-                    row += n;
-                    if (padBin && n >= 2 && !(n & 1)) { fRows.push_back(0); ++row; }
+                if (pad) {
+                    // Pattern mode: ring rows in table order, every key with its (odd) table stride — the lanes of a quarter warp
+                    // read the pairs of eight consecutive keys with one LDS.128 without bank conflicts, and what is contiguous in
+                    // the table is contiguous in the ring: the bin's segments, one bulk copy each per grid step
+                    std::sort(keyOrder.begin(), keyOrder.end(), [&](int a, int b) {
+                        return out.keyPairBase[(size_t)E.keyOff + a] < out.keyPairBase[(size_t)E.keyOff + b];
+                    });
+                    out.binSegOff[(size_t)bI] = (int)(out.kSegs.size() / 2);
+                    int segSrc = 0, segDst = 0, segLen = 1, nSeg = 0, bytes = 0;      // row 0 = pair 0 of the step row
+                    auto close = [&]() {
+                        out.kSegs.push_back((uint32_t)segSrc);
+                        out.kSegs.push_back((uint32_t)segDst | ((uint32_t)segLen << 16));
+                        ++nSeg;
+                        bytes += segLen * 16;
+                    };
+                    for (int key : keyOrder) {
+                        startOf[key] = row;
+                        const int n = rowsOf[key], st = rc_pair_stride(n), src = out.keyPairBase[(size_t)E.keyOff + key];
+                        for (int j = 0; j < st; ++j) fRows.push_back(src + j);
+                        if (src == segSrc + segLen) segLen += st;
+                        else { close(); segSrc = src; segDst = row; segLen = st; }
+                        row += st;
+                    }
+                    close();
+                    out.binSegCnt[(size_t)bI] = nSeg;
+                    out.binSegBytes[(size_t)bI] = bytes;
+                } else {
+                    for (int key : keyOrder) {
+                        startOf[key] = row;
+                        int n = rowsOf[key];
+                        for (int j = 0; j < n; ++j) fRows.push_back(out.keyPairBase[(size_t)E.keyOff + key] + j);
+                        row += n;
+                    }
                 }
                 for (int q = patOff[(size_t)bI]; q < patOff[(size_t)bI + 1]; ++q) {
                     int i = pats[(size_t)q];
@@ -1390,15 +1411,18 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         }
         lap("per-epoch bins");
         out.kRowBase.assign(out.kBinPats.size() * (size_t)P, 0xFFFF);
+        out.kSegs.clear();
+        out.binSegOff.assign(out.kBinPatOff.size(), 0);
+        out.binSegCnt.assign(out.kBinPatOff.size(), 0);
+        out.binSegBytes.assign(out.kBinPatOff.size(), 0);
         for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
             const int e = v / RC_NGROUP, b0 = out.kBinBase[(size_t)v];
             // fetch offsets are stored at the same index as the bin offsets (one extra entry per group)
             std::vector<int> fOff;
             if (out.grpDirect[(size_t)v]) fOff.assign((size_t)out.nKBins[(size_t)v], (int)out.kFetchRows.size());     // nothing to fetch
             else {
-                static const bool padEnv = std::getenv("RC_PAT_PAD") ? std::atoi(std::getenv("RC_PAT_PAD")) != 0 : true;
                 fetch_lists(e, out.kBinPatOff, out.kBinPats, b0, b0 + out.nKBins[(size_t)v], fOff, out.kFetchRows, out.kRowBase, 0,
-                            padEnv && out.epochMode[(size_t)v] >= RC_MODE_PAT);
+                            out.epochMode[(size_t)v] >= RC_MODE_PAT);
             }
             fOff.push_back((int)out.kFetchRows.size());
             out.kFetchOff.insert(out.kFetchOff.end(), fOff.begin(), fOff.end());
@@ -1647,6 +1671,23 @@ std::string check_plan(const PlanHost& h) {
                     return fail("image header direct hand-over");
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
+                if (patM && !directG) {
+                    // the segments cover the ring rows of the bin exactly once and agree with the fetch list row by row
+                    if (hdr[8] < 0 || hdr[9] < 1 || (size_t)(hdr[8] + hdr[9]) * 2 > h.kSegs.size()) return fail("image segments range");
+                    std::vector<char> cov((size_t)nFetch, 0);
+                    int bytes = 0;
+                    for (int q = hdr[8]; q < hdr[8] + hdr[9]; ++q) {
+                        const int src = (int)h.kSegs[(size_t)q * 2], dst = (int)(h.kSegs[(size_t)q * 2 + 1] & 0xFFFFu), len = (int)(h.kSegs[(size_t)q * 2 + 1] >> 16);
+                        if (len < 1 || dst + len > nFetch || src < 0 || src + len > h.ep[(size_t)e].rowPairs) return fail("image segment bounds");
+                        for (int j = 0; j < len; ++j) {
+                            if (cov[(size_t)(dst + j)] || h.kFetchRows[(size_t)(hdr[4] + dst + j)] != src + j) return fail("image segment rows");
+                            cov[(size_t)(dst + j)] = 1;
+                        }
+                        bytes += len * 16;
+                    }
+                    for (int r = 0; r < nFetch; ++r) if (!cov[(size_t)r]) return fail("image segment cover");
+                    if (bytes != hdr[10]) return fail("image segment bytes");
+                }
                 if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * patMax : RC_ROW_BCAP))
                     return fail("image header lanes");
                 if (hdr[6] < 0 || hdr[6] + (long long)lanes * (patM ? RC_PLANE_N / 4 : rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)

@@ -88,6 +88,8 @@ struct PlanHost {
                                            // trajectory keys, so their pairs are read straight from the table (no ring, no row limit)
     std::vector<int> grpMaxFetch, grpMaxB;   // per bin group: most pair rows / most b doubles of one bin (sizes the pattern kernel's shared memory)
     std::vector<uint32_t> kLane, kElem;
+    std::vector<uint32_t> kSegs;           // ring segments of the pattern-mode bins, 2 words each
+    std::vector<int> binSegOff, binSegCnt, binSegBytes;   // per bin (same indexing as kBinPatOff): its segments / bytes per grid step
     long long maxEpochSlots = 0;           // largest number of live states in one epoch; after the bin images are built: stride
                                            // of the b carry buffers = that (slot order) + the lane-ordered region behind it
     long long dirOff = 0, dirSize = 0;     // lane-ordered region of the carry buffers (direct hand-over between pattern-mode epochs)

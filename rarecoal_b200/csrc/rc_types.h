@@ -123,6 +123,7 @@ struct RcPlanDev {
     const int* kPatRec;          // [position in kBinPats][2]: pattern id, first lane | first b double << 16
     const uint32_t* kLane;       // lane records, RC_LANE_N (state mode) or RC_RLANE_N (row mode) words each
     const uint32_t* kElem;       // [element][2], row mode: gather record of every b double of a bin
+    const uint32_t* kSegs;       // [segment][2], pattern mode: runs of pairs a bin copies per grid step (RC_HDR_N comment)
 };
 
 // Bin header (ints): 0 first entry in kBinPats/kPatRec, 1 patterns, 2 lanes (states or rows), 3 b doubles (row mode, padded
@@ -131,7 +132,13 @@ struct RcPlanDev {
 // element record.
 #define RC_HDR_DIRIN 0x40000000
 #define RC_PLANE_DIROUT 0x80000000u
-#define RC_HDR_N 8
+#define RC_HDR_N 12
+// Pattern mode, further header ints: 8 first ring segment of the bin in kSegs, 9 segments, 10 bytes they bring in per grid step.
+// A segment (2 x u32: first pair inside a step row of the trajectory table; first ring row | pair rows << 16) is a run of
+// pairs that is contiguous both in the table and in the ring: one bulk copy per segment and grid step fills a ring slot.
+// To make the runs long, a key's pairs are stored with the same odd stride in the table and in the ring and the ring rows of a
+// bin are sorted by their place in the table.
+static inline __host__ __device__ int rc_pair_stride(int n) { return (n >= 2 && !(n & 1)) ? n + 1 : n; }
 // Lane record (8 x u32).
 //   state mode: [0..1] pair row of component d (8 x u8; RC_KROWS-1 = the {1,0} padding pair)
 //               [2..3] lane of the neighbour x + e_k (8 x u8; own lane = no such state)
