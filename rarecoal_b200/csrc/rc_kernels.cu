@@ -1785,6 +1785,7 @@ struct RcPatRegs {
     const double* dptr;           // direct bins (no ring): the pattern's first pair in the step row to be read next, else null
     int dPairBase;                // ... and its pair index inside the step row (pair 0 of the row is {dt, 0})
     bool direct;                  // block-uniform
+    bool anyU;                    // block-uniform: some pattern of the bin has a branch with m = 1
     bool on, unit;
     double dacc;
 #if RC_PAT_TMA
@@ -1822,7 +1823,7 @@ __device__ __forceinline__ void rc_pat_fill(RcPatRegs<MAXS>& R, const unsigned s
 }
 #endif
 
-template <int MA, int MB, int MC, int MD, int ME, int MAXS>
+template <int MA, int MB, int MC, int MD, int ME, bool HASU, int MAXS>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                            unsigned& slot, const unsigned RE_SLOT) {
     constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1, MEp = ME ? ME : 1;
@@ -1888,16 +1889,20 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
             }
             // branches with m = 1 contribute G_k(1) only.  Every lane multiplies all 7 - NS slots: a spare slot points at pair
             // row 0, whose first half is 1.0 — no predicates, no constants to materialise, a balanced product
-            // (skipping the loads with one uniform branch in bins without any such branch measured slower: 10.21 against 10.13 ms)
-            double g[7];
+            // A bin without any such branch (HASU false: the last epochs of a tree) runs a loop of its own without these loads
+            // and products (a uniform branch around them inside one loop measured slower: 10.21 against 10.13 ms)
+            double D1 = 1.0;
+            if constexpr (HASU) {
+                double g[7];
 #pragma unroll
-            for (int u = 0; u < 7 - NS; ++u) g[u] = rc_lds64(sBase + slot + ((unsigned)(unitRows >> (8 * u)) & 0xFFu) * 16u);
-            const double D1 = ((g[0] * g[1]) * (g[2] * (NS < 4 ? g[3] : 1.0))) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
+                for (int u = 0; u < 7 - NS; ++u) g[u] = rc_lds64(sBase + slot + ((unsigned)(unitRows >> (8 * u)) & 0xFFu) * 16u);
+                D1 = ((g[0] * g[1]) * (g[2] * (NS < 4 ? g[3] : 1.0))) * ((NS < 3 ? g[4] : 1.0) * (NS < 2 ? g[5] : 1.0) * (NS < 1 ? g[6] : 1.0));
+            }
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
                 double gA, eA;
                 rc_lds128(aA + slot + (unsigned)i * 16u, gA, eA);
-                const double dA = D1 * gA;
+                const double dA = HASU ? D1 * gA : gA;
 #pragma unroll
                 for (int j = 0; j < MBp; ++j) {
                     const double dB = MB ? dA * gB[j] : dA;
@@ -1946,7 +1951,8 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsi
 #define RC_PAT_CASE(A)                                                                                         \
     case A:                                                                                                    \
         if constexpr (A >= MB && A * SA <= MAXS && (MAXS <= RC_PAT_MAXS || A * SA > RC_PAT_MAXS)) {            \
-            rc_pat_run<A, MB, MC, MD, ME>(R, sBase, strideD, s, nextStop, slot, reSlot);                       \
+            if (R.anyU) rc_pat_run<A, MB, MC, MD, ME, true>(R, sBase, strideD, s, nextStop, slot, reSlot);    \
+            else rc_pat_run<A, MB, MC, MD, ME, false>(R, sBase, strideD, s, nextStop, slot, reSlot);           \
         }                                                                                                      \
         break;
     switch (MA) {
@@ -2142,6 +2148,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     __syncthreads();
     const unsigned shapeB = shapeS & 0xFFFFFu;
     R.nU = (int)((la.z >> 20) & 0xFu);
+    R.anyU = __syncthreads_or(R.on && R.nU > 0) != 0;
 
     R.unit = R.on && (shapeB >> 4) == 0 && R.nU == 0;        // x = e_A is the first state of a single-branch pattern
     const int MAw = (int)(shapeB & 0xFu);
