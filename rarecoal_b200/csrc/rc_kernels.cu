@@ -1995,8 +1995,9 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     double* bb = reinterpret_cast<double*>(smemRaw);
     const unsigned sBase = rc_smem_base(smemRaw);
     const unsigned reSlot = (unsigned)ringRows * 16u;
-    const int np = hdrA.y, nB = hdrA.w & ~RC_HDR_DIRIN;
+    const int np = hdrA.y, nB = RC_HDR_NB(hdrA.w);
     const bool dirIn = (hdrA.w & RC_HDR_DIRIN) != 0;      // b arrives in lane order (the previous epoch's lanes applied the Join)
+    const bool seedIn = (hdrA.w & RC_HDR_SEED) != 0;      // first epoch: b = 1 at the pattern itself, the lane's last state
     if (np == 0) return;              // the unused header between two bin groups launched together
     const bool isLast = e + 1 == pl.nEpochs;
     const int sShort = mSShort;
@@ -2087,7 +2088,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        if (dirIn) {
+        if (seedIn) {
+        } else if (dirIn) {
             // direct hand-over: the bin's b is one contiguous run of the lane-ordered region
             // (all loads of a thread in flight at once: one round trip)
             const double* src = bp + pl.dirOff + (hdrB.w - epd.elBase);
@@ -2138,9 +2140,14 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     __syncthreads();
     if (R.on) {
         const double* mine = bb + lb.y;
+        if (seedIn) {
 #pragma unroll
-        for (int x = 0; x < MAXS; ++x)
-            if (x < n) R.b[x] = mine[x];
+            for (int x = 0; x < MAXS; ++x) R.b[x] = x == n - 1 ? 1.0 : 0.0;       // Core.hs:60-66
+        } else {
+#pragma unroll
+            for (int x = 0; x < MAXS; ++x)
+                if (x < n) R.b[x] = mine[x];
+        }
     }
     // the block's shape and number of unit branches: bins hold one class
     __shared__ unsigned shapeS;

@@ -723,6 +723,18 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             }
             hdr[2] = lanes;
             hdr[3] = bOff;
+            if (patM && e == 0) {
+                // the seed state m is the last one in the lane's own order too (all coordinates at their maximum)
+                bool seedLast = true;
+                size_t el0 = (size_t)hdr[7] * 2;
+                for (int q = p0; q < p1 && seedLast; ++q) {
+                    const int live = so[out.kBinPats[(size_t)q] + 1] - so[out.kBinPats[(size_t)q]];
+                    for (int x = 0; x < live; ++x)
+                        if ((out.kElem[el0 + (size_t)x * 2] == RC_IMG_SEED) != (x == live - 1)) seedLast = false;
+                    el0 += (size_t)live * 2;
+                }
+                if (seedLast) hdr[3] |= RC_HDR_SEED;
+            }
             out.grpMaxFetch[(size_t)v] = std::max(out.grpMaxFetch[(size_t)v], hdr[5]);
             out.grpMaxB[(size_t)v] = std::max(out.grpMaxB[(size_t)v], bOff);
         }
@@ -1337,8 +1349,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     int M[5];
                     for (int q = 0; q < 5; ++q) M[q] = (int)((sh >> (4 * q)) & 0xFu);
                     long long pre = M[0], states = M[0];
+                    // (counted for the patterns that have such branches; a bin that mixes both kinds executes them for all)
                     n += nU ? 6 - nS : 0;
-                    n += pre;                                               // dA = D1 * gA
+                    n += nU ? pre : 0;                                      // dA = D1 * gA
                     for (int q = 1; q <= nS; ++q) { pre *= M[q]; n += pre; states *= M[q]; }
                     n += states;                                            // b = fma(b, d, t2)
                     for (int q = 0; q <= nS; ++q) n += states / M[q] * (M[q] - 1);   // neighbours along each shaped branch
@@ -1664,7 +1677,8 @@ std::string check_plan(const PlanHost& h) {
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int* hdr = &h.kBinHdr[(size_t)bI * RC_HDR_N];
-                const int np = hdr[1], lanes = hdr[2], nB = hdr[3] & ~RC_HDR_DIRIN, nFetch = hdr[5];
+                const int np = hdr[1], lanes = hdr[2], nB = RC_HDR_NB(hdr[3]), nFetch = hdr[5];
+                if ((hdr[3] & RC_HDR_SEED) && (!patM || e != 0)) return fail("image header seed flag");
                 const bool dirIn = (hdr[3] & RC_HDR_DIRIN) != 0;
                 if (dirIn && (!patM || e == 0 || h.grpDirIn.empty() || !h.grpDirIn[(size_t)v] ||
                               hdr[7] - h.ep[(size_t)e].elBase < 0 || hdr[7] - h.ep[(size_t)e].elBase + nB > h.dirSize))

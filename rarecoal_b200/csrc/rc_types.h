@@ -131,6 +131,8 @@ struct RcPlanDev {
 // lane-ordered region), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first
 // element record.
 #define RC_HDR_DIRIN 0x40000000
+#define RC_HDR_SEED 0x20000000      // first epoch, pattern mode: b is 1 at the last state of every lane (the pattern itself), else 0
+#define RC_HDR_NB(x) ((x) & 0x1FFFFFFF)
 #define RC_PLANE_DIROUT 0x80000000u
 #define RC_HDR_N 12
 // Pattern mode, further header ints: 8 first ring segment of the bin in kSegs, 9 segments, 10 bytes they bring in per grid step.
