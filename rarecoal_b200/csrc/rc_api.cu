@@ -171,7 +171,8 @@ struct rc_ctx {
     long long planMisses = 0, planEvictions = 0, planMissesAtCall = 0, planEvictionsAtCall = 0;
     double planBuildMs = 0.0, planBuildMsAtCall = 0.0;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch;
+    int optBigSmemKB = 0;             // > 0: shared-memory budget of the big tier (tests: forces the global-memory mode)
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
@@ -444,7 +445,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     std::memset(&d, 0, sizeof d);
     const rc::PlanHost& h = pe->h;
     d.P = h.P; d.maxAf = h.maxAf; d.A1 = h.maxAf + 1; d.nPat = h.nPat; d.nEpochs = h.nEpochs; d.nnzw = h.nnzw;
-    d.nBins = h.nBins; d.nBinsKB = h.nBinsKB; d.cap = h.cap; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
+    d.nBins = h.nBins; d.nBinsKB = h.nBinsKB; d.cap = h.cap; d.bigGlobal = h.bigGlobal; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
     int rc;
     if ((rc = upload(ctx, pe, h.fBinPatOff, &d.fBinPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
@@ -543,7 +544,8 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     const auto t0 = std::chrono::steady_clock::now();
     PlanEntry* pe = new PlanEntry();
     std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
-                                   mh.hasSplit, ctx->smemOptin, pe->h, ctx->optPattern);
+                                   mh.hasSplit, ctx->optBigSmemKB > 0 ? std::min(ctx->smemOptin, ctx->optBigSmemKB * 1024) : ctx->smemOptin, pe->h,
+                                   ctx->optPattern);
     if (!e.empty()) {
         delete pe;
         ctx->err = e;
@@ -831,10 +833,23 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
         // b carried from one epoch's launch to the next (two buffers) and the per-pattern updateD accumulators
         size_t needC = (size_t)std::max<long long>(2 * carrySlots * B, 1) * sizeof(double);
+        // global-memory mode of the big tier: one slice per block, at most 4 GiB (the launch is cut into model ranges beyond that)
+        size_t needBig = 0;
+        for (int pos = 0; pos < B;) {
+            const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
+            int end = pos + 1;
+            while (end < B && mhs[(size_t)order[(size_t)end]].plan == pe) ++end;
+            if (pe && pe->d.bigGlobal && pe->d.nBins > 0) {
+                const size_t per = rc_big_scratch_bytes(pe->d.cap, pe->d.nnzw) * (size_t)pe->d.nBins;
+                needBig = std::max(needBig, std::max(per, std::min(per * (size_t)(end - pos), (size_t)4 << 30)));
+            }
+            pos = end;
+        }
         if (needTab > ctx->dTab.cap || needOut > ctx->dPOut.cap || needK > ctx->dKTab.cap || needA > ctx->dAEnd.cap ||
             needS > ctx->dAShort.cap || needC > ctx->dBCarry.cap || needOut > ctx->dDAcc.cap)
             CK(cudaStreamSynchronize(st));
         CK(ctx->dBCarry.ensure(needC));
+        if (needBig > ctx->dBigScratch.cap) { CK(cudaStreamSynchronize(st)); CK(ctx->dBigScratch.ensure(needBig)); }
         CK(ctx->dDAcc.ensure(needOut));
         CK(ctx->dTab.ensure(needTab));
         CK(ctx->dPOut.ensure(needOut));
@@ -963,7 +978,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     ++launches;
                 }
                 if (pe->d.nBins > 0 && (anySelf || pe->d.nBins > pe->d.nBinsKB)) {
-                    CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos, st));
+                    CK(rc_launch_propagate(pe->d, dM, dSev, (const double*)ctx->dTab.p, dW, (double*)ctx->dPOut.p, pos, end - pos,
+                                           (unsigned char*)ctx->dBigScratch.p, ctx->dBigScratch.cap, st));
                     ++launches;
                 }
             }
@@ -981,10 +997,10 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         std::string key;
         auto put = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
         auto putv = [&](long long v) { put(&v, sizeof v); };
-        putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat);
+        putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat); putv((long long)ctx->dBigScratch.cap);
         const void* ptrs[] = {db + oModels, db + oSev, db + oMep, db + oW, db + oSizeOff, db + oMaskOff, db + oMasks, db + oSizes,
                               ctx->dTab.p, ctx->dPOut.p, ctx->dKTab.p, ctx->dAEnd.p, ctx->dAShort.p, ctx->dBCarry.p, ctx->dDAcc.p,
-                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p};
+                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p};
         put(ptrs, sizeof ptrs);
         for (int pos = 0; pos < B;) {
             const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
@@ -1234,7 +1250,7 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
-                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc};
+                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();
@@ -1488,6 +1504,9 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
     else if (n == "plan_cache_max") ctx->optPlanCacheMax = std::max(1, (int)value);
     else if (n == "plan_cache_mb") ctx->optPlanCacheMB = std::max(1.0, value);
     else if (n == "ktab_model_mb") { ctx->optKtabModelMB = value; ctx->chunkHint = 256; }
+    else if (n == "big_smem_kb") {
+        if ((int)value != ctx->optBigSmemKB) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->clear_plans(); ctx->optBigSmemKB = (int)value; }
+    }
     else if (n == "ktab_total_mb") { ctx->optKtabTotalMB = value; ctx->chunkHint = 256; }
     else { ctx->err = "rc_set_option: unknown option " + n; return RC_ERR_ARG; }
     return RC_OK;

@@ -174,26 +174,44 @@ struct RcSmem {
     unsigned short* owner;
 };
 
-__device__ __forceinline__ RcSmem rc_carve(unsigned char* base, int cap, int nnzw, int P, int rowLen) {
+// big: per-slot arrays of a block whose live sets do not fit shared memory (global scratch, rc_big_scratch_bytes per block);
+// null: everything in shared memory
+__device__ __forceinline__ RcSmem rc_carve(unsigned char* base, int cap, int nnzw, int P, int rowLen, unsigned char* big) {
     RcSmem S;
     double* d = reinterpret_cast<double*>(base);
-    S.bA = d; d += cap;
-    S.bB = d; d += cap;
-    S.dacc = d; d += cap;
+    if (big) {
+        double* g = reinterpret_cast<double*>(big);
+        S.bA = g; g += cap;
+        S.bB = g; g += cap;
+        S.dacc = g; g += cap;
+        uint32_t* gu = reinterpret_cast<uint32_t*>(g);
+        S.words = gu; gu += (size_t)cap * nnzw;
+        S.meta = gu; gu += cap;
+        S.owner = reinterpret_cast<unsigned short*>(gu);
+        cap = 0;
+    } else {
+        S.bA = d; d += cap;
+        S.bB = d; d += cap;
+        S.dacc = d; d += cap;
+    }
     S.a = d; d += RC_NPB * P;
     S.r = d; d += RC_NPB * P;
     S.dpat = d; d += RC_NPB;
     S.tab = d; d += rowLen;
     uint32_t* u = reinterpret_cast<uint32_t*>(d);
-    S.words = u; u += (size_t)cap * nnzw;
-    S.meta = u; u += cap;
+    if (!big) { S.words = u; u += (size_t)cap * nnzw; S.meta = u; u += cap; }
     int* ip = reinterpret_cast<int*>(u);
     S.patOff = ip; ip += RC_NPB + 1;
     S.patOff2 = ip; ip += RC_NPB + 1;
     S.patId = ip; ip += RC_NPB;
     S.patDone = ip; ip += RC_NPB;
-    S.owner = reinterpret_cast<unsigned short*>(ip);
+    if (!big) S.owner = reinterpret_cast<unsigned short*>(ip);
     return S;
+}
+
+size_t rc_big_scratch_bytes(int cap, int nnzw) {
+    size_t n = (size_t)3 * cap * sizeof(double) + ((size_t)cap * nnzw + cap) * sizeof(uint32_t) + (size_t)cap * sizeof(unsigned short);
+    return (n + 255) & ~(size_t)255;
 }
 
 size_t rc_propagate_smem_bytes(int cap, int nnzw, int P, int rowLen) {
@@ -210,7 +228,7 @@ size_t rc_propagate_smem_bytes(int cap, int nnzw, int P, int rowLen) {
 __global__ void __launch_bounds__(RC_BLOCK)
 rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const RcSEvDev* __restrict__ sevs,
                     const double* __restrict__ tab, const double* __restrict__ wpool,
-                    double* __restrict__ pOut) {
+                    double* __restrict__ pOut, unsigned char* scratch, long long scratchPerBlock) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int bin = blockIdx.x, b = blockIdx.y;
@@ -219,7 +237,11 @@ rc_propagate_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, const R
     if (M.mode == 1 && bin < pl.nBinsKB) return;   // these patterns run in row mode on the trajectory-key tier for this model
     const int P = pl.P, A1 = pl.A1, nnzw = pl.nnzw, nPat = pl.nPat, cap = pl.cap;
     const int rowLen = rc_row_len(P, A1);
-    RcSmem S = rc_carve(smemRaw, pl.cap, nnzw, P, rowLen);
+    // live sets beyond the shared-memory tier (pl.bigGlobal): b, the structure words and the accumulators of the block live in
+    // its slice of a global scratch buffer (same code, L1 / L2 instead of shared memory; the reference's dense vectors take any
+    // size, Core.hs:58-70)
+    RcSmem S = rc_carve(smemRaw, pl.cap, nnzw, P, rowLen,
+                        scratch ? scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)scratchPerBlock : nullptr);
     const double* PR = S.tab + RC_ROW_PAIRS;   // pairs: (k,0) = {EA, invN}, (k,j) = {CN, E2}
     const int dtIdx = 0;
 
@@ -2348,14 +2370,28 @@ cudaError_t rc_launch_tables(const RcModelDev* models, const RcSizeStepDev* size
 
 cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
                                 const double* tab, const double* wpool, double* pOut, int b0, int nB,
-                                cudaStream_t st) {
+                                unsigned char* scratch, size_t scratchBytes, cudaStream_t st) {
     if (pl.nBins <= 0 || nB <= 0) return cudaSuccess;
-    size_t smem = rc_propagate_smem_bytes(pl.cap, pl.nnzw, pl.P, rc_row_len(pl.P, pl.A1));
+    size_t smem = rc_propagate_smem_bytes(pl.bigGlobal ? 0 : pl.cap, pl.nnzw, pl.P, rc_row_len(pl.P, pl.A1));
     cudaError_t e = rc_ensure_smem((const void*)rc_propagate_kernel, smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)pl.nBins, (unsigned)nB);
-    rc_propagate_kernel<<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, sevs, tab, wpool, pOut + (size_t)b0 * pl.nPat);
-    return cudaGetLastError();
+    if (!pl.bigGlobal) {
+        dim3 grid((unsigned)pl.nBins, (unsigned)nB);
+        rc_propagate_kernel<<<grid, RC_BLOCK, smem, st>>>(pl, models + b0, sevs, tab, wpool, pOut + (size_t)b0 * pl.nPat, nullptr, 0);
+        return cudaGetLastError();
+    }
+    // global-memory tier: as many models per launch as the scratch buffer holds
+    const size_t per = rc_big_scratch_bytes(pl.cap, pl.nnzw);
+    const int slice = (int)std::min<size_t>((size_t)nB, scratchBytes / (per * (size_t)pl.nBins));
+    if (slice < 1) return cudaErrorMemoryAllocation;
+    for (int m0 = 0; m0 < nB; m0 += slice) {
+        dim3 grid((unsigned)pl.nBins, (unsigned)std::min(slice, nB - m0));
+        rc_propagate_kernel<<<grid, RC_BLOCK, smem, st>>>(pl, models + b0 + m0, sevs, tab, wpool, pOut + (size_t)(b0 + m0) * pl.nPat,
+                                                         scratch, (long long)per);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }
 
 template <int NNZ, int BLOCK>

@@ -11,7 +11,8 @@ cudaError_t rc_launch_tables(const RcModelDev* models, const RcSizeStepDev* size
                              const int* maskOff, const double* dts, double* tab, int P, int A1, int rowsMax, int B, cudaStream_t st);
 cudaError_t rc_launch_propagate(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
                                 const double* tab, const double* wpool, double* pOut, int b0, int nB,
-                                cudaStream_t st);
+                                unsigned char* scratch, size_t scratchBytes, cudaStream_t st);
+size_t rc_big_scratch_bytes(int cap, int nnzw);
 cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* models, const RcSEvDev* sevs,
                                      const double* tab, const double* wpool, double* pOut, int b0, int nB,
                                      cudaStream_t st);

@@ -900,8 +900,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     // bytes per slot in the big-tier kernel: 2 b buffers + d accumulator (24) + words (4*nnzw) + meta (4) + owner (2)
     int perSlot = 24 + 4 * nnzw + 4 + 2;
     int fixed = RC_NPB * P * 16 + RC_NPB * 32 + rc_row_len(P, maxAf + 1) * 8 + 1024;
-    if (!bigIds.empty() && (long long)cap * perSlot + fixed > smemBudgetBytes)
-        return "live set of one pattern (" + std::to_string(maxLiveBig) + " states) exceeds the shared-memory tier";
+    // a live set beyond the shared-memory tier: the same kernel with its per-slot arrays in global memory (rc_kernels.cu)
+    out.bigGlobal = (!bigIds.empty() && (long long)cap * perSlot + fixed > smemBudgetBytes) ? 1 : 0;
+    if (maxLiveBig >= (int)RC_NO_UP) return "live set of one pattern (" + std::to_string(maxLiveBig) + " states) exceeds 16-bit slot indices";
     out.cap = cap;
 
     // best-fit decreasing on the per-pattern maximum live size, under the tier's pattern / rate-row limits

@@ -45,6 +45,7 @@ struct GapInfo {
 
 struct PlanHost {
     int P = 0, maxAf = 0, nPat = 0, nEpochs = 0, nnzw = 1, nBins = 0, nBinsKB = 0, cap = RC_BLOCK;
+    int bigGlobal = 0;                     // the largest live set does not fit the big tier's shared memory: global scratch instead
     std::vector<int> binPatOff, binPats;   // big tier bins
     int nFastBins = 0;
     int fastBlock = RC_BLOCK;              // 64, 128 or 256 state slots per fast-tier block

@@ -68,6 +68,7 @@ struct RcPlanDev {
     int nBins;
     int nBinsKB;                 // the first nBinsKB big-tier bins hold patterns that models on the trajectory-key tier run in row mode
     int cap;                     // slots per block
+    int bigGlobal;               // 1: the big tier keeps its per-slot arrays in a global scratch buffer (live sets beyond shared memory)
     const int* binPatOff;        // [nBins+1]          big-tier bins (several states per thread)
     const int* binPats;          // shard-local pattern ids, bin after bin
     int nFastBins;

@@ -369,3 +369,29 @@ def test_c3_batch_mixing_join_orders_uses_one_plan_per_order(default_times):
     logl2, _, _ = e.eval_models(specs[:4])                                       # rebuilt on demand, same answers
     assert np.array_equal(logl2, logl[:4]) and e.stats()["plan_misses"] >= 3
     e.close()
+
+
+def test_live_sets_beyond_shared_memory_run_in_global_memory(fourpop, default_times):
+    # the reference's dense vectors take a live set of any size (Core.hs:58-70); here the big tier keeps b, the structure
+    # words and the accumulators in a global scratch buffer when the largest live set does not fit its shared memory.
+    # Forced on the fourPop maxAf=10 model (live sets of up to 668 states after the admixture pulses) with an 8 KB budget,
+    # trajectory-key tier off so that the big tier runs these patterns; several models so that the scratch slices are used
+    std = R.computeStandardOrder(fourpop["nVec"], 10)
+    cnt = _counts(fourpop, std)
+    e = R.Engine(0)
+    e.set_option("keyed", 0.0)
+    e.set_option("big_smem_kb", 8.0)
+    e.set_problem(fourpop["nVec"], 10, std, cnt, fourpop["totalSites"])
+    spec = _spec(4, default_times, fourpop["events"], fourpop["theta"])
+    spec2 = _spec(4, default_times, fourpop["events"], fourpop["theta"] * 1.5)
+    logl, probs, status = e.eval_models([spec, spec2, spec], want_probs=True)
+    assert not status.any()
+    ll_o, probs_o, w_o = O.logl(4, 10, default_times, fourpop["theta"], [1.0] * 4, False, fourpop["events"],
+                                fourpop["nVec"], std, cnt, fourpop["totalSites"])
+    assert _relerr(probs[0], probs_o) < PROB_RTOL and abs(logl[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    assert np.array_equal(probs[0], probs[2]) and _relerr(probs[1], probs_o * 1.5) < PROB_RTOL
+    # the same engine with the default budget gives the same numbers (same kernel, shared memory)
+    e.set_option("big_smem_kb", 0.0)
+    logl_s, probs_s, _ = e.eval_models([spec], want_probs=True)
+    assert np.array_equal(probs_s[0], probs[0]) and logl_s[0] == logl[0]
+    e.close()
