@@ -963,6 +963,9 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     const int k = pl.keyBranch[kk];
     const int j = t - pl.keyThrBase[kk] + 1;
     const bool hasPair = j <= (int)pl.keyMaxJ[kk];
+    // a key of even length is stored with an odd stride (rc_pair_stride): the thread of its last pair also writes the padding
+    // pair, so that a step row is written in whole 32-byte sectors
+    const bool padLast = j == (int)pl.keyMaxJ[kk] && rc_pair_stride(j) != j;
     // ---- starting value ----
     double a;
     {
@@ -1018,6 +1021,7 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
             }
         }
         if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
+        if (padLast) *reinterpret_cast<double2*>(out + 2) = make_double2(1.0, 0.0);
     }
     if (j == 1) {
         aEnd[M.aEndOff + kk] = a;
