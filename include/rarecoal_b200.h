@@ -197,7 +197,10 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
  *   "graphs" (1)           the launch chain of a call is captured as a CUDA graph the second time the same launch signature
  *                          (batch size, event structures, buffers) is seen and replayed from then on; 0 = plain launches
  *   "plan_cache_max" (64)  transition plans (one per event structure) kept per context, least recently used evicted first
- *   "plan_cache_mb" (49152) device memory the cached plans may hold                                        */
+ *   "plan_cache_mb" (49152) device memory the cached plans may hold
+ *   "big_smem_kb" (0)      > 0: shared-memory budget of the big tier (patterns with more than 256 live states).  A live
+ *                          set that does not fit runs the same kernel on a global scratch buffer (any size up to 65 534
+ *                          states per pattern); the option exists so that tests can force that mode on a small problem */
 int rc_set_option(rc_ctx* ctx, const char* name, double value);
 
 int rc_last_stats(rc_ctx* ctx, rc_stats* out);

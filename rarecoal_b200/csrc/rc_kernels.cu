@@ -2258,6 +2258,14 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     if (tid >= np) return;
     if (!isLast) {
         // ---- hand b and the updateD sums to the next epoch's launch ----
+        // (the lane record is read again here instead of being kept through the grid-step loop: twelve registers less in the loop)
+        {
+            const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + (RC_PLANE_N / 4) * (size_t)tid;
+            la = __ldcg(lane);
+            lb = __ldcg(lane + 1);
+            lc = __ldcg(lane + 2);
+            ld = __ldcg(lane + 3);
+        }
         const unsigned refW[9] = {lb.z, lb.w, lc.x, lc.y, lc.z, lc.w, ld.x, ld.y, ld.z};
         if (la.z & RC_PLANE_DIROUT) {
             // direct hand-over: the lane applies the Join itself, new_b[J(x)] += b(x) (Core.hs:172-188), summing in its own
