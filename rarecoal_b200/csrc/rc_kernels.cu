@@ -1812,6 +1812,7 @@ struct RcPatRegs {
     int dPairBase;                // ... and its pair index inside the step row (pair 0 of the row is {dt, 0})
     bool direct;                  // block-uniform
     bool anyU;                    // block-uniform: some pattern of the bin has a branch with m = 1
+    int pf;                       // block-uniform: pair rows of the bin in units of RC_PBLOCK, rounded up to 1, 2 or RC_PFETCH
     bool on, unit;
     double dacc;
 #if RC_PAT_TMA
@@ -1849,7 +1850,7 @@ __device__ __forceinline__ void rc_pat_fill(RcPatRegs<MAXS>& R, const unsigned s
 }
 #endif
 
-template <int MA, int MB, int MC, int MD, int ME, bool HASU, int MAXS>
+template <int MA, int MB, int MC, int MD, int ME, bool HASU, int PF, int MAXS>
 __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sBase, const long long strideD, int& s, const int nextStop,
                                            unsigned& slot, const unsigned RE_SLOT) {
     constexpr int MBp = MB ? MB : 1, MCp = MC ? MC : 1, MDp = MD ? MD : 1, MEp = ME ? ME : 1;
@@ -1888,8 +1889,9 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
         const unsigned slot = (R.k & (RC_PDEPTH - 1)) * RE_SLOT;
 #else
         const unsigned prev = slot == 0 ? (RC_PDEPTH - 1) * RE_SLOT : slot - RE_SLOT;      // slot of step s - 1: free again
+        // (PF: the bin has at most PF * RC_PBLOCK pair rows — a loop of its own per ring size, chosen once per block)
 #pragma unroll
-        for (int q = 0; q < RC_PFETCH; ++q) {
+        for (int q = 0; q < PF; ++q) {
             rc_cp_async16_if(myRE + prev + (unsigned)q * RC_PBLOCK * 16u, R.fp[q], (R.fmask >> q) & 1u);
             R.fp[q] += strideD;
         }
@@ -1977,8 +1979,15 @@ __device__ __forceinline__ void rc_pat_dispatch_a(RcPatRegs<MAXS>& R, const unsi
 #define RC_PAT_CASE(A)                                                                                         \
     case A:                                                                                                    \
         if constexpr (A >= MB && A * SA <= MAXS && (MAXS <= RC_PAT_MAXS || A * SA > RC_PAT_MAXS)) {            \
-            if (R.anyU) rc_pat_run<A, MB, MC, MD, ME, true>(R, sBase, strideD, s, nextStop, slot, reSlot);    \
-            else rc_pat_run<A, MB, MC, MD, ME, false>(R, sBase, strideD, s, nextStop, slot, reSlot);           \
+            if (R.anyU) {                                                                                      \
+                if (R.pf == 1) rc_pat_run<A, MB, MC, MD, ME, true, 1>(R, sBase, strideD, s, nextStop, slot, reSlot);           \
+                else if (R.pf == 2) rc_pat_run<A, MB, MC, MD, ME, true, 2>(R, sBase, strideD, s, nextStop, slot, reSlot);      \
+                else rc_pat_run<A, MB, MC, MD, ME, true, RC_PFETCH>(R, sBase, strideD, s, nextStop, slot, reSlot);             \
+            } else {                                                                                           \
+                if (R.pf == 1) rc_pat_run<A, MB, MC, MD, ME, false, 1>(R, sBase, strideD, s, nextStop, slot, reSlot);          \
+                else if (R.pf == 2) rc_pat_run<A, MB, MC, MD, ME, false, 2>(R, sBase, strideD, s, nextStop, slot, reSlot);     \
+                else rc_pat_run<A, MB, MC, MD, ME, false, RC_PFETCH>(R, sBase, strideD, s, nextStop, slot, reSlot);            \
+            }                                                                                                  \
         }                                                                                                      \
         break;
     switch (MA) {
@@ -2077,6 +2086,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
 #else
     // ---- pair ring: every thread copies the pair rows tid, tid + RC_PBLOCK, ... of the bin ----
     R.fmask = 0u;
+    R.pf = hdrB.y <= RC_PBLOCK ? 1 : hdrB.y <= 2 * RC_PBLOCK ? 2 : RC_PFETCH;
     int fOff[RC_PFETCH];
 #pragma unroll
     for (int q = 0; q < RC_PFETCH; ++q) {
