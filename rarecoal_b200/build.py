@@ -12,14 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 SO = os.path.join(HERE, "librarecoal_b200.so")
-SOURCES = ["rc_kernels.cu", "rc_api.cu", "rc_plan.cpp", "rc_frontend.cpp", "rc_multi.cpp", "rc_nccl.cpp"]
+SOURCES = ["rc_pat25.cu", "rc_pat36.cu", "rc_pat12.cu", "rc_kernels.cu", "rc_api.cu", "rc_plan.cpp", "rc_frontend.cpp", "rc_multi.cpp", "rc_nccl.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-Wall", "--fmad=true"]
 LDFLAGS = ARCH + ["-shared", "-cudart", "shared", "-ldl", "-lpthread"]
 
 
 def _headers():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + \
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h") or f.endswith(".cuh")] + \
            [os.path.join(os.path.dirname(HERE), "include", "rarecoal_b200.h")]
 
 
