@@ -176,6 +176,7 @@ struct rc_ctx {
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
+    int optPatternEmbed = 0;          // ... and live sets that are not boxes on their bounding boxes (rc_plan.cpp, pat_box)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
     double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
     PinBuf hBlob, hOut;
@@ -445,7 +446,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     std::memset(&d, 0, sizeof d);
     const rc::PlanHost& h = pe->h;
     d.P = h.P; d.maxAf = h.maxAf; d.A1 = h.maxAf + 1; d.nPat = h.nPat; d.nEpochs = h.nEpochs; d.nnzw = h.nnzw;
-    d.nBins = h.nBins; d.nBinsKB = h.nBinsKB; d.cap = h.cap; d.bigGlobal = h.bigGlobal; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
+    d.nBins = h.nBins; d.nBinsKB = h.nBinsKB; d.cap = h.cap; d.bigGlobal = h.bigGlobal; d.zeroRow = h.zeroRow; d.nFastBins = h.nFastBins; d.fastBlock = h.fastBlock;
     int rc;
     if ((rc = upload(ctx, pe, h.fBinPatOff, &d.fBinPatOff))) return rc;
     if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
@@ -545,7 +546,7 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     PlanEntry* pe = new PlanEntry();
     std::string e = rc::build_plan(ctx->P, ctx->maxAf, ctx->nPat, ctx->patS.data(), ctx->nVec.data(), mh.sev, mh.gaps,
                                    mh.hasSplit, ctx->optBigSmemKB > 0 ? std::min(ctx->smemOptin, ctx->optBigSmemKB * 1024) : ctx->smemOptin, pe->h,
-                                   ctx->optPattern);
+                                   ctx->optPattern ? (ctx->optPatternEmbed ? 3 : 1) : 0);
     if (!e.empty()) {
         delete pe;
         ctx->err = e;
@@ -1498,6 +1499,15 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
             cudaDeviceSynchronize();
             ctx->clear_plans();
             ctx->optPattern = v;
+        }
+    }
+    else if (n == "pattern_embed") {
+        const int v = value != 0.0;
+        if (v != ctx->optPatternEmbed) {
+            cudaSetDevice(ctx->device);
+            cudaDeviceSynchronize();
+            ctx->clear_plans();
+            ctx->optPatternEmbed = v;
         }
     }
     else if (n == "graphs") { ctx->optGraphs = value != 0.0; if (!ctx->optGraphs) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->clear_graphs(); } }

@@ -821,7 +821,9 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     const bool hasPair = j <= (int)pl.keyMaxJ[kk];
     // a key of even length is stored with an odd stride (rc_pair_stride): the thread of its last pair also writes the padding
     // pair, so that a step row is written in whole 32-byte sectors
-    const bool padLast = j == (int)pl.keyMaxJ[kk] && rc_pair_stride(j) != j;
+    const bool padLast = j == (int)pl.keyMaxJ[kk] && rc_pair_stride(j + pl.zeroRow) != j + pl.zeroRow;
+    // a plan with a Split: the pair of x = 0, {1, 0}, in front of the key's pairs (pattern mode on bounding boxes, rc_plan.cpp)
+    const bool zeroFirst = pl.zeroRow && j == 1;
     // ---- starting value ----
     double a;
     {
@@ -878,6 +880,7 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
         }
         if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
         if (padLast) *reinterpret_cast<double2*>(out + 2) = make_double2(1.0, 0.0);
+        if (zeroFirst) *reinterpret_cast<double2*>(out - 2) = make_double2(1.0, 0.0);
     }
     if (j == 1) {
         aEnd[M.aEndOff + kk] = a;

@@ -439,7 +439,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     R.nU = (int)((la.z >> 20) & 0xFu);
     R.anyU = __syncthreads_or(R.on && R.nU > 0) != 0;
 
-    R.unit = R.on && (shapeB >> 4) == 0 && R.nU == 0;        // x = e_A is the first state of a single-branch pattern
+    R.unit = R.on && (la.z & RC_PLANE_UNIT) != 0;            // x = e_A, the lane's first state, is a state of the pattern (updateD)
     const int MAw = (int)(shapeB & 0xFu);
 
     bool finished = false, parked = false;
@@ -533,8 +533,11 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
 #pragma unroll
             for (int x = 0; x < MAXS; ++x)
                 if (x < n) {
-                    double* t = col + ((refW[x >> 2] >> (8 * (x & 3))) & 0xFFu) * RC_PBLOCK;
-                    *t = *t + R.b[x];
+                    const unsigned y = (refW[x >> 2] >> (8 * (x & 3))) & 0xFFu;      // 0xFF: a place of the bounding box without a state
+                    if (y != 0xFFu) {
+                        double* t = col + y * RC_PBLOCK;
+                        *t = *t + R.b[x];
+                    }
                 }
             double* out = bCur + (size_t)b * bStride + pl.dirOff + la.w;
             for (int y = 0; y < nOut; ++y) out[y] = col[y * RC_PBLOCK];
@@ -542,7 +545,10 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
             double* out = bCur + (size_t)b * bStride + la.w;
 #pragma unroll
             for (int x = 0; x < MAXS; ++x)
-                if (x < n) out[(refW[x >> 2] >> (8 * (x & 3))) & 0xFFu] = R.b[x];
+                if (x < n) {
+                    const unsigned ref = (refW[x >> 2] >> (8 * (x & 3))) & 0xFFu;
+                    if (ref != 0xFFu) out[ref] = R.b[x];
+                }
         }
         dAcc[(size_t)b * nPat + pid] = dp;
         return;

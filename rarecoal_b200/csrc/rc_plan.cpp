@@ -163,6 +163,7 @@ struct PatPlan {
     std::vector<int> trCnt;         // per transition: live_{e+1} counts
     std::vector<uint32_t> trEnt;
     std::vector<uint8_t> mx;        // per epoch: P bytes, largest x_k over the live states
+    std::vector<uint8_t> mn;        // per epoch: P bytes, 1 if every live state has x_k >= 1 (and some has), else 0
     // row view of a box-shaped live set (one thread per row along the widest branch), per epoch
     std::vector<uint8_t> rowOK, rowM, rowK, rowNO;   // usable / row length / row branch / other non-zero branches
     std::vector<uint8_t> fullBox;                    // per epoch: the live set is exactly prod_k {1..mx_k} (every state has every live branch)
@@ -224,12 +225,14 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     pp.words.resize(w0 + L.size() * (size_t)c.stride, 0u);
     size_t m0 = pp.mx.size();
     pp.mx.resize(m0 + (size_t)c.P, 0);
+    pp.mn.resize(m0 + (size_t)c.P, L.empty() ? 0 : 1);
     for (size_t i = 0; i < L.size(); ++i) {
         St s = L[i];
         int nnz = 0, sum = 0;
         for (int k = 0; k < c.P; ++k) {
             int xk = s.x[k];
             if (xk > pp.mx[m0 + (size_t)k]) pp.mx[m0 + (size_t)k] = (uint8_t)xk;
+            if (!xk) pp.mn[m0 + (size_t)k] = 0;
             if (!xk) continue;
             sum += xk;
             s.x[k] = (uint8_t)(xk + 1);
@@ -522,6 +525,60 @@ static uint32_t pat_shape(const uint8_t* mx, int P, int rk, int maxStates, int* 
     return (uint32_t)MA | ((uint32_t)sh[0] << 4) | ((uint32_t)sh[1] << 8) | ((uint32_t)sh[2] << 12) | ((uint32_t)sh[3] << 16);
 }
 
+// Pattern mode for a live set that is not a box of all live branches (what a Split leaves: a union of boxes by support, down-
+// closed): the pattern runs on its BOUNDING box, a branch whose coordinate reaches 0 taking the values 0 .. mx (pair row of
+// x = 0: {1, 0}, the table's leading pair of every key when the plan has a Split).  updateB couples x only to x + e_k of its
+// non-zero components (Core.hs:272-280) and the live set is down-closed within a support, so the states of the box that are not
+// live receive nothing and stay exactly 0; the lanes carry them along.  The row branch A must never reach 0 (then e_A is the
+// only unit state the box can hold, at local index 0).  Returns the shape (sizes including the value 0) or 0.
+struct PatBox {
+    uint32_t shape = 0;
+    int rk = 0, dims[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nS = 0, nU = 0, n = 0;
+    uint32_t zeroMask = 0;      // bit q: dims[q] (q >= 1, a shaped branch) includes the value 0
+    bool unit = false;          // e_A is a state of the box: no unit branch and every shaped branch includes 0
+};
+static bool pat_box(const uint8_t* mx, const uint8_t* mn, bool fullBox, int rowK, int P, int maxStates, PatBox& B) {
+    B = PatBox();
+    if (fullBox) {
+        B.rk = rowK;
+        B.shape = pat_shape(mx, P, rowK, maxStates, B.dims, &B.nS, &B.nU);
+        if (!B.shape) return false;
+    } else {
+        int rk = -1;
+        for (int k = 0; k < P; ++k) if (mx[k] && mn[k] && (rk < 0 || mx[k] > mx[rk])) rk = k;
+        if (rk < 0) return false;
+        const int MA = mx[rk];
+        if (MA > RC_ROW_MAXM) return false;
+        int sh[4] = {0, 0, 0, 0}, shK[4] = {0, 0, 0, 0}, shZ[4] = {0, 0, 0, 0}, nS = 0, nU = 0, un[RC_MAX_P];
+        for (int k = 0; k < P; ++k) {
+            if (k == rk || !mx[k]) continue;
+            const int sz = mx[k] + (mn[k] ? 0 : 1);
+            if (sz == 1) { un[nU++] = k; continue; }
+            if (nS == 4) return false;
+            int q = nS++;
+            while (q > 0 && sh[q - 1] < sz) { sh[q] = sh[q - 1]; shK[q] = shK[q - 1]; shZ[q] = shZ[q - 1]; --q; }
+            sh[q] = sz;
+            shK[q] = k;
+            shZ[q] = mn[k] ? 0 : 1;
+        }
+        long long prod = MA;
+        for (int q = 0; q < nS; ++q) prod *= sh[q];
+        if (prod > maxStates || 1 + nS + nU > 8 || (nS && sh[0] > MA)) return false;
+        B.rk = rk;
+        B.dims[0] = rk;
+        for (int q = 0; q < nS; ++q) { B.dims[1 + q] = shK[q]; if (shZ[q]) B.zeroMask |= 1u << (1 + q); }
+        for (int q = 0; q < nU; ++q) B.dims[1 + nS + q] = un[q];
+        B.nS = nS;
+        B.nU = nU;
+        B.shape = (uint32_t)MA | ((uint32_t)sh[0] << 4) | ((uint32_t)sh[1] << 8) | ((uint32_t)sh[2] << 12) | ((uint32_t)sh[3] << 16);
+    }
+    B.n = (int)(B.shape & 0xFu);
+    for (int q = 1; q < 5; ++q) B.n *= std::max(1, (int)((B.shape >> (4 * q)) & 0xFu));
+    B.unit = B.nU == 0;
+    for (int q = 1; q <= B.nS; ++q) B.unit = B.unit && ((B.zeroMask >> q) & 1u);
+    return true;
+}
+
 // Bin images of the keyed tier (record layouts in rc_types.h).  Everything the set-up of a block used to look up through
 // pattern ids, slot offsets, packed words and transition offsets is resolved here once, in the order the lanes of the
 // block consume it: the block reads its header, every lane one 32-byte record, and the gather goes straight to the
@@ -539,7 +596,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
     if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
     // pattern-mode lanes: where the record of (epoch, pattern) went, its group and its first element record
     std::vector<long long> recPos((size_t)nE * nPat, -1);
-    std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0);
+    std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0), boxN((size_t)nE * nPat, 0);
     std::vector<long long> patElemEnd((size_t)nE, 0);
     // gather record of the state with reference index `ref` of pattern i in epoch e
     auto gather_rec = [&](int e, int i, int ref, int live, uint32_t& r0, uint32_t& r1) -> bool {
@@ -588,59 +645,71 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 if (patM) {
                     // pattern mode: one lane per pattern; its states in mixed-radix order over (A, B, C, D, E), see rc_types.h
                     const uint32_t pr = out.patRow[(size_t)e * nPat + i];
-                    const int rk = (int)((pr >> 8) & 0xFFu), NO = (int)((pr >> 16) & 0xFFu);
-                    int dims[8], nS = 0, nU = 0;
-                    const uint32_t shape = pat_shape(&out.maxX[((size_t)e * nPat + i) * P], P, rk, patMax, dims, &nS, &nU);
-                    if (!shape) return "pattern-mode bin with an unsuitable pattern";
+                    const bool full = out.patFull[(size_t)e * nPat + i] != 0;
+                    PatBox pb;
+                    if (!pat_box(&out.maxX[((size_t)e * nPat + i) * P], &out.minX[((size_t)e * nPat + i) * P], full, (int)((pr >> 8) & 0xFFu), P, patMax, pb))
+                        return "pattern-mode bin with an unsuitable pattern";
+                    const uint32_t shape = pb.shape;
+                    const int nS = pb.nS, nU = pb.nU, nBox = pb.n;
+                    const int* dims = pb.dims;
                     const int MA = (int)(shape & 0xFu);
                     int Mp[4];
                     for (int q = 0; q < 4; ++q) Mp[q] = std::max(1, (int)((shape >> (4 * (q + 1))) & 0xFu));
-                    const int SA = Mp[0] * Mp[1] * Mp[2] * Mp[3], nr = ro[i + 1] - ro[i];
-                    if (MA * SA != live || nr != SA || NO != nS + nU) return "pattern-mode image: shape does not match the live set";
+                    const int SA = Mp[0] * Mp[1] * Mp[2] * Mp[3];
+                    if (live > nBox || (full && live != nBox)) return "pattern-mode image: shape does not match the live set";
                     uint32_t rec[RC_PLANE_N];
                     for (int q = 0; q < RC_PLANE_N; ++q) rec[q] = 0u;
                     const bool direct = out.grpDirect[(size_t)v] != 0;
                     for (int q = 0; q < 8; ++q) {
-                        // an unused slot points at pair row 0, {1, dt}: a neutral decay factor (direct bins have no ring: marker)
-                        const uint32_t row = direct ? (uint32_t)(RC_KROWS - 1) : q < 1 + nS + nU ? (uint32_t)rb[dims[q]] : 0u;
+                        // an unused slot points at pair row 0, {1, dt}: a neutral decay factor (direct bins have no ring: marker);
+                        // a branch that includes the value 0 starts one row earlier, at the key's leading {1, 0} pair
+                        const uint32_t row = direct ? (uint32_t)(RC_KROWS - 1) : q < 1 + nS + nU ? (uint32_t)rb[dims[q]] - ((pb.zeroMask >> q) & 1u) : 0u;
                         if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
                         rec[q >> 2] |= row << (8 * (q & 3));
                     }
                     if (direct) {
                         // first pair of the pattern's only key inside a step row of the trajectory table
                         if (nS + nU != 0) return "direct group with a multi-branch pattern";
-                        rec[15] = (uint32_t)out.keyPairBase[(size_t)out.ep[(size_t)e].keyOff + out.keyId[((size_t)e * nPat + i) * P + rk]];
+                        rec[15] = (uint32_t)out.keyPairBase[(size_t)out.ep[(size_t)e].keyOff + out.keyId[((size_t)e * nPat + i) * P + pb.rk]];
                     }
-                    std::vector<uint32_t> el((size_t)live * 2, 0u);
-                    for (int r = 0; r < nr; ++r) {
-                        const long long grow = out.rowEpochBase[(size_t)e] + ro[i] + r;
-                        int xs[4] = {1, 1, 1, 1};
-                        for (int d = 0; d < NO; ++d) {
-                            const uint32_t w = out.rowWordsAll[(size_t)grow * RC_ROW_NO + d];
-                            const int k = (int)(w & 0xFFu), x = (int)((w >> 8) & 0xFFu);
-                            for (int q = 0; q < nS; ++q) if (dims[1 + q] == k) xs[q] = x;
+                    // every live state (reference order) at its place in the box; the places without one stay empty (0xFF: b = 0)
+                    for (int w = 6; w < 15; ++w) rec[w] = 0xFFFFFFFFu;
+                    std::vector<uint32_t> el((size_t)nBox * 2, 0u);
+                    for (int ref = 0; ref < live; ++ref) {
+                        const long long g = out.epochBase[(size_t)e] + so[i] + ref;
+                        const int nnz = (int)(out.meta[(size_t)g] & 0xFFu);
+                        int x[RC_MAX_P];
+                        for (int k = 0; k < P; ++k) x[k] = 0;
+                        for (int d = 0; d < nnz; ++d) {
+                            const uint32_t w = out.words[(size_t)g * nnzw + d];
+                            x[w & 0xFFu] = (int)((w >> 8) & 0xFFu);
                         }
-                        const int other = (((xs[0] - 1) * Mp[1] + (xs[1] - 1)) * Mp[2] + (xs[2] - 1)) * Mp[3] + (xs[3] - 1);
-                        if (other < 0 || other >= SA) return "pattern-mode image out of range (other index)";
-                        for (int a = 0; a < MA; ++a) {
-                            const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + a], idx = a * SA + other;
-                            if (ref > 0xFF) return "pattern-mode image out of range (state index)";
-                            rec[6 + (idx >> 2)] |= (uint32_t)ref << (8 * (idx & 3));
-                            if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
-                        }
+                        int xs[4] = {0, 0, 0, 0};
+                        for (int q = 0; q < nS; ++q) xs[q] = x[dims[1 + q]] - (((pb.zeroMask >> (1 + q)) & 1u) ? 0 : 1);
+                        const int a = x[pb.rk] - 1;
+                        const int other = ((xs[0] * Mp[1] + xs[1]) * Mp[2] + xs[2]) * Mp[3] + xs[3];
+                        bool in = a >= 0 && a < MA && other >= 0 && other < SA;
+                        for (int q = 0; q < nS && in; ++q) in = xs[q] >= 0 && xs[q] < Mp[q];
+                        for (int q = 0; q < nU && in; ++q) in = x[dims[1 + nS + q]] == 1;
+                        if (!in) return "pattern-mode image out of range (state outside the box)";
+                        const int idx = a * SA + other;
+                        if (ref > 0xFE || ((rec[6 + (idx >> 2)] >> (8 * (idx & 3))) & 0xFFu) != 0xFFu) return "pattern-mode image out of range (state index)";
+                        rec[6 + (idx >> 2)] = (rec[6 + (idx >> 2)] & ~(0xFFu << (8 * (idx & 3)))) | ((uint32_t)ref << (8 * (idx & 3)));
+                        if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
                     }
                     static_assert(6 * 4 + RC_PAT_MAXL <= RC_PLANE_N * 4, "state indices fit the lane record");
-                    rec[2] = shape | ((uint32_t)nU << 20);
+                    rec[2] = shape | ((uint32_t)nU << 20) | (pb.unit ? RC_PLANE_UNIT : 0u);
                     rec[3] = (uint32_t)so[i];
                     rec[4] = (uint32_t)i;
                     rec[5] = (uint32_t)bOff;
                     recPos[(size_t)e * nPat + i] = (long long)out.kLane.size();
                     elPos[(size_t)e * nPat + i] = hdr[7] + bOff;
                     grpOf[(size_t)e * nPat + i] = v;
+                    boxN[(size_t)e * nPat + i] = nBox;
                     out.kLane.insert(out.kLane.end(), rec, rec + RC_PLANE_N);
                     out.kElem.insert(out.kElem.end(), el.begin(), el.end());
                     lanes += 1;
-                    bOff += live;
+                    bOff += nBox;
                 } else if (!rows) {
                     for (int s = 0; s < live; ++s) {
                         const long long g = out.epochBase[(size_t)e] + so[i] + s;
@@ -728,10 +797,10 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 bool seedLast = true;
                 size_t el0 = (size_t)hdr[7] * 2;
                 for (int q = p0; q < p1 && seedLast; ++q) {
-                    const int live = so[out.kBinPats[(size_t)q] + 1] - so[out.kBinPats[(size_t)q]];
-                    for (int x = 0; x < live; ++x)
-                        if ((out.kElem[el0 + (size_t)x * 2] == RC_IMG_SEED) != (x == live - 1)) seedLast = false;
-                    el0 += (size_t)live * 2;
+                    const int nb = boxN[(size_t)e * nPat + out.kBinPats[(size_t)q]];
+                    for (int x = 0; x < nb; ++x)
+                        if ((out.kElem[el0 + (size_t)x * 2] == RC_IMG_SEED) != (x == nb - 1)) seedLast = false;
+                    el0 += (size_t)nb * 2;
                 }
                 if (seedLast) hdr[3] |= RC_HDR_SEED;
             }
@@ -765,24 +834,31 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 if (rpN < 0 || rpO < 0) { ok = false; break; }
                 const uint32_t* rn = &out.kLane[(size_t)rpN];
                 const uint32_t* ro = &out.kLane[(size_t)rpO];
-                const int liveN = out.slotOff[(size_t)e * (nPat + 1) + i + 1] - out.slotOff[(size_t)e * (nPat + 1) + i];
                 const int liveO = out.slotOff[(size_t)(e - 1) * (nPat + 1) + i + 1] - out.slotOff[(size_t)(e - 1) * (nPat + 1) + i];
-                if (liveN > RC_PAT_MAXL || liveO > RC_PAT_MAXL) { ok = false; break; }
+                const int nN = boxN[(size_t)e * nPat + i], nO = boxN[(size_t)(e - 1) * nPat + i];
+                if (nN > RC_PAT_MAXL || nO > RC_PAT_MAXL || liveO > nO) { ok = false; break; }
+                // (places of a bounding box without a live state: 0xFF on both sides)
                 uint8_t localOfRef[RC_PAT_MAXL];
-                for (int x = 0; x < liveO; ++x) localOfRef[(ro[6 + (x >> 2)] >> (8 * (x & 3))) & 0xFFu] = (uint8_t)x;
+                for (int x = 0; x < nO; ++x) {
+                    const uint32_t ref = (ro[6 + (x >> 2)] >> (8 * (x & 3))) & 0xFFu;
+                    if (ref != 0xFFu) localOfRef[ref] = (uint8_t)x;
+                }
                 uint8_t* mp = &maps[(size_t)(q - q0) * RC_PAT_MAXL];
-                for (int x = 0; x < liveO; ++x) mp[x] = 0xFF;
-                for (int y = 0; y < liveN && ok; ++y) {
+                for (int x = 0; x < RC_PAT_MAXL; ++x) mp[x] = 0xFF;
+                int mapped = 0;
+                for (int y = 0; y < nN && ok; ++y) {
                     const int ref = (int)((rn[6 + (y >> 2)] >> (8 * (y & 3))) & 0xFFu);
+                    if (ref == 0xFF) continue;
                     const int sl = out.slotOff[(size_t)e * (nPat + 1) + i] + ref;
                     for (int t = trOff[sl]; t < trOff[sl + 1]; ++t) {
                         const uint32_t ent = out.trEnt[(size_t)(out.trEntBase[(size_t)e - 1] + t)];
                         const int src = (int)(ent & 0xFFFFu);
                         if ((ent >> 16) != RC_W_ONE || src >= liveO || mp[localOfRef[src]] != 0xFF) { ok = false; break; }
                         mp[localOfRef[src]] = (uint8_t)y;
+                        ++mapped;
                     }
                 }
-                for (int x = 0; x < liveO && ok; ++x) if (mp[x] == 0xFF) ok = false;     // a Join maps every state somewhere
+                ok = ok && mapped == liveO;                            // a Join maps every live state somewhere
             }
             if (!ok) continue;
             out.grpDirIn[(size_t)v] = 1;
@@ -790,16 +866,15 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             for (int q = q0; q < q1; ++q) {
                 const int i = out.kBinPats[(size_t)q];
                 uint32_t* ro = &out.kLane[(size_t)recPos[(size_t)(e - 1) * nPat + i]];
-                const int liveN = out.slotOff[(size_t)e * (nPat + 1) + i + 1] - out.slotOff[(size_t)e * (nPat + 1) + i];
-                const int liveO = out.slotOff[(size_t)(e - 1) * (nPat + 1) + i + 1] - out.slotOff[(size_t)(e - 1) * (nPat + 1) + i];
+                const int nN = boxN[(size_t)e * nPat + i], nO = boxN[(size_t)(e - 1) * nPat + i];
                 const uint8_t* mp = &maps[(size_t)(q - q0) * RC_PAT_MAXL];
-                for (int w = 6; w < 15; ++w) ro[w] = 0u;
-                for (int x = 0; x < liveO; ++x) ro[6 + (x >> 2)] |= (uint32_t)mp[x] << (8 * (x & 3));
-                ro[2] |= RC_PLANE_DIROUT | ((uint32_t)liveN << 24);
+                for (int w = 6; w < 15; ++w) ro[w] = 0xFFFFFFFFu;
+                for (int x = 0; x < nO; ++x) ro[6 + (x >> 2)] = (ro[6 + (x >> 2)] & ~(0xFFu << (8 * (x & 3)))) | ((uint32_t)mp[x] << (8 * (x & 3)));
+                ro[2] |= RC_PLANE_DIROUT | ((uint32_t)nN << 24);
                 ro[3] = (uint32_t)(elPos[(size_t)e * nPat + i] - out.ep[(size_t)e].elBase);
                 // the lane sums into [state][lane] doubles of its block's shared memory
                 int& mb = out.grpMaxB[(size_t)grpOf[(size_t)(e - 1) * nPat + i]];
-                mb = std::max(mb, RC_PBLOCK * liveN);
+                mb = std::max(mb, RC_PBLOCK * nN);
             }
             out.dirSize = std::max(out.dirSize, patElemEnd[(size_t)e] - out.ep[(size_t)e].elBase);
         }
@@ -862,6 +937,12 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
 
     out = PlanHost();
     out.P = P; out.maxAf = maxAf; out.nPat = nPat; out.nEpochs = nEpochs; out.nnzw = nnzw; out.maxLive = maxLive;
+    // patternMode & 2 ("pattern_embed" option, or RC_PAT_EMBED=1): live sets that are not boxes run in pattern mode on their
+    // bounding boxes (pat_box) instead of row / state mode.  Off by default: measured slower on the reference's fourPop data
+    // (C2, 64 models: 5.76 against 5.12 ms) and on C5 (0.94 against 0.82 ms) — 1 000 patterns spread over so many shape classes
+    // that a 64-lane bin holds 3 - 10 of them, and the boxes carry states that are not live.
+    static const bool embEnv = std::getenv("RC_PAT_EMBED") ? std::atoi(std::getenv("RC_PAT_EMBED")) != 0 : false;
+    out.zeroRow = (hasSplit && (embEnv || (patternMode & 2)) && patternMode != 0) ? 1 : 0;
 
     // Two tiers.  Fast tier (rc_propagate_fast_kernel): one live state per thread, <= RC_BLOCK states per
     // pattern, <= 8 non-zero components per state.  Big tier (rc_propagate_kernel): several states per thread,
@@ -1005,8 +1086,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             for (int q = 0; q < E.nKeys; ++q) {
                 int mj = out.keyMaxJ[(size_t)E.keyOff + q];
                 out.keyThrBase.push_back((int)out.thrKey.size() - E.thrOff);
-                out.keyPairBase.push_back(pairs);
-                pairs += rc_pair_stride(mj);        // odd stride: see rc_types.h (RC_HDR_N)
+                // (a plan with a Split: the pair of x = 0, {1, 0}, leads every key — pattern mode on bounding boxes, pat_box)
+                out.keyPairBase.push_back(pairs + out.zeroRow);
+                pairs += rc_pair_stride(mj + out.zeroRow);        // odd stride: see rc_types.h (RC_HDR_N)
                 for (int t = 0; t < std::max(1, mj); ++t) out.thrKey.push_back(q);
             }
             E.nThr = (int)out.thrKey.size() - E.thrOff;
@@ -1057,8 +1139,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             auto clsOf = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
                 if (patMode) {
-                    int nU = 0;
-                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e0 * P], P, pp.rowK[(size_t)e0], patMaxStates, nullptr, nullptr, &nU);
+                    PatBox pb;
+                    pat_box(&pp.mx[(size_t)e0 * P], &pp.mn[(size_t)e0 * P], pp.fullBox[(size_t)e0] != 0, pp.rowK[(size_t)e0], P, patMaxStates, pb);
+                    const uint32_t sh = pb.shape;
+                    const int nU = pb.nU;
                     static const bool nuClass = std::getenv("RC_PAT_NUCLASS") ? std::atoi(std::getenv("RC_PAT_NUCLASS")) != 0 : false;
                     return (int)(sh | (nuClass ? (uint32_t)nU << 20 : 0u));   // blocks are uniform in shape (the unrolled update)
                 }
@@ -1110,7 +1194,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
                         auto it = ob.keyRows[(size_t)q].find(key);
                         int have = it == ob.keyRows[(size_t)q].end() ? 0 : it->second;
-                        if (mxk > have) add[(size_t)q] += patMode ? rc_pair_stride(mxk) - rc_pair_stride(have) : mxk - have;
+                        if (mxk > have) add[(size_t)q] += patMode ? rc_pair_stride(mxk + out.zeroRow) - (have ? rc_pair_stride(have + out.zeroRow) : 0) : mxk - have;
                     }
                     if (!packDirect && ob.rowsUsed[(size_t)q] + add[(size_t)q] > rowCap) return false;
                     // (pair rows without de-duplication: a limit of the self-contained kernel's rate table only)
@@ -1123,7 +1207,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         if (!mxk) continue;
                         int key = out.keyId[((size_t)e * nPat + i) * P + k];
                         int& have = ob.keyRows[(size_t)q][key];
-                        if (mxk > have) { ob.rowsUsed[(size_t)q] += patMode ? rc_pair_stride(mxk) - rc_pair_stride(have) : mxk - have; have = mxk; }
+                        if (mxk > have) { ob.rowsUsed[(size_t)q] += patMode ? rc_pair_stride(mxk + out.zeroRow) - (have ? rc_pair_stride(have + out.zeroRow) : 0) : mxk - have; have = mxk; }
                     }
                     ob.rowsSelf[(size_t)q] += addSelf[(size_t)q];
                     ob.slotsE[(size_t)q] += lanesOf(pp, e);
@@ -1225,8 +1309,9 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         bytes += segLen * 16;
                     };
                     for (int key : keyOrder) {
-                        startOf[key] = row;
-                        const int n = rowsOf[key], st = rc_pair_stride(n), src = out.keyPairBase[(size_t)E.keyOff + key];
+                        // (with a leading pair of x = 0 when the plan has one: the key's first row then precedes startOf)
+                        startOf[key] = row + out.zeroRow;
+                        const int n = rowsOf[key], st = rc_pair_stride(n + out.zeroRow), src = out.keyPairBase[(size_t)E.keyOff + key] - out.zeroRow;
                         for (int j = 0; j < st; ++j) fRows.push_back(src + j);
                         if (src == segSrc + segLen) segLen += st;
                         else { close(); segSrc = src; segDst = row; segLen = st; }
@@ -1279,12 +1364,16 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             int maxNO = 0;
             for (int i : orderK) {
                 const PatPlan& pp = pps[(size_t)i];
-                const bool box = patEnv && pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
+                // a box of all live branches, or (not in the last epoch, whose shortcut and epilogue assume the former) a live set
+                // that runs on its bounding box (pat_box)
+                const bool full = pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
+                const bool box = patEnv && (full || (out.zeroRow && e + 1 < nEpochs && pp.live[(size_t)e] > 0));
                 int g = RC_NGROUP - 1;                               // one state per thread
                 if (box)
                     for (int q = 0; q < RC_NPATG; ++q) {
                         if (q > 0 && !patLEnv && rc_pat_cap(RC_MODE_PAT + q) > RC_PAT_MAXS) break;
-                        if (pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], rc_pat_cap(RC_MODE_PAT + q)) != 0) { g = q; break; }
+                        PatBox pb;
+                        if (pat_box(&pp.mx[(size_t)e * P], &pp.mn[(size_t)e * P], full, pp.rowK[(size_t)e], P, rc_pat_cap(RC_MODE_PAT + q), pb)) { g = q; break; }
                     }
                 if (g == RC_NGROUP - 1) {
                     // row mode: a big pattern always (that is why it is here); a small one when its rows are long enough to pay
@@ -1345,8 +1434,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 if (mode >= RC_MODE_PAT) {
                     // rc_pat_run: D1 tree over the m = 1 branches, one DMUL per prefix of the shaped branches, per state one
                     // DMUL / DFMA per existing neighbour and the combining DFMA; updateD for a single-branch pattern
-                    int nS = 0, nU = 0;
-                    const uint32_t sh = pat_shape(&pp.mx[(size_t)e * P], P, pp.rowK[(size_t)e], rc_pat_cap(mode), nullptr, &nS, &nU);
+                    PatBox pb;
+                    pat_box(&pp.mx[(size_t)e * P], &pp.mn[(size_t)e * P], pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e], pp.rowK[(size_t)e], P, rc_pat_cap(mode), pb);
+                    const int nS = pb.nS, nU = pb.nU;
+                    const uint32_t sh = pb.shape;
                     int M[5];
                     for (int q = 0; q < 5; ++q) M[q] = (int)((sh >> (4 * q)) & 0xFu);
                     long long pre = M[0], states = M[0];
@@ -1356,7 +1447,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     for (int q = 1; q <= nS; ++q) { pre *= M[q]; n += pre; states *= M[q]; }
                     n += states;                                            // b = fma(b, d, t2)
                     for (int q = 0; q <= nS; ++q) n += states / M[q] * (M[q] - 1);   // neighbours along each shaped branch
-                    if (nS + nU == 0) n += 1;                               // updateD
+                    if (pb.unit) n += 1;                                    // updateD
                     if (direct) n = 2LL * M[0] - 1 + 1;
                 } else if (mode) {
                     // rc_row_run: per row NO DMUL (D), per state DMUL (D * G_r), DMUL (row neighbour), NO DFMA, DFMA
@@ -1471,6 +1562,13 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         }
         out.nBins = out.nBinsKB + nRest;
     }
+    out.minX.assign((size_t)nEpochs * nPat * P, 0);
+    out.patFull.assign((size_t)nEpochs * nPat, 0);
+    for (int i = 0; i < nPat; ++i)
+        for (int e = 0; e < nEpochs; ++e) {
+            for (int k = 0; k < P; ++k) out.minX[((size_t)e * nPat + i) * P + k] = pps[(size_t)i].mn[(size_t)e * P + k];
+            out.patFull[(size_t)e * nPat + i] = pps[(size_t)i].rowOK[(size_t)e] && pps[(size_t)i].fullBox[(size_t)e];
+        }
     out.maxX.assign((size_t)nEpochs * nPat * P, 0);
     for (int e = 0; e < nEpochs; ++e)
         for (int i = 0; i < nPat; ++i)
@@ -1727,26 +1825,37 @@ std::string check_plan(const PlanHost& h) {
                             const int row = (int)((r[q >> 2] >> (8 * (q & 3))) & 0xFFu);
                             const int len = q <= nS ? M[q] : 1;
                             if (directG) { if (row != RC_KROWS - 1) return fail("image pattern pair rows (direct)"); }
-                            else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch) : row != 0) return fail("image pattern pair rows");
+                            else if (q < 1 + nS + nU ? (row < 1 || row + len - 1 >= nFetch + (h.zeroRow ? 1 : 0)) : row != 0) return fail("image pattern pair rows");
                         }
                         if ((int)r[4] >= nPat || eOff + n > nB) return fail("image pattern hand-over");
+                        // n: states of the (bounding) box; live of them carry a state, the others are marked 0xFF
                         const int live = h.slotOff[(size_t)e * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)e * (nPat + 1) + r[4]];
-                        if (live != n) return fail("image pattern states");
+                        if (live > n || (live != n && (!h.zeroRow || e + 1 >= nE))) return fail("image pattern states");
                         if (r[2] & RC_PLANE_DIROUT) {
                             // the lane applies the next Join itself: next-epoch state index per state, lane-ordered destination
                             const int nOut = (int)((r[2] >> 24) & 0x3Fu);
                             if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + nOut > h.dirSize) return fail("image direct hand-over");
-                            if (nOut != h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4]]) return fail("image direct hand-over states");
-                            for (int q = 0; q < n; ++q)
-                                if ((int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu) >= nOut) return fail("image direct hand-over map");
+                            if (nOut < h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4]]) return fail("image direct hand-over states");
+                            int mapped = 0;
+                            for (int q = 0; q < n; ++q) {
+                                const int y = (int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
+                                if (y == 0xFF) continue;
+                                if (y >= nOut) return fail("image direct hand-over map");
+                                ++mapped;
+                            }
+                            if (mapped != live) return fail("image direct hand-over map size");
                         } else {
-                            if ((long long)r[3] + n > h.epochSlots[(size_t)e] || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
+                            if ((long long)r[3] + live > h.epochSlots[(size_t)e] || (int)r[3] != h.slotOff[(size_t)e * (nPat + 1) + r[4]]) return fail("image pattern states");
                             std::vector<char> hit((size_t)n, 0);
+                            int found = 0;
                             for (int q = 0; q < n; ++q) {
                                 const int ref = (int)((r[6 + (q >> 2)] >> (8 * (q & 3))) & 0xFFu);
-                                if (ref >= n || hit[(size_t)ref]) return fail("image pattern state order");
+                                if (ref == 0xFF && live != n) continue;
+                                if (ref >= live || hit[(size_t)ref]) return fail("image pattern state order");
                                 hit[(size_t)ref] = 1;
+                                ++found;
                             }
+                            if (found != live) return fail("image pattern state cover");
                         }
                     } else if (!rows) {
                         for (int d = 0; d < 8; ++d) {

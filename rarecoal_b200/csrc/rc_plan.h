@@ -51,6 +51,9 @@ struct PlanHost {
     int fastBlock = RC_BLOCK;              // 64, 128 or 256 state slots per fast-tier block
     std::vector<int> fBinPatOff, fBinPats; // fast tier bins
     std::vector<uint8_t> maxX;             // [nEpochs][nPat][P] largest x_k over the live states
+    std::vector<uint8_t> minX;             // [nEpochs][nPat][P] 1 if every live state has x_k >= 1 (host only)
+    std::vector<uint8_t> patFull;          // [nEpochs][nPat] the live set is the box of all its live branches (host only)
+    int zeroRow = 0;                       // 1: every trajectory key is led by the pair of x = 0, {1, 0} (plans with a Split)
     // Trajectory keys.  The ancestral count a_k(t) of a pattern (updateA, Core.hs:229-240, and the a-part of
     // Join/Split, Core.hs:165-170,195-200) is a function of the model and of the pattern's counts m on the leaves
     // merged into branch k so far.  One key per distinct (epoch, branch, sub-tuple); the trajectory kernel computes

@@ -68,6 +68,7 @@ struct RcPlanDev {
     int nBins;
     int nBinsKB;                 // the first nBinsKB big-tier bins hold patterns that models on the trajectory-key tier run in row mode
     int cap;                     // slots per block
+    int zeroRow;                 // 1: every trajectory key is led by the pair of x = 0, {1, 0}, at keyPairBase - 1
     int bigGlobal;               // 1: the big tier keeps its per-slot arrays in a global scratch buffer (live sets beyond shared memory)
     const int* binPatOff;        // [nBins+1]          big-tier bins (several states per thread)
     const int* binPats;          // shard-local pattern ids, bin after bin
@@ -135,6 +136,7 @@ struct RcPlanDev {
 #define RC_HDR_SEED 0x20000000      // first epoch, pattern mode: b is 1 at the last state of every lane (the pattern itself), else 0
 #define RC_HDR_NB(x) ((x) & 0x1FFFFFFF)
 #define RC_PLANE_DIROUT 0x80000000u
+#define RC_PLANE_UNIT 0x40000000u     // lane record [2]: the state at local index 0 is e_A (updateD reads it)
 #define RC_HDR_N 12
 // Pattern mode, further header ints: 8 first ring segment of the bin in kSegs, 9 segments, 10 bytes they bring in per grid step.
 // A segment (2 x u32: first pair inside a step row of the trajectory table; first ring row | pair rows << 16) is a run of

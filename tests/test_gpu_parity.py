@@ -395,3 +395,26 @@ def test_live_sets_beyond_shared_memory_run_in_global_memory(fourpop, default_ti
     logl_s, probs_s, _ = e.eval_models([spec], want_probs=True)
     assert np.array_equal(probs_s[0], probs[0]) and logl_s[0] == logl[0]
     e.close()
+
+
+@pytest.mark.parametrize("key", ["c2", "c5"])
+def test_bounding_box_pattern_mode_after_splits(default_times, key):
+    # "pattern_embed": the live sets a Split leaves (unions of boxes by support) run one pattern per thread on their bounding
+    # boxes, the states that are not live carried along as exact zeros (rc_plan.cpp, pat_box).  Off by default (slower than
+    # the row kernel on these workloads); same answers as the default path and as the oracle
+    wl = Wk.get(key)
+    nvec, pats, cnt = wl.problem()
+    e = R.Engine(0)
+    e.set_problem(nvec, wl.max_af, pats, cnt, wl.total_sites)
+    evs = wl.proposal_batches(1, 5, seed=11)[0]
+    specs = [_spec(wl.P, default_times, ev, wl.theta) for ev in evs]
+    logl0, probs0, st0 = e.eval_models(specs, want_probs=True)
+    steps0 = e.stats()["state_steps"]
+    e.set_option("pattern_embed", 1.0)
+    logl1, probs1, st1 = e.eval_models(specs, want_probs=True)
+    assert not st0.any() and not st1.any() and e.stats()["state_steps"] == steps0
+    assert _relerr(probs1, probs0) < PROB_RTOL and np.max(np.abs(logl1 - logl0) / np.abs(logl0)) < LOGL_RTOL
+    ev0 = Wk.desugar_growth_py(default_times, evs[0])
+    ll_o, probs_o, _ = O.logl(wl.P, wl.max_af, default_times, wl.theta, [1.0] * wl.P, False, ev0, nvec, pats, cnt, wl.total_sites)
+    assert _relerr(probs1[0], probs_o) < PROB_RTOL and abs(logl1[0] - ll_o) / abs(ll_o) < LOGL_RTOL
+    e.close()
