@@ -269,7 +269,8 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     const int binIdx0 = binBase + (int)blockIdx.x;
     const int4 hdrA = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0);
     const int4 hdrB = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0 + 1);
-    const int4 hdrC = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0 + 2);      // x first segment, y segments, z bytes per step
+    const int4 hdrC = __ldg(reinterpret_cast<const int4*>(pl.kBinHdr) + (RC_HDR_N / 4) * binIdx0 + 2);      // x first segment, y segments, z bytes per step, w shape
+    const int hdrDir = __ldg(pl.kBinHdr + RC_HDR_N * binIdx0 + 12);                                            // the bin in the lane-ordered region
     const RcEpochDev epd = pl.ep[e];
     if (mSteps < 0 || mMode != 1) return;
     const int P = pl.P, nPat = pl.nPat;
@@ -358,6 +359,18 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     // ---- the pattern's record; b of every state of the bin gathered cooperatively into shared memory (the ring starts
     //      afterwards: it lives in the same bytes; starting it before the gather, in bytes of its own, keeps the fetch
     //      pointers live across the gather and measured slower — spills, 9.96 -> 10.26 ms on C3) ----
+    const unsigned shapeB = (unsigned)hdrC.w & 0xFFFFFu;      // MA | MB << 4 | MC << 8 | MD << 12 | ME << 16: one shape per bin
+    int n = (int)(shapeB & 0xFu);
+#pragma unroll
+    for (int q = 1; q < 5; ++q) n *= max(1, (int)((shapeB >> (4 * q)) & 0xFu));
+    if (dirIn) {
+        // direct hand-over: the bin's b lies [state][lane] in the lane-ordered region — every lane reads its own states at
+        // stride RC_PBLOCK, a warp 256 contiguous bytes per state, straight into registers; nothing but the header is needed
+        const double* src = bPrev + (size_t)b * bStride + pl.dirOff + hdrDir + tid;
+#pragma unroll
+        for (int x = 0; x < MAXS; ++x)
+            if (x < n) R.b[x] = __ldcg(src + x * RC_PBLOCK);
+    }
     uint4 la = make_uint4(0u, 0u, 0u, 0u), lb = la, lc = la, ld = la;
     if (R.on) {
         const uint4* lane = reinterpret_cast<const uint4*>(pl.kLane) + (size_t)hdrB.z + (RC_PLANE_N / 4) * (size_t)tid;
@@ -370,17 +383,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
         const uint2* el = reinterpret_cast<const uint2*>(pl.kElem) + hdrB.w;
         const double* W = e > 0 ? wpool + models[b].wPool + sevs[models[b].sevOff + e - 1].wOff : nullptr;
         const double* bp = bPrev + (size_t)b * bStride;
-        if (seedIn) {
-        } else if (dirIn) {
-            // direct hand-over: the bin's b is one contiguous run of the lane-ordered region
-            // (all loads of a thread in flight at once: one round trip)
-            const double* src = bp + pl.dirOff + (hdrB.w - epd.elBase);
-            double v[MAXS];
-#pragma unroll
-            for (int u = 0; u < MAXS; ++u) v[u] = tid + u * RC_PBLOCK < nB ? src[tid + u * RC_PBLOCK] : 0.0;
-#pragma unroll
-            for (int u = 0; u < MAXS; ++u)
-                if (tid + u * RC_PBLOCK < nB) bb[tid + u * RC_PBLOCK] = v[u];
+        if (seedIn || dirIn) {
         } else if (e > 0 && sevs[models[b].sevOff + e - 1].type == RC_EV_JOIN_D) {
             // a Join: all weights are 1, twice as many states per batch
             constexpr int GU = 2 * RC_PAT_GU;
@@ -408,10 +411,6 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
             }
         }
     }
-    const unsigned shape = la.z & 0xFFFFFu;         // MA | MB << 4 | MC << 8 | MD << 12 | ME << 16
-    int n = (int)(shape & 0xFu);
-#pragma unroll
-    for (int q = 1; q < 5; ++q) n *= max(1, (int)((shape >> (4 * q)) & 0xFu));
     const int pid = (int)lb.x;
     double dp = (R.on && e > 0) ? dAcc[(size_t)b * nPat + pid] : 0.0;
     R.rows64 = (unsigned long long)la.x | ((unsigned long long)la.y << 32);
@@ -419,23 +418,19 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
     R.dPairBase = (int)ld.w;
     R.direct = hdrB.y == 0;
     R.dptr = ktab + (mE.tabBase + (long long)R.dPairBase) * 2;
-    __syncthreads();
-    if (R.on) {
-        const double* mine = bb + lb.y;
-        if (seedIn) {
+    if (seedIn) {
 #pragma unroll
-            for (int x = 0; x < MAXS; ++x) R.b[x] = x == n - 1 ? 1.0 : 0.0;       // Core.hs:60-66
-        } else {
+        for (int x = 0; x < MAXS; ++x) R.b[x] = x == n - 1 ? 1.0 : 0.0;       // Core.hs:60-66
+    } else if (!dirIn) {
+        __syncthreads();
+        if (R.on) {
+            const double* mine = bb + lb.y;
 #pragma unroll
             for (int x = 0; x < MAXS; ++x)
                 if (x < n) R.b[x] = mine[x];
         }
+        __syncthreads();          // the ring starts in the same bytes
     }
-    // the block's shape and number of unit branches: bins hold one class
-    __shared__ unsigned shapeS;
-    if (tid == 0) shapeS = la.z;
-    __syncthreads();
-    const unsigned shapeB = shapeS & 0xFFFFFu;
     R.nU = (int)((la.z >> 20) & 0xFu);
     R.anyU = __syncthreads_or(R.on && R.nU > 0) != 0;
 
@@ -540,7 +535,7 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
                     }
                 }
             double* out = bCur + (size_t)b * bStride + pl.dirOff + la.w;
-            for (int y = 0; y < nOut; ++y) out[y] = col[y * RC_PBLOCK];
+            for (int y = 0; y < nOut; ++y) out[y * RC_PBLOCK] = col[y * RC_PBLOCK];
         } else {
             double* out = bCur + (size_t)b * bStride + la.w;
 #pragma unroll

@@ -596,7 +596,8 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
     if ((long long)out.trEnt.size() >= 0xFFFFFFFFLL) return "too many transition entries for the keyed tier";
     // pattern-mode lanes: where the record of (epoch, pattern) went, its group and its first element record
     std::vector<long long> recPos((size_t)nE * nPat, -1);
-    std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0), boxN((size_t)nE * nPat, 0);
+    std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0), boxN((size_t)nE * nPat, 0), laneOf((size_t)nE * nPat, 0),
+        binOf((size_t)nE * nPat, 0);
     std::vector<long long> patElemEnd((size_t)nE, 0);
     // gather record of the state with reference index `ref` of pattern i in epoch e
     auto gather_rec = [&](int e, int i, int ref, int live, uint32_t& r0, uint32_t& r1) -> bool {
@@ -636,6 +637,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             hdr[9] = out.binSegCnt[(size_t)bI];
             hdr[10] = out.binSegBytes[(size_t)bI];
             int lanes = 0, bOff = 0;
+            uint32_t binShape = 0;
             for (int q = p0; q < p1; ++q) {
                 const int i = out.kBinPats[(size_t)q];
                 const int live = so[i + 1] - so[i];
@@ -706,6 +708,10 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                     elPos[(size_t)e * nPat + i] = hdr[7] + bOff;
                     grpOf[(size_t)e * nPat + i] = v;
                     boxN[(size_t)e * nPat + i] = nBox;
+                    laneOf[(size_t)e * nPat + i] = lanes;
+                    binOf[(size_t)e * nPat + i] = bI;
+                    if (lanes == 0) binShape = shape;
+                    else if (binShape != shape) return "pattern-mode bin with more than one shape";
                     out.kLane.insert(out.kLane.end(), rec, rec + RC_PLANE_N);
                     out.kElem.insert(out.kElem.end(), el.begin(), el.end());
                     lanes += 1;
@@ -792,6 +798,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             }
             hdr[2] = lanes;
             hdr[3] = bOff;
+            if (patM) hdr[11] = (int)binShape;        // one shape per pattern bin: the block dispatches on it without waiting for a lane record
             if (patM && e == 0) {
                 // the seed state m is the last one in the lane's own order too (all coordinates at their maximum)
                 bool seedLast = true;
@@ -815,6 +822,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
     //      gathers through element records and transition entries (three dependent loads per state at the start of every block).
     //      A bin group reads this way if every pattern of it was in pattern mode in the previous epoch. ----
     out.grpDirIn.assign((size_t)nE * RC_NGROUP, 0);
+    std::vector<long long> dirRun((size_t)nE, 0);
     out.dirOff = out.maxEpochSlots;
     out.dirSize = 0;
     static const bool dirEnv = std::getenv("RC_PAT_DIRHAND") ? std::atoi(std::getenv("RC_PAT_DIRHAND")) != 0 : true;
@@ -862,7 +870,17 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             }
             if (!ok) continue;
             out.grpDirIn[(size_t)v] = 1;
-            for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) out.kBinHdr[(size_t)bI * RC_HDR_N + 3] |= RC_HDR_DIRIN;
+            // the bin's region of the lane-ordered part: [state of the box][lane], RC_PBLOCK lanes — lane t reads its states at
+            // stride RC_PBLOCK, a warp 256 contiguous bytes per state, straight into registers
+            for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
+                int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
+                hdr[3] |= RC_HDR_DIRIN;
+                const uint32_t sh = (uint32_t)hdr[11];
+                int nb = (int)(sh & 0xFu);
+                for (int w = 1; w < 5; ++w) nb *= std::max(1, (int)((sh >> (4 * w)) & 0xFu));
+                hdr[12] = (int)dirRun[(size_t)e];
+                dirRun[(size_t)e] += (long long)RC_PBLOCK * nb;
+            }
             for (int q = q0; q < q1; ++q) {
                 const int i = out.kBinPats[(size_t)q];
                 uint32_t* ro = &out.kLane[(size_t)recPos[(size_t)(e - 1) * nPat + i]];
@@ -871,12 +889,12 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 for (int w = 6; w < 15; ++w) ro[w] = 0xFFFFFFFFu;
                 for (int x = 0; x < nO; ++x) ro[6 + (x >> 2)] = (ro[6 + (x >> 2)] & ~(0xFFu << (8 * (x & 3)))) | ((uint32_t)mp[x] << (8 * (x & 3)));
                 ro[2] |= RC_PLANE_DIROUT | ((uint32_t)nN << 24);
-                ro[3] = (uint32_t)(elPos[(size_t)e * nPat + i] - out.ep[(size_t)e].elBase);
+                ro[3] = (uint32_t)(out.kBinHdr[(size_t)binOf[(size_t)e * nPat + i] * RC_HDR_N + 12] + laneOf[(size_t)e * nPat + i]);
                 // the lane sums into [state][lane] doubles of its block's shared memory
                 int& mb = out.grpMaxB[(size_t)grpOf[(size_t)(e - 1) * nPat + i]];
                 mb = std::max(mb, RC_PBLOCK * nN);
             }
-            out.dirSize = std::max(out.dirSize, patElemEnd[(size_t)e] - out.ep[(size_t)e].elBase);
+            out.dirSize = std::max(out.dirSize, dirRun[(size_t)e]);
         }
     }
     if (out.dirSize > 0) {
@@ -1779,8 +1797,8 @@ std::string check_plan(const PlanHost& h) {
                 const int np = hdr[1], lanes = hdr[2], nB = RC_HDR_NB(hdr[3]), nFetch = hdr[5];
                 if ((hdr[3] & RC_HDR_SEED) && (!patM || e != 0)) return fail("image header seed flag");
                 const bool dirIn = (hdr[3] & RC_HDR_DIRIN) != 0;
-                if (dirIn && (!patM || e == 0 || h.grpDirIn.empty() || !h.grpDirIn[(size_t)v] ||
-                              hdr[7] - h.ep[(size_t)e].elBase < 0 || hdr[7] - h.ep[(size_t)e].elBase + nB > h.dirSize))
+                if (dirIn && (!patM || e == 0 || h.grpDirIn.empty() || !h.grpDirIn[(size_t)v] || hdr[12] < 0 ||
+                              (long long)hdr[12] + (long long)RC_PBLOCK * (np ? nB / np : 0) > h.dirSize))
                     return fail("image header direct hand-over");
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
@@ -1819,6 +1837,7 @@ std::string check_plan(const PlanHost& h) {
                         int n = M[0], nS = 0;
                         for (int q = 1; q < 5; ++q) if (M[q]) { n *= M[q]; ++nS; if (M[q] < 2 || M[q] > M[q - 1] || nS != q) return fail("image pattern shape order"); }
                         if (M[0] < 1 || M[0] > RC_ROW_MAXM || n > patMax || 1 + nS + nU > 8) return fail("image pattern shape");
+                        if ((uint32_t)hdr[11] != (r[2] & 0xFFFFFu)) return fail("image bin shape");
                         if (n <= patMin) return fail("pattern in the group of a larger kernel instantiation");
                         if (directG && (nS + nU != 0 || (int)r[15] < 1 || (int)r[15] + M[0] > h.ep[(size_t)e].rowPairs)) return fail("image direct pair base");
                         for (int q = 0; q < 8; ++q) {
@@ -1834,7 +1853,7 @@ std::string check_plan(const PlanHost& h) {
                         if (r[2] & RC_PLANE_DIROUT) {
                             // the lane applies the next Join itself: next-epoch state index per state, lane-ordered destination
                             const int nOut = (int)((r[2] >> 24) & 0x3Fu);
-                            if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + nOut > h.dirSize) return fail("image direct hand-over");
+                            if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + (long long)(nOut - 1) * RC_PBLOCK >= h.dirSize) return fail("image direct hand-over");
                             if (nOut < h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4]]) return fail("image direct hand-over states");
                             int mapped = 0;
                             for (int q = 0; q < n; ++q) {

@@ -129,16 +129,17 @@ struct RcPlanDev {
 };
 
 // Bin header (ints): 0 first entry in kBinPats/kPatRec, 1 patterns, 2 lanes (states or rows), 3 b doubles (row mode, padded
-// rows; pattern mode: | RC_HDR_DIRIN if the bin's b arrives in lane order at element index [7] - RcEpochDev::elBase of the
-// lane-ordered region), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first
+// rows; pattern mode: | RC_HDR_DIRIN if the bin's b arrives in lane order, see [12]), 4 first entry in kFetchRows, 5 pair rows to fetch, 6 first lane record (in 16-byte units), 7 first
 // element record.
 #define RC_HDR_DIRIN 0x40000000
 #define RC_HDR_SEED 0x20000000      // first epoch, pattern mode: b is 1 at the last state of every lane (the pattern itself), else 0
 #define RC_HDR_NB(x) ((x) & 0x1FFFFFFF)
 #define RC_PLANE_DIROUT 0x80000000u
 #define RC_PLANE_UNIT 0x40000000u     // lane record [2]: the state at local index 0 is e_A (updateD reads it)
-#define RC_HDR_N 12
-// Pattern mode, further header ints: 8 first ring segment of the bin in kSegs, 9 segments, 10 bytes they bring in per grid step.
+#define RC_HDR_N 16
+// Pattern mode, further header ints: 8 first ring segment of the bin in kSegs, 9 segments, 10 bytes they bring in per grid step,
+// 11 the shape of the bin's patterns (one per bin: MA | MB << 4 | ...), 12 (RC_HDR_DIRIN) first double of the bin in the
+// lane-ordered region of the carry buffers, laid out [state of the box][lane], RC_PBLOCK lanes.
 // A segment (2 x u32: first pair inside a step row of the trajectory table; first ring row | pair rows << 16) is a run of
 // pairs that is contiguous both in the table and in the ring: one bulk copy per segment and grid step fills a ring slot.
 // To make the runs long, a key's pairs are stored with the same odd stride in the table and in the ring and the ring rows of a
@@ -162,7 +163,8 @@ static inline __host__ __device__ int rc_pair_stride(int n) { return (n >= 2 && 
 //               [6..14] reference-order index of every state (36 x u8)
 //               Direct hand-over (bit 31 of [2]): the next event is a Join and the pattern's next bin reads b in lane order.
 //               The lane then applies the Join itself: [6..14] hold the next epoch's lane-local index of every state, bits
-//               24..29 of [2] the number of states there and [3] the first double of the pattern in the lane-ordered region.
+//               24..29 of [2] the number of states there and [3] the pattern's first double in the lane-ordered region (its
+//               states follow at stride RC_PBLOCK).
 //   The header's first-lane-record field counts 16-byte units (2 per state lane, 3 per row lane, 4 per pattern lane).
 // Gather record (2 x u32): first transition entry (absolute index in trEnt; RC_IMG_SEED: the value is 1, the seed state)
 // and (first slot of the pattern in the previous epoch) | entries << RC_IMG_CNT_SHIFT.
