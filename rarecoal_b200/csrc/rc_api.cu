@@ -176,6 +176,7 @@ struct rc_ctx {
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
+    int optFuseLast = 1;              // a last epoch without grid steps is finished by the launches of the last but one epoch
     int optPatternEmbed = 0;          // ... and live sets that are not boxes on their bounding boxes (rc_plan.cpp, pat_box)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
     double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
@@ -471,6 +472,7 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     if ((rc = upload(ctx, pe, h.keyThrBase, &d.keyThrBase))) return rc;
     if ((rc = upload(ctx, pe, h.thrKey, &d.thrKey))) return rc;
     if ((rc = upload(ctx, pe, h.lastKeyId, &d.lastKeyId))) return rc;
+    if ((rc = upload(ctx, pe, h.lastPairBase, &d.lastPairBase))) return rc;
     if ((rc = upload(ctx, pe, h.kBinBase, &d.kBinBase))) return rc;
     if ((rc = upload(ctx, pe, h.nKBins, &d.nKBins))) return rc;
     if ((rc = upload(ctx, pe, h.kBinPatOff, &d.kBinPatOff))) return rc;
@@ -884,6 +886,23 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         // under capture a timing event must be an event-record NODE (it is recorded when the graph runs)
         return capturing ? cudaEventRecordWithFlags(e, s2, cudaEventRecordExternal) : cudaEventRecord(e, s2);
     };
+    // fuse[c]: model range c of the plan group [pos, end) finishes its patterns in the launches of the last but one epoch
+    auto fuse_flags = [&](const PlanEntry* pe, int pos, int end, int nChains, bool* fuse) {
+        const int nE = pe->h.nEpochs, nModels = end - pos;
+        bool fuseOK = ctx->optFuseLast && nE >= 2 && pe->allShortcut && pe->h.lastSingle && !pe->h.grpDirIn.empty();
+        for (int v = RC_NGROUP * (nE - 1); fuseOK && v < RC_NGROUP * nE; ++v)
+            if (pe->h.nKBins[(size_t)v] > 0 && (pe->h.epochMode[(size_t)v] < RC_MODE_PAT || !pe->h.grpDirIn[(size_t)v])) fuseOK = false;
+        for (int c = 0; c < nChains; ++c) {
+            const int p0 = pos + (int)((long long)nModels * c / nChains), p1 = pos + (int)((long long)nModels * (c + 1) / nChains);
+            fuse[c] = fuseOK;
+            for (int q = p0; q < p1 && fuse[c]; ++q) {
+                if (hM[q].nSteps < 0 || hM[q].mode != 1) continue;          // skipped by the kernels
+                const RcModelEpochDev& me = hMep[hM[q].mepOff + nE - 1];
+                // (the step at which the last event fires is executed before the shortcut can apply: normally one grid step)
+                if (hM[q].sShort < 0 || hM[q].sShort != me.end || me.end - me.beg > 4 || hM[q].sShort >= hM[q].nSteps) fuse[c] = false;
+            }
+        }
+    };
     auto enqueue = [&](cudaStream_t st) -> int {
         launches = 0;
         CK(rec_timing(ctx->evt[1], st));
@@ -927,13 +946,22 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                         CK(cudaEventRecord(ctx->evChain[0], st));         // everything queued so far (blob, tables) precedes the chains
                         for (int c = 1; c < nChains; ++c) CK(cudaStreamWaitEvent(ctx->chainStream[c], ctx->evChain[0], 0));
                     }
+                    // Last epoch without a grid step (the shortcut applies at its first step, the usual case of a tree model) and
+                    // reached by direct hand-over: the launches of the last but one epoch finish the patterns (RC_E_FUSE) and the
+                    // last epoch is not launched.  Decided per model range.
+                    const int nE = pe->h.nEpochs;
+                    bool fuse[RC_NCHAIN];
+                    fuse_flags(pe, pos, end, nChains, fuse);
                     for (int e = 0; e < pe->h.nEpochs; ++e) {
                         double* c0 = (double*)ctx->dBCarry.p;
                         double* c1 = c0 + (size_t)carrySlots * B;
                         for (int c = 0; c < nChains; ++c) {
+                            if (fuse[c] && e == nE - 1) continue;
+                            const int eArg = (fuse[c] && e == nE - 2) ? (e | RC_E_FUSE) : e;
                             cudaStream_t cs = c == 0 ? st : ctx->chainStream[c];
                             const int p0 = pos + (int)((long long)nModels * c / nChains), p1 = pos + (int)((long long)nModels * (c + 1) / nChains);
                             CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)e], 0));
+                            if (eArg != e) CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)nE - 1], 0));      // the a-values at the shortcut step
                             // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
                             // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
                             struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
@@ -960,7 +988,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                             for (int q = nL - 1; q >= 0; --q) {
                                 cudaStream_t gs = q == 0 ? cs : ctx->grpStream[c][q - 1];
                                 if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch[c], 0));
-                                CK(rc_launch_propagate_keyed(pe->d, e, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
+                                CK(rc_launch_propagate_keyed(pe->d, eArg, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
                                                              (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1,
                                                              (e & 1) ? c1 : c0, carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, p0, p1 - p0, gs));
                                 ++launches;
@@ -1010,6 +1038,12 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
             bool anyKeyed = false, anySelf = false;
             for (int q = pos; q < end; ++q) (hM[q].mode == 1 ? anyKeyed : anySelf) = true;
             putv((long long)(uintptr_t)pe); putv(end); putv(anyKeyed); putv(anySelf);
+            if (pe && anyKeyed) {
+                const int nCh = end - pos >= 16 ? RC_NCHAIN : 1;
+                bool fuse[RC_NCHAIN];
+                fuse_flags(pe, pos, end, nCh, fuse);
+                for (int c = 0; c < nCh; ++c) putv(fuse[c]);
+            }
             pos = end;
         }
         cudaGraphExec_t exec = nullptr;
@@ -1501,6 +1535,7 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
             ctx->optPattern = v;
         }
     }
+    else if (n == "fuse_last") ctx->optFuseLast = value != 0.0;
     else if (n == "pattern_embed") {
         const int v = value != 0.0;
         if (v != ctx->optPatternEmbed) {

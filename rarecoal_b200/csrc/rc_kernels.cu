@@ -1749,6 +1749,8 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
     if (nBins <= 0 || nB <= 0) return cudaSuccess;
+    const int eArg = e;                 // RC_E_FUSE (pattern kernel only)
+    e &= ~RC_E_FUSE;
     const size_t smem = (sizeof(RcKeySmem) + 15) & ~(size_t)15;
     dim3 grid((unsigned)nBins, (unsigned)nB);
     double* out = pOut + (size_t)b0 * pl.nPat;
@@ -1759,9 +1761,9 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
         // ring of RC_PDEPTH slots sized for the group's largest fetch list, aliased with the gathered b of the largest bin
         const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
         const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
-        if (rowMode == RC_MODE_PAT) return rc_launch_pat12(grid, psmem, st, pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
-        if (rowMode == RC_MODE_PAT + 1) return rc_launch_pat25(grid, psmem, st, pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
-        return rc_launch_pat36(grid, psmem, st, pl, e, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        if (rowMode == RC_MODE_PAT) return rc_launch_pat12(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        if (rowMode == RC_MODE_PAT + 1) return rc_launch_pat25(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
+        return rc_launch_pat36(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
     }
     if (rowMode) {
         const size_t rsmem = (sizeof(RcRowSmem) + 15) & ~(size_t)15;

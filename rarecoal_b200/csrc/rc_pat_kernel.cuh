@@ -256,13 +256,17 @@ template <int MAXS>
 #define RC_PATT_MINB 8      // measured on C3: 8 -> 11.0 ms, 10 -> 11.2, 12 -> 11.6 (without this instantiation 11.5)
 #endif
 __global__ void __launch_bounds__(RC_PBLOCK, MAXS <= RC_PAT_MAXT ? RC_PATT_MINB : MAXS <= RC_PAT_MAXS ? RC_PAT_MINB : RC_PATL_MINB)
-rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+rc_propagate_pat_kernel(RcPlanDev pl, int eArg, int binBase, int ringRows, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
                         const RcSEvDev* __restrict__ sevs, const double* __restrict__ ktab, const double* __restrict__ aShort,
                         const double* __restrict__ wpool, const double* __restrict__ bPrev, double* __restrict__ bCur,
                         long long bStride, double* __restrict__ dAcc, double* __restrict__ pOut) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
+    // RC_E_FUSE: the models of this launch execute no grid step in the last epoch (the shortcut applies at its first step) and
+    // every pattern passes it, so this launch — the last but one epoch — finishes the patterns itself (hand-over below)
+    const int e = eArg & ~RC_E_FUSE;
+    const bool fuseLast = (eArg & RC_E_FUSE) != 0;
     // every load of the first level (model header, bin header, epoch record) is issued before the first branch: a warp issues
     // in order, so a branch on one of them would keep the others from starting until it has arrived
     const int mSteps = models[b].nSteps, mMode = models[b].mode, mSShort = models[b].sShort, mMepOff = models[b].mepOff;
@@ -534,6 +538,48 @@ rc_propagate_pat_kernel(RcPlanDev pl, int e, int binBase, int ringRows, const Rc
                         *t = *t + R.b[x];
                     }
                 }
+            if (fuseLast) {
+                // The last epoch would run its one grid step (the step at which the last Join fires), then the shortcut (Core.hs:
+                // 80-118) on these values — its patterns have one live branch, state y holding y + 1 lineages — and end with the
+                // getProb epilogue (Core.hs:49-54): done here, the last epoch's launches (one block set-up per bin and model for a
+                // handful of flops) are not issued at all
+                {
+                    const RcModelEpochDev mL = mep[mMepOff + e + 1];
+                    const int rowPairsL = pl.ep[e + 1].rowPairs;
+                    const double* row = ktab + (mL.tabBase + (long long)pl.lastPairBase[pid]) * 2;
+                    double dlast = 0.0;
+                    for (int s2 = mL.beg; s2 < mL.end; ++s2, row += 2 * (long long)rowPairsL) {
+                        for (int y = 0; y < nOut; ++y) {
+                            const double2 pr = *reinterpret_cast<const double2*>(row + 2 * y);
+                            const double t2 = y + 1 < nOut ? col[(y + 1) * RC_PBLOCK] * pr.y : 0.0;
+                            col[y * RC_PBLOCK] = fma(col[y * RC_PBLOCK], pr.x, t2);                       // updateB, Core.hs:259
+                        }
+                        dlast = fma(*(row - 2 * (long long)pl.lastPairBase[pid] + 1), col[0], dlast);     // updateD, Core.hs:282-288
+                    }
+                    dp = dp + dlast;
+                }
+                const double* aK = aShort + models[b].aShortOff;
+                const int* kid = pl.lastKeyId + (size_t)pid * P;
+                double nrA = 0.0;
+                int popIndex = -1;
+                for (int k = 0; k < P; ++k) {
+                    const double ak = aK[kid[k]];
+                    nrA = nrA + ak;
+                    if (popIndex < 0 && ak > 0.0) popIndex = k;
+                }
+                const double popSize = models[b].Nshort[popIndex < 0 ? 0 : popIndex];
+                double add = 0.0, cc = 1.0;
+                for (int y = 0; y < nOut; ++y) {
+                    const double nd = (double)(y + 1);
+                    cc = cc * ((nrA + nd) / nd);
+                    add = add + col[y * RC_PBLOCK] * (2.0 * popSize / nd / cc);
+                }
+                dp = dp + add;
+                double discFac = 1.0;
+                for (int k = 0; k < P; ++k) discFac = discFac * (pl.support[(size_t)pid * P + k] ? models[b].disc[k] : 1.0);
+                pOut[(size_t)b * nPat + pid] = dp * models[b].theta * pl.combFac[pid] * discFac;
+                return;
+            }
             double* out = bCur + (size_t)b * bStride + pl.dirOff + la.w;
             for (int y = 0; y < nOut; ++y) out[y * RC_PBLOCK] = col[y * RC_PBLOCK];
         } else {

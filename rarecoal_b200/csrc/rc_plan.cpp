@@ -1114,6 +1114,15 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         }
         out.totalKeys = (int)out.keyBranch.size();
         out.lastKeyId.assign(out.keyId.end() - (size_t)nPat * P, out.keyId.end());
+        out.lastPairBase.assign((size_t)nPat, -1);
+        out.lastSingle = nPat > 0;
+        for (int i = 0; i < nPat; ++i) {
+            int rk = -1, nz = 0;
+            for (int k = 0; k < P; ++k) if (pps[(size_t)i].mx[(size_t)(nEpochs - 1) * P + k]) { rk = k; ++nz; }
+            if (nz == 1)
+                out.lastPairBase[(size_t)i] = out.keyPairBase[(size_t)out.ep[(size_t)nEpochs - 1].keyOff + out.lastKeyId[(size_t)i * P + rk]];
+            else out.lastSingle = false;
+        }
     }
 
     lap("trajectory keys");

@@ -97,6 +97,8 @@ struct PlanHost {
     long long maxEpochSlots = 0;           // largest number of live states in one epoch; after the bin images are built: stride
                                            // of the b carry buffers = that (slot order) + the lane-ordered region behind it
     long long dirOff = 0, dirSize = 0;     // lane-ordered region of the carry buffers (direct hand-over between pattern-mode epochs)
+    std::vector<int> lastPairBase;         // [nPat] first pair (in a step row of the last epoch) of the pattern's only live branch there, -1 if it has several
+    bool lastSingle = false;               // every pattern has one live branch in the last epoch
     std::vector<int> grpDirIn;             // per bin group: 1 if its blocks read b in lane order (written by the previous epoch's lanes)
     std::vector<int> slotOff;              // [nEpochs][nPat+1]
     std::vector<long long> epochBase;      // [nEpochs]

@@ -104,6 +104,7 @@ struct RcPlanDev {
     const int* keyThrBase;       // first trajectory-kernel thread of the key
     const int* thrKey;           // trajectory-kernel thread -> key (RcEpochDev::thrOff)
     const int* lastKeyId;        // [nPat][P] keys of the final epoch
+    const int* lastPairBase;     // [nPat] first pair of the pattern's only live branch in a step row of the final epoch (-1: several)
     const int* kBinBase;         // [nEpochs] first entry of the epoch in kBinPatOff / kFetchOff
     const int* nKBins;           // [nEpochs] keyed bins of the epoch
     const int* kBinPatOff;       // per epoch nKBins[e]+1 offsets into kBinPats
@@ -134,6 +135,7 @@ struct RcPlanDev {
 #define RC_HDR_DIRIN 0x40000000
 #define RC_HDR_SEED 0x20000000      // first epoch, pattern mode: b is 1 at the last state of every lane (the pattern itself), else 0
 #define RC_HDR_NB(x) ((x) & 0x1FFFFFFF)
+#define RC_E_FUSE 0x40000000          // epoch argument of the pattern kernel: finish the patterns here, the last epoch is not launched
 #define RC_PLANE_DIROUT 0x80000000u
 #define RC_PLANE_UNIT 0x40000000u     // lane record [2]: the state at local index 0 is e_A (updateD reads it)
 #define RC_HDR_N 16

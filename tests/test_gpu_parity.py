@@ -418,3 +418,28 @@ def test_bounding_box_pattern_mode_after_splits(default_times, key):
     ll_o, probs_o, _ = O.logl(wl.P, wl.max_af, default_times, wl.theta, [1.0] * wl.P, False, ev0, nvec, pats, cnt, wl.total_sites)
     assert _relerr(probs1[0], probs_o) < PROB_RTOL and abs(logl1[0] - ll_o) / abs(ll_o) < LOGL_RTOL
     e.close()
+
+
+def test_last_epoch_finished_by_the_launches_before_it(default_times):
+    # a tree model's last epoch starts with the shortcut and executes no grid step: the launches of the last but one epoch
+    # apply the Join, the shortcut and the epilogue themselves and the last epoch is not launched ("fuse_last", default on).
+    # Same numbers bit for bit, fewer launches; a model whose last epoch does run steps (noShortcut) is not touched
+    nvec, pats, cnt = Wk.c3_problem(max_af=6)
+    e = R.Engine(0)
+    e.set_option("graphs", 0.0)
+    e.set_problem(nvec, 6, pats, cnt, Wk.TOTAL_SITES)
+    specs = [_spec(8, default_times, ev) for ev in Wk.c4_batch(5)]
+    logl1, probs1, st1 = e.eval_models(specs, want_probs=True)
+    n1 = e.stats()["launches"]
+    e.set_option("fuse_last", 0.0)
+    logl0, probs0, st0 = e.eval_models(specs, want_probs=True)
+    n0 = e.stats()["launches"]
+    assert not st0.any() and not st1.any()
+    assert np.array_equal(probs0, probs1) and np.array_equal(logl0, logl1) and n1 < n0
+    e.set_option("fuse_last", 1.0)
+    ns = [_spec(8, default_times, ev, no_shortcut=True) for ev in Wk.c4_batch(2)]
+    la, pa, _ = e.eval_models(ns, want_probs=True)
+    e.set_option("fuse_last", 0.0)
+    lb, pb, _ = e.eval_models(ns, want_probs=True)
+    assert np.array_equal(pa, pb) and np.array_equal(la, lb)
+    e.close()
