@@ -52,7 +52,8 @@ def kind(r):
     return "rows" if "rows" in n else "states"
 
 
-ms = [float(r[col(names["ms"])]) for r in body]
+_tu = {"us": 1e-3, "usecond": 1e-3, "ms": 1.0, "ns": 1e-6, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}.get(units[col(names["ms"])], 1.0)
+ms = [float(r[col(names["ms"])].replace(",", "")) * _tu for r in body]
 tms = sum(ms)
 pipes = {k: sum(float(r[col(names[k])]) * m for r, m in zip(body, ms)) / tms for k in ("smem", "issue", "fp64", "warps")}
 share = {}
@@ -69,12 +70,12 @@ json.dump({
     "pipes_pct_of_peak_time_weighted": {"shared_memory_wavefronts": round(pipes["smem"], 1), "fp64_pipe": round(pipes["fp64"], 1),
                                         "issue_slots": round(pipes["issue"], 1), "warps_active": round(pipes["warps"], 1)},
     "source": "profiles/" + TAG + "_propagate_raw.csv (ncu --set full, per-launch metrics; DRAM = dram__bytes_read.sum + dram__bytes_write.sum summed)",
-    "note": "trajectory tables (~60 MB per model) written by rc_traj_kernel and read here, bin images re-read per model, b carried "
-            "between epoch launches; a few hundred GB/s against the measured 6539 GB/s copy bandwidth - not the bound",
+    "note": "trajectory tables (~57 MB per model) written by rc_traj_kernel and read here, bin images re-read per model, b carried "
+            "between epoch launches (lane-ordered region); a few hundred GB/s against the measured copy bandwidth - not the bound",
 }, open(os.path.join(ROOT, "profiles", TAG + "_traffic.json"), "w"))
 print("| launch | kernel | grid | ms | smem pipe % | issue % | FP64 pipe % | warps % | regs | DRAM rd / wr |")
 for e, r in enumerate(body):
     g = lambda k: r[col(names[k])]
-    print(f"| {e} | {kind(r)} | {g('grid')} | {float(g('ms')):.2f} | {float(g('smem')):.1f} | {float(g('issue')):.1f} | {float(g('fp64')):.1f} | "
+    print(f"| {e} | {kind(r)} | {g('grid')} | {ms[e]:.3f} | {float(g('smem')):.1f} | {float(g('issue')):.1f} | {float(g('fp64')):.1f} | "
           f"{float(g('warps')):.1f} | {g('regs')} | {scale(r[rd], units[rd]) / 1e9:.2f} GB / {scale(r[wr], units[wr]) / 1e6:.0f} MB |")
 print("sum ms", tms, "dram GB", (tot_r + tot_w) / 1e9, "pipes", pipes, "share", share)
