@@ -209,7 +209,8 @@ __device__ __forceinline__ void rc_pat_run(RcPatRegs<MAXS>& R, const unsigned sB
         __syncthreads();       // ... and every thread is done with the slot the next fill overwrites
 #else
         rc_cp_wait<RC_PDEPTH - 2>();
-        __syncthreads();       // (probe: with a warp-level sync here instead — results undefined — C3 ran 3.8 % faster: the barrier is not the bound)
+        __syncthreads();       // (probe: with a warp-level sync here instead — results undefined — C3 ran 3.8 % faster: the barrier is not the
+                               // bound; two grid steps per barrier, the step body instantiated twice per round: 7.59 -> 10.1 ms and a 10-minute build)
         slot = slot + RE_SLOT == RC_PDEPTH * RE_SLOT ? 0u : slot + RE_SLOT;
 #endif
     }
