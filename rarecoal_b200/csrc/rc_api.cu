@@ -964,7 +964,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                             if (eArg != e) CK(cudaStreamWaitEvent(cs, ctx->evTraj[(size_t)nE - 1], 0));      // the a-values at the shortcut step
                             // bin groups of the epoch: tiny / small / large patterns (one thread each), and the rest (rows or states).
                             // The group with the fewest, longest blocks goes first; every further group runs on its own stream.
-                            struct Launch { int binBase, nBins, mode, maxFetch, maxB; };
+                            struct Launch { int binBase, nBins, mode, maxFetch, maxB, z; };
                             Launch L[RC_NGROUP];
                             int nL = 0;
                             for (int v = RC_NGROUP * e; v < RC_NGROUP * (e + 1); ++v) {
@@ -978,17 +978,17 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                                     (long long)(nb0 + nb1) * nModels < 3LL * 7 * ctx->smCount) {
                                     L[nL++] = {pe->h.kBinBase[(size_t)v], nb0 + 1 + nb1, RC_MODE_PAT + 1,
                                                std::max(pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxFetch[(size_t)v + 1]),
-                                               std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1])};
+                                               std::max(pe->h.grpMaxB[(size_t)v], pe->h.grpMaxB[(size_t)v + 1]), RC_PAT12_NP};
                                     ++v;
                                     continue;
                                 }
-                                L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v]};
+                                L[nL++] = {pe->h.kBinBase[(size_t)v], nb0, pe->h.epochMode[(size_t)v], pe->h.grpMaxFetch[(size_t)v], pe->h.grpMaxB[(size_t)v], 1};
                             }
                             if (nL > 1) CK(cudaEventRecord(ctx->evEpoch[c], cs));
                             for (int q = nL - 1; q >= 0; --q) {
                                 cudaStream_t gs = q == 0 ? cs : ctx->grpStream[c][q - 1];
                                 if (q > 0) CK(cudaStreamWaitEvent(gs, ctx->evEpoch[c], 0));
-                                CK(rc_launch_propagate_keyed(pe->d, eArg, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, dM, dMep, dSev,
+                                CK(rc_launch_propagate_keyed(pe->d, eArg, L[q].binBase, L[q].nBins, L[q].mode, L[q].maxFetch, L[q].maxB, L[q].z, dM, dMep, dSev,
                                                              (const double*)ctx->dKTab.p, (const double*)ctx->dAShort.p, dW, (e & 1) ? c0 : c1,
                                                              (e & 1) ? c1 : c0, carrySlots, (double*)ctx->dDAcc.p, (double*)ctx->dPOut.p, p0, p1 - p0, gs));
                                 ++launches;

@@ -1744,7 +1744,7 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
     return cudaGetLastError();
 }
 
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, int zSlices, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st) {
@@ -1761,6 +1761,7 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
         // ring of RC_PDEPTH slots sized for the group's largest fetch list, aliased with the gathered b of the largest bin
         const int ringRows = ((maxFetch + RC_PBLOCK - 1) / RC_PBLOCK) * RC_PBLOCK;
         const size_t psmem = (std::max((size_t)RC_PDEPTH * ringRows * 16, (size_t)maxB * 8) + 15) & ~(size_t)15;
+        grid.z = (unsigned)std::max(1, zSlices);      // > 1: bins of the <RC_PAT_MAXT> group (RC_PAT12_NP patterns per thread there) in a <RC_PAT_MAXS> launch
         if (rowMode == RC_MODE_PAT) return rc_launch_pat12(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         if (rowMode == RC_MODE_PAT + 1) return rc_launch_pat25(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);
         return rc_launch_pat36(grid, psmem, st, pl, eArg, binBase, ringRows, models + b0, mep, sevs, ktab, aShort, wpool, bp, bc, bStride, dac, out);

@@ -27,7 +27,7 @@ cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDe
 cudaError_t rc_launch_pat12(RC_PAT_LAUNCH_ARGS);
 cudaError_t rc_launch_pat25(RC_PAT_LAUNCH_ARGS);
 cudaError_t rc_launch_pat36(RC_PAT_LAUNCH_ARGS);
-cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, const RcModelDev* models,
+cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, int nBins, int rowMode, int maxFetch, int maxB, int zSlices, const RcModelDev* models,
                                       const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab,
                                       const double* aShort, const double* wpool, const double* bPrev, double* bCur,
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st);

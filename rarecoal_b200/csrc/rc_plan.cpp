@@ -870,8 +870,8 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             }
             if (!ok) continue;
             out.grpDirIn[(size_t)v] = 1;
-            // the bin's region of the lane-ordered part: [state of the box][lane], RC_PBLOCK lanes — lane t reads its states at
-            // stride RC_PBLOCK, a warp 256 contiguous bytes per state, straight into registers
+            // the bin's region of the lane-ordered part: [state of the box][lane], RC_DIR_LANES lanes — a lane reads its states at
+            // that stride, a warp 256 contiguous bytes per state, straight into registers
             for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
                 int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
                 hdr[3] |= RC_HDR_DIRIN;
@@ -879,7 +879,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 int nb = (int)(sh & 0xFu);
                 for (int w = 1; w < 5; ++w) nb *= std::max(1, (int)((sh >> (4 * w)) & 0xFu));
                 hdr[12] = (int)dirRun[(size_t)e];
-                dirRun[(size_t)e] += (long long)RC_PBLOCK * nb;
+                dirRun[(size_t)e] += (long long)RC_DIR_LANES * nb;
             }
             for (int q = q0; q < q1; ++q) {
                 const int i = out.kBinPats[(size_t)q];
@@ -892,7 +892,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 ro[3] = (uint32_t)(out.kBinHdr[(size_t)binOf[(size_t)e * nPat + i] * RC_HDR_N + 12] + laneOf[(size_t)e * nPat + i]);
                 // the lane sums into [state][lane] doubles of its block's shared memory
                 int& mb = out.grpMaxB[(size_t)grpOf[(size_t)(e - 1) * nPat + i]];
-                mb = std::max(mb, RC_PBLOCK * nN);
+                mb = std::max(mb, rc_pat_lanes(out.epochMode[(size_t)grpOf[(size_t)(e - 1) * nPat + i]]) * nN);
             }
             out.dirSize = std::max(out.dirSize, dirRun[(size_t)e]);
         }
@@ -1520,7 +1520,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     if (groupIds[(size_t)v].empty()) continue;
                     const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
                     const bool direct = out.grpDirect[(size_t)v] != 0;
-                    if (mode >= 3) pack_range(e, e, RC_PBLOCK, mode, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
+                    if (mode >= 3) pack_range(e, e, rc_pat_lanes(mode), mode, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
                     else if (mode) pack_range(e, e, RC_NPBR, 1, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
                     else pack_range(e, e, RC_NPB, 0, true, groupIds[(size_t)v], offV[(size_t)v], patsV[(size_t)v], direct);
                 }
@@ -1732,7 +1732,7 @@ std::string check_plan(const PlanHost& h) {
             const int b0 = h.kBinBase[(size_t)v];
             for (int bI = b0; bI < b0 + h.nKBins[(size_t)v]; ++bI) {
                 const int p0 = h.kBinPatOff[(size_t)bI], p1 = h.kBinPatOff[(size_t)bI + 1];
-                if (p1 - p0 < 1 || p1 - p0 > (patM ? RC_PBLOCK : rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
+                if (p1 - p0 < 1 || p1 - p0 > (patM ? rc_pat_lanes(h.epochMode[(size_t)v]) : rows ? RC_NPBR : RC_NPB)) return fail("patterns per keyed bin");
                 const int f0 = h.kFetchOff[(size_t)bI], f1 = h.kFetchOff[(size_t)bI + 1];
                 const bool direct = !h.grpDirect.empty() && h.grpDirect[(size_t)v] != 0;
                 if (direct ? f1 != f0 : (f1 - f0 < 1 || f1 - f0 > RC_KROWS - 1)) return fail("pair rows per keyed bin");
@@ -1807,7 +1807,7 @@ std::string check_plan(const PlanHost& h) {
                 if ((hdr[3] & RC_HDR_SEED) && (!patM || e != 0)) return fail("image header seed flag");
                 const bool dirIn = (hdr[3] & RC_HDR_DIRIN) != 0;
                 if (dirIn && (!patM || e == 0 || h.grpDirIn.empty() || !h.grpDirIn[(size_t)v] || hdr[12] < 0 ||
-                              (long long)hdr[12] + (long long)RC_PBLOCK * (np ? nB / np : 0) > h.dirSize))
+                              (long long)hdr[12] + (long long)RC_DIR_LANES * (np ? nB / np : 0) > h.dirSize))
                     return fail("image header direct hand-over");
                 if (hdr[0] != h.kBinPatOff[(size_t)bI] || np != h.kBinPatOff[(size_t)bI + 1] - hdr[0]) return fail("image header patterns");
                 if (hdr[4] != h.kFetchOff[(size_t)bI] || nFetch != h.kFetchOff[(size_t)bI + 1] - hdr[4]) return fail("image header fetch");
@@ -1828,7 +1828,7 @@ std::string check_plan(const PlanHost& h) {
                     for (int r = 0; r < nFetch; ++r) if (!cov[(size_t)r]) return fail("image segment cover");
                     if (bytes != hdr[10]) return fail("image segment bytes");
                 }
-                if (lanes < 1 || lanes > (patM ? RC_PBLOCK : RC_BLOCK) || nB < 0 || nB > (patM ? RC_PBLOCK * patMax : RC_ROW_BCAP))
+                if (lanes < 1 || lanes > (patM ? rc_pat_lanes(h.epochMode[(size_t)v]) : RC_BLOCK) || nB < 0 || nB > (patM ? rc_pat_lanes(h.epochMode[(size_t)v]) * patMax : RC_ROW_BCAP))
                     return fail("image header lanes");
                 if (hdr[6] < 0 || hdr[6] + (long long)lanes * (patM ? RC_PLANE_N / 4 : rows ? RC_RLANE_N / 4 : RC_LANE_N / 4) > nLaneQ || hdr[7] < 0 || hdr[7] + nB > nElemRec)
                     return fail("image record range");
@@ -1862,7 +1862,7 @@ std::string check_plan(const PlanHost& h) {
                         if (r[2] & RC_PLANE_DIROUT) {
                             // the lane applies the next Join itself: next-epoch state index per state, lane-ordered destination
                             const int nOut = (int)((r[2] >> 24) & 0x3Fu);
-                            if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + (long long)(nOut - 1) * RC_PBLOCK >= h.dirSize) return fail("image direct hand-over");
+                            if (e + 1 >= nE || nOut < 1 || nOut > RC_PAT_MAXL || (long long)r[3] + (long long)(nOut - 1) * RC_DIR_LANES >= h.dirSize) return fail("image direct hand-over");
                             if (nOut < h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4] + 1] - h.slotOff[(size_t)(e + 1) * (nPat + 1) + r[4]]) return fail("image direct hand-over states");
                             int mapped = 0;
                             for (int q = 0; q < n; ++q) {

@@ -29,6 +29,15 @@
 // epochMode of a pattern group = RC_MODE_PAT + index of its capacity in {RC_PAT_MAXT, RC_PAT_MAXS, RC_PAT_MAXL}
 #define RC_MODE_PAT 3
 static inline __host__ __device__ int rc_pat_cap(int mode) { return mode == RC_MODE_PAT ? RC_PAT_MAXT : mode == RC_MODE_PAT + 1 ? RC_PAT_MAXS : RC_PAT_MAXL; }
+// patterns per thread of the smallest pattern group (rc_pat_kernel.cuh) — its bins hold RC_PBLOCK * RC_PAT12_NP patterns — and
+// lanes per state in the lane-ordered region of the carry buffers (one stride for the bins of every group).  Two patterns per
+// thread (sharing the per-step ring copies, barrier and slot arithmetic) measured slower on C3: 7.73 ms against 7.61 with 6
+// resident blocks, 7.9 with 5 or 4 — the tier is bound by its shared-memory loads, which two patterns per thread do not reduce.
+#ifndef RC_PAT12_NP
+#define RC_PAT12_NP 1
+#endif
+#define RC_DIR_LANES (RC_PBLOCK * RC_PAT12_NP)
+static inline __host__ __device__ int rc_pat_lanes(int mode) { return mode == RC_MODE_PAT ? RC_PBLOCK * RC_PAT12_NP : RC_PBLOCK; }
 static inline __host__ __device__ int rc_pat_floor(int mode) { return mode == RC_MODE_PAT ? 0 : mode == RC_MODE_PAT + 1 ? RC_PAT_MAXT : RC_PAT_MAXS; }
 #define RC_PLANE_N 16        // words of a pattern-mode lane record
 #define RC_ROW_SUM 11        // with more than 3 other branches: other branches + row length <= RC_ROW_SUM (bounds the kernel variants)
