@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -946,6 +947,21 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         for (auto& th : pool) th.join();
     }
     lap("live sets per pattern");
+    // the same pool for the later per-pattern copy loops: fn(i0, i1) on chunks of patterns with disjoint outputs
+    auto par_for = [&](int n, int chunk, const std::function<void(int, int)>& fn) {
+        if (nThreads == 1 || n <= chunk) { fn(0, n); return; }
+        std::atomic<int> nxt(0);
+        auto w = [&]() {
+            for (;;) {
+                const int i0 = nxt.fetch_add(chunk);
+                if (i0 >= n) break;
+                fn(i0, std::min(n, i0 + chunk));
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nThreads; ++t) pool.emplace_back(w);
+        for (auto& th : pool) th.join();
+    };
     int nnzw = 1, maxLive = 1;
     for (auto& pp : pps) {
         if (!pp.err.empty()) return pp.err;
@@ -1628,21 +1644,23 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     for (int e = 0; e < nEpochs; ++e) out.maxEpochSlots = std::max(out.maxEpochSlots, out.epochSlots[(size_t)e]);
     out.words.assign((size_t)total * nnzw, 0u);
     out.meta.assign((size_t)total, 0u);
-    for (int i = 0; i < nPat; ++i) {
-        const PatPlan& pp = pps[(size_t)i];
-        out.shortcutOK[(size_t)i] = pp.shortcutOK ? 1 : 0;
-        size_t wp = 0, mp = 0;
-        for (int e = 0; e < nEpochs; ++e) {
-            long long g0 = out.epochBase[(size_t)e] + out.slotOff[(size_t)e * (nPat + 1) + i];
-            int n = pp.live[(size_t)e];
-            for (int s = 0; s < n; ++s) {
-                for (int d = 0; d < nnzw; ++d) out.words[(size_t)(g0 + s) * nnzw + d] = pp.words[wp + (size_t)s * c.stride + d];
-                out.meta[(size_t)(g0 + s)] = pp.meta[mp + s];
+    par_for(nPat, 256, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            const PatPlan& pp = pps[(size_t)i];
+            out.shortcutOK[(size_t)i] = pp.shortcutOK ? 1 : 0;
+            size_t wp = 0, mp = 0;
+            for (int e = 0; e < nEpochs; ++e) {
+                long long g0 = out.epochBase[(size_t)e] + out.slotOff[(size_t)e * (nPat + 1) + i];
+                int n = pp.live[(size_t)e];
+                for (int s = 0; s < n; ++s) {
+                    for (int d = 0; d < nnzw; ++d) out.words[(size_t)(g0 + s) * nnzw + d] = pp.words[wp + (size_t)s * c.stride + d];
+                    out.meta[(size_t)(g0 + s)] = pp.meta[mp + s];
+                }
+                wp += (size_t)n * c.stride;
+                mp += (size_t)n;
             }
-            wp += (size_t)n * c.stride;
-            mp += (size_t)n;
         }
-    }
+    });
     // transitions
     out.trBase.assign((size_t)nEpochs, 0);
     out.trEntBase.assign((size_t)nEpochs, 0);
