@@ -171,11 +171,14 @@ struct rc_ctx {
     long long planMisses = 0, planEvictions = 0, planMissesAtCall = 0, planEvictionsAtCall = 0;
     double planBuildMs = 0.0, planBuildMsAtCall = 0.0;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch, dATab;
     int optBigSmemKB = 0;             // > 0: shared-memory budget of the big tier (tests: forces the global-memory mode)
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
+    int optTrajSplit = 0;             // trajectory kernels: 0 one kernel (every allele-count thread of a key repeats its a-chain); 1 the
+                                      // chain once per key, then the pairs (bitwise equal; measured slower: 7.65 against 7.61 ms on C3, 11.7
+                                      // against 11.1 ms on one rank's share of the 8-GPU pattern-sharded step); -1 by batch size (>= 8)
     int optFuseLast = 1;              // a last epoch without grid steps is finished by the launches of the last but one epoch
     int optPatternEmbed = 0;          // ... and live sets that are not boxes on their bounding boxes (rc_plan.cpp, pat_box)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
@@ -710,7 +713,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     double* hW = (double*)(hb + oW);
     RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
     size_t mepPos = 0;
-    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0, carrySlots = 0;
+    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0, carrySlots = 0, aTabDoubles = 0;
     const long long ktabModelMax = (long long)(ctx->optKtabModelMB * 1048576.0 / 16.0);
     const long long ktabTotalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
 
@@ -742,7 +745,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         // ---- keyed mode: per-epoch step ranges and the model's slice of the trajectory table ----
         {
             const int finalEnd = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort : T;
-            long long pairs = 0;
+            long long pairs = 0, aLocal = 0;
             M.mepOff = (int)mepPos;
             for (int e = 0; e < hp.nEpochs; ++e) {
                 RcModelEpochDev& me = hMep[mepPos++];
@@ -750,6 +753,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 me.end = e + 1 < hp.nEpochs ? mh.sevStep[(size_t)e] : finalEnd;
                 if (me.end < me.beg) me.end = me.beg;
                 me.tabBase = ktabPairs + pairs;
+                me.aBase = aTabDoubles + aLocal;
+                aLocal += (long long)(me.end - me.beg) * hp.ep[(size_t)e].nKeys;
                 pairs += (long long)(me.end - me.beg) * hp.ep[(size_t)e].rowPairs;
                 maxRowPairs = std::max<long long>(maxRowPairs, hp.ep[(size_t)e].rowPairs);
             }
@@ -758,6 +763,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 // only models that own a slice of the trajectory table bound the chunk size
                 if (maxPairsOut && pairs > *maxPairsOut) *maxPairsOut = pairs;
                 ktabPairs += pairs;
+                aTabDoubles += aLocal;
                 M.aEndOff = aEndDoubles;
                 M.aShortOff = aShortDoubles;
                 aEndDoubles += hp.totalKeys;
@@ -833,6 +839,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         // the keyed kernel prefetches up to 8 step rows past the end of an epoch: keep that much slack
         size_t needK = (size_t)(std::max<long long>(ktabPairs, 1) + 8 * maxRowPairs + 64) * 16;
         size_t needA = (size_t)std::max<long long>(aEndDoubles, 1) * sizeof(double);
+        size_t needAT = (size_t)std::max<long long>(aTabDoubles, 1) * sizeof(double);
         size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
         // b carried from one epoch's launch to the next (two buffers) and the per-pattern updateD accumulators
         size_t needC = (size_t)std::max<long long>(2 * carrySlots * B, 1) * sizeof(double);
@@ -858,6 +865,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         CK(ctx->dPOut.ensure(needOut));
         CK(ctx->dKTab.ensure(needK));
         CK(ctx->dAEnd.ensure(needA));
+        if (needAT > ctx->dATab.cap) { CK(cudaStreamSynchronize(st)); CK(ctx->dATab.ensure(needAT)); }
         CK(ctx->dAShort.ensure(needS));
     }
 
@@ -931,8 +939,11 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     CK(cudaStreamWaitEvent(ts, ctx->evFork, 0));
                     if (timeIt) CK(rec_timing(ctx->evt[6], ts));
                     for (int e = 0; e < pe->h.nEpochs; ++e) {
-                        CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
-                                          (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, pos, end - pos, ts));
+                        const bool trajSplit = ctx->optTrajSplit >= 0 ? ctx->optTrajSplit != 0 : end - pos >= 8;
+                        CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, pe->h.ep[(size_t)e].nKeys, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
+                                          (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, (double*)ctx->dATab.p,
+                                          trajSplit, pos, end - pos, ts));
+                        if (trajSplit) ++launches;
                         // (the timing record precedes the epoch's join event: a captured side stream must end in a join)
                         if (timeIt && e + 1 == pe->h.nEpochs) { CK(rec_timing(ctx->evt[7], ts)); ctx->trajTimed = true; }
                         CK(cudaEventRecord(ctx->evTraj[(size_t)e], ts));
@@ -1029,7 +1040,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat); putv((long long)ctx->dBigScratch.cap);
         const void* ptrs[] = {db + oModels, db + oSev, db + oMep, db + oW, db + oSizeOff, db + oMaskOff, db + oMasks, db + oSizes,
                               ctx->dTab.p, ctx->dPOut.p, ctx->dKTab.p, ctx->dAEnd.p, ctx->dAShort.p, ctx->dBCarry.p, ctx->dDAcc.p,
-                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p};
+                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p, ctx->dATab.p};
         put(ptrs, sizeof ptrs);
         for (int pos = 0; pos < B;) {
             const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
@@ -1285,7 +1296,7 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
-                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch};
+                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch, &ctx->dATab};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();
@@ -1536,6 +1547,7 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
         }
     }
     else if (n == "fuse_last") ctx->optFuseLast = value != 0.0;
+    else if (n == "traj_split") { ctx->optTrajSplit = value < 0.0 ? -1 : value != 0.0; cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->clear_graphs(); }
     else if (n == "pattern_embed") {
         const int v = value != 0.0;
         if (v != ctx->optPatternEmbed) {

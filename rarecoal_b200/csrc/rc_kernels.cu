@@ -888,6 +888,117 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     }
 }
 
+// The same in two kernels, for batches large enough to be bound by instruction issue rather than by the latency of the chain:
+// all allele-count threads of a key repeat the key's a-chain (two divisions per step).  rc_traj_a_kernel follows the chain
+// once per key and writes a(t) — [step][key] — and rc_traj_b_kernel, one thread per (key, j) as before but without a carried
+// dependency, reads it and writes the pairs.  Same formulas on the same values: the pairs are identical bit for bit.
+__global__ void __launch_bounds__(128)
+rc_traj_a_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+                 const RcSEvDev* __restrict__ sevs, const double* __restrict__ tab, const double* __restrict__ dts,
+                 double* __restrict__ aTab, double* __restrict__ aEnd, double* __restrict__ aShort) {
+    const int b = blockIdx.y;
+    const RcModelDev& M = models[b];
+    if (M.nSteps < 0 || M.mode != 1) return;
+    const RcEpochDev E = pl.ep[e];
+    const RcModelEpochDev me = mep[M.mepOff + e];
+    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= E.nKeys) return;
+    const bool lastEpoch = e + 1 == pl.nEpochs;
+    const int kk = E.keyOff + key;
+    const int k = pl.keyBranch[kk];
+    double a;
+    {
+        const int op = pl.keyOp[kk];
+        const double* aPrev = e > 0 ? aEnd + M.aEndOff + pl.ep[e - 1].keyOff : aEnd;
+        const int pa = pl.keyPa[kk], pb = pl.keyPb[kk];
+        if (op == RC_KOP_INIT) a = (double)pl.keyInit[kk];                 // makeInitCoalState, Core.hs:60
+        else if (op == RC_KOP_COPY) a = aPrev[pa];
+        else if (op == RC_KOP_JOIN) a = aPrev[pb] + aPrev[pa];             // popJoinA: al + ak
+        else if (op == RC_KOP_ZERO) a = 0.0;
+        else {
+            const double m = sevs[M.sevOff + e - 1].m;
+            if (op == RC_KOP_SPLIT_K) a = m * aPrev[pb] + aPrev[pa];       // popSplitA: m * al + ak
+            else a = (1.0 - m) * aPrev[pa];                                // (1 - m) * al
+        }
+    }
+    const int rowLen = rc_row_len(pl.P, pl.A1);
+    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
+    double* out = aTab + me.aBase + key;
+    double2 p0n = make_double2(1.0, 0.0);
+    double dtn = 0.0;
+    if (me.beg < me.end) {
+        p0n = *reinterpret_cast<const double2*>(row);
+        dtn = dts[me.beg];
+    }
+    for (int s = me.beg; s < me.end; ++s, out += E.nKeys, row += rowLen) {
+        if (lastEpoch && s == M.sShort) aShort[M.aShortOff + key] = a;
+        const double2 p0 = p0n;                                               // {EA, 1/N}; 1/N == 0: frozen
+        const double dt = dtn;
+        if (s + 1 < me.end) {
+            p0n = *reinterpret_cast<const double2*>(row + rowLen);
+            dtn = dts[s + 1];
+        }
+        if (dt > 0.0 && p0.y != 0.0) {
+            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * p0.x);         // propagateA, Core.hs:239-240
+        }
+        *out = a;
+    }
+    aEnd[M.aEndOff + kk] = a;
+    if (lastEpoch && M.sShort == me.end) aShort[M.aShortOff + key] = a;
+}
+
+__global__ void __launch_bounds__(128)
+rc_traj_b_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+                 const double* __restrict__ tab, const double* __restrict__ dts, const double* __restrict__ aTab,
+                 double* __restrict__ ktab) {
+    const int b = blockIdx.y;
+    const RcModelDev& M = models[b];
+    if (M.nSteps < 0 || M.mode != 1) return;
+    const RcEpochDev E = pl.ep[e];
+    const RcModelEpochDev me = mep[M.mepOff + e];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nst = me.end - me.beg;
+    for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
+        const double dt = dts[me.beg + i];
+        double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
+        p0[0] = 1.0;                                                          // pair 0 = {1, dt}, as in rc_traj_kernel
+        p0[1] = dt > 0.0 ? dt : 0.0;
+    }
+    if (t >= E.nThr) return;
+    const int key = pl.thrKey[E.thrOff + t];
+    const int kk = E.keyOff + key;
+    const int k = pl.keyBranch[kk];
+    const int j = t - pl.keyThrBase[kk] + 1;
+    const int maxJ = (int)pl.keyMaxJ[kk];
+    const bool hasPair = j <= maxJ;
+    const bool padLast = j == maxJ && rc_pair_stride(j + pl.zeroRow) != j + pl.zeroRow;
+    const bool zeroFirst = pl.zeroRow && j == 1;
+    if (!hasPair && !zeroFirst) return;
+    const double xx = (double)j;
+    double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2;
+    const long long stride = (long long)E.rowPairs * 2;
+    const int rowLen = rc_row_len(pl.P, pl.A1);
+    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
+    const int jOff = hasPair ? 2 * j : 0;
+    const double* aT = aTab + me.aBase + key;
+#pragma unroll 2
+    for (int s = me.beg; s < me.end; ++s, out += stride, row += rowLen, aT += E.nKeys) {
+        const double2 p0 = *reinterpret_cast<const double2*>(row);           // {EA, 1/N}; 1/N == 0: frozen
+        const double2 pj = *reinterpret_cast<const double2*>(row + jOff);    // {CN, E2}
+        const double dt = dts[s];
+        const double a = *aT;
+        double G = 1.0, E2 = 0.0;
+        if (dt > 0.0 && p0.y != 0.0 && hasPair) {
+            const double t1k = pj.x + xx * a * p0.y;                           // Core.hs:270 (new a)
+            G = exp(-(t1k * dt));
+            E2 = pj.y;
+        }
+        if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
+        if (padLast) *reinterpret_cast<double2*>(out + 2) = make_double2(1.0, 0.0);
+        if (zeroFirst) *reinterpret_cast<double2*>(out - 2) = make_double2(1.0, 0.0);
+    }
+}
+
 // rc_propagate_keyed_kernel — the state side.  One live state per thread; per non-zero component one LDS.128 of the
 // pair {G, E2}, one multiply into the decay factor, one LDS.64 of the neighbour and one FMA:
 //     b'(x) = b(x) * prod_k G_k(x_k) + sum_k b(x + e_k) E2_k(x_k)            (Core.hs:259)
@@ -1735,12 +1846,20 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
     }
 }
 
-cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
+cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, int nKeys, const RcModelDev* models, const RcModelEpochDev* mep,
                            const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
-                           double* aEnd, double* aShort, int b0, int nB, cudaStream_t st) {
+                           double* aEnd, double* aShort, double* aTab, bool split, int b0, int nB, cudaStream_t st) {
     if (nB <= 0) return cudaSuccess;
     dim3 grid((unsigned)((nThr + 127) / 128), (unsigned)nB);
-    rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, ktab, aEnd, aShort);
+    if (!split) {
+        rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, ktab, aEnd, aShort);
+        return cudaGetLastError();
+    }
+    dim3 gridA((unsigned)((nKeys + 127) / 128), (unsigned)nB);
+    rc_traj_a_kernel<<<gridA, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, aTab, aEnd, aShort);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    rc_traj_b_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, tab, dts, aTab, ktab);
     return cudaGetLastError();
 }
 

@@ -443,3 +443,29 @@ def test_last_epoch_finished_by_the_launches_before_it(default_times):
     lb, pb, _ = e.eval_models(ns, want_probs=True)
     assert np.array_equal(pa, pb) and np.array_equal(la, lb)
     e.close()
+
+
+@pytest.mark.parametrize("key", ["c3", "c2"])
+def test_split_trajectory_kernels_equal_the_fused_one(default_times, key):
+    # "traj_split": the a-chain once per key (rc_traj_a_kernel), then the pairs per (key, allele count) (rc_traj_b_kernel) —
+    # chosen for batches of 8 or more models — against the single kernel in which every allele-count thread repeats the chain:
+    # same formulas on the same values, so the probabilities are equal bit for bit
+    if key == "c3":
+        nvec, pats, cnt = Wk.c3_problem(max_af=6)
+        P, max_af, sites = 8, 6, Wk.TOTAL_SITES
+        specs = [_spec(8, default_times, ev) for ev in Wk.c4_batch(5)]
+    else:
+        wl = Wk.get("c2")
+        nvec, pats, cnt = wl.problem()
+        P, max_af, sites = wl.P, wl.max_af, wl.total_sites
+        specs = [_spec(P, default_times, ev, wl.theta) for ev in wl.proposal_batches(1, 3, seed=3)[0]]
+    e = R.Engine(0)
+    e.set_problem(nvec, max_af, pats, cnt, sites)
+    out = []
+    for mode in (0.0, 1.0):
+        e.set_option("traj_split", mode)
+        logl, probs, st = e.eval_models(specs, want_probs=True)
+        assert not st.any()
+        out.append((logl, probs))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    e.close()
