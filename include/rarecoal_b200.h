@@ -265,6 +265,11 @@ int rc_template_to_json(const char* text, char* out, int cap, char* err, int err
  * -RC_ERR_MODEL (unknown branch, violated constraint) with a message in err.                        */
 int rc_template_instantiate(const char* text, int nParams, const char* const* names, const double* values,
                             rc_event* out, int cap, char* err, int errCap);
+/* The same for B parameter vectors (values[B][nParams]), the template parsed once: events of the models one after the other in
+ * `out` (evOff[b] .. evOff[b+1], ready for rc_eval), per model a status (0, RC_ERR_MODEL, RC_ERR_TEMPLATE: no events) and, if
+ * `penalty` is given, getRegularizationPenalty.  Returns the number of events or a negative code.                              */
+int rc_template_instantiate_batch(const char* text, int nParams, const char* const* names, int B, const double* values, double reg,
+                                  rc_event* out, int cap, int32_t* evOff, int32_t* status, double* penalty, char* err, int errCap);
 /* makeParameterDict (ModelTemplate.hs:243-255): text of a maxl ("name value") or mcmc ('#' header, 3 lines skipped,
  * MaxL column) output file.  namesOut receives the names separated by '\n'.  Returns the number of pairs.          */
 int rc_params_parse(const char* text, char* namesOut, int namesCap, double* values, int cap);

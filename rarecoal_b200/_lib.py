@@ -68,6 +68,8 @@ SIGNATURES = {
     "rc_ss_fill_up": (C.c_int, [_vp, _ip, C.c_int, _ip, C.c_int]),
     "rc_template_to_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "rc_template_instantiate": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _dp, _evp, C.c_int, C.c_char_p, C.c_int]),
+    "rc_template_instantiate_batch": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _dp, C.c_double, _evp, C.c_int,
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp, C.c_char_p, C.c_int]),
     "rc_params_parse": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _dp, C.c_int]),
     "rc_hist_read": (_vp, [C.c_char_p, C.c_char_p, C.c_int]),
     "rc_hist_free": (None, [_vp]),

@@ -267,12 +267,10 @@ int rc_template_to_json(const char* text, char* out, int cap, char* err, int err
     return 0;
 }
 
-int rc_template_instantiate(const char* text, int nParams, const char* const* names, const double* values, rc_event* out,
-                            int cap, char* err, int errCap) {
-    if (!text || nParams < 0 || (nParams > 0 && (!names || !values))) return RC_ERR_ARG;
-    Template t;
-    std::string e;
-    if (!parse_template(text, t, e)) { copy_out(e, err, errCap); return -RC_ERR_TEMPLATE; }
+// instantiateModel for one parameter vector on a parsed template (ModelTemplate.hs:176-241): 0, or -RC_ERR_MODEL / -RC_ERR_TEMPLATE
+// with a message
+static int instantiate_one(const Template& t, int nParams, const char* const* names, const double* values, std::vector<rc_event>& evs,
+                           std::string& msg) {
     bool missing = false;
     std::string missingName;
     auto get = [&](const ParamSpec& p) -> double {
@@ -286,11 +284,11 @@ int rc_template_instantiate(const char* text, int nParams, const char* const* na
         for (size_t i = 0; i < t.branches.size(); ++i) if (t.branches[i] == n) return (int)i;
         return -1;
     };
-    std::vector<rc_event> evs;
+    evs.clear();
     for (const MTEvent& m : t.events) {
         int a = branch(m.a), b = m.b.empty() ? 0 : branch(m.b);
         if (a < 0 || b < 0) {
-            copy_out("did not find model-branch name \"" + (a < 0 ? m.a : m.b) + "\"", err, errCap);
+            msg = "did not find model-branch name \"" + (a < 0 ? m.a : m.b) + "\"";
             return -RC_ERR_MODEL;                     // getModelBranchIndex, ModelTemplate.hs:215-219
         }
         double tt = get(m.t);
@@ -312,20 +310,60 @@ int rc_template_instantiate(const char* text, int nParams, const char* const* na
         }
     }
     if (missing) {
-        copy_out("Error in Template: could not find parameter \"" + missingName + "\"", err, errCap);
+        msg = "Error in Template: could not find parameter \"" + missingName + "\"";
         return -RC_ERR_TEMPLATE;                      // RarecoalModeltemplateException, ModelTemplate.hs:226
     }
     for (const MTConstraint& c : t.constraints) {     // validateConstraints, ModelTemplate.hs:229-241
         double p1 = get(c.lhs), p2 = get(c.rhs);
-        if (missing) { copy_out("Error in Template: could not find parameter \"" + missingName + "\"", err, errCap); return -RC_ERR_TEMPLATE; }
+        if (missing) { msg = "Error in Template: could not find parameter \"" + missingName + "\""; return -RC_ERR_TEMPLATE; }
         if ((c.greater && p1 <= p2) || (!c.greater && p1 >= p2)) {
-            copy_out("constraint violated", err, errCap);
+            msg = "constraint violated";
             return -RC_ERR_MODEL;
         }
     }
+    return 0;
+}
+
+int rc_template_instantiate(const char* text, int nParams, const char* const* names, const double* values, rc_event* out,
+                            int cap, char* err, int errCap) {
+    if (!text || nParams < 0 || (nParams > 0 && (!names || !values))) return RC_ERR_ARG;
+    Template t;
+    std::string e;
+    if (!parse_template(text, t, e)) { copy_out(e, err, errCap); return -RC_ERR_TEMPLATE; }
+    std::vector<rc_event> evs;
+    const int rc = instantiate_one(t, nParams, names, values, evs, e);
+    if (rc < 0) { copy_out(e, err, errCap); return rc; }
     if (out)
         for (size_t i = 0; i < evs.size() && (int)i < cap; ++i) out[i] = evs[i];
     return (int)evs.size();
+}
+
+// The same for B parameter vectors (values[B][nParams]) with the template parsed once: the events of the models one after the
+// other in `out` (evOff[b] .. evOff[b + 1]), per model a status (0, RC_ERR_MODEL or RC_ERR_TEMPLATE: no events) and, if
+// `penalty` is given, the regularisation penalty (rc_reg_penalty).  What an optimiser or sampler needs per step as one call;
+// returns the number of events or a negative code (template does not parse, `out` too small).
+int rc_template_instantiate_batch(const char* text, int nParams, const char* const* names, int B, const double* values, double reg,
+                                  rc_event* out, int cap, int32_t* evOff, int32_t* status, double* penalty, char* err, int errCap) {
+    if (!text || nParams < 0 || B < 0 || (nParams > 0 && (!names || !values)) || !out || !evOff || !status) return RC_ERR_ARG;
+    Template t;
+    std::string e;
+    if (!parse_template(text, t, e)) { copy_out(e, err, errCap); return -RC_ERR_TEMPLATE; }
+    std::vector<rc_event> evs;
+    int n = 0;
+    evOff[0] = 0;
+    for (int b = 0; b < B; ++b) {
+        std::string msg;
+        const int rc = instantiate_one(t, nParams, names, values + (size_t)b * nParams, evs, msg);
+        status[b] = rc < 0 ? -rc : 0;
+        if (rc < 0) evs.clear();
+        if (n + (int)evs.size() > cap) { copy_out("rc_template_instantiate_batch: event buffer too small", err, errCap); return RC_ERR_ARG; }
+        for (const rc_event& ev : evs) out[n++] = ev;
+        evOff[b + 1] = n;
+        if (penalty) penalty[b] = rc < 0 ? 0.0 : rc_reg_penalty((int)t.branches.size(), reg, out + evOff[b], (int)evs.size());
+        if (rc < 0 && e.empty()) e = msg;
+    }
+    if (!e.empty()) copy_out(e, err, errCap);
+    return n;
 }
 
 // makeParameterDict (ModelTemplate.hs:243-263): text of a maxl (name value) or mcmc ('#' first, skip 3 lines, MaxL

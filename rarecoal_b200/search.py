@@ -12,6 +12,7 @@ Trajectories are not bit-comparable with GSL / System.Random (pa
 are the same function (minFunc, MaxUtils.hs:63-76) evaluated on the GPU.
 Output files keep the reference's names and layouts (Maxl.hs:99-116, Mcmc.hs:211-244, MaxUtils.hs:125-195).
 """
+import ctypes as C
 import math
 import sys
 from decimal import Decimal
@@ -57,32 +58,38 @@ class Objective:
         eng.set_times(self.times)
         self.n_evals = 0
         self.n_launches = 0
+        self._names_c = self._text_c = self._ev = None
 
     def __call__(self, X):
-        X = np.atleast_2d(np.asarray(X, dtype=float))
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=float)))
         lib = L.load()
-        evs, off, ok, pen = [], [0], [], []
-        for x in X:
-            try:
-                ev = F.instantiateEvents(self.mt, list(zip(self.names, x.tolist())))
-                arr = _events_array(ev)
-                pen.append(lib.rc_reg_penalty(self.P, self.opts.optRegPenalty, arr, len(ev)))
-                evs.extend(ev)
-                ok.append(True)
-            except RarecoalException:
-                pen.append(0.0)
-                ok.append(False)
-            off.append(len(evs))
-        B = len(X)
+        B, k = X.shape
+        # one call instantiates the template for the whole batch (parsed once) and returns the events packed for rc_eval, the
+        # per-model status (a violated constraint, ModelTemplate.hs:229-241, is a Left: the 1e20 penalty) and the regularisation
+        # penalties
+        if self._names_c is None:
+            self._names_c = (C.c_char_p * max(1, k))(*[n.encode() for n in self.names])
+            self._text_c = self.mt.text.encode()
+        cap = B * (2 * len(self.mt.mtEvents) + 1)
+        if self._ev is None or len(self._ev) < cap:
+            self._ev = (L.rc_event * max(1, cap))()
+        off = np.zeros(B + 1, dtype=np.int32)
+        st = np.zeros(B, dtype=np.int32)
+        pen = np.zeros(B)
+        err = C.create_string_buffer(256)
+        n = lib.rc_template_instantiate_batch(self._text_c, k, self._names_c, B, X.ctypes.data_as(C.POINTER(C.c_double)),
+                                              float(self.opts.optRegPenalty), self._ev, cap, off.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              st.ctypes.data_as(C.POINTER(C.c_int32)), pen.ctypes.data_as(C.POINTER(C.c_double)), err, 256)
+        if n < 0:
+            raise RarecoalException(err.value.decode() or "template instantiation failed")
+        ok = st == 0
         scores = np.full(B, PENALTY)
-        if any(ok):
-            logl, _, status = self.eng.eval_raw(_events_array(evs), np.array(off, dtype=np.int32),
-                                                np.full(B, self.opts.optTheta), np.ones(B * self.P),
+        if ok.any():
+            logl, _, status = self.eng.eval_raw(self._ev, off, np.full(B, self.opts.optTheta), np.ones(B * self.P),
                                                 self.opts.optNoShortcut, self.hp.siteRed)
             self.n_launches += 1
-            for b in range(B):
-                if ok[b] and status[b] == 0 and np.isfinite(logl[b]) and np.isfinite(pen[b]):
-                    scores[b] = -logl[b] + self.hp.siteRed * pen[b]
+            good = ok & (status == 0) & np.isfinite(logl) & np.isfinite(pen)
+            scores[good] = -logl[good] + self.hp.siteRed * pen[good]
         self.n_evals += B
         return scores
 

@@ -183,3 +183,35 @@ def test_workload_templates_instantiate_to_the_written_out_events(fourpop):
     assert F.getParamNames(mt) == [n for n, _ in Wk.c5_param_dict()]           # optimiser-vector order
     assert any(isinstance(e, F.MTGrowthRate) for e in mt.mtEvents)
     assert F.getParamNames(F.parseModelTemplate(Wk.C3_TEMPLATE)) == Wk.c3_param_names()
+
+
+def test_batched_instantiation_equals_one_at_a_time(fourpop):
+    # rc_template_instantiate_batch (what the optimiser's objective calls once per step): same events, offsets, statuses and
+    # regularisation penalties as instantiating and penalising model by model; a violated constraint gives a status, no events
+    import ctypes as C
+    from rarecoal_b200 import _lib as L
+    from rarecoal_b200.api import _events_array
+    lib = L.load()
+    text = open(os.path.join(GOLDEN, "fourPop.template.txt")).read()          # CONSTRAINTS = [C <tAdm_FAM_SIB> > 0.00022]
+    mt = F.parseModelTemplate(text)
+    names = F.getParamNames(mt)
+    x0 = np.array([fourpop["params"][n] for n in names])
+    X = np.stack([x0, x0 * 1.01, x0 * 0.99, x0])
+    X[3, names.index("tAdm_FAM_SIB")] = 0.0001            # violates the constraint
+    B, k = X.shape
+    names_c = (C.c_char_p * k)(*[n.encode() for n in names])
+    cap = B * (2 * len(mt.mtEvents) + 1)
+    ev = (L.rc_event * cap)()
+    off, st, pen = np.zeros(B + 1, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B)
+    err = C.create_string_buffer(256)
+    n = lib.rc_template_instantiate_batch(text.encode(), k, names_c, B, X.ctypes.data_as(C.POINTER(C.c_double)), 10.0, ev, cap,
+                                          off.ctypes.data_as(C.POINTER(C.c_int32)), st.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          pen.ctypes.data_as(C.POINTER(C.c_double)), err, 256)
+    assert n == off[B] and list(st) == [0, 0, 0, L.RC_ERR_MODEL] and off[3] == off[4]
+    for b in range(3):
+        one = F.instantiateEvents(mt, list(zip(names, X[b].tolist())))
+        got = [(ev[i].t, ev[i].type, ev[i].k, ev[i].l, ev[i].v) for i in range(off[b], off[b + 1])]
+        assert got == one
+        assert pen[b] == lib.rc_reg_penalty(4, 10.0, _events_array(one), len(one))
+    with pytest.raises(F.RarecoalModelException):
+        F.instantiateEvents(mt, list(zip(names, X[3].tolist())))
