@@ -192,7 +192,52 @@ struct Ctx {
     }
 };
 
-typedef std::unordered_map<uint64_t, int> Index;
+// state key -> index.  Open addressing over a flat array that keeps its capacity across clear(): the planner builds a few of
+// these per pattern and epoch (live sets of 1 - 700 states), and node allocation made std::unordered_map the largest item of
+// the per-pattern phase.  The subset of the map interface the planner uses; keys are < 2^63, so ~0 marks an empty slot.
+class Index {
+public:
+    typedef std::pair<uint64_t, int> Slot;
+    typedef Slot* iterator;
+    typedef const Slot* const_iterator;
+    Index() { rehash(32); }
+    void clear() {
+        for (Slot& s : t_) s.first = EMPTY;
+        n_ = 0;
+    }
+    iterator end() { return nullptr; }
+    const_iterator end() const { return nullptr; }
+    iterator find(uint64_t k) { return const_cast<iterator>(static_cast<const Index*>(this)->find(k)); }
+    const_iterator find(uint64_t k) const {
+        for (size_t i = hash(k);; i = (i + 1) & mask_) {
+            if (t_[i].first == k) return &t_[i];
+            if (t_[i].first == EMPTY) return nullptr;
+        }
+    }
+    std::pair<iterator, bool> emplace(uint64_t k, int v) {
+        if ((n_ + 1) * 2 > t_.size()) rehash(t_.size() * 2);
+        for (size_t i = hash(k);; i = (i + 1) & mask_) {
+            if (t_[i].first == k) return {&t_[i], false};
+            if (t_[i].first == EMPTY) { t_[i] = Slot(k, v); ++n_; return {&t_[i], true}; }
+        }
+    }
+    int& operator[](uint64_t k) { return emplace(k, 0).first->second; }
+    size_t size() const { return n_; }
+    void swap(Index& o) { t_.swap(o.t_); std::swap(n_, o.n_); std::swap(mask_, o.mask_); }
+private:
+    static constexpr uint64_t EMPTY = ~0ull;
+    std::vector<Slot> t_;
+    size_t n_ = 0, mask_ = 0;
+    size_t hash(uint64_t k) const { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> 29) & mask_; }
+    void rehash(size_t cap) {
+        std::vector<Slot> old;
+        old.swap(t_);
+        t_.assign(cap, Slot(EMPTY, 0));
+        mask_ = cap - 1;
+        n_ = 0;
+        for (const Slot& s : old) if (s.first != EMPTY) emplace(s.first, s.second);
+    }
+};
 
 // fillUpStateSpace over explicit states: for every seed, every y with 1 <= y_k <= x_k where x_k > 0
 // (component 0 slowest), first occurrence kept (nub).
@@ -413,7 +458,7 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
         struct Rec { uint64_t key; int src; uint32_t widx; };
         std::vector<Rec> recs;
         seeds.clear();
-        std::unordered_map<uint64_t, char> pos;          // target -> b' > 0 ?
+        Index pos;                                       // target -> b' > 0 ?
         if (e.type == RC_EV_JOIN_D) {                      // Core.hs:172-188
             Index seen;
             for (size_t i = 0; i < L.size(); ++i) {
@@ -425,7 +470,7 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
                 uint64_t h = c.key(y);
                 recs.push_back({h, (int)i, RC_W_ONE});
                 if (seen.emplace(h, 0).second) seeds.push_back(y);   // nub newNonZeroStateIds (no b>0 filter)
-                char& pz = pos[h];
+                int& pz = pos[h];
                 pz = pz || Z[i];
             }
             apos[k] = apos[k] || apos[l];                // Core.hs:165-170
@@ -441,7 +486,7 @@ void plan_pattern(const Ctx& c, const int32_t* m, const int32_t* nVec, const std
                     uint64_t h = c.key(y);
                     recs.push_back({h, (int)i, (uint32_t)(xl * (c.maxAf + 1) + s)});
                     bool wpos = e.mclass == 2 || (e.mclass == 0 && s == 0) || (e.mclass == 1 && s == xl);
-                    char& pz = pos[h];
+                    int& pz = pos[h];
                     pz = pz || (Z[i] && wpos);
                     targets.emplace_back(h, y);
                 }
