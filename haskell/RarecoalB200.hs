@@ -10,7 +10,7 @@
 -- This module was written against the reference at v1.5.1; it cannot be compiled in the build image of this
 -- repository (no ghc) and is shipped as source for the maintainer.  See INTEGRATION.md.
 module RarecoalLib.RarecoalB200
-    ( B200Context, withB200, setProblem, setTimes, evalModels, B200Result(..)
+    ( B200Context, withB200, withB200Multi, setProblem, setTimes, evalModels, B200Result(..)
     ) where
 
 import           Control.Exception     (bracket, throwIO)
@@ -48,12 +48,15 @@ toRcEvent (ModelEvent t e) = case e of
 
 -- `safe` calls from a bound thread: rc_eval blocks on the GPU; one context per OS thread.
 foreign import ccall safe "rc_create"      c_rc_create      :: CInt -> Ptr (Ptr RcCtx) -> IO CInt
+-- one context that drives the first n GPUs of the process (devices = nullPtr): rc_eval then shards the models of a batch over
+-- them, or the patterns of a single likelihood with an NCCL all-reduce of the partial sums — what parMap does with cores
+foreign import ccall safe "rc_create_multi" c_rc_create_multi :: CInt -> Ptr Int32 -> Ptr (Ptr RcCtx) -> IO CInt
 foreign import ccall safe "rc_destroy"     c_rc_destroy     :: Ptr RcCtx -> IO ()
 foreign import ccall safe "rc_last_error"  c_rc_last_error  :: Ptr RcCtx -> IO CString
 foreign import ccall safe "rc_set_problem" c_rc_set_problem ::
     Ptr RcCtx -> CInt -> CInt -> CInt -> Ptr Int32 -> Ptr Int32 -> Ptr Int64 -> Int64 -> IO CInt
 foreign import ccall safe "rc_set_times"   c_rc_set_times   :: Ptr RcCtx -> CInt -> Ptr Double -> IO CInt
--- mNoShortcut is a field of every ModelSpec (StateSpace.hs:49): rc_eval_models takes one flag per model
+-- mNoShortcut is a field of every ModelSpec (StateSpace.hs:48): rc_eval_models takes one flag per model
 foreign import ccall safe "rc_eval_models" c_rc_eval_models ::
     Ptr RcCtx -> CInt -> Ptr RcEvent -> Ptr Int32 -> Ptr Double -> Ptr Double -> Ptr Int32 -> Double
     -> Ptr Double -> Ptr Double -> Ptr Int32 -> IO CInt
@@ -73,6 +76,16 @@ withB200 device = bracket create destroy
     create = alloca $ \pp -> do
         rc <- c_rc_create (fromIntegral device) pp
         when (rc /= 0) $ throwIO (RarecoalCompException "rc_create failed: no usable CUDA device")
+        B200Context <$> peek pp
+    destroy (B200Context p) = c_rc_destroy p
+
+-- | The same over the first @n@ GPUs of the machine (@--nrGpus@): every call below works unchanged on such a context.
+withB200Multi :: Int -> (B200Context -> IO a) -> IO a
+withB200Multi n = bracket create destroy
+  where
+    create = alloca $ \pp -> do
+        rc <- c_rc_create_multi (fromIntegral n) nullPtr pp
+        when (rc /= 0) $ throwIO (RarecoalCompException ("rc_create_multi failed for " ++ show n ++ " devices"))
         B200Context <$> peek pp
     destroy (B200Context p) = c_rc_destroy p
 
