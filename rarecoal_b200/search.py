@@ -59,6 +59,8 @@ class Objective:
         self.n_evals = 0
         self.n_launches = 0
         self._names_c = self._text_c = self._ev = None
+        self.gpu_ms = self.host_ms = self.plan_ms = 0.0
+        self.plan_misses = 0
 
     def __call__(self, X):
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=float)))
@@ -88,6 +90,11 @@ class Objective:
             logl, _, status = self.eng.eval_raw(self._ev, off, np.full(B, self.opts.optTheta), np.ones(B * self.P),
                                                 self.opts.optNoShortcut, self.hp.siteRed)
             self.n_launches += 1
+            st_ = self.eng.stats()
+            self.gpu_ms += st_["total_ms"]
+            self.host_ms += st_["host_ms"]
+            self.plan_ms += st_["plan_build_ms"]
+            self.plan_misses += st_["plan_misses"]
             good = ok & (status == 0) & np.isfinite(logl) & np.isfinite(pen)
             scores[good] = -logl[good] + self.hp.siteRed * pen[good]
         self.n_evals += B
@@ -289,7 +296,8 @@ def run_maxl(a, opts, mt, params, hp, eng):
         for row in trace:
             h.write("\t".join(hs_show(v) for v in row) + "\n")
     _write_fit_tables(a.prefix, opts, mt, list(zip(names, x.tolist())), hp, eng)
-    print(f"maxl: score {score!r} after {f.n_evals} likelihoods in {f.n_launches} launches", file=sys.stderr)
+    print(f"maxl: score {score!r} after {f.n_evals} likelihoods in {f.n_launches} launches (GPU {f.gpu_ms / 1e3:.2f} s, host side of the "
+          f"calls {f.host_ms / 1e3:.2f} s of which {f.plan_misses} transition plans built in {f.plan_ms / 1e3:.2f} s)", file=sys.stderr)
     return x, score
 
 
