@@ -644,7 +644,6 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
     std::vector<long long> recPos((size_t)nE * nPat, -1);
     std::vector<int> elPos((size_t)nE * nPat, 0), grpOf((size_t)nE * nPat, 0), boxN((size_t)nE * nPat, 0), laneOf((size_t)nE * nPat, 0),
         binOf((size_t)nE * nPat, 0);
-    std::vector<long long> patElemEnd((size_t)nE, 0);
     // gather record of the state with reference index `ref` of pattern i in epoch e
     auto gather_rec = [&](int e, int i, int ref, int live, uint32_t& r0, uint32_t& r1) -> bool {
         if (e == 0) {
@@ -661,24 +660,30 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
         r1 = (uint32_t)out.slotOff[(size_t)(e - 1) * (nPat + 1) + i] | ((uint32_t)(b - a) << RC_IMG_CNT_SHIFT);
         return true;
     };
-    for (int v = 0; v < nE * RC_NGROUP; ++v) {
+    // every bin group builds its records into vectors of its own (the groups are independent: a pattern is in one group per
+    // epoch), side by side on the planner's threads; positions are local until the groups are put one behind the other below
+    const int nGrp = nE * RC_NGROUP;
+    std::vector<std::vector<uint32_t>> grpLane((size_t)nGrp), grpElem((size_t)nGrp);
+    std::vector<std::string> grpErr((size_t)nGrp);
+    auto do_group = [&](int v) {
+        std::vector<uint32_t>& GL = grpLane[(size_t)v];
+        std::vector<uint32_t>& GE = grpElem[(size_t)v];
+        std::string& gerr = grpErr[(size_t)v];
         const int e = v / RC_NGROUP;
         const bool rows = out.epochMode[(size_t)v] != 0, patM = out.epochMode[(size_t)v] >= 3;
         const int patMax = rc_pat_cap(out.epochMode[(size_t)v]);
         const int* so = &out.slotOff[(size_t)e * (nPat + 1)];
         const int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
         const int b0 = out.kBinBase[(size_t)v];
-        if (v % RC_NGROUP == 0) out.ep[(size_t)e].elBase = (int)(out.kElem.size() / 2);
         for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
             const int p0 = out.kBinPatOff[(size_t)bI], p1 = out.kBinPatOff[(size_t)bI + 1];
-            if (out.kLane.size() / 4 > 0x7FFFFFFFull || out.kElem.size() / 2 > 0x7FFFFFFFull) return "bin images too large";
             int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
             hdr[0] = p0;
             hdr[1] = p1 - p0;
             hdr[4] = out.kFetchOff[(size_t)bI];
             hdr[5] = out.kFetchOff[(size_t)bI + 1] - out.kFetchOff[(size_t)bI];
-            hdr[6] = (int)(out.kLane.size() / 4);
-            hdr[7] = (int)(out.kElem.size() / 2);
+            hdr[6] = (int)(GL.size() / 4);
+            hdr[7] = (int)(GE.size() / 2);
             hdr[8] = out.binSegOff[(size_t)bI];
             hdr[9] = out.binSegCnt[(size_t)bI];
             hdr[10] = out.binSegBytes[(size_t)bI];
@@ -696,7 +701,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                     const bool full = out.patFull[(size_t)e * nPat + i] != 0;
                     PatBox pb;
                     if (!pat_box(&out.maxX[((size_t)e * nPat + i) * P], &out.minX[((size_t)e * nPat + i) * P], full, (int)((pr >> 8) & 0xFFu), P, patMax, pb))
-                        return "pattern-mode bin with an unsuitable pattern";
+                        { gerr = "pattern-mode bin with an unsuitable pattern"; return; }
                     const uint32_t shape = pb.shape;
                     const int nS = pb.nS, nU = pb.nU, nBox = pb.n;
                     const int* dims = pb.dims;
@@ -704,7 +709,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                     int Mp[4];
                     for (int q = 0; q < 4; ++q) Mp[q] = std::max(1, (int)((shape >> (4 * (q + 1))) & 0xFu));
                     const int SA = Mp[0] * Mp[1] * Mp[2] * Mp[3];
-                    if (live > nBox || (full && live != nBox)) return "pattern-mode image: shape does not match the live set";
+                    if (live > nBox || (full && live != nBox)) { gerr = "pattern-mode image: shape does not match the live set"; return; }
                     uint32_t rec[RC_PLANE_N];
                     for (int q = 0; q < RC_PLANE_N; ++q) rec[q] = 0u;
                     const bool direct = out.grpDirect[(size_t)v] != 0;
@@ -712,12 +717,12 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                         // an unused slot points at pair row 0, {1, dt}: a neutral decay factor (direct bins have no ring: marker);
                         // a branch that includes the value 0 starts one row earlier, at the key's leading {1, 0} pair
                         const uint32_t row = direct ? (uint32_t)(RC_KROWS - 1) : q < 1 + nS + nU ? (uint32_t)rb[dims[q]] - ((pb.zeroMask >> q) & 1u) : 0u;
-                        if (row > 0xFFu) return "pattern-mode image out of range (pair row)";
+                        if (row > 0xFFu) { gerr = "pattern-mode image out of range (pair row)"; return; }
                         rec[q >> 2] |= row << (8 * (q & 3));
                     }
                     if (direct) {
                         // first pair of the pattern's only key inside a step row of the trajectory table
-                        if (nS + nU != 0) return "direct group with a multi-branch pattern";
+                        if (nS + nU != 0) { gerr = "direct group with a multi-branch pattern"; return; }
                         rec[15] = (uint32_t)out.keyPairBase[(size_t)out.ep[(size_t)e].keyOff + out.keyId[((size_t)e * nPat + i) * P + pb.rk]];
                     }
                     // every live state (reference order) at its place in the box; the places without one stay empty (0xFF: b = 0)
@@ -739,27 +744,27 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                         bool in = a >= 0 && a < MA && other >= 0 && other < SA;
                         for (int q = 0; q < nS && in; ++q) in = xs[q] >= 0 && xs[q] < Mp[q];
                         for (int q = 0; q < nU && in; ++q) in = x[dims[1 + nS + q]] == 1;
-                        if (!in) return "pattern-mode image out of range (state outside the box)";
+                        if (!in) { gerr = "pattern-mode image out of range (state outside the box)"; return; }
                         const int idx = a * SA + other;
-                        if (ref > 0xFE || ((rec[6 + (idx >> 2)] >> (8 * (idx & 3))) & 0xFFu) != 0xFFu) return "pattern-mode image out of range (state index)";
+                        if (ref > 0xFE || ((rec[6 + (idx >> 2)] >> (8 * (idx & 3))) & 0xFFu) != 0xFFu) { gerr = "pattern-mode image out of range (state index)"; return; }
                         rec[6 + (idx >> 2)] = (rec[6 + (idx >> 2)] & ~(0xFFu << (8 * (idx & 3)))) | ((uint32_t)ref << (8 * (idx & 3)));
-                        if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) return "too many transition entries per state";
+                        if (!gather_rec(e, i, ref, live, el[(size_t)idx * 2], el[(size_t)idx * 2 + 1])) { gerr = "too many transition entries per state"; return; }
                     }
                     static_assert(6 * 4 + RC_PAT_MAXL <= RC_PLANE_N * 4, "state indices fit the lane record");
                     rec[2] = shape | ((uint32_t)nU << 20) | (pb.unit ? RC_PLANE_UNIT : 0u);
                     rec[3] = (uint32_t)so[i];
                     rec[4] = (uint32_t)i;
                     rec[5] = (uint32_t)bOff;
-                    recPos[(size_t)e * nPat + i] = (long long)out.kLane.size();
+                    recPos[(size_t)e * nPat + i] = (long long)GL.size();
                     elPos[(size_t)e * nPat + i] = hdr[7] + bOff;
                     grpOf[(size_t)e * nPat + i] = v;
                     boxN[(size_t)e * nPat + i] = nBox;
                     laneOf[(size_t)e * nPat + i] = lanes;
                     binOf[(size_t)e * nPat + i] = bI;
                     if (lanes == 0) binShape = shape;
-                    else if (binShape != shape) return "pattern-mode bin with more than one shape";
-                    out.kLane.insert(out.kLane.end(), rec, rec + RC_PLANE_N);
-                    out.kElem.insert(out.kElem.end(), el.begin(), el.end());
+                    else if (binShape != shape) { gerr = "pattern-mode bin with more than one shape"; return; }
+                    GL.insert(GL.end(), rec, rec + RC_PLANE_N);
+                    GE.insert(GE.end(), el.begin(), el.end());
                     lanes += 1;
                     bOff += nBox;
                 } else if (!rows) {
@@ -767,7 +772,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                         const long long g = out.epochBase[(size_t)e] + so[i] + s;
                         const uint32_t mt = out.meta[(size_t)g];
                         const int n = (int)(mt & 0xFFu);
-                        if (n > 8) return "keyed bin with more than 8 components";
+                        if (n > 8) { gerr = "keyed bin with more than 8 components"; return; }
                         uint32_t rec[RC_LANE_N] = {0, 0, 0, 0, 0, 0, 0, 0};
                         for (int d = 0; d < 8; ++d) {
                             uint32_t row = RC_KROWS - 1, up = (uint32_t)(lanes + s);
@@ -777,14 +782,14 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                                 row = (uint32_t)((int)rb[k] + x - 1);
                                 if ((w >> 16) != RC_NO_UP) up = (uint32_t)(lanes + (int)(w >> 16));
                             }
-                            if (row > 0xFFu || up > 0xFFu) return "keyed bin image out of range";
+                            if (row > 0xFFu || up > 0xFFu) { gerr = "keyed bin image out of range"; return; }
                             rec[d >> 2] |= row << (8 * (d & 3));
                             rec[2 + (d >> 2)] |= up << (8 * (d & 3));
                         }
                         rec[4] = mt;
                         rec[5] = (uint32_t)(so[i] + s);
-                        if (!gather_rec(e, i, s, live, rec[6], rec[7])) return "too many transition entries per state";
-                        out.kLane.insert(out.kLane.end(), rec, rec + RC_LANE_N);
+                        if (!gather_rec(e, i, s, live, rec[6], rec[7])) { gerr = "too many transition entries per state"; return; }
+                        GL.insert(GL.end(), rec, rec + RC_LANE_N);
                     }
                     lanes += live;
                 } else {
@@ -816,26 +821,26 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                                 row = (uint32_t)((int)rb[k] + x - 1);
                                 if ((w >> 16) != RC_NO_UP) off[d + 1] = (uint32_t)(bOff + rOff[(size_t)(w >> 16)]);
                             }
-                            if (row > 0xFFu || off[d + 1] > RC_ROW_BCAP) return "row bin image out of range";
+                            if (row > 0xFFu || off[d + 1] > RC_ROW_BCAP) { gerr = "row bin image out of range"; return; }
                             rec[d >> 2] |= row << (8 * (d & 3));
                         }
-                        if (rb[rk] > 0xFFu || off[0] > RC_ROW_BCAP) return "row bin image out of range";
+                        if (rb[rk] > 0xFFu || off[0] > RC_ROW_BCAP) { gerr = "row bin image out of range"; return; }
                         rec[1] |= (uint32_t)rb[rk] << 24;
                         rec[2] = (uint32_t)M | ((uint32_t)NO << 8);
                         for (int q = 0; q < RC_ROW_NO + 1; ++q) rec[3 + (q >> 1)] |= off[q] << (16 * (q & 1));
                         rec[7] = (uint32_t)so[i];
-                        if (grow > 0xFFFFFFFFLL) return "bin images too large";
+                        if (grow > 0xFFFFFFFFLL) { gerr = "bin images too large"; return; }
                         rec[8] = (uint32_t)grow;
                         rec[9] = (uint32_t)i;
-                        out.kLane.insert(out.kLane.end(), rec, rec + RC_RLANE_N);
+                        GL.insert(GL.end(), rec, rec + RC_RLANE_N);
                         for (int j = 0; j < Mp; ++j) {
                             uint32_t g0 = 0u, g1 = 0u;
                             if (j < M) {
                                 const int ref = (int)out.rowRefAll[(size_t)grow * RC_ROW_MAXM + j];
-                                if (!gather_rec(e, i, ref, live, g0, g1)) return "too many transition entries per state";
+                                if (!gather_rec(e, i, ref, live, g0, g1)) { gerr = "too many transition entries per state"; return; }
                             }
-                            out.kElem.push_back(g0);
-                            out.kElem.push_back(g1);
+                            GE.push_back(g0);
+                            GE.push_back(g1);
                         }
                     }
                     lanes += nr;
@@ -852,7 +857,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 for (int q = p0; q < p1 && seedLast; ++q) {
                     const int nb = boxN[(size_t)e * nPat + out.kBinPats[(size_t)q]];
                     for (int x = 0; x < nb; ++x)
-                        if ((out.kElem[el0 + (size_t)x * 2] == RC_IMG_SEED) != (x == nb - 1)) seedLast = false;
+                        if ((GE[el0 + (size_t)x * 2] == RC_IMG_SEED) != (x == nb - 1)) seedLast = false;
                     el0 += (size_t)nb * 2;
                 }
                 if (seedLast) hdr[3] |= RC_HDR_SEED;
@@ -860,7 +865,55 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             out.grpMaxFetch[(size_t)v] = std::max(out.grpMaxFetch[(size_t)v], hdr[5]);
             out.grpMaxB[(size_t)v] = std::max(out.grpMaxB[(size_t)v], bOff);
         }
-        if (patM) patElemEnd[(size_t)e] = (long long)(out.kElem.size() / 2);
+    };
+    {
+        int nT = (int)std::thread::hardware_concurrency();
+        nT = std::max(1, std::min(nT, 16));
+        if (nPat < 256) nT = 1;
+        std::atomic<int> nxt(0);
+        auto w = [&]() {
+            for (;;) {
+                const int v = nxt.fetch_add(1);
+                if (v >= nGrp) break;
+                do_group(v);
+            }
+        };
+        if (nT == 1) w();
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nT; ++t) pool.emplace_back(w);
+            for (auto& th : pool) th.join();
+        }
+        for (int v = 0; v < nGrp; ++v) if (!grpErr[(size_t)v].empty()) return grpErr[(size_t)v];
+        // one behind the other, in group order: local positions become global ones
+        size_t nLane = 0, nElem = 0;
+        for (int v = 0; v < nGrp; ++v) { nLane += grpLane[(size_t)v].size(); nElem += grpElem[(size_t)v].size(); }
+        if (nLane / 4 > 0x7FFFFFFFull || nElem / 2 > 0x7FFFFFFFull) return "bin images too large";
+        out.kLane.resize(nLane);
+        out.kElem.resize(nElem);
+        size_t lp = 0, ep = 0;
+        for (int v = 0; v < nGrp; ++v) {
+            const int e = v / RC_NGROUP;
+            if (v % RC_NGROUP == 0) out.ep[(size_t)e].elBase = (int)(ep / 2);
+            const int b0 = out.kBinBase[(size_t)v];
+            for (int bI = b0; bI < b0 + out.nKBins[(size_t)v]; ++bI) {
+                int* hdr = &out.kBinHdr[(size_t)bI * RC_HDR_N];
+                hdr[6] += (int)(lp / 4);
+                hdr[7] += (int)(ep / 2);
+                if (out.epochMode[(size_t)v] >= 3)
+                    for (int q = out.kBinPatOff[(size_t)bI]; q < out.kBinPatOff[(size_t)bI + 1]; ++q) {
+                        const int i = out.kBinPats[(size_t)q];
+                        recPos[(size_t)e * nPat + i] += (long long)lp;
+                        elPos[(size_t)e * nPat + i] += (int)(ep / 2);
+                    }
+            }
+            std::copy(grpLane[(size_t)v].begin(), grpLane[(size_t)v].end(), out.kLane.begin() + (long long)lp);
+            std::copy(grpElem[(size_t)v].begin(), grpElem[(size_t)v].end(), out.kElem.begin() + (long long)ep);
+            lp += grpLane[(size_t)v].size();
+            ep += grpElem[(size_t)v].size();
+            std::vector<uint32_t>().swap(grpLane[(size_t)v]);
+            std::vector<uint32_t>().swap(grpElem[(size_t)v]);
+        }
     }
     // ---- direct hand-over across a Join between pattern-mode epochs.  The lane that owns a pattern holds all its b(x): it
     //      applies the Join itself (new_b[J(x)] += b(x), Core.hs:172-188) and writes the result where the pattern's lane of the
