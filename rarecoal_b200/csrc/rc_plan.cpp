@@ -1500,7 +1500,11 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         static const bool patLEnv = std::getenv("RC_PATLARGE") ? std::atoi(std::getenv("RC_PATLARGE")) != 0 : true;
         std::vector<std::vector<int>> groupIds((size_t)nEpochs * RC_NGROUP);
         static const double minLen = std::getenv("RC_ROWMODE_MIN") ? std::atof(std::getenv("RC_ROWMODE_MIN")) : 2.0;
-        for (int e = 0; e < nEpochs; ++e) {
+        // one task per epoch; the row arrays of an epoch are collected locally and put one behind the other afterwards
+        std::vector<std::vector<uint16_t>> eRef((size_t)nEpochs);
+        std::vector<std::vector<uint32_t>> eWords((size_t)nEpochs);
+        std::vector<std::vector<uint8_t>> eBr((size_t)nEpochs), ePm((size_t)nEpochs);
+        auto do_epoch = [&](int e) {
             bool anyPat = false, use = false;
             int maxNO = 0;
             for (int i : orderK) {
@@ -1537,7 +1541,6 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             for (int q = 0; q < RC_NPATG; ++q) out.epochMode[(size_t)e * RC_NGROUP + q] = RC_MODE_PAT + q;
             out.epochMode[(size_t)e * RC_NGROUP + RC_NPATG] = maxNO <= 3 ? 1 : 2;     // row kernel for <= 3 / <= RC_ROW_NO other branches
             out.epochMode[(size_t)e * RC_NGROUP + RC_NGROUP - 1] = 0;
-            out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
             if (use || anyPat) {
                 int* ro = &out.rowOff[(size_t)e * (nPat + 1)];
                 long long run = 0;
@@ -1548,10 +1551,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     for (int q = 0; q < e; ++q) r0 += (size_t)pp.rowCnt[(size_t)q];
                     const int n = pp.rowOK[(size_t)e] ? pp.rowCnt[(size_t)e] : 0;
                     for (int q = 0; q < n; ++q) {
-                        for (int j = 0; j < RC_ROW_MAXM; ++j) out.rowRefAll.push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
-                        for (int d = 0; d < RC_ROW_NO; ++d) out.rowWordsAll.push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
-                        out.rowBrAll.push_back(pp.rowBr[r0 + (size_t)q]);
-                        out.rowPmAll.push_back(pp.rowPm[r0 + (size_t)q]);
+                        for (int j = 0; j < RC_ROW_MAXM; ++j) eRef[(size_t)e].push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
+                        for (int d = 0; d < RC_ROW_NO; ++d) eWords[(size_t)e].push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
+                        eBr[(size_t)e].push_back(pp.rowBr[r0 + (size_t)q]);
+                        ePm[(size_t)e].push_back(pp.rowPm[r0 + (size_t)q]);
                     }
                     run += n;
                     out.patRow[(size_t)e * nPat + i] = (uint32_t)pp.rowM[(size_t)e] | ((uint32_t)pp.rowK[(size_t)e] << 8) |
@@ -1560,12 +1563,31 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 }
                 ro[nPat] = (int)run;
             }
+        };
+        {
+            std::atomic<int> nextE(0);
+            auto worker = [&]() { for (;;) { const int e = nextE.fetch_add(1); if (e >= nEpochs) break; do_epoch(e); } };
+            const int nT = nPat < 2048 ? 1 : std::min(nThreads, nEpochs);
+            if (nT <= 1) worker();
+            else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nT; ++t) pool.emplace_back(worker);
+                for (auto& th : pool) th.join();
+            }
+            for (int e = 0; e < nEpochs; ++e) {
+                out.rowEpochBase[(size_t)e] = (long long)out.rowRefAll.size() / RC_ROW_MAXM;
+                out.rowRefAll.insert(out.rowRefAll.end(), eRef[(size_t)e].begin(), eRef[(size_t)e].end());
+                out.rowWordsAll.insert(out.rowWordsAll.end(), eWords[(size_t)e].begin(), eWords[(size_t)e].end());
+                out.rowBrAll.insert(out.rowBrAll.end(), eBr[(size_t)e].begin(), eBr[(size_t)e].end());
+                out.rowPmAll.insert(out.rowPmAll.end(), ePm[(size_t)e].begin(), ePm[(size_t)e].end());
+            }
         }
         lap("groups and row arrays");
         // ---- executed FP64 instructions per grid step (rc_kernels.cu, the update of each tier as written) ----
         out.epochFp64.assign((size_t)nEpochs, 0);
         out.epochFp64Short.assign((size_t)nEpochs, 0);
-        for (int v = 0; v < nEpochs * RC_NGROUP; ++v) {
+        std::vector<long long> vFp((size_t)nEpochs * RC_NGROUP, 0), vFpS((size_t)nEpochs * RC_NGROUP, 0);
+        auto count_group = [&](int v) {
             const int e = v / RC_NGROUP, mode = out.epochMode[(size_t)v];
             bool direct = mode >= RC_MODE_PAT && !groupIds[(size_t)v].empty();
             for (int i : groupIds[(size_t)v]) direct = direct && pps[(size_t)i].rowNO[(size_t)e] == 0;
@@ -1607,8 +1629,24 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     for (int q = 0; q < e; ++q) m0 += (size_t)pp.live[(size_t)q];
                     for (int sI = 0; sI < pp.live[(size_t)e]; ++sI) n += 2LL * (long long)(pp.meta[m0 + (size_t)sI] & 0xFFu);
                 }
-                out.epochFp64[(size_t)e] += n;
-                if (pp.shortcutOK) out.epochFp64Short[(size_t)e] += n;
+                vFp[(size_t)v] += n;
+                if (pp.shortcutOK) vFpS[(size_t)v] += n;
+            }
+        };
+        {
+            const int nV = nEpochs * RC_NGROUP;
+            std::atomic<int> nextV(0);
+            auto worker = [&]() { for (;;) { const int v = nextV.fetch_add(1); if (v >= nV) break; count_group(v); } };
+            const int nT = nPat < 2048 ? 1 : std::min(nThreads, nV);
+            if (nT <= 1) worker();
+            else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nT; ++t) pool.emplace_back(worker);
+                for (auto& th : pool) th.join();
+            }
+            for (int v = 0; v < nV; ++v) {
+                out.epochFp64[(size_t)(v / RC_NGROUP)] += vFp[(size_t)v];
+                out.epochFp64Short[(size_t)(v / RC_NGROUP)] += vFpS[(size_t)v];
             }
         }
         lap("instruction counts");
@@ -1762,31 +1800,51 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     // transitions
     out.trBase.assign((size_t)nEpochs, 0);
     out.trEntBase.assign((size_t)nEpochs, 0);
+    // pass 1 (patterns side by side): entries of every pattern in every epoch; pass 2 after a prefix sum per epoch
+    const int nTr = nEpochs > 0 ? nEpochs - 1 : 0;
+    std::vector<long long> patEnt((size_t)nTr * ((size_t)nPat + 1), 0);
+    par_for(nPat, 256, [&](int i0, int i1) { for (int i = i0; i < i1; ++i) {
+        const PatPlan& pp = pps[(size_t)i];
+        size_t cp = 0;
+        for (int e = 0; e < nTr; ++e) {
+            int n = pp.live[(size_t)e + 1];
+            long long c = 0;
+            for (int s = 0; s < n; ++s) c += pp.trCnt[cp + s];
+            cp += (size_t)n;
+            patEnt[(size_t)e * (nPat + 1) + i + 1] = c;
+        }
+    } });
     long long tb = 0, te = 0;
-    std::vector<size_t> cntPos((size_t)nPat, 0), entPos((size_t)nPat, 0);
-    for (int e = 0; e + 1 < nEpochs; ++e) {
+    for (int e = 0; e < nTr; ++e) {
+        long long* row = &patEnt[(size_t)e * (nPat + 1)];
+        for (int i = 0; i < nPat; ++i) row[i + 1] += row[i];
+        if (row[nPat] > 0x7FFFFFFFLL) return "too many transition entries in one epoch";
         out.trBase[(size_t)e] = tb;
         out.trEntBase[(size_t)e] = te;
-        long long nNew = out.epochSlots[(size_t)e + 1];
-        out.trOff.resize((size_t)(tb + nNew + 1));
-        long long run = 0;
-        for (int i = 0; i < nPat; ++i) {
-            const PatPlan& pp = pps[(size_t)i];
+        tb += out.epochSlots[(size_t)e + 1] + 1;
+        te += row[nPat];
+    }
+    out.trOff.assign((size_t)tb, 0);
+    out.trEnt.resize((size_t)te);
+    for (int e = 0; e < nTr; ++e)
+        out.trOff[(size_t)(out.trBase[(size_t)e] + out.epochSlots[(size_t)e + 1])] = (int)patEnt[(size_t)e * (nPat + 1) + nPat];
+    par_for(nPat, 256, [&](int i0, int i1) { for (int i = i0; i < i1; ++i) {
+        const PatPlan& pp = pps[(size_t)i];
+        size_t cp = 0, ep = 0;
+        for (int e = 0; e < nTr; ++e) {
             int n = pp.live[(size_t)e + 1];
-            long long s0 = tb + out.slotOff[(size_t)(e + 1) * (nPat + 1) + i];
+            long long s0 = out.trBase[(size_t)e] + out.slotOff[(size_t)(e + 1) * (nPat + 1) + i];
+            long long run = patEnt[(size_t)e * (nPat + 1) + i];
+            long long dst = out.trEntBase[(size_t)e] + run;
             for (int s = 0; s < n; ++s) {
                 out.trOff[(size_t)(s0 + s)] = (int)run;
-                int cn = pp.trCnt[cntPos[(size_t)i] + s];
-                for (int q = 0; q < cn; ++q) out.trEnt.push_back(pp.trEnt[entPos[(size_t)i]++]);
+                int cn = pp.trCnt[cp + s];
+                for (int q = 0; q < cn; ++q) out.trEnt[(size_t)dst++] = pp.trEnt[ep++];
                 run += cn;
             }
-            cntPos[(size_t)i] += (size_t)n;
+            cp += (size_t)n;
         }
-        if (run > 0x7FFFFFFFLL) return "too many transition entries in one epoch";
-        out.trOff[(size_t)(tb + nNew)] = (int)run;
-        tb += nNew + 1;
-        te += run;
-    }
+    } });
     lap("concatenation");
     std::string r = build_bin_images(out, sev);
     lap("bin images");
