@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rarecoal_b200.h"
@@ -83,6 +85,10 @@ struct PlanEntry {
     rc::PlanHost h;
     RcPlanDev d;
     std::vector<void*> allocs;
+    struct Pending { const void* src; size_t bytes, off; const void** out; };
+    std::vector<Pending> pending;        // arrays of the plan waiting for finish_upload (one device arena)
+    size_t arenaBytes = 0;
+    std::vector<RcEpochDev> eps;
     bool allShortcut = false;
     size_t allocBytes = 0, bytes = 0;    // device bytes uploaded so far / accounted in the cache
     long long lastUse = 0;               // serial of the last eval call that used the plan (LRU)
@@ -90,6 +96,8 @@ struct PlanEntry {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         allocBytes = 0;
+        pending.clear();
+        arenaBytes = 0;
     }
 };
 
@@ -183,7 +191,7 @@ struct rc_ctx {
     int optPatternEmbed = 0;          // ... and live sets that are not boxes on their bounding boxes (rc_plan.cpp, pat_box)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
     double optKtabTotalMB = 12288.0;  // largest trajectory table memory of one call
-    PinBuf hBlob, hOut;
+    PinBuf hBlob, hOut, hPlanStage;
     cudaStream_t stream = nullptr;
     cudaEvent_t evt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // side stream of the trajectory kernels: rc_traj_kernel(e) depends only on rc_traj_kernel(e-1), so the chain runs beside
@@ -432,15 +440,59 @@ void resolve_model(const rc_ctx* ctx, const rc_event* ev, int nEv, const double*
     }
 }
 
+// Arrays of a plan are laid out in one device allocation: upload() reserves a 256-byte aligned range, finish_upload()
+// allocates the arena, gathers the arrays into a pinned staging buffer with a few host threads and sends them as one copy
+// (a C3 plan is 340 MB: array-by-array copies from pageable memory took 0.1-0.4 s, a third of the planner's own time).
 template <typename T>
-int upload(rc_ctx* ctx, PlanEntry* pe, const std::vector<T>& v, const T** out) {
-    void* p = nullptr;
-    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CK(cudaMalloc(&p, n));
-    pe->allocs.push_back(p);
-    pe->allocBytes += n;
-    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = reinterpret_cast<const T*>(p);
+int upload(rc_ctx*, PlanEntry* pe, const std::vector<T>& v, const T** out) {
+    PlanEntry::Pending q;
+    q.src = v.data();
+    q.bytes = v.size() * sizeof(T);
+    q.off = pe->arenaBytes;
+    q.out = reinterpret_cast<const void**>(out);
+    pe->arenaBytes += (std::max<size_t>(q.bytes, 1) + 255) & ~(size_t)255;
+    pe->pending.push_back(q);
+    return RC_OK;
+}
+
+int finish_upload(rc_ctx* ctx, PlanEntry* pe) {
+    void* dev = nullptr;
+    const size_t total = std::max<size_t>(pe->arenaBytes, 256);
+    CK(cudaMalloc(&dev, total));
+    pe->allocs.push_back(dev);
+    pe->allocBytes += total;
+    for (const auto& q : pe->pending) *q.out = static_cast<const char*>(dev) + q.off;
+    if (ctx->hPlanStage.ensure(total) == cudaSuccess) {
+        char* stage = static_cast<char*>(ctx->hPlanStage.p);
+        // tasks of at most 4 MB
+        struct Task { const char* src; char* dst; size_t n; };
+        std::vector<Task> tasks;
+        for (const auto& q : pe->pending)
+            for (size_t o = 0; o < q.bytes; o += (size_t)4 << 20)
+                tasks.push_back({static_cast<const char*>(q.src) + o, stage + q.off + o, std::min(q.bytes - o, (size_t)4 << 20)});
+        std::atomic<size_t> next(0);
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) break;
+                std::memcpy(tasks[i].dst, tasks[i].src, tasks[i].n);
+            }
+        };
+        int nT = (int)std::thread::hardware_concurrency();
+        nT = std::max(1, std::min(nT, 8));
+        if (total < ((size_t)8 << 20)) nT = 1;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nT; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+        CK(cudaMemcpy(dev, stage, total, cudaMemcpyHostToDevice));
+    } else {
+        cudaGetLastError();          // no pinned memory to be had: array by array from pageable memory
+        for (const auto& q : pe->pending)
+            if (q.bytes) CK(cudaMemcpy(static_cast<char*>(dev) + q.off, q.src, q.bytes, cudaMemcpyHostToDevice));
+    }
+    pe->pending.clear();
+    pe->eps.clear();
     return RC_OK;
 }
 
@@ -456,7 +508,8 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     if ((rc = upload(ctx, pe, h.fBinPats, &d.fBinPats))) return rc;
     if ((rc = upload(ctx, pe, h.maxX, &d.maxX))) return rc;
     {
-        std::vector<RcEpochDev> eps(h.ep.size());
+        std::vector<RcEpochDev>& eps = pe->eps;
+        eps.assign(h.ep.size(), RcEpochDev());
         for (size_t e = 0; e < h.ep.size(); ++e) {
             eps[e].nKeys = h.ep[e].nKeys; eps[e].nThr = h.ep[e].nThr; eps[e].rowPairs = h.ep[e].rowPairs;
             eps[e].keyOff = h.ep[e].keyOff; eps[e].thrOff = h.ep[e].thrOff; eps[e].elBase = h.ep[e].elBase;
@@ -513,6 +566,13 @@ int upload_plan(rc_ctx* ctx, PlanEntry* pe) {
     d.patGlobal = (const int32_t*)ctx->dPatGlobal.p;
     pe->allShortcut = true;
     for (uint8_t f : h.shortcutOK) pe->allShortcut = pe->allShortcut && f;
+    if ((rc = finish_upload(ctx, pe))) return rc;
+    // the host keeps the small per-epoch / per-group arrays it launches from; the bulk now lives on the device only
+    rc::PlanHost& hm = pe->h;
+    auto drop = [](auto& v) { std::decay_t<decltype(v)>().swap(v); };
+    drop(hm.words); drop(hm.meta); drop(hm.trOff); drop(hm.trEnt); drop(hm.slotOff); drop(hm.kLane); drop(hm.kElem);
+    drop(hm.kPatRec); drop(hm.kRowBase); drop(hm.kFetchRows); drop(hm.kBinHdr); drop(hm.rowRefAll); drop(hm.rowWordsAll);
+    drop(hm.patRow); drop(hm.thrKey);
     return RC_OK;
 }
 
@@ -557,6 +617,7 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
         ctx->err = e;
         return RC_ERR_UNSUPPORTED;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     evict_plans(ctx, 0);
     int rc = upload_plan(ctx, pe);
     if (rc != RC_OK && cudaPeekAtLastError() == cudaErrorMemoryAllocation) {
@@ -580,6 +641,9 @@ int get_plan(rc_ctx* ctx, ModelHost& mh, bool* hit) {
     ctx->plans[mh.sig] = pe;
     mh.plan = pe;
     ++ctx->planMisses;
+    if (std::getenv("RC_PLAN_TIMING"))
+        std::fprintf(stderr, "[rc plan] built in %.1f ms, uploaded %.1f MB in %.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                     (double)pe->bytes / 1048576.0, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     ctx->planBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return RC_OK;
 }
@@ -1300,6 +1364,7 @@ void rc_destroy(rc_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();
+    ctx->hPlanStage.release();
     for (auto& e : ctx->evt) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->trajStream) cudaStreamDestroy(ctx->trajStream);
@@ -1745,9 +1810,14 @@ int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int
     resolve_model(&tmp, ev, nEv, disc.data(), noShortcut, mh);
     if (mh.status != RC_OK) return mh.status;
     rc::PlanHost h;
+    const auto tp0 = std::chrono::steady_clock::now();
     std::string e = rc::build_plan(P, maxAf, nPat, patterns, nVec, mh.sev, mh.gaps, mh.hasSplit, 227 * 1024, h);
     if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
+    const auto tp1 = std::chrono::steady_clock::now();
     e = rc::check_plan(h);
+    if (std::getenv("RC_PLAN_TIMING"))
+        std::fprintf(stderr, "[rc plan] build_plan %.1f ms, check_plan %.1f ms\n", std::chrono::duration<double, std::milli>(tp1 - tp0).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count());
     if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
     if (stateSteps) *stateSteps = count_state_steps(mh, h, T);
     if (slots0) *slots0 = h.epochSlots[0];

@@ -1846,7 +1846,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         }
     } });
     lap("concatenation");
+    // the per-pattern plans (several hundred thousand small vectors) are released while the bin images are built
+    std::thread reaper([dead = std::move(pps)]() mutable { std::vector<PatPlan>().swap(dead); });
     std::string r = build_bin_images(out, sev);
+    reaper.join();
     lap("bin images");
     return r;
 }

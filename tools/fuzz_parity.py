@@ -48,6 +48,10 @@ def run(n_cases=40, seed=1, verbose=True):
     e.set_option("ktab_total_mb", 1.0)                # models fall back to the self-contained kernels
     e.set_option("ktab_model_mb", 0.5)
     engs.append(e)
+    e = R.Engine(0)                                   # pattern kernels on bounding boxes (opt-in), last epoch not fused
+    e.set_option("pattern_embed", 1.0)
+    e.set_option("fuse_last", 0.0)
+    engs.append(e)
     worst = 0.0
     for case in range(n_cases):
         if os.environ.get("FUZZ_BIG"):                 # many branches, many alleles: the multi-branch shapes of the pattern kernels
