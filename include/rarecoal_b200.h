@@ -200,8 +200,6 @@ int rc_get_prob(rc_ctx* ctx, int P, int maxAf, const int32_t* nVec, const int32_
  *   "plan_cache_mb" (49152) device memory the cached plans may hold
  *   "fuse_last" (1)        a last epoch that consists of the grid step of the last Join and the shortcut (a tree model) is
  *                          finished by the launches of the epoch before it and not launched itself; same numbers bit for bit
- *   "traj_split" (0)       1: the trajectory kernels follow the a-chain once per key and compute the pairs in a second kernel
- *                          (bitwise the same pairs; measured slower than the single kernel), -1: for batches of 8 models or more
  *   "pattern_embed" (0)    1: live sets that are not boxes (what a Split leaves) also run one pattern per thread, on their
  *                          bounding boxes of at most 36 states; measured slower than the row kernel on the example data
  *   "big_smem_kb" (0)      > 0: shared-memory budget of the big tier (patterns with more than 256 live states).  A live

@@ -179,14 +179,11 @@ struct rc_ctx {
     long long planMisses = 0, planEvictions = 0, planMissesAtCall = 0, planEvictionsAtCall = 0;
     double planBuildMs = 0.0, planBuildMsAtCall = 0.0;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch, dATab;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch, dCum;
     int optBigSmemKB = 0;             // > 0: shared-memory budget of the big tier (tests: forces the global-memory mode)
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
     int optPattern = 1;               // boxes of few states run one pattern per thread (else rows / states)
-    int optTrajSplit = 0;             // trajectory kernels: 0 one kernel (every allele-count thread of a key repeats its a-chain); 1 the
-                                      // chain once per key, then the pairs (bitwise equal; measured slower: 7.65 against 7.61 ms on C3, 11.7
-                                      // against 11.1 ms on one rank's share of the 8-GPU pattern-sharded step); -1 by batch size (>= 8)
     int optFuseLast = 1;              // a last epoch without grid steps is finished by the launches of the last but one epoch
     int optPatternEmbed = 0;          // ... and live sets that are not boxes on their bounding boxes (rc_plan.cpp, pat_box)
     double optKtabModelMB = 1024.0;   // largest trajectory table of one model
@@ -777,7 +774,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
     double* hW = (double*)(hb + oW);
     RcModelEpochDev* hMep = (RcModelEpochDev*)(hb + oMep);
     size_t mepPos = 0;
-    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0, carrySlots = 0, aTabDoubles = 0;
+    long long ktabPairs = 0, aEndDoubles = 0, aShortDoubles = 0, maxRowPairs = 0, carrySlots = 0;
     const long long ktabModelMax = (long long)(ctx->optKtabModelMB * 1048576.0 / 16.0);
     const long long ktabTotalMax = (long long)(ctx->optKtabTotalMB * 1048576.0 / 16.0);
 
@@ -809,7 +806,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         // ---- keyed mode: per-epoch step ranges and the model's slice of the trajectory table ----
         {
             const int finalEnd = (mh.sShort >= 0 && pe->allShortcut) ? mh.sShort : T;
-            long long pairs = 0, aLocal = 0;
+            long long pairs = 0;
             M.mepOff = (int)mepPos;
             for (int e = 0; e < hp.nEpochs; ++e) {
                 RcModelEpochDev& me = hMep[mepPos++];
@@ -817,8 +814,6 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 me.end = e + 1 < hp.nEpochs ? mh.sevStep[(size_t)e] : finalEnd;
                 if (me.end < me.beg) me.end = me.beg;
                 me.tabBase = ktabPairs + pairs;
-                me.aBase = aTabDoubles + aLocal;
-                aLocal += (long long)(me.end - me.beg) * hp.ep[(size_t)e].nKeys;
                 pairs += (long long)(me.end - me.beg) * hp.ep[(size_t)e].rowPairs;
                 maxRowPairs = std::max<long long>(maxRowPairs, hp.ep[(size_t)e].rowPairs);
             }
@@ -827,7 +822,6 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                 // only models that own a slice of the trajectory table bound the chunk size
                 if (maxPairsOut && pairs > *maxPairsOut) *maxPairsOut = pairs;
                 ktabPairs += pairs;
-                aTabDoubles += aLocal;
                 M.aEndOff = aEndDoubles;
                 M.aShortOff = aShortDoubles;
                 aEndDoubles += hp.totalKeys;
@@ -903,7 +897,8 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         // the keyed kernel prefetches up to 8 step rows past the end of an epoch: keep that much slack
         size_t needK = (size_t)(std::max<long long>(ktabPairs, 1) + 8 * maxRowPairs + 64) * 16;
         size_t needA = (size_t)std::max<long long>(aEndDoubles, 1) * sizeof(double);
-        size_t needAT = (size_t)std::max<long long>(aTabDoubles, 1) * sizeof(double);
+        // cumulative products of exp(-dt/2N) per (table row, branch): rc_cum_kernel
+        size_t needCum = (size_t)std::max<long long>(tabDoubles / rowLen, 1) * P * sizeof(double);
         size_t needS = (size_t)std::max<long long>(aShortDoubles, 1) * sizeof(double);
         // b carried from one epoch's launch to the next (two buffers) and the per-pattern updateD accumulators
         size_t needC = (size_t)std::max<long long>(2 * carrySlots * B, 1) * sizeof(double);
@@ -929,7 +924,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         CK(ctx->dPOut.ensure(needOut));
         CK(ctx->dKTab.ensure(needK));
         CK(ctx->dAEnd.ensure(needA));
-        if (needAT > ctx->dATab.cap) { CK(cudaStreamSynchronize(st)); CK(ctx->dATab.ensure(needAT)); }
+        CK(ctx->dCum.ensure(needCum));
         CK(ctx->dAShort.ensure(needS));
     }
 
@@ -1002,12 +997,12 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
                     CK(cudaEventRecord(ctx->evFork, st));     // tables written, previous work on st finished
                     CK(cudaStreamWaitEvent(ts, ctx->evFork, 0));
                     if (timeIt) CK(rec_timing(ctx->evt[6], ts));
+                    CK(rc_launch_cum(pe->h.nEpochs, P, A1, dM, dMep, (const double*)ctx->dTab.p, (double*)ctx->dCum.p, pos, end - pos, ts));
+                    ++launches;
                     for (int e = 0; e < pe->h.nEpochs; ++e) {
-                        const bool trajSplit = ctx->optTrajSplit >= 0 ? ctx->optTrajSplit != 0 : end - pos >= 8;
-                        CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, pe->h.ep[(size_t)e].nKeys, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dDts.p,
-                                          (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p, (double*)ctx->dATab.p,
-                                          trajSplit, pos, end - pos, ts));
-                        if (trajSplit) ++launches;
+                        CK(rc_launch_traj(pe->d, e, pe->h.ep[(size_t)e].nThr, dM, dMep, dSev, (const double*)ctx->dTab.p, (const double*)ctx->dCum.p,
+                                          (const double*)ctx->dDts.p, (double*)ctx->dKTab.p, (double*)ctx->dAEnd.p, (double*)ctx->dAShort.p,
+                                          pos, end - pos, ts));
                         // (the timing record precedes the epoch's join event: a captured side stream must end in a join)
                         if (timeIt && e + 1 == pe->h.nEpochs) { CK(rec_timing(ctx->evt[7], ts)); ctx->trajTimed = true; }
                         CK(cudaEventRecord(ctx->evTraj[(size_t)e], ts));
@@ -1104,7 +1099,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat); putv((long long)ctx->dBigScratch.cap);
         const void* ptrs[] = {db + oModels, db + oSev, db + oMep, db + oW, db + oSizeOff, db + oMaskOff, db + oMasks, db + oSizes,
                               ctx->dTab.p, ctx->dPOut.p, ctx->dKTab.p, ctx->dAEnd.p, ctx->dAShort.p, ctx->dBCarry.p, ctx->dDAcc.p,
-                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p, ctx->dATab.p};
+                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p, ctx->dCum.p};
         put(ptrs, sizeof ptrs);
         for (int pos = 0; pos < B;) {
             const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
@@ -1324,7 +1319,7 @@ int rc_create(int device, rc_ctx** out) {
     // the trajectory chain feeds every propagation launch: its blocks go first when both are runnable
     int prLo = 0, prHi = 0;
     cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
-    if (cudaStreamCreateWithPriority(&ctx->trajStream, cudaStreamNonBlocking, prHi) != cudaSuccess ||
+    if (cudaStreamCreateWithPriority(&ctx->trajStream, cudaStreamNonBlocking, std::getenv("RC_TRAJ_LOWPRIO") ? prLo : prHi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RC_ERR_CUDA; }
     for (int c = 0; c < RC_NCHAIN; ++c) {
         if ((c > 0 && cudaStreamCreateWithFlags(&ctx->chainStream[c], cudaStreamNonBlocking) != cudaSuccess) ||
@@ -1360,7 +1355,7 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
-                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch, &ctx->dATab};
+                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch, &ctx->dCum};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();
@@ -1612,7 +1607,6 @@ int rc_set_option(rc_ctx* ctx, const char* name, double value) {
         }
     }
     else if (n == "fuse_last") ctx->optFuseLast = value != 0.0;
-    else if (n == "traj_split") { ctx->optTrajSplit = value < 0.0 ? -1 : value != 0.0; cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->clear_graphs(); }
     else if (n == "pattern_embed") {
         const int v = value != 0.0;
         if (v != ctx->optPatternEmbed) {

@@ -13,6 +13,14 @@
 
 #include "rc_kernels.h"
 #include "rc_dev.cuh"
+#include <cstdlib>
+
+#ifndef RC_TRAJ_FILL
+#define RC_TRAJ_FILL 151552     // threads a trajectory launch aims for: 148 SMs x 8 blocks of 128
+#endif
+#ifndef RC_TRAJ_ZMAX
+#define RC_TRAJ_ZMAX 16
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Per-step tables.  Formulas keep the reference's operation order (Core.hs:240,270,279).
@@ -785,16 +793,59 @@ rc_propagate_fast_kernel(RcPlanDev pl, const RcModelDev* __restrict__ models, co
 // ------------------------------------------------------------------------------------------------
 // Keyed fast tier.
 //
-// rc_traj_kernel — one launch per structural epoch.  Thread (key, j) follows the ancestral count a of one
-// trajectory key (branch k, derived-allele counts on the leaves merged into k) through the epoch's grid steps
-// with the reference's own formulas (updateA, Core.hs:229-240; the starting value comes from the parent keys via
-// popJoinA / popSplitA, Core.hs:165-170,195-200) and writes, for every step, the pair
+// Trajectories.  updateA (Core.hs:239-240) is a' = 1 / (1 + (1/a - 1) EA) with EA = exp(-dt/2N_k): with u = 1/a - 1 the
+// recursion is u' = u EA, so inside a structural epoch
+//     a(s) = 1 / (1 + u0 C_k(s)),   u0 = 1/a0 - 1,   C_k(s) = prod of EA_k over the epoch's steps up to and including s
+// and C does not depend on the key, only on (model, branch).  rc_cum_kernel writes C (one warp scan per model, epoch and
+// branch over the table rows rc_tables_kernel has written: EA is exactly 1 where the reference performs no update, i.e.
+// dt <= 0 or a frozen branch); rc_traj_kernel then has NO sequential chain inside an epoch: every (key, allele count, step)
+// is independent, and a launch cuts the epoch's steps into slices (grid.z) so that even a single model fills the device.
+// Only the epochs follow each other (a0 comes from the parents' values at the end of the previous epoch through
+// popJoinA / popSplitA, Core.hs:165-170,195-200, and u0 is formed from it with the reference's expression).  Against the
+// literal recursion, a is not rounded and inverted again between steps: the values differ by a few 1e-16 relative (the first
+// step of an epoch not at all), three orders of magnitude inside the 1e-10 the probabilities are tested to.  a < 1 is never
+// propagated (Core.hs:239), and 1 / (1 + u) with -1 < u <= 0 cannot fall below 1, so "a >= 1" holds for the whole epoch or
+// not at all.
+// With the literal recursion a single model spent 0.26 of its 0.42 ms on the GPU in this chain (eight kernels of a few warps,
+// each step two dependent divisions and an exp).
+//
+// For every step the kernel writes the pair
 //     { G = exp(-(j(j-1)/2 (1/N_k) + j a_k (1/N_k)) dt),   E2 = 1 - exp(-j(j+1)/2 (1/N_k) dt) }
 // i.e. the k-th factor of exp(-t1 dt) for a state with x_k = j (Core.hs:259,270) and the coalescence factor of
 // b(x+e_k) (Core.hs:279).  All patterns that share the key read the same pairs.
+__global__ void __launch_bounds__(32 * RC_MAX_P)
+rc_cum_kernel(int nEpochs, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
+              const double* __restrict__ tab, double* __restrict__ cum, int P, int A1) {
+    const int b = blockIdx.y, e = blockIdx.x;
+    const RcModelDev& M = models[b];
+    if (M.nSteps < 0 || M.mode != 1 || e >= nEpochs) return;
+    const RcModelEpochDev me = mep[M.mepOff + e];
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= P) return;
+    const int rowLen = rc_row_len(P, A1);
+    const double* ea = tab + M.tabOff + RC_ROW_PAIRS + 2 * (k * A1);
+    double* out = cum + (M.tabOff / rowLen) * P + k;
+    double carry = 1.0;
+    for (int s0 = me.beg; s0 < me.end; s0 += 32) {
+        const int s = s0 + lane;
+        double v = s < me.end ? ea[(long long)s * rowLen] : 1.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v *= t;
+        }
+        v *= carry;
+        if (s < me.end) out[(long long)s * P] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+}
+
+#ifndef RC_TCH
+#define RC_TCH 1
+#endif
 __global__ void __launch_bounds__(128)
 rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
-               const RcSEvDev* __restrict__ sevs, const double* __restrict__ tab,
+               const RcSEvDev* __restrict__ sevs, const double* __restrict__ tab, const double* __restrict__ cum,
                const double* __restrict__ dts, double* __restrict__ ktab, double* __restrict__ aEnd,
                double* __restrict__ aShort) {
     const int b = blockIdx.y;
@@ -805,14 +856,18 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nst = me.end - me.beg;
     const bool lastEpoch = e + 1 == pl.nEpochs;
-    // pair 0 of every step row: {dt, 0}; a step with dt <= 0 performs no update (Core.hs:130)
-    for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
-        const double dt = dts[me.beg + i];
-        double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
-        // pair 0 = {1, dt}: its first half doubles as the neutral decay factor of the pattern kernel's unused unit-branch slots
-        p0[0] = 1.0;
-        p0[1] = dt > 0.0 ? dt : 0.0;
-    }
+    // this slice of the epoch's steps
+    const int per = (nst + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int sBeg = me.beg + (int)blockIdx.z * per, sEnd = min(me.end, sBeg + per);
+    // pair 0 of every step row: {1, dt}: its first half doubles as the neutral decay factor of the pattern kernel's unused
+    // unit-branch slots; a step with dt <= 0 performs no update (Core.hs:130)
+    if (blockIdx.z == 0)
+        for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
+            const double dt = dts[me.beg + i];
+            double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
+            p0[0] = 1.0;
+            p0[1] = dt > 0.0 ? dt : 0.0;
+        }
     if (t >= E.nThr) return;
     const int key = pl.thrKey[E.thrOff + t];
     const int kk = E.keyOff + key;
@@ -824,178 +879,72 @@ rc_traj_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const
     const bool padLast = j == (int)pl.keyMaxJ[kk] && rc_pair_stride(j + pl.zeroRow) != j + pl.zeroRow;
     // a plan with a Split: the pair of x = 0, {1, 0}, in front of the key's pairs (pattern mode on bounding boxes, rc_plan.cpp)
     const bool zeroFirst = pl.zeroRow && j == 1;
+    const bool special = j == 1 && blockIdx.z == 0;          // writes the key's a at the end of the epoch / at the shortcut step
+    if (sBeg >= sEnd && !special) return;
     // ---- starting value ----
-    double a;
+    double a0;
     {
         const int op = pl.keyOp[kk];
         const double* aPrev = e > 0 ? aEnd + M.aEndOff + pl.ep[e - 1].keyOff : aEnd;
         const int pa = pl.keyPa[kk], pb = pl.keyPb[kk];
-        if (op == RC_KOP_INIT) a = (double)pl.keyInit[kk];                 // makeInitCoalState, Core.hs:60
-        else if (op == RC_KOP_COPY) a = aPrev[pa];
-        else if (op == RC_KOP_JOIN) a = aPrev[pb] + aPrev[pa];             // popJoinA: al + ak
-        else if (op == RC_KOP_ZERO) a = 0.0;
+        if (op == RC_KOP_INIT) a0 = (double)pl.keyInit[kk];                // makeInitCoalState, Core.hs:60
+        else if (op == RC_KOP_COPY) a0 = aPrev[pa];
+        else if (op == RC_KOP_JOIN) a0 = aPrev[pb] + aPrev[pa];            // popJoinA: al + ak
+        else if (op == RC_KOP_ZERO) a0 = 0.0;
         else {
             const double m = sevs[M.sevOff + e - 1].m;
-            if (op == RC_KOP_SPLIT_K) a = m * aPrev[pb] + aPrev[pa];       // popSplitA: m * al + ak
-            else a = (1.0 - m) * aPrev[pa];                                // (1 - m) * al
+            if (op == RC_KOP_SPLIT_K) a0 = m * aPrev[pb] + aPrev[pa];      // popSplitA: m * al + ak
+            else a0 = (1.0 - m) * aPrev[pa];                               // (1 - m) * al
         }
     }
-    // The key-independent factors of a step — EA = exp(-dt/2N_k) (Core.hs:240), 1/N_k, CN = j(j-1)/2N_k (Core.hs:270) and
-    // E2 (Core.hs:279) — come from the per-step table rc_tables_kernel has already written for this model (rc_types.h, table
-    // row layout); only the a-dependent exponential is left per (key, j, step).
-    const double xx = (double)j;
-    double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2;
-    const long long stride = (long long)E.rowPairs * 2;
+    const bool act = a0 >= 1.0;
+    const double u0 = act ? (1.0 / a0) - 1.0 : 0.0;
     const int rowLen = rc_row_len(pl.P, pl.A1);
-    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
-    const int jOff = hasPair ? 2 * j : 0;
-    // The chain of a-values is sequential and every step costs two divisions and an exp; the step's table entries do not
-    // depend on it, so the loads of step s+1 are issued before the arithmetic of step s (the warp issues in order: left in
-    // program order they would sit behind it and their L2 latency would be added to every step).
-    double2 p0n = make_double2(1.0, 0.0), pjn = p0n;
-    double dtn = 0.0;
-    if (me.beg < me.end) {
-        p0n = *reinterpret_cast<const double2*>(row);
-        pjn = *reinterpret_cast<const double2*>(row + jOff);
-        dtn = dts[me.beg];
+    const double* cm = cum + (M.tabOff / rowLen) * pl.P + k;
+    if (special) {
+        // a after the step before s (the value the step s starts from)
+        const double aLast = (act && nst > 0) ? 1.0 / (1.0 + u0 * cm[(long long)(me.end - 1) * pl.P]) : a0;
+        aEnd[M.aEndOff + kk] = aLast;
+        if (lastEpoch && M.sShort >= me.beg && M.sShort <= me.end)
+            aShort[M.aShortOff + key] = (act && M.sShort > me.beg) ? 1.0 / (1.0 + u0 * cm[(long long)(M.sShort - 1) * pl.P]) : a0;
     }
-    for (int s = me.beg; s < me.end; ++s, out += stride, row += rowLen) {
-        if (lastEpoch && s == M.sShort && j == 1) aShort[M.aShortOff + key] = a;
-        const double2 p0 = p0n;                                               // {EA, 1/N}; 1/N == 0: frozen
-        const double2 pj = pjn;                                               // {CN, E2}
-        const double dt = dtn;
-        if (s + 1 < me.end) {
-            p0n = *reinterpret_cast<const double2*>(row + rowLen);
-            pjn = *reinterpret_cast<const double2*>(row + rowLen + jOff);
-            dtn = dts[s + 1];
+    if (!hasPair && !padLast && !zeroFirst) return;
+    // The key-independent factors of a step — 1/N_k, CN = j(j-1)/2N_k (Core.hs:270) and E2 (Core.hs:279) — come from the
+    // per-step table rc_tables_kernel has written for this model (rc_types.h, table row layout); only the a-dependent
+    // exponential is left per (key, j, step).
+    const double xx = (double)j;
+    const long long stride = (long long)E.rowPairs * 2;
+    double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2 + (long long)(sBeg - me.beg) * stride;
+    const double* row = tab + M.tabOff + (long long)sBeg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
+    const int jOff = hasPair ? 2 * j : 0;
+    cm += (long long)sBeg * pl.P;
+    // The steps are independent: the table entries of RC_TCH steps are loaded first (one L2 round trip for all of them),
+    // then the steps are computed without a branch around the arithmetic (a step without update — dt <= 0 or a frozen
+    // branch — selects {1, 0} afterwards).
+    for (int s0 = sBeg; s0 < sEnd; s0 += RC_TCH) {
+        double2 p0[RC_TCH], pj[RC_TCH];
+        double dt[RC_TCH], c[RC_TCH];
+#pragma unroll
+        for (int q = 0; q < RC_TCH; ++q) {
+            const long long o = min(s0 + q, sEnd - 1) - sBeg;
+            p0[q] = *reinterpret_cast<const double2*>(row + o * rowLen);          // {EA, 1/N}; 1/N == 0: frozen
+            pj[q] = *reinterpret_cast<const double2*>(row + o * rowLen + jOff);   // {CN, E2}
+            dt[q] = dts[sBeg + o];
+            c[q] = cm[o * pl.P];
         }
-        double G = 1.0, E2 = 0.0;
-        if (dt > 0.0 && p0.y != 0.0) {
-            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * p0.x);         // propagateA, Core.hs:239-240
-            if (hasPair) {
-                const double t1k = pj.x + xx * a * p0.y;                       // Core.hs:270 (new a)
-                G = exp(-(t1k * dt));
-                E2 = pj.y;
+#pragma unroll
+        for (int q = 0; q < RC_TCH; ++q) {
+            if (s0 + q < sEnd) {
+                const bool upd = dt[q] > 0.0 && p0[q].y != 0.0;
+                const double a = act ? 1.0 / (1.0 + u0 * c[q]) : a0;               // propagateA, Core.hs:239-240
+                const double t1k = pj[q].x + xx * a * p0[q].y;                     // Core.hs:270 (new a)
+                const double G = exp(-(t1k * dt[q]));
+                double* o = out + (long long)(s0 + q - sBeg) * stride;
+                if (hasPair) *reinterpret_cast<double2*>(o) = upd ? make_double2(G, pj[q].y) : make_double2(1.0, 0.0);
+                if (padLast) *reinterpret_cast<double2*>(o + 2) = make_double2(1.0, 0.0);
+                if (zeroFirst) *reinterpret_cast<double2*>(o - 2) = make_double2(1.0, 0.0);
             }
         }
-        if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
-        if (padLast) *reinterpret_cast<double2*>(out + 2) = make_double2(1.0, 0.0);
-        if (zeroFirst) *reinterpret_cast<double2*>(out - 2) = make_double2(1.0, 0.0);
-    }
-    if (j == 1) {
-        aEnd[M.aEndOff + kk] = a;
-        if (lastEpoch && M.sShort == me.end) aShort[M.aShortOff + key] = a;
-    }
-}
-
-// The same in two kernels, for batches large enough to be bound by instruction issue rather than by the latency of the chain:
-// all allele-count threads of a key repeat the key's a-chain (two divisions per step).  rc_traj_a_kernel follows the chain
-// once per key and writes a(t) — [step][key] — and rc_traj_b_kernel, one thread per (key, j) as before but without a carried
-// dependency, reads it and writes the pairs.  Same formulas on the same values: the pairs are identical bit for bit.
-__global__ void __launch_bounds__(128)
-rc_traj_a_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
-                 const RcSEvDev* __restrict__ sevs, const double* __restrict__ tab, const double* __restrict__ dts,
-                 double* __restrict__ aTab, double* __restrict__ aEnd, double* __restrict__ aShort) {
-    const int b = blockIdx.y;
-    const RcModelDev& M = models[b];
-    if (M.nSteps < 0 || M.mode != 1) return;
-    const RcEpochDev E = pl.ep[e];
-    const RcModelEpochDev me = mep[M.mepOff + e];
-    const int key = blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= E.nKeys) return;
-    const bool lastEpoch = e + 1 == pl.nEpochs;
-    const int kk = E.keyOff + key;
-    const int k = pl.keyBranch[kk];
-    double a;
-    {
-        const int op = pl.keyOp[kk];
-        const double* aPrev = e > 0 ? aEnd + M.aEndOff + pl.ep[e - 1].keyOff : aEnd;
-        const int pa = pl.keyPa[kk], pb = pl.keyPb[kk];
-        if (op == RC_KOP_INIT) a = (double)pl.keyInit[kk];                 // makeInitCoalState, Core.hs:60
-        else if (op == RC_KOP_COPY) a = aPrev[pa];
-        else if (op == RC_KOP_JOIN) a = aPrev[pb] + aPrev[pa];             // popJoinA: al + ak
-        else if (op == RC_KOP_ZERO) a = 0.0;
-        else {
-            const double m = sevs[M.sevOff + e - 1].m;
-            if (op == RC_KOP_SPLIT_K) a = m * aPrev[pb] + aPrev[pa];       // popSplitA: m * al + ak
-            else a = (1.0 - m) * aPrev[pa];                                // (1 - m) * al
-        }
-    }
-    const int rowLen = rc_row_len(pl.P, pl.A1);
-    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
-    double* out = aTab + me.aBase + key;
-    double2 p0n = make_double2(1.0, 0.0);
-    double dtn = 0.0;
-    if (me.beg < me.end) {
-        p0n = *reinterpret_cast<const double2*>(row);
-        dtn = dts[me.beg];
-    }
-    for (int s = me.beg; s < me.end; ++s, out += E.nKeys, row += rowLen) {
-        if (lastEpoch && s == M.sShort) aShort[M.aShortOff + key] = a;
-        const double2 p0 = p0n;                                               // {EA, 1/N}; 1/N == 0: frozen
-        const double dt = dtn;
-        if (s + 1 < me.end) {
-            p0n = *reinterpret_cast<const double2*>(row + rowLen);
-            dtn = dts[s + 1];
-        }
-        if (dt > 0.0 && p0.y != 0.0) {
-            if (a >= 1.0) a = 1.0 / (1.0 + ((1.0 / a) - 1.0) * p0.x);         // propagateA, Core.hs:239-240
-        }
-        *out = a;
-    }
-    aEnd[M.aEndOff + kk] = a;
-    if (lastEpoch && M.sShort == me.end) aShort[M.aShortOff + key] = a;
-}
-
-__global__ void __launch_bounds__(128)
-rc_traj_b_kernel(RcPlanDev pl, int e, const RcModelDev* __restrict__ models, const RcModelEpochDev* __restrict__ mep,
-                 const double* __restrict__ tab, const double* __restrict__ dts, const double* __restrict__ aTab,
-                 double* __restrict__ ktab) {
-    const int b = blockIdx.y;
-    const RcModelDev& M = models[b];
-    if (M.nSteps < 0 || M.mode != 1) return;
-    const RcEpochDev E = pl.ep[e];
-    const RcModelEpochDev me = mep[M.mepOff + e];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nst = me.end - me.beg;
-    for (int i = t; i < nst; i += gridDim.x * blockDim.x) {
-        const double dt = dts[me.beg + i];
-        double* p0 = ktab + (me.tabBase + (long long)i * E.rowPairs) * 2;
-        p0[0] = 1.0;                                                          // pair 0 = {1, dt}, as in rc_traj_kernel
-        p0[1] = dt > 0.0 ? dt : 0.0;
-    }
-    if (t >= E.nThr) return;
-    const int key = pl.thrKey[E.thrOff + t];
-    const int kk = E.keyOff + key;
-    const int k = pl.keyBranch[kk];
-    const int j = t - pl.keyThrBase[kk] + 1;
-    const int maxJ = (int)pl.keyMaxJ[kk];
-    const bool hasPair = j <= maxJ;
-    const bool padLast = j == maxJ && rc_pair_stride(j + pl.zeroRow) != j + pl.zeroRow;
-    const bool zeroFirst = pl.zeroRow && j == 1;
-    if (!hasPair && !zeroFirst) return;
-    const double xx = (double)j;
-    double* out = ktab + (me.tabBase * 2) + (long long)(pl.keyPairBase[kk] + j - 1) * 2;
-    const long long stride = (long long)E.rowPairs * 2;
-    const int rowLen = rc_row_len(pl.P, pl.A1);
-    const double* row = tab + M.tabOff + (long long)me.beg * rowLen + RC_ROW_PAIRS + 2 * (k * pl.A1);
-    const int jOff = hasPair ? 2 * j : 0;
-    const double* aT = aTab + me.aBase + key;
-#pragma unroll 2
-    for (int s = me.beg; s < me.end; ++s, out += stride, row += rowLen, aT += E.nKeys) {
-        const double2 p0 = *reinterpret_cast<const double2*>(row);           // {EA, 1/N}; 1/N == 0: frozen
-        const double2 pj = *reinterpret_cast<const double2*>(row + jOff);    // {CN, E2}
-        const double dt = dts[s];
-        const double a = *aT;
-        double G = 1.0, E2 = 0.0;
-        if (dt > 0.0 && p0.y != 0.0 && hasPair) {
-            const double t1k = pj.x + xx * a * p0.y;                           // Core.hs:270 (new a)
-            G = exp(-(t1k * dt));
-            E2 = pj.y;
-        }
-        if (hasPair) *reinterpret_cast<double2*>(out) = make_double2(G, E2);
-        if (padLast) *reinterpret_cast<double2*>(out + 2) = make_double2(1.0, 0.0);
-        if (zeroFirst) *reinterpret_cast<double2*>(out - 2) = make_double2(1.0, 0.0);
     }
 }
 
@@ -1846,20 +1795,27 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
     }
 }
 
-cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, int nKeys, const RcModelDev* models, const RcModelEpochDev* mep,
-                           const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
-                           double* aEnd, double* aShort, double* aTab, bool split, int b0, int nB, cudaStream_t st) {
+cudaError_t rc_launch_cum(int nEpochs, int P, int A1, const RcModelDev* models, const RcModelEpochDev* mep, const double* tab,
+                          double* cum, int b0, int nB, cudaStream_t st) {
+    if (nB <= 0 || nEpochs <= 0) return cudaSuccess;
+    dim3 grid((unsigned)nEpochs, (unsigned)nB);
+    rc_cum_kernel<<<grid, 32 * P, 0, st>>>(nEpochs, models + b0, mep, tab, cum, P, A1);
+    return cudaGetLastError();
+}
+
+cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
+                           const RcSEvDev* sevs, const double* tab, const double* cum, const double* dts, double* ktab,
+                           double* aEnd, double* aShort, int b0, int nB, cudaStream_t st) {
     if (nB <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((nThr + 127) / 128), (unsigned)nB);
-    if (!split) {
-        rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, ktab, aEnd, aShort);
-        return cudaGetLastError();
-    }
-    dim3 gridA((unsigned)((nKeys + 127) / 128), (unsigned)nB);
-    rc_traj_a_kernel<<<gridA, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, dts, aTab, aEnd, aShort);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
-    rc_traj_b_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, tab, dts, aTab, ktab);
+    // slices of the epoch's steps: enough threads to fill the device when the batch is small (the count depends on the batch
+    // and the plan only, so a captured launch graph stays valid when the event times move)
+    const long long thr = (long long)((nThr + 127) / 128) * 128 * nB;
+    static const long long fill = std::getenv("RC_TRAJ_FILL") ? std::atoll(std::getenv("RC_TRAJ_FILL")) : RC_TRAJ_FILL;
+    static const int zMax = std::getenv("RC_TRAJ_ZMAX") ? std::atoi(std::getenv("RC_TRAJ_ZMAX")) : RC_TRAJ_ZMAX;
+    int z = (int)((fill + thr - 1) / thr);
+    z = std::max(1, std::min(z, zMax));
+    dim3 grid((unsigned)((nThr + 127) / 128), (unsigned)nB, (unsigned)z);
+    rc_traj_kernel<<<grid, 128, 0, st>>>(pl, e, models + b0, mep, sevs, tab, cum, dts, ktab, aEnd, aShort);
     return cudaGetLastError();
 }
 

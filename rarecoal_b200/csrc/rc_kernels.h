@@ -17,9 +17,11 @@ cudaError_t rc_launch_propagate_fast(const RcPlanDev& pl, const RcModelDev* mode
                                      const double* tab, const double* wpool, double* pOut, int b0, int nB,
                                      cudaStream_t st);
 size_t rc_fast_smem_bytes(int block);
-cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, int nKeys, const RcModelDev* models, const RcModelEpochDev* mep,
-                           const RcSEvDev* sevs, const double* tab, const double* dts, double* ktab,
-                           double* aEnd, double* aShort, double* aTab, bool split, int b0, int nB, cudaStream_t st);
+cudaError_t rc_launch_cum(int nEpochs, int P, int A1, const RcModelDev* models, const RcModelEpochDev* mep, const double* tab,
+                          double* cum, int b0, int nB, cudaStream_t st);
+cudaError_t rc_launch_traj(const RcPlanDev& pl, int e, int nThr, const RcModelDev* models, const RcModelEpochDev* mep,
+                           const RcSEvDev* sevs, const double* tab, const double* cum, const double* dts, double* ktab,
+                           double* aEnd, double* aShort, int b0, int nB, cudaStream_t st);
 // the three instantiations of the pattern kernel live in translation units of their own (rc_pat12.cu, rc_pat25.cu, rc_pat36.cu)
 #define RC_PAT_LAUNCH_ARGS dim3 grid, size_t smem, cudaStream_t st, const RcPlanDev& pl, int e, int binBase, int ringRows, \
     const RcModelDev* models, const RcModelEpochDev* mep, const RcSEvDev* sevs, const double* ktab, const double* aShort, \

@@ -194,7 +194,6 @@ struct RcEpochDev {
 struct RcModelEpochDev {
     int beg, end;
     long long tabBase;
-    long long aBase;       // first double of the model's a-values of this epoch in the a table ([step][key], RcEpochDev::nKeys per step)
 };
 
 // Structural event as executed by the kernel.
