@@ -9,10 +9,12 @@ python bench.py --steps 2 --warmup 1 > $O/r02g_bench_plain.json 2> $O/r02g_bench
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/r02g_launches.csv \
     python bench.py --steps 2 --warmup 1 > $O/r02g_ncu1.log 2>&1
 python tools/one_eval.py c3 44 > $O/r02g_plain.log 2>&1 || exit 1
+if [ -z "$RC_CAPTURE_SKIP_PROPAGATE" ]; then
 ncu --set full --clock-control none -k regex:rc_propagate -s 80 -c 40 -o $O/r02g_propagate -f python tools/one_eval.py c3 44 > $O/r02g_ncu2.log 2>&1
 ncu -i $O/r02g_propagate.ncu-rep --page raw --csv > $O/r02g_propagate_raw.csv 2>/dev/null
 rm -f $O/r02g_propagate.ncu-rep
-ncu --set full --clock-control none -k regex:rc_traj -s 16 -c 8 -o $O/r02g_traj -f python tools/one_eval.py c3 44 > $O/r02g_ncu3.log 2>&1
+fi
+ncu --set full --clock-control none -k 'regex:rc_traj|rc_cum' -s 18 -c 9 -o $O/r02g_traj -f python tools/one_eval.py c3 44 > $O/r02g_ncu3.log 2>&1
 ncu -i $O/r02g_traj.ncu-rep --page raw --csv > $O/r02g_traj_raw.csv 2>/dev/null
 rm -f $O/r02g_traj.ncu-rep
 ls -la $O/r02g_*
