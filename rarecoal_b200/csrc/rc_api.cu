@@ -179,7 +179,7 @@ struct rc_ctx {
     long long planMisses = 0, planEvictions = 0, planMissesAtCall = 0, planEvictionsAtCall = 0;
     double planBuildMs = 0.0, planBuildMsAtCall = 0.0;
     // eval scratch
-    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch, dCum;
+    DevBuf dBlob, dTab, dPOut, dPartial, dLogl, dProbs, dKTab, dAEnd, dAShort, dBCarry, dDAcc, dBigScratch, dCum, dRed;
     int optBigSmemKB = 0;             // > 0: shared-memory budget of the big tier (tests: forces the global-memory mode)
     // options (rc_set_option)
     int optKeyed = 1;                 // fast-tier patterns through the keyed kernels when the table fits
@@ -925,6 +925,15 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         CK(ctx->dKTab.ensure(needK));
         CK(ctx->dAEnd.ensure(needA));
         CK(ctx->dCum.ensure(needCum));
+        {
+            // slice sums and arrival counters of rc_reduce_kernel: the counters start at zero and the kernel leaves them there
+            const size_t needRed = rc_reduce_scratch_bytes(B);
+            if (needRed > ctx->dRed.cap) {
+                CK(cudaStreamSynchronize(st));
+                CK(ctx->dRed.ensure(needRed));
+                CK(cudaMemsetAsync(ctx->dRed.p, 0, ctx->dRed.cap, st));
+            }
+        }
         CK(ctx->dAShort.ensure(needS));
     }
 
@@ -1086,7 +1095,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         }
         CK(rec_timing(ctx->evt[3], st));
         CK(rc_launch_reduce((const double*)ctx->dPOut.p, (const long long*)ctx->dCounts.p, (const int*)ctx->dPatGlobal.p, dM,
-                            ctx->nPat, ctx->nPatGlobal, B, dPartial, dProbs, st));
+                            ctx->nPat, ctx->nPatGlobal, B, dPartial, dProbs, ctx->dRed.p, st));
         ++launches;
         CK(rec_timing(ctx->evt[4], st));
         return RC_OK;
@@ -1099,7 +1108,7 @@ int eval_chunk(rc_ctx* ctx, int B, const rc_event* ev, const int32_t* evOff, con
         putv(B); putv(rowsGrid); putv(carrySlots); putv((long long)(dProbs != nullptr)); putv(ctx->nPat); putv((long long)ctx->dBigScratch.cap);
         const void* ptrs[] = {db + oModels, db + oSev, db + oMep, db + oW, db + oSizeOff, db + oMaskOff, db + oMasks, db + oSizes,
                               ctx->dTab.p, ctx->dPOut.p, ctx->dKTab.p, ctx->dAEnd.p, ctx->dAShort.p, ctx->dBCarry.p, ctx->dDAcc.p,
-                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p, ctx->dCum.p};
+                              ctx->dDts.p, dPartial, dProbs, ctx->dCounts.p, ctx->dPatGlobal.p, ctx->dBigScratch.p, ctx->dCum.p, ctx->dRed.p};
         put(ptrs, sizeof ptrs);
         for (int pos = 0; pos < B;) {
             const PlanEntry* pe = mhs[(size_t)order[(size_t)pos]].plan;
@@ -1355,7 +1364,7 @@ void rc_destroy(rc_ctx* ctx) {
     ctx->clear_plans();
     DevBuf* bufs[] = {&ctx->dAInit, &ctx->dCombFac, &ctx->dSupport, &ctx->dPatGlobal, &ctx->dCounts, &ctx->dDts,
                       &ctx->dBlob, &ctx->dTab, &ctx->dPOut, &ctx->dPartial, &ctx->dLogl, &ctx->dProbs, &ctx->dKTab, &ctx->dAEnd,
-                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch, &ctx->dCum};
+                      &ctx->dAShort, &ctx->dBCarry, &ctx->dDAcc, &ctx->dBigScratch, &ctx->dCum, &ctx->dRed};
     for (DevBuf* b : bufs) b->release();
     ctx->hBlob.release();
     ctx->hOut.release();

@@ -35,7 +35,8 @@ cudaError_t rc_launch_propagate_keyed(const RcPlanDev& pl, int e, int binBase, i
                                       long long bStride, double* dAcc, double* pOut, int b0, int nB, cudaStream_t st);
 cudaError_t rc_launch_reduce(const double* pOut, const long long* counts, const int* patGlobal,
                              const RcModelDev* models, int nPat, int nPatGlobal, int B, double* partial,
-                             double* dProbs, cudaStream_t st);
+                             double* dProbs, void* scratch, cudaStream_t st);
+size_t rc_reduce_scratch_bytes(int B);
 cudaError_t rc_launch_finalize(const double* partial, int B, double other, double siteRed, double* logl,
                                cudaStream_t st);
 cudaError_t rc_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t st);
