@@ -1277,7 +1277,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             const bool rowMode = mode != 0, patMode = mode >= 3;
             const int patMaxStates = rc_pat_cap(mode);
             auto lanesOf = [&](const PatPlan& pp, int e) { return patMode ? 1 : rowMode ? pp.rowCnt[(size_t)e] : pp.live[(size_t)e]; };
-            auto clsOf = [&](int i) {
+            auto clsCompute = [&](int i) {
                 const PatPlan& pp = pps[(size_t)i];
                 if (patMode) {
                     PatBox pb;
@@ -1292,6 +1292,10 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 for (int k = 0; k < P; ++k) c += pp.mx[(size_t)e0 * P + k] ? 1 : 0;
                 return c;
             };
+            // (the class of a pattern is asked for by every comparison of the sorts below and by every probe of an open bin)
+            std::vector<int> clsV((size_t)nPat, 0);
+            for (int i : ids) clsV[(size_t)i] = clsCompute(i);
+            auto clsOf = [&](int i) { return clsV[(size_t)i]; };
             const size_t WINDOW = 12;
             std::vector<OpenBin> open;
             auto flush = [&](OpenBin& ob) {
@@ -1325,7 +1329,11 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                 // padded states of the rows (odd stride) must fit the block's b buffer
                 const int padAdd = (rowMode && !patMode) ? pp.rowPad[(size_t)e0] : 0;
                 if (ob.rowStates + padAdd > RC_ROW_BCAP) return false;
-                std::vector<int> add((size_t)nE, 0), addSelf((size_t)nE, 0);
+                int addS[16] = {0}, selfS[16] = {0};
+                std::vector<int> addV, selfV;
+                if (nE > 16) { addV.assign((size_t)nE, 0); selfV.assign((size_t)nE, 0); }
+                int* add = nE > 16 ? addV.data() : addS;
+                int* addSelf = nE > 16 ? selfV.data() : selfS;
                 for (int q = 0; q < nE; ++q) {
                     const int e = e0 + q;
                     for (int k = 0; k < P; ++k) {
@@ -1381,11 +1389,16 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                         kb = out.keyId[((size_t)e0 * nPat + i) * P + other];
                         return true;
                     };
+                    std::vector<int> twoA((size_t)nPat, -1), twoB((size_t)nPat, -1);
+                    for (int i : ids) {
+                        int ka = 0, kb = 0;
+                        if (two(i, ka, kb)) { twoA[(size_t)i] = ka; twoB[(size_t)i] = kb; }
+                    }
                     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
                         const int ca = clsOf(a), cb = clsOf(b);
                         if (ca != cb) return ca > cb;
-                        int a1 = 0, a2 = 0, b1 = 0, b2 = 0;
-                        const bool ta = two(a, a1, a2), tb = two(b, b1, b2);
+                        const int a1 = twoA[(size_t)a], a2 = twoB[(size_t)a], b1 = twoA[(size_t)b], b2 = twoB[(size_t)b];
+                        const bool ta = a1 >= 0, tb = b1 >= 0;
                         if (ta != tb) return ta;                        // a consistent order: two-branch patterns first,
                         if (!ta) return false;                          // the others keep their lexicographic order
                         if ((a1 >> 3) != (b1 >> 3)) return (a1 >> 3) < (b1 >> 3);
@@ -1480,10 +1493,20 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             }
         };
         // (1) bins spanning all epochs (self-contained fast kernel)
+        // (one sequential first-fit pass over all patterns; nothing below reads its result before the summary, so it runs
+        // beside the per-epoch phases)
         out.fBinPatOff.assign(1, 0);
         out.fBinPats.clear();
-        pack_range(0, nEpochs - 1, maxPatFast, 0, false, order, out.fBinPatOff, out.fBinPats);
-        out.nFastBins = (int)out.fBinPatOff.size() - 1;
+        struct Joiner {
+            std::thread t;
+            ~Joiner() { if (t.joinable()) t.join(); }
+        } allEpochBins;
+        auto pack_all = [&]() {
+            pack_range(0, nEpochs - 1, maxPatFast, 0, false, order, out.fBinPatOff, out.fBinPats);
+            out.nFastBins = (int)out.fBinPatOff.size() - 1;
+        };
+        if (nThreads > 1) allEpochBins.t = std::thread(pack_all);
+        else pack_all();
         lap("all-epoch bins");
         // (2) per-epoch bins (keyed kernel).  kBinPatOff holds, epoch after epoch, nKBins[e]+1 offsets into kBinPats.
         // Two bin groups per epoch (index 2e + g): g = 0 the patterns small enough for one thread each (pattern mode), g = 1
@@ -1723,6 +1746,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                              E.nKeys, E.nThr, E.rowPairs, m == 3 ? "patterns<12>" : m == 4 ? "patterns<25>" : m == 5 ? "patterns<36>" : m ? "rows" : "states", (int)groupIds[(size_t)v].size(), nb,
                              (double)(f1 - f0) / nb);
             }
+            if (allEpochBins.t.joinable()) allEpochBins.t.join();
             std::fprintf(stderr, "[rc plan] all-epoch fast bins %d (block %d); big patterns %d, of which %d in row mode on the key tier\n",
                          out.nFastBins, fastBlock, (int)bigIds.size(), (int)keyedBig.size());
         }
