@@ -870,12 +870,25 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
         int nT = (int)std::thread::hardware_concurrency();
         nT = std::max(1, std::min(nT, 16));
         if (nPat < 256) nT = 1;
+        // largest groups first: the longest task bounds the phase
+        std::vector<int> bysize((size_t)nGrp);
+        std::vector<long long> gsz((size_t)nGrp, 0);
+        for (int v = 0; v < nGrp; ++v) {
+            bysize[(size_t)v] = v;
+            const int b0 = out.kBinBase[(size_t)v], nb = out.nKBins[(size_t)v];
+            if (nb > 0) gsz[(size_t)v] = (long long)out.kBinPatOff[(size_t)(b0 + nb)] - out.kBinPatOff[(size_t)b0];
+        }
+        std::stable_sort(bysize.begin(), bysize.end(), [&](int a, int b) { return gsz[(size_t)a] > gsz[(size_t)b]; });
+        std::vector<double> grpMs((size_t)nGrp, 0.0);
+        const auto tAll0 = std::chrono::steady_clock::now();
         std::atomic<int> nxt(0);
         auto w = [&]() {
             for (;;) {
-                const int v = nxt.fetch_add(1);
-                if (v >= nGrp) break;
-                do_group(v);
+                const int q = nxt.fetch_add(1);
+                if (q >= nGrp) break;
+                const auto tg0 = std::chrono::steady_clock::now();
+                do_group(bysize[(size_t)q]);
+                grpMs[(size_t)bysize[(size_t)q]] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
             }
         };
         if (nT == 1) w();
@@ -883,6 +896,12 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             std::vector<std::thread> pool;
             for (int t = 0; t < nT; ++t) pool.emplace_back(w);
             for (auto& th : pool) th.join();
+        }
+        if (std::getenv("RC_PLAN_TIMING")) {
+            double mx = 0.0, sum = 0.0;
+            for (double m : grpMs) { mx = std::max(mx, m); sum += m; }
+            std::fprintf(stderr, "[rc plan]   bin images: groups %.1f ms wall, longest %.1f ms, sum %.1f ms\n",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tAll0).count(), mx, sum);
         }
         for (int v = 0; v < nGrp; ++v) if (!grpErr[(size_t)v].empty()) return grpErr[(size_t)v];
         // one behind the other, in group order: local positions become global ones
@@ -920,6 +939,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
     //      next epoch reads it — contiguous, in that lane's own state order — instead of writing slots that the next block
     //      gathers through element records and transition entries (three dependent loads per state at the start of every block).
     //      A bin group reads this way if every pattern of it was in pattern mode in the previous epoch. ----
+    const auto tDir0 = std::chrono::steady_clock::now();
     out.grpDirIn.assign((size_t)nE * RC_NGROUP, 0);
     std::vector<long long> dirRun((size_t)nE, 0);
     out.dirOff = out.maxEpochSlots;
@@ -934,8 +954,11 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             const int b0 = out.kBinBase[(size_t)v];
             const int q0 = out.kBinPatOff[(size_t)b0], q1 = out.kBinPatOff[(size_t)(b0 + out.nKBins[(size_t)v])];
             std::vector<uint8_t> maps((size_t)(q1 - q0) * RC_PAT_MAXL, 0);
+            std::atomic<bool> okAll(true);
+            // (the maps of the patterns are independent of each other: built side by side)
+            auto build_maps = [&](int qa, int qb) {
             bool ok = true;
-            for (int q = q0; q < q1 && ok; ++q) {
+            for (int q = qa; q < qb && ok && okAll.load(std::memory_order_relaxed); ++q) {
                 const int i = out.kBinPats[(size_t)q];
                 const long long rpN = recPos[(size_t)e * nPat + i], rpO = recPos[(size_t)(e - 1) * nPat + i];
                 if (rpN < 0 || rpO < 0) { ok = false; break; }
@@ -967,7 +990,27 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
                 }
                 ok = ok && mapped == liveO;                            // a Join maps every live state somewhere
             }
-            if (!ok) continue;
+            if (!ok) okAll.store(false, std::memory_order_relaxed);
+            };
+            {
+                int nT = (int)std::thread::hardware_concurrency();
+                nT = std::max(1, std::min(nT, 16));
+                const int chunk = 512;
+                if (q1 - q0 < 4 * chunk) nT = 1;
+                std::atomic<int> nxt(q0);
+                auto w = [&]() {
+                    for (;;) {
+                        const int qa = nxt.fetch_add(chunk);
+                        if (qa >= q1) break;
+                        build_maps(qa, std::min(q1, qa + chunk));
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nT; ++t) pool.emplace_back(w);
+                w();
+                for (auto& th : pool) th.join();
+            }
+            if (!okAll.load()) continue;
             out.grpDirIn[(size_t)v] = 1;
             // the bin's region of the lane-ordered part: [state of the box][lane], RC_DIR_LANES lanes — a lane reads its states at
             // that stride, a warp 256 contiguous bytes per state, straight into registers
@@ -1000,6 +1043,9 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
         out.dirOff = (out.maxEpochSlots + 1) & ~1LL;
         out.maxEpochSlots = out.dirOff + out.dirSize;
     }
+    if (std::getenv("RC_PLAN_TIMING"))
+        std::fprintf(stderr, "[rc plan]   bin images: hand-over maps %.1f ms\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tDir0).count());
     return "";
 }
 
