@@ -238,6 +238,9 @@ int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int wo
 int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T,
                   const double* times, const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps,
                   int64_t* slots0, int32_t* maxLive, int32_t* nEpochs, int32_t* nBins);
+/* FNV-1a checksum of the plan the calling thread's last successful rc_plan_stats built (every array a kernel reads): a plan
+ * is a function of the problem and the event structure, not of the host threads that built it (RC_PLAN_THREADS).   */
+uint64_t rc_plan_last_checksum(void);
 
 /* JointStateSpace (StateSpace.hs:20-28,73-124): ids are positions in computeAllConfigs.            */
 typedef struct rc_statespace rc_statespace;

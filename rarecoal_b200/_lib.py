@@ -58,6 +58,7 @@ SIGNATURES = {
     "rc_shard_patterns": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.c_int, _ip, C.c_int]),
     "rc_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp, _evp, C.c_int, C.c_int,
                                 _lp, _lp, _ip, _ip, _ip]),
+    "rc_plan_last_checksum": (C.c_uint64, []),
     "rc_ss_create": (_vp, [C.c_int, C.c_int]),
     "rc_ss_destroy": (None, [_vp]),
     "rc_ss_nr_states": (C.c_int, [_vp]),

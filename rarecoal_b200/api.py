@@ -241,7 +241,8 @@ def planStats(nVec, maxAf, patterns, times, events, noShortcut=False):
                                 C.byref(nb))
     if rc:
         _raise(rc, "rc_plan_stats failed")
-    return dict(state_steps=w.value, slots0=s0.value, max_live=ml.value, n_epochs=ne.value, n_bins=nb.value)
+    return dict(state_steps=w.value, slots0=s0.value, max_live=ml.value, n_epochs=ne.value, n_bins=nb.value,
+                checksum=int(L.load().rc_plan_last_checksum()))
 
 
 class JointStateSpace:

@@ -1799,6 +1799,10 @@ int rc_shard_patterns(int P, int nPat, const int32_t* patterns, int rank, int wo
     return (int)mine.size();
 }
 
+static thread_local uint64_t tlsPlanChecksum = 0;
+
+uint64_t rc_plan_last_checksum(void) { return tlsPlanChecksum; }
+
 int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int32_t* nVec, int T, const double* times,
                   const rc_event* ev, int nEv, int noShortcut, int64_t* stateSteps, int64_t* slots0, int32_t* maxLive,
                   int32_t* nEpochs, int32_t* nBins) {
@@ -1822,6 +1826,7 @@ int rc_plan_stats(int P, int maxAf, int nPat, const int32_t* patterns, const int
         std::fprintf(stderr, "[rc plan] build_plan %.1f ms, check_plan %.1f ms\n", std::chrono::duration<double, std::milli>(tp1 - tp0).count(),
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count());
     if (!e.empty()) { std::fprintf(stderr, "%s\n", e.c_str()); return RC_ERR_UNSUPPORTED; }
+    tlsPlanChecksum = rc::plan_checksum(h);
     if (stateSteps) *stateSteps = count_state_steps(mh, h, T);
     if (slots0) *slots0 = h.epochSlots[0];
     if (maxLive) *maxLive = h.maxLive;

@@ -26,6 +26,16 @@
 
 namespace rc {
 
+// host threads of the planner: the machine's, at most 16; RC_PLAN_THREADS overrides (tests: a plan must not depend on it)
+static int plan_threads() {
+    static const int n = [] {
+        const char* env = std::getenv("RC_PLAN_THREADS");
+        int v = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(v, 16));
+    }();
+    return n;
+}
+
 // ---- enumeration -------------------------------------------------------------------------------
 // computeAllConfigs (Utils.hs:100-112,121-127).  The reference enumerates (P-1)-subsets of
 // {1..P+af-1} in `allSubsets` order (those without the largest element first) and takes gaps; that
@@ -867,8 +877,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
         }
     };
     {
-        int nT = (int)std::thread::hardware_concurrency();
-        nT = std::max(1, std::min(nT, 16));
+        int nT = plan_threads();
         if (nPat < 256) nT = 1;
         // largest groups first: the longest task bounds the phase
         std::vector<int> bysize((size_t)nGrp);
@@ -993,8 +1002,7 @@ static std::string build_bin_images(PlanHost& out, const std::vector<StructEv>& 
             if (!ok) okAll.store(false, std::memory_order_relaxed);
             };
             {
-                int nT = (int)std::thread::hardware_concurrency();
-                nT = std::max(1, std::min(nT, 16));
+                int nT = plan_threads();
                 const int chunk = 512;
                 if (q1 - q0 < 4 * chunk) nT = 1;
                 std::atomic<int> nxt(q0);
@@ -1070,9 +1078,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         tPhase = now;
     };
 
-    int nThreads = (int)std::thread::hardware_concurrency();
-    if (nThreads < 1) nThreads = 1;
-    if (nThreads > 16) nThreads = 16;
+    int nThreads = plan_threads();
     if (nPat < 256) nThreads = 1;
     std::atomic<int> next(0);
     auto worker = [&]() {
@@ -1929,6 +1935,35 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
 // shared-memory limits of the kernel that runs it.  Returns "" or a description of the first violation.  (The pool's
 // compute-sanitizer is closed, so the bounds are verified on the host — tests/test_host_cpu.py runs this on every
 // workload shape.)
+// FNV-1a over everything a kernel reads from the plan (tests: the plan is a function of its inputs, not of the host threads
+// that built it or the order in which they finished).
+uint64_t plan_checksum(const PlanHost& h) {
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { x ^= b[i]; x *= 1099511628211ull; }
+    };
+    auto vec = [&](const auto& v) {
+        const uint64_t n = v.size();
+        mix(&n, sizeof n);
+        if (!v.empty()) mix(v.data(), v.size() * sizeof(v[0]));
+    };
+    for (const auto& e : h.ep) {
+        const int f[6] = {e.nKeys, e.nThr, e.rowPairs, e.keyOff, e.thrOff, e.elBase};
+        mix(f, sizeof f);
+    }
+    vec(h.keyBranch); vec(h.keyMaxJ); vec(h.keyOp); vec(h.keyPa); vec(h.keyPb); vec(h.keyInit); vec(h.keyPairBase);
+    vec(h.keyThrBase); vec(h.thrKey); vec(h.lastKeyId); vec(h.kBinBase); vec(h.nKBins); vec(h.kBinPatOff); vec(h.kBinPats);
+    vec(h.kFetchOff); vec(h.kFetchRows); vec(h.kRowBase); vec(h.epochMode); vec(h.rowOff); vec(h.rowEpochBase);
+    vec(h.rowRefAll); vec(h.rowWordsAll); vec(h.patRow); vec(h.kBinHdr); vec(h.kPatRec); vec(h.grpDirect); vec(h.grpMaxFetch);
+    vec(h.grpMaxB); vec(h.kLane); vec(h.kElem); vec(h.kSegs); vec(h.lastPairBase); vec(h.grpDirIn); vec(h.slotOff);
+    vec(h.epochBase); vec(h.words); vec(h.meta); vec(h.trBase); vec(h.trEntBase); vec(h.trOff); vec(h.trEnt); vec(h.shortcutOK);
+    vec(h.fBinPatOff); vec(h.fBinPats); vec(h.binPatOff); vec(h.binPats); vec(h.epochFp64); vec(h.epochFp64Short);
+    const long long g[4] = {h.maxEpochSlots, h.dirOff, h.dirSize, h.totalSlots};
+    mix(g, sizeof g);
+    return x;
+}
+
 std::string check_plan(const PlanHost& h) {
     const int P = h.P, nPat = h.nPat, nE = h.nEpochs;
     auto fail = [](const std::string& m) { return std::string("plan check: ") + m; };

@@ -126,5 +126,6 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
 
 // Bounds / capacity self-check of a built plan ("" if consistent).
 std::string check_plan(const PlanHost& h);
+uint64_t plan_checksum(const PlanHost& h);
 
 }  // namespace rc

@@ -103,7 +103,7 @@ def test_planner_state_steps_c3():
     nvec, pats, _ = Wk.c3_problem()
     assert len(pats) == 43757
     st = R.planStats(nvec, 10, pats, R.defaultTimes(), Wk.c3_events())
-    assert st == dict(state_steps=298329136, slots0=545327, max_live=36, n_epochs=8, n_bins=st["n_bins"])
+    assert st == dict(state_steps=298329136, slots0=545327, max_live=36, n_epochs=8, n_bins=st["n_bins"], checksum=st["checksum"])
 
 
 @pytest.mark.parametrize("events,no_shortcut,T", [
@@ -134,6 +134,31 @@ def test_plan_self_check_on_every_workload_shape(fourpop):
     std8 = R.computeStandardOrder(fourpop["nVec"], 8)
     assert R.planStats(fourpop["nVec"], 8, std8, T, fourpop["events"])["max_live"] > 256      # big tier engaged
     assert R.planStats([5, 5], 3, R.computeStandardOrder([5, 5], 3), T[:50], [], True)["n_epochs"] == 1
+
+
+def test_plan_does_not_depend_on_the_host_threads_that_build_it(fourpop):
+    # Every phase of the planner runs on a thread pool (per pattern, per epoch, per bin group, results put one behind the
+    # other afterwards).  The plan — every array a kernel reads, rc_plan_last_checksum — must be the same with 1, 3 and 8
+    # threads and from run to run: C3 (tree, pattern mode, direct hand-over), fourPop at maxAf 10 (Split pulses: rows, states,
+    # big tier) and C5 (13 epochs).
+    import subprocess, sys
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import rarecoal_b200 as R\nfrom rarecoal_b200 import workloads as Wk\n"
+        "T = R.defaultTimes(); out = []\n"
+        "nvec, pats, _ = Wk.c3_problem(); out.append(R.planStats(nvec, 10, pats, T, Wk.c3_events())['checksum'])\n"
+        "wl = Wk.get('c2'); nvec, pats, _ = wl.problem(); ev = wl.proposal_batches(1, 1, seed=3)[0][0]\n"
+        "out.append(R.planStats(nvec, wl.max_af, pats, T, ev)['checksum'])\n"
+        "nv = [100] * 10; out.append(R.planStats(nv, 4, R.computeStandardOrder(nv, 4), T, Wk.c5_events())['checksum'])\n"
+        "print(json.dumps(out))\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sums = []
+    for threads in ("1", "3", "8", "8"):
+        env = dict(os.environ, RC_PLAN_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sums.append(r.stdout.strip().splitlines()[-1])
+    assert len(set(sums)) == 1, sums
+    assert all(v != 0 for v in __import__("json").loads(sums[0]))
 
 
 def test_c_abi_rejects_bad_arguments_without_device():
