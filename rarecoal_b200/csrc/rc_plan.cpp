@@ -1625,11 +1625,12 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     size_t r0 = 0;
                     for (int q = 0; q < e; ++q) r0 += (size_t)pp.rowCnt[(size_t)q];
                     const int n = pp.rowOK[(size_t)e] ? pp.rowCnt[(size_t)e] : 0;
-                    for (int q = 0; q < n; ++q) {
-                        for (int j = 0; j < RC_ROW_MAXM; ++j) eRef[(size_t)e].push_back(pp.rowRefs[(r0 + (size_t)q) * RC_ROW_MAXM + j]);
-                        for (int d = 0; d < RC_ROW_NO; ++d) eWords[(size_t)e].push_back(pp.rowWords[(r0 + (size_t)q) * RC_ROW_NO + d]);
-                        eBr[(size_t)e].push_back(pp.rowBr[r0 + (size_t)q]);
-                        ePm[(size_t)e].push_back(pp.rowPm[r0 + (size_t)q]);
+                    if (n > 0) {
+                        // (a pattern's rows of an epoch are contiguous in its own arrays)
+                        eRef[(size_t)e].insert(eRef[(size_t)e].end(), pp.rowRefs.begin() + (long long)(r0 * RC_ROW_MAXM), pp.rowRefs.begin() + (long long)((r0 + (size_t)n) * RC_ROW_MAXM));
+                        eWords[(size_t)e].insert(eWords[(size_t)e].end(), pp.rowWords.begin() + (long long)(r0 * RC_ROW_NO), pp.rowWords.begin() + (long long)((r0 + (size_t)n) * RC_ROW_NO));
+                        eBr[(size_t)e].insert(eBr[(size_t)e].end(), pp.rowBr.begin() + (long long)r0, pp.rowBr.begin() + (long long)(r0 + (size_t)n));
+                        ePm[(size_t)e].insert(ePm[(size_t)e].end(), pp.rowPm.begin() + (long long)r0, pp.rowPm.begin() + (long long)(r0 + (size_t)n));
                     }
                     run += n;
                     out.patRow[(size_t)e * nPat + i] = (uint32_t)pp.rowM[(size_t)e] | ((uint32_t)pp.rowK[(size_t)e] << 8) |
