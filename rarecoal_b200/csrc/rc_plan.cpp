@@ -1224,19 +1224,22 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
             }
             PlanHost::Epoch& E = out.ep[(size_t)e];
             E.keyOff = (int)out.keyBranch.size();
-            std::unordered_map<std::string, int> ids;
-            std::string ks;
+            // key of (branch k, counts on the leaves merged into k): the counts as digits base maxAf + 1 (fits 63 bits:
+            // key_fits), one index per branch; ids in order of first appearance over the patterns
+            std::vector<Index> ids((size_t)P);
+            int nIds = 0;
+            const uint64_t deadKey = ~(uint64_t)0 - 1;
             for (int i = 0; i < nPat; ++i) {
                 const int32_t* m = patterns + (size_t)i * P;
                 for (int k = 0; k < P; ++k) {
-                    ks.assign(1, (char)k);
-                    if (dead[(size_t)k]) ks.push_back((char)0xFF);
-                    else for (int q = 0; q < P; ++q) if ((leaf[(size_t)k] >> q) & 1u) ks.push_back((char)m[q]);
-                    auto it = ids.find(ks);
+                    uint64_t ks = 0;
+                    if (dead[(size_t)k]) ks = deadKey;
+                    else for (int q = 0; q < P; ++q) if ((leaf[(size_t)k] >> q) & 1u) ks = ks * c.base + (uint64_t)m[q];
+                    auto it = ids[(size_t)k].find(ks);
                     int id;
-                    if (it == ids.end()) {
-                        id = (int)ids.size();
-                        ids.emplace(ks, id);
+                    if (it == ids[(size_t)k].end()) {
+                        id = nIds++;
+                        ids[(size_t)k].emplace(ks, id);
                         out.keyBranch.push_back((uint8_t)k);
                         out.keyMaxJ.push_back(0);
                         int pa = -1, pb = -1, op = RC_KOP_COPY, init = 0;
@@ -1264,7 +1267,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
                     if (mxk > mj) mj = mxk;
                 }
             }
-            E.nKeys = (int)ids.size();
+            E.nKeys = nIds;
             E.thrOff = (int)out.thrKey.size();
             int pairs = 1;   // pair 0 of every step row is {dt, 0}
             for (int q = 0; q < E.nKeys; ++q) {
