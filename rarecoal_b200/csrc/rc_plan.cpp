@@ -1485,10 +1485,13 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
         auto fetch_lists = [&](int e, const std::vector<int>& patOff, const std::vector<int>& pats, int b0, int b1,
                                std::vector<int>& fOff, std::vector<int>& fRows, std::vector<uint16_t>& rBase, size_t rBaseOff, bool pad) {
             const PlanHost::Epoch& E = out.ep[(size_t)e];
+            Index rowsOf, startOf;                   // (flat, cleared per bin: a bin has a few dozen keys)
+            std::vector<int> keyOrder;
             for (int bI = b0; bI < b1; ++bI) {
                 fOff.push_back((int)fRows.size());
-                std::unordered_map<int, int> rowsOf, startOf;
-                std::vector<int> keyOrder;
+                rowsOf.clear();
+                startOf.clear();
+                keyOrder.clear();
                 for (int q = patOff[(size_t)bI]; q < patOff[(size_t)bI + 1]; ++q) {
                     int i = pats[(size_t)q];
                     for (int k = 0; k < P; ++k) {
