@@ -1826,16 +1826,19 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     }
     out.minX.assign((size_t)nEpochs * nPat * P, 0);
     out.patFull.assign((size_t)nEpochs * nPat, 0);
-    for (int i = 0; i < nPat; ++i)
-        for (int e = 0; e < nEpochs; ++e) {
-            for (int k = 0; k < P; ++k) out.minX[((size_t)e * nPat + i) * P + k] = pps[(size_t)i].mn[(size_t)e * P + k];
-            out.patFull[(size_t)e * nPat + i] = pps[(size_t)i].rowOK[(size_t)e] && pps[(size_t)i].fullBox[(size_t)e];
-        }
     out.maxX.assign((size_t)nEpochs * nPat * P, 0);
-    for (int e = 0; e < nEpochs; ++e)
-        for (int i = 0; i < nPat; ++i)
-            for (int k = 0; k < P; ++k)
-                out.maxX[((size_t)e * nPat + i) * P + k] = pps[(size_t)i].mx[(size_t)e * P + k];
+    par_for(nPat, 256, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            const PatPlan& pp = pps[(size_t)i];
+            for (int e = 0; e < nEpochs; ++e) {
+                for (int k = 0; k < P; ++k) {
+                    out.minX[((size_t)e * nPat + i) * P + k] = pp.mn[(size_t)e * P + k];
+                    out.maxX[((size_t)e * nPat + i) * P + k] = pp.mx[(size_t)e * P + k];
+                }
+                out.patFull[(size_t)e * nPat + i] = pp.rowOK[(size_t)e] && pp.fullBox[(size_t)e];
+            }
+        }
+    });
 
     // concatenate per-epoch arrays
     out.slotOff.assign((size_t)nEpochs * (nPat + 1), 0);
@@ -1843,15 +1846,22 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     out.epochSlots.assign((size_t)nEpochs, 0);
     out.epochSlotsShort.assign((size_t)nEpochs, 0);
     out.shortcutOK.resize((size_t)nPat);
+    // (live counts gathered per pattern side by side, then one prefix sum per epoch)
+    std::vector<int> liveAll((size_t)nEpochs * nPat, 0);
+    par_for(nPat, 256, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i)
+            for (int e = 0; e < nEpochs; ++e) liveAll[(size_t)e * nPat + i] = pps[(size_t)i].live[(size_t)e];
+    });
     long long total = 0;
     for (int e = 0; e < nEpochs; ++e) {
         out.epochBase[(size_t)e] = total;
         int* so = &out.slotOff[(size_t)e * (nPat + 1)];
+        const int* lv = &liveAll[(size_t)e * nPat];
         long long tot = 0, totS = 0;
         for (int i = 0; i < nPat; ++i) {
             so[i] = (int)tot;
-            tot += pps[(size_t)i].live[(size_t)e];
-            if (pps[(size_t)i].shortcutOK) totS += pps[(size_t)i].live[(size_t)e];
+            tot += lv[i];
+            if (pps[(size_t)i].shortcutOK) totS += lv[i];
         }
         if (tot > 0x7FFFFFFFLL) return "too many live states in one epoch";
         so[nPat] = (int)tot;
@@ -1966,6 +1976,8 @@ uint64_t plan_checksum(const PlanHost& h) {
     vec(h.grpMaxB); vec(h.kLane); vec(h.kElem); vec(h.kSegs); vec(h.lastPairBase); vec(h.grpDirIn); vec(h.slotOff);
     vec(h.epochBase); vec(h.words); vec(h.meta); vec(h.trBase); vec(h.trEntBase); vec(h.trOff); vec(h.trEnt); vec(h.shortcutOK);
     vec(h.fBinPatOff); vec(h.fBinPats); vec(h.binPatOff); vec(h.binPats); vec(h.epochFp64); vec(h.epochFp64Short);
+    vec(h.maxX); vec(h.minX); vec(h.patFull); vec(h.epochSlots); vec(h.epochSlotsShort); vec(h.binSegOff); vec(h.binSegCnt);
+    vec(h.binSegBytes); vec(h.patRowStride);
     const long long g[4] = {h.maxEpochSlots, h.dirOff, h.dirSize, h.totalSlots};
     mix(g, sizeof g);
     return x;
