@@ -195,6 +195,7 @@ struct PatPlan {
 struct Ctx {
     int P, maxAf, stride;
     uint64_t base;
+    uint64_t pw[RC_MAX_P];          // weight of x[k] in key(): base^(P-1-k)
     uint64_t key(const St& s) const {
         uint64_t h = 0;
         for (int k = 0; k < P; ++k) h = h * base + s.x[k];
@@ -283,7 +284,8 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
     pp.mx.resize(m0 + (size_t)c.P, 0);
     pp.mn.resize(m0 + (size_t)c.P, L.empty() ? 0 : 1);
     for (size_t i = 0; i < L.size(); ++i) {
-        St s = L[i];
+        const St& s = L[i];
+        const uint64_t hs = c.key(s);
         int nnz = 0, sum = 0;
         for (int k = 0; k < c.P; ++k) {
             int xk = s.x[k];
@@ -291,13 +293,11 @@ void emit_epoch(const Ctx& c, const std::vector<St>& L, const Index& idx, PatPla
             if (!xk) pp.mn[m0 + (size_t)k] = 0;
             if (!xk) continue;
             sum += xk;
-            s.x[k] = (uint8_t)(xk + 1);
             uint32_t up = RC_NO_UP;
             if (xk + 1 <= c.maxAf) {
-                auto it = idx.find(c.key(s));
+                auto it = idx.find(hs + c.pw[k]);            // key of x + e_k
                 if (it != idx.end()) up = (uint32_t)it->second;
             }
-            s.x[k] = (uint8_t)xk;
             pp.words[w0 + i * c.stride + nnz] = (uint32_t)k | ((uint32_t)xk << 8) | (up << 16);
             ++nnz;
         }
@@ -1066,6 +1066,7 @@ std::string build_plan(int P, int maxAf, int nPat, const int32_t* patterns, cons
     c.maxAf = maxAf;
     c.stride = std::min(P, maxAf);
     c.base = (uint64_t)(maxAf + 1);
+    for (int k = P - 1; k >= 0; --k) c.pw[k] = k == P - 1 ? 1 : c.pw[k + 1] * c.base;
     const int nEpochs = (int)sev.size() + 1;
     std::vector<PatPlan> pps((size_t)nPat);
     // RC_PLAN_TIMING=1: wall time of the planner's phases on stderr
